@@ -1,0 +1,353 @@
+"""Generate golden input/output vectors from the UNMODIFIED reference (`/root/reference/dgpsi`).
+
+Run in the build container only (the reference is not present on the GPU box):
+
+    python tests/golden/make_golden.py
+
+Writes `tests/golden/*.npz`.  Every fixture stores the exact inputs fed to the reference function
+together with what it returned, so `tests/` can check (a) the oracle (`oracle/dgp_oracle.py`) on CPU
+and (b) the CUDA path on a B200 against the reference's own numbers.  The reference ships no tests of
+its own so these files ARE the pin.
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+from ref_shim import import_reference  # noqa: E402
+
+dgpsi = import_reference()
+from dgpsi import functions as F  # noqa: E402
+from dgpsi import imputation as IMP  # noqa: E402
+from dgpsi import vecchia as V  # noqa: E402
+from dgpsi.kernel_class import kernel  # noqa: E402
+
+SEED = 20261017
+
+
+def save(name, **arrays):
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **arrays)
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
+def make_node(rng, n, d_loc, d_glob, name, ard, nugget=1e-6, scale=1.0, nugget_est=False, scale_est=False):
+    D = d_loc + d_glob
+    length = rng.uniform(0.4, 1.6, size=D if ard else 1)
+    k = kernel(length=length, scale=scale, nugget=nugget, name=name, nugget_est=nugget_est, scale_est=scale_est,
+               connect=np.arange(d_glob) if d_glob else None)
+    k.input = rng.uniform(0, 1, size=(n, d_loc))
+    k.input_dim = np.arange(d_loc)
+    if d_glob:
+        k.global_input = rng.uniform(0, 1, size=(n, d_glob))
+    X = k.input if not d_glob else np.concatenate((k.input, k.global_input), 1)
+    k.output = (np.sin(3 * X.sum(1)) + 0.3 * rng.standard_normal(n)).reshape(-1, 1)
+    k.D = D
+    k.para_path = np.atleast_2d(np.concatenate((k.scale, k.length, k.nugget)))
+    return k, X
+
+
+# ---------------------------------------------------------------- 1+2: dense kernels / likelihoods
+def gen_dense():
+    rng = np.random.default_rng(SEED)
+    out = {}
+    cases = []
+    ci = 0
+    for name in ("sexp", "matern2.5"):
+        for ard in (False, True):
+            for d_glob in (0, 2):
+                for nugget_est, scale_est, nugget in ((False, False, 1e-6), (True, True, 1e-3)):
+                    n, d_loc = 37 + 3 * ci, 2
+                    k, X = make_node(rng, n, d_loc, d_glob, name, ard, nugget=nugget, scale=1.3,
+                                     nugget_est=nugget_est, scale_est=scale_est)
+                    p = f"c{ci}_"
+                    out[p + "X"] = X
+                    out[p + "y"] = k.output.copy()
+                    out[p + "length"] = k.length.copy()
+                    out[p + "scale"] = k.scale.copy()
+                    out[p + "nugget"] = k.nugget.copy()
+                    out[p + "flags"] = np.array([nugget_est, scale_est, d_loc, d_glob], dtype=np.int64)
+                    out[p + "name"] = np.array(name)
+                    K, fod = k.k_matrix(fod_eval=True)
+                    out[p + "K"], out[p + "fod"] = K, fod
+                    assert np.array_equal(k.k_matrix(), K) or np.allclose(k.k_matrix(), K, rtol=1e-15, atol=0)
+                    out[p + "K_plain"] = k.k_matrix()
+                    out[p + "loglik"] = np.atleast_1d(k.log_likelihood_func()).astype(np.float64)
+                    x0 = k.log_t()
+                    f, g = k.llik(x0.copy())
+                    out[p + "nllik"], out[p + "nllik_grad"] = np.atleast_1d(f), np.atleast_1d(g)
+                    out[p + "scale_after"] = np.atleast_1d(k.scale).copy()
+                    k.compute_stats()
+                    out[p + "Rinv"], out[p + "Rinv_y"] = k.Rinv, k.Rinv_y
+                    # prediction: plain GP on deterministic inputs
+                    M = 23
+                    xt = rng.uniform(-0.1, 1.1, size=(M, d_loc))
+                    zt = rng.uniform(-0.1, 1.1, size=(M, d_glob)) if d_glob else None
+                    m1, v1 = k.gp_prediction(xt, zt)
+                    out[p + "xt"] = xt
+                    if d_glob:
+                        out[p + "zt"] = zt
+                    out[p + "gp_m"], out[p + "gp_v"] = m1, v1
+                    # prediction: linked GP on Gaussian inputs (one zero-variance column entry)
+                    mt = rng.uniform(0, 1, size=(M, d_loc))
+                    vt = rng.uniform(1e-4, 0.05, size=(M, d_loc))
+                    vt[0, 0] = 0.0
+                    m2, v2 = k.linkgp_prediction(mt, vt, zt)
+                    out[p + "lk_m_in"], out[p + "lk_v_in"] = mt, vt
+                    out[p + "lk_m"], out[p + "lk_v"] = m2, v2
+                    cases.append(ci)
+                    ci += 1
+    out["ncases"] = np.array(ci)
+    save("dense_nodes", **out)
+
+
+# ---------------------------------------------------------------- Jd / Jd0 scalar known answers
+def gen_jd():
+    rng = np.random.default_rng(SEED + 1)
+    N = 400
+    X1, X2 = rng.uniform(-0.5, 1.5, N), rng.uniform(-0.5, 1.5, N)
+    zm = rng.uniform(-0.2, 1.2, N)
+    zv = 10 ** rng.uniform(-6, -0.5, N)
+    ell = 10 ** rng.uniform(-0.7, 0.7, N)
+    jd = np.array([V.Jd(X1[i], X2[i], zm[i], zv[i], ell[i]) for i in range(N)])
+    jd0 = np.array([V.Jd0(X1[i], zm[i], zv[i], ell[i]) for i in range(N)])
+    save("jd", X1=X1, X2=X2, zm=zm, zv=zv, ell=ell, jd=jd, jd0=jd0)
+
+
+# ---------------------------------------------------------------- 4: Vecchia
+def gen_vecchia():
+    rng = np.random.default_rng(SEED + 2)
+    out = {}
+    ci = 0
+    for name in ("sexp", "matern2.5"):
+        for ard in (False, True):
+            for d_glob in (0, 1):
+                nugget_est, scale_est = bool(ci % 2), bool((ci // 2) % 2)
+                n, d_loc, m = 150 + 10 * ci, 2, 8
+                k, X = make_node(rng, n, d_loc, d_glob, name, ard, nugget=1e-3 if nugget_est else 1e-6,
+                                 scale=0.8, nugget_est=nugget_est, scale_est=scale_est)
+                k.vecch, k.m = True, m
+                np.random.seed(SEED + ci)
+                k.ord_nn()
+                p = f"c{ci}_"
+                out[p + "X"], out[p + "y"] = X, k.output.copy()
+                out[p + "length"], out[p + "scale"], out[p + "nugget"] = k.length.copy(), k.scale.copy(), k.nugget.copy()
+                out[p + "flags"] = np.array([nugget_est, scale_est, d_loc, d_glob, m], dtype=np.int64)
+                out[p + "name"] = np.array(name)
+                out[p + "ord"], out[p + "NNarray"] = k.ord.copy(), k.NNarray.copy()
+                out[p + "llik"] = np.atleast_1d(k.log_likelihood_func_vecch())
+                Xo = X[k.ord]
+                Lm = V.L_matrix(Xo, k.NNarray, k.length, k.nugget[0], name)
+                out[p + "Lmatrix"] = Lm
+                z = rng.standard_normal(n)
+                out[p + "z"] = z
+                out[p + "draw"] = V.forward_solve_sp(Lm / np.sqrt(k.scale[0]), k.NNarray, z)
+                x0 = k.log_t()
+                f, g = k.llik_vecch(x0.copy())
+                out[p + "nllik"], out[p + "nllik_grad"] = np.atleast_1d(f), np.atleast_1d(g)
+                out[p + "scale_after"] = np.atleast_1d(k.scale).copy()
+                # predictions
+                M, pm = 40, 12
+                k.pred_m = pm
+                xt = rng.uniform(0, 1, size=(M, d_loc))
+                zt = rng.uniform(0, 1, size=(M, d_glob)) if d_glob else None
+                xq = xt if zt is None else np.concatenate((xt, zt), 1)
+                out[p + "pred_NN"] = V.get_pred_nn(xq / k.length, X / k.length, pm)
+                m1, v1 = k.gp_prediction(xt, zt)
+                out[p + "xt"] = xt
+                if d_glob:
+                    out[p + "zt"] = zt
+                out[p + "gp_m"], out[p + "gp_v"] = m1, v1
+                mt = rng.uniform(0, 1, size=(M, d_loc))
+                vt = rng.uniform(1e-4, 0.05, size=(M, d_loc))
+                xq2 = mt if zt is None else np.concatenate((mt, zt), 1)
+                out[p + "lk_NN"] = V.get_pred_nn(xq2 / k.length, X / k.length, pm)
+                m2, v2 = k.linkgp_prediction(mt, vt, zt)
+                out[p + "lk_m_in"], out[p + "lk_v_in"] = mt, vt
+                out[p + "lk_m"], out[p + "lk_v"] = m2, v2
+                ci += 1
+    out["ncases"] = np.array(ci)
+    # a bigger ordered-NN / kNN index fixture (bit-exact integers)
+    for j, (n, d, m) in enumerate(((1000, 3, 25), (700, 10, 25), (60, 2, 25), (20, 2, 25))):
+        x = rng.uniform(0, 1, size=(n, d))
+        out[f"nn{j}_x"] = x
+        out[f"nn{j}_m"] = np.array(m)
+        out[f"nn{j}_NN"] = V.nn(x, m)
+        q = rng.uniform(0, 1, size=(333, d))
+        out[f"nn{j}_q"] = q
+        out[f"nn{j}_pred"] = V.get_pred_nn(q, x, 50)
+    save("vecchia_nodes", **out)
+
+
+# ---------------------------------------------------------------- 3: ESS with injected draws
+class Injector:
+    """Replays pre-generated draws through the names `dgpsi.imputation` imported
+    (imputation.py:1-4): `fmvn`, `fmvn_sp`, `uniform`."""
+
+    def __init__(self, Z, U):
+        self.Z, self.U = Z, U
+        self.zi = self.ui = 0
+        self.thetas = []
+        self.block_log = []
+
+    def fmvn(self, cov):
+        z = self.Z[self.zi]
+        self.zi += 1
+        return np.linalg.cholesky(cov) @ z
+
+    def fmvn_sp(self, X, NNarray, scale, length, nugget, name):
+        z = self.Z[self.zi]
+        self.zi += 1
+        L = V.L_matrix(X, NNarray, length, nugget, name) / np.sqrt(scale)
+        return V.forward_solve_sp(L, NNarray, z)
+
+    def uniform(self, low=0.0, high=1.0):
+        u = self.U[self.ui]
+        self.ui += 1
+        val = low + (high - low) * u
+        self.thetas.append(val)
+        return val
+
+
+def build_ref_dgp(rng, n, d, widths, name, vecchia=False, m=8):
+    X = rng.uniform(0, 1, size=(n, d))
+    Y = np.stack([np.sin(4 * X.sum(1)) + X[:, 0] * X[:, -1], np.cos(3 * X[:, 0]) - X[:, -1] ** 2], 1)[:, : widths[-1]]
+    layers = []
+    for li, w in enumerate(widths):
+        last = li == len(widths) - 1
+        layers.append([kernel(length=np.array([1.0 + 0.1 * kk]), name=name, scale_est=last,
+                              connect=np.arange(d) if li > 0 else None) for kk in range(w)])
+    model = dgpsi.dgp(X, Y, dgpsi.combine(*layers), vecchia=vecchia, m=m)
+    return X, Y, model
+
+
+def snapshot(all_layer, prefix, out):
+    for l, layer in enumerate(all_layer):
+        for k, node in enumerate(layer):
+            p = f"{prefix}L{l}K{k}_"
+            out[p + "input"] = node.input.copy()
+            out[p + "output"] = node.output.copy()
+            out[p + "length"], out[p + "scale"], out[p + "nugget"] = node.length.copy(), node.scale.copy(), node.nugget.copy()
+            if node.global_input is not None:
+                out[p + "global_input"] = node.global_input.copy()
+            if node.vecch:
+                out[p + "ord"], out[p + "NNarray"] = node.ord.copy(), node.NNarray.copy()
+
+
+def gen_ess():
+    out = {}
+    for ci, (name, vecch, widths) in enumerate((("sexp", False, (3, 2, 2)), ("matern2.5", False, (3, 1)),
+                                                ("sexp", True, (3, 2)))):
+        rng = np.random.default_rng(SEED + 10 + ci)
+        np.random.seed(SEED + ci)
+        dgpsi.nb_seed(SEED + ci)
+        n, d = (45, 3) if not vecch else (120, 3)
+        X, Y, model = build_ref_dgp(rng, n, d, widths, name, vecchia=vecch)
+        p = f"c{ci}_"
+        out[p + "X"], out[p + "Y"] = X, Y
+        out[p + "name"] = np.array(name)
+        out[p + "widths"] = np.array(widths)
+        out[p + "vecch"] = np.array(vecch)
+        snapshot(model.all_layer, p + "pre_", out)
+        sweeps = 3
+        nblk = sweeps * (len(widths) - 1)
+        Z = rng.standard_normal((nblk * max(widths), n))
+        U = rng.uniform(size=4000)
+        inj = Injector(Z, U)
+        old = IMP.fmvn, IMP.fmvn_sp, IMP.uniform
+        IMP.fmvn, IMP.fmvn_sp, IMP.uniform = inj.fmvn, inj.fmvn_sp, inj.uniform
+        try:
+            model.imp.sample(burnin=sweeps - 1)
+        finally:
+            IMP.fmvn, IMP.fmvn_sp, IMP.uniform = old
+        out[p + "Z"], out[p + "U"] = Z[: inj.zi], U[: inj.ui]
+        out[p + "draw_values"] = np.array(inj.thetas)
+        out[p + "sweeps"] = np.array(sweeps)
+        snapshot(model.all_layer, p + "post_", out)
+        # one M-step on the imputed state (dgp.py:1391-1398)
+        for l, layer in enumerate(model.all_layer):
+            for k, node in enumerate(layer):
+                node.maximise()
+                out[p + f"mstep_L{l}K{k}"] = np.concatenate((node.scale, node.length, node.nugget))
+    out["ncases"] = np.array(3)
+    save("ess_replay", **out)
+
+
+# ---------------------------------------------------------------- end-to-end: step function (config 1) + 2-layer
+def gen_e2e():
+    out = {}
+    np.random.seed(SEED)
+    dgpsi.nb_seed(SEED)
+    X = np.linspace(0, 1, 10)[:, None]
+    Y = np.array([[-1.0] if i < 0.5 else [1.0] for i in X[:, 0]])
+    layer1 = [kernel(length=np.array([1.0]), name="sexp")]
+    layer2 = [kernel(length=np.array([1.0]), name="sexp")]
+    layer3 = [kernel(length=np.array([1.0]), name="sexp", scale_est=True)]
+    model = dgpsi.dgp(X, Y, dgpsi.combine(layer1, layer2, layer3))
+    model.train(N=60, disable=True)
+    final = model.estimate()
+    emu = dgpsi.emulator(final, N=4)
+    xt = np.linspace(0, 1, 41)[:, None]
+    mu, var = emu.predict(xt)
+    out["step_X"], out["step_Y"], out["step_xt"] = X, Y, xt
+    out["step_mu"], out["step_var"] = mu, var
+    out["step_nimp"] = np.array(len(emu.all_layer_set))
+    for s, al in enumerate(emu.all_layer_set):
+        snapshot(al, f"step_S{s}_", out)
+    # 2-layer Matern with global connection (config-2 shape, small n) -- frozen imputations
+    rng = np.random.default_rng(SEED + 5)
+    n, d = 60, 3
+    Xm = rng.uniform(0, 1, size=(n, d))
+    Ym = (np.sin(2 * np.pi * Xm[:, 0] * Xm[:, 1]) + (Xm[:, 2] - 0.5) ** 2).reshape(-1, 1)
+    l1 = [kernel(length=np.array([1.0]), name="matern2.5") for _ in range(d)]
+    l2 = [kernel(length=np.array([1.0]), name="matern2.5", scale_est=True, connect=np.arange(d))]
+    model2 = dgpsi.dgp(Xm, Ym, dgpsi.combine(l1, l2))
+    model2.train(N=15, disable=True)
+    emu2 = dgpsi.emulator(model2.estimate(), N=3)
+    xt2 = rng.uniform(0, 1, size=(57, d))
+    mu2, var2 = emu2.predict(xt2)
+    out["mat_X"], out["mat_Y"], out["mat_xt"] = Xm, Ym, xt2
+    out["mat_mu"], out["mat_var"] = mu2, var2
+    out["mat_nimp"] = np.array(len(emu2.all_layer_set))
+    for s, al in enumerate(emu2.all_layer_set):
+        snapshot(al, f"mat_S{s}_", out)
+    # linked system GP -> DGP -> GP (config-5 shape, small n)
+    n = 40
+    X1 = rng.uniform(0, 1, size=(n, 2))
+    Y1 = (np.sin(3 * X1[:, 0]) + X1[:, 1] ** 2).reshape(-1, 1)
+    g1 = dgpsi.gp(X1, Y1, kernel(length=np.array([1.0, 1.0]), name="matern2.5", scale_est=True))
+    g1.train()
+    X2 = rng.uniform(-0.2, 2.0, size=(n, 1))
+    Y2 = np.tanh(2 * (X2 - 0.9))
+    d2 = dgpsi.dgp(X2, Y2, dgpsi.combine([kernel(length=np.array([1.0]), name="matern2.5")],
+                                         [kernel(length=np.array([1.0]), name="matern2.5", scale_est=True,
+                                                 connect=np.arange(1))]))
+    d2.train(N=12, disable=True)
+    X3 = rng.uniform(-1.1, 1.1, size=(n, 1))
+    Y3 = X3**2 - 0.3 * X3
+    g3 = dgpsi.gp(X3, Y3, kernel(length=np.array([1.0]), name="sexp", scale_est=True))
+    g3.train()
+    c1 = dgpsi.container(g1.export(), np.array([0, 1]))
+    c2 = dgpsi.container(d2.estimate(), np.array([0]))
+    c3 = dgpsi.container(g3.export(), np.array([0]))
+    system = dgpsi.lgp(dgpsi.combine([c1], [c2], [c3]), N=3)
+    xt3 = rng.uniform(0, 1, size=(31, 2))
+    mu3, var3 = system.predict(xt3)
+    out["lgp_xt"], out["lgp_mu"], out["lgp_var"] = xt3, mu3[0], var3[0]
+    out["lgp_nimp"] = np.array(len(system.all_layer_set))
+    for s, one in enumerate(system.all_layer_set):
+        for l, layer in enumerate(one):
+            cont = layer[0]
+            if cont.type == "gp":
+                snapshot([[cont.structure]], f"lgp_S{s}_E{l}_", out)
+            else:
+                snapshot(cont.structure, f"lgp_S{s}_E{l}_", out)
+    save("e2e", **out)
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["dense", "jd", "vecchia", "ess", "e2e"]
+    for w in which:
+        {"dense": gen_dense, "jd": gen_jd, "vecchia": gen_vecchia, "ess": gen_ess, "e2e": gen_e2e}[w]()
