@@ -1,0 +1,208 @@
+/*
+ * dgpb.h -- C-ABI of libdgpb.so: the B200 (sm_100a) implementation of the dgpsi
+ * stochastic-imputation (SI) hot path.
+ *
+ * The reference (mingdeyu/DGP, `dgpsi` 2.6.0) is pure Python + numba and has NO FFI; the drop-in
+ * boundary is therefore the "GP-node seam" of SURVEY.md section 8(b): every numeric method of the
+ * reference's `kernel` class (dgpsi/kernel_class.py) and the njit kernels they call
+ * (dgpsi/functions.py, dgpsi/vecchia.py, dgpsi/imputation.py).  Each entry point below cites the
+ * reference function it replaces.  `dgp_b200/` (Python, mirrors the reference API) binds these
+ * symbols through ctypes; INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - every data pointer is a DEVICE pointer unless the name ends in `_host`;
+ *   - FP64, row-major (C order), contiguous; index arrays are int64 (numpy default, vecchia.py:65);
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - return value: DGPB_OK, DGPB_NOT_PD (Cholesky hit a non-positive pivot -> the Python shim raises
+ *     numpy.linalg.LinAlgError so dgp.train's restart logic, dgp.py:1402, keeps working),
+ *     DGPB_BAD_ARG, DGPB_CUDA_ERROR; dgpb_last_error() returns a message for the calling thread;
+ *   - functions that return scalars through `*_host` pointers synchronise `stream` before
+ *     returning; all others are asynchronous with respect to the host;
+ *   - the library owns only the opaque workspace (scratch + cached factorizations); callers own
+ *     every data buffer.
+ */
+#ifndef DGPB_H
+#define DGPB_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DGPB_OK 0
+#define DGPB_NOT_PD 1
+#define DGPB_BAD_ARG 2
+#define DGPB_CUDA_ERROR 3
+
+#define DGPB_SEXP 0      /* kernel(name='sexp')      kernel_class.py:325-332 */
+#define DGPB_MATERN25 1  /* kernel(name='matern2.5') kernel_class.py:333-345 */
+
+#define DGPB_MAX_DIM 32  /* maximum node input dimension (local + connected global) */
+
+typedef struct dgpb_ws dgpb_ws; /* opaque workspace */
+
+/* One GP node of the hierarchy: the numeric state of the reference's `kernel` object
+ * (kernel_class.py:86-144) that the hot path reads.
+ *
+ * The node input is X = [ src[input_dim[0..n_local), :]^T | gsrc[connect[0..n_global), :]^T ]  (n x D):
+ * `src` is the feeding layer stored one variable per ROW (width x n, so a latent column is a
+ * contiguous n-vector) and `gsrc` is the global input X^T (d x n).  This is `kernel.input` /
+ * `kernel.global_input` (dgp.py:592-624) without materialising per-node copies. */
+typedef struct dgpb_node {
+    int32_t kind;              /* DGPB_SEXP | DGPB_MATERN25 */
+    int32_t n_local;           /* len(input_dim) */
+    int32_t n_global;          /* len(connect) or 0 */
+    int32_t nlen;              /* len(length): 1 (shared) or n_local+n_global (ARD), kernel_class.py:14-20 */
+    int32_t input_dim[DGPB_MAX_DIM];
+    int32_t connect[DGPB_MAX_DIM];
+    double length[DGPB_MAX_DIM];
+    double scale;              /* kernel.scale[0]  */
+    double nugget;             /* kernel.nugget[0] */
+    int32_t scale_est;         /* kernel.scale_est  */
+    int32_t nugget_est;        /* kernel.nugget_est */
+    const double* src;         /* device, (src_width x n) */
+    const double* gsrc;        /* device, (gsrc_width x n) or NULL */
+    double* output;            /* device, n : kernel.output[:,0] */
+    /* Vecchia state (kernel_class.py:245-267); NULL when dense */
+    const int64_t* ord;        /* device, n  */
+    const int64_t* NNarray;    /* device, n x (m+1), index-descending, -1 padded */
+    int32_t m;                 /* conditioning-set size */
+    int32_t vecch;
+} dgpb_node;
+
+const char* dgpb_last_error(void);
+int dgpb_version(void);
+
+int dgpb_ws_create(dgpb_ws** ws, int device);
+int dgpb_ws_destroy(dgpb_ws* ws);
+/* bytes of device scratch currently held by the workspace */
+int64_t dgpb_ws_bytes(const dgpb_ws* ws);
+
+/* ---- 1. kernel matrices -------------------------------------------------------------------- */
+
+/* kernel.k_matrix(fod_eval)  kernel_class.py:304-359; functions.py:16-93 (Matern coefficient loops,
+ * fod_exp).  X: n x D.  K: n x n (full, symmetric, diag 1+nugget*wdiag_i).  dK: P x n x n or NULL,
+ * P = nlen (+1 when nugget_est: the last slice is nugget*diag(wdiag)).  wdiag NULL = ones. */
+int dgpb_kmatrix(const double* X, int64_t n, int64_t D, const double* length_host, int64_t nlen,
+                 double nugget, const double* wdiag, int kind, int nugget_est,
+                 double* K, double* dK, void* stream);
+
+/* ---- 2. dense likelihood / gradient / statistics ------------------------------------------- */
+
+/* kernel.log_likelihood_func  kernel_class.py:481-488: -0.5*(logdet(scale*K) + y'(scale*K)^-1 y).
+ * Blocked FP64 Cholesky (DMMA trailing updates) with y carried as an extra row so the forward
+ * solve is fused into the factorisation. out_host[0] = llik. */
+int dgpb_loglik_dense(dgpb_ws* ws, const dgpb_node* node, int64_t n, double* out_host, void* stream);
+
+/* kernel.llik(x)  kernel_class.py:403-445 (no-replicate branch), WITHOUT the prior terms (the host
+ * adds log_prior / log_prior_fod, kernel_class.py:446-448).  node->length/nugget hold exp(x).
+ * out_host = [nllik, scale, grad[0..P)],  P = nlen + nugget_est.  K^-1 comes from one sliding-window
+ * partial Cholesky of [[K],[y'],[I]]; the P traces/quadratic forms are one fused pass over K^-1 with
+ * dK recomputed on the fly (the P x n x n `fod` tensor of functions.py:36-93 is never built). */
+int dgpb_nllik_grad_dense(dgpb_ws* ws, const dgpb_node* node, int64_t n, double* out_host, void* stream);
+
+/* kernel.compute_stats  kernel_class.py:735-748: Rinv (n x n, full symmetric) and Rinv_y (n). */
+int dgpb_compute_stats(dgpb_ws* ws, const dgpb_node* node, int64_t n, double* Rinv, double* Rinv_y,
+                       void* stream);
+
+/* fmvn(scale*K)  functions.py:113-121 with the standard-normal vector z injected:
+ * nu = chol(scale*K) z. */
+int dgpb_mvn_draw(dgpb_ws* ws, const dgpb_node* node, int64_t n, const double* z, double* nu, void* stream);
+
+/* ---- 3. elliptical slice sampling ---------------------------------------------------------- */
+
+/* imputer.one_sample_block  imputation.py:44-119 (and one_sample :166-221 when n_targets == 1).
+ * targets[k].output is f[:,k]; it is the row `target_rows[k]` of the matrix `layer_out`
+ * (width x n) that every upper node reads through src/input_dim.  z: (n_targets x n) standard
+ * normals; u_host: nu uniforms consumed in the reference's order (threshold, first angle, one per
+ * rejection).  On return the accepted proposal has been written to the target outputs,
+ * *n_prop_host = proposals evaluated, theta_host (optional, length >= nu) receives the angles
+ * tried.  Returns DGPB_BAD_ARG if the uniforms ran out before acceptance. */
+int dgpb_ess_block(dgpb_ws* ws, const dgpb_node* targets, int n_targets, const int32_t* target_rows_host,
+                   double* layer_out, int64_t layer_width, const dgpb_node* uppers, int n_uppers,
+                   int64_t n, const double* z, const double* u_host, int nu,
+                   int* n_prop_host, double* theta_host, void* stream);
+
+/* ---- 4. Vecchia ---------------------------------------------------------------------------- */
+
+/* nn()  vecchia.py:42-109: ordered nearest neighbours of the (already ordered, already scaled)
+ * points x (n x D): row i = {i} U (m nearest j<i), index-descending, -1 padded. NN: n x (m+1). */
+int dgpb_knn_ordered(const double* x, int64_t n, int64_t D, int64_t m, int64_t* NN, void* stream);
+
+/* get_pred_nn()  vecchia.py:20-40: plain kNN of M queries against n points, distance ascending
+ * (ties: smaller index first).  NN: M x min(m,n). */
+int dgpb_knn(const double* query, int64_t M, const double* x, int64_t n, int64_t D, int64_t m,
+             int64_t* NN, void* stream);
+
+/* vecchia_llik  vecchia.py:164-180.  X: n x D and y: n in Vecchia order.  out_host[0] = llik. */
+int dgpb_vecchia_llik(const double* X, const double* y, const int64_t* NN, int64_t n, int64_t D, int64_t m1,
+                      const double* length_host, int64_t nlen, double scale, double nugget,
+                      const double* nugget_diag, int kind, double* out_host, void* stream);
+
+/* vecchia_nllik  vecchia.py:182-242 (origin_n == n branch), without prior terms.
+ * out_host = [nllik, scale, grad[0..P)]. */
+int dgpb_vecchia_nllik(const double* X, const double* y, const int64_t* NN, int64_t n, int64_t D, int64_t m1,
+                       const double* length_host, int64_t nlen, double scale, double nugget,
+                       const double* nugget_diag, int kind, int scale_est, int nugget_est,
+                       double* out_host, void* stream);
+
+/* L_matrix  vecchia.py:409-424: rows of the sparse inverse Cholesky factor, n x m1. */
+int dgpb_vecchia_Lmatrix(const double* X, const int64_t* NN, int64_t n, int64_t D, int64_t m1,
+                         const double* length_host, int64_t nlen, double nugget, int kind,
+                         double* L, void* stream);
+
+/* fmvn_sp  vecchia.py:133-140 with injected z: x = (L/sqrt(scale))^-1 z by a dependency-driven
+ * sparse forward solve (forward_solve_sp, vecchia.py:111-120).  out: n (Vecchia order). */
+int dgpb_vecchia_mvn_draw(const double* X, const int64_t* NN, int64_t n, int64_t D, int64_t m1,
+                          const double* length_host, int64_t nlen, double scale, double nugget, int kind,
+                          const double* z, double* out, void* stream);
+
+/* gp_vecch  vecchia.py:635-654.  x: M x D test inputs, w: n x D training inputs, NN: M x mp. */
+int dgpb_gp_vecch(const double* x, int64_t M, const double* w, const double* y, int64_t n, int64_t D,
+                  const int64_t* NN, int64_t mp, const double* length_host, int64_t nlen, double scale,
+                  double nugget, const double* nugget_diag, int kind, double* mean, double* var, void* stream);
+
+/* link_gp_vecch + IJ_nb  vecchia.py:758-907.  m_in/v_in: M x Dw, z: M x Dz or NULL,
+ * w1: n x Dw, gw: n x Dz or NULL. */
+int dgpb_linkgp_vecch(const double* m_in, const double* v_in, const double* z, int64_t M,
+                      const double* w1, const double* gw, const double* y, int64_t n, int64_t Dw, int64_t Dz,
+                      const int64_t* NN, int64_t mp, const double* length_host, int64_t nlen, double scale,
+                      double nugget, const double* nugget_diag, int kind, double* mean, double* var,
+                      void* stream);
+
+/* ---- 5. closed-form prediction ------------------------------------------------------------- */
+
+/* gp()  functions.py:379-394: m = r'R^-1y, v = |scale(1+nugget - r'R^-1 r)|.
+ * x: M x D, W: n x D (local and global columns concatenated). */
+int dgpb_gp_predict(dgpb_ws* ws, const double* x, int64_t M, const double* W, int64_t n, int64_t D,
+                    const double* Rinv, const double* Rinv_y, const double* length_host, int64_t nlen,
+                    double scale, double nugget, int kind, double* mean, double* var, void* stream);
+
+/* link_gp()  functions.py:396-430 with IJ_sexp / IJ_matern (functions.py:432-494), Jd / Jd0
+ * (vecchia.py:915-988), trace_sum / quad (functions.py:496-506, vecchia.py:990-1000).
+ * m_in/v_in: M x Dw Gaussian inputs, z: M x Dz deterministic global inputs or NULL.
+ * The sexp R2sexp/Psexp tables of kernel_class.py:752-764 are recomputed on the fly. */
+int dgpb_linkgp_predict(dgpb_ws* ws, const double* m_in, const double* v_in, const double* z, int64_t M,
+                        const double* w1, const double* gw, int64_t n, int64_t Dw, int64_t Dz,
+                        const double* Rinv, const double* Rinv_y, const double* length_host, int64_t nlen,
+                        double scale, double nugget, int kind, double* mean, double* var, void* stream);
+
+/* mixture over S imputations  emulation.py:846-847, linkgp.py:493-494.
+ * means/vars: S x len; mu = mean_s m; sigma2 = mean_s(m^2+v) - mu^2. */
+int dgpb_aggregate(const double* means, const double* vars, int64_t S, int64_t len, double* mu,
+                   double* sigma2, void* stream);
+
+/* ---- measurement helpers (bench.py / DESIGN.md roofline denominators) ----------------------- */
+
+/* C (M x N) = A (M x K) * B (N x K)^T with the library's own DMMA tile kernel. */
+int dgpb_dgemm_nt(const double* A, const double* B, double* C, int64_t M, int64_t N, int64_t K, void* stream);
+/* in-place lower Cholesky of the n x n matrix A (ld = n); info_host = 0 or failing column + 1 */
+int dgpb_potrf(dgpb_ws* ws, double* A, int64_t n, int* info_host, void* stream);
+/* number of kernels this library has launched since load (bench.py's gpu_launches) */
+int64_t dgpb_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DGPB_H */
