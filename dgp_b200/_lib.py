@@ -1,0 +1,223 @@
+"""ctypes binding of libdgpb.so (include/dgpb.h) plus the device-buffer plumbing.
+
+PyTorch is used ONLY as the owner of device memory and streams (`torch.Tensor.data_ptr()` goes straight
+into the C-ABI); no torch kernel is on the hot path.  There is NO CPU fallback: importing works without
+a GPU (so the host logic can be unit-tested), but the first numeric call raises if the CUDA library or
+a CUDA device is missing.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdgpb.so")
+
+DGPB_OK, DGPB_NOT_PD, DGPB_BAD_ARG, DGPB_CUDA_ERROR = 0, 1, 2, 3
+SEXP, MATERN25 = 0, 1
+MAX_DIM = 32
+KIND = {"sexp": SEXP, "matern2.5": MATERN25}
+
+c_i64, c_i32, c_dbl, c_vp = ctypes.c_int64, ctypes.c_int32, ctypes.c_double, ctypes.c_void_p
+
+
+class DgpbNode(ctypes.Structure):
+    """Mirror of `struct dgpb_node` (include/dgpb.h)."""
+
+    _fields_ = [
+        ("kind", c_i32), ("n_local", c_i32), ("n_global", c_i32), ("nlen", c_i32),
+        ("input_dim", c_i32 * MAX_DIM), ("connect", c_i32 * MAX_DIM), ("length", c_dbl * MAX_DIM),
+        ("scale", c_dbl), ("nugget", c_dbl), ("scale_est", c_i32), ("nugget_est", c_i32),
+        ("src", c_vp), ("gsrc", c_vp), ("output", c_vp),
+        ("ord", c_vp), ("NNarray", c_vp), ("m", c_i32), ("vecch", c_i32),
+    ]
+
+
+_PROTOS = {
+    # name: (restype, argtypes)
+    "dgpb_last_error": (ctypes.c_char_p, []),
+    "dgpb_version": (ctypes.c_int, []),
+    "dgpb_launch_count": (c_i64, []),
+    "dgpb_sizeof_node": (c_i64, []),
+    "dgpb_ws_create": (ctypes.c_int, [ctypes.POINTER(c_vp), ctypes.c_int]),
+    "dgpb_ws_destroy": (ctypes.c_int, [c_vp]),
+    "dgpb_ws_bytes": (c_i64, [c_vp]),
+    "dgpb_kmatrix": (ctypes.c_int, [c_vp, c_i64, c_i64, c_vp, c_i64, c_dbl, c_vp, ctypes.c_int, ctypes.c_int, c_vp,
+                                    c_vp, c_vp]),
+    "dgpb_loglik_dense": (ctypes.c_int, [c_vp, ctypes.POINTER(DgpbNode), c_i64, c_vp, c_vp]),
+    "dgpb_nllik_grad_dense": (ctypes.c_int, [c_vp, ctypes.POINTER(DgpbNode), c_i64, c_vp, c_vp]),
+    "dgpb_compute_stats": (ctypes.c_int, [c_vp, ctypes.POINTER(DgpbNode), c_i64, c_vp, c_vp, c_vp]),
+    "dgpb_mvn_draw": (ctypes.c_int, [c_vp, ctypes.POINTER(DgpbNode), c_i64, c_vp, c_vp, c_vp]),
+    "dgpb_ess_block": (ctypes.c_int, [c_vp, ctypes.POINTER(DgpbNode), ctypes.c_int, c_vp, c_vp, c_i64,
+                                      ctypes.POINTER(DgpbNode), ctypes.c_int, c_i64, c_vp, c_vp, ctypes.c_int,
+                                      ctypes.POINTER(ctypes.c_int), c_vp, c_vp]),
+    "dgpb_knn_ordered": (ctypes.c_int, [c_vp, c_i64, c_i64, c_i64, c_vp, c_vp]),
+    "dgpb_knn": (ctypes.c_int, [c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp]),
+    "dgpb_vecchia_llik": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_dbl, c_dbl, c_vp,
+                                         ctypes.c_int, c_vp, c_vp]),
+    "dgpb_vecchia_nllik": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_dbl, c_dbl, c_vp,
+                                          ctypes.c_int, ctypes.c_int, ctypes.c_int, c_vp, c_vp]),
+    "dgpb_vecchia_Lmatrix": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_dbl, ctypes.c_int, c_vp,
+                                            c_vp]),
+    "dgpb_vecchia_mvn_draw": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_dbl, c_dbl,
+                                             ctypes.c_int, c_vp, c_vp, c_vp]),
+    "dgpb_gp_vecch": (ctypes.c_int, [c_vp, c_i64, c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_i64, c_dbl, c_dbl,
+                                     c_vp, ctypes.c_int, c_vp, c_vp, c_vp]),
+    "dgpb_linkgp_vecch": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_vp,
+                                         c_i64, c_vp, c_i64, c_dbl, c_dbl, c_vp, ctypes.c_int, c_vp, c_vp, c_vp]),
+    "dgpb_gp_predict": (ctypes.c_int, [c_vp, c_vp, c_i64, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_i64, c_dbl, c_dbl,
+                                       ctypes.c_int, c_vp, c_vp, c_vp]),
+    "dgpb_linkgp_predict": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, c_i64, c_i64, c_vp,
+                                           c_vp, c_vp, c_i64, c_dbl, c_dbl, ctypes.c_int, c_vp, c_vp, c_vp]),
+    "dgpb_aggregate": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp]),
+    "dgpb_dgemm_nt": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_vp]),
+    "dgpb_potrf": (ctypes.c_int, [c_vp, c_vp, c_i64, ctypes.POINTER(ctypes.c_int), c_vp]),
+}
+
+_lib = None
+_lib_lock = threading.Lock()
+
+
+def exported_symbols():
+    """Names every entry point include/dgpb.h declares (used by the symbol-export test)."""
+    return sorted(_PROTOS)
+
+
+def load():
+    """Load libdgpb.so (built in-tree by `__graft_entry__.build()` / dgp_b200/csrc/build.sh)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lib_lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"dgp_b200: {LIB_PATH} is missing. Build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a). There is no CPU fallback.")
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _PROTOS.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def check(status):
+    """Map a C status to the exception the reference would raise at that point."""
+    if status == DGPB_OK:
+        return
+    msg = load().dgpb_last_error().decode("utf-8", "replace")
+    if status == DGPB_NOT_PD:
+        # scipy/numpy Cholesky failure in the reference -> caught by dgp.train (dgp.py:1402)
+        raise np.linalg.LinAlgError(msg)
+    if status == DGPB_BAD_ARG:
+        raise ValueError("dgp_b200: " + msg)
+    raise RuntimeError("dgp_b200: " + msg)
+
+
+# ------------------------------------------------------------------------------------------------
+# device plumbing (torch = allocator + streams only)
+# ------------------------------------------------------------------------------------------------
+_tls = threading.local()
+
+
+def torch_mod():
+    import torch
+
+    return torch
+
+
+def device():
+    """The CUDA device of this process: LOCAL_RANK under torchrun, else the current device."""
+    torch = torch_mod()
+    if not torch.cuda.is_available():
+        raise RuntimeError("dgp_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback.")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def workspace():
+    """Per-thread, per-device opaque workspace handle."""
+    dev = device()
+    key = f"ws{dev.index}"
+    ws = getattr(_tls, key, None)
+    if ws is None:
+        h = c_vp()
+        check(load().dgpb_ws_create(ctypes.byref(h), dev.index))
+        ws = h
+        setattr(_tls, key, ws)
+    return ws
+
+
+def stream():
+    torch = torch_mod()
+    return c_vp(torch.cuda.current_stream().cuda_stream)
+
+
+def to_dev(a, dtype=None):
+    """numpy (or tensor) -> contiguous device tensor (float64 / int64)."""
+    torch = torch_mod()
+    if isinstance(a, torch.Tensor):
+        t = a.to(device())
+        return t.contiguous()
+    a = np.ascontiguousarray(a, dtype=dtype if dtype is not None else (np.int64 if np.issubdtype(
+        np.asarray(a).dtype, np.integer) else np.float64))
+    return torch.from_numpy(a).to(device(), non_blocking=False)
+
+
+def empty(shape, dtype="f8"):
+    torch = torch_mod()
+    return torch.empty(shape, dtype=torch.float64 if dtype == "f8" else torch.int64, device=device())
+
+
+def cols(t, idx):
+    """t[:, idx] for a device tensor and a numpy/list column index (contiguous copy)."""
+    torch = torch_mod()
+    ix = torch.as_tensor(np.atleast_1d(np.asarray(idx)).astype(np.int64), device=t.device)
+    return t.index_select(1, ix).contiguous()
+
+
+def ptr(t):
+    return c_vp(0) if t is None else c_vp(t.data_ptr())
+
+
+def host_doubles(n):
+    return (c_dbl * n)()
+
+
+def length_host(length):
+    arr = np.ascontiguousarray(np.atleast_1d(length), dtype=np.float64)
+    return arr, arr.ctypes.data_as(c_vp)
+
+
+def fill_node(node: DgpbNode, *, kind, input_dim, connect, length, scale, nugget, scale_est=False, nugget_est=False,
+              src=None, gsrc=None, output=None, ord=None, NNarray=None, m=0, vecch=False):
+    """Populate a `dgpb_node`; `src`, `gsrc`, `output`, `ord`, `NNarray` are device tensors (kept alive by caller)."""
+    node.kind = KIND[kind] if isinstance(kind, str) else int(kind)
+    input_dim = [] if input_dim is None else list(np.atleast_1d(input_dim))
+    connect = [] if connect is None else list(np.atleast_1d(connect))
+    if len(input_dim) + len(connect) > MAX_DIM:
+        raise ValueError(f"dgp_b200 supports at most {MAX_DIM} input dimensions per GP node")
+    node.n_local, node.n_global = len(input_dim), len(connect)
+    for i, v in enumerate(input_dim):
+        node.input_dim[i] = int(v)
+    for i, v in enumerate(connect):
+        node.connect[i] = int(v)
+    length = np.atleast_1d(np.asarray(length, dtype=np.float64))
+    node.nlen = len(length)
+    for i, v in enumerate(length):
+        node.length[i] = float(v)
+    node.scale = float(np.atleast_1d(scale)[0])
+    node.nugget = float(np.atleast_1d(nugget)[0])
+    node.scale_est, node.nugget_est = int(bool(scale_est)), int(bool(nugget_est))
+    node.src = src.data_ptr() if src is not None else None
+    node.gsrc = gsrc.data_ptr() if gsrc is not None else None
+    node.output = output.data_ptr() if output is not None else None
+    node.ord = ord.data_ptr() if ord is not None else None
+    node.NNarray = NNarray.data_ptr() if NNarray is not None else None
+    node.m, node.vecch = int(m), int(bool(vecch))
+    return node

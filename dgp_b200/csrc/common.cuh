@@ -1,0 +1,196 @@
+// common.cuh -- shared declarations for libdgpb.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/dgpb.h"
+
+namespace dgpb {
+
+extern thread_local char g_err[512];
+extern std::atomic<long long> g_launches;
+
+inline void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+#define DGPB_CUDA_TRY(expr)                                                                     \
+    do {                                                                                        \
+        cudaError_t e__ = (expr);                                                               \
+        if (e__ != cudaSuccess) {                                                               \
+            dgpb::set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #expr,                  \
+                            cudaGetErrorString(e__));                                           \
+            return DGPB_CUDA_ERROR;                                                             \
+        }                                                                                       \
+    } while (0)
+
+// after every kernel launch: count it and surface launch-configuration errors
+#define DGPB_LAUNCHED()                                                                         \
+    do {                                                                                        \
+        dgpb::g_launches.fetch_add(1, std::memory_order_relaxed);                               \
+        cudaError_t e__ = cudaGetLastError();                                                   \
+        if (e__ != cudaSuccess) {                                                               \
+            dgpb::set_error("%s:%d: kernel launch failed: %s", __FILE__, __LINE__,              \
+                            cudaGetErrorString(e__));                                           \
+            return DGPB_CUDA_ERROR;                                                             \
+        }                                                                                       \
+    } while (0)
+
+#define DGPB_TRY(expr)                                                                          \
+    do {                                                                                        \
+        int s__ = (expr);                                                                       \
+        if (s__ != DGPB_OK) return s__;                                                         \
+    } while (0)
+
+#define DGPB_REQUIRE(cond, msg)                                                                 \
+    do {                                                                                        \
+        if (!(cond)) {                                                                          \
+            dgpb::set_error("%s:%d: bad argument: %s", __FILE__, __LINE__, msg);                \
+            return DGPB_BAD_ARG;                                                                \
+        }                                                                                       \
+    } while (0)
+
+// layout of the small device result buffer (SLOT_OUT), in doubles:
+//   [0, 128)    dense batch results, 4 per matrix (logdet, quad, sigma2, -)
+//   [256, 512)  Vecchia per-node results, 2 per node (quad, logdet)
+//   [512, 1024) gradient results (nllik, sigma2, grad[P])
+constexpr int kOutDoubles = 1024;
+constexpr int kOutVecchia = 256;
+constexpr int kOutGrad = 512;
+
+constexpr double kSqrt5 = 2.2360679774997896964;
+constexpr int kMaxDim = DGPB_MAX_DIM;
+
+inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+inline int64_t cdiv(int64_t x, int64_t m) { return (x + m - 1) / m; }
+
+// ---------------------------------------------------------------------------------------------
+// Workspace: slot-addressed device scratch that only grows.  No allocation on the hot path after
+// warm-up (SURVEY.md 8b "ownership").
+// ---------------------------------------------------------------------------------------------
+enum Slot : int {
+    SLOT_T = 0,       // factorisation matrices (batched)
+    SLOT_DIAG,        // diag(L) per batch entry
+    SLOT_OUT,         // small result scalars
+    SLOT_INFO,        // int info flags
+    SLOT_PART,        // reduction partials
+    SLOT_NU,          // ESS prior draws
+    SLOT_PROP,        // ESS proposal layer
+    SLOT_GEMM_A,      // prediction: cross-kernel matrix R
+    SLOT_GEMM_B,      // prediction: padded R^-1
+    SLOT_GEMM_C,      // prediction: R * R^-1
+    SLOT_MISC,
+    SLOT_MISC2,
+    SLOT_VX,          // Vecchia: inputs gathered in Vecchia order
+    SLOT_VY,          // Vecchia: outputs gathered in Vecchia order
+    SLOT_VL,          // Vecchia: sparse inverse-Cholesky rows
+    SLOT_VFLAG,       // Vecchia: ready flags of the sparse solve
+    SLOT_COUNT
+};
+
+struct Workspace {
+    int device = 0;
+    void* buf[SLOT_COUNT] = {};
+    size_t cap[SLOT_COUNT] = {};
+    double* pinned = nullptr;  // small pinned host staging buffer (4096 doubles)
+
+    int reserve(int slot, size_t bytes, void** out) {
+        if (bytes > cap[slot]) {
+            if (buf[slot]) DGPB_CUDA_TRY(cudaFree(buf[slot]));
+            buf[slot] = nullptr;
+            cap[slot] = 0;
+            size_t want = bytes + bytes / 8 + 256;
+            DGPB_CUDA_TRY(cudaMalloc(&buf[slot], want));
+            cap[slot] = want;
+        }
+        *out = buf[slot];
+        return DGPB_OK;
+    }
+    size_t total() const {
+        size_t t = 0;
+        for (int i = 0; i < SLOT_COUNT; ++i) t += cap[i];
+        return t;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Device-side description of a node's kernel function, passed to kernels BY VALUE.
+// The input of point i is gathered straight from the variable-major sources:
+//   x_d(i) = ptr[d][i] * inv_len[d]   -- this is `X/self.length` (kernel_class.py:324) without
+// materialising per-node input copies.
+// ---------------------------------------------------------------------------------------------
+struct KernelDev {
+    int kind;
+    int D;
+    int ard;                     // 1: one length per dimension
+    int64_t stride;              // element stride between consecutive points (1 = variable-major)
+    const double* ptr[kMaxDim];  // base of dimension d: x_d(i) = ptr[d][i*stride] / len[d]
+    double len[kMaxDim];         // length-scale per dimension (shared value replicated)
+    double nugget;
+    __device__ __forceinline__ double x(int d, int64_t i) const { return ptr[d][i * stride] / len[d]; }
+    __device__ __forceinline__ double raw(int d, int64_t i) const { return ptr[d][i * stride]; }
+};
+
+// scaled coordinate: the reference divides (X / length), it does not multiply by a reciprocal
+__device__ __forceinline__ double scaled(double x, double len) { return x / len; }
+
+// Correlation between two scaled points given as register arrays / pointers with stride.
+// sexp   : exp(-sum_d (a_d-b_d)^2)                                  kernel_class.py:326-327
+// matern : prod_d(1+sqrt5 r+5/3 r^2) * exp(-sqrt5 sum_d r)          kernel_class.py:343-345
+template <typename FA, typename FB>
+__device__ __forceinline__ double corr_pair(int kind, int D, FA a, FB b) {
+    if (kind == DGPB_SEXP) {
+        double dist = 0.0;
+        for (int d = 0; d < D; ++d) {
+            double df = a(d) - b(d);
+            dist = __dadd_rn(dist, __dmul_rn(df, df));
+        }
+        return exp(-dist);
+    } else {
+        double coef = 1.0, s = 0.0;
+        for (int d = 0; d < D; ++d) {
+            double r = fabs(a(d) - b(d));
+            coef *= 1.0 + kSqrt5 * r + (5.0 / 3.0) * (r * r);
+            s += r;
+        }
+        return coef * exp(-kSqrt5 * s);
+    }
+}
+
+// block-wide deterministic sum (fixed tree order); result valid in thread 0 (and broadcast via smem)
+template <int THREADS>
+__device__ __forceinline__ double block_sum(double v, double* sred) {
+    const int tid = threadIdx.x;
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if ((tid & 31) == 0) sred[tid >> 5] = v;
+    __syncthreads();
+    double r = 0.0;
+    if (tid < 32) {
+        r = (tid < THREADS / 32) ? sred[tid] : 0.0;
+        for (int o = 16; o > 0; o >>= 1) r += __shfl_down_sync(0xffffffffu, r, o);
+    }
+    __syncthreads();
+    return r;
+}
+
+// host helpers implemented in common.cu
+// node -> KernelDev; `src_override` (if not NULL) replaces node->src (ESS proposals)
+int make_kernel_dev(const dgpb_node* node, int64_t n, const double* src_override, KernelDev* out);
+// row-major X (n x D) -> KernelDev
+int make_kernel_dev_rowmajor(const double* X, int64_t D, const double* length_host, int64_t nlen,
+                             double nugget, int kind, KernelDev* out);
+
+}  // namespace dgpb
+
+// the opaque C handle is the workspace itself
+struct dgpb_ws : public dgpb::Workspace {};

@@ -1,0 +1,803 @@
+// dense.cu -- dense FP64 GP-node linear algebra on sm_100a:
+//   * tiled kernel-matrix construction (sexp / Matern-2.5, shared or per-dimension length-scales),
+//   * blocked right-looking Cholesky whose panel TRSM and trailing SYRK run on the FP64 tensor path
+//     (mma.sync.m8n8k4.f64 -> DMMA), batched over GP nodes with blockIdx.z,
+//   * the "sliding window" partial factorisation of [[K],[y'],[I]] that yields log|K|, y'K^-1y,
+//     K^-1y and K^-1 in one pass of identical panel/update kernels (n^3 flop total),
+//   * the fused gradient contraction sum_ij (K^-1 - aa'/s2)_ij dK_ij/dlog(theta_p) with dK recomputed
+//     on the fly.
+// Reference semantics: dgpsi/kernel_class.py:304-359 (k_matrix), :403-449 (llik), :481-492
+// (log_likelihood_func), :735-748 (compute_stats); dgpsi/functions.py:16-121.
+#include "dense.cuh"
+
+namespace dgpb {
+
+// ------------------------------------------------------------------------------------------------
+// small PTX helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool pred) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    int sz = pred ? 16 : 0;  // src-size 0 -> 16 bytes of zero fill
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gsrc), "r"(sz));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+// ------------------------------------------------------------------------------------------------
+// 1. kernel-matrix construction
+// ------------------------------------------------------------------------------------------------
+// One CTA builds a 64x64 tile (lower-triangular tile pairs only).  Scaled coordinates of the 64 row
+// points and 64 column points are staged in shared memory (coalesced loads from the variable-major
+// sources); each thread then produces 16 entries with consecutive threads on consecutive columns so
+// the stores are full 128-byte lines.  HBM-write bound: 8 n^2 / 2 bytes (lower) or 8 n^2 (MIRROR).
+template <bool MIRROR>
+__global__ void __launch_bounds__(256) kbuild_kernel(KernelDev kd, double* __restrict__ T, int64_t ld, int n, int npad,
+                                                     const double* __restrict__ wdiag) {
+    __shared__ double xi[kMaxDim][64];
+    __shared__ double xj[kMaxDim][64];
+    const int tid = threadIdx.x;
+    int t = blockIdx.x;
+    int ti = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+    while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
+    while (ti * (ti + 1) / 2 > t) --ti;
+    const int tj = t - ti * (ti + 1) / 2;
+    const int D = kd.D;
+    for (int idx = tid; idx < D * 64; idx += 256) {
+        int d = idx >> 6, l = idx & 63;
+        int gi = ti * 64 + l, gj = tj * 64 + l;
+        xi[d][l] = gi < n ? kd.x(d, gi) : 0.0;
+        xj[d][l] = gj < n ? kd.x(d, gj) : 0.0;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int e = 0; e < 16; ++e) {
+        int idx = tid + 256 * e;
+        int li = idx >> 6, lj = idx & 63;
+        int gi = ti * 64 + li, gj = tj * 64 + lj;
+        if (gj > gi) continue;
+        double v;
+        if (gi == gj) {
+            v = gi < n ? 1.0 + kd.nugget * (wdiag ? wdiag[gi] : 1.0) : 1.0;
+        } else if (gi >= n) {
+            v = 0.0;
+        } else {
+            v = corr_pair(kd.kind, D, [&](int d) { return xi[d][li]; }, [&](int d) { return xj[d][lj]; });
+        }
+        if (MIRROR) {
+            if (gi < n) {
+                T[(int64_t)gi * ld + gj] = v;
+                T[(int64_t)gj * ld + gi] = v;
+            }
+        } else {
+            T[(int64_t)gi * ld + gj] = v;
+        }
+    }
+}
+
+// dK/dlog(theta_p) slices for the API-parity entry point dgpb_kmatrix (kernel_class.py:328-351).
+// One thread per (i,j); not on the training hot path (the gradient kernel never materialises these).
+__global__ void dk_kernel(KernelDev kd, double* __restrict__ dK, int n, int P, int nugget_est,
+                          const double* __restrict__ wdiag) {
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)n * n) return;
+    int i = (int)(idx / n), j = (int)(idx % n);
+    const int D = kd.D;
+    const int nl = kd.ard ? D : 1;
+    const int64_t nn = (int64_t)n * n;
+    if (i == j) {
+        for (int p = 0; p < nl; ++p) dK[p * nn + idx] = 0.0;
+        if (nugget_est) dK[nl * nn + idx] = kd.nugget * (wdiag ? wdiag[i] : 1.0);
+        return;
+    }
+    if (nugget_est) dK[nl * nn + idx] = 0.0;
+    if (kd.kind == DGPB_SEXP) {
+        double dist = 0.0;
+        for (int d = 0; d < D; ++d) {
+            double df = kd.x(d, i) - kd.x(d, j);
+            dist = __dadd_rn(dist, __dmul_rn(df, df));
+        }
+        double K = exp(-dist);
+        if (kd.ard) {
+            for (int d = 0; d < D; ++d) {
+                double df = kd.x(d, i) - kd.x(d, j);
+                dK[d * nn + idx] = 2.0 * (df * df) * K;
+            }
+        } else {
+            dK[idx] = (2.0 * dist) * K;
+        }
+    } else {
+        double coef = 1.0, s = 0.0, csum = 0.0;
+        for (int d = 0; d < D; ++d) {
+            double r = fabs(kd.x(d, i) - kd.x(d, j));
+            double poly = 1.0 + kSqrt5 * r + (5.0 / 3.0) * (r * r);
+            coef *= poly;
+            s += r;
+            csum += (5.0 / 3.0) * (r * r) * (1.0 + kSqrt5 * r) / poly;
+        }
+        double K = coef * exp(-kSqrt5 * s);
+        if (kd.ard) {
+            for (int d = 0; d < D; ++d) {
+                double r = fabs(kd.x(d, i) - kd.x(d, j));
+                double poly = 1.0 + kSqrt5 * r + (5.0 / 3.0) * (r * r);
+                dK[d * nn + idx] = ((5.0 / 3.0) * (r * r) * (1.0 + kSqrt5 * r) / poly) * K;
+            }
+        } else {
+            dK[idx] = csum * K;
+        }
+    }
+}
+
+// y row (row npad) and, for the augmented layout, the unit entries of the identity rows.
+__global__ void rows_init_kernel(double* __restrict__ T, int64_t ld, int n, int npad, const double* __restrict__ y,
+                                 int aug) {
+    int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < ld) T[(int64_t)npad * ld + j] = (j < n && y) ? y[j] : 0.0;
+    if (aug && j < npad) T[(int64_t)(npad + 1 + j) * ld + j] = 1.0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// 2. blocked Cholesky: panel kernel (POTF2 + triangular inverse + TRSM-as-GEMM on DMMA)
+// ------------------------------------------------------------------------------------------------
+// Every CTA of the launch factors the same NB x NB diagonal block redundantly in shared memory (it is on
+// the critical path either way, and this removes one dependent launch per panel), inverts it, and then
+// applies X <- X * inv(L_kk)' to its own 128 rows of the panel with FP64 mma.  CTA 0 publishes L_kk and
+// diag(L_kk) to the side buffer (not into T: sibling CTAs are still reading the unfactored block).
+__device__ __forceinline__ void tri_inv_offdiag(const double* sL, double* sD, double* sT, int r0, int c0, int s,
+                                                int tid, int nthr) {
+    // sD[r0.., c0..] (s x s) = -D[r0.., r0..] * ( L[r0.., c0..] * D[c0.., c0..] ),  D lower-triangular blocks
+    for (int idx = tid; idx < s * s; idx += nthr) {
+        int a = idx / s, b = idx % s;
+        double acc = 0.0;
+        for (int k = b; k < s; ++k) acc += sL[(r0 + a) * LDS + c0 + k] * sD[(c0 + k) * LDS + c0 + b];
+        sT[a * 33 + b] = acc;
+    }
+    __syncthreads();
+    for (int idx = tid; idx < s * s; idx += nthr) {
+        int a = idx / s, b = idx % s;
+        double acc = 0.0;
+        for (int k = 0; k <= a; ++k) acc += sD[(r0 + a) * LDS + r0 + k] * sT[k * 33 + b];
+        sD[(r0 + a) * LDS + c0 + b] = -acc;
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(256, 1) panel_kernel(Batch bt, int64_t ld, int npad, int k0, int row_lo, int row_hi) {
+    extern __shared__ double smem[];
+    double* sL = smem;               // 64 x LDS : diagonal block -> L_kk
+    double* sD = sL + 64 * LDS;      // 64 x LDS : inv(L_kk)
+    double* sA = sD + 64 * LDS;      // 128 x LDS: this CTA's panel rows
+    double* sT = sA + TM * LDS;      // 32 x 33 scratch (also 2 x 16 x 33)
+    __shared__ double col[64];
+    const int tid = threadIdx.x;
+    double* __restrict__ T = bt.T[blockIdx.z];
+    const int r0 = row_lo + blockIdx.x * TM;
+
+    // (1) asynchronous load of the row tile; overlaps the diagonal-block factorisation
+    for (int c = tid; c < TM * 32; c += 256) {
+        int lr = c >> 5, ch = c & 31;
+        int gr = r0 + lr;
+        bool ok = gr < row_hi;
+        const double* src = T + (int64_t)(ok ? gr : k0) * ld + k0 + ch * 2;
+        cp_async16(&sA[lr * LDS + ch * 2], src, ok);
+    }
+    cp_async_commit();
+
+    // (2) diagonal block (lower part) into shared memory
+    for (int idx = tid; idx < 64 * 64; idx += 256) {
+        int i = idx >> 6, j = idx & 63;
+        sL[i * LDS + j] = (j <= i) ? T[(int64_t)(k0 + i) * ld + k0 + j] : 0.0;
+        sD[i * LDS + j] = 0.0;
+    }
+    __syncthreads();
+
+    // (3) unblocked right-looking Cholesky; thread (pi = tid/4, pc = tid%4) owns row pi, columns == pc mod 4
+    const int pi = tid >> 2, pc = tid & 3;
+    for (int j = 0; j < 64; ++j) {
+        double d = sL[j * LDS + j];
+        if (!(d > 0.0) && tid == 0 && blockIdx.x == 0) atomicCAS(&bt.info[blockIdx.z], 0, k0 + j + 1);
+        double sq = sqrt(d);
+        double inv = 1.0 / sq;
+        if (tid < 64) col[tid] = (tid > j) ? sL[tid * LDS + j] * inv : (tid == j ? sq : 0.0);
+        __syncthreads();
+        if (pi > j) {
+            double ci = col[pi];
+            for (int q = (j + 1) >> 2; q <= (pi >> 2); ++q) {
+                int k = 4 * q + pc;
+                if (k > j && k <= pi) sL[pi * LDS + k] -= ci * col[k];
+            }
+        }
+        if (tid < 64 && tid >= j) sL[tid * LDS + j] = col[tid];
+        __syncthreads();
+    }
+
+    // (4) inv(L_kk): 16x16 diagonal blocks by column-parallel substitution, then two block levels
+    if (tid < 64) {
+        int o = (tid >> 4) * 16, c = tid & 15;
+        sD[(o + c) * LDS + o + c] = 1.0 / sL[(o + c) * LDS + o + c];
+        for (int i = c + 1; i < 16; ++i) {
+            double s = 0.0;
+            for (int k = c; k < i; ++k) s += sL[(o + i) * LDS + o + k] * sD[(o + k) * LDS + o + c];
+            sD[(o + i) * LDS + o + c] = -s / sL[(o + i) * LDS + o + i];
+        }
+    }
+    __syncthreads();
+    {
+        // two independent 16x16 off-diagonal blocks, one per half CTA (uniform barriers: every thread
+        // makes the same calls, only the per-thread block coordinates differ)
+        const int half = tid >> 7;
+        tri_inv_offdiag(sL, sD, sT + half * 16 * 33, half ? 48 : 16, half ? 32 : 0, 16, tid & 127, 128);
+    }
+    tri_inv_offdiag(sL, sD, sT, 32, 0, 32, tid, 256);
+
+    if (blockIdx.x == 0) {
+        double* dg = bt.diag[blockIdx.z];
+        double* blk = dg + npad + (size_t)(k0 / NB) * NB * NB;
+        for (int idx = tid; idx < 64 * 64; idx += 256) blk[idx] = sL[(idx >> 6) * LDS + (idx & 63)];
+        if (tid < 64) dg[k0 + tid] = sL[tid * LDS + tid];
+    }
+
+    // (5) X = A * inv(L)'  on the FP64 tensor path: warp w owns rows [16w, 16w+16), all 64 columns
+    cp_async_wait<0>();
+    __syncthreads();
+    if (r0 >= row_hi) return;
+    const int w = tid >> 5, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
+    double acc[2][8][2];
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+        for (int nj = 0; nj < 8; ++nj) acc[mi][nj][0] = acc[mi][nj][1] = 0.0;
+#pragma unroll 4
+    for (int kk = 0; kk < 64; kk += 4) {
+        double a[2];
+#pragma unroll
+        for (int mi = 0; mi < 2; ++mi) a[mi] = sA[(16 * w + 8 * mi + g) * LDS + kk + t4];
+#pragma unroll
+        for (int nj = 0; nj < 8; ++nj) {
+            double b = sD[(8 * nj + g) * LDS + kk + t4];
+#pragma unroll
+            for (int mi = 0; mi < 2; ++mi) dmma884(acc[mi][nj][0], acc[mi][nj][1], a[mi], b);
+        }
+    }
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi) {
+        int gr = r0 + 16 * w + 8 * mi + g;
+        if (gr < row_hi) {
+#pragma unroll
+            for (int nj = 0; nj < 8; ++nj)
+                *reinterpret_cast<double2*>(&T[(int64_t)gr * ld + k0 + 8 * nj + 2 * t4]) =
+                    make_double2(acc[mi][nj][0], acc[mi][nj][1]);
+        }
+    }
+}
+
+constexpr size_t kPanelSmem = (size_t)(64 * LDS * 2 + TM * LDS + 32 * 33 + 16) * sizeof(double);
+
+// ------------------------------------------------------------------------------------------------
+// 3. trailing update  C[i,j] -= P_i P_j'  (lower tiles of the active window), FP64 mma, K = NB
+// ------------------------------------------------------------------------------------------------
+// 128x128 tile per CTA, 8 warps as 2 (rows) x 4 (cols), warp tile 64x32 = 8x4 m8n8 accumulators.
+// The accumulators are INITIALISED with the C tile (global loads issued before the panel data is
+// needed) and the A fragments are negated, so D = (-A)B' + C is a single DMMA chain per k-step.
+__global__ void __launch_bounds__(256, 1) update_kernel(Batch bt, int64_t ld, int k0, int row_lo, int row_hi) {
+    extern __shared__ double smem[];
+    int t = blockIdx.x;
+    int ti = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+    while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
+    while (ti * (ti + 1) / 2 > t) --ti;
+    const int tj = t - ti * (ti + 1) / 2;
+    double* sA = smem;
+    double* sB = (ti == tj) ? smem : smem + TM * LDS;
+    const int tid = threadIdx.x;
+    double* __restrict__ T = bt.T[blockIdx.z];
+    const int ra = row_lo + ti * TM, rb = row_lo + tj * TM;
+
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        for (int c = tid; c < TM * 16; c += 256) {
+            int lr = c >> 4, colo = half * 32 + (c & 15) * 2;
+            int gr = ra + lr;
+            bool ok = gr < row_hi;
+            cp_async16(&sA[lr * LDS + colo], T + (int64_t)(ok ? gr : k0) * ld + k0 + colo, ok);
+            if (ti != tj) {
+                int gq = rb + lr;
+                bool okb = gq < row_hi;
+                cp_async16(&sB[lr * LDS + colo], T + (int64_t)(okb ? gq : k0) * ld + k0 + colo, okb);
+            }
+        }
+        cp_async_commit();
+    }
+
+    const int w = tid >> 5, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
+    const int wm = w >> 2, wn = w & 3;
+    double acc[8][4][2];
+#pragma unroll
+    for (int mi = 0; mi < 8; ++mi) {
+        int gr = ra + 64 * wm + 8 * mi + g;
+#pragma unroll
+        for (int nj = 0; nj < 4; ++nj) {
+            int gc = rb + 32 * wn + 8 * nj + 2 * t4;
+            if (gr < row_hi && gc < row_hi) {
+                double2 v = *reinterpret_cast<const double2*>(&T[(int64_t)gr * ld + gc]);
+                acc[mi][nj][0] = v.x;
+                acc[mi][nj][1] = v.y;
+            } else {
+                acc[mi][nj][0] = acc[mi][nj][1] = 0.0;
+            }
+        }
+    }
+
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        if (half == 0) cp_async_wait<1>(); else cp_async_wait<0>();
+        __syncthreads();
+#pragma unroll 2
+        for (int kk = half * 32; kk < half * 32 + 32; kk += 4) {
+            double a[8], b[4];
+#pragma unroll
+            for (int mi = 0; mi < 8; ++mi) a[mi] = -sA[(64 * wm + 8 * mi + g) * LDS + kk + t4];
+#pragma unroll
+            for (int nj = 0; nj < 4; ++nj) b[nj] = sB[(32 * wn + 8 * nj + g) * LDS + kk + t4];
+#pragma unroll
+            for (int mi = 0; mi < 8; ++mi)
+#pragma unroll
+                for (int nj = 0; nj < 4; ++nj) dmma884(acc[mi][nj][0], acc[mi][nj][1], a[mi], b[nj]);
+        }
+    }
+
+#pragma unroll
+    for (int mi = 0; mi < 8; ++mi) {
+        int gr = ra + 64 * wm + 8 * mi + g;
+#pragma unroll
+        for (int nj = 0; nj < 4; ++nj) {
+            int gc = rb + 32 * wn + 8 * nj + 2 * t4;
+            if (gr < row_hi && gc < row_hi)
+                *reinterpret_cast<double2*>(&T[(int64_t)gr * ld + gc]) = make_double2(acc[mi][nj][0], acc[mi][nj][1]);
+        }
+    }
+}
+constexpr size_t kUpdateSmem = (size_t)(2 * TM * LDS) * sizeof(double);
+
+// ------------------------------------------------------------------------------------------------
+// 4. reductions / extraction
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) reduce_kernel(Batch bt, int64_t ld, int n, int npad, ScaleArgs sa,
+                                                     double* __restrict__ out) {
+    __shared__ double sred[8];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const double* dg = bt.diag[b];
+    const double* yrow = bt.T[b] + (int64_t)npad * ld;
+    double s1 = 0.0, s2 = 0.0;
+    for (int i = tid; i < n; i += 256) s1 += log(fabs(dg[i]));
+    for (int i = tid; i < npad; i += 256) s2 += yrow[i] * yrow[i];
+    s1 = block_sum<256>(s1, sred);
+    s2 = block_sum<256>(s2, sred);
+    if (tid == 0) {
+        out[b * 4 + 0] = 2.0 * s1;
+        out[b * 4 + 1] = s2;
+        out[b * 4 + 2] = sa.est[b] ? s2 / (double)n : sa.scale[b];
+        out[b * 4 + 3] = 0.0;
+    }
+}
+
+__global__ void restore_diag_kernel(Batch bt, int64_t ld, int npad) {
+    const int b = blockIdx.z, kb = blockIdx.x;
+    double* T = bt.T[b];
+    const double* blk = bt.diag[b] + npad + (size_t)kb * NB * NB;
+    for (int idx = threadIdx.x; idx < NB * NB; idx += blockDim.x) {
+        int i = idx >> 6, j = idx & 63;
+        if (j <= i) T[(int64_t)(kb * NB + i) * ld + kb * NB + j] = blk[idx];
+    }
+}
+
+// K^-1 (full symmetric n x n, ld = n) and K^-1 y out of the Schur complement of the augmented layout
+__global__ void extract_inverse_kernel(const double* __restrict__ T, int64_t ld, int n, int npad,
+                                       double* __restrict__ Rinv, double* __restrict__ Rinv_y) {
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)n * n) return;
+    int i = (int)(idx / n), j = (int)(idx % n);
+    int hi = i > j ? i : j, lo = i > j ? j : i;
+    Rinv[idx] = -T[(int64_t)(npad + 1 + hi) * ld + npad + 1 + lo];
+    if (j == 0 && Rinv_y) Rinv_y[i] = -T[(int64_t)(npad + 1 + i) * ld + npad];
+}
+
+// nu = sqrt(scale) * L z   (fmvn, functions.py:113-121, z injected); one warp per row, fixed order
+__global__ void trmv_kernel(const double* __restrict__ T, int64_t ld, int n, double sqrt_scale,
+                            const double* __restrict__ z, double* __restrict__ nu) {
+    int row = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    int lane = threadIdx.x & 31;
+    if (row >= n) return;
+    const double* Lr = T + (int64_t)row * ld;
+    double s = 0.0;
+    for (int j = lane; j <= row; j += 32) s += Lr[j] * z[j];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if (lane == 0) nu[row] = sqrt_scale * s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// 5. fused gradient contraction (kernel_class.py:418-427,435 without the P dense cho_solves)
+//    S_p = sum_ij W_ij dK_p,ij,  W = K^-1 - a a'/sigma2;  partials[tile][p] summed in fixed order later.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) grad_kernel(KernelDev kd, const double* __restrict__ T, int64_t ld, int n,
+                                                   int npad, int P, int nugget_est, const double* __restrict__ out4,
+                                                   double* __restrict__ partials) {
+    __shared__ double xi[kMaxDim][64];
+    __shared__ double xj[kMaxDim][64];
+    __shared__ double ai[64], aj[64];
+    __shared__ double sred[8];
+    const int tid = threadIdx.x;
+    int t = blockIdx.x;
+    int ti = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+    while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
+    while (ti * (ti + 1) / 2 > t) --ti;
+    const int tj = t - ti * (ti + 1) / 2;
+    const int D = kd.D;
+    const double sigma2 = out4[2];
+    for (int idx = tid; idx < D * 64; idx += 256) {
+        int d = idx >> 6, l = idx & 63;
+        int gi = ti * 64 + l, gj = tj * 64 + l;
+        xi[d][l] = gi < n ? kd.x(d, gi) : 0.0;
+        xj[d][l] = gj < n ? kd.x(d, gj) : 0.0;
+    }
+    if (tid < 64) {
+        int gi = ti * 64 + tid, gj = tj * 64 + tid;
+        ai[tid] = gi < n ? -T[(int64_t)(npad + 1 + gi) * ld + npad] : 0.0;
+        aj[tid] = gj < n ? -T[(int64_t)(npad + 1 + gj) * ld + npad] : 0.0;
+    }
+    __syncthreads();
+    // per-entry weights W_ij (x2 for strict lower, 0 for masked) and kernel values, kept in registers
+    double Wv[16], Kv[16];
+    double diagW = 0.0;
+#pragma unroll
+    for (int e = 0; e < 16; ++e) {
+        int idx = tid + 256 * e;
+        int li = idx >> 6, lj = idx & 63;
+        int gi = ti * 64 + li, gj = tj * 64 + lj;
+        Wv[e] = 0.0;
+        Kv[e] = 0.0;
+        if (gi < n && gj <= gi) {
+            double kinv = -T[(int64_t)(npad + 1 + gi) * ld + npad + 1 + gj];
+            double wgt = kinv - ai[li] * aj[lj] / sigma2;
+            if (gi == gj) {
+                diagW += wgt;
+            } else {
+                Wv[e] = 2.0 * wgt;
+                if (kd.kind == DGPB_SEXP) {
+                    double dist = 0.0;
+                    for (int d = 0; d < D; ++d) {
+                        double df = xi[d][li] - xj[d][lj];
+                        dist = __dadd_rn(dist, __dmul_rn(df, df));
+                    }
+                    Kv[e] = exp(-dist);
+                } else {
+                    double coef = 1.0, s = 0.0;
+                    for (int d = 0; d < D; ++d) {
+                        double r = fabs(xi[d][li] - xj[d][lj]);
+                        coef *= 1.0 + kSqrt5 * r + (5.0 / 3.0) * (r * r);
+                        s += r;
+                    }
+                    Kv[e] = coef * exp(-kSqrt5 * s);
+                }
+            }
+        }
+    }
+    const int nl = kd.ard ? D : 1;
+    for (int p = 0; p < nl; ++p) {
+        double acc = 0.0;
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+            int idx = tid + 256 * e;
+            int li = idx >> 6, lj = idx & 63;
+            double c = 0.0;
+            const int d0 = kd.ard ? p : 0, d1 = kd.ard ? p + 1 : D;
+            for (int d = d0; d < d1; ++d) {
+                double df = xi[d][li] - xj[d][lj];
+                if (kd.kind == DGPB_SEXP) {
+                    c += 2.0 * (df * df);
+                } else {
+                    double r = fabs(df);
+                    c += (5.0 / 3.0) * (r * r) * (1.0 + kSqrt5 * r) / (1.0 + kSqrt5 * r + (5.0 / 3.0) * (r * r));
+                }
+            }
+            acc += Wv[e] * (c * Kv[e]);
+        }
+        acc = block_sum<256>(acc, sred);
+        if (tid == 0) partials[(int64_t)t * P + p] = acc;
+    }
+    if (nugget_est) {
+        double acc = block_sum<256>(diagW, sred);
+        if (tid == 0) partials[(int64_t)t * P + nl] = kd.nugget * acc;
+    }
+}
+
+// out_final = [nllik, sigma2, grad[0..P)]
+__global__ void __launch_bounds__(256) grad_finish_kernel(const double* __restrict__ partials, int ntiles, int P, int n,
+                                                          int scale_est, const double* __restrict__ out4,
+                                                          double* __restrict__ out_final) {
+    __shared__ double sred[8];
+    const int p = blockIdx.x, tid = threadIdx.x;
+    double s = 0.0;
+    for (int t = tid; t < ntiles; t += 256) s += partials[(int64_t)t * P + p];
+    s = block_sum<256>(s, sred);
+    if (tid == 0) {
+        out_final[2 + p] = 0.5 * s;
+        if (p == 0) {
+            double logdet = out4[0], quad = out4[1], sigma2 = out4[2];
+            out_final[0] = scale_est ? 0.5 * (logdet + (double)n * log(sigma2)) : 0.5 * (logdet + quad / sigma2);
+            out_final[1] = sigma2;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host-side orchestration
+// ------------------------------------------------------------------------------------------------
+static int configure_once() {
+    static bool done = false;
+    if (done) return DGPB_OK;
+    DGPB_CUDA_TRY(cudaFuncSetAttribute(panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPanelSmem));
+    DGPB_CUDA_TRY(cudaFuncSetAttribute(update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUpdateSmem));
+    done = true;
+    return DGPB_OK;
+}
+
+int launch_trmv(const double* T, int64_t ld, int n, double sqrt_scale, const double* z, double* nu, cudaStream_t st) {
+    trmv_kernel<<<(unsigned)cdiv((int64_t)n * 32, 256), 256, 0, st>>>(T, ld, n, sqrt_scale, z, nu);
+    DGPB_LAUNCHED();
+    return DGPB_OK;
+}
+
+int setup_batch(Workspace* ws, const Geom& g, int B, Batch* bt, double** out_dev) {
+    DGPB_REQUIRE(B >= 1 && B <= MAXB, "batch size out of range");
+    void *pT, *pD, *pO, *pI;
+    DGPB_TRY(ws->reserve(SLOT_T, g.elems() * sizeof(double) * B, &pT));
+    DGPB_TRY(ws->reserve(SLOT_DIAG, diag_elems(g) * sizeof(double) * B, &pD));
+    DGPB_TRY(ws->reserve(SLOT_OUT, sizeof(double) * kOutDoubles, &pO));
+    DGPB_TRY(ws->reserve(SLOT_INFO, sizeof(int) * MAXB, &pI));
+    for (int b = 0; b < MAXB; ++b) {
+        bt->T[b] = b < B ? (double*)pT + g.elems() * b : nullptr;
+        bt->diag[b] = b < B ? (double*)pD + diag_elems(g) * b : nullptr;
+    }
+    bt->info = (int*)pI;
+    *out_dev = (double*)pO;
+    return DGPB_OK;
+}
+
+int assemble(const Geom& g, const KernelDev* kds, const double* const* ys, const Batch& bt, int B, cudaStream_t st) {
+    const int nt = g.npad / 64;
+    for (int b = 0; b < B; ++b) {
+        if (g.aug) {
+            // identity rows and the Schur-complement block start at zero
+            DGPB_CUDA_TRY(cudaMemsetAsync(bt.T[b] + (size_t)(g.npad + 1) * g.ld, 0,
+                                          (size_t)(g.R - g.npad - 1) * g.ld * sizeof(double), st));
+        }
+        kbuild_kernel<false><<<nt * (nt + 1) / 2, 256, 0, st>>>(kds[b], bt.T[b], g.ld, g.n, g.npad, nullptr);
+        DGPB_LAUNCHED();
+        rows_init_kernel<<<(unsigned)cdiv(g.ld, 256), 256, 0, st>>>(bt.T[b], g.ld, g.n, g.npad, ys ? ys[b] : nullptr,
+                                                                   g.aug ? 1 : 0);
+        DGPB_LAUNCHED();
+    }
+    DGPB_CUDA_TRY(cudaMemsetAsync(bt.info, 0, sizeof(int) * MAXB, st));
+    return DGPB_OK;
+}
+
+int factorize(const Geom& g, const Batch& bt, int B, cudaStream_t st) {
+    DGPB_TRY(configure_once());
+    for (int k0 = 0; k0 < g.npad; k0 += NB) {
+        const int k1 = k0 + NB;
+        const int row_hi = g.aug ? g.npad + 1 + k1 : g.R;
+        const int rows = row_hi - k1;
+        dim3 pg((unsigned)(rows > 0 ? cdiv(rows, TM) : 1), 1, (unsigned)B);
+        panel_kernel<<<pg, 256, kPanelSmem, st>>>(bt, g.ld, g.npad, k0, k1, row_hi);
+        DGPB_LAUNCHED();
+        if (rows > 0) {
+            const int nt = (int)cdiv(rows, TM);
+            dim3 ug((unsigned)(nt * (nt + 1) / 2), 1, (unsigned)B);
+            update_kernel<<<ug, 256, kUpdateSmem, st>>>(bt, g.ld, k0, k1, row_hi);
+            DGPB_LAUNCHED();
+        }
+    }
+    return DGPB_OK;
+}
+
+int reduce_logdet_quad(const Geom& g, const Batch& bt, int B, const ScaleArgs& sa, double* out, cudaStream_t st) {
+    reduce_kernel<<<B, 256, 0, st>>>(bt, g.ld, g.n, g.npad, sa, out);
+    DGPB_LAUNCHED();
+    return DGPB_OK;
+}
+
+int restore_diag_blocks(const Geom& g, const Batch& bt, int B, cudaStream_t st) {
+    dim3 grid((unsigned)(g.npad / NB), 1, (unsigned)B);
+    restore_diag_kernel<<<grid, 256, 0, st>>>(bt, g.ld, g.npad);
+    DGPB_LAUNCHED();
+    return DGPB_OK;
+}
+
+int loglik_batch_device(Workspace* ws, const KernelDev* kds, const double* const* ys, const ScaleArgs& sa, int B,
+                        int64_t n, Batch* bt_out, Geom* g_out, double** out_dev, cudaStream_t st) {
+    Geom g = make_geom(n, false);
+    Batch bt;
+    double* out;
+    DGPB_TRY(setup_batch(ws, g, B, &bt, &out));
+    DGPB_TRY(assemble(g, kds, ys, bt, B, st));
+    DGPB_TRY(factorize(g, bt, B, st));
+    DGPB_TRY(reduce_logdet_quad(g, bt, B, sa, out, st));
+    if (bt_out) *bt_out = bt;
+    if (g_out) *g_out = g;
+    *out_dev = out;
+    return DGPB_OK;
+}
+
+// copy `count` doubles + the info flags back and check positive-definiteness
+static int fetch_results(Workspace* ws, const Batch& bt, const double* dev, int count, int B, double* host,
+                         cudaStream_t st) {
+    int* info_host = reinterpret_cast<int*>(ws->pinned + 2048);
+    DGPB_CUDA_TRY(cudaMemcpyAsync(ws->pinned, dev, sizeof(double) * count, cudaMemcpyDeviceToHost, st));
+    DGPB_CUDA_TRY(cudaMemcpyAsync(info_host, bt.info, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
+    DGPB_CUDA_TRY(cudaStreamSynchronize(st));
+    for (int b = 0; b < B; ++b) {
+        if (info_host[b] != 0) {
+            set_error("matrix %d is not positive definite (pivot %d)", b, info_host[b]);
+            return DGPB_NOT_PD;
+        }
+    }
+    for (int i = 0; i < count; ++i) host[i] = ws->pinned[i];
+    return DGPB_OK;
+}
+
+// host formula of kernel_class.py:482-488 from (logdet K, y'K^-1y): cov = scale*K
+static inline double llik_from(double logdetK, double quadK, double scale, int64_t n) {
+    return -0.5 * (logdetK + (double)n * log(scale) + quadK / scale);
+}
+
+int grad_pipeline(Workspace* ws, const dgpb_node* node, int64_t n, bool want_grad, double* Rinv, double* Rinv_y,
+                  double* out_host, cudaStream_t st) {
+    KernelDev kd;
+    DGPB_TRY(make_kernel_dev(node, n, nullptr, &kd));
+    Geom g = make_geom(n, true);
+    Batch bt;
+    double* out;
+    DGPB_TRY(setup_batch(ws, g, 1, &bt, &out));
+    const double* ys[1] = {node->output};
+    DGPB_TRY(assemble(g, &kd, ys, bt, 1, st));
+    DGPB_TRY(factorize(g, bt, 1, st));
+    ScaleArgs sa;
+    sa.scale[0] = node->scale;
+    sa.est[0] = node->scale_est;
+    DGPB_TRY(reduce_logdet_quad(g, bt, 1, sa, out, st));
+    if (Rinv) {
+        extract_inverse_kernel<<<(unsigned)cdiv(n * n, 256), 256, 0, st>>>(bt.T[0], g.ld, g.n, g.npad, Rinv, Rinv_y);
+        DGPB_LAUNCHED();
+    }
+    if (want_grad) {
+        const int nl = node->nlen;
+        const int P = nl + (node->nugget_est ? 1 : 0);
+        const int nt = (int)cdiv(n, 64);
+        const int ntiles = nt * (nt + 1) / 2;
+        void* part;
+        DGPB_TRY(ws->reserve(SLOT_PART, sizeof(double) * (size_t)ntiles * P, &part));
+        grad_kernel<<<ntiles, 256, 0, st>>>(kd, bt.T[0], g.ld, g.n, g.npad, P, node->nugget_est, out, (double*)part);
+        DGPB_LAUNCHED();
+        double* fin = out + kOutGrad;
+        grad_finish_kernel<<<P, 256, 0, st>>>((double*)part, ntiles, P, g.n, node->scale_est, out, fin);
+        DGPB_LAUNCHED();
+        DGPB_TRY(fetch_results(ws, bt, fin, P + 2, 1, out_host, st));
+    } else {
+        double tmp[4];
+        DGPB_TRY(fetch_results(ws, bt, out, 4, 1, tmp, st));
+    }
+    return DGPB_OK;
+}
+
+}  // namespace dgpb
+
+using namespace dgpb;
+
+extern "C" {
+
+int dgpb_kmatrix(const double* X, int64_t n, int64_t D, const double* length_host, int64_t nlen, double nugget,
+                 const double* wdiag, int kind, int nugget_est, double* K, double* dK, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    DGPB_REQUIRE(n >= 1 && K != nullptr, "n < 1 or K is NULL");
+    KernelDev kd;
+    DGPB_TRY(make_kernel_dev_rowmajor(X, D, length_host, nlen, nugget, kind, &kd));
+    const int nt = (int)cdiv(n, 64);
+    kbuild_kernel<true><<<nt * (nt + 1) / 2, 256, 0, st>>>(kd, K, n, (int)n, nt * 64, wdiag);
+    DGPB_LAUNCHED();
+    if (dK) {
+        const int P = (int)nlen + (nugget_est ? 1 : 0);
+        dk_kernel<<<(unsigned)cdiv(n * n, 256), 256, 0, st>>>(kd, dK, (int)n, P, nugget_est, wdiag);
+        DGPB_LAUNCHED();
+    }
+    return DGPB_OK;
+}
+
+int dgpb_loglik_dense(dgpb_ws* ws, const dgpb_node* node, int64_t n, double* out_host, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    DGPB_REQUIRE(ws && node && out_host && n >= 1, "NULL argument");
+    KernelDev kd;
+    DGPB_TRY(make_kernel_dev(node, n, nullptr, &kd));
+    const double* ys[1] = {node->output};
+    ScaleArgs sa;
+    sa.scale[0] = node->scale;
+    sa.est[0] = 0;
+    Batch bt;
+    Geom g;
+    double* out;
+    DGPB_TRY(loglik_batch_device(ws, &kd, ys, sa, 1, n, &bt, &g, &out, st));
+    double r[4];
+    DGPB_TRY(fetch_results(ws, bt, out, 4, 1, r, st));
+    out_host[0] = llik_from(r[0], r[1], node->scale, n);
+    return DGPB_OK;
+}
+
+int dgpb_nllik_grad_dense(dgpb_ws* ws, const dgpb_node* node, int64_t n, double* out_host, void* stream) {
+    DGPB_REQUIRE(ws && node && out_host && n >= 1, "NULL argument");
+    return grad_pipeline(ws, node, n, true, nullptr, nullptr, out_host, (cudaStream_t)stream);
+}
+
+int dgpb_compute_stats(dgpb_ws* ws, const dgpb_node* node, int64_t n, double* Rinv, double* Rinv_y, void* stream) {
+    DGPB_REQUIRE(ws && node && Rinv && Rinv_y && n >= 1, "NULL argument");
+    return grad_pipeline(ws, node, n, false, Rinv, Rinv_y, nullptr, (cudaStream_t)stream);
+}
+
+int dgpb_mvn_draw(dgpb_ws* ws, const dgpb_node* node, int64_t n, const double* z, double* nu, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    DGPB_REQUIRE(ws && node && z && nu && n >= 1, "NULL argument");
+    KernelDev kd;
+    DGPB_TRY(make_kernel_dev(node, n, nullptr, &kd));
+    Geom g = make_geom(n, false);
+    Batch bt;
+    double* out;
+    DGPB_TRY(setup_batch(ws, g, 1, &bt, &out));
+    DGPB_TRY(assemble(g, &kd, nullptr, bt, 1, st));
+    DGPB_TRY(factorize(g, bt, 1, st));
+    DGPB_TRY(restore_diag_blocks(g, bt, 1, st));
+    DGPB_TRY(launch_trmv(bt.T[0], g.ld, g.n, sqrt(node->scale), z, nu, st));
+    int* info_host = reinterpret_cast<int*>(ws->pinned + 2048);
+    DGPB_CUDA_TRY(cudaMemcpyAsync(info_host, bt.info, sizeof(int), cudaMemcpyDeviceToHost, st));
+    DGPB_CUDA_TRY(cudaStreamSynchronize(st));
+    if (info_host[0] != 0) {
+        set_error("covariance is not positive definite (pivot %d)", info_host[0]);
+        return DGPB_NOT_PD;
+    }
+    return DGPB_OK;
+}
+
+int dgpb_potrf(dgpb_ws* ws, double* A, int64_t n, int* info_host, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    DGPB_REQUIRE(ws && A && n >= 1, "NULL argument");
+    Geom g = make_geom(n, false);
+    Batch bt;
+    double* out;
+    DGPB_TRY(setup_batch(ws, g, 1, &bt, &out));
+    DGPB_CUDA_TRY(cudaMemsetAsync(bt.T[0], 0, g.elems() * sizeof(double), st));
+    DGPB_CUDA_TRY(cudaMemcpy2DAsync(bt.T[0], g.ld * sizeof(double), A, n * sizeof(double), n * sizeof(double), n,
+                                    cudaMemcpyDeviceToDevice, st));
+    if (g.npad > g.n) {
+        // identity padding on the diagonal
+        std::vector<double> one(1, 1.0);
+        for (int i = g.n; i < g.npad; ++i)
+            DGPB_CUDA_TRY(cudaMemcpyAsync(bt.T[0] + (size_t)i * g.ld + i, one.data(), sizeof(double),
+                                          cudaMemcpyHostToDevice, st));
+    }
+    DGPB_CUDA_TRY(cudaMemsetAsync(bt.info, 0, sizeof(int) * MAXB, st));
+    DGPB_TRY(factorize(g, bt, 1, st));
+    DGPB_TRY(restore_diag_blocks(g, bt, 1, st));
+    DGPB_CUDA_TRY(cudaMemcpy2DAsync(A, n * sizeof(double), bt.T[0], g.ld * sizeof(double), n * sizeof(double), n,
+                                    cudaMemcpyDeviceToDevice, st));
+    int* ih = reinterpret_cast<int*>(ws->pinned + 2048);
+    DGPB_CUDA_TRY(cudaMemcpyAsync(ih, bt.info, sizeof(int), cudaMemcpyDeviceToHost, st));
+    DGPB_CUDA_TRY(cudaStreamSynchronize(st));
+    if (info_host) *info_host = ih[0];
+    return DGPB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,260 @@
+// ess.cu -- elliptical slice sampling of one latent layer (Murray, Adams & MacKay) on the device.
+// Restates imputer.one_sample_block / one_sample  (dgpsi/imputation.py:44-119, :166-221):
+//   nu_k  = chol(scale_k K_k) z_k                      for every target node k   (fmvn / fmvn_sp)
+//   log_y = sum_upper loglik(current) + log(u0)
+//   theta = 2 pi u1, bracket [theta-2pi, theta]; proposal f' = f cos(theta) + nu sin(theta);
+//   accept iff sum_upper loglik(f') > log_y, else shrink the bracket towards 0 and redraw.
+// The latent layer, the prior draws and every proposal stay in HBM; the likelihoods of all upper
+// nodes of a proposal are evaluated by ONE batched factorisation (blockIdx.z = node).  The host only
+// sees one scalar per proposal (the summed log-likelihood) to take the accept/shrink decision with the
+// caller's uniforms, which keeps the decision sequence identical to the reference under injected draws.
+#include "dense.cuh"
+#include "vecchia.cuh"
+
+namespace dgpb {
+
+__global__ void propose_kernel(double* __restrict__ prop, const double* __restrict__ f, const double* __restrict__ nu,
+                               double c, double s, int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    // update_f (functions.py:203-208): f*cos(theta) + nu*sin(theta), two products then one sum
+    if (i < n) prop[i] = __dadd_rn(__dmul_rn(f[i], c), __dmul_rn(nu[i], s));
+}
+
+// raw node inputs and outputs gathered in Vecchia order: Xo[r][k] = x_k(ord[r]), yo[r] = y[ord[r]]
+__global__ void gather_ord_kernel(KernelDev kd, const double* __restrict__ y, const int64_t* __restrict__ ord, int64_t n,
+                                  double* __restrict__ Xo, double* __restrict__ yo) {
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    int64_t i = ord[r];
+    for (int d = 0; d < kd.D; ++d) Xo[r * kd.D + d] = kd.raw(d, i);
+    if (yo) yo[r] = y[i];
+}
+
+// out[ord[r]] = in[r]      ( x[rev_ord] of imputation.py:61 )
+__global__ void scatter_ord_kernel(const double* __restrict__ in, const int64_t* __restrict__ ord, int64_t n,
+                                   double* __restrict__ out) {
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < n) out[ord[r]] = in[r];
+}
+
+static int node_lengths(const dgpb_node* nd, double* len, int* D) {
+    *D = nd->n_local + nd->n_global;
+    for (int d = 0; d < *D; ++d) len[d] = nd->length[nd->nlen == 1 ? 0 : d];
+    return DGPB_OK;
+}
+
+// sum of the log-likelihoods of `U` nodes whose local inputs are read from `src_override`
+// (or from node->src when NULL).  Dense nodes are batched; Vecchia nodes use the block kernel.
+static int nodes_loglik(Workspace* ws, const dgpb_node* nodes, int U, int64_t n, const double* src_override,
+                        double* sum_host, cudaStream_t st) {
+    double lls[256];
+    DGPB_REQUIRE(U >= 1 && U <= 256, "too many upper nodes");
+    int nv = 0;
+    // Vecchia nodes first (results land in the Vecchia section of the result buffer)
+    void* outv = nullptr;
+    DGPB_TRY(ws->reserve(SLOT_OUT, sizeof(double) * kOutDoubles, &outv));
+    double* out = (double*)outv;
+    for (int u = 0; u < U; ++u) {
+        if (!nodes[u].vecch) continue;
+        DGPB_REQUIRE(nv < (kOutGrad - kOutVecchia) / 2, "too many Vecchia nodes in one layer");
+        const dgpb_node* nd = &nodes[u];
+        DGPB_REQUIRE(nd->ord && nd->NNarray, "Vecchia node without ord/NNarray");
+        KernelDev kd;
+        DGPB_TRY(make_kernel_dev(nd, n, src_override, &kd));
+        void *Xo, *yo;
+        // per-node gather buffers: the stream orders reuse across nodes
+        DGPB_TRY(ws->reserve(SLOT_VX, sizeof(double) * (size_t)n * kd.D, &Xo));
+        DGPB_TRY(ws->reserve(SLOT_VY, sizeof(double) * (size_t)n, &yo));
+        gather_ord_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(kd, nd->output, nd->ord, n, (double*)Xo, (double*)yo);
+        DGPB_LAUNCHED();
+        VKern vk;
+        double len[kMaxDim];
+        int D;
+        node_lengths(nd, len, &D);
+        DGPB_TRY(make_vkern(nd->kind, D, len, D, &vk));
+        DGPB_TRY(vecchia_llik_device(ws, vk, (double*)Xo, (double*)yo, nd->NNarray, n, nd->m + 1, nd->nugget, nullptr,
+                                     out + kOutVecchia + 2 * nv, st));
+        ++nv;
+    }
+    // dense nodes in batches
+    int u0 = 0;
+    while (u0 < U) {
+        KernelDev kds[MAXB];
+        const double* ys[MAXB];
+        int map[MAXB];
+        ScaleArgs sa;
+        int B = 0;
+        while (u0 < U && B < MAXB) {
+            if (!nodes[u0].vecch) {
+                DGPB_TRY(make_kernel_dev(&nodes[u0], n, src_override, &kds[B]));
+                ys[B] = nodes[u0].output;
+                sa.scale[B] = nodes[u0].scale;
+                sa.est[B] = 0;
+                map[B] = u0;
+                ++B;
+            }
+            ++u0;
+        }
+        if (B == 0) break;
+        Batch bt;
+        Geom g;
+        double* outd;
+        DGPB_TRY(loglik_batch_device(ws, kds, ys, sa, B, n, &bt, &g, &outd, st));
+        int* info_host = reinterpret_cast<int*>(ws->pinned + 2048);
+        DGPB_CUDA_TRY(cudaMemcpyAsync(ws->pinned, outd, sizeof(double) * 4 * B, cudaMemcpyDeviceToHost, st));
+        DGPB_CUDA_TRY(cudaMemcpyAsync(info_host, bt.info, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
+        DGPB_CUDA_TRY(cudaStreamSynchronize(st));
+        for (int b = 0; b < B; ++b) {
+            if (info_host[b] != 0) {
+                set_error("covariance of upper node %d is not positive definite (pivot %d)", map[b], info_host[b]);
+                return DGPB_NOT_PD;
+            }
+            const double sc = nodes[map[b]].scale;
+            lls[map[b]] = -0.5 * (ws->pinned[4 * b] + (double)n * log(sc) + ws->pinned[4 * b + 1] / sc);
+        }
+    }
+    if (nv > 0) {
+        DGPB_CUDA_TRY(cudaMemcpyAsync(ws->pinned + 1024, out + kOutVecchia, sizeof(double) * 2 * nv,
+                                      cudaMemcpyDeviceToHost, st));
+        DGPB_CUDA_TRY(cudaStreamSynchronize(st));
+        int v = 0;
+        for (int u = 0; u < U; ++u) {
+            if (!nodes[u].vecch) continue;
+            double quad = ws->pinned[1024 + 2 * v], logdet = ws->pinned[1024 + 2 * v + 1];
+            if (!(quad == quad) || !(logdet == logdet)) {
+                set_error("Vecchia block of upper node %d is not positive definite", u);
+                return DGPB_NOT_PD;
+            }
+            lls[u] = -0.5 * (logdet + quad / nodes[u].scale);  // vecchia.py:179
+            ++v;
+        }
+    }
+    double s = 0.0;
+    for (int u = 0; u < U; ++u) s += lls[u];  // same left-to-right order as imputation.py:70-78
+    *sum_host = s;
+    return DGPB_OK;
+}
+
+// prior draws nu[k] = chol(scale K) z_k for the target nodes
+static int prior_draws(Workspace* ws, const dgpb_node* targets, int M, int64_t n, const double* z, double* nu,
+                       cudaStream_t st) {
+    for (int k = 0; k < M; ++k) {
+        const dgpb_node* nd = &targets[k];
+        if (!nd->vecch) continue;
+        DGPB_REQUIRE(nd->ord && nd->NNarray, "Vecchia node without ord/NNarray");
+        KernelDev kd;
+        DGPB_TRY(make_kernel_dev(nd, n, nullptr, &kd));
+        void *Xo, *tmp;
+        DGPB_TRY(ws->reserve(SLOT_VX, sizeof(double) * (size_t)n * kd.D, &Xo));
+        DGPB_TRY(ws->reserve(SLOT_VY, sizeof(double) * (size_t)n, &tmp));
+        gather_ord_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(kd, nullptr, nd->ord, n, (double*)Xo, nullptr);
+        DGPB_LAUNCHED();
+        VKern vk;
+        double len[kMaxDim];
+        int D;
+        node_lengths(nd, len, &D);
+        DGPB_TRY(make_vkern(nd->kind, D, len, D, &vk));
+        DGPB_TRY(vecchia_mvn_draw_device(ws, vk, (double*)Xo, nd->NNarray, n, nd->m + 1, nd->scale, nd->nugget,
+                                         z + (int64_t)k * n, (double*)tmp, st));
+        scatter_ord_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>((double*)tmp, nd->ord, n, nu + (int64_t)k * n);
+        DGPB_LAUNCHED();
+    }
+    int k0 = 0;
+    while (k0 < M) {
+        KernelDev kds[MAXB];
+        int map[MAXB];
+        int B = 0;
+        while (k0 < M && B < MAXB) {
+            if (!targets[k0].vecch) {
+                DGPB_TRY(make_kernel_dev(&targets[k0], n, nullptr, &kds[B]));
+                map[B] = k0;
+                ++B;
+            }
+            ++k0;
+        }
+        if (B == 0) break;
+        Geom g = make_geom(n, false);
+        Batch bt;
+        double* outd;
+        DGPB_TRY(setup_batch(ws, g, B, &bt, &outd));
+        DGPB_TRY(assemble(g, kds, nullptr, bt, B, st));
+        DGPB_TRY(factorize(g, bt, B, st));
+        DGPB_TRY(restore_diag_blocks(g, bt, B, st));
+        for (int b = 0; b < B; ++b) {
+            DGPB_TRY(launch_trmv(bt.T[b], g.ld, g.n, sqrt(targets[map[b]].scale), z + (int64_t)map[b] * n,
+                                 nu + (int64_t)map[b] * n, st));
+        }
+        int* info_host = reinterpret_cast<int*>(ws->pinned + 2048);
+        DGPB_CUDA_TRY(cudaMemcpyAsync(info_host, bt.info, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
+        DGPB_CUDA_TRY(cudaStreamSynchronize(st));
+        for (int b = 0; b < B; ++b)
+            if (info_host[b] != 0) {
+                set_error("prior covariance of target node %d is not positive definite (pivot %d)", map[b], info_host[b]);
+                return DGPB_NOT_PD;
+            }
+    }
+    return DGPB_OK;
+}
+
+}  // namespace dgpb
+
+using namespace dgpb;
+
+extern "C" int dgpb_ess_block(dgpb_ws* ws, const dgpb_node* targets, int n_targets, const int32_t* target_rows_host,
+                              double* layer_out, int64_t layer_width, const dgpb_node* uppers, int n_uppers, int64_t n,
+                              const double* z, const double* u_host, int nu, int* n_prop_host, double* theta_host,
+                              void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    DGPB_REQUIRE(ws && targets && uppers && layer_out && z && u_host && target_rows_host, "NULL argument");
+    DGPB_REQUIRE(n_targets >= 1 && n_uppers >= 1 && n >= 1 && nu >= 3, "bad sizes");
+    for (int k = 0; k < n_targets; ++k)
+        DGPB_REQUIRE(target_rows_host[k] >= 0 && target_rows_host[k] < layer_width, "target row out of range");
+    void *pnu, *pprop;
+    DGPB_TRY(ws->reserve(SLOT_NU, sizeof(double) * (size_t)n_targets * n, &pnu));
+    DGPB_TRY(ws->reserve(SLOT_PROP, sizeof(double) * (size_t)layer_width * n, &pprop));
+    double* nuv = (double*)pnu;
+    double* prop = (double*)pprop;
+
+    DGPB_TRY(prior_draws(ws, targets, n_targets, n, z, nuv, st));
+
+    double log_y = 0.0;
+    DGPB_TRY(nodes_loglik(ws, uppers, n_uppers, n, nullptr, &log_y, st));
+    int ui = 0;
+    log_y += log(u_host[ui++]);                       // imputation.py:79
+    double theta = 0.0 + (2.0 * M_PI - 0.0) * u_host[ui++];  // uniform(0, 2pi)          imputation.py:81
+    double tmin = theta - 2.0 * M_PI, tmax = theta;
+
+    // rows of the layer that are not being updated are shared by every proposal
+    DGPB_CUDA_TRY(cudaMemcpyAsync(prop, layer_out, sizeof(double) * (size_t)layer_width * n, cudaMemcpyDeviceToDevice, st));
+    int nprop = 0;
+    while (true) {
+        if (theta_host) theta_host[nprop] = theta;
+        ++nprop;
+        const double c = cos(theta), s = sin(theta);
+        for (int k = 0; k < n_targets; ++k) {
+            const int64_t row = target_rows_host[k];
+            propose_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(prop + row * n, layer_out + row * n, nuv + (int64_t)k * n,
+                                                                  c, s, n);
+            DGPB_LAUNCHED();
+        }
+        double log_yp = 0.0;
+        DGPB_TRY(nodes_loglik(ws, uppers, n_uppers, n, prop, &log_yp, st));
+        if (log_yp > log_y) {  // imputation.py:107-110
+            for (int k = 0; k < n_targets; ++k) {
+                const int64_t row = target_rows_host[k];
+                DGPB_CUDA_TRY(cudaMemcpyAsync(layer_out + row * n, prop + row * n, sizeof(double) * n,
+                                              cudaMemcpyDeviceToDevice, st));
+            }
+            break;
+        }
+        if (theta < 0.0) tmin = theta; else tmax = theta;  // imputation.py:115-118
+        if (ui >= nu) {
+            if (n_prop_host) *n_prop_host = nprop;
+            set_error("ESS ran out of uniforms after %d proposals", nprop);
+            return DGPB_BAD_ARG;
+        }
+        theta = tmin + (tmax - tmin) * u_host[ui++];  // imputation.py:119
+    }
+    if (n_prop_host) *n_prop_host = nprop;
+    return DGPB_OK;
+}

@@ -1,0 +1,635 @@
+// predict.cu -- closed-form GP / linked-GP predictive moments on sm_100a.
+//   gp()       dgpsi/functions.py:379-394   -> cross-kernel matrix + FP64-mma GEMM (R * R^-1) + row reductions
+//   link_gp()  dgpsi/functions.py:396-430   -> streaming kernels over (test-point tile) x (training-pair tile):
+//              IJ_sexp functions.py:432-451, IJ_matern functions.py:453-494, Jd/Jd0 vecchia.py:915-988,
+//              trace_sum functions.py:496-506, quad vecchia.py:990-1000.
+//   The J matrix (n x n per test point) and the sexp R2sexp/Psexp tables (kernel_class.py:752-764) are never
+//   materialised: each J entry is produced in registers and immediately contracted with R^-1 and aa'.
+#include "common.cuh"
+#include "linkmath.cuh"
+
+namespace dgpb {
+
+__device__ __forceinline__ void dmma884p(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void cp_async16p(void* smem_dst, const void* gsrc, bool pred) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    int sz = pred ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gsrc), "r"(sz));
+}
+
+// ------------------------------------------------------------------------------------------------
+// general FP64 GEMM  C (M x N) = A (M x K) * B (N x K)'   (K a multiple of 32, lda/ldb even)
+// 128x128 tile, 8 warps (2x4), warp tile 64x32, BK = 32, two cp.async stages.
+// ------------------------------------------------------------------------------------------------
+constexpr int GBK = 32;
+constexpr int GLD = 36;  // 36 % 16 == 4: conflict-free fragment loads
+constexpr size_t kGemmSmem = (size_t)2 * 2 * 128 * GLD * sizeof(double);
+
+__global__ void __launch_bounds__(256, 1) gemm_nt_kernel(const double* __restrict__ A, int64_t lda,
+                                                         const double* __restrict__ B, int64_t ldb,
+                                                         double* __restrict__ C, int64_t ldc, int M, int N, int K) {
+    extern __shared__ double smem[];
+    const int tid = threadIdx.x;
+    const int m0 = blockIdx.y * 128, n0 = blockIdx.x * 128;
+    auto stageA = [&](int s) { return smem + (size_t)s * 2 * 128 * GLD; };
+    auto stageB = [&](int s) { return smem + (size_t)s * 2 * 128 * GLD + 128 * GLD; };
+    auto load_stage = [&](int s, int kbase) {
+        double* sA = stageA(s);
+        double* sB = stageB(s);
+        for (int c = tid; c < 128 * 16; c += 256) {
+            int lr = c >> 4, co = (c & 15) * 2;
+            bool oka = m0 + lr < M, okb = n0 + lr < N;
+            cp_async16p(&sA[lr * GLD + co], A + (int64_t)(oka ? m0 + lr : 0) * lda + kbase + co, oka);
+            cp_async16p(&sB[lr * GLD + co], B + (int64_t)(okb ? n0 + lr : 0) * ldb + kbase + co, okb);
+        }
+        asm volatile("cp.async.commit_group;\n" ::);
+    };
+    const int w = tid >> 5, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
+    const int wm = w >> 2, wn = w & 3;
+    double acc[8][4][2];
+#pragma unroll
+    for (int mi = 0; mi < 8; ++mi)
+#pragma unroll
+        for (int nj = 0; nj < 4; ++nj) acc[mi][nj][0] = acc[mi][nj][1] = 0.0;
+    const int nk = K / GBK;
+    load_stage(0, 0);
+    for (int kt = 0; kt < nk; ++kt) {
+        if (kt + 1 < nk) {
+            load_stage((kt + 1) & 1, (kt + 1) * GBK);
+            asm volatile("cp.async.wait_group 1;\n" ::);
+        } else {
+            asm volatile("cp.async.wait_group 0;\n" ::);
+        }
+        __syncthreads();
+        const double* sA = stageA(kt & 1);
+        const double* sB = stageB(kt & 1);
+#pragma unroll 2
+        for (int kk = 0; kk < GBK; kk += 4) {
+            double a[8], b[4];
+#pragma unroll
+            for (int mi = 0; mi < 8; ++mi) a[mi] = sA[(64 * wm + 8 * mi + g) * GLD + kk + t4];
+#pragma unroll
+            for (int nj = 0; nj < 4; ++nj) b[nj] = sB[(32 * wn + 8 * nj + g) * GLD + kk + t4];
+#pragma unroll
+            for (int mi = 0; mi < 8; ++mi)
+#pragma unroll
+                for (int nj = 0; nj < 4; ++nj) dmma884p(acc[mi][nj][0], acc[mi][nj][1], a[mi], b[nj]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int mi = 0; mi < 8; ++mi) {
+        int gr = m0 + 64 * wm + 8 * mi + g;
+        if (gr >= M) continue;
+#pragma unroll
+        for (int nj = 0; nj < 4; ++nj) {
+            int gc = n0 + 32 * wn + 8 * nj + 2 * t4;
+            if (gc + 1 < N) {
+                *reinterpret_cast<double2*>(&C[(int64_t)gr * ldc + gc]) = make_double2(acc[mi][nj][0], acc[mi][nj][1]);
+            } else if (gc < N) {
+                C[(int64_t)gr * ldc + gc] = acc[mi][nj][0];
+            }
+        }
+    }
+}
+
+int launch_gemm_nt(const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc, int M, int N,
+                   int K, cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        DGPB_CUDA_TRY(cudaFuncSetAttribute(gemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem));
+        configured = true;
+    }
+    DGPB_REQUIRE(K % GBK == 0 && lda % 2 == 0 && ldb % 2 == 0 && ldc % 2 == 0, "gemm: K%32, even leading dims required");
+    dim3 grid((unsigned)cdiv(N, 128), (unsigned)cdiv(M, 128));
+    gemm_nt_kernel<<<grid, 256, kGemmSmem, st>>>(A, lda, B, ldb, C, ldc, M, N, K);
+    DGPB_LAUNCHED();
+    return DGPB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// gp(): cross-kernel matrix  R[t][i] = k(x_t, W_i)   (K_vec_nb, vecchia.py:244-265), zero padded to ldr
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) kcross_kernel(KernelDev kw, KernelDev kx, double* __restrict__ R, int64_t ldr,
+                                                     int M, int n, int ncols) {
+    __shared__ double xt[kMaxDim][64];
+    __shared__ double xw[kMaxDim][64];
+    const int tid = threadIdx.x;
+    const int t0 = blockIdx.y * 64, i0 = blockIdx.x * 64;
+    const int D = kw.D;
+    for (int idx = tid; idx < D * 64; idx += 256) {
+        int d = idx >> 6, l = idx & 63;
+        xt[d][l] = t0 + l < M ? kx.x(d, t0 + l) : 0.0;
+        xw[d][l] = i0 + l < n ? kw.x(d, i0 + l) : 0.0;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int e = 0; e < 16; ++e) {
+        int idx = tid + 256 * e;
+        int lt = idx >> 6, li = idx & 63;
+        int gt = t0 + lt, gi = i0 + li;
+        if (gt >= M || gi >= ncols) continue;
+        double v = 0.0;
+        if (gi < n) v = corr_pair(kw.kind, D, [&](int d) { return xw[d][li]; }, [&](int d) { return xt[d][lt]; });
+        R[(int64_t)gt * ldr + gi] = v;
+    }
+}
+
+// m_t = R_t . a ;  v_t = | scale (1 + nugget - R_t . (R R^-1)_t) |   -- one warp per test point
+__global__ void gp_finish_kernel(const double* __restrict__ R, const double* __restrict__ TR, int64_t ldr, int M, int n,
+                                 const double* __restrict__ alpha, double scale, double nugget,
+                                 double* __restrict__ mean, double* __restrict__ var) {
+    int t = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    int lane = threadIdx.x & 31;
+    if (t >= M) return;
+    const double* r = R + (int64_t)t * ldr;
+    const double* q = TR + (int64_t)t * ldr;
+    double s1 = 0.0, s2 = 0.0;
+    for (int i = lane; i < n; i += 32) {
+        double ri = r[i];
+        s1 += ri * alpha[i];
+        s2 += ri * q[i];
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        s1 += __shfl_down_sync(0xffffffffu, s1, o);
+        s2 += __shfl_down_sync(0xffffffffu, s2, o);
+    }
+    if (lane == 0) {
+        mean[t] = s1;
+        var[t] = fabs(scale * (1.0 + nugget - s2));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// link_gp(): shared argument block
+// ------------------------------------------------------------------------------------------------
+struct LinkArgs {
+    int kind, n, Dw, Dz, M;
+    const double* w1;     // n x Dw
+    const double* gw;     // n x Dz or NULL
+    const double* Rinv;   // n x n
+    const double* alpha;  // n
+    const double* m_in;   // M x Dw
+    const double* v_in;   // M x Dw
+    const double* z;      // M x Dz or NULL
+    double len[kMaxDim];  // first Dw local, then Dz global (a shared length is replicated)
+    double scale, nugget;
+};
+
+constexpr int TT = 8;   // test points per CTA
+constexpr int PT = 32;  // pair tile edge
+
+__device__ __forceinline__ void tile_from_linear(int t, int& ti, int& tj) {
+    ti = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+    while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
+    while (ti * (ti + 1) / 2 > t) --ti;
+    tj = t - ti * (ti + 1) / 2;
+}
+
+// global-dimension factor Iz_i = k(gw_i, z_t) on the Dz connected dims (K_vec_nb); returns the factor
+__device__ __forceinline__ double global_factor(const LinkArgs& a, int gi, int gt) {
+    if (a.Dz == 0) return 1.0;
+    if (a.kind == DGPB_SEXP) {
+        double dist = 0.0;
+        for (int k = 0; k < a.Dz; ++k) {
+            double l = a.len[a.Dw + k];
+            double df = a.gw[(int64_t)gi * a.Dz + k] / l - a.z[(int64_t)gt * a.Dz + k] / l;
+            dist += df * df;
+        }
+        return exp(-dist);
+    }
+    double coef = 1.0, s = 0.0;
+    for (int k = 0; k < a.Dz; ++k) {
+        double l = a.len[a.Dw + k];
+        double r = fabs(a.gw[(int64_t)gi * a.Dz + k] / l - a.z[(int64_t)gt * a.Dz + k] / l);
+        coef *= 1.0 + kSqrt5 * r + (5.0 / 3.0) * (r * r);
+        s += r;
+    }
+    return coef * exp(-kSqrt5 * s);
+}
+
+// ------------------------------------------------------------------------------------------------
+// link_gp mean:  m_t = sum_i I_i(t) a_i          (one warp per test point, fixed summation order)
+// ------------------------------------------------------------------------------------------------
+__global__ void linkgp_mean_kernel(LinkArgs a, double* __restrict__ mean) {
+    int t = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    int lane = threadIdx.x & 31;
+    if (t >= a.M) return;
+    double Ic = 1.0;
+    if (a.kind == DGPB_SEXP) {
+        for (int k = 0; k < a.Dw; ++k) Ic *= 1.0 + 2.0 * a.v_in[(int64_t)t * a.Dw + k] / (a.len[k] * a.len[k]);
+        Ic = 1.0 / sqrt(Ic);
+    }
+    double s = 0.0;
+    for (int i = lane; i < a.n; i += 32) {
+        double Ii;
+        if (a.kind == DGPB_SEXP) {
+            double e = 0.0;
+            for (int k = 0; k < a.Dw; ++k) {
+                double xz = a.w1[(int64_t)i * a.Dw + k] - a.m_in[(int64_t)t * a.Dw + k];
+                e += xz * xz / (2.0 * a.v_in[(int64_t)t * a.Dw + k] + a.len[k] * a.len[k]);
+            }
+            Ii = Ic * exp(-e);
+        } else {
+            Ii = 1.0;
+            for (int k = 0; k < a.Dw; ++k)
+                Ii *= I_matern_dim(a.w1[(int64_t)i * a.Dw + k], a.m_in[(int64_t)t * a.Dw + k],
+                                   a.v_in[(int64_t)t * a.Dw + k], a.len[k]);
+        }
+        Ii *= global_factor(a, i, t);
+        s += Ii * a.alpha[i];
+    }
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if (lane == 0) mean[t] = s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// link_gp second moments, squared-exponential kernel.
+// part[(chunk*M + t)*2 + {0,1}] = partial (a'Ja , tr(R^-1 J)) over the pair tiles of this chunk.
+// ------------------------------------------------------------------------------------------------
+template <int DW, int NP>
+__global__ void __launch_bounds__(256) linkgp_sexp_pairs_kernel(LinkArgs a, int PC, double* __restrict__ part) {
+    __shared__ double2 sAB[TT][DW];
+    __shared__ double sJc[TT];
+    __shared__ double sI[PT][DW + 1], sJ[PT][DW + 1];
+    __shared__ double gzI[TT][PT], gzJ[TT][PT];
+    __shared__ double alI[PT], alJ[PT];
+    __shared__ double sred[8];
+    const int tid = threadIdx.x;
+    const int t0 = blockIdx.x * TT;
+    for (int idx = tid; idx < TT * DW; idx += 256) {
+        int t = idx / DW, k = idx % DW, gt = t0 + t;
+        double2 ab = make_double2(0.0, 0.0);
+        if (gt < a.M && k < a.Dw) {
+            double l = a.len[k];
+            double div = 2.0 * a.v_in[(int64_t)gt * a.Dw + k] / (l * l);
+            ab.x = 2.0 * a.m_in[(int64_t)gt * a.Dw + k] / l;
+            ab.y = 1.0 / (2.0 + 4.0 * div);
+        }
+        sAB[t][k] = ab;
+    }
+    if (tid < TT) {
+        int gt = t0 + tid;
+        double jc = 0.0;
+        if (gt < a.M) {
+            jc = 1.0;
+            for (int k = 0; k < a.Dw; ++k) jc *= 1.0 + 4.0 * a.v_in[(int64_t)gt * a.Dw + k] / (a.len[k] * a.len[k]);
+            jc = 1.0 / sqrt(jc);
+        }
+        sJc[tid] = jc;
+    }
+    double accq[TT], acct[TT];
+#pragma unroll
+    for (int t = 0; t < TT; ++t) accq[t] = acct[t] = 0.0;
+    const int nt = (a.n + PT - 1) / PT;
+    const int ntiles = nt * (nt + 1) / 2;
+    for (int tl = blockIdx.y; tl < ntiles; tl += PC) {
+        int ti, tj;
+        tile_from_linear(tl, ti, tj);
+        __syncthreads();
+        for (int idx = tid; idx < PT * DW; idx += 256) {
+            int r = idx / DW, k = idx % DW;
+            int gi = ti * PT + r, gj = tj * PT + r;
+            sI[r][k] = (gi < a.n && k < a.Dw) ? a.w1[(int64_t)gi * a.Dw + k] / a.len[k] : 0.0;
+            sJ[r][k] = (gj < a.n && k < a.Dw) ? a.w1[(int64_t)gj * a.Dw + k] / a.len[k] : 0.0;
+        }
+        if (tid < PT) {
+            int gi = ti * PT + tid, gj = tj * PT + tid;
+            alI[tid] = gi < a.n ? a.alpha[gi] : 0.0;
+            alJ[tid] = gj < a.n ? a.alpha[gj] : 0.0;
+        }
+        for (int idx = tid; idx < TT * PT; idx += 256) {
+            int t = idx / PT, r = idx % PT, gt = t0 + t;
+            int gi = ti * PT + r, gj = tj * PT + r;
+            double e1 = 0.0, e2 = 0.0;
+            if (a.Dz > 0 && gt < a.M) {
+                for (int k = 0; k < a.Dz; ++k) {
+                    double l = a.len[a.Dw + k];
+                    double zt = a.z[(int64_t)gt * a.Dz + k] / l;
+                    if (gi < a.n) {
+                        double df = a.gw[(int64_t)gi * a.Dz + k] / l - zt;
+                        e1 += df * df;
+                    }
+                    if (gj < a.n) {
+                        double df = a.gw[(int64_t)gj * a.Dz + k] / l - zt;
+                        e2 += df * df;
+                    }
+                }
+            }
+            gzI[t][r] = e1;
+            gzJ[t][r] = e2;
+        }
+        __syncthreads();
+#pragma unroll 1
+        for (int e0 = 0; e0 < 4; e0 += NP) {
+            double p[NP][DW], e2v[NP], wq[NP], wr[NP];
+            int lis[NP], ljs[NP];
+#pragma unroll
+            for (int q = 0; q < NP; ++q) {
+                int idx = tid + 256 * (e0 + q);
+                int li = idx >> 5, lj = idx & 31;
+                int gi = ti * PT + li, gj = tj * PT + lj;
+                lis[q] = li;
+                ljs[q] = lj;
+                bool valid = gi < a.n && gj <= gi;
+                double wgt = valid ? (gi == gj ? 1.0 : 2.0) : 0.0;
+                double rinv = valid ? a.Rinv[(int64_t)gi * a.n + gj] : 0.0;
+                wq[q] = wgt * alI[li] * alJ[lj];
+                wr[q] = wgt * rinv;
+                double ee = 0.0;
+#pragma unroll
+                for (int k = 0; k < DW; ++k) {
+                    double si = sI[li][k], sj = sJ[lj][k];
+                    p[q][k] = si + sj;
+                    double df = si - sj;
+                    ee += df * df;
+                }
+                e2v[q] = (gi == gj) ? 0.0 : 0.5 * ee;
+            }
+#pragma unroll
+            for (int t = 0; t < TT; ++t) {
+                double E[NP];
+#pragma unroll
+                for (int q = 0; q < NP; ++q) E[q] = e2v[q] + gzI[t][lis[q]] + gzJ[t][ljs[q]];
+#pragma unroll
+                for (int k = 0; k < DW; ++k) {
+                    double2 ab = sAB[t][k];
+#pragma unroll
+                    for (int q = 0; q < NP; ++q) {
+                        double u = p[q][k] - ab.x;
+                        E[q] += (u * u) * ab.y;
+                    }
+                }
+                double jc = sJc[t];
+#pragma unroll
+                for (int q = 0; q < NP; ++q) {
+                    double Jv = jc * exp(-E[q]);
+                    accq[t] += wq[q] * Jv;
+                    acct[t] += wr[q] * Jv;
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < TT; ++t) {
+        double s1 = block_sum<256>(accq[t], sred);
+        double s2 = block_sum<256>(acct[t], sred);
+        if (tid == 0 && t0 + t < a.M) {
+            part[((int64_t)blockIdx.y * a.M + t0 + t) * 2 + 0] = s1;
+            part[((int64_t)blockIdx.y * a.M + t0 + t) * 2 + 1] = s2;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// link_gp second moments, Matern-2.5 kernel (direct closed form per pair and dimension)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) linkgp_matern_pairs_kernel(LinkArgs a, int PC, double* __restrict__ part) {
+    __shared__ double sM[TT][kMaxDim], sV[TT][kMaxDim];
+    __shared__ double sI[PT][kMaxDim + 1], sJ[PT][kMaxDim + 1];
+    __shared__ double gzI[TT][PT], gzJ[TT][PT];
+    __shared__ double alI[PT], alJ[PT];
+    __shared__ double sred[8];
+    const int tid = threadIdx.x;
+    const int t0 = blockIdx.x * TT;
+    const int Dw = a.Dw;
+    for (int idx = tid; idx < TT * Dw; idx += 256) {
+        int t = idx / Dw, k = idx % Dw, gt = t0 + t;
+        sM[t][k] = gt < a.M ? a.m_in[(int64_t)gt * Dw + k] : 0.0;
+        sV[t][k] = gt < a.M ? a.v_in[(int64_t)gt * Dw + k] : 0.0;
+    }
+    double accq[TT], acct[TT];
+#pragma unroll
+    for (int t = 0; t < TT; ++t) accq[t] = acct[t] = 0.0;
+    const int nt = (a.n + PT - 1) / PT;
+    const int ntiles = nt * (nt + 1) / 2;
+    for (int tl = blockIdx.y; tl < ntiles; tl += PC) {
+        int ti, tj;
+        tile_from_linear(tl, ti, tj);
+        __syncthreads();
+        for (int idx = tid; idx < PT * Dw; idx += 256) {
+            int r = idx / Dw, k = idx % Dw;
+            int gi = ti * PT + r, gj = tj * PT + r;
+            sI[r][k] = gi < a.n ? a.w1[(int64_t)gi * Dw + k] : 0.0;
+            sJ[r][k] = gj < a.n ? a.w1[(int64_t)gj * Dw + k] : 0.0;
+        }
+        if (tid < PT) {
+            int gi = ti * PT + tid, gj = tj * PT + tid;
+            alI[tid] = gi < a.n ? a.alpha[gi] : 0.0;
+            alJ[tid] = gj < a.n ? a.alpha[gj] : 0.0;
+        }
+        for (int idx = tid; idx < TT * PT; idx += 256) {
+            int t = idx / PT, r = idx % PT, gt = t0 + t;
+            int gi = ti * PT + r, gj = tj * PT + r;
+            gzI[t][r] = (gt < a.M && gi < a.n) ? global_factor(a, gi, gt) : 0.0;
+            gzJ[t][r] = (gt < a.M && gj < a.n) ? global_factor(a, gj, gt) : 0.0;
+        }
+        __syncthreads();
+#pragma unroll 1
+        for (int e = 0; e < 4; ++e) {
+            int idx = tid + 256 * e;
+            int li = idx >> 5, lj = idx & 31;
+            int gi = ti * PT + li, gj = tj * PT + lj;
+            bool valid = gi < a.n && gj <= gi;
+            if (!valid) continue;
+            double wgt = (gi == gj) ? 1.0 : 2.0;
+            double wq = wgt * alI[li] * alJ[lj];
+            double wr = wgt * a.Rinv[(int64_t)gi * a.n + gj];
+#pragma unroll 1
+            for (int t = 0; t < TT; ++t) {
+                if (t0 + t >= a.M) break;
+                double Jv = 1.0;
+                for (int k = 0; k < Dw; ++k) {
+                    double zm = sM[t][k], zv = sV[t][k], l = a.len[k];
+                    double xi = sI[li][k], xj = sJ[lj][k];
+                    if (zv != 0.0) {
+                        Jv *= (gi == gj) ? Jd0_dev(xi, zm, zv, l) : Jd_dev(xj, xi, zm, zv, l);
+                    } else {
+                        Jv *= matern_plain(zm - xi, l) * matern_plain(zm - xj, l);
+                    }
+                }
+                Jv *= gzI[t][li] * gzJ[t][lj];
+                // accumulate with a static index (TT is small): select by comparison to stay in registers
+#pragma unroll
+                for (int tt = 0; tt < TT; ++tt)
+                    if (tt == t) {
+                        accq[tt] += wq * Jv;
+                        acct[tt] += wr * Jv;
+                    }
+            }
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < TT; ++t) {
+        double s1 = block_sum<256>(accq[t], sred);
+        double s2 = block_sum<256>(acct[t], sred);
+        if (tid == 0 && t0 + t < a.M) {
+            part[((int64_t)blockIdx.y * a.M + t0 + t) * 2 + 0] = s1;
+            part[((int64_t)blockIdx.y * a.M + t0 + t) * 2 + 1] = s2;
+        }
+    }
+}
+
+// v_t = | a'Ja - m_t^2 + scale (1 + nugget - tr(R^-1 J)) |     (functions.py:429)
+__global__ void linkgp_finish_kernel(const double* __restrict__ part, int PC, int M, const double* __restrict__ mean,
+                                     double scale, double nugget, double* __restrict__ var) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= M) return;
+    double q = 0.0, tr = 0.0;
+    for (int c = 0; c < PC; ++c) {
+        q += part[((int64_t)c * M + t) * 2 + 0];
+        tr += part[((int64_t)c * M + t) * 2 + 1];
+    }
+    double m = mean[t];
+    var[t] = fabs(q - m * m + scale * (1.0 + nugget - tr));
+}
+
+__global__ void aggregate_kernel(const double* __restrict__ means, const double* __restrict__ vars, int S, int64_t len,
+                                 double* __restrict__ mu, double* __restrict__ sigma2) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= len) return;
+    double sm = 0.0, s2 = 0.0;
+    for (int s = 0; s < S; ++s) {
+        double m = means[(int64_t)s * len + i];
+        sm += m;
+        s2 += m * m + vars[(int64_t)s * len + i];
+    }
+    double mbar = sm / (double)S;
+    mu[i] = mbar;
+    sigma2[i] = s2 / (double)S - mbar * mbar;
+}
+
+template <int DW, int NP>
+static int launch_sexp_pairs(const LinkArgs& a, dim3 grid, int PC, double* part, cudaStream_t st) {
+    linkgp_sexp_pairs_kernel<DW, NP><<<grid, 256, 0, st>>>(a, PC, part);
+    DGPB_LAUNCHED();
+    return DGPB_OK;
+}
+
+}  // namespace dgpb
+
+using namespace dgpb;
+
+extern "C" {
+
+int dgpb_dgemm_nt(const double* A, const double* B, double* C, int64_t M, int64_t N, int64_t K, void* stream) {
+    DGPB_REQUIRE(A && B && C && M > 0 && N > 0 && K > 0, "NULL or empty operand");
+    DGPB_REQUIRE(K % 32 == 0 && N % 2 == 0, "dgpb_dgemm_nt needs K % 32 == 0 and even N");
+    return launch_gemm_nt(A, K, B, K, C, N, (int)M, (int)N, (int)K, (cudaStream_t)stream);
+}
+
+int dgpb_gp_predict(dgpb_ws* ws, const double* x, int64_t M, const double* W, int64_t n, int64_t D, const double* Rinv,
+                    const double* Rinv_y, const double* length_host, int64_t nlen, double scale, double nugget,
+                    int kind, double* mean, double* var, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    DGPB_REQUIRE(ws && x && W && Rinv && Rinv_y && mean && var, "NULL argument");
+    if (M == 0) return DGPB_OK;
+    KernelDev kw, kx;
+    DGPB_TRY(make_kernel_dev_rowmajor(W, D, length_host, nlen, nugget, kind, &kw));
+    const int64_t Kp = round_up(n, 32);
+    const int64_t chunk = 8192;
+    void *pR, *pB, *pC;
+    DGPB_TRY(ws->reserve(SLOT_GEMM_B, sizeof(double) * (size_t)n * Kp, &pB));
+    DGPB_TRY(ws->reserve(SLOT_GEMM_A, sizeof(double) * (size_t)std::min(M, chunk) * Kp, &pR));
+    DGPB_TRY(ws->reserve(SLOT_GEMM_C, sizeof(double) * (size_t)std::min(M, chunk) * Kp, &pC));
+    // R^-1 with the contraction dimension zero padded to a multiple of 32
+    DGPB_CUDA_TRY(cudaMemsetAsync(pB, 0, sizeof(double) * (size_t)n * Kp, st));
+    DGPB_CUDA_TRY(cudaMemcpy2DAsync(pB, Kp * sizeof(double), Rinv, n * sizeof(double), n * sizeof(double), n,
+                                    cudaMemcpyDeviceToDevice, st));
+    for (int64_t m0 = 0; m0 < M; m0 += chunk) {
+        const int Mc = (int)std::min(chunk, M - m0);
+        DGPB_TRY(make_kernel_dev_rowmajor(x + m0 * D, D, length_host, nlen, nugget, kind, &kx));
+        dim3 g1((unsigned)cdiv(Kp, 64), (unsigned)cdiv(Mc, 64));
+        kcross_kernel<<<g1, 256, 0, st>>>(kw, kx, (double*)pR, Kp, Mc, (int)n, (int)Kp);
+        DGPB_LAUNCHED();
+        DGPB_TRY(launch_gemm_nt((double*)pR, Kp, (double*)pB, Kp, (double*)pC, Kp, Mc, (int)n, (int)Kp, st));
+        gp_finish_kernel<<<(unsigned)cdiv((int64_t)Mc * 32, 256), 256, 0, st>>>((double*)pR, (double*)pC, Kp, Mc, (int)n,
+                                                                               Rinv_y, scale, nugget, mean + m0,
+                                                                               var + m0);
+        DGPB_LAUNCHED();
+    }
+    return DGPB_OK;
+}
+
+int dgpb_linkgp_predict(dgpb_ws* ws, const double* m_in, const double* v_in, const double* z, int64_t M,
+                        const double* w1, const double* gw, int64_t n, int64_t Dw, int64_t Dz, const double* Rinv,
+                        const double* Rinv_y, const double* length_host, int64_t nlen, double scale, double nugget,
+                        int kind, double* mean, double* var, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    DGPB_REQUIRE(ws && m_in && v_in && w1 && Rinv && Rinv_y && mean && var && length_host, "NULL argument");
+    DGPB_REQUIRE(Dw >= 1 && Dz >= 0 && Dw + Dz <= kMaxDim, "dimension out of range");
+    DGPB_REQUIRE(Dz == 0 || (z && gw), "z/gw required when Dz > 0");
+    DGPB_REQUIRE(nlen == 1 || nlen == Dw + Dz, "len(length) must be 1 or Dw+Dz");
+    DGPB_REQUIRE(kind == DGPB_SEXP || kind == DGPB_MATERN25, "unknown kernel kind");
+    if (M == 0) return DGPB_OK;
+    LinkArgs a;
+    a.kind = kind;
+    a.n = (int)n;
+    a.Dw = (int)Dw;
+    a.Dz = (int)Dz;
+    a.w1 = w1;
+    a.gw = gw;
+    a.Rinv = Rinv;
+    a.alpha = Rinv_y;
+    for (int k = 0; k < kMaxDim; ++k) a.len[k] = 1.0;
+    for (int k = 0; k < Dw + Dz; ++k) a.len[k] = length_host[nlen == 1 ? 0 : k];
+    a.scale = scale;
+    a.nugget = nugget;
+    const int nt = (int)cdiv(n, PT);
+    const int ntiles = nt * (nt + 1) / 2;
+    // test points are processed in slabs so the partial buffer stays small
+    const int64_t slab = 65536;
+    for (int64_t m0 = 0; m0 < M; m0 += slab) {
+        const int Mc = (int)std::min(slab, M - m0);
+        a.M = Mc;
+        a.m_in = m_in + m0 * Dw;
+        a.v_in = v_in + m0 * Dw;
+        a.z = z ? z + m0 * Dz : nullptr;
+        const int ntt = (int)cdiv(Mc, TT);
+        int PC = (int)cdiv(148 * 4, ntt);
+        PC = std::max(1, std::min(PC, ntiles));
+        void* part;
+        DGPB_TRY(ws->reserve(SLOT_PART, sizeof(double) * (size_t)PC * Mc * 2, &part));
+        linkgp_mean_kernel<<<(unsigned)cdiv((int64_t)Mc * 32, 256), 256, 0, st>>>(a, mean + m0);
+        DGPB_LAUNCHED();
+        dim3 grid((unsigned)ntt, (unsigned)PC);
+        if (kind == DGPB_SEXP) {
+            int rc;
+            if (Dw <= 1) rc = launch_sexp_pairs<1, 4>(a, grid, PC, (double*)part, st);
+            else if (Dw <= 2) rc = launch_sexp_pairs<2, 4>(a, grid, PC, (double*)part, st);
+            else if (Dw <= 3) rc = launch_sexp_pairs<3, 4>(a, grid, PC, (double*)part, st);
+            else if (Dw <= 4) rc = launch_sexp_pairs<4, 4>(a, grid, PC, (double*)part, st);
+            else if (Dw <= 5) rc = launch_sexp_pairs<5, 4>(a, grid, PC, (double*)part, st);
+            else if (Dw <= 6) rc = launch_sexp_pairs<6, 4>(a, grid, PC, (double*)part, st);
+            else if (Dw <= 8) rc = launch_sexp_pairs<8, 4>(a, grid, PC, (double*)part, st);
+            else if (Dw <= 10) rc = launch_sexp_pairs<10, 2>(a, grid, PC, (double*)part, st);
+            else if (Dw <= 12) rc = launch_sexp_pairs<12, 2>(a, grid, PC, (double*)part, st);
+            else if (Dw <= 16) rc = launch_sexp_pairs<16, 2>(a, grid, PC, (double*)part, st);
+            else if (Dw <= 24) rc = launch_sexp_pairs<24, 1>(a, grid, PC, (double*)part, st);
+            else rc = launch_sexp_pairs<32, 1>(a, grid, PC, (double*)part, st);
+            DGPB_TRY(rc);
+        } else {
+            linkgp_matern_pairs_kernel<<<grid, 256, 0, st>>>(a, PC, (double*)part);
+            DGPB_LAUNCHED();
+        }
+        linkgp_finish_kernel<<<(unsigned)cdiv(Mc, 256), 256, 0, st>>>((double*)part, PC, Mc, mean + m0, scale, nugget,
+                                                                     var + m0);
+        DGPB_LAUNCHED();
+    }
+    return DGPB_OK;
+}
+
+int dgpb_aggregate(const double* means, const double* vars, int64_t S, int64_t len, double* mu, double* sigma2,
+                   void* stream) {
+    DGPB_REQUIRE(means && vars && mu && sigma2 && S >= 1, "NULL argument");
+    if (len == 0) return DGPB_OK;
+    aggregate_kernel<<<(unsigned)cdiv(len, 256), 256, 0, (cudaStream_t)stream>>>(means, vars, (int)S, len, mu, sigma2);
+    DGPB_LAUNCHED();
+    return DGPB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,802 @@
+// vecchia.cu -- nearest-neighbour (Vecchia) conditioning on sm_100a.
+//   nn / get_pred_nn      dgpsi/vecchia.py:20-109   -> exact FP64 brute-force kNN, bit-exact index output
+//   vecchia_llik/_nllik   dgpsi/vecchia.py:164-242  -> one warp per conditioning block (<= 64 points):
+//   L_matrix, fmvn_sp     dgpsi/vecchia.py:111-140,409-424     kernel block + Cholesky in shared memory
+//   gp_vecch              dgpsi/vecchia.py:635-654
+//   link_gp_vecch, IJ_nb  dgpsi/vecchia.py:758-907
+// All per-point results are written to arrays and reduced in a fixed order (deterministic sums).
+#include "common.cuh"
+#include "linkmath.cuh"
+#include "vecchia.cuh"
+
+namespace dgpb {
+
+
+// ------------------------------------------------------------------------------------------------
+// kNN.  Distances are sum_k (a_k-b_k)^2 with separate multiply and add in ascending k (what the CPU
+// libraries compute) so the index sets match bit for bit; ties keep the smaller index.
+// Each thread owns one query and scans candidate tiles staged in shared memory, keeping its current
+// m best in a sorted private list (insertions become rare after the first few hundred candidates).
+// ------------------------------------------------------------------------------------------------
+template <int DMAX, bool ORDERED>
+__global__ void __launch_bounds__(128) knn_kernel(const double* __restrict__ q, int64_t M, const double* __restrict__ x,
+                                                  int64_t n, int D, int m, int64_t* __restrict__ NN, int ldnn) {
+    constexpr int TC = 128;
+    __shared__ double xc[TC][DMAX];
+    const int tid = threadIdx.x;
+    const int64_t qi = (int64_t)blockIdx.x * 128 + tid;
+    const bool active = qi < M;
+    double qv[DMAX];
+#pragma unroll
+    for (int k = 0; k < DMAX; ++k) qv[k] = (active && k < D) ? q[qi * D + k] : 0.0;
+    double bd[kMaxBlock];
+    int bi[kMaxBlock];
+    int cnt = 0;
+    double thr = INFINITY;
+    // ORDERED: candidates are j < i only (vecchia.py:42-51,84-107)
+    const int64_t cmax = ORDERED ? min(n, (int64_t)blockIdx.x * 128 + 128) : n;
+    for (int64_t c0 = 0; c0 < cmax; c0 += TC) {
+        __syncthreads();
+        for (int idx = tid; idx < TC * DMAX; idx += 128) {
+            int r = idx / DMAX, k = idx % DMAX;
+            int64_t j = c0 + r;
+            xc[r][k] = (j < n && k < D) ? x[j * D + k] : 0.0;
+        }
+        __syncthreads();
+        if (!active) continue;
+        int64_t lim = min((int64_t)TC, (ORDERED ? qi : n) - c0);
+        for (int r = 0; r < lim; ++r) {
+            double dist = 0.0;
+#pragma unroll
+            for (int k = 0; k < DMAX; ++k) {
+                double df = __dsub_rn(qv[k], xc[r][k]);
+                dist = __dadd_rn(dist, __dmul_rn(df, df));
+            }
+            if (m > 0 && (cnt < m || dist < thr)) {
+                int pos = cnt < m ? cnt : m - 1;
+                while (pos > 0 && bd[pos - 1] > dist) {
+                    bd[pos] = bd[pos - 1];
+                    bi[pos] = bi[pos - 1];
+                    --pos;
+                }
+                bd[pos] = dist;
+                bi[pos] = (int)(c0 + r);
+                if (cnt < m) ++cnt;
+                if (cnt == m) thr = bd[m - 1];
+            }
+        }
+    }
+    if (!active) return;
+    if (ORDERED) {
+        // row = {i} U neighbours, sorted by index descending, -1 padded
+        for (int a = 1; a < cnt; ++a) {  // insertion sort of indices, descending
+            int v = bi[a], p = a;
+            while (p > 0 && bi[p - 1] < v) {
+                bi[p] = bi[p - 1];
+                --p;
+            }
+            bi[p] = v;
+        }
+        NN[qi * ldnn] = qi;
+        for (int a = 0; a < ldnn - 1; ++a) NN[qi * ldnn + 1 + a] = a < cnt ? (int64_t)bi[a] : -1;
+    } else {
+        for (int a = 0; a < m; ++a) NN[qi * ldnn + a] = (int64_t)bi[a];
+    }
+}
+
+__global__ void knn_all_kernel(int64_t M, int m, int64_t* NN) {
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= M * m) return;
+    int64_t k = idx / m, c = idx % m;
+    NN[idx] = (c + k) % m;  // (arange(m)+arange(k)[:,None]) % m   vecchia.py:23-26
+}
+
+template <bool ORDERED>
+static int launch_knn(const double* q, int64_t M, const double* x, int64_t n, int D, int m, int64_t* NN, int ldnn,
+                      cudaStream_t st) {
+    unsigned grid = (unsigned)cdiv(M, 128);
+#define KNN_CASE(DM)                                                                      \
+    if (D <= DM) {                                                                        \
+        knn_kernel<DM, ORDERED><<<grid, 128, 0, st>>>(q, M, x, n, D, m, NN, ldnn);        \
+        DGPB_LAUNCHED();                                                                  \
+        return DGPB_OK;                                                                   \
+    }
+    KNN_CASE(2) KNN_CASE(4) KNN_CASE(8) KNN_CASE(12) KNN_CASE(16) KNN_CASE(24) KNN_CASE(32)
+#undef KNN_CASE
+    set_error("kNN: dimension %d > %d", D, kMaxDim);
+    return DGPB_BAD_ARG;
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-warp conditioning-block machinery (packed lower-triangular storage: (i,j) -> i(i+1)/2 + j)
+// ------------------------------------------------------------------------------------------------
+int make_vkern(int kind, int64_t D, const double* length_host, int64_t nlen, VKern* vk) {
+    DGPB_REQUIRE(kind == DGPB_SEXP || kind == DGPB_MATERN25, "unknown kernel kind");
+    DGPB_REQUIRE(D >= 1 && D <= kMaxDim, "dimension out of range");
+    DGPB_REQUIRE(length_host && (nlen == 1 || nlen == D), "len(length) must be 1 or D");
+    vk->kind = kind;
+    vk->D = (int)D;
+    vk->ard = nlen != 1;
+    for (int d = 0; d < kMaxDim; ++d) vk->len[d] = d < D ? length_host[nlen == 1 ? 0 : d] : 1.0;
+    return DGPB_OK;
+}
+
+__device__ __forceinline__ int tri(int i, int j) { return i * (i + 1) / 2 + j; }
+
+// correlation of two points whose SCALED coordinates are rows of xl (b x D)
+__device__ __forceinline__ double corr_rows(const VKern& vk, const double* xa, const double* xb) {
+    if (vk.kind == DGPB_SEXP) {
+        double dist = 0.0;
+        for (int k = 0; k < vk.D; ++k) {
+            double df = xa[k] - xb[k];
+            dist += df * df;
+        }
+        return exp(-dist);
+    }
+    double coef = 1.0, s = 0.0;
+    for (int k = 0; k < vk.D; ++k) {
+        double r = fabs(xa[k] - xb[k]);
+        coef *= 1.0 + kSqrt5 * r + (5.0 / 3.0) * (r * r);
+        s += r;
+    }
+    return coef * exp(-kSqrt5 * s);
+}
+
+// K (packed lower) of the b gathered points; diagonal = 1 + nug[i]        (K_matrix_nb + add_to_diag_square)
+__device__ __forceinline__ void warp_build_K(const VKern& vk, const double* xl, int b, const double* nug, double* A,
+                                             int lane) {
+    const int np = b * (b + 1) / 2;
+    for (int p = lane; p < np; p += 32) {
+        int i = (int)((sqrt(8.0 * (double)p + 1.0) - 1.0) * 0.5);
+        while ((i + 1) * (i + 2) / 2 <= p) ++i;
+        while (i * (i + 1) / 2 > p) --i;
+        int j = p - i * (i + 1) / 2;
+        A[p] = (i == j) ? 1.0 + nug[i] : corr_rows(vk, xl + i * vk.D, xl + j * vk.D);
+    }
+    __syncwarp();
+}
+
+// in-place Cholesky (column Crout form); every lane recomputes the pivot, lanes split the rows
+__device__ __forceinline__ void warp_chol(double* A, int b, int lane) {
+    for (int j = 0; j < b; ++j) {
+        double d = A[tri(j, j)];
+        for (int p = 0; p < j; ++p) {
+            double l = A[tri(j, p)];
+            d -= l * l;
+        }
+        double sq = sqrt(d);
+        double inv = 1.0 / sq;
+        for (int i = j + 1 + lane; i < b; i += 32) {
+            double s = A[tri(i, j)];
+            for (int p = 0; p < j; ++p) s -= A[tri(i, p)] * A[tri(j, p)];
+            A[tri(i, j)] = s * inv;
+        }
+        __syncwarp();
+        if (lane == 0) A[tri(j, j)] = sq;
+        __syncwarp();
+    }
+}
+
+// w = L^-1 v in place (column-oriented), lanes over rows
+__device__ __forceinline__ void warp_fwd(const double* L, double* v, int b, int lane) {
+    for (int j = 0; j < b; ++j) {
+        double wj = v[j] / L[tri(j, j)];
+        __syncwarp();
+        if (lane == 0) v[j] = wj;
+        for (int i = j + 1 + lane; i < b; i += 32) v[i] -= L[tri(i, j)] * wj;
+        __syncwarp();
+    }
+}
+
+// v = L^-T v in place
+__device__ __forceinline__ void warp_bwd(const double* L, double* v, int b, int lane) {
+    for (int j = b - 1; j >= 0; --j) {
+        double wj = v[j] / L[tri(j, j)];
+        __syncwarp();
+        if (lane == 0) v[j] = wj;
+        for (int i = lane; i < j; i += 32) v[i] -= L[tri(j, i)] * wj;
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// training-side kernel: likelihood terms, gradients, inverse-Cholesky rows
+//   mode 0: vecchia_llik  -> vals[i*2 + {0,1}]   = (w_last^2, 2 log L_last)
+//   mode 1: vecchia_nllik -> vals[i*(2P+2) + ..] = (w_last^2, 2 log L_last, dquad[P], dlogdet[P])
+//   mode 2: L_matrix      -> Lout[i*m1 + c]
+// ------------------------------------------------------------------------------------------------
+__global__ void vecchia_train_kernel(VKern vk, const double* __restrict__ X, const double* __restrict__ y,
+                                     const int64_t* __restrict__ NN, int64_t n, int m1, double nugget,
+                                     const double* __restrict__ nugget_diag, int mode, int P, int nugget_est,
+                                     double* __restrict__ vals, double* __restrict__ Lout, int per_warp) {
+    extern __shared__ double smem[];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, W = blockDim.x >> 5;
+    const int64_t i = (int64_t)blockIdx.x * W + w;
+    if (i >= n) return;
+    double* base = smem + (size_t)w * per_warp;
+    double* A = base;                                  // packed K -> L       m1(m1+1)/2
+    double* xl = A + m1 * (m1 + 1) / 2;                // scaled coords       m1 * D
+    double* yv = xl + m1 * vk.D;                       // y -> w              m1
+    double* nug = yv + m1;                             // nugget_i            m1
+    double* bv = nug + m1;                             // L^-T e_last         m1
+    double* vp = bv + m1;                              // P x m1 (mode 1)
+    int* idx = reinterpret_cast<int*>(vp + (mode == 1 ? P * m1 : 0));
+    // idx = NN[i][valid][::-1]  (ascending, the point itself last)
+    int b = 0;
+    for (int c = 0; c < m1; ++c) b += NN[i * m1 + c] >= 0;
+    for (int c = lane; c < b; c += 32) idx[c] = (int)NN[i * m1 + (b - 1 - c)];
+    __syncwarp();
+    for (int p = lane; p < b * vk.D; p += 32) {
+        int r = p / vk.D, k = p % vk.D;
+        xl[p] = X[(int64_t)idx[r] * vk.D + k] / vk.len[k];
+    }
+    for (int c = lane; c < b; c += 32) {
+        yv[c] = y ? y[idx[c]] : 0.0;
+        nug[c] = nugget * (nugget_diag ? nugget_diag[idx[c]] : 1.0);
+        bv[c] = (c == b - 1) ? 1.0 : 0.0;
+    }
+    __syncwarp();
+    warp_build_K(vk, xl, b, nug, A, lane);
+    warp_chol(A, b, lane);
+    if (mode == 2) {
+        warp_bwd(A, bv, b, lane);
+        for (int c = lane; c < m1; c += 32) Lout[i * m1 + c] = c < b ? bv[b - 1 - c] : 0.0;
+        return;
+    }
+    warp_fwd(A, yv, b, lane);
+    const double wl = yv[b - 1], Lll = A[tri(b - 1, b - 1)];
+    const int stride = mode == 1 ? 2 * P + 2 : 2;
+    if (lane == 0) {
+        vals[i * stride + 0] = wl * wl;
+        vals[i * stride + 1] = 2.0 * log(fabs(Lll));
+    }
+    if (mode != 1) return;
+    warp_bwd(A, bv, b, lane);
+    // vp[p][r] = (dK_p b)_r with the kernel derivatives recomputed from the scaled coordinates
+    const int nl = vk.ard ? vk.D : 1;
+    for (int r = lane; r < b; r += 32) {
+        for (int p = 0; p < nl; ++p) vp[p * m1 + r] = 0.0;
+        for (int c = 0; c < b; ++c) {
+            if (c == r) continue;
+            const double* xa = xl + r * vk.D;
+            const double* xb = xl + c * vk.D;
+            double Kv = corr_rows(vk, xa, xb) * bv[c];
+            double csum = 0.0;
+            for (int k = 0; k < vk.D; ++k) {
+                double df = xa[k] - xb[k];
+                double ck;
+                if (vk.kind == DGPB_SEXP) {
+                    ck = 2.0 * (df * df);
+                } else {
+                    double rr = fabs(df);
+                    double el1 = 1.0 + kSqrt5 * rr, el2 = (5.0 / 3.0) * (rr * rr);
+                    ck = el2 * el1 / (el1 + el2);
+                }
+                if (vk.ard) vp[k * m1 + r] += ck * Kv; else csum += ck;
+            }
+            if (!vk.ard) vp[r] += csum * Kv;
+        }
+        if (nugget_est) vp[nl * m1 + r] = nug[r] * bv[r];
+    }
+    __syncwarp();
+    for (int p = 0; p < P; ++p) {
+        double* v = vp + p * m1;
+        warp_fwd(A, v, b, lane);
+        double s = 0.0;
+        for (int c = lane; c < b; c += 32) s += yv[c] * v[c];
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) {
+            double last = v[b - 1];
+            vals[i * stride + 2 + p] = 2.0 * s * wl - last * wl * wl;
+            vals[i * stride + 2 + P + p] = last;
+        }
+    }
+}
+
+// column sums of vals (rows x cols) in a fixed order: one CTA per column
+__global__ void __launch_bounds__(1024) colsum_kernel(const double* __restrict__ vals, int64_t rows, int cols,
+                                                      double* __restrict__ out) {
+    __shared__ double sred[32];
+    const int c = blockIdx.x, tid = threadIdx.x;
+    double s = 0.0;
+    for (int64_t r = tid; r < rows; r += 1024) s += vals[r * cols + c];
+    s = block_sum<1024>(s, sred);
+    if (tid == 0) out[c] = s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// sparse forward solve  x_i = (z_i - sum_{j>=1} L[i,j] x[NN[i,j]]) / L[i,0]     (forward_solve_sp)
+// Dependency-driven: one warp per row, rows claimed in increasing order through a ticket so every
+// dependency (always a smaller row index) is owned by a warp that is already running or finished.
+// ------------------------------------------------------------------------------------------------
+__global__ void sp_solve_kernel(const double* __restrict__ L, const int64_t* __restrict__ NN, int64_t n, int m1,
+                                double inv_sqrt_scale, const double* __restrict__ z, double* x, int* ready,
+                                unsigned int* ticket) {
+    __shared__ unsigned int s_blk;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, W = blockDim.x >> 5;
+    if (threadIdx.x == 0) s_blk = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const int64_t i = (int64_t)s_blk * W + w;
+    if (i >= n) return;
+    const int kmax = (int)min((int64_t)m1, i + 1);
+    double s = 0.0;
+    for (int j = 1 + lane; j < kmax; j += 32) {
+        int64_t dep = NN[i * m1 + j];
+        // bounded spin: a dependency that never arrives (corrupt NNarray) poisons the result instead of
+        // hanging the device
+        long long spins = 0;
+        while (atomicAdd(&ready[dep], 0) == 0 && ++spins < (1LL << 28)) {
+        }
+        __threadfence();
+        double xd = spins < (1LL << 28) ? ((volatile double*)x)[dep] : NAN;
+        s += (L[i * m1 + j] * inv_sqrt_scale) * xd;
+    }
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) {
+        x[i] = (z[i] - s) / (L[i * m1] * inv_sqrt_scale);
+        __threadfence();
+        atomicExch(&ready[i], 1);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// prediction: gp_vecch (mode 0) and link_gp_vecch (mode 1), one warp per test point
+// ------------------------------------------------------------------------------------------------
+struct VPredArgs {
+    int mode;
+    int64_t M, n;
+    int Dw, Dz, mp;
+    const double* xq;    // mode 0: M x D test inputs;  mode 1: M x Dw means
+    const double* vq;    // mode 1: M x Dw variances
+    const double* zq;    // mode 1: M x Dz deterministic global inputs or NULL
+    const double* w1;    // mode 0: n x D ; mode 1: n x Dw
+    const double* gw;    // mode 1: n x Dz or NULL
+    const double* y;     // n
+    const int64_t* NN;   // M x mp
+    const double* nugget_diag;
+    double scale, nugget;
+    double* mean;
+    double* var;
+};
+
+__global__ void vecchia_pred_kernel(VKern vk, VPredArgs a, int per_warp) {
+    extern __shared__ double smem[];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, W = blockDim.x >> 5;
+    const int64_t t = (int64_t)blockIdx.x * W + w;
+    if (t >= a.M) return;
+    const int D = vk.D, mp = a.mp;
+    const int bmax = mp + 1;
+    double* base = smem + (size_t)w * per_warp;
+    double* A = base;                           // packed K -> L -> (mode 1) L^-1
+    double* xl = A + bmax * (bmax + 1) / 2;     // scaled coords (bmax x D)
+    double* yv = xl + bmax * D;                 // bmax
+    double* nug = yv + bmax;                    // bmax
+    double* Jm = nug + bmax;                    // mode 1: packed J
+    double* Kinv = Jm + (a.mode ? bmax * (bmax + 1) / 2 : 0);   // mode 1: packed K^-1
+    double* Iv = Kinv + (a.mode ? bmax * (bmax + 1) / 2 : 0);   // mode 1: I, then alpha
+    double* al = Iv + (a.mode ? bmax : 0);
+    int* idx = reinterpret_cast<int*>(al + (a.mode ? bmax : 0));
+    int nb = 0;
+    for (int c = 0; c < mp; ++c) nb += a.NN[t * mp + c] >= 0;
+    for (int c = lane; c < nb; c += 32) idx[c] = (int)a.NN[t * mp + c];
+    __syncwarp();
+    if (a.mode == 0) {
+        const int b = nb + 1;
+        for (int p = lane; p < b * D; p += 32) {
+            int r = p / D, k = p % D;
+            double v = r < nb ? a.w1[(int64_t)idx[r] * D + k] : a.xq[t * D + k];
+            xl[p] = v / vk.len[k];
+        }
+        for (int c = lane; c < b; c += 32) {
+            yv[c] = c < nb ? a.y[idx[c]] : 0.0;
+            nug[c] = c < nb ? a.nugget * (a.nugget_diag ? a.nugget_diag[idx[c]] : 1.0) : a.nugget;
+        }
+        __syncwarp();
+        warp_build_K(vk, xl, b, nug, A, lane);
+        warp_chol(A, b, lane);
+        warp_fwd(A, yv, nb, lane);   // only the leading nb x nb block is needed for L11^-1 y
+        double s = 0.0;
+        for (int c = lane; c < nb; c += 32) s += A[tri(nb, c)] * yv[c];
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) {
+            double Lll = A[tri(nb, nb)];
+            a.mean[t] = s;
+            a.var[t] = a.scale * Lll * Lll;
+        }
+        return;
+    }
+    // ---- linked prediction on the neighbour set (no test point in the block) ----
+    const int b = nb, Dw = a.Dw, Dz = a.Dz;
+    for (int p = lane; p < b * D; p += 32) {
+        int r = p / D, k = p % D;
+        double v = k < Dw ? a.w1[(int64_t)idx[r] * Dw + k] : a.gw[(int64_t)idx[r] * Dz + (k - Dw)];
+        xl[p] = v / vk.len[k];
+    }
+    for (int c = lane; c < b; c += 32) {
+        yv[c] = a.y[idx[c]];
+        nug[c] = a.nugget * (a.nugget_diag ? a.nugget_diag[idx[c]] : 1.0);
+    }
+    __syncwarp();
+    warp_build_K(vk, xl, b, nug, A, lane);
+    warp_chol(A, b, lane);
+    // Iz factors from the connected global dims (K_vec_nb on the scaled coords)
+    const double* zm = a.xq + t * Dw;
+    const double* zv = a.vq + t * Dw;
+    for (int c = lane; c < b; c += 32) {
+        double f = 1.0;
+        if (Dz > 0) {
+            if (vk.kind == DGPB_SEXP) {
+                double dist = 0.0;
+                for (int k = 0; k < Dz; ++k) {
+                    double df = xl[c * D + Dw + k] - a.zq[t * Dz + k] / vk.len[Dw + k];
+                    dist += df * df;
+                }
+                f = exp(-dist);
+            } else {
+                double coef = 1.0, s = 0.0;
+                for (int k = 0; k < Dz; ++k) {
+                    double r = fabs(xl[c * D + Dw + k] - a.zq[t * Dz + k] / vk.len[Dw + k]);
+                    coef *= 1.0 + kSqrt5 * r + (5.0 / 3.0) * (r * r);
+                    s += r;
+                }
+                f = coef * exp(-kSqrt5 * s);
+            }
+        }
+        al[c] = f;  // temporarily holds Iz
+    }
+    __syncwarp();
+    // I vector and J matrix (IJ_nb, vecchia.py:838-907)
+    double Ic = 1.0, Jc = 1.0;
+    if (vk.kind == DGPB_SEXP) {
+        for (int k = 0; k < Dw; ++k) {
+            double l2 = vk.len[k] * vk.len[k];
+            Ic *= 1.0 + 2.0 * zv[k] / l2;
+            Jc *= 1.0 + 4.0 * zv[k] / l2;
+        }
+        Ic = 1.0 / sqrt(Ic);
+        Jc = 1.0 / sqrt(Jc);
+    }
+    for (int c = lane; c < b; c += 32) {
+        double v;
+        if (vk.kind == DGPB_SEXP) {
+            double e = 0.0;
+            for (int k = 0; k < Dw; ++k) {
+                double xz = a.w1[(int64_t)idx[c] * Dw + k] - zm[k];
+                e += xz * xz / (2.0 * zv[k] + vk.len[k] * vk.len[k]);
+            }
+            v = Ic * exp(-e);
+        } else {
+            v = 1.0;
+            for (int k = 0; k < Dw; ++k) v *= I_matern_dim(a.w1[(int64_t)idx[c] * Dw + k], zm[k], zv[k], vk.len[k]);
+        }
+        Iv[c] = v * al[c];
+    }
+    const int np = b * (b + 1) / 2;
+    for (int p = lane; p < np; p += 32) {
+        int i = (int)((sqrt(8.0 * (double)p + 1.0) - 1.0) * 0.5);
+        while ((i + 1) * (i + 2) / 2 <= p) ++i;
+        while (i * (i + 1) / 2 > p) --i;
+        int j = p - i * (i + 1) / 2;
+        const double* xi = a.w1 + (int64_t)idx[i] * Dw;
+        const double* xj = a.w1 + (int64_t)idx[j] * Dw;
+        double v;
+        if (vk.kind == DGPB_SEXP) {
+            double e = 0.0;
+            for (int k = 0; k < Dw; ++k) {
+                double l2 = vk.len[k] * vk.len[k];
+                double xzi = xi[k] - zm[k], xzj = xj[k] - zm[k];
+                if (i == j) {
+                    e += 2.0 * xzi * xzi / (4.0 * zv[k] + l2);
+                } else {
+                    double sp = xzi + xzj, sd = xzi - xzj;
+                    e += sp * sp / (8.0 * zv[k] + 2.0 * l2) + sd * sd / (2.0 * l2);
+                }
+            }
+            v = Jc * exp(-e);
+        } else {
+            v = 1.0;
+            for (int k = 0; k < Dw; ++k) {
+                if (zv[k] != 0.0) {
+                    v *= (i == j) ? Jd0_dev(xi[k], zm[k], zv[k], vk.len[k]) : Jd_dev(xj[k], xi[k], zm[k], zv[k], vk.len[k]);
+                } else {
+                    v *= matern_plain(zm[k] - xi[k], vk.len[k]) * matern_plain(zm[k] - xj[k], vk.len[k]);
+                }
+            }
+        }
+        Jm[p] = v * al[i] * al[j];
+    }
+    __syncwarp();
+    // L^-1 in place: lane c owns column c (forward substitution on e_c)
+    for (int c = lane; c < b; c += 32) {
+        double dcc = 1.0 / A[tri(c, c)];
+        // compute column into Kinv scratch column-wise (use Kinv as temporary full storage of L^-1 packed)
+        Kinv[tri(c, c)] = dcc;
+        for (int i = c + 1; i < b; ++i) {
+            double s = 0.0;
+            for (int k = c; k < i; ++k) s += A[tri(i, k)] * Kinv[tri(k, c)];
+            Kinv[tri(i, c)] = -s / A[tri(i, i)];
+        }
+    }
+    __syncwarp();
+    for (int p = lane; p < np; p += 32) A[p] = Kinv[p];   // A <- L^-1
+    __syncwarp();
+    // K^-1 = L^-T L^-1 (packed lower):  Kinv_ij = sum_{p >= i} Linv[p][i] Linv[p][j],  i >= j
+    for (int p = lane; p < np; p += 32) {
+        int i = (int)((sqrt(8.0 * (double)p + 1.0) - 1.0) * 0.5);
+        while ((i + 1) * (i + 2) / 2 <= p) ++i;
+        while (i * (i + 1) / 2 > p) --i;
+        int j = p - i * (i + 1) / 2;
+        double s = 0.0;
+        for (int r = i; r < b; ++r) s += A[tri(r, i)] * A[tri(r, j)];
+        Kinv[p] = s;
+    }
+    __syncwarp();
+    // alpha = K^-1 y
+    for (int c = lane; c < b; c += 32) {
+        double s = 0.0;
+        for (int k = 0; k < b; ++k) s += Kinv[k <= c ? tri(c, k) : tri(k, c)] * yv[k];
+        al[c] = s;
+    }
+    __syncwarp();
+    double tr = 0.0, qd = 0.0, mt = 0.0;
+    for (int p = lane; p < np; p += 32) {
+        int i = (int)((sqrt(8.0 * (double)p + 1.0) - 1.0) * 0.5);
+        while ((i + 1) * (i + 2) / 2 <= p) ++i;
+        while (i * (i + 1) / 2 > p) --i;
+        int j = p - i * (i + 1) / 2;
+        double wgt = (i == j) ? 1.0 : 2.0;
+        tr += wgt * Kinv[p] * Jm[p];
+        qd += wgt * Jm[p] * al[i] * al[j];
+    }
+    for (int c = lane; c < b; c += 32) mt += Iv[c] * al[c];
+    for (int o = 16; o > 0; o >>= 1) {
+        tr += __shfl_xor_sync(0xffffffffu, tr, o);
+        qd += __shfl_xor_sync(0xffffffffu, qd, o);
+        mt += __shfl_xor_sync(0xffffffffu, mt, o);
+    }
+    if (lane == 0) {
+        a.mean[t] = mt;
+        a.var[t] = fabs(qd - mt * mt + a.scale * (1.0 + a.nugget - tr));
+    }
+}
+
+static int train_launch(const VKern& vk, const double* X, const double* y, const int64_t* NN, int64_t n, int64_t m1,
+                        double nugget, const double* nugget_diag, int mode, int P, int nugget_est, double* vals,
+                        double* Lout, cudaStream_t st) {
+    DGPB_REQUIRE(m1 >= 1 && m1 <= kMaxBlock, "conditioning block larger than 64");
+    const int per_warp = (int)(m1 * (m1 + 1) / 2 + m1 * vk.D + 3 * m1 + (mode == 1 ? P * m1 : 0) + (m1 + 1) / 2 + 2);
+    int W = 8;
+    while (W > 1 && (size_t)W * per_warp * sizeof(double) > 200 * 1024) W >>= 1;
+    size_t smem = (size_t)W * per_warp * sizeof(double);
+    static size_t configured = 0;
+    if (smem > configured) {
+        DGPB_CUDA_TRY(cudaFuncSetAttribute(vecchia_train_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        configured = 220 * 1024;
+    }
+    vecchia_train_kernel<<<(unsigned)cdiv(n, W), W * 32, smem, st>>>(vk, X, y, NN, n, (int)m1, nugget, nugget_diag, mode,
+                                                                    P, nugget_est, vals, Lout, per_warp);
+    DGPB_LAUNCHED();
+    return DGPB_OK;
+}
+
+static int pred_launch(const VKern& vk, const VPredArgs& a, cudaStream_t st) {
+    const int bmax = a.mp + 1;
+    DGPB_REQUIRE(bmax <= kMaxBlock, "prediction conditioning set larger than 63");
+    const int tri_sz = bmax * (bmax + 1) / 2;
+    const int per_warp = tri_sz + bmax * vk.D + 2 * bmax + (a.mode ? 2 * tri_sz + 2 * bmax : 0) + (bmax + 1) / 2 + 2;
+    int W = 8;
+    while (W > 1 && (size_t)W * per_warp * sizeof(double) > 200 * 1024) W >>= 1;
+    size_t smem = (size_t)W * per_warp * sizeof(double);
+    static bool configured = false;
+    if (!configured) {
+        DGPB_CUDA_TRY(cudaFuncSetAttribute(vecchia_pred_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        configured = true;
+    }
+    vecchia_pred_kernel<<<(unsigned)cdiv(a.M, W), W * 32, smem, st>>>(vk, a, per_warp);
+    DGPB_LAUNCHED();
+    return DGPB_OK;
+}
+
+// shared by the C entry points and ess.cu
+int vecchia_llik_device(Workspace* ws, const VKern& vk, const double* X, const double* y, const int64_t* NN, int64_t n,
+                        int64_t m1, double nugget, const double* nugget_diag, double* out2_dev, cudaStream_t st) {
+    void* vals;
+    DGPB_TRY(ws->reserve(SLOT_MISC, sizeof(double) * (size_t)n * 2, &vals));
+    DGPB_TRY(train_launch(vk, X, y, NN, n, m1, nugget, nugget_diag, 0, 0, 0, (double*)vals, nullptr, st));
+    colsum_kernel<<<2, 1024, 0, st>>>((double*)vals, n, 2, out2_dev);
+    DGPB_LAUNCHED();
+    return DGPB_OK;
+}
+
+int vecchia_mvn_draw_device(Workspace* ws, const VKern& vk, const double* X, const int64_t* NN, int64_t n, int64_t m1,
+                            double scale, double nugget, const double* z, double* out, cudaStream_t st) {
+    void *Lm, *flags;
+    DGPB_TRY(ws->reserve(SLOT_VL, sizeof(double) * (size_t)n * m1, &Lm));
+    DGPB_TRY(ws->reserve(SLOT_VFLAG, sizeof(int) * ((size_t)n + 8), &flags));
+    DGPB_TRY(train_launch(vk, X, nullptr, NN, n, m1, nugget, nullptr, 2, 0, 0, nullptr, (double*)Lm, st));
+    DGPB_CUDA_TRY(cudaMemsetAsync(flags, 0, sizeof(int) * ((size_t)n + 8), st));
+    int* ready = (int*)flags + 8;
+    unsigned int* ticket = (unsigned int*)flags;
+    const int W = 8;
+    sp_solve_kernel<<<(unsigned)cdiv(n, W), W * 32, 0, st>>>((double*)Lm, NN, n, (int)m1, 1.0 / sqrt(scale), z, out, ready,
+                                                            ticket);
+    DGPB_LAUNCHED();
+    return DGPB_OK;
+}
+
+}  // namespace dgpb
+
+using namespace dgpb;
+
+// a private workspace for the entry points that do not take one (scratch for per-point values)
+static thread_local dgpb_ws* tls_ws = nullptr;
+static int get_tls_ws(dgpb_ws** out) {
+    if (!tls_ws) {
+        int dev = 0;
+        DGPB_CUDA_TRY(cudaGetDevice(&dev));
+        DGPB_TRY(dgpb_ws_create(&tls_ws, dev));
+    }
+    *out = tls_ws;
+    return DGPB_OK;
+}
+
+extern "C" {
+
+int dgpb_knn_ordered(const double* x, int64_t n, int64_t D, int64_t m, int64_t* NN, void* stream) {
+    DGPB_REQUIRE(x && NN && n >= 1 && D >= 1 && D <= kMaxDim, "bad argument");
+    m = std::min(m, n - 1);
+    DGPB_REQUIRE(m >= 0 && m < kMaxBlock, "m out of range");
+    if (m == 0) {
+        // single point: NN = [[0]]
+        return launch_knn<true>(x, n, x, n, (int)D, 0, NN, 1, (cudaStream_t)stream);
+    }
+    return launch_knn<true>(x, n, x, n, (int)D, (int)m, NN, (int)m + 1, (cudaStream_t)stream);
+}
+
+int dgpb_knn(const double* query, int64_t M, const double* x, int64_t n, int64_t D, int64_t m, int64_t* NN,
+             void* stream) {
+    DGPB_REQUIRE(query && x && NN && n >= 1 && D >= 1 && D <= kMaxDim, "bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    m = std::min(m, n);
+    if (M == 0) return DGPB_OK;
+    if (m == n) {
+        knn_all_kernel<<<(unsigned)cdiv(M * m, 256), 256, 0, st>>>(M, (int)m, NN);
+        DGPB_LAUNCHED();
+        return DGPB_OK;
+    }
+    DGPB_REQUIRE(m >= 1 && m <= kMaxBlock, "m out of range (max 64)");
+    return launch_knn<false>(query, M, x, n, (int)D, (int)m, NN, (int)m, st);
+}
+
+int dgpb_vecchia_llik(const double* X, const double* y, const int64_t* NN, int64_t n, int64_t D, int64_t m1,
+                      const double* length_host, int64_t nlen, double scale, double nugget, const double* nugget_diag,
+                      int kind, double* out_host, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    DGPB_REQUIRE(X && y && NN && out_host, "NULL argument");
+    VKern vk;
+    DGPB_TRY(make_vkern(kind, D, length_host, nlen, &vk));
+    dgpb_ws* ws;
+    DGPB_TRY(get_tls_ws(&ws));
+    void* out;
+    DGPB_TRY(ws->reserve(SLOT_OUT, sizeof(double) * kOutDoubles, &out));
+    DGPB_TRY(vecchia_llik_device(ws, vk, X, y, NN, n, m1, nugget, nugget_diag, (double*)out, st));
+    DGPB_CUDA_TRY(cudaMemcpyAsync(ws->pinned, out, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    DGPB_CUDA_TRY(cudaStreamSynchronize(st));
+    const double quad = ws->pinned[0], logdet = ws->pinned[1];
+    if (!(quad == quad) || !(logdet == logdet)) {
+        set_error("Vecchia block is not positive definite");
+        return DGPB_NOT_PD;
+    }
+    out_host[0] = -0.5 * (logdet + quad / scale);  // vecchia.py:179
+    return DGPB_OK;
+}
+
+int dgpb_vecchia_nllik(const double* X, const double* y, const int64_t* NN, int64_t n, int64_t D, int64_t m1,
+                       const double* length_host, int64_t nlen, double scale, double nugget, const double* nugget_diag,
+                       int kind, int scale_est, int nugget_est, double* out_host, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    DGPB_REQUIRE(X && y && NN && out_host, "NULL argument");
+    VKern vk;
+    DGPB_TRY(make_vkern(kind, D, length_host, nlen, &vk));
+    const int P = (int)nlen + (nugget_est ? 1 : 0);
+    const int cols = 2 * P + 2;
+    dgpb_ws* ws;
+    DGPB_TRY(get_tls_ws(&ws));
+    void *vals, *out;
+    DGPB_TRY(ws->reserve(SLOT_MISC, sizeof(double) * (size_t)n * cols, &vals));
+    DGPB_TRY(ws->reserve(SLOT_OUT, sizeof(double) * kOutDoubles, &out));
+    DGPB_TRY(train_launch(vk, X, y, NN, n, m1, nugget, nugget_diag, 1, P, nugget_est, (double*)vals, nullptr, st));
+    colsum_kernel<<<cols, 1024, 0, st>>>((double*)vals, n, cols, (double*)out);
+    DGPB_LAUNCHED();
+    DGPB_CUDA_TRY(cudaMemcpyAsync(ws->pinned, out, cols * sizeof(double), cudaMemcpyDeviceToHost, st));
+    DGPB_CUDA_TRY(cudaStreamSynchronize(st));
+    const double quad = ws->pinned[0], logdet = ws->pinned[1];
+    if (!(quad == quad) || !(logdet == logdet)) {
+        set_error("Vecchia block is not positive definite");
+        return DGPB_NOT_PD;
+    }
+    // vecchia.py:224-238 (origin_n == n)
+    double s2 = scale_est ? quad / (double)n : scale;
+    out_host[0] = scale_est ? 0.5 * (logdet + (double)n * log(s2)) : 0.5 * (logdet + quad / s2);
+    out_host[1] = s2;
+    for (int p = 0; p < P; ++p) out_host[2 + p] = 0.5 * (ws->pinned[2 + P + p] - ws->pinned[2 + p] / s2);
+    return DGPB_OK;
+}
+
+int dgpb_vecchia_Lmatrix(const double* X, const int64_t* NN, int64_t n, int64_t D, int64_t m1, const double* length_host,
+                         int64_t nlen, double nugget, int kind, double* L, void* stream) {
+    DGPB_REQUIRE(X && NN && L, "NULL argument");
+    VKern vk;
+    DGPB_TRY(make_vkern(kind, D, length_host, nlen, &vk));
+    return train_launch(vk, X, nullptr, NN, n, m1, nugget, nullptr, 2, 0, 0, nullptr, L, (cudaStream_t)stream);
+}
+
+int dgpb_vecchia_mvn_draw(const double* X, const int64_t* NN, int64_t n, int64_t D, int64_t m1,
+                          const double* length_host, int64_t nlen, double scale, double nugget, int kind,
+                          const double* z, double* out, void* stream) {
+    DGPB_REQUIRE(X && NN && z && out, "NULL argument");
+    VKern vk;
+    DGPB_TRY(make_vkern(kind, D, length_host, nlen, &vk));
+    dgpb_ws* ws;
+    DGPB_TRY(get_tls_ws(&ws));
+    return vecchia_mvn_draw_device(ws, vk, X, NN, n, m1, scale, nugget, z, out, (cudaStream_t)stream);
+}
+
+int dgpb_gp_vecch(const double* x, int64_t M, const double* w, const double* y, int64_t n, int64_t D, const int64_t* NN,
+                  int64_t mp, const double* length_host, int64_t nlen, double scale, double nugget,
+                  const double* nugget_diag, int kind, double* mean, double* var, void* stream) {
+    DGPB_REQUIRE(x && w && y && NN && mean && var, "NULL argument");
+    if (M == 0) return DGPB_OK;
+    VKern vk;
+    DGPB_TRY(make_vkern(kind, D, length_host, nlen, &vk));
+    VPredArgs a{};
+    a.mode = 0;
+    a.M = M;
+    a.n = n;
+    a.Dw = (int)D;
+    a.Dz = 0;
+    a.mp = (int)mp;
+    a.xq = x;
+    a.w1 = w;
+    a.y = y;
+    a.NN = NN;
+    a.nugget_diag = nugget_diag;
+    a.scale = scale;
+    a.nugget = nugget;
+    a.mean = mean;
+    a.var = var;
+    return pred_launch(vk, a, (cudaStream_t)stream);
+}
+
+int dgpb_linkgp_vecch(const double* m_in, const double* v_in, const double* z, int64_t M, const double* w1,
+                      const double* gw, const double* y, int64_t n, int64_t Dw, int64_t Dz, const int64_t* NN,
+                      int64_t mp, const double* length_host, int64_t nlen, double scale, double nugget,
+                      const double* nugget_diag, int kind, double* mean, double* var, void* stream) {
+    DGPB_REQUIRE(m_in && v_in && w1 && y && NN && mean && var, "NULL argument");
+    DGPB_REQUIRE(Dz == 0 || (z && gw), "z/gw required when Dz > 0");
+    if (M == 0) return DGPB_OK;
+    VKern vk;
+    DGPB_TRY(make_vkern(kind, Dw + Dz, length_host, nlen, &vk));
+    VPredArgs a{};
+    a.mode = 1;
+    a.M = M;
+    a.n = n;
+    a.Dw = (int)Dw;
+    a.Dz = (int)Dz;
+    a.mp = (int)mp;
+    a.xq = m_in;
+    a.vq = v_in;
+    a.zq = z;
+    a.w1 = w1;
+    a.gw = gw;
+    a.y = y;
+    a.NN = NN;
+    a.nugget_diag = nugget_diag;
+    a.scale = scale;
+    a.nugget = nugget;
+    a.mean = mean;
+    a.var = var;
+    return pred_launch(vk, a, (cudaStream_t)stream);
+}
+
+}  // extern "C"

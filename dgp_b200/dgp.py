@@ -1,0 +1,251 @@
+"""`dgp` -- deep Gaussian process trained by stochastic-imputation EM, API as dgpsi/dgp.py:26-129,1364-1541.
+
+Python keeps the object graph, the SEM loop, the L-BFGS-B driver and the parameter traces; the I-step
+(ESS sweeps) and every likelihood / gradient evaluation of the M-step run in libdgpb.so.  Scope follows
+SURVEY.md section 2 row 5: `__init__`, the generic branch of `initialize` (dgp.py:565-691), `train`,
+`estimate`, Vecchia switches and the restart logic.  Likelihood layers, replicated inputs, `update_xy*`,
+`ptrain` and plotting are not part of the SI hot path and raise NotImplementedError.
+"""
+from __future__ import annotations
+
+import copy
+
+import numpy as np
+
+from .imputation import imputer
+from .kernel_class import combine
+from .kernel_class import kernel as ker
+from .utils import NystromKPCA
+
+try:  # tqdm is optional plumbing for the progress bar
+    from tqdm import tqdm, trange
+except Exception:  # pragma: no cover
+    tqdm = None
+
+    def trange(a, b, disable=False):
+        class _R:
+            def __iter__(self):
+                return iter(range(a, b))
+
+            def set_description(self, *_):
+                pass
+
+            def close(self):
+                pass
+
+        return _R()
+
+
+class dgp:
+    """Deep GP hierarchy for stochastic imputation inference (arguments: dgp.py:71)."""
+
+    def __init__(self, X, Y, all_layer=None, check_rep=True, block=True, vecchia=False, m=25, ord_fun=None):
+        self.Y = Y
+        if isinstance(self.Y, list):
+            if len(self.Y) == 1:
+                self.Y = self.Y[0]
+            else:
+                raise Exception('Y has to be a numpy 2d-array rather than a list. The list version of Y (for linked '
+                                'emulation) has been reduced. Please use the dedicated lgp class for linked emulation.')
+        if (self.Y).ndim == 1 or X.ndim == 1:
+            raise Exception('The input and output data have to be numpy 2d-arrays.')
+        self.check_rep = check_rep
+        self.indices = None
+        self.counts = None
+        if self.check_rep:
+            X0 = np.unique(X, axis=0)
+            if len(X0) != len(X):
+                raise NotImplementedError("dgp_b200: repeated input rows (replicates) are outside the SI hot path")
+        self.X = X
+        self.vecch = vecchia
+        self.n_data = self.X.shape[0]
+        self.nn_method = 'exact'
+        self.m = min(m, self.n_data - 1)
+        self.ord_fun = ord_fun
+        if all_layer is None:  # default input-connected two-layer DGP (dgp.py:105-109)
+            D, Y_D = np.shape(self.X)[1], np.shape(self.Y)[1]
+            layer1 = [ker(length=np.array([1.])) for _ in range(D)]
+            layer2 = [ker(length=np.array([1.]), scale_est=True, connect=np.arange(D)) for _ in range(Y_D)]
+            all_layer = combine(layer1, layer2)
+        self.all_layer = all_layer
+        self.n_layer = len(self.all_layer)
+        for layer in self.all_layer:
+            for node in layer:
+                if getattr(node, 'type', 'gp') != 'gp':
+                    raise NotImplementedError("dgp_b200: likelihood layers are outside the SI hot path")
+        self.initialize()
+        self.block = block
+        self.imp = imputer(self.all_layer, self.block)
+        (self.imp).sample(burnin=10)
+        self.compute_r2()
+        self.N = 0
+        self.burnin = None
+
+    def __setstate__(self, state):
+        for key, val in (('block', True), ('vecch', False), ('nn_method', 'exact'), ('m', 25), ('ord_fun', None),
+                         ('counts', None)):
+            state.setdefault(key, val)
+        state.setdefault('n_data', state['X'].shape[0])
+        self.__dict__.update(state)
+
+    # ---- wiring of inputs / outputs (generic branch of dgp.py:154-691 and :1097-1362) ---------------
+    def _latent_init(self, In, width):
+        """Warm start of a latent layer: copy of its input, Nystrom kernel-PCA when it narrows, column
+        resampling when it widens (dgp.py:565-576)."""
+        d = np.shape(In)[1]
+        if d == width:
+            return copy.copy(In)
+        if d > width:
+            if self.vecch or self.n_data >= 500:
+                return NystromKPCA(n_components=width).fit_transform(In)
+            from sklearn.decomposition import KernelPCA
+            return KernelPCA(n_components=width, kernel='sigmoid').fit_transform(In)
+        return np.concatenate((In, In[:, np.random.choice(d, width - d)]), 1)
+
+    def _share_or_draw_ord(self, layer, k):
+        kernel = layer[k]
+        for j in range(k):
+            same = np.array_equal(kernel.input_dim, layer[j].input_dim) and np.array_equal(kernel.connect,
+                                                                                           layer[j].connect)
+            if len(kernel.length) == 1 and same and len(layer[j].length) == 1:
+                kernel.ord_nn(ord=layer[j].ord, NNarray=layer[j].NNarray)
+                return
+            if len(kernel.length) != 1 and same and np.array_equal(kernel.length, layer[j].length):
+                kernel.ord_nn(ord=layer[j].ord.copy(), NNarray=layer[j].NNarray.copy())
+                return
+        kernel.ord_nn()
+
+    def _wire(self, first_time, reset_row=None):
+        In = self.X
+        for l, layer in enumerate(self.all_layer):
+            last = l == self.n_layer - 1
+            if not last:
+                Out = self._latent_init(In, len(layer))
+            for k, kernel in enumerate(layer):
+                if kernel.input_dim is None:
+                    kernel.input_dim = np.arange(np.shape(In)[1])
+                kernel.input = In[:, kernel.input_dim].copy()
+                if kernel.connect is not None:
+                    if l == 0 and len(np.intersect1d(kernel.connect, kernel.input_dim)) != 0:
+                        raise Exception('The local input and global input should not have any overlap. Change '
+                                        'input_dim or connect so they do not have any common indices.')
+                    kernel.global_input = self.X[:, kernel.connect]
+                kernel.m = self.m
+                if first_time:
+                    kernel.vecch, kernel.nn_method = self.vecch, self.nn_method
+                    if self.ord_fun is not None:
+                        kernel.ord_fun = self.ord_fun
+                    kernel.D = np.shape(kernel.input)[1] + (len(kernel.connect) if kernel.connect is not None else 0)
+                elif reset_row is not None:
+                    hyp = kernel.para_path[reset_row, :]
+                    kernel.scale, kernel.length, kernel.nugget = hyp[[0]], hyp[1:-1], hyp[[-1]]
+                if kernel.vecch:
+                    self._share_or_draw_ord(layer, k)
+                kernel.output = self.Y[:, [k]] if last else Out[:, [k]].copy()
+                if kernel.prior_name == 'ref':
+                    if first_time:
+                        p = kernel.D
+                        b = 1 / len(kernel.output) ** (1 / p) * (kernel.prior_coef + p)
+                        kernel.prior_coef = np.concatenate((kernel.prior_coef, b))
+                    kernel.compute_cl()
+                if first_time:
+                    kernel.para_path = np.atleast_2d(np.concatenate((kernel.scale, kernel.length, kernel.nugget)))
+            if not last:
+                In = copy.copy(Out)
+
+    def initialize(self):
+        """Initialise all_layer attribute for training (dgp.py:154)."""
+        self._wire(first_time=True)
+
+    def reinit_all_layer(self, reset_lengthscale, row=0):
+        """Re-initialise the latent layers (and optionally the hyper-parameters) after a failed run
+        (dgp.py:1097-1362, generic branch)."""
+        self._wire(first_time=False, reset_row=row if reset_lengthscale else None)
+
+    def to_vecchia(self, m=25, ord_fun=None):
+        """Convert the DGP structure to the Vecchia mode (dgp.py:693-746)."""
+        if self.vecch:
+            raise Exception('The DGP structure is already in Vecchia mode.')
+        self.vecch = True
+        self.m = min(m, self.n_data - 1)
+        self.ord_fun = ord_fun
+        for layer in self.all_layer:
+            for k, kernel in enumerate(layer):
+                kernel.vecch, kernel.m, kernel.ord_fun = self.vecch, self.m, self.ord_fun
+                self._share_or_draw_ord(layer, k)
+
+    def remove_vecchia(self):
+        """Remove the Vecchia mode from the DGP structure (dgp.py:748-758)."""
+        if not self.vecch:
+            raise Exception('The DGP structure is already in non-Vecchia mode.')
+        self.vecch = False
+        for layer in self.all_layer:
+            for kernel in layer:
+                kernel.vecch = self.vecch
+
+    # ---- stochastic EM ----------------------------------------------------------------------------------
+    def train(self, N=500, ess_burn=10, disable=False):
+        """Train the DGP model by stochastic EM (dgp.py:1364-1412): per iteration an I-step of `ess_burn`+1
+        ESS sweeps and an M-step (L-BFGS-B) over every GP node; up to three restarts on LinAlgError."""
+        N0 = self.N
+        restarts, max_restarts = 0, 3
+        pgb = None
+        while True:
+            try:
+                pgb = trange(1, N + 1, disable=disable)
+                for i in pgb:
+                    (self.imp).sample(burnin=ess_burn)
+                    if self.vecch and (self.N + i & (self.N + i - 1)) == 0 and self.N + i > 1:
+                        (self.imp).update_ord_nn()
+                    for l in range(self.n_layer):
+                        for kernel in self.all_layer[l]:
+                            if kernel.prior_name == 'ref':
+                                kernel.compute_cl()
+                            if l != 0:
+                                kernel.r2()
+                            kernel.maximise()
+                        pgb.set_description('Iteration %i: Layer %i' % (i, l + 1))
+                self.N += N
+                return
+            except (np.linalg.LinAlgError, SystemError):
+                restarts += 1
+                if pgb is not None:
+                    pgb.close()
+                if restarts > max_restarts:
+                    raise RuntimeError(f"Training failed after {max_restarts} restarts.")
+                if not disable and tqdm is not None:
+                    tqdm.write(f"Restart {restarts}/{max_restarts}:")
+                self.N = N0
+                self.reinit_all_layer(reset_lengthscale=True, row=self.N)
+
+    def ptrain(self, *args, **kwargs):
+        raise NotImplementedError("dgp_b200: process-pool training is replaced by the GPU path; use train()")
+
+    def compute_r2(self):
+        for l in range(1, self.n_layer):
+            for kernel in self.all_layer[l]:
+                kernel.r2(overwritten=True)
+
+    def aggregate_r2(self, burnin=0.75, agg='median'):
+        """dgp.py:1481-1515."""
+        if burnin < 0 or burnin > 1:
+            raise Exception('burnin must be between 0 and 1.')
+        if agg not in ('mean', 'median'):
+            raise Exception("agg must be either 'median' or 'mean'.")
+        f = np.mean if agg == 'mean' else np.median
+        res = []
+        for layer in self.all_layer:
+            res.append([None if k.R2 is None else f(k.R2[int(len(k.R2) * burnin):, :], axis=0) for k in layer])
+        return res
+
+    def estimate(self, burnin=None):
+        """Point estimates = mean of the parameter traces after burn-in (dgp.py:1517-1541)."""
+        self.burnin = int(self.N * (3 / 4)) if burnin is None else burnin
+        final_struct = copy.deepcopy(self.all_layer)
+        for layer in final_struct:
+            for kernel in layer:
+                point_est = np.mean(kernel.para_path[self.burnin:, :], axis=0)
+                kernel.scale = np.atleast_1d(point_est[0])
+                kernel.length = np.atleast_1d(point_est[1:-1])
+                kernel.nugget = np.atleast_1d(point_est[-1])
+        return final_struct

@@ -1,0 +1,146 @@
+"""`emulator` -- predictions from a trained DGP (dgpsi/emulation.py:14-44, 631-854) on the GPU.
+
+`__init__` draws N imputations (ESS on the device) and computes each node's R^-1 / R^-1y with the
+sliding-window factorisation; `predict(x, method='mean_var')` pushes the test inputs through the layers on
+the device -- first layer `gp`, deeper layers `link_gp` -- keeps the per-imputation moments in HBM and
+aggregates them with one kernel.  With a process group (one process per GPU) the test points are sharded
+and the moments all-gathered over NCCL (`dgp_b200.parallel`).
+Out of scope: LOO, ALM/MICE/VIGF, nllik, ppredict.
+"""
+from __future__ import annotations
+
+import copy
+
+import numpy as np
+
+from . import _lib as L
+from .imputation import imputer
+
+
+class emulator:
+    """Class to make predictions from the trained DGP model (arguments: emulation.py:24)."""
+
+    def __init__(self, all_layer, N=10, block=True):
+        self.all_layer = all_layer
+        self.n_layer = len(all_layer)
+        self.vecch = bool(self.all_layer[0][0].vecch)
+        self.imp = imputer(self.all_layer, block)
+        if self.vecch:
+            (self.imp).update_ord_nn()
+            (self.imp).sample(burnin=20)
+        else:
+            (self.imp).sample(burnin=50)
+        self.all_layer_set = []
+        for _ in range(N):
+            if self.vecch:
+                (self.imp).update_ord_nn()
+            (self.imp).sample()
+            if not self.vecch:
+                (self.imp).key_stats()
+            (self.all_layer_set).append(copy.deepcopy(self.all_layer))
+
+    def __setstate__(self, state):
+        state.pop('all_layer_set_copy', None)
+        state.pop('nb_parallel', None)
+        state.setdefault('vecch', False)
+        self.__dict__.update(state)
+
+    def to_vecchia(self):
+        """emulation.py:62-74."""
+        if self.vecch:
+            raise Exception('The DGP emulator is already in Vecchia mode.')
+        self.vecch = True
+        for one in self.all_layer_set:
+            for layer in one:
+                for kernel in layer:
+                    kernel.vecch = True
+                    if kernel.ord is None:
+                        kernel.m = min(25, kernel.input.shape[0] - 1) if kernel.m is None else kernel.m
+
+    def remove_vecchia(self):
+        """emulation.py:76-89."""
+        if not self.vecch:
+            raise Exception('The DGP emulator is already in non-Vecchia mode.')
+        self.vecch = False
+        for one in self.all_layer_set:
+            for layer in one:
+                for kernel in layer:
+                    kernel.vecch = False
+                    kernel.compute_stats()
+
+    # ---- prediction -------------------------------------------------------------------------------------
+    def _predict_one_imputation(self, layers, xd, m, collect_layers):
+        """Propagate device test inputs `xd` (M x d) through one imputed hierarchy; returns device tensors."""
+        torch = L.torch_mod()
+        mean = var = None
+        per_layer = []
+        for l, layer in enumerate(layers):
+            ms, vs = [], []
+            for kernel in layer:
+                kernel.pred_m = m
+                z = L.cols(xd, kernel.connect) if kernel.connect is not None else None
+                if l == 0:
+                    mk, vk = kernel._gp_prediction_dev(L.cols(xd, kernel.input_dim), z)
+                else:
+                    mk, vk = kernel._linkgp_prediction_dev(L.cols(mean, kernel.input_dim), L.cols(var, kernel.input_dim), z)
+                ms.append(mk)
+                vs.append(vk)
+            mean, var = torch.stack(ms, 1), torch.stack(vs, 1)
+            if collect_layers:
+                per_layer.append((mean, var))
+        return mean, var, per_layer
+
+    def predict(self, x, method='mean_var', full_layer=False, sample_size=50, m=50, aggregation=True):
+        """Predictions from the trained DGP (emulation.py:631-854).  `x`: (M x d) numpy array.
+        method='mean_var' returns (mu, sigma2) exactly as the reference; method='sampling' draws
+        `sample_size` normal samples per imputation from the final-layer moments."""
+        if x.ndim == 1:
+            raise Exception('The testing input has to be a numpy 2d-array')
+        lib = L.load()
+        torch = L.torch_mod()
+        xd = L.to_dev(x, np.float64)
+        S = len(self.all_layer_set)
+        means, variances, layers_all = [], [], []
+        for s in range(S):
+            mean, var, per_layer = self._predict_one_imputation(self.all_layer_set[s], xd, m, full_layer)
+            means.append(mean)
+            variances.append(var)
+            layers_all.append(per_layer)
+        if method == 'sampling':
+            if full_layer:
+                out = []
+                for l in range(self.n_layer):
+                    mu_l = torch.stack([layers_all[s][l][0] for s in range(S)], 0).cpu().numpy()
+                    va_l = torch.stack([layers_all[s][l][1] for s in range(S)], 0).cpu().numpy()
+                    draws = np.random.normal(np.repeat(mu_l, sample_size, 0), np.sqrt(np.repeat(va_l, sample_size, 0)))
+                    out.append(list(draws.transpose(2, 1, 0)))
+                return out
+            mu_s = torch.stack(means, 0).cpu().numpy()
+            va_s = torch.stack(variances, 0).cpu().numpy()
+            draws = np.random.normal(np.repeat(mu_s, sample_size, 0), np.sqrt(np.repeat(va_s, sample_size, 0)))
+            return list(draws.transpose(2, 1, 0))
+        if method != 'mean_var':
+            raise Exception("method must be 'mean_var' or 'sampling'")
+
+        def agg(ms, vs):
+            ms, vs = torch.stack(ms, 0).contiguous(), torch.stack(vs, 0).contiguous()
+            mu, s2 = torch.empty_like(ms[0]), torch.empty_like(ms[0])
+            L.check(lib.dgpb_aggregate(L.ptr(ms), L.ptr(vs), ms.shape[0], ms[0].numel(), L.ptr(mu), L.ptr(s2),
+                                       L.stream()))
+            return mu.cpu().numpy(), s2.cpu().numpy()
+
+        if full_layer:
+            mu, sigma2 = [], []
+            for l in range(self.n_layer):
+                a, b = agg([layers_all[s][l][0] for s in range(S)], [layers_all[s][l][1] for s in range(S)])
+                mu.append(a)
+                sigma2.append(b)
+            return mu, sigma2
+        if aggregation:
+            return agg(means, variances)
+        return [t.cpu().numpy() for t in means], [t.cpu().numpy() for t in variances]
+
+    def ppredict(self, x, method='mean_var', full_layer=False, sample_size=50, m=50, chunk_num=None, core_num=None):
+        """The reference splits test points over a process pool (emulation.py:578-629); one GPU replaces the
+        pool, so this is `predict`.  Use dgp_b200.parallel.predict_sharded for several GPUs."""
+        return self.predict(x, method, full_layer, sample_size, m, True)

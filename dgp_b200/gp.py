@@ -1,0 +1,104 @@
+"""`gp` -- single Gaussian-process emulator (dgpsi/gp.py:12-60, 211-222, 412-453), GPU-backed through
+`kernel`.  In scope as a member of linked systems: construction, `train`,
+`predict`, `export`; LOO / design metrics are not."""
+from __future__ import annotations
+
+import copy
+
+import numpy as np
+
+
+class gp:
+    """Class for Gaussian process emulation (arguments: gp.py:26)."""
+
+    def __init__(self, X, Y, kernel, check_rep=True, vecchia=False, m=25, ord_fun=None):
+        if Y.ndim == 1 or X.ndim == 1:
+            raise Exception('The input and output data have to be numpy 2d-arrays.')
+        self.check_rep = check_rep
+        self.indices = None
+        if self.check_rep and len(np.unique(X, axis=0)) != len(X):
+            raise NotImplementedError("dgp_b200: repeated input rows (replicates) are outside the SI hot path")
+        self.X, self.Y = X, Y
+        self.kernel = kernel
+        self.vecch = vecchia
+        self.n_data = self.X.shape[0]
+        self.m = min(m, self.n_data - 1)
+        self.ord_fun = ord_fun
+        self.initialize()
+        if self.vecch:
+            self.kernel.ord_nn()
+        else:
+            self.kernel.compute_stats()
+
+    def __setstate__(self, state):
+        for key, val in (('vecch', False), ('nn_method', 'exact'), ('m', 25), ('ord_fun', None), ('indices', None),
+                         ('check_rep', False)):
+            state.setdefault(key, val)
+        state.setdefault('n_data', state['X'].shape[0])
+        self.__dict__.update(state)
+        self.kernel.target = 'gp'
+
+    def initialize(self):
+        """Assign input/output data to the kernel for training (gp.py:79-115)."""
+        k = self.kernel
+        if k.input_dim is not None:
+            k.input = self.X[:, k.input_dim]
+        else:
+            k.input = (self.X).copy()
+            k.input_dim = np.arange(np.shape(self.X)[1])
+        if k.connect is not None:
+            if len(np.intersect1d(k.connect, k.input_dim)) != 0:
+                raise Exception('The local input and global input should not have any overlap. Change input_dim or '
+                                'connect so they do not have any common indices.')
+            k.global_input = self.X[:, k.connect]
+        k.output = (self.Y).copy()
+        k.D = np.shape(k.input)[1] + (len(k.connect) if k.connect is not None else 0)
+        k.para_path = np.atleast_2d(np.concatenate((k.scale, k.length, k.nugget)))
+        k.vecch, k.m, k.target = self.vecch, self.m, 'gp'
+        if self.ord_fun is not None:
+            k.ord_fun = self.ord_fun
+        if k.prior_name == 'ref':
+            p = k.D
+            b = 1 / len(k.output) ** (1 / p) * (k.prior_coef + p)
+            k.prior_coef = np.concatenate((k.prior_coef, b))
+            k.compute_cl()
+
+    def to_vecchia(self, m=25, ord_fun=None):
+        if self.vecch:
+            raise Exception('The GP emulator is already in Vecchia mode.')
+        self.vecch = True
+        self.m = min(m, self.n_data - 1)
+        self.ord_fun = ord_fun
+        self.kernel.vecch, self.kernel.m, self.kernel.ord_fun = True, self.m, ord_fun
+        self.kernel.ord_nn()
+
+    def remove_vecchia(self):
+        if not self.vecch:
+            raise Exception('The GP emulator is already in non-Vecchia mode.')
+        self.vecch = False
+        self.kernel.vecch = False
+        self.kernel.compute_stats()
+
+    def train(self):
+        """Train the GP model (gp.py:211-216)."""
+        self.kernel.maximise()
+        if not self.vecch:
+            self.kernel.compute_stats()
+
+    def export(self):
+        """Export the trained GP (gp.py:218-222)."""
+        return [copy.deepcopy(self.kernel)]
+
+    def predict(self, x, method='mean_var', sample_size=50, m=50):
+        """gp.py:412-453."""
+        if x.ndim == 1:
+            raise Exception('The testing input has to be a numpy 2d-array')
+        k = self.kernel
+        z = x[:, k.connect] if k.connect is not None else None
+        k.pred_m = m
+        mu, sigma2 = k.gp_prediction(x=x[:, k.input_dim], z=z)
+        if method == 'mean_var':
+            return mu.reshape(-1, 1), sigma2.reshape(-1, 1)
+        if method == 'sampling':
+            return np.random.normal(mu, np.sqrt(sigma2), size=(sample_size, len(x))).T
+        raise Exception("method must be 'mean_var' or 'sampling'")

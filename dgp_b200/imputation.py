@@ -1,0 +1,182 @@
+"""`imputer` -- ESS-within-Gibbs imputation of the latent layers (dgpsi/imputation.py:6-262) with the whole
+I-step resident on the GPU: latent layers are uploaded once per `sample()` call, every block update runs in
+libdgpb.so (`dgpb_ess_block`), and the imputed layers are written back to the nodes' numpy attributes at the
+end, so the object graph looks exactly as the reference leaves it (`kernel.output`, `kernel.input`).
+
+Randomness: standard normals for dense prior draws come from the module RNG seeded by `nb_seed` (the
+reference draws them from numba's RNG inside `fmvn`, functions.py:118), Vecchia prior draws and all uniforms
+from numpy's global RNG (vecchia.py:137, imputation.py:79-119).  The number of uniforms consumed per block
+update equals the reference's (threshold, first angle, one per rejection).
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+
+from . import _lib as L
+
+_nb_rng = np.random.RandomState()
+
+
+def nb_seed(value):
+    """Seed the generator behind the dense prior draws (the role numba's RNG plays in the reference,
+    utils.py:51-55)."""
+    _nb_rng.seed(value)
+
+
+class _DeviceLayers:
+    """Device image of a DGP hierarchy during one I-step."""
+
+    def __init__(self, all_layer):
+        self.all_layer = all_layer
+        self.n = len(all_layer[0][0].output)
+        self.F, self.nodes, self.keep = [], [], []
+        n = self.n
+        for l, layer in enumerate(all_layer):
+            for kern in layer:
+                if kern.type != 'gp':
+                    raise NotImplementedError("dgp_b200: likelihood layers are outside the SI hot path "
+                                              "(SURVEY.md section 2, row 10)")
+                if kern.rep is not None:
+                    raise NotImplementedError("dgp_b200: replicate pooling is outside the SI hot path")
+            Fl = L.to_dev(np.ascontiguousarray(np.stack([k.output[:, 0] for k in layer], 0)))
+            self.F.append(Fl)
+            arr = (L.DgpbNode * len(layer))()
+            for k, kern in enumerate(layer):
+                if l == 0:
+                    src = L.to_dev(np.ascontiguousarray(kern.input.T))
+                    input_dim = np.arange(kern.input.shape[1])
+                else:
+                    src = self.F[l - 1]
+                    input_dim = kern.input_dim
+                gsrc = L.to_dev(np.ascontiguousarray(kern.global_input.T)) if kern.global_input is not None else None
+                ordd = nnd = None
+                if kern.vecch:
+                    ordd, nnd = L.to_dev(kern.ord, np.int64), L.to_dev(kern.NNarray, np.int64)
+                self.keep += [src, gsrc, ordd, nnd]
+                L.fill_node(arr[k], kind=kern.name, input_dim=input_dim,
+                            connect=None if gsrc is None else np.arange(gsrc.shape[0]), length=kern.length,
+                            scale=kern.scale, nugget=kern.nugget, src=src, gsrc=gsrc, output=None, ord=ordd,
+                            NNarray=nnd, m=(kern.NNarray.shape[1] - 1) if kern.vecch else 0, vecch=bool(kern.vecch))
+                arr[k].output = Fl.data_ptr() + k * n * 8
+            self.nodes.append(arr)
+
+    def ess_call(self, l, tks, uks, z, u):
+        """One `dgpb_ess_block` call with explicit draws: z (len(tks) x n) standard normals, u uniforms in the
+        reference's consumption order.  Returns (proposals evaluated, angles tried)."""
+        lib = L.load()
+        n = self.n
+        targets = (L.DgpbNode * len(tks))(*[self.nodes[l][k] for k in tks])
+        uppers = (L.DgpbNode * len(uks))(*[self.nodes[l + 1][j] for j in uks])
+        rows = np.ascontiguousarray(tks, dtype=np.int32)
+        zd = L.to_dev(np.ascontiguousarray(z, dtype=np.float64))
+        u = np.ascontiguousarray(u, dtype=np.float64)
+        theta = np.zeros(len(u))
+        nprop = ctypes.c_int(0)
+        status = lib.dgpb_ess_block(L.workspace(), targets, len(tks), rows.ctypes.data_as(L.c_vp), L.ptr(self.F[l]),
+                                    self.F[l].shape[0], uppers, len(uks), n, L.ptr(zd), u.ctypes.data_as(L.c_vp),
+                                    len(u), ctypes.byref(nprop), theta.ctypes.data_as(L.c_vp), L.stream())
+        self.last_nprop = nprop.value
+        L.check(status)
+        return nprop.value, theta[:nprop.value]
+
+    def block_update(self, l, tks, uks, max_u=64):
+        """One ESS update of the target nodes `tks` of layer l given the upper nodes `uks` of layer l+1,
+        drawing from the RNG streams described in the module docstring."""
+        n = self.n
+        layer = self.all_layer[l]
+        z = np.empty((len(tks), n))
+        for i, k in enumerate(tks):
+            # fmvn_sp draws from numpy's global RNG, fmvn from the (numba-role) module RNG
+            z[i] = np.random.randn(n) if layer[k].vecch else _nb_rng.standard_normal(n)
+        while True:
+            state = np.random.get_state()
+            u = np.random.uniform(size=max_u)
+            try:
+                nprop, _ = self.ess_call(l, tks, uks, z, u)
+            except ValueError:
+                if self.last_nprop + 1 < max_u:
+                    raise
+                np.random.set_state(state)  # ran out of uniforms: redo the same update with a longer array
+                max_u *= 4
+                continue
+            np.random.set_state(state)
+            np.random.uniform(size=1 + nprop)  # consume exactly what the reference would have
+            return nprop
+
+    def write_back(self):
+        """Imputed layers -> `kernel.output` of their nodes and `kernel.input` of the nodes they feed."""
+        for l in range(len(self.all_layer) - 1):
+            Fl = self.F[l].cpu().numpy()
+            for k, kern in enumerate(self.all_layer[l]):
+                kern.output[:, 0] = Fl[k]
+            for kern in self.all_layer[l + 1]:
+                kern.input = np.ascontiguousarray(Fl[kern.input_dim].T)
+
+
+class imputer:
+    """Class to implement imputation of latent variables (imputation.py:6-20)."""
+
+    def __init__(self, all_layer, block=True):
+        self.all_layer = all_layer
+        self.block = block
+        self.n_proposals = 0      # instrumentation for the roofline accounting
+        self.n_block_updates = 0
+
+    def __setstate__(self, state):
+        state.setdefault('block', True)
+        state.setdefault('n_proposals', 0)
+        state.setdefault('n_block_updates', 0)
+        self.__dict__.update(state)
+
+    def sample(self, burnin=0):
+        """ESS-within-Gibbs: burnin+1 sweeps over the layer pairs (imputation.py:22-42)."""
+        n_layer = len(self.all_layer)
+        if n_layer < 2:
+            return
+        dev = _DeviceLayers(self.all_layer)
+        for _ in range(burnin + 1):
+            for l in range(n_layer - 1):
+                layer, linked = self.all_layer[l], self.all_layer[l + 1]
+                if self.block:
+                    self.n_proposals += dev.block_update(l, list(range(len(layer))), list(range(len(linked))))
+                    self.n_block_updates += 1
+                else:
+                    for k in range(len(layer)):
+                        uks = [j for j, kern in enumerate(linked) if k in kern.input_dim]
+                        self.n_proposals += dev.block_update(l, [k], uks)
+                        self.n_block_updates += 1
+        dev.write_back()
+
+    def key_stats(self):
+        """Compute and store key statistics used in predictions (imputation.py:223-231)."""
+        for layer in self.all_layer:
+            for kernel in layer:
+                if kernel.type == 'gp':
+                    kernel.compute_stats()
+
+    def update_ord_nn(self):
+        """Re-draw the Vecchia ordering / neighbours of every node, sharing them between nodes of a layer
+        that see the same inputs and length-scales (imputation.py:233-262)."""
+        for layer in self.all_layer:
+            for k, kernel in enumerate(layer):
+                if kernel.type != 'gp':
+                    continue
+                match = None
+                for j in range(k):
+                    same_in = np.array_equal(kernel.input_dim, layer[j].input_dim) and np.array_equal(
+                        kernel.connect, layer[j].connect)
+                    if len(kernel.length) == 1:
+                        ok = same_in and len(layer[j].length) == 1
+                    else:
+                        ok = same_in and np.array_equal(kernel.length, layer[j].length)
+                    if ok:
+                        match = layer[j]
+                        break
+                if match is None:
+                    kernel.ord_nn()
+                elif len(kernel.length) == 1:
+                    kernel.ord_nn(ord=match.ord, NNarray=match.NNarray)
+                else:
+                    kernel.ord_nn(ord=match.ord.copy(), NNarray=match.NNarray.copy())

@@ -73,6 +73,8 @@ typedef struct dgpb_node {
 
 const char* dgpb_last_error(void);
 int dgpb_version(void);
+/* sizeof(dgpb_node) as compiled into the library (binding self-check) */
+int64_t dgpb_sizeof_node(void);
 
 int dgpb_ws_create(dgpb_ws** ws, int device);
 int dgpb_ws_destroy(dgpb_ws* ws);

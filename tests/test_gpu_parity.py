@@ -1,0 +1,493 @@
+"""GPU parity tests: the CUDA path (through the C-ABI / the reference-shaped Python API) against
+(a) the golden vectors produced by the unmodified reference and (b) the CPU oracle on seeded inputs.
+
+Tolerances follow BASELINE.json: kernel matrices / log-likelihoods / gradients / predictions <= 1e-9
+relative in FP64 where the problem is well conditioned; for the reference's default 1e-6 nugget
+(cond(K) ~ 1e7-1e9) the comparison is made against the cancellation scale of the quantity (the sum of the
+absolute values of its terms), which is the reference's own BLAS-thread noise floor.
+Index arrays are compared bit-exactly; ESS accept/shrink decisions must be identical.
+"""
+import numpy as np
+import pytest
+
+from conftest import relerr
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+
+def _case(g, ci):
+    p = f"c{ci}_"
+    d = {k[len(p):]: g[k] for k in g.files if k.startswith(p)}
+    d["name"] = str(d["name"])
+    return d
+
+
+def _node_from_case(c, with_stats=False):
+    import dgp_b200 as D
+
+    nugget_est, scale_est, d_loc, d_glob = [int(v) for v in c["flags"][:4]]
+    k = D.kernel(length=c["length"].copy(), scale=c["scale"][0], nugget=c["nugget"][0], name=c["name"],
+                 nugget_est=bool(nugget_est), scale_est=bool(scale_est),
+                 connect=np.arange(d_glob) if d_glob else None)
+    X = c["X"]
+    k.input = X[:, :d_loc].copy()
+    k.input_dim = np.arange(d_loc)
+    if d_glob:
+        k.global_input = X[:, d_loc:].copy()
+    k.output = c["y"].copy()
+    k.D = d_loc + d_glob
+    k.para_path = np.atleast_2d(np.concatenate((k.scale, k.length, k.nugget)))
+    if with_stats:
+        k.scale = c["scale_after"].copy()
+        k.Rinv, k.Rinv_y = c["Rinv"], c["Rinv_y"]
+    return k
+
+
+# ------------------------------------------------------------------------------------------------ 1
+def test_kmatrix_and_derivatives_vs_reference(golden_dense):
+    g = golden_dense
+    for ci in range(int(g["ncases"])):
+        c = _case(g, ci)
+        k = _node_from_case(c)
+        K, fod = k.k_matrix(fod_eval=True)
+        assert relerr(K, c["K"], 1e-300) <= 1e-12, ci
+        assert fod.shape == c["fod"].shape
+        assert np.max(np.abs(fod - c["fod"])) <= 1e-12, ci
+        assert relerr(k.k_matrix(), c["K_plain"], 1e-300) <= 1e-12
+
+
+def test_kmatrix_symmetry_and_ragged_sizes():
+    import dgp_b200 as D
+    from oracle import dgp_oracle as O
+
+    rng = np.random.default_rng(3)
+    for n, d, name in ((1, 1, "sexp"), (2, 3, "matern2.5"), (63, 2, "sexp"), (64, 5, "matern2.5"), (65, 4, "sexp"),
+                       (200, 16, "sexp"), (333, 7, "matern2.5")):
+        k = D.kernel(length=rng.uniform(0.5, 2, d), name=name, nugget=1e-4)
+        k.input = rng.uniform(0, 1, (n, d))
+        K = k.k_matrix()
+        assert np.array_equal(K, K.T)
+        assert relerr(K, O.k_matrix(k.input, k.length, 1e-4, name), 1e-300) <= 1e-12
+
+
+# ------------------------------------------------------------------------------------------------ 2
+def test_dense_loglik_gradient_vs_reference(golden_dense):
+    g = golden_dense
+    for ci in range(int(g["ncases"])):
+        c = _case(g, ci)
+        k = _node_from_case(c)
+        well = c["nugget"][0] >= 1e-3
+        ll = k.log_likelihood_func()
+        assert abs(ll - c["loglik"][0]) <= (1e-9 if well else 1e-7) * abs(c["loglik"][0]), (ci, ll, c["loglik"])
+        f, gr = k.llik(k.log_t().copy())
+        assert abs(f[0] - c["nllik"][0]) <= (1e-9 if well else 1e-7) * max(1.0, abs(c["nllik"][0])), ci
+        gtol = (1e-8 if well else 2e-5) * max(1.0, np.max(np.abs(c["nllik_grad"])))
+        assert np.max(np.abs(gr - c["nllik_grad"])) <= gtol, (ci, gr, c["nllik_grad"])
+        assert abs(k.scale[0] - c["scale_after"][0]) <= (1e-9 if well else 1e-7) * abs(c["scale_after"][0])
+
+
+def test_dense_pipeline_vs_oracle_midsize():
+    """n not a multiple of the 64-column panel / 128-row tile, several kernels; oracle = LAPACK."""
+    import dgp_b200 as D
+    from oracle import dgp_oracle as O
+
+    rng = np.random.default_rng(11)
+    for n, d, name, ard in ((130, 3, "sexp", False), (257, 4, "matern2.5", True), (700, 6, "sexp", True)):
+        length = rng.uniform(0.6, 1.5, d if ard else 1)
+        k = D.kernel(length=length.copy(), name=name, nugget=1e-3, scale=0.7, nugget_est=True, scale_est=True)
+        k.input = rng.uniform(0, 1, (n, d))
+        k.output = np.sin(k.input.sum(1, keepdims=True) * 2) + 0.1 * rng.standard_normal((n, 1))
+        k.D = d
+        ll = k.log_likelihood_func()
+        ll0 = O.loglik_dense(k.input, k.output, length, 0.7, 1e-3, name)
+        assert abs(ll - ll0) <= 1e-9 * abs(ll0), (n, ll, ll0)
+        f0, g0, s0 = O.nllik_grad_dense(k.input, k.output, length, 0.7, 1e-3, name, True, True)
+        k.prior_name = None
+        f, gr = k.llik(k.log_t().copy())
+        assert abs(f[0] - f0) <= 1e-9 * max(1.0, abs(f0))
+        assert np.max(np.abs(gr - g0)) <= 1e-8 * max(1.0, np.max(np.abs(g0))), (n, gr, g0)
+        assert abs(k.scale[0] - s0) <= 1e-9 * s0
+        # compute_stats: K * Rinv = I and Rinv_y = Rinv y
+        k.compute_stats()
+        K = O.k_matrix(k.input, k.length, k.nugget, name)
+        Ri = k.Rinv
+        assert np.array_equal(Ri, Ri.T)
+        assert np.max(np.abs(K @ Ri - np.eye(n))) <= 1e-8
+        assert relerr(k.Rinv_y, np.linalg.solve(K, k.output[:, 0]), 1e-6) <= 1e-8
+        # prior draw: chol(scale K) z
+        from dgp_b200 import _lib as L
+        import ctypes
+        z = rng.standard_normal(n)
+        node = k._node(k._upload())
+        zd, nud = L.to_dev(z), L.empty((n,))
+        L.check(L.load().dgpb_mvn_draw(L.workspace(), ctypes.byref(node), n, L.ptr(zd), L.ptr(nud), L.stream()))
+        ref = np.linalg.cholesky(k.scale[0] * K) @ z
+        assert relerr(nud.cpu().numpy(), ref, 1e-6) <= 1e-9
+
+
+def test_not_positive_definite_raises_linalgerror():
+    import dgp_b200 as D
+
+    k = D.kernel(length=np.array([50.0]), nugget=-0.5)
+    x = np.linspace(0, 1, 40)[:, None]
+    k.input = np.concatenate((x, x[:5]), 0)  # diagonal 0.5 under off-diagonals ~1 -> indefinite
+    k.output = np.ones((45, 1))
+    with pytest.raises(np.linalg.LinAlgError):
+        k.log_likelihood_func()
+
+
+def test_potrf_and_gemm_building_blocks():
+    from dgp_b200 import _lib as L
+    import ctypes
+
+    lib = L.load()
+    rng = np.random.default_rng(5)
+    for n in (64, 100, 513, 1500):
+        A = rng.standard_normal((n, n))
+        A = A @ A.T / n + np.eye(n)
+        Ad = L.to_dev(A)
+        info = ctypes.c_int(-1)
+        L.check(lib.dgpb_potrf(L.workspace(), L.ptr(Ad), n, ctypes.byref(info), L.stream()))
+        assert info.value == 0
+        Lc = np.tril(Ad.cpu().numpy())
+        assert np.max(np.abs(Lc @ Lc.T - A)) <= 1e-12 * n
+    M, N, K = 300, 258, 96
+    A, B = rng.standard_normal((M, K)), rng.standard_normal((N, K))
+    C = L.empty((M, N))
+    L.check(lib.dgpb_dgemm_nt(L.ptr(L.to_dev(A)), L.ptr(L.to_dev(B)), L.ptr(C), M, N, K, L.stream()))
+    assert np.max(np.abs(C.cpu().numpy() - A @ B.T)) <= 1e-12 * K
+
+
+# ------------------------------------------------------------------------------------------------ 5
+def _gp_scales(c, xt):
+    from oracle import dgp_oracle as O
+
+    r = O.k_cross(c["X"], xt, c["length"], c["name"])
+    Sm = np.abs(r) @ np.abs(c["Rinv_y"])
+    Sv = np.einsum("ti,ij,tj->t", np.abs(r), np.abs(c["Rinv"]), np.abs(r)) * c["scale_after"][0]
+    return Sm, Sv
+
+
+def test_predictions_given_reference_stats(golden_dense):
+    g = golden_dense
+    for ci in range(int(g["ncases"])):
+        c = _case(g, ci)
+        k = _node_from_case(c, with_stats=True)
+        d_glob = int(c["flags"][3])
+        well = c["nugget"][0] >= 1e-3
+        zt = c["zt"] if d_glob else None
+        m, v = k.gp_prediction(c["xt"], zt)
+        xt = c["xt"] if zt is None else np.concatenate((c["xt"], zt), 1)
+        Sm, Sv = _gp_scales(c, xt)
+        assert np.all(np.abs(m - c["gp_m"]) <= 1e-13 * Sm), ci
+        assert np.all(np.abs(v - c["gp_v"]) <= 1e-13 * Sv), ci
+        if well:
+            assert relerr(m, c["gp_m"], 1e-3) <= 1e-9
+            assert np.max(np.abs(v - c["gp_v"])) <= 1e-9 * c["scale_after"][0]
+        m2, v2 = k.linkgp_prediction(c["lk_m_in"], c["lk_v_in"], zt)
+        a = np.abs(c["Rinv_y"])
+        Slm = a.sum()
+        Slv = a.sum() ** 2 + c["scale_after"][0] * np.abs(c["Rinv"]).sum()
+        assert np.all(np.abs(m2 - c["lk_m"]) <= 1e-13 * Slm), (ci, np.max(np.abs(m2 - c["lk_m"])))
+        assert np.all(np.abs(v2 - c["lk_v"]) <= 1e-13 * Slv), (ci, np.max(np.abs(v2 - c["lk_v"])))
+        if well:
+            assert relerr(m2, c["lk_m"], 1e-3) <= 1e-9, ci
+            assert np.max(np.abs(v2 - c["lk_v"])) <= 1e-9 * c["scale_after"][0], ci
+
+
+def test_linkgp_wide_inputs_vs_oracle():
+    """Dw beyond the register-tiled template sizes and n not a multiple of the pair tile."""
+    import dgp_b200 as D
+    from oracle import dgp_oracle as O
+
+    rng = np.random.default_rng(21)
+    for name, Dw, Dz, n in (("sexp", 9, 0, 70), ("sexp", 13, 2, 45), ("sexp", 3, 1, 100), ("matern2.5", 2, 1, 50)):
+        length = rng.uniform(0.8, 1.6, Dw + Dz)
+        k = D.kernel(length=length.copy(), name=name, nugget=1e-3, scale=1.2,
+                     connect=np.arange(Dz) if Dz else None)
+        k.input = rng.uniform(0, 1, (n, Dw))
+        if Dz:
+            k.global_input = rng.uniform(0, 1, (n, Dz))
+        X = k._X()
+        k.output = np.cos(X.sum(1, keepdims=True))
+        Rinv, Rinv_y = O.compute_stats(X, k.output, length, 1e-3, name)
+        k.Rinv, k.Rinv_y = Rinv, Rinv_y
+        M = 19
+        m_in, v_in = rng.uniform(0, 1, (M, Dw)), rng.uniform(1e-4, 0.03, (M, Dw))
+        z = rng.uniform(0, 1, (M, Dz)) if Dz else None
+        m, v = k.linkgp_prediction(m_in, v_in, z)
+        R2, P = O.sexp_stats(k.input, length[:Dw]) if name == "sexp" else (None, None)
+        m0, v0 = O.link_gp(m_in, v_in, z, k.input, k.global_input, Rinv, Rinv_y, R2, P, 1.2, length, 1e-3, name)
+        assert relerr(m, m0, 1e-3) <= 1e-9, (name, Dw)
+        assert np.max(np.abs(v - v0)) <= 1e-9 * 1.2, (name, Dw, np.max(np.abs(v - v0)))
+
+
+# ------------------------------------------------------------------------------------------------ 4
+def test_nn_indices_bit_exact(golden_vecchia):
+    from dgp_b200 import vecchia as V
+    from oracle import dgp_oracle as O
+
+    g = golden_vecchia
+    for j in range(4):
+        x, m = g[f"nn{j}_x"], int(g[f"nn{j}_m"])
+        assert np.array_equal(V.nn(x, m), g[f"nn{j}_NN"]), j
+        assert np.array_equal(V.get_pred_nn(g[f"nn{j}_q"], x, 50), g[f"nn{j}_pred"]), j
+    rng = np.random.default_rng(2)
+    x = rng.uniform(0, 1, (5000, 10))
+    q = rng.uniform(0, 1, (777, 10))
+    assert np.array_equal(V.nn(x, 25), O.nn_ordered(x, 25))
+    assert np.array_equal(V.get_pred_nn(q, x, 50), O.knn(q, x, 50))
+    # m >= n shortcut and tiny inputs
+    assert np.array_equal(V.get_pred_nn(q[:7], x[:5], 50), O.knn(q[:7], x[:5], 50))
+    assert np.array_equal(V.nn(x[:3], 25), O.nn_ordered(x[:3], 25))
+    assert np.array_equal(V.nn(x[:1], 25), O.nn_ordered(x[:1], 25))
+
+
+def test_vecchia_kernels_vs_reference(golden_vecchia):
+    import dgp_b200 as D
+    from dgp_b200 import vecchia as V
+
+    g = golden_vecchia
+    for ci in range(int(g["ncases"])):
+        c = _case(g, ci)
+        nugget_est, scale_est, d_loc, d_glob, m = [int(v) for v in c["flags"]]
+        X, y, o, NN = c["X"], c["y"], c["ord"], c["NNarray"]
+        assert np.array_equal(V.nn((X / c["length"])[o], m), NN), ci
+        ll = V.vecchia_llik(X[o], y[o], NN, c["scale"][0], c["length"], c["nugget"][0], None, c["name"])
+        assert abs(ll - c["llik"][0]) <= 1e-9 * abs(c["llik"][0]), ci
+        Lm = V.L_matrix(X[o], NN, c["length"], c["nugget"][0], c["name"])
+        assert np.max(np.abs(Lm - c["Lmatrix"])) <= 1e-7 * np.max(np.abs(c["Lmatrix"])), ci
+        draw = V.fmvn_sp(X[o], NN, c["scale"][0], c["length"], c["nugget"][0], c["name"], z=c["z"])
+        assert relerr(draw, c["draw"], 1e-3 * np.max(np.abs(c["draw"]))) <= 1e-6, ci
+        k = D.kernel(length=c["length"].copy(), scale=c["scale"][0], nugget=c["nugget"][0], name=c["name"],
+                     nugget_est=bool(nugget_est), scale_est=bool(scale_est),
+                     connect=np.arange(d_glob) if d_glob else None)
+        k.input, k.output = X[:, :d_loc].copy(), y.copy()
+        if d_glob:
+            k.global_input = X[:, d_loc:].copy()
+        k.vecch, k.m, k.ord, k.NNarray, k.rev_ord = True, m, o, NN, np.argsort(o)
+        f, gr = k.llik_vecch(k.log_t().copy())
+        assert abs(f[0] - c["nllik"][0]) <= 1e-9 * max(1.0, abs(c["nllik"][0])), ci
+        assert np.max(np.abs(gr - c["nllik_grad"])) <= 1e-7 * max(1.0, np.max(np.abs(c["nllik_grad"]))), (ci, gr)
+        assert abs(k.scale[0] - c["scale_after"][0]) <= 1e-9 * abs(c["scale_after"][0])
+        # predictions (neighbour search + block kernels)
+        k.pred_m = c["pred_NN"].shape[1]
+        zt = c["zt"] if d_glob else None
+        tol = 1e-9 if nugget_est else 1e-6
+        m1, v1 = k.gp_prediction(c["xt"], zt)
+        assert relerr(m1, c["gp_m"], 1e-3) <= tol, ci
+        assert relerr(v1, c["gp_v"], 1e-9) <= 1e-5 * (1.0 if nugget_est else 100.0), ci
+        m2, v2 = k.linkgp_prediction(c["lk_m_in"], c["lk_v_in"], zt)
+        assert relerr(m2, c["lk_m"], 1e-3) <= tol, ci
+        if nugget_est:
+            assert relerr(v2, c["lk_v"], 1e-6) <= 1e-6, ci
+        else:
+            assert relerr(v2, c["lk_v"], 1.0) <= 1e-2, ci
+
+
+# ------------------------------------------------------------------------------------------------ 3
+def _load_layers(g, prefix, widths, name, vecch):
+    import dgp_b200 as D
+
+    layers = []
+    for l, w in enumerate(widths):
+        layer = []
+        for k in range(w):
+            p = f"{prefix}L{l}K{k}_"
+            node = D.kernel(length=g[p + "length"].copy(), scale=g[p + "scale"][0], nugget=g[p + "nugget"][0], name=name,
+                            scale_est=(l == len(widths) - 1))
+            node.input = g[p + "input"].copy()
+            node.output = g[p + "output"].copy()
+            node.input_dim = np.arange(node.input.shape[1])
+            if p + "global_input" in g.files:
+                node.global_input = g[p + "global_input"].copy()
+                node.connect = np.arange(node.global_input.shape[1])
+            node.D = node.input.shape[1] + (0 if node.global_input is None else node.global_input.shape[1])
+            node.para_path = np.atleast_2d(np.concatenate((node.scale, node.length, node.nugget)))
+            node.vecch = vecch
+            if vecch:
+                node.ord, node.NNarray = g[p + "ord"], g[p + "NNarray"]
+                node.rev_ord = np.argsort(node.ord)
+                node.m = node.NNarray.shape[1] - 1
+            layer.append(node)
+        layers.append(layer)
+    return layers
+
+
+def test_ess_replay_identical_decisions(golden_ess):
+    from dgp_b200.imputation import _DeviceLayers
+
+    g = golden_ess
+    for ci in range(int(g["ncases"])):
+        p = f"c{ci}_"
+        widths, name, vecch = [int(w) for w in g[p + "widths"]], str(g[p + "name"]), bool(g[p + "vecch"])
+        layers = _load_layers(g, p + "pre_", widths, name, vecch)
+        dev = _DeviceLayers(layers)
+        Z, U, sweeps = g[p + "Z"], g[p + "U"], int(g[p + "sweeps"])
+        zi = ui = 0
+        values = []
+        for _ in range(sweeps):
+            for l in range(len(widths) - 1):
+                M = widths[l]
+                nprop, thetas = dev.ess_call(l, list(range(M)), list(range(widths[l + 1])), Z[zi:zi + M],
+                                             np.concatenate((U[ui:], np.full(4, 0.5))))
+                zi += M
+                values.append(U[ui])
+                values.extend(thetas)
+                ui += 1 + nprop
+        assert zi == len(Z) and ui == len(U), (ci, ui, len(U))  # same draws consumed == identical decisions
+        assert np.allclose(values, g[p + "draw_values"], rtol=1e-12, atol=0), ci
+        dev.write_back()
+        post = _load_layers(g, p + "post_", widths, name, vecch)
+        for l in range(len(widths)):
+            for k in range(widths[l]):
+                assert relerr(layers[l][k].output, post[l][k].output, 1e-4) <= 1e-6, (ci, l, k)
+                assert relerr(layers[l][k].input, post[l][k].input, 1e-4) <= 1e-6, (ci, l, k)
+        # M-step from the reference's imputed state reproduces its optimiser path
+        for l in range(len(widths)):
+            for k in range(widths[l]):
+                node = post[l][k]
+                node.maximise()
+                got = np.concatenate((node.scale, node.length, node.nugget))
+                assert np.allclose(got, g[p + f"mstep_L{l}K{k}"], rtol=5e-4), (ci, l, k, got)
+
+
+# ------------------------------------------------------------------------------------------------ e2e
+def _snapshot_layers(g, prefix, name_of=lambda l, k: "sexp", scale_est_last=True):
+    import dgp_b200 as D
+
+    layers, l = [], 0
+    while f"{prefix}L{l}K0_input" in g.files:
+        layer, k = [], 0
+        while f"{prefix}L{l}K{k}_input" in g.files:
+            p = f"{prefix}L{l}K{k}_"
+            node = D.kernel(length=g[p + "length"].copy(), scale=g[p + "scale"][0], nugget=g[p + "nugget"][0],
+                            name=name_of(l, k))
+            node.input, node.output = g[p + "input"].copy(), g[p + "output"].copy()
+            node.input_dim = np.arange(node.input.shape[1])
+            if p + "global_input" in g.files:
+                node.global_input = g[p + "global_input"].copy()
+                node.connect = np.arange(node.global_input.shape[1])
+            node.vecch = False
+            layer.append(node)
+            k += 1
+        layers.append(layer)
+        l += 1
+    return layers
+
+
+def _frozen_emulator(g, tag, name):
+    import dgp_b200 as D
+
+    emu = D.emulator.__new__(D.emulator)
+    emu.all_layer_set = []
+    for s in range(int(g[f"{tag}_nimp"])):
+        layers = _snapshot_layers(g, f"{tag}_S{s}_", lambda l, k: name)
+        for layer in layers:
+            for node in layer:
+                node.compute_stats()
+        emu.all_layer_set.append(layers)
+    emu.all_layer = emu.all_layer_set[0]
+    emu.n_layer = len(emu.all_layer)
+    emu.vecch = False
+    return emu
+
+
+def test_end_to_end_predict_with_frozen_imputations(golden_e2e):
+    """emulator.predict on the reference's own imputed states (step function = BASELINE config 1, and the
+    2-layer Matern model = config-2 shape): K^-1 is recomputed on the GPU, so this checks kernel build +
+    factorisation + gp + link_gp + aggregation end to end."""
+    g = golden_e2e
+    emu = _frozen_emulator(g, "step", "sexp")
+    mu, var = emu.predict(g["step_xt"])
+    assert mu.shape == g["step_mu"].shape
+    assert np.max(np.abs(mu - g["step_mu"])) <= 2e-6
+    assert np.max(np.abs(var - g["step_var"])) <= 2e-6 * max(1.0, np.max(g["step_var"]))
+    emu2 = _frozen_emulator(g, "mat", "matern2.5")
+    mu2, var2 = emu2.predict(g["mat_xt"])
+    assert np.max(np.abs(mu2 - g["mat_mu"])) <= 2e-6
+    assert np.max(np.abs(var2 - g["mat_var"])) <= 2e-6 * max(1.0, np.max(g["mat_var"]))
+
+
+def test_linked_system_with_frozen_imputations(golden_e2e):
+    import dgp_b200 as D
+
+    g = golden_e2e
+    kinds = {0: "matern2.5", 1: "matern2.5", 2: "sexp"}
+    sets = []
+    for s in range(int(g["lgp_nimp"])):
+        one = []
+        for e in range(3):
+            layers = _snapshot_layers(g, f"lgp_S{s}_E{e}_", lambda l, k, e=e: kinds[e])
+            for layer in layers:
+                for node in layer:
+                    node.compute_stats()
+            cont = D.container.__new__(D.container)
+            if len(layers) == 1:
+                cont.type, cont.structure = 'gp', layers[0][0]
+            else:
+                cont.type, cont.structure = 'dgp', layers
+            cont.vecch = False
+            cont.local_input_idx = np.array([0, 1]) if e == 0 else np.array([0])
+            one.append([cont])
+        sets.append(one)
+    system = D.lgp.__new__(D.lgp)
+    system.L, system.all_layer, system.all_layer_set, system.num_model = 3, sets[0], sets, [1, 1]
+    mu, var = system.predict(g["lgp_xt"])
+    assert np.max(np.abs(mu[0] - g["lgp_mu"])) <= 5e-6 * max(1.0, np.max(np.abs(g["lgp_mu"])))
+    assert np.max(np.abs(var[0] - g["lgp_var"])) <= 5e-6 * max(1.0, np.max(g["lgp_var"]))
+
+
+def test_public_api_train_and_predict_smoke():
+    """The user-facing path runs: dgp(X,Y).train -> estimate -> emulator -> predict; the fit is sane."""
+    import dgp_b200 as D
+
+    np.random.seed(7)
+    D.nb_seed(7)
+    X = np.linspace(0, 1, 12)[:, None]
+    Y = np.where(X > 0.5, 1.0, -1.0)
+    model = D.dgp(X, Y)
+    model.train(N=8, disable=True)
+    assert model.N == 8 and model.all_layer[0][0].para_path.shape[0] == 9
+    emu = D.emulator(model.estimate(), N=2)
+    mu, var = emu.predict(np.linspace(0, 1, 33)[:, None])
+    assert mu.shape == (33, 1) and var.shape == (33, 1)
+    assert np.all(np.isfinite(mu)) and np.all(var >= 0)
+    assert np.mean(np.sign(mu[:, 0]) == np.sign(np.linspace(0, 1, 33) - 0.5 + 1e-9)) > 0.8
+    with pytest.raises(Exception):
+        emu.predict(np.linspace(0, 1, 5))
+
+
+def test_property_checks_at_baseline_scale():
+    """Size-independent properties at a BASELINE-sized node (n=2000, D=10): the factor reproduces K, the
+    inverse is an inverse, log-likelihood agrees with an independent FP64 computation (torch/cuSOLVER used
+    as a CHECKER only)."""
+    import ctypes
+    import dgp_b200 as D
+    from dgp_b200 import _lib as L
+
+    rng = np.random.default_rng(99)
+    n, d = 2000, 10
+    k = D.kernel(length=np.full(d, 1.3), name="matern2.5", nugget=1e-4, scale=1.7)
+    k.input = rng.uniform(0, 1, (n, d))
+    k.output = np.sin(k.input.sum(1, keepdims=True))
+    K = torch.from_numpy(k.k_matrix()).cuda()
+    Lt = torch.linalg.cholesky(1.7 * K)
+    y = torch.from_numpy(k.output).cuda()
+    w = torch.linalg.solve_triangular(Lt, y, upper=False)
+    ll_ref = float(-0.5 * (2 * torch.log(torch.diagonal(Lt)).sum() + (w * w).sum()))
+    ll = k.log_likelihood_func()
+    assert abs(ll - ll_ref) <= 1e-9 * abs(ll_ref), (ll, ll_ref)
+    k.compute_stats()
+    Ri = k._Rinv
+    resid = (K @ Ri - torch.eye(n, dtype=torch.float64, device="cuda")).abs().max().item()
+    assert resid <= 1e-8, resid
+    # linearity of the predictor in y: predicting with 2y doubles the mean, leaves the variance
+    xt = rng.uniform(0, 1, (257, d))
+    m1, v1 = k.gp_prediction(xt, None)
+    k.output = 2 * k.output
+    k.compute_stats()
+    m2, v2 = k.gp_prediction(xt, None)
+    assert relerr(m2, 2 * m1, 1e-6) <= 1e-8 and np.max(np.abs(v2 - v1)) <= 1e-9 * 1.7
