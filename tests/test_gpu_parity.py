@@ -120,7 +120,8 @@ def test_dense_pipeline_vs_oracle_midsize():
         from dgp_b200 import _lib as L
         import ctypes
         z = rng.standard_normal(n)
-        node = k._node(k._upload())
+        bufs = k._upload()  # keep the device buffers alive while the node descriptor points at them
+        node = k._node(bufs)
         zd, nud = L.to_dev(z), L.empty((n,))
         L.check(L.load().dgpb_mvn_draw(L.workspace(), ctypes.byref(node), n, L.ptr(zd), L.ptr(nud), L.stream()))
         ref = np.linalg.cholesky(k.scale[0] * K) @ z
@@ -155,8 +156,8 @@ def test_potrf_and_gemm_building_blocks():
         assert np.max(np.abs(Lc @ Lc.T - A)) <= 1e-12 * n
     M, N, K = 300, 258, 96
     A, B = rng.standard_normal((M, K)), rng.standard_normal((N, K))
-    C = L.empty((M, N))
-    L.check(lib.dgpb_dgemm_nt(L.ptr(L.to_dev(A)), L.ptr(L.to_dev(B)), L.ptr(C), M, N, K, L.stream()))
+    C, Ad, Bd = L.empty((M, N)), L.to_dev(A), L.to_dev(B)
+    L.check(lib.dgpb_dgemm_nt(L.ptr(Ad), L.ptr(Bd), L.ptr(C), M, N, K, L.stream()))
     assert np.max(np.abs(C.cpu().numpy() - A @ B.T)) <= 1e-12 * K
 
 
