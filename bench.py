@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the SI hot path (BASELINE.json):
+    SI train iters/sec (n=5k DGP) + predict points/sec, FP64, at 1/2/4/8 B200.
+
+    python bench.py --gpus N --steps K --warmup W            (N>1: launched by torch.distributed.run)
+    python bench.py --impl reference --steps K --warmup W    (CPU path on the box's host cores)
+
+One "step" = one stochastic-EM iteration of `dgp.train` (I-step: ess_burn+1 = 11 ESS sweeps; M-step: L-BFGS-B
+over every GP node) on BASELINE config 3: 3-layer DGP (8+8+2 squared-exponential nodes, global input
+connections), n=5000, d=8, 2 outputs, synthetic data.  At N>1 every rank runs an independent replica of the
+chain (the Markov chain itself does not shard, DESIGN.md "multi-GPU") and `value` is the aggregate.
+The secondary metric `predict` is `emulator.predict(x, 'mean_var')` points/s with the test points sharded
+over the ranks and the moments all-gathered over NCCL.
+
+Prints ONE JSON line (see the task contract): metric/value/unit/..., `e2e`, `roofline`, `cpu_baseline`,
+`gpu_launches`, `clocks`.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SEED = 20261017 + 2
+METRIC = "SI train iters/sec (n=5k DGP)"
+
+
+# ------------------------------------------------------------------------------------------------ workload
+def make_config3(n, rng):
+    """BASELINE config 3: X~U[0,1]^{n x 8}; y1=sin(sum x)+x1 x2; y2=cos(2 pi x3) x4 + x5^2."""
+    X = rng.uniform(0, 1, size=(n, 8))
+    Y = np.stack([np.sin(X.sum(1)) + X[:, 0] * X[:, 1], np.cos(2 * np.pi * X[:, 2]) * X[:, 3] + X[:, 4] ** 2], 1)
+    return X, Y
+
+
+def layers_config3(make):
+    l1 = [make(length=np.array([1.0]), name="sexp") for _ in range(8)]
+    l2 = [make(length=np.array([1.0]), name="sexp", connect=np.arange(8)) for _ in range(8)]
+    l3 = [make(length=np.array([1.0]), name="sexp", scale_est=True, connect=np.arange(8)) for _ in range(2)]
+    return [l1, l2, l3]
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.stop_flag = index, [], threading.Event()
+        self.thread = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def __enter__(self):
+        self.thread.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop_flag.set()
+        self.thread.join(timeout=6)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [nm for i, nm in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
+                "samples": len(self.rows), "power_w_max": max(float(r[2]) for r in self.rows)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_counts_small(n_small=250):
+    """Evaluation counts of one SEM iteration (they are what the reference executes per iteration: one
+    Cholesky per prior draw, per threshold node and per proposal node, kernel_class.py:481-488,
+    imputation.py:54-107; one `llik` per L-BFGS-B evaluation).  Measured on a small-n oracle run of the same
+    model because they depend on the chain, not on n."""
+    from oracle import dgp_oracle as O
+
+    rng = np.random.default_rng(SEED)
+    X, Y = make_config3(n_small, rng)
+    layers = O.build_dgp(X, Y, layers_config3(lambda **kw: O.Node(**kw)))
+    cnt = {"ll": 0, "grad": 0}
+    orig_ll, orig_draw, orig_obj = O.Node.loglik, O.Node.prior_draw, O.Node.objective
+
+    def ll(self):
+        cnt["ll"] += 1
+        return orig_ll(self)
+
+    def draw(self, z):
+        cnt["ll"] += 1  # one n^3/3 factorisation, same cost class as a likelihood
+        return orig_draw(self, z)
+
+    def obj(self, x):
+        cnt["grad"] += 1
+        return orig_obj(self, x)
+
+    O.Node.loglik, O.Node.prior_draw, O.Node.objective = ll, draw, obj
+    try:
+        O.ess_sweeps(layers, 10, rng)  # burn-in sweep of the constructor (dgp.py:126)
+        cnt["ll"] = cnt["grad"] = 0
+        O.sem_iteration(layers, rng)
+    finally:
+        O.Node.loglik, O.Node.prior_draw, O.Node.objective = orig_ll, orig_draw, orig_obj
+    return cnt
+
+
+def cpu_step(n, rng):
+    """One bounded CPU sample at the full n: one ESS likelihood (K build + Cholesky + solve) and one M-step
+    objective with gradient, for a config-3 upper node (D = 8 local + 8 global)."""
+    from oracle import dgp_oracle as O
+
+    X = rng.uniform(0, 1, size=(n, 16))
+    y = np.sin(X.sum(1))
+    t0 = time.perf_counter()
+    O.loglik_dense(X, y, np.array([1.0]), 1.0, 1e-6, "sexp")
+    t1 = time.perf_counter()
+    O.nllik_grad_dense(X, y, np.array([1.0]), 1.0, 1e-6, "sexp", False, False)
+    t2 = time.perf_counter()
+    return t1 - t0, t2 - t1
+
+
+def cpu_cores():
+    try:
+        import psutil
+        return psutil.cpu_count(logical=False) or os.cpu_count()
+    except Exception:
+        return os.cpu_count()
+
+
+def blas_info():
+    try:
+        from threadpoolctl import threadpool_info
+        return "; ".join(f"{d.get('internal_api')} {d.get('version')} x{d.get('num_threads')}" for d in threadpool_info())
+    except Exception:
+        return "unknown"
+
+
+def run_reference(args):
+    """`--impl reference`: the reference's CPU algorithm (oracle port: numpy + LAPACK on all host cores)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n = args.n
+    rng = np.random.default_rng(SEED)
+    cnt = cpu_counts_small()
+    for _ in range(args.warmup):
+        cpu_step(min(n, 1500), rng)
+    tl, tg = [], []
+    t_start = time.perf_counter()
+    for _ in range(args.steps):
+        a, b = cpu_step(n, rng)
+        tl.append(a)
+        tg.append(b)
+    wall = time.perf_counter() - t_start
+    t_iter = cnt["ll"] * float(np.mean(tl)) + cnt["grad"] * float(np.mean(tg))
+    value = 1.0 / t_iter
+    sample = (f"per step: 1 ESS likelihood + 1 llik(grad) at n={n}, D=16 on the host "
+              f"(mean {np.mean(tl):.2f}s / {np.mean(tg):.2f}s); extrapolated to one SEM iteration with the evaluation "
+              f"counts of the oracle chain at n=250: {cnt['ll']} factorisations + {cnt['grad']} gradient evaluations; "
+              f"BLAS: {blas_info()}")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "iters/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_iter, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args, 1),
+            "cpu_baseline": {"value": value, "unit": "iters/s", "cores": cpu_cores(), "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "wall_s": wall}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, world):
+    return {"workload": f"BASELINE config 3: 3-layer DGP, 8+8+2 sexp nodes with global connections, n={args.n}, d=8, "
+                        f"2 outputs; one step = one SEM iteration (11 ESS sweeps + M-step)",
+            "n": args.n, "ess_burn": 10, "nodes": 18, "replicas": world,
+            "cache": "working set per batched factorisation >> 126 MB L2 (8 x n^2 doubles); no L2 flush needed",
+            "predict_points": args.predict_points, "predict_imputations": args.predict_imputations}
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def measure_fp64_peak(torch):
+    """FP64 roofline denominator: cuBLAS DGEMM 8192^3 (MEASURED_PEAKS.json holds no FP64 figure)."""
+    a = torch.randn(8192, 8192, dtype=torch.float64, device="cuda")
+    b = torch.randn(8192, 8192, dtype=torch.float64, device="cuda")
+    best = 0.0
+    for i in range(6):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        torch.matmul(a, b)
+        e1.record()
+        torch.cuda.synchronize()
+        if i:
+            best = max(best, 2 * 8192 ** 3 / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+    del a, b
+    torch.cuda.empty_cache()
+    return best
+
+
+def run_gpu(args):
+    import torch
+
+    import dgp_b200 as D
+    from dgp_b200 import _lib as L
+
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lib = L.load()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    peak = measure_fp64_peak(torch) if rank == 0 else 0.0
+
+    rng = np.random.default_rng(SEED + rank)  # independent replica per rank
+    np.random.seed(SEED + rank)
+    D.nb_seed(SEED + rank)
+    X, Y = make_config3(args.n, rng)
+    model = D.dgp(X, Y, layers_config3(lambda **kw: D.kernel(**kw)))
+    for _ in range(args.warmup):
+        model.train(1, disable=True)
+
+    h2d0, d2h0 = L.COUNTERS["h2d"], L.COUNTERS["d2h"]
+    launches0 = lib.dgpb_launch_count()
+    prop0 = model.imp.n_proposals
+    lib.dgpb_profile(1)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(args.steps):
+            model.train(1, disable=True)
+        e1.record()
+        barrier()
+        wall = time.perf_counter() - t0
+    dev_ms = e0.elapsed_time(e1)
+    prof = (L.c_dbl * 4)()
+    lib.dgpb_profile_read(prof)
+    lib.dgpb_profile(0)
+    launches = lib.dgpb_launch_count() - launches0
+    h2d, d2h = L.COUNTERS["h2d"] - h2d0, L.COUNTERS["d2h"] - d2h0
+    nprop = model.imp.n_proposals - prop0
+
+    times = torch.tensor([dev_ms, wall * 1e3], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    dev_ms_max, wall_ms_max = float(times[0]), float(times[1])
+
+    # ---- secondary metric: predict points/s (test points sharded over ranks, NCCL all-gather) -------
+    predict = None
+    if args.predict_points > 0:
+        from dgp_b200.parallel import predict_sharded
+        emu = D.emulator(model.estimate(), N=args.predict_imputations)
+        xt_all = np.random.default_rng(SEED + 99).uniform(0, 1, size=(args.predict_points * world, 8))
+        predict_sharded(emu, xt_all[: 64 * world], dist)  # warm-up
+        barrier()
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        tp0 = time.perf_counter()
+        p0.record()
+        mu, var = predict_sharded(emu, xt_all, dist)
+        p1.record()
+        barrier()
+        tp = time.perf_counter() - tp0
+        tt = torch.tensor([p0.elapsed_time(p1), tp * 1e3], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        predict = {"metric": "predict points/sec (mean_var)", "value": len(xt_all) / (float(tt[0]) * 1e-3),
+                   "e2e_value": len(xt_all) / (float(tt[1]) * 1e-3), "unit": "points/s", "points": len(xt_all),
+                   "imputations": args.predict_imputations, "sharding": "test points / rank, all_gather of (mu, var)",
+                   "finite": bool(np.all(np.isfinite(mu)) and np.all(np.isfinite(var)))}
+
+    if rank == 0:
+        value = world * args.steps / (dev_ms_max * 1e-3)
+        e2e = world * args.steps / (wall_ms_max * 1e-3)
+        upd_ms, upd_n, upd_flops = prof[0], prof[1], prof[2]
+        achieved = (upd_flops / upd_n) / (upd_ms / upd_n * 1e-3) / 1e12 if upd_n > 0 else None
+        roof = {"bound": "tensor", "kernel": "update_kernel (FP64 DMMA SYRK trailing update, K=64)",
+                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": (achieved / peak) if achieved else None,
+                "traffic": None, "launches_timed": int(upd_n), "avg_launch_ms": upd_ms / upd_n if upd_n else None,
+                "share_of_step": upd_ms / (dev_ms * 1.0) if dev_ms else None,
+                "peak_source": "cuBLAS DGEMM 8192^3 via torch.matmul(float64), best of 5, measured in this run "
+                               "(MEASURED_PEAKS.json has no FP64 entry)"}
+        cpu = None
+        if not args.no_cpu_baseline:
+            cnt = cpu_counts_small()
+            r2 = np.random.default_rng(1)
+            cpu_step(1000, r2)
+            a, b = cpu_step(args.n, r2)
+            t_iter = cnt["ll"] * a + cnt["grad"] * b
+            cpu = {"value": 1.0 / t_iter, "unit": "iters/s", "cores": cpu_cores(), "kind": "port",
+                   "sample": f"1 ESS likelihood ({a:.2f}s) + 1 llik with gradient ({b:.2f}s) at n={args.n}, D=16 on "
+                             f"the host, extrapolated with the oracle chain's counts at n=250 ({cnt['ll']} "
+                             f"factorisations + {cnt['grad']} gradient evaluations per SEM iteration); BLAS: "
+                             f"{blas_info()}"}
+        line = {"metric": METRIC, "value": value, "unit": "iters/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": workload_config(args, world),
+                "e2e": {"value": e2e, "unit": "iters/s", "h2d_bytes_per_step": h2d // args.steps,
+                        "d2h_bytes_per_step": d2h // args.steps},
+                "gpu_launches": int(launches), "ess_proposals_per_step": nprop / args.steps, "roofline": roof,
+                "cpu_baseline": cpu, "clocks": clocks.summary(), "predict": predict}
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n", type=int, default=5000, help="training points (BASELINE config 3: 5000)")
+    ap.add_argument("--predict-points", type=int, default=2048, help="test points PER GPU for the predict metric")
+    ap.add_argument("--predict-imputations", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -42,6 +42,8 @@ _PROTOS = {
     "dgpb_version": (ctypes.c_int, []),
     "dgpb_launch_count": (c_i64, []),
     "dgpb_sizeof_node": (c_i64, []),
+    "dgpb_profile": (ctypes.c_int, [ctypes.c_int]),
+    "dgpb_profile_read": (ctypes.c_int, [c_vp]),
     "dgpb_ws_create": (ctypes.c_int, [ctypes.POINTER(c_vp), ctypes.c_int]),
     "dgpb_ws_destroy": (ctypes.c_int, [c_vp]),
     "dgpb_ws_bytes": (c_i64, [c_vp]),
@@ -124,6 +126,7 @@ def check(status):
 # device plumbing (torch = allocator + streams only)
 # ------------------------------------------------------------------------------------------------
 _tls = threading.local()
+COUNTERS = {"h2d": 0, "d2h": 0}  # bytes moved by to_dev / to_host (bench.py's e2e accounting)
 
 
 def torch_mod():
@@ -166,7 +169,14 @@ def to_dev(a, dtype=None):
         return t.contiguous()
     a = np.ascontiguousarray(a, dtype=dtype if dtype is not None else (np.int64 if np.issubdtype(
         np.asarray(a).dtype, np.integer) else np.float64))
+    COUNTERS["h2d"] += a.nbytes
     return torch.from_numpy(a).to(device(), non_blocking=False)
+
+
+def to_host(t):
+    """device tensor -> numpy (counts the bytes for the end-to-end accounting)."""
+    COUNTERS["d2h"] += t.numel() * t.element_size()
+    return t.detach().cpu().numpy()
 
 
 def empty(shape, dtype="f8"):

@@ -588,6 +588,28 @@ int assemble(const Geom& g, const KernelDev* kds, const double* const* ys, const
     return DGPB_OK;
 }
 
+// ---- optional launch profiler (bench.py roofline): CUDA-event pairs around every trailing-update launch ----
+struct UpdateProfiler {
+    bool on = false;
+    std::vector<cudaEvent_t> ev;   // pairs
+    int used = 0;                  // events in flight
+    double ms = 0.0, launches = 0.0, flops = 0.0;
+    cudaStream_t last = nullptr;
+    int drain() {
+        if (used == 0) return DGPB_OK;
+        DGPB_CUDA_TRY(cudaEventSynchronize(ev[used - 1]));
+        for (int i = 0; i < used; i += 2) {
+            float t = 0.f;
+            DGPB_CUDA_TRY(cudaEventElapsedTime(&t, ev[i], ev[i + 1]));
+            ms += t;
+            launches += 1.0;
+        }
+        used = 0;
+        return DGPB_OK;
+    }
+};
+static UpdateProfiler g_prof;
+
 int factorize(const Geom& g, const Batch& bt, int B, cudaStream_t st) {
     DGPB_TRY(configure_once());
     for (int k0 = 0; k0 < g.npad; k0 += NB) {
@@ -600,8 +622,18 @@ int factorize(const Geom& g, const Batch& bt, int B, cudaStream_t st) {
         if (rows > 0) {
             const int nt = (int)cdiv(rows, TM);
             dim3 ug((unsigned)(nt * (nt + 1) / 2), 1, (unsigned)B);
+            if (g_prof.on) {
+                if (g_prof.used + 2 > (int)g_prof.ev.size()) DGPB_TRY(g_prof.drain());
+                DGPB_CUDA_TRY(cudaEventRecord(g_prof.ev[g_prof.used], st));
+            }
             update_kernel<<<ug, 256, kUpdateSmem, st>>>(bt, g.ld, k0, k1, row_hi);
             DGPB_LAUNCHED();
+            if (g_prof.on) {
+                DGPB_CUDA_TRY(cudaEventRecord(g_prof.ev[g_prof.used + 1], st));
+                g_prof.used += 2;
+                // algorithmic work of this launch: lower triangle of the rows x rows window, rank-NB update
+                g_prof.flops += (double)B * 0.5 * (double)rows * (double)(rows + 1) * 2.0 * NB;
+            }
         }
     }
     return DGPB_OK;
@@ -768,6 +800,31 @@ int dgpb_mvn_draw(dgpb_ws* ws, const dgpb_node* node, int64_t n, const double* z
         set_error("covariance is not positive definite (pivot %d)", info_host[0]);
         return DGPB_NOT_PD;
     }
+    return DGPB_OK;
+}
+
+int dgpb_profile(int on) {
+    if (on && g_prof.ev.empty()) {
+        g_prof.ev.resize(4096);
+        for (auto& e : g_prof.ev) DGPB_CUDA_TRY(cudaEventCreate(&e));
+    }
+    if (on) {
+        g_prof.used = 0;
+        g_prof.ms = g_prof.launches = g_prof.flops = 0.0;
+    } else {
+        DGPB_TRY(g_prof.drain());
+    }
+    g_prof.on = on != 0;
+    return DGPB_OK;
+}
+
+int dgpb_profile_read(double* out_host) {
+    DGPB_REQUIRE(out_host != nullptr, "NULL argument");
+    DGPB_TRY(g_prof.drain());
+    out_host[0] = g_prof.ms;
+    out_host[1] = g_prof.launches;
+    out_host[2] = g_prof.flops;
+    out_host[3] = 0.0;
     return DGPB_OK;
 }
 

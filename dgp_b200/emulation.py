@@ -110,13 +110,13 @@ class emulator:
             if full_layer:
                 out = []
                 for l in range(self.n_layer):
-                    mu_l = torch.stack([layers_all[s][l][0] for s in range(S)], 0).cpu().numpy()
-                    va_l = torch.stack([layers_all[s][l][1] for s in range(S)], 0).cpu().numpy()
+                    mu_l = L.to_host(torch.stack([layers_all[s][l][0] for s in range(S)], 0))
+                    va_l = L.to_host(torch.stack([layers_all[s][l][1] for s in range(S)], 0))
                     draws = np.random.normal(np.repeat(mu_l, sample_size, 0), np.sqrt(np.repeat(va_l, sample_size, 0)))
                     out.append(list(draws.transpose(2, 1, 0)))
                 return out
-            mu_s = torch.stack(means, 0).cpu().numpy()
-            va_s = torch.stack(variances, 0).cpu().numpy()
+            mu_s = L.to_host(torch.stack(means, 0))
+            va_s = L.to_host(torch.stack(variances, 0))
             draws = np.random.normal(np.repeat(mu_s, sample_size, 0), np.sqrt(np.repeat(va_s, sample_size, 0)))
             return list(draws.transpose(2, 1, 0))
         if method != 'mean_var':
@@ -127,7 +127,7 @@ class emulator:
             mu, s2 = torch.empty_like(ms[0]), torch.empty_like(ms[0])
             L.check(lib.dgpb_aggregate(L.ptr(ms), L.ptr(vs), ms.shape[0], ms[0].numel(), L.ptr(mu), L.ptr(s2),
                                        L.stream()))
-            return mu.cpu().numpy(), s2.cpu().numpy()
+            return L.to_host(mu), L.to_host(s2)
 
         if full_layer:
             mu, sigma2 = [], []
@@ -138,7 +138,7 @@ class emulator:
             return mu, sigma2
         if aggregation:
             return agg(means, variances)
-        return [t.cpu().numpy() for t in means], [t.cpu().numpy() for t in variances]
+        return [L.to_host(t) for t in means], [L.to_host(t) for t in variances]
 
     def ppredict(self, x, method='mean_var', full_layer=False, sample_size=50, m=50, chunk_num=None, core_num=None):
         """The reference splits test points over a process pool (emulation.py:578-629); one GPU replaces the

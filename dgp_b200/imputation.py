@@ -108,7 +108,7 @@ class _DeviceLayers:
     def write_back(self):
         """Imputed layers -> `kernel.output` of their nodes and `kernel.input` of the nodes they feed."""
         for l in range(len(self.all_layer) - 1):
-            Fl = self.F[l].cpu().numpy()
+            Fl = L.to_host(self.F[l])
             for k, kern in enumerate(self.all_layer[l]):
                 kern.output[:, 0] = Fl[k]
             for kern in self.all_layer[l + 1]:

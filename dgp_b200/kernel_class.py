@@ -245,8 +245,8 @@ class kernel:
         L.check(lib.dgpb_kmatrix(L.ptr(X), n, D, lptr, len(larr), float(self.nugget[0]), None, L.KIND[self.name],
                                  int(bool(self.nugget_est)), L.ptr(K), L.ptr(dK), L.stream()))
         if fod_eval:
-            return K.cpu().numpy(), dK.cpu().numpy()
-        return K.cpu().numpy()
+            return L.to_host(K), L.to_host(dK)
+        return L.to_host(K)
 
     # ---- 2. dense likelihoods ----------------------------------------------------------------------
     def log_likelihood_func(self):
@@ -455,24 +455,24 @@ class kernel:
     def gp_prediction(self, x, z):
         """GP predictive mean/variance at deterministic inputs (kernel_class.py:587-625)."""
         m, v = self._gp_prediction_dev(L.to_dev(x), None if z is None else L.to_dev(z))
-        return m.cpu().numpy(), v.cpu().numpy()
+        return L.to_host(m), L.to_host(v)
 
     def linkgp_prediction(self, m, v, z):
         """Linked-GP moments for Gaussian inputs N(m, diag v) (kernel_class.py:627-670)."""
         mo, vo = self._linkgp_prediction_dev(L.to_dev(m), L.to_dev(v), None if z is None else L.to_dev(z))
-        return mo.cpu().numpy(), vo.cpu().numpy()
+        return L.to_host(mo), L.to_host(vo)
 
     def linkgp_prediction_full(self, m, v, m_z, v_z, z):
         """As `linkgp_prediction` with some connected inputs also Gaussian (kernel_class.py:672-733)."""
         mo, vo = self._linkgp_prediction_full_dev(L.to_dev(m), L.to_dev(v), L.to_dev(m_z), L.to_dev(v_z),
                                                   None if z is None else L.to_dev(z))
-        return mo.cpu().numpy(), vo.cpu().numpy()
+        return L.to_host(mo), L.to_host(vo)
 
 
 def _as_numpy(v):
     if v is None or isinstance(v, np.ndarray):
         return v
-    return v.detach().cpu().numpy()
+    return L.to_host(v)
 
 
 def combine(*layers):

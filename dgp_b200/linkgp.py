@@ -233,12 +233,12 @@ class lgp:
             ms = torch.stack([per_imp[s][l][k][0] for s in range(S)], 0).contiguous()
             vs = torch.stack([per_imp[s][l][k][1] for s in range(S)], 0).contiguous()
             if method == 'sampling':
-                mu_s, va_s = ms.cpu().numpy(), vs.cpu().numpy()
+                mu_s, va_s = L.to_host(ms), L.to_host(vs)
                 draws = np.random.normal(np.repeat(mu_s, sample_size, 0), np.sqrt(np.repeat(va_s, sample_size, 0)))
                 return draws.transpose(2, 1, 0), None
             mu, s2 = torch.empty_like(ms[0]), torch.empty_like(ms[0])
             L.check(lib.dgpb_aggregate(L.ptr(ms), L.ptr(vs), S, ms[0].numel(), L.ptr(mu), L.ptr(s2), L.stream()))
-            return mu.cpu().numpy(), s2.cpu().numpy()
+            return L.to_host(mu), L.to_host(s2)
 
         layers = range(self.L) if full_layer else [self.L - 1]
         mus, s2s = [], []

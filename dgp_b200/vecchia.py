@@ -23,7 +23,7 @@ def get_pred_nn(query, x, m=50, method='exact', **_):
     """vecchia.py:20-40.  Only the exact search exists here (the reference's default)."""
     if method != 'exact':
         raise NotImplementedError("dgp_b200 implements the exact neighbour search only")
-    return get_pred_nn_dev(L.to_dev(query, np.float64), L.to_dev(x, np.float64), m).cpu().numpy()
+    return L.to_host(get_pred_nn_dev(L.to_dev(query, np.float64), L.to_dev(x, np.float64), m))
 
 
 def nn(x, m, method='exact', **_):
@@ -36,7 +36,7 @@ def nn(x, m, method='exact', **_):
     m = min(int(m), n - 1)
     NN = L.empty((n, m + 1), "i8")
     L.check(L.load().dgpb_knn_ordered(L.ptr(xd), n, D, m, L.ptr(NN), L.stream()))
-    return NN.cpu().numpy()
+    return L.to_host(NN)
 
 
 def _prep(X, y, NNarray, nugget_diag):
@@ -77,7 +77,7 @@ def L_matrix(X, NNarray, length, nugget, name):
     out = L.empty((Xd.shape[0], NNd.shape[1]))
     L.check(L.load().dgpb_vecchia_Lmatrix(L.ptr(Xd), L.ptr(NNd), Xd.shape[0], Xd.shape[1], NNd.shape[1], lptr,
                                           len(larr), float(nugget), L.KIND[name], L.ptr(out), L.stream()))
-    return out.cpu().numpy()
+    return L.to_host(out)
 
 
 def fmvn_sp(X, NNarray, scale, length, nugget, name, z=None):
@@ -93,4 +93,4 @@ def fmvn_sp(X, NNarray, scale, length, nugget, name, z=None):
     L.check(L.load().dgpb_vecchia_mvn_draw(L.ptr(Xd), L.ptr(NNd), n, Xd.shape[1], NNd.shape[1], lptr, len(larr),
                                            float(scale), float(nugget), L.KIND[name], L.ptr(zd), L.ptr(out),
                                            L.stream()))
-    return out.cpu().numpy()
+    return L.to_host(out)

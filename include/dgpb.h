@@ -201,6 +201,11 @@ int dgpb_aggregate(const double* means, const double* vars, int64_t S, int64_t l
 int dgpb_dgemm_nt(const double* A, const double* B, double* C, int64_t M, int64_t N, int64_t K, void* stream);
 /* in-place lower Cholesky of the n x n matrix A (ld = n); info_host = 0 or failing column + 1 */
 int dgpb_potrf(dgpb_ws* ws, double* A, int64_t n, int* info_host, void* stream);
+/* Launch profiler for the roofline line of bench.py: while on, every trailing-update (SYRK) launch of the
+ * blocked factorisation is bracketed by CUDA events on its stream.  dgpb_profile_read fills
+ * out_host[0..3] = {total ms, launches timed, algorithmic FLOPs of those launches, 0}. */
+int dgpb_profile(int on);
+int dgpb_profile_read(double* out_host);
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 int64_t dgpb_launch_count(void);
 
