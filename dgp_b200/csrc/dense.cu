@@ -10,6 +10,8 @@
 // (log_likelihood_func), :735-748 (compute_stats); dgpsi/functions.py:16-121.
 #include "dense.cuh"
 
+#include <algorithm>
+
 namespace dgpb {
 
 // ------------------------------------------------------------------------------------------------
@@ -173,22 +175,26 @@ __global__ void __launch_bounds__(256, 1) panel_kernel(Batch bt, int64_t ld, int
     extern __shared__ double smem[];
     double* sL = smem;               // 64 x LDS : diagonal block -> L_kk
     double* sD = sL + 64 * LDS;      // 64 x LDS : inv(L_kk)
-    double* sA = sD + 64 * LDS;      // 128 x LDS: this CTA's panel rows
+    double* sA = sD + 64 * LDS;      // 128 x LDS: panel rows being solved
     double* sT = sA + TM * LDS;      // 32 x 33 scratch (also 2 x 16 x 33)
     __shared__ double col[64];
     const int tid = threadIdx.x;
     double* __restrict__ T = bt.T[blockIdx.z];
-    const int r0 = row_lo + blockIdx.x * TM;
+    const int ntiles = row_hi > row_lo ? (row_hi - row_lo + TM - 1) / TM : 0;
 
-    // (1) asynchronous load of the row tile; overlaps the diagonal-block factorisation
-    for (int c = tid; c < TM * 32; c += 256) {
-        int lr = c >> 5, ch = c & 31;
-        int gr = r0 + lr;
-        bool ok = gr < row_hi;
-        const double* src = T + (int64_t)(ok ? gr : k0) * ld + k0 + ch * 2;
-        cp_async16(&sA[lr * LDS + ch * 2], src, ok);
-    }
-    cp_async_commit();
+    // (1) asynchronous load of this CTA's first row tile; overlaps the diagonal-block factorisation
+    auto load_tile = [&](int tile) {
+        const int r0 = row_lo + tile * TM;
+        for (int c = tid; c < TM * 32; c += 256) {
+            int lr = c >> 5, ch = c & 31;
+            int gr = r0 + lr;
+            bool ok = gr < row_hi;
+            const double* src = T + (int64_t)(ok ? gr : k0) * ld + k0 + ch * 2;
+            cp_async16(&sA[lr * LDS + ch * 2], src, ok);
+        }
+        cp_async_commit();
+    };
+    if ((int)blockIdx.x < ntiles) load_tile(blockIdx.x);
 
     // (2) diagonal block (lower part) into shared memory
     for (int idx = tid; idx < 64 * 64; idx += 256) {
@@ -244,36 +250,41 @@ __global__ void __launch_bounds__(256, 1) panel_kernel(Batch bt, int64_t ld, int
         if (tid < 64) dg[k0 + tid] = sL[tid * LDS + tid];
     }
 
-    // (5) X = A * inv(L)'  on the FP64 tensor path: warp w owns rows [16w, 16w+16), all 64 columns
-    cp_async_wait<0>();
-    __syncthreads();
-    if (r0 >= row_hi) return;
+    // (5) X = A * inv(L)'  on the FP64 tensor path for every row tile owned by this CTA (grid-stride), so
+    //     the redundant factorisation above is paid once per CTA and the grid stays within one wave.
     const int w = tid >> 5, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
-    double acc[2][8][2];
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int r0 = row_lo + tile * TM;
+        cp_async_wait<0>();
+        __syncthreads();
+        double acc[2][8][2];
 #pragma unroll
-    for (int mi = 0; mi < 2; ++mi)
+        for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
-        for (int nj = 0; nj < 8; ++nj) acc[mi][nj][0] = acc[mi][nj][1] = 0.0;
+            for (int nj = 0; nj < 8; ++nj) acc[mi][nj][0] = acc[mi][nj][1] = 0.0;
 #pragma unroll 4
-    for (int kk = 0; kk < 64; kk += 4) {
-        double a[2];
+        for (int kk = 0; kk < 64; kk += 4) {
+            double a[2];
 #pragma unroll
-        for (int mi = 0; mi < 2; ++mi) a[mi] = sA[(16 * w + 8 * mi + g) * LDS + kk + t4];
+            for (int mi = 0; mi < 2; ++mi) a[mi] = sA[(16 * w + 8 * mi + g) * LDS + kk + t4];
 #pragma unroll
-        for (int nj = 0; nj < 8; ++nj) {
-            double b = sD[(8 * nj + g) * LDS + kk + t4];
+            for (int nj = 0; nj < 8; ++nj) {
+                double b = sD[(8 * nj + g) * LDS + kk + t4];
 #pragma unroll
-            for (int mi = 0; mi < 2; ++mi) dmma884(acc[mi][nj][0], acc[mi][nj][1], a[mi], b);
+                for (int mi = 0; mi < 2; ++mi) dmma884(acc[mi][nj][0], acc[mi][nj][1], a[mi], b);
+            }
         }
-    }
+        __syncthreads();  // every warp is done reading sA before the next tile overwrites it
+        if (tile + (int)gridDim.x < ntiles) load_tile(tile + gridDim.x);
 #pragma unroll
-    for (int mi = 0; mi < 2; ++mi) {
-        int gr = r0 + 16 * w + 8 * mi + g;
-        if (gr < row_hi) {
+        for (int mi = 0; mi < 2; ++mi) {
+            int gr = r0 + 16 * w + 8 * mi + g;
+            if (gr < row_hi) {
 #pragma unroll
-            for (int nj = 0; nj < 8; ++nj)
-                *reinterpret_cast<double2*>(&T[(int64_t)gr * ld + k0 + 8 * nj + 2 * t4]) =
-                    make_double2(acc[mi][nj][0], acc[mi][nj][1]);
+                for (int nj = 0; nj < 8; ++nj)
+                    *reinterpret_cast<double2*>(&T[(int64_t)gr * ld + k0 + 8 * nj + 2 * t4]) =
+                        make_double2(acc[mi][nj][0], acc[mi][nj][1]);
+            }
         }
     }
 }
@@ -281,50 +292,70 @@ __global__ void __launch_bounds__(256, 1) panel_kernel(Batch bt, int64_t ld, int
 constexpr size_t kPanelSmem = (size_t)(64 * LDS * 2 + TM * LDS + 32 * 33 + 16) * sizeof(double);
 
 // ------------------------------------------------------------------------------------------------
-// 3. trailing update  C[i,j] -= P_i P_j'  (lower tiles of the active window), FP64 mma, K = NB
+// 3. trailing update  C[r,c] -= P_r P_c'  over the lower triangle of rows/cols [lo, row_hi) restricted to
+//    columns [lo, col_hi), FP64 mma, K = NB.
 // ------------------------------------------------------------------------------------------------
-// 128x128 tile per CTA, 8 warps as 2 (rows) x 4 (cols), warp tile 64x32 = 8x4 m8n8 accumulators.
-// The accumulators are INITIALISED with the C tile (global loads issued before the panel data is
-// needed) and the A fragments are negated, so D = (-A)B' + C is a single DMMA chain per k-step.
-__global__ void __launch_bounds__(256, 1) update_kernel(Batch bt, int64_t ld, int k0, int row_lo, int row_hi) {
+// 128 (rows) x 64 (cols) tile per CTA, 8 warps as 4 x 2, warp tile 32x32 = 4x4 m8n8 accumulators (64
+// registers), so TWO CTAs fit per SM (<= 128 registers, 2 x 108 KB shared memory): while one CTA waits for
+// its C tile / panel rows or drains its stores, the other keeps the DMMA pipe busy.  The accumulators are
+// INITIALISED with the C tile (global loads issued before the panel data is needed) and the A fragments
+// are negated, so D = (-A)B' + C is a single DMMA chain per k-step.  `narrow` = only the first 64-column
+// block (the next panel's columns: the look-ahead part of the update).
+constexpr int UBN = 64;
+constexpr int ULD = 36;  // 32-wide K chunks, 36 % 16 == 4
+constexpr size_t kUpdateSmem = (size_t)(2 * (TM + UBN) * ULD) * sizeof(double);
+
+__global__ void __launch_bounds__(256, 2) update_kernel(Batch bt, int64_t ld, int k0, int lo, int row_hi, int col_hi,
+                                                        int narrow) {
     extern __shared__ double smem[];
-    int t = blockIdx.x;
-    int ti = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
-    while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
-    while (ti * (ti + 1) / 2 > t) --ti;
-    const int tj = t - ti * (ti + 1) / 2;
-    double* sA = smem;
-    double* sB = (ti == tj) ? smem : smem + TM * LDS;
+    int ti, tj;
+    if (narrow) {
+        ti = blockIdx.x;
+        tj = 0;
+    } else {
+        // row tile ti owns column tiles 0 .. 2 ti + 1  ->  ti (ti + 1) tiles precede it
+        const int t = blockIdx.x;
+        ti = (int)((sqrt(4.0 * (double)t + 1.0) - 1.0) * 0.5);
+        while ((ti + 1) * (ti + 2) <= t) ++ti;
+        while (ti * (ti + 1) > t) --ti;
+        tj = t - ti * (ti + 1);
+    }
+    const int ra = lo + ti * TM, rb = lo + tj * UBN;
+    if (rb >= col_hi || ra >= row_hi) return;
     const int tid = threadIdx.x;
     double* __restrict__ T = bt.T[blockIdx.z];
-    const int ra = row_lo + ti * TM, rb = row_lo + tj * TM;
+    auto sA = [&](int st) { return smem + (size_t)st * (TM + UBN) * ULD; };
+    auto sB = [&](int st) { return smem + (size_t)st * (TM + UBN) * ULD + TM * ULD; };
 
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
+        double* a = sA(half);
+        double* b = sB(half);
         for (int c = tid; c < TM * 16; c += 256) {
-            int lr = c >> 4, colo = half * 32 + (c & 15) * 2;
+            int lr = c >> 4, colo = (c & 15) * 2;
             int gr = ra + lr;
             bool ok = gr < row_hi;
-            cp_async16(&sA[lr * LDS + colo], T + (int64_t)(ok ? gr : k0) * ld + k0 + colo, ok);
-            if (ti != tj) {
-                int gq = rb + lr;
-                bool okb = gq < row_hi;
-                cp_async16(&sB[lr * LDS + colo], T + (int64_t)(okb ? gq : k0) * ld + k0 + colo, okb);
-            }
+            cp_async16(&a[lr * ULD + colo], T + (int64_t)(ok ? gr : k0) * ld + k0 + half * 32 + colo, ok);
+        }
+        for (int c = tid; c < UBN * 16; c += 256) {
+            int lr = c >> 4, colo = (c & 15) * 2;
+            int gq = rb + lr;
+            bool ok = gq < col_hi;
+            cp_async16(&b[lr * ULD + colo], T + (int64_t)(ok ? gq : k0) * ld + k0 + half * 32 + colo, ok);
         }
         cp_async_commit();
     }
 
     const int w = tid >> 5, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
-    const int wm = w >> 2, wn = w & 3;
-    double acc[8][4][2];
+    const int wm = w >> 1, wn = w & 1;
+    double acc[4][4][2];
 #pragma unroll
-    for (int mi = 0; mi < 8; ++mi) {
-        int gr = ra + 64 * wm + 8 * mi + g;
+    for (int mi = 0; mi < 4; ++mi) {
+        int gr = ra + 32 * wm + 8 * mi + g;
 #pragma unroll
         for (int nj = 0; nj < 4; ++nj) {
             int gc = rb + 32 * wn + 8 * nj + 2 * t4;
-            if (gr < row_hi && gc < row_hi) {
+            if (gr < row_hi && gc < col_hi) {
                 double2 v = *reinterpret_cast<const double2*>(&T[(int64_t)gr * ld + gc]);
                 acc[mi][nj][0] = v.x;
                 acc[mi][nj][1] = v.y;
@@ -338,32 +369,33 @@ __global__ void __launch_bounds__(256, 1) update_kernel(Batch bt, int64_t ld, in
     for (int half = 0; half < 2; ++half) {
         if (half == 0) cp_async_wait<1>(); else cp_async_wait<0>();
         __syncthreads();
+        const double* a_s = sA(half);
+        const double* b_s = sB(half);
 #pragma unroll 2
-        for (int kk = half * 32; kk < half * 32 + 32; kk += 4) {
-            double a[8], b[4];
+        for (int kk = 0; kk < 32; kk += 4) {
+            double a[4], b[4];
 #pragma unroll
-            for (int mi = 0; mi < 8; ++mi) a[mi] = -sA[(64 * wm + 8 * mi + g) * LDS + kk + t4];
+            for (int mi = 0; mi < 4; ++mi) a[mi] = -a_s[(32 * wm + 8 * mi + g) * ULD + kk + t4];
 #pragma unroll
-            for (int nj = 0; nj < 4; ++nj) b[nj] = sB[(32 * wn + 8 * nj + g) * LDS + kk + t4];
+            for (int nj = 0; nj < 4; ++nj) b[nj] = b_s[(32 * wn + 8 * nj + g) * ULD + kk + t4];
 #pragma unroll
-            for (int mi = 0; mi < 8; ++mi)
+            for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
                 for (int nj = 0; nj < 4; ++nj) dmma884(acc[mi][nj][0], acc[mi][nj][1], a[mi], b[nj]);
         }
     }
 
 #pragma unroll
-    for (int mi = 0; mi < 8; ++mi) {
-        int gr = ra + 64 * wm + 8 * mi + g;
+    for (int mi = 0; mi < 4; ++mi) {
+        int gr = ra + 32 * wm + 8 * mi + g;
 #pragma unroll
         for (int nj = 0; nj < 4; ++nj) {
             int gc = rb + 32 * wn + 8 * nj + 2 * t4;
-            if (gr < row_hi && gc < row_hi)
+            if (gr < row_hi && gc < col_hi)
                 *reinterpret_cast<double2*>(&T[(int64_t)gr * ld + gc]) = make_double2(acc[mi][nj][0], acc[mi][nj][1]);
         }
     }
 }
-constexpr size_t kUpdateSmem = (size_t)(2 * TM * LDS) * sizeof(double);
 
 // ------------------------------------------------------------------------------------------------
 // 4. reductions / extraction
@@ -610,32 +642,83 @@ struct UpdateProfiler {
 };
 static UpdateProfiler g_prof;
 
+// Two-stream look-ahead: the caller's stream carries the critical path (panel k, then the NARROW update of
+// the next panel's 64 columns), a side stream carries the BULK update of everything to the right.  Panel k+1
+// therefore overlaps bulk update k.  Dependencies:
+//   bulk_k   needs panel_k (event) and bulk_{k-1} (side-stream order);
+//   narrow_k needs panel_k (main-stream order) and bulk_{k-1} (event: both write columns [k1, k1+64)).
+struct LookAhead {
+    cudaStream_t side = nullptr;
+    std::vector<cudaEvent_t> ev;
+    int init(size_t need) {
+        if (!side) DGPB_CUDA_TRY(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+        while (ev.size() < need) {
+            cudaEvent_t e;
+            DGPB_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            ev.push_back(e);
+        }
+        return DGPB_OK;
+    }
+};
+static thread_local LookAhead g_la;
+
 int factorize(const Geom& g, const Batch& bt, int B, cudaStream_t st) {
     DGPB_TRY(configure_once());
+    const int nsteps = g.npad / NB;
+    DGPB_TRY(g_la.init(2 * (size_t)nsteps + 4));
+    cudaStream_t side = g_la.side;
+    int evi = 0;
+    // the side stream starts after everything already queued on the caller's stream
+    DGPB_CUDA_TRY(cudaEventRecord(g_la.ev[evi], st));
+    DGPB_CUDA_TRY(cudaStreamWaitEvent(side, g_la.ev[evi], 0));
+    ++evi;
+    cudaEvent_t prev_bulk = nullptr;
+    const int max_ctas = std::max(1, 148 / B);
     for (int k0 = 0; k0 < g.npad; k0 += NB) {
         const int k1 = k0 + NB;
         const int row_hi = g.aug ? g.npad + 1 + k1 : g.R;
         const int rows = row_hi - k1;
-        dim3 pg((unsigned)(rows > 0 ? cdiv(rows, TM) : 1), 1, (unsigned)B);
+        const int ptiles = rows > 0 ? (int)cdiv(rows, TM) : 1;
+        dim3 pg((unsigned)std::min(ptiles, max_ctas), 1, (unsigned)B);
         panel_kernel<<<pg, 256, kPanelSmem, st>>>(bt, g.ld, g.npad, k0, k1, row_hi);
         DGPB_LAUNCHED();
-        if (rows > 0) {
-            const int nt = (int)cdiv(rows, TM);
-            dim3 ug((unsigned)(nt * (nt + 1) / 2), 1, (unsigned)B);
+        if (rows <= 0) continue;
+        cudaEvent_t ev_panel = g_la.ev[evi++];
+        DGPB_CUDA_TRY(cudaEventRecord(ev_panel, st));
+        // ---- bulk: columns [k1 + 64, row_hi) on the side stream
+        const int brows = row_hi - (k1 + UBN);
+        cudaEvent_t this_bulk = nullptr;
+        if (brows > 0) {
+            DGPB_CUDA_TRY(cudaStreamWaitEvent(side, ev_panel, 0));
+            const int ntr = (int)cdiv(brows, TM);
+            dim3 ug((unsigned)(ntr * (ntr + 1)), 1, (unsigned)B);
             if (g_prof.on) {
                 if (g_prof.used + 2 > (int)g_prof.ev.size()) DGPB_TRY(g_prof.drain());
-                DGPB_CUDA_TRY(cudaEventRecord(g_prof.ev[g_prof.used], st));
+                DGPB_CUDA_TRY(cudaEventRecord(g_prof.ev[g_prof.used], side));
             }
-            update_kernel<<<ug, 256, kUpdateSmem, st>>>(bt, g.ld, k0, k1, row_hi);
+            update_kernel<<<ug, 256, kUpdateSmem, side>>>(bt, g.ld, k0, k1 + UBN, row_hi, row_hi, 0);
             DGPB_LAUNCHED();
             if (g_prof.on) {
-                DGPB_CUDA_TRY(cudaEventRecord(g_prof.ev[g_prof.used + 1], st));
+                DGPB_CUDA_TRY(cudaEventRecord(g_prof.ev[g_prof.used + 1], side));
                 g_prof.used += 2;
-                // algorithmic work of this launch: lower triangle of the rows x rows window, rank-NB update
-                g_prof.flops += (double)B * 0.5 * (double)rows * (double)(rows + 1) * 2.0 * NB;
+                g_prof.flops += (double)B * 0.5 * (double)brows * (double)(brows + 1) * 2.0 * NB;
             }
+            this_bulk = g_la.ev[evi++];
+            DGPB_CUDA_TRY(cudaEventRecord(this_bulk, side));
         }
+        // ---- narrow: the next panel's columns [k1, k1 + 64) on the critical path
+        if (prev_bulk) DGPB_CUDA_TRY(cudaStreamWaitEvent(st, prev_bulk, 0));
+        {
+            const int ntr = (int)cdiv(rows, TM);
+            dim3 ug((unsigned)ntr, 1, (unsigned)B);
+            update_kernel<<<ug, 256, kUpdateSmem, st>>>(bt, g.ld, k0, k1, row_hi, std::min(k1 + UBN, row_hi), 1);
+            DGPB_LAUNCHED();
+        }
+        prev_bulk = this_bulk;
     }
+    // join: later work on the caller's stream sees every bulk update
+    DGPB_CUDA_TRY(cudaEventRecord(g_la.ev[evi], side));
+    DGPB_CUDA_TRY(cudaStreamWaitEvent(st, g_la.ev[evi], 0));
     return DGPB_OK;
 }
 
