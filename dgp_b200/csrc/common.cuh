@@ -167,6 +167,23 @@ __device__ __forceinline__ double corr_pair(int kind, int D, FA a, FB b) {
     }
 }
 
+// linear index t over the lower triangle (row-major: 0 -> (0,0), 1 -> (1,0), 2 -> (1,1), ...) -> (i, j).
+// FP32 sqrt + integer correction: the FP64 sqrt competed with the DMMA stream for the FP64 pipe and was 15%
+// of the trailing-update kernel's stall samples (profiles/r1_update_v2_ncu.md).
+__device__ __forceinline__ void tri_index(int t, int& i, int& j) {
+    i = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+    while ((i + 1) * (i + 2) / 2 <= t) ++i;
+    while (i * (i + 1) / 2 > t) --i;
+    j = t - i * (i + 1) / 2;
+}
+// linear index over the "double-width" staircase: row i owns 2 i + 2 entries -> i (i + 1) precede it
+__device__ __forceinline__ void stair_index(int t, int& i, int& j) {
+    i = (int)((sqrtf(4.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+    while ((i + 1) * (i + 2) <= t) ++i;
+    while (i * (i + 1) > t) --i;
+    j = t - i * (i + 1);
+}
+
 // block-wide deterministic sum (fixed tree order); result valid in thread 0 (and broadcast via smem)
 template <int THREADS>
 __device__ __forceinline__ double block_sum(double v, double* sred) {

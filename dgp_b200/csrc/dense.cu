@@ -46,11 +46,9 @@ __global__ void __launch_bounds__(256) kbuild_kernel(KernelDev kd, double* __res
     __shared__ double xi[kMaxDim][64];
     __shared__ double xj[kMaxDim][64];
     const int tid = threadIdx.x;
-    int t = blockIdx.x;
-    int ti = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
-    while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
-    while (ti * (ti + 1) / 2 > t) --ti;
-    const int tj = t - ti * (ti + 1) / 2;
+    const int t = blockIdx.x;
+    int ti, tj;
+    tri_index(t, ti, tj);
     const int D = kd.D;
     for (int idx = tid; idx < D * 64; idx += 256) {
         int d = idx >> 6, l = idx & 63;
@@ -171,60 +169,52 @@ __device__ __forceinline__ void tri_inv_offdiag(const double* sL, double* sD, do
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(256, 1) panel_kernel(Batch bt, int64_t ld, int npad, int k0, int row_lo, int row_hi) {
+// (a) diagonal block: ONE CTA per matrix.  Thread (pi = tid/4, pc = tid%4) keeps its 16 entries of row pi
+//     (columns 4q+pc) in registers; per column j the owners publish the raw column, everybody scales by 1/d
+//     and applies the rank-1 update in registers -- one barrier and no shared-memory read-modify-write per
+//     column.  Then inv(L_kk) by 16x16 substitution + two block levels.  Results go to the side buffer.
+__global__ void __launch_bounds__(256, 1) potf2_kernel(Batch bt, int64_t ld, int npad, int k0) {
     extern __shared__ double smem[];
-    double* sL = smem;               // 64 x LDS : diagonal block -> L_kk
-    double* sD = sL + 64 * LDS;      // 64 x LDS : inv(L_kk)
-    double* sA = sD + 64 * LDS;      // 128 x LDS: panel rows being solved
-    double* sT = sA + TM * LDS;      // 32 x 33 scratch (also 2 x 16 x 33)
-    __shared__ double col[64];
+    double* sL = smem;
+    double* sD = sL + 64 * LDS;
+    double* sT = sD + 64 * LDS;
+    __shared__ double colv[2][64];
     const int tid = threadIdx.x;
-    double* __restrict__ T = bt.T[blockIdx.z];
-    const int ntiles = row_hi > row_lo ? (row_hi - row_lo + TM - 1) / TM : 0;
-
-    // (1) asynchronous load of this CTA's first row tile; overlaps the diagonal-block factorisation
-    auto load_tile = [&](int tile) {
-        const int r0 = row_lo + tile * TM;
-        for (int c = tid; c < TM * 32; c += 256) {
-            int lr = c >> 5, ch = c & 31;
-            int gr = r0 + lr;
-            bool ok = gr < row_hi;
-            const double* src = T + (int64_t)(ok ? gr : k0) * ld + k0 + ch * 2;
-            cp_async16(&sA[lr * LDS + ch * 2], src, ok);
+    const double* __restrict__ T = bt.T[blockIdx.x];
+    const int pi = tid >> 2, pc = tid & 3;
+    double reg[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+        int k = 4 * q + pc;
+        reg[q] = (k <= pi) ? T[(int64_t)(k0 + pi) * ld + k0 + k] : 0.0;
+    }
+    for (int idx = tid; idx < 64 * LDS; idx += 256) {
+        sL[idx] = 0.0;
+        sD[idx] = 0.0;
+    }
+#pragma unroll
+    for (int j = 0; j < 64; ++j) {
+        const int qj = j >> 2;
+        const bool owner = (pc == (j & 3)) && (pi >= j);
+        if (owner) colv[j & 1][pi] = reg[qj];
+        __syncthreads();
+        const double d = colv[j & 1][j];
+        if (!(d > 0.0) && tid == 0) atomicCAS(&bt.info[blockIdx.x], 0, k0 + j + 1);
+        const double rd = 1.0 / d;
+        const double rs = rsqrt(d);
+        if (pi > j) {
+            const double ci = colv[j & 1][pi] * rd;
+#pragma unroll
+            for (int q = qj; q < 16; ++q) {
+                int k = 4 * q + pc;
+                if (k > j && k <= pi) reg[q] -= ci * colv[j & 1][k];
+            }
         }
-        cp_async_commit();
-    };
-    if ((int)blockIdx.x < ntiles) load_tile(blockIdx.x);
-
-    // (2) diagonal block (lower part) into shared memory
-    for (int idx = tid; idx < 64 * 64; idx += 256) {
-        int i = idx >> 6, j = idx & 63;
-        sL[i * LDS + j] = (j <= i) ? T[(int64_t)(k0 + i) * ld + k0 + j] : 0.0;
-        sD[i * LDS + j] = 0.0;
+        if (owner) sL[pi * LDS + j] = (pi == j) ? d * rs : reg[qj] * rs;
     }
     __syncthreads();
 
-    // (3) unblocked right-looking Cholesky; thread (pi = tid/4, pc = tid%4) owns row pi, columns == pc mod 4
-    const int pi = tid >> 2, pc = tid & 3;
-    for (int j = 0; j < 64; ++j) {
-        double d = sL[j * LDS + j];
-        if (!(d > 0.0) && tid == 0 && blockIdx.x == 0) atomicCAS(&bt.info[blockIdx.z], 0, k0 + j + 1);
-        double sq = sqrt(d);
-        double inv = 1.0 / sq;
-        if (tid < 64) col[tid] = (tid > j) ? sL[tid * LDS + j] * inv : (tid == j ? sq : 0.0);
-        __syncthreads();
-        if (pi > j) {
-            double ci = col[pi];
-            for (int q = (j + 1) >> 2; q <= (pi >> 2); ++q) {
-                int k = 4 * q + pc;
-                if (k > j && k <= pi) sL[pi * LDS + k] -= ci * col[k];
-            }
-        }
-        if (tid < 64 && tid >= j) sL[tid * LDS + j] = col[tid];
-        __syncthreads();
-    }
-
-    // (4) inv(L_kk): 16x16 diagonal blocks by column-parallel substitution, then two block levels
+    // inv(L_kk): 16x16 diagonal blocks by column-parallel substitution, then two block levels
     if (tid < 64) {
         int o = (tid >> 4) * 16, c = tid & 15;
         sD[(o + c) * LDS + o + c] = 1.0 / sL[(o + c) * LDS + o + c];
@@ -236,22 +226,46 @@ __global__ void __launch_bounds__(256, 1) panel_kernel(Batch bt, int64_t ld, int
     }
     __syncthreads();
     {
-        // two independent 16x16 off-diagonal blocks, one per half CTA (uniform barriers: every thread
-        // makes the same calls, only the per-thread block coordinates differ)
         const int half = tid >> 7;
         tri_inv_offdiag(sL, sD, sT + half * 16 * 33, half ? 48 : 16, half ? 32 : 0, 16, tid & 127, 128);
     }
     tri_inv_offdiag(sL, sD, sT, 32, 0, 32, tid, 256);
 
-    if (blockIdx.x == 0) {
-        double* dg = bt.diag[blockIdx.z];
-        double* blk = dg + npad + (size_t)(k0 / NB) * NB * NB;
-        for (int idx = tid; idx < 64 * 64; idx += 256) blk[idx] = sL[(idx >> 6) * LDS + (idx & 63)];
-        if (tid < 64) dg[k0 + tid] = sL[tid * LDS + tid];
+    double* dg = bt.diag[blockIdx.x];
+    double* blk = dg + npad + (size_t)(k0 / NB) * NB * NB;
+    double* dinv = dg + (size_t)npad * (1 + NB);
+    for (int idx = tid; idx < 64 * 64; idx += 256) {
+        blk[idx] = sL[(idx >> 6) * LDS + (idx & 63)];
+        dinv[idx] = sD[(idx >> 6) * LDS + (idx & 63)];
     }
+    if (tid < 64) dg[k0 + tid] = sL[tid * LDS + tid];
+}
 
-    // (5) X = A * inv(L)'  on the FP64 tensor path for every row tile owned by this CTA (grid-stride), so
-    //     the redundant factorisation above is paid once per CTA and the grid stays within one wave.
+// (b) panel rows: X <- X * inv(L_kk)'  on the FP64 tensor path, 128-row tiles, grid-stride over tiles.
+//     105 KB of shared memory and < 128 registers so a CTA co-resides with a trailing-update CTA.
+__global__ void __launch_bounds__(256, 2) trsm_kernel(Batch bt, int64_t ld, int npad, int k0, int row_lo, int row_hi) {
+    extern __shared__ double smem[];
+    double* sD = smem;             // 64 x LDS : inv(L_kk)
+    double* sA = sD + 64 * LDS;    // 128 x LDS: panel rows being solved
+    const int tid = threadIdx.x;
+    double* __restrict__ T = bt.T[blockIdx.z];
+    const double* __restrict__ dinv = bt.diag[blockIdx.z] + (size_t)npad * (1 + NB);
+    const int ntiles = (row_hi - row_lo + TM - 1) / TM;
+    auto load_tile = [&](int tile) {
+        const int r0 = row_lo + tile * TM;
+        for (int c = tid; c < TM * 32; c += 256) {
+            int lr = c >> 5, ch = c & 31;
+            int gr = r0 + lr;
+            bool ok = gr < row_hi;
+            cp_async16(&sA[lr * LDS + ch * 2], T + (int64_t)(ok ? gr : k0) * ld + k0 + ch * 2, ok);
+        }
+        cp_async_commit();
+    };
+    for (int c = tid; c < 64 * 32; c += 256) {
+        int lr = c >> 5, ch = c & 31;
+        cp_async16(&sD[lr * LDS + ch * 2], dinv + lr * 64 + ch * 2, true);
+    }
+    load_tile(blockIdx.x);
     const int w = tid >> 5, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int r0 = row_lo + tile * TM;
@@ -288,8 +302,8 @@ __global__ void __launch_bounds__(256, 1) panel_kernel(Batch bt, int64_t ld, int
         }
     }
 }
-
-constexpr size_t kPanelSmem = (size_t)(64 * LDS * 2 + TM * LDS + 32 * 33 + 16) * sizeof(double);
+constexpr size_t kTrsmSmem = (size_t)(64 * LDS + TM * LDS) * sizeof(double);
+constexpr size_t kPotf2Smem = (size_t)(2 * 64 * LDS + 32 * 33 + 16) * sizeof(double);
 
 // ------------------------------------------------------------------------------------------------
 // 3. trailing update  C[r,c] -= P_r P_c'  over the lower triangle of rows/cols [lo, row_hi) restricted to
@@ -305,46 +319,48 @@ constexpr int UBN = 64;
 constexpr int ULD = 36;  // 32-wide K chunks, 36 % 16 == 4
 constexpr size_t kUpdateSmem = (size_t)(2 * (TM + UBN) * ULD) * sizeof(double);
 
-__global__ void __launch_bounds__(256, 2) update_kernel(Batch bt, int64_t ld, int k0, int lo, int row_hi, int col_hi,
-                                                        int narrow) {
+__global__ void __launch_bounds__(256, 2) update_kernel(Batch bt, int64_t ld, int k0, int kc, int lo, int row_hi,
+                                                        int col_hi, int ncol_tiles) {
     extern __shared__ double smem[];
     int ti, tj;
-    if (narrow) {
-        ti = blockIdx.x;
-        tj = 0;
-    } else {
-        // row tile ti owns column tiles 0 .. 2 ti + 1  ->  ti (ti + 1) tiles precede it
-        const int t = blockIdx.x;
-        ti = (int)((sqrt(4.0 * (double)t + 1.0) - 1.0) * 0.5);
-        while ((ti + 1) * (ti + 2) <= t) ++ti;
-        while (ti * (ti + 1) > t) --ti;
-        tj = t - ti * (ti + 1);
+    if (ncol_tiles > 0) {  // look-ahead part: the first `ncol_tiles` 64-column blocks of every row tile
+        ti = blockIdx.x / ncol_tiles;
+        tj = blockIdx.x - ti * ncol_tiles;
+    } else {               // row tile ti owns column tiles 0 .. 2 ti + 1
+        stair_index(blockIdx.x, ti, tj);
     }
     const int ra = lo + ti * TM, rb = lo + tj * UBN;
-    if (rb >= col_hi || ra >= row_hi) return;
+    if (rb >= col_hi || ra >= row_hi || rb > ra + TM - 1) return;
     const int tid = threadIdx.x;
     double* __restrict__ T = bt.T[blockIdx.z];
-    auto sA = [&](int st) { return smem + (size_t)st * (TM + UBN) * ULD; };
-    auto sB = [&](int st) { return smem + (size_t)st * (TM + UBN) * ULD + TM * ULD; };
-
+    // per-thread cp.async slots: 8 (A) + 4 (B) 16-byte chunks per 32-wide K chunk
+    const int lr0 = tid >> 4, colo = (tid & 15) * 2;
+    const int64_t stride16 = 16 * ld;
+    const double* gA = T + (int64_t)(ra + lr0) * ld + k0 + colo;
+    const double* gB = T + (int64_t)(rb + lr0) * ld + k0 + colo;
+    unsigned okA = 0, okB = 0;
 #pragma unroll
-    for (int half = 0; half < 2; ++half) {
-        double* a = sA(half);
-        double* b = sB(half);
-        for (int c = tid; c < TM * 16; c += 256) {
-            int lr = c >> 4, colo = (c & 15) * 2;
-            int gr = ra + lr;
-            bool ok = gr < row_hi;
-            cp_async16(&a[lr * ULD + colo], T + (int64_t)(ok ? gr : k0) * ld + k0 + half * 32 + colo, ok);
+    for (int r = 0; r < 8; ++r) okA |= (unsigned)(ra + lr0 + 16 * r < row_hi) << r;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) okB |= (unsigned)(rb + lr0 + 16 * r < col_hi) << r;
+    const int soff = lr0 * ULD + colo;
+    auto load_chunk = [&](int c) {
+        double* a = smem + (size_t)(c & 1) * (TM + UBN) * ULD + soff;
+        double* b = a + TM * ULD;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            bool ok = (okA >> r) & 1u;
+            cp_async16(a + r * 16 * ULD, ok ? gA + r * stride16 + c * 32 : T, ok);
         }
-        for (int c = tid; c < UBN * 16; c += 256) {
-            int lr = c >> 4, colo = (c & 15) * 2;
-            int gq = rb + lr;
-            bool ok = gq < col_hi;
-            cp_async16(&b[lr * ULD + colo], T + (int64_t)(ok ? gq : k0) * ld + k0 + half * 32 + colo, ok);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            bool ok = (okB >> r) & 1u;
+            cp_async16(b + r * 16 * ULD, ok ? gB + r * stride16 + c * 32 : T, ok);
         }
         cp_async_commit();
-    }
+    };
+    load_chunk(0);
+    load_chunk(1);
 
     const int w = tid >> 5, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
     const int wm = w >> 1, wn = w & 1;
@@ -365,12 +381,11 @@ __global__ void __launch_bounds__(256, 2) update_kernel(Batch bt, int64_t ld, in
         }
     }
 
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {
-        if (half == 0) cp_async_wait<1>(); else cp_async_wait<0>();
+    for (int c = 0; c < kc; ++c) {
+        if (c + 1 < kc) cp_async_wait<1>(); else cp_async_wait<0>();
         __syncthreads();
-        const double* a_s = sA(half);
-        const double* b_s = sB(half);
+        const double* a_s = smem + (size_t)(c & 1) * (TM + UBN) * ULD;
+        const double* b_s = a_s + TM * ULD;
 #pragma unroll 2
         for (int kk = 0; kk < 32; kk += 4) {
             double a[4], b[4];
@@ -382,6 +397,10 @@ __global__ void __launch_bounds__(256, 2) update_kernel(Batch bt, int64_t ld, in
             for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
                 for (int nj = 0; nj < 4; ++nj) dmma884(acc[mi][nj][0], acc[mi][nj][1], a[mi], b[nj]);
+        }
+        if (c + 2 < kc) {
+            __syncthreads();  // all warps finished with this stage before it is refilled
+            load_chunk(c + 2);
         }
     }
 
@@ -465,11 +484,9 @@ __global__ void __launch_bounds__(256) grad_kernel(KernelDev kd, const double* _
     __shared__ double ai[64], aj[64];
     __shared__ double sred[8];
     const int tid = threadIdx.x;
-    int t = blockIdx.x;
-    int ti = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
-    while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
-    while (ti * (ti + 1) / 2 > t) --ti;
-    const int tj = t - ti * (ti + 1) / 2;
+    const int t = blockIdx.x;
+    int ti, tj;
+    tri_index(t, ti, tj);
     const int D = kd.D;
     const double sigma2 = out4[2];
     for (int idx = tid; idx < D * 64; idx += 256) {
@@ -574,7 +591,8 @@ __global__ void __launch_bounds__(256) grad_finish_kernel(const double* __restri
 static int configure_once() {
     static bool done = false;
     if (done) return DGPB_OK;
-    DGPB_CUDA_TRY(cudaFuncSetAttribute(panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPanelSmem));
+    DGPB_CUDA_TRY(cudaFuncSetAttribute(trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTrsmSmem));
+    DGPB_CUDA_TRY(cudaFuncSetAttribute(potf2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPotf2Smem));
     DGPB_CUDA_TRY(cudaFuncSetAttribute(update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUpdateSmem));
     done = true;
     return DGPB_OK;
@@ -662,61 +680,90 @@ struct LookAhead {
 };
 static thread_local LookAhead g_la;
 
+static int launch_panel(const Geom& g, const Batch& bt, int B, int k0, int row_hi, cudaStream_t st) {
+    potf2_kernel<<<B, 256, kPotf2Smem, st>>>(bt, g.ld, g.npad, k0);
+    DGPB_LAUNCHED();
+    const int rows = row_hi - (k0 + NB);
+    if (rows > 0) {
+        const int tiles = (int)cdiv(rows, TM);
+        dim3 grid((unsigned)std::min(tiles, std::max(1, 296 / B)), 1, (unsigned)B);
+        trsm_kernel<<<grid, 256, kTrsmSmem, st>>>(bt, g.ld, g.npad, k0, k0 + NB, row_hi);
+        DGPB_LAUNCHED();
+    }
+    return DGPB_OK;
+}
+
+static int launch_update(const Batch& bt, int B, int64_t ld, int k0, int K, int lo, int row_hi, int col_hi,
+                         int ncol_tiles, cudaStream_t st) {
+    const int rows = row_hi - lo;
+    if (rows <= 0 || col_hi <= lo) return DGPB_OK;
+    const int ntr = (int)cdiv(rows, TM);
+    const unsigned nblk = ncol_tiles > 0 ? (unsigned)(ntr * ncol_tiles) : (unsigned)(ntr * (ntr + 1));
+    update_kernel<<<dim3(nblk, 1, (unsigned)B), 256, kUpdateSmem, st>>>(bt, ld, k0, K / 32, lo, row_hi, col_hi,
+                                                                      ncol_tiles);
+    DGPB_LAUNCHED();
+    return DGPB_OK;
+}
+
+// Right-looking factorisation in super-steps of two 64-column panels:
+//   panel A -> narrow update of panel B's columns (K = 64) -> panel B
+//   -> look-ahead update (K = 128) of the NEXT super-step's 128 columns, on the caller's stream (critical path)
+//   -> bulk update (K = 128) of everything further right, on a side stream.
+// K = 128 halves the read-modify-write traffic of the trailing matrix per flop (16 flop/B instead of 8, ridge
+// of the chip ~5.5) and doubles the DMMA work per tile prologue; the side stream lets the next super-step's
+// panels overlap the bulk update.  Dependencies: bulk_s needs panels_s (event) and bulk_{s-1} (stream order);
+// look-ahead_s needs panels_s (stream order) and bulk_{s-1} (event: both write columns [lo, lo+128)).
 int factorize(const Geom& g, const Batch& bt, int B, cudaStream_t st) {
     DGPB_TRY(configure_once());
-    const int nsteps = g.npad / NB;
-    DGPB_TRY(g_la.init(2 * (size_t)nsteps + 4));
+    const int nsuper = (g.npad + 2 * NB - 1) / (2 * NB);
+    DGPB_TRY(g_la.init(2 * (size_t)nsuper + 4));
     cudaStream_t side = g_la.side;
     int evi = 0;
-    // the side stream starts after everything already queued on the caller's stream
     DGPB_CUDA_TRY(cudaEventRecord(g_la.ev[evi], st));
     DGPB_CUDA_TRY(cudaStreamWaitEvent(side, g_la.ev[evi], 0));
     ++evi;
     cudaEvent_t prev_bulk = nullptr;
-    const int max_ctas = std::max(1, 148 / B);
-    for (int k0 = 0; k0 < g.npad; k0 += NB) {
-        const int k1 = k0 + NB;
-        const int row_hi = g.aug ? g.npad + 1 + k1 : g.R;
-        const int rows = row_hi - k1;
-        const int ptiles = rows > 0 ? (int)cdiv(rows, TM) : 1;
-        dim3 pg((unsigned)std::min(ptiles, max_ctas), 1, (unsigned)B);
-        panel_kernel<<<pg, 256, kPanelSmem, st>>>(bt, g.ld, g.npad, k0, k1, row_hi);
-        DGPB_LAUNCHED();
-        if (rows <= 0) continue;
+    for (int kA = 0; kA < g.npad; kA += 2 * NB) {
+        const int kB = kA + NB;
+        const bool has_b = kB < g.npad;
+        const int rhA = g.aug ? g.npad + 1 + kA + NB : g.R;
+        DGPB_TRY(launch_panel(g, bt, B, kA, rhA, st));
+        int K = NB, lo2 = kA + NB, rh = rhA;
+        if (has_b) {
+            DGPB_TRY(launch_update(bt, B, g.ld, kA, NB, kB, rhA, std::min(kB + NB, rhA), 1, st));
+            const int rhB = g.aug ? g.npad + 1 + kB + NB : g.R;
+            DGPB_TRY(launch_panel(g, bt, B, kB, rhB, st));
+            K = 2 * NB;
+            lo2 = kB + NB;
+            rh = rhB;
+        }
+        if (rh - lo2 <= 0) continue;
         cudaEvent_t ev_panel = g_la.ev[evi++];
         DGPB_CUDA_TRY(cudaEventRecord(ev_panel, st));
-        // ---- bulk: columns [k1 + 64, row_hi) on the side stream
-        const int brows = row_hi - (k1 + UBN);
+        // ---- bulk: columns [lo2 + 128, rh) on the side stream
+        const int blo = lo2 + 2 * UBN;
+        const int brows = rh - blo;
         cudaEvent_t this_bulk = nullptr;
         if (brows > 0) {
             DGPB_CUDA_TRY(cudaStreamWaitEvent(side, ev_panel, 0));
-            const int ntr = (int)cdiv(brows, TM);
-            dim3 ug((unsigned)(ntr * (ntr + 1)), 1, (unsigned)B);
             if (g_prof.on) {
                 if (g_prof.used + 2 > (int)g_prof.ev.size()) DGPB_TRY(g_prof.drain());
                 DGPB_CUDA_TRY(cudaEventRecord(g_prof.ev[g_prof.used], side));
             }
-            update_kernel<<<ug, 256, kUpdateSmem, side>>>(bt, g.ld, k0, k1 + UBN, row_hi, row_hi, 0);
-            DGPB_LAUNCHED();
+            DGPB_TRY(launch_update(bt, B, g.ld, kA, K, blo, rh, rh, 0, side));
             if (g_prof.on) {
                 DGPB_CUDA_TRY(cudaEventRecord(g_prof.ev[g_prof.used + 1], side));
                 g_prof.used += 2;
-                g_prof.flops += (double)B * 0.5 * (double)brows * (double)(brows + 1) * 2.0 * NB;
+                g_prof.flops += (double)B * 0.5 * (double)brows * (double)(brows + 1) * 2.0 * K;
             }
             this_bulk = g_la.ev[evi++];
             DGPB_CUDA_TRY(cudaEventRecord(this_bulk, side));
         }
-        // ---- narrow: the next panel's columns [k1, k1 + 64) on the critical path
+        // ---- look-ahead: the next super-step's columns [lo2, lo2 + 128) on the critical path
         if (prev_bulk) DGPB_CUDA_TRY(cudaStreamWaitEvent(st, prev_bulk, 0));
-        {
-            const int ntr = (int)cdiv(rows, TM);
-            dim3 ug((unsigned)ntr, 1, (unsigned)B);
-            update_kernel<<<ug, 256, kUpdateSmem, st>>>(bt, g.ld, k0, k1, row_hi, std::min(k1 + UBN, row_hi), 1);
-            DGPB_LAUNCHED();
-        }
+        DGPB_TRY(launch_update(bt, B, g.ld, kA, K, lo2, rh, std::min(lo2 + 2 * UBN, rh), 2, st));
         prev_bulk = this_bulk;
     }
-    // join: later work on the caller's stream sees every bulk update
     DGPB_CUDA_TRY(cudaEventRecord(g_la.ev[evi], side));
     DGPB_CUDA_TRY(cudaStreamWaitEvent(st, g_la.ev[evi], 0));
     return DGPB_OK;

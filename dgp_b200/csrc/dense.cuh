@@ -33,12 +33,13 @@ inline Geom make_geom(int64_t n, bool aug) {
 
 struct Batch {
     double* T[MAXB];
-    double* diag[MAXB];   // per matrix: npad diagonal entries of L followed by npad/NB diagonal blocks (NB x NB)
+    double* diag[MAXB];   // per matrix: npad diagonal entries of L, npad/NB diagonal blocks (NB x NB), then
+                          // inv(L_kk) of the panel in flight (NB x NB)
     int* info;            // device int[B]: 0 or (failing column + 1)
 };
 
 // size in doubles of one `diag` side buffer
-inline size_t diag_elems(const Geom& g) { return (size_t)g.npad * (1 + NB); }
+inline size_t diag_elems(const Geom& g) { return (size_t)g.npad * (1 + NB) + (size_t)NB * NB; }
 
 // Assemble T for every batch entry: K (lower) from the kernel descriptor, y row, identity rows.
 int assemble(const Geom& g, const KernelDev* kds, const double* const* ys, const Batch& bt, int B, cudaStream_t st);

@@ -184,10 +184,7 @@ constexpr int TT = 8;   // test points per CTA
 constexpr int PT = 32;  // pair tile edge
 
 __device__ __forceinline__ void tile_from_linear(int t, int& ti, int& tj) {
-    ti = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
-    while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
-    while (ti * (ti + 1) / 2 > t) --ti;
-    tj = t - ti * (ti + 1) / 2;
+    tri_index(t, ti, tj);
 }
 
 // global-dimension factor Iz_i = k(gw_i, z_t) on the Dz connected dims (K_vec_nb); returns the factor

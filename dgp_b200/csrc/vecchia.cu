@@ -147,10 +147,8 @@ __device__ __forceinline__ void warp_build_K(const VKern& vk, const double* xl, 
                                              int lane) {
     const int np = b * (b + 1) / 2;
     for (int p = lane; p < np; p += 32) {
-        int i = (int)((sqrt(8.0 * (double)p + 1.0) - 1.0) * 0.5);
-        while ((i + 1) * (i + 2) / 2 <= p) ++i;
-        while (i * (i + 1) / 2 > p) --i;
-        int j = p - i * (i + 1) / 2;
+        int i, j;
+        tri_index(p, i, j);
         A[p] = (i == j) ? 1.0 + nug[i] : corr_rows(vk, xl + i * vk.D, xl + j * vk.D);
     }
     __syncwarp();
@@ -473,10 +471,8 @@ __global__ void vecchia_pred_kernel(VKern vk, VPredArgs a, int per_warp) {
     }
     const int np = b * (b + 1) / 2;
     for (int p = lane; p < np; p += 32) {
-        int i = (int)((sqrt(8.0 * (double)p + 1.0) - 1.0) * 0.5);
-        while ((i + 1) * (i + 2) / 2 <= p) ++i;
-        while (i * (i + 1) / 2 > p) --i;
-        int j = p - i * (i + 1) / 2;
+        int i, j;
+        tri_index(p, i, j);
         const double* xi = a.w1 + (int64_t)idx[i] * Dw;
         const double* xj = a.w1 + (int64_t)idx[j] * Dw;
         double v;
@@ -522,10 +518,8 @@ __global__ void vecchia_pred_kernel(VKern vk, VPredArgs a, int per_warp) {
     __syncwarp();
     // K^-1 = L^-T L^-1 (packed lower):  Kinv_ij = sum_{p >= i} Linv[p][i] Linv[p][j],  i >= j
     for (int p = lane; p < np; p += 32) {
-        int i = (int)((sqrt(8.0 * (double)p + 1.0) - 1.0) * 0.5);
-        while ((i + 1) * (i + 2) / 2 <= p) ++i;
-        while (i * (i + 1) / 2 > p) --i;
-        int j = p - i * (i + 1) / 2;
+        int i, j;
+        tri_index(p, i, j);
         double s = 0.0;
         for (int r = i; r < b; ++r) s += A[tri(r, i)] * A[tri(r, j)];
         Kinv[p] = s;
@@ -540,10 +534,8 @@ __global__ void vecchia_pred_kernel(VKern vk, VPredArgs a, int per_warp) {
     __syncwarp();
     double tr = 0.0, qd = 0.0, mt = 0.0;
     for (int p = lane; p < np; p += 32) {
-        int i = (int)((sqrt(8.0 * (double)p + 1.0) - 1.0) * 0.5);
-        while ((i + 1) * (i + 2) / 2 <= p) ++i;
-        while (i * (i + 1) / 2 > p) --i;
-        int j = p - i * (i + 1) / 2;
+        int i, j;
+        tri_index(p, i, j);
         double wgt = (i == j) ? 1.0 : 2.0;
         tr += wgt * Kinv[p] * Jm[p];
         qd += wgt * Jm[p] * al[i] * al[j];
