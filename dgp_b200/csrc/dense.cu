@@ -11,6 +11,7 @@
 #include "dense.cuh"
 
 #include <algorithm>
+#include <mutex>
 
 namespace dgpb {
 
@@ -150,22 +151,34 @@ __global__ void rows_init_kernel(double* __restrict__ T, int64_t ld, int n, int 
 // the critical path either way, and this removes one dependent launch per panel), inverts it, and then
 // applies X <- X * inv(L_kk)' to its own 128 rows of the panel with FP64 mma.  CTA 0 publishes L_kk and
 // diag(L_kk) to the side buffer (not into T: sibling CTAs are still reading the unfactored block).
+template <int NU>
 __device__ __forceinline__ void tri_inv_offdiag(const double* sL, double* sD, double* sT, int r0, int c0, int s,
                                                 int tid, int nthr) {
-    // sD[r0.., c0..] (s x s) = -D[r0.., r0..] * ( L[r0.., c0..] * D[c0.., c0..] ),  D lower-triangular blocks
-    for (int idx = tid; idx < s * s; idx += nthr) {
-        int a = idx / s, b = idx % s;
-        double acc = 0.0;
-        for (int k = b; k < s; ++k) acc += sL[(r0 + a) * LDS + c0 + k] * sD[(c0 + k) * LDS + c0 + b];
-        sT[a * 33 + b] = acc;
+    // sD[r0.., c0..] (s x s) = -D[r0.., r0..] * ( L[r0.., c0..] * D[c0.., c0..] ),  D lower-triangular blocks.
+    // Thread t owns row a = t / (s/NU) and NU columns b_u = (t % (s/NU)) + u * (s/NU): NU independent
+    // accumulators hide the shared-memory latency of the dot products.  Requires nthr * NU == s * s.
+    const int per = s / NU;
+    const int a = tid / per, b0 = tid % per;
+    double acc[NU];
+#pragma unroll
+    for (int u = 0; u < NU; ++u) acc[u] = 0.0;
+    for (int k = 0; k < s; ++k) {
+        const double l = sL[(r0 + a) * LDS + c0 + k];
+#pragma unroll
+        for (int u = 0; u < NU; ++u) acc[u] += l * sD[(c0 + k) * LDS + c0 + b0 + u * per];  // D[k][b] = 0 for k < b
     }
+#pragma unroll
+    for (int u = 0; u < NU; ++u) sT[a * 33 + b0 + u * per] = acc[u];
     __syncthreads();
-    for (int idx = tid; idx < s * s; idx += nthr) {
-        int a = idx / s, b = idx % s;
-        double acc = 0.0;
-        for (int k = 0; k <= a; ++k) acc += sD[(r0 + a) * LDS + r0 + k] * sT[k * 33 + b];
-        sD[(r0 + a) * LDS + c0 + b] = -acc;
+#pragma unroll
+    for (int u = 0; u < NU; ++u) acc[u] = 0.0;
+    for (int k = 0; k <= a; ++k) {
+        const double d = sD[(r0 + a) * LDS + r0 + k];
+#pragma unroll
+        for (int u = 0; u < NU; ++u) acc[u] += d * sT[k * 33 + b0 + u * per];
     }
+#pragma unroll
+    for (int u = 0; u < NU; ++u) sD[(r0 + a) * LDS + c0 + b0 + u * per] = -acc[u];
     __syncthreads();
 }
 
@@ -178,7 +191,8 @@ __global__ void __launch_bounds__(256, 1) potf2_kernel(Batch bt, int64_t ld, int
     double* sL = smem;
     double* sD = sL + 64 * LDS;
     double* sT = sD + 64 * LDS;
-    __shared__ double colv[2][64];
+    __shared__ double colA[2][64];
+    __shared__ double colB[2][64];
     const int tid = threadIdx.x;
     const double* __restrict__ T = bt.T[blockIdx.x];
     const int pi = tid >> 2, pc = tid & 3;
@@ -192,25 +206,37 @@ __global__ void __launch_bounds__(256, 1) potf2_kernel(Batch bt, int64_t ld, int
         sL[idx] = 0.0;
         sD[idx] = 0.0;
     }
+    // two columns (j, j+1) per barrier: the 2x2 pivot is factored redundantly by every thread, the
+    // rank-2 update is applied to the register-resident rows
 #pragma unroll
-    for (int j = 0; j < 64; ++j) {
-        const int qj = j >> 2;
-        const bool owner = (pc == (j & 3)) && (pi >= j);
-        if (owner) colv[j & 1][pi] = reg[qj];
+    for (int j = 0; j < 64; j += 2) {
+        const int qj = j >> 2, buf = (j >> 1) & 1;
+        const bool ownA = (pc == (j & 3)) && (pi >= j);
+        const bool ownB = (pc == (j & 3) + 1) && (pi >= j + 1);
+        if (ownA) colA[buf][pi] = reg[qj];
+        if (ownB) colB[buf][pi] = reg[qj];
         __syncthreads();
-        const double d = colv[j & 1][j];
-        if (!(d > 0.0) && tid == 0) atomicCAS(&bt.info[blockIdx.x], 0, k0 + j + 1);
-        const double rd = 1.0 / d;
-        const double rs = rsqrt(d);
-        if (pi > j) {
-            const double ci = colv[j & 1][pi] * rd;
+        const double d0 = colA[buf][j];
+        const double rs0 = rsqrt(d0);
+        const double l10 = colA[buf][j + 1] * rs0;
+        const double d1 = colB[buf][j + 1] - l10 * l10;
+        const double rs1 = rsqrt(d1);
+        if ((!(d0 > 0.0) || !(d1 > 0.0)) && tid == 0) atomicCAS(&bt.info[blockIdx.x], 0, k0 + j + (d0 > 0.0 ? 2 : 1));
+        const double li0 = colA[buf][pi] * rs0;                       // valid for pi > j
+        const double li1 = (colB[buf][pi] - li0 * l10) * rs1;         // valid for pi > j + 1
+        if (pi > j + 1) {
 #pragma unroll
             for (int q = qj; q < 16; ++q) {
-                int k = 4 * q + pc;
-                if (k > j && k <= pi) reg[q] -= ci * colv[j & 1][k];
+                const int k = 4 * q + pc;
+                if (k > j + 1 && k <= pi) {
+                    const double lk0 = colA[buf][k] * rs0;
+                    const double lk1 = (colB[buf][k] - lk0 * l10) * rs1;
+                    reg[q] -= li0 * lk0 + li1 * lk1;
+                }
             }
         }
-        if (owner) sL[pi * LDS + j] = (pi == j) ? d * rs : reg[qj] * rs;
+        if (ownA) sL[pi * LDS + j] = (pi == j) ? d0 * rs0 : li0;
+        if (ownB) sL[pi * LDS + j + 1] = (pi == j + 1) ? d1 * rs1 : li1;
     }
     __syncthreads();
 
@@ -227,9 +253,9 @@ __global__ void __launch_bounds__(256, 1) potf2_kernel(Batch bt, int64_t ld, int
     __syncthreads();
     {
         const int half = tid >> 7;
-        tri_inv_offdiag(sL, sD, sT + half * 16 * 33, half ? 48 : 16, half ? 32 : 0, 16, tid & 127, 128);
+        tri_inv_offdiag<2>(sL, sD, sT + half * 16 * 33, half ? 48 : 16, half ? 32 : 0, 16, tid & 127, 128);
     }
-    tri_inv_offdiag(sL, sD, sT, 32, 0, 32, tid, 256);
+    tri_inv_offdiag<4>(sL, sD, sT, 32, 0, 32, tid, 256);
 
     double* dg = bt.diag[blockIdx.x];
     double* blk = dg + npad + (size_t)(k0 / NB) * NB * NB;
@@ -659,6 +685,7 @@ struct UpdateProfiler {
     }
 };
 static UpdateProfiler g_prof;
+static std::mutex g_prof_mutex;  // the M-step issues factorisations from several host threads
 
 // Two-stream look-ahead: the caller's stream carries the critical path (panel k, then the NARROW update of
 // the next panel's 64 columns), a side stream carries the BULK update of everything to the right.  Panel k+1
@@ -669,7 +696,13 @@ struct LookAhead {
     cudaStream_t side = nullptr;
     std::vector<cudaEvent_t> ev;
     int init(size_t need) {
-        if (!side) DGPB_CUDA_TRY(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+        if (!side) {
+            // lowest priority: CTAs of the critical-path kernels on the caller's stream are scheduled ahead of
+            // queued bulk-update CTAs whenever an SM slot frees up
+            int lo_pri = 0, hi_pri = 0;
+            DGPB_CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri));
+            DGPB_CUDA_TRY(cudaStreamCreateWithPriority(&side, cudaStreamNonBlocking, lo_pri));
+        }
         while (ev.size() < need) {
             cudaEvent_t e;
             DGPB_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -747,14 +780,16 @@ int factorize(const Geom& g, const Batch& bt, int B, cudaStream_t st) {
         if (brows > 0) {
             DGPB_CUDA_TRY(cudaStreamWaitEvent(side, ev_panel, 0));
             if (g_prof.on) {
+                std::lock_guard<std::mutex> lock(g_prof_mutex);
                 if (g_prof.used + 2 > (int)g_prof.ev.size()) DGPB_TRY(g_prof.drain());
-                DGPB_CUDA_TRY(cudaEventRecord(g_prof.ev[g_prof.used], side));
-            }
-            DGPB_TRY(launch_update(bt, B, g.ld, kA, K, blo, rh, rh, 0, side));
-            if (g_prof.on) {
-                DGPB_CUDA_TRY(cudaEventRecord(g_prof.ev[g_prof.used + 1], side));
+                const int slot = g_prof.used;
+                DGPB_CUDA_TRY(cudaEventRecord(g_prof.ev[slot], side));
+                DGPB_TRY(launch_update(bt, B, g.ld, kA, K, blo, rh, rh, 0, side));
+                DGPB_CUDA_TRY(cudaEventRecord(g_prof.ev[slot + 1], side));
                 g_prof.used += 2;
                 g_prof.flops += (double)B * 0.5 * (double)brows * (double)(brows + 1) * 2.0 * K;
+            } else {
+                DGPB_TRY(launch_update(bt, B, g.ld, kA, K, blo, rh, rh, 0, side));
             }
             this_bulk = g_la.ev[evi++];
             DGPB_CUDA_TRY(cudaEventRecord(this_bulk, side));
@@ -934,6 +969,7 @@ int dgpb_mvn_draw(dgpb_ws* ws, const dgpb_node* node, int64_t n, const double* z
 }
 
 int dgpb_profile(int on) {
+    std::lock_guard<std::mutex> lock(g_prof_mutex);
     if (on && g_prof.ev.empty()) {
         g_prof.ev.resize(4096);
         for (auto& e : g_prof.ev) DGPB_CUDA_TRY(cudaEventCreate(&e));
@@ -950,6 +986,7 @@ int dgpb_profile(int on) {
 
 int dgpb_profile_read(double* out_host) {
     DGPB_REQUIRE(out_host != nullptr, "NULL argument");
+    std::lock_guard<std::mutex> lock(g_prof_mutex);
     DGPB_TRY(g_prof.drain());
     out_host[0] = g_prof.ms;
     out_host[1] = g_prof.launches;

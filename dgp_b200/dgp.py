@@ -9,6 +9,7 @@ SURVEY.md section 2 row 5: `__init__`, the generic branch of `initialize` (dgp.p
 from __future__ import annotations
 
 import copy
+import threading
 
 import numpy as np
 
@@ -34,6 +35,9 @@ except Exception:  # pragma: no cover
                 pass
 
         return _R()
+
+
+_tls = threading.local()
 
 
 class dgp:
@@ -197,14 +201,8 @@ class dgp:
                     (self.imp).sample(burnin=ess_burn)
                     if self.vecch and (self.N + i & (self.N + i - 1)) == 0 and self.N + i > 1:
                         (self.imp).update_ord_nn()
-                    for l in range(self.n_layer):
-                        for kernel in self.all_layer[l]:
-                            if kernel.prior_name == 'ref':
-                                kernel.compute_cl()
-                            if l != 0:
-                                kernel.r2()
-                            kernel.maximise()
-                        pgb.set_description('Iteration %i: Layer %i' % (i, l + 1))
+                    self._m_step()
+                    pgb.set_description('Iteration %i' % i)
                 self.N += N
                 return
             except (np.linalg.LinAlgError, SystemError):
@@ -217,6 +215,44 @@ class dgp:
                     tqdm.write(f"Restart {restarts}/{max_restarts}:")
                 self.N = N0
                 self.reinit_all_layer(reset_lengthscale=True, row=self.N)
+
+    def _m_step(self):
+        """M-step over every GP node (dgp.py:1391-1398).  Given the imputation the nodes are independent, so
+        their L-BFGS-B runs are issued from a small thread pool, one CUDA stream and workspace per thread: the
+        serial part of one node's blocked factorisation (panel kernels) overlaps the tensor-core updates of
+        the others.  Results do not depend on the scheduling (each node's optimisation is self-contained)."""
+        import os
+        from concurrent.futures import ThreadPoolExecutor
+
+        from . import _lib as L
+
+        nodes = [(l, kernel) for l in range(self.n_layer) for kernel in self.all_layer[l]]
+        nthreads = max(1, min(len(nodes), int(os.environ.get('DGPB_MSTEP_THREADS', '6'))))
+        torch = L.torch_mod()
+        dev = L.device()
+
+        def work(item):
+            l, kernel = item
+            torch.cuda.set_device(dev)
+            stream = getattr(_tls, 'stream', None)
+            if stream is None:
+                stream = _tls.stream = torch.cuda.Stream(device=dev)
+            with torch.cuda.stream(stream):
+                if kernel.prior_name == 'ref':
+                    kernel.compute_cl()
+                if l != 0:
+                    kernel.r2()
+                kernel.maximise()
+                stream.synchronize()
+
+        if nthreads == 1:
+            for item in nodes:
+                work(item)
+            return
+        torch.cuda.current_stream().synchronize()
+        with ThreadPoolExecutor(max_workers=nthreads) as pool:
+            for fut in [pool.submit(work, item) for item in nodes]:
+                fut.result()
 
     def ptrain(self, *args, **kwargs):
         raise NotImplementedError("dgp_b200: process-pool training is replaced by the GPU path; use train()")
