@@ -673,9 +673,9 @@ struct UpdateProfiler {
     cudaStream_t last = nullptr;
     int drain() {
         if (used == 0) return DGPB_OK;
-        DGPB_CUDA_TRY(cudaEventSynchronize(ev[used - 1]));
         for (int i = 0; i < used; i += 2) {
             float t = 0.f;
+            DGPB_CUDA_TRY(cudaEventSynchronize(ev[i + 1]));  // pairs may sit on different streams (threaded M-step)
             DGPB_CUDA_TRY(cudaEventElapsedTime(&t, ev[i], ev[i + 1]));
             ms += t;
             launches += 1.0;
