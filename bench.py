@@ -302,7 +302,7 @@ def run_gpu(args):
         e2e = world * args.steps / (wall_ms_max * 1e-3)
         upd_ms, upd_n, upd_flops = prof[0], prof[1], prof[2]
         achieved = (upd_flops / upd_n) / (upd_ms / upd_n * 1e-3) / 1e12 if upd_n > 0 else None
-        roof = {"bound": "tensor", "kernel": "update_kernel (FP64 DMMA SYRK trailing update, K=64)",
+        roof = {"bound": "tensor", "kernel": "update_kernel, bulk launches (FP64 DMMA SYRK trailing update, K=128)",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": (achieved / peak) if achieved else None,
                 "traffic": None, "launches_timed": int(upd_n), "avg_launch_ms": upd_ms / upd_n if upd_n else None,
                 "share_of_step": upd_ms / (dev_ms * 1.0) if dev_ms else None,
