@@ -388,6 +388,31 @@ __global__ void __launch_bounds__(256, 2) update_kernel(Batch bt, int64_t ld, in
     load_chunk(0);
     load_chunk(1);
 
+    // L2 prefetch of the C tile that the CTA taking over this SM slot will need (CTAs are dispatched in
+    // linear order, 2 per SM): its accumulator loads then hit L2 instead of queueing on HBM behind the
+    // store bursts of the current wave.
+    {
+        const int lin2 = (int)(blockIdx.z * gridDim.x + blockIdx.x) + 296;
+        const int z2 = lin2 / (int)gridDim.x, x2 = lin2 - z2 * (int)gridDim.x;
+        if (z2 < (int)gridDim.z) {
+            int ti2, tj2;
+            if (ncol_tiles > 0) {
+                ti2 = x2 / ncol_tiles;
+                tj2 = x2 - ti2 * ncol_tiles;
+            } else {
+                stair_index(x2, ti2, tj2);
+            }
+            const int ra2 = lo + ti2 * TM, rb2 = lo + tj2 * UBN;
+            const double* T2 = bt.T[z2];
+#pragma unroll
+            for (int l = tid; l < TM * 4; l += 256) {
+                const int r = ra2 + (l >> 2), cseg = rb2 + (l & 3) * 16;
+                if (r < row_hi && cseg < col_hi)
+                    asm volatile("prefetch.global.L2 [%0];\n" ::"l"(T2 + (int64_t)r * ld + cseg));
+            }
+        }
+    }
+
     const int w = tid >> 5, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
     const int wm = w >> 1, wn = w & 1;
     double acc[4][4][2];
