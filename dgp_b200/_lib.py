@@ -44,6 +44,7 @@ _PROTOS = {
     "dgpb_sizeof_node": (c_i64, []),
     "dgpb_profile": (ctypes.c_int, [ctypes.c_int]),
     "dgpb_profile_read": (ctypes.c_int, [c_vp]),
+    "dgpb_probe_update": (ctypes.c_int, [c_vp, c_i64, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_vp]),
     "dgpb_ws_create": (ctypes.c_int, [ctypes.POINTER(c_vp), ctypes.c_int]),
     "dgpb_ws_destroy": (ctypes.c_int, [c_vp]),
     "dgpb_ws_bytes": (c_i64, [c_vp]),
@@ -56,6 +57,10 @@ _PROTOS = {
     "dgpb_ess_block": (ctypes.c_int, [c_vp, ctypes.POINTER(DgpbNode), ctypes.c_int, c_vp, c_vp, c_i64,
                                       ctypes.POINTER(DgpbNode), ctypes.c_int, c_i64, c_vp, c_vp, ctypes.c_int,
                                       ctypes.POINTER(ctypes.c_int), c_vp, c_vp]),
+    "dgpb_ess_block_cached": (ctypes.c_int, [c_vp, ctypes.POINTER(DgpbNode), ctypes.c_int, c_vp, c_vp, c_i64,
+                                             ctypes.POINTER(DgpbNode), ctypes.c_int, c_i64, c_vp, c_vp, ctypes.c_int,
+                                             ctypes.POINTER(ctypes.c_int), c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "dgpb_cache_clear": (ctypes.c_int, [c_vp]),
     "dgpb_knn_ordered": (ctypes.c_int, [c_vp, c_i64, c_i64, c_i64, c_vp, c_vp]),
     "dgpb_knn": (ctypes.c_int, [c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp]),
     "dgpb_vecchia_llik": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_dbl, c_dbl, c_vp,

@@ -85,11 +85,24 @@ int dgpb_ws_destroy(dgpb_ws* ws) {
     if (!ws) return DGPB_OK;
     for (int i = 0; i < SLOT_COUNT; ++i)
         if (ws->buf[i]) cudaFree(ws->buf[i]);
+    for (auto& kv : ws->cache)
+        if (kv.second.T) cudaFree(kv.second.T);
     if (ws->pinned) cudaFreeHost(ws->pinned);
     delete ws;
     return DGPB_OK;
 }
 
-int64_t dgpb_ws_bytes(const dgpb_ws* ws) { return ws ? (int64_t)ws->total() : 0; }
+int64_t dgpb_ws_bytes(const dgpb_ws* ws) {
+    if (!ws) return 0;
+    size_t t = ws->total();
+    for (const auto& kv : ws->cache) t += kv.second.cap * sizeof(double);
+    return (int64_t)t;
+}
+
+int dgpb_cache_clear(dgpb_ws* ws) {
+    DGPB_REQUIRE(ws != nullptr, "ws is NULL");
+    for (auto& kv : ws->cache) kv.second.valid = false;
+    return DGPB_OK;
+}
 
 }  // extern "C"

@@ -5,6 +5,7 @@
 #include <math.h>
 
 #include <atomic>
+#include <map>
 #include <cstdarg>
 #include <cstdio>
 #include <string>
@@ -98,8 +99,17 @@ enum Slot : int {
     SLOT_COUNT
 };
 
+// chol(K) of a GP node kept across ESS block updates of one I-step (hyper-parameters fixed)
+struct CachedFactor {
+    double* T = nullptr;   // complete lower factor (diagonal blocks restored), Geom(n, false) layout
+    size_t cap = 0;        // doubles allocated
+    int64_t n = 0;
+    bool valid = false;
+};
+
 struct Workspace {
     int device = 0;
+    std::map<int, CachedFactor> cache;
     void* buf[SLOT_COUNT] = {};
     size_t cap[SLOT_COUNT] = {};
     double* pinned = nullptr;  // small pinned host staging buffer (4096 doubles)

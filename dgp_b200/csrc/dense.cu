@@ -345,8 +345,10 @@ constexpr int UBN = 64;
 constexpr int ULD = 36;  // 32-wide K chunks, 36 % 16 == 4
 constexpr size_t kUpdateSmem = (size_t)(2 * (TM + UBN) * ULD) * sizeof(double);
 
+// `flags` (probe only, 0 in production): 1 = skip C loads, 2 = skip C stores, 4 = skip the DMMA loop body,
+// 8 = skip the panel loads.
 __global__ void __launch_bounds__(256, 2) update_kernel(Batch bt, int64_t ld, int k0, int kc, int lo, int row_hi,
-                                                        int col_hi, int ncol_tiles) {
+                                                        int col_hi, int ncol_tiles, int flags) {
     extern __shared__ double smem[];
     int ti, tj;
     if (ncol_tiles > 0) {  // look-ahead part: the first `ncol_tiles` 64-column blocks of every row tile
@@ -385,8 +387,10 @@ __global__ void __launch_bounds__(256, 2) update_kernel(Batch bt, int64_t ld, in
         }
         cp_async_commit();
     };
-    load_chunk(0);
-    load_chunk(1);
+    if (!(flags & 8)) {
+        load_chunk(0);
+        load_chunk(1);
+    }
 
     // L2 prefetch of the C tile that the CTA taking over this SM slot will need (CTAs are dispatched in
     // linear order, 2 per SM): its accumulator loads then hit L2 instead of queueing on HBM behind the
@@ -422,7 +426,7 @@ __global__ void __launch_bounds__(256, 2) update_kernel(Batch bt, int64_t ld, in
 #pragma unroll
         for (int nj = 0; nj < 4; ++nj) {
             int gc = rb + 32 * wn + 8 * nj + 2 * t4;
-            if (gr < row_hi && gc < col_hi) {
+            if (gr < row_hi && gc < col_hi && !(flags & 1)) {
                 double2 v = *reinterpret_cast<const double2*>(&T[(int64_t)gr * ld + gc]);
                 acc[mi][nj][0] = v.x;
                 acc[mi][nj][1] = v.y;
@@ -438,7 +442,7 @@ __global__ void __launch_bounds__(256, 2) update_kernel(Batch bt, int64_t ld, in
         const double* a_s = smem + (size_t)(c & 1) * (TM + UBN) * ULD;
         const double* b_s = a_s + TM * ULD;
 #pragma unroll 2
-        for (int kk = 0; kk < 32; kk += 4) {
+        for (int kk = 0; kk < ((flags & 4) ? 0 : 32); kk += 4) {
             double a[4], b[4];
 #pragma unroll
             for (int mi = 0; mi < 4; ++mi) a[mi] = -a_s[(32 * wm + 8 * mi + g) * ULD + kk + t4];
@@ -449,7 +453,7 @@ __global__ void __launch_bounds__(256, 2) update_kernel(Batch bt, int64_t ld, in
 #pragma unroll
                 for (int nj = 0; nj < 4; ++nj) dmma884(acc[mi][nj][0], acc[mi][nj][1], a[mi], b[nj]);
         }
-        if (c + 2 < kc) {
+        if (c + 2 < kc && !(flags & 8)) {
             __syncthreads();  // all warps finished with this stage before it is refilled
             load_chunk(c + 2);
         }
@@ -461,7 +465,7 @@ __global__ void __launch_bounds__(256, 2) update_kernel(Batch bt, int64_t ld, in
 #pragma unroll
         for (int nj = 0; nj < 4; ++nj) {
             int gc = rb + 32 * wn + 8 * nj + 2 * t4;
-            if (gr < row_hi && gc < col_hi)
+            if (gr < row_hi && gc < col_hi && !(flags & 2))
                 *reinterpret_cast<double2*>(&T[(int64_t)gr * ld + gc]) = make_double2(acc[mi][nj][0], acc[mi][nj][1]);
         }
     }
@@ -758,7 +762,7 @@ static int launch_update(const Batch& bt, int B, int64_t ld, int k0, int K, int 
     const int ntr = (int)cdiv(rows, TM);
     const unsigned nblk = ncol_tiles > 0 ? (unsigned)(ntr * ncol_tiles) : (unsigned)(ntr * (ntr + 1));
     update_kernel<<<dim3(nblk, 1, (unsigned)B), 256, kUpdateSmem, st>>>(bt, ld, k0, K / 32, lo, row_hi, col_hi,
-                                                                      ncol_tiles);
+                                                                      ncol_tiles, 0);
     DGPB_LAUNCHED();
     return DGPB_OK;
 }
@@ -990,6 +994,36 @@ int dgpb_mvn_draw(dgpb_ws* ws, const dgpb_node* node, int64_t n, const double* z
         set_error("covariance is not positive definite (pivot %d)", info_host[0]);
         return DGPB_NOT_PD;
     }
+    return DGPB_OK;
+}
+
+// Probe: time `reps` bulk trailing-update launches (K = 128, window = n) on B scratch matrices; see `flags` of
+// update_kernel.  out_host[0] = average ms per launch, out_host[1] = algorithmic TFLOP/s.
+int dgpb_probe_update(dgpb_ws* ws, int64_t n, int B, int flags, int reps, double* out_host) {
+    DGPB_REQUIRE(ws && out_host && n >= 256 && B >= 1 && B <= MAXB, "bad argument");
+    DGPB_TRY(configure_once());
+    Geom g = make_geom(n, false);
+    Batch bt;
+    double* out;
+    DGPB_TRY(setup_batch(ws, g, B, &bt, &out));
+    DGPB_CUDA_TRY(cudaMemset(bt.T[0], 0, g.elems() * sizeof(double) * B));
+    const int lo = 128, rows = g.R - lo;
+    const int ntr = (int)cdiv(rows, TM);
+    cudaEvent_t e0, e1;
+    DGPB_CUDA_TRY(cudaEventCreate(&e0));
+    DGPB_CUDA_TRY(cudaEventCreate(&e1));
+    dim3 grid((unsigned)(ntr * (ntr + 1)), 1, (unsigned)B);
+    update_kernel<<<grid, 256, kUpdateSmem, 0>>>(bt, g.ld, 0, 4, lo, g.R, g.R, 0, flags);
+    DGPB_CUDA_TRY(cudaEventRecord(e0, 0));
+    for (int r = 0; r < reps; ++r) update_kernel<<<grid, 256, kUpdateSmem, 0>>>(bt, g.ld, 0, 4, lo, g.R, g.R, 0, flags);
+    DGPB_CUDA_TRY(cudaEventRecord(e1, 0));
+    DGPB_CUDA_TRY(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    DGPB_CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    out_host[0] = ms / reps;
+    out_host[1] = (double)B * 0.5 * (double)rows * (double)(rows + 1) * 2.0 * 128.0 / (out_host[0] * 1e-3) / 1e12;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
     return DGPB_OK;
 }
 

@@ -45,8 +45,39 @@ static int node_lengths(const dgpb_node* nd, double* len, int* D) {
 
 // sum of the log-likelihoods of `U` nodes whose local inputs are read from `src_override`
 // (or from node->src when NULL).  Dense nodes are batched; Vecchia nodes use the block kernel.
+struct DenseBatchInfo {
+    Batch bt;
+    Geom g;
+    int B = 0;           // matrices in the (single) dense batch, 0 if none or if it needed several batches
+    int map[MAXB];       // batch slot -> node index
+};
+
+// keep chol(K) of batch slot b (just factored, diagonal blocks still in the side buffer) under `key`
+static int cache_store(Workspace* ws, int key, const Geom& g, const Batch& bt, int b, cudaStream_t st) {
+    CachedFactor& cf = ws->cache[key];
+    if (cf.cap < g.elems()) {
+        if (cf.T) DGPB_CUDA_TRY(cudaFree(cf.T));
+        cf.T = nullptr;
+        cf.cap = 0;
+        DGPB_CUDA_TRY(cudaMalloc((void**)&cf.T, g.elems() * sizeof(double)));
+        cf.cap = g.elems();
+    }
+    DGPB_CUDA_TRY(cudaMemcpyAsync(cf.T, bt.T[b], g.elems() * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    Batch one;
+    for (int i = 0; i < MAXB; ++i) one.T[i] = one.diag[i] = nullptr;
+    one.T[0] = cf.T;
+    one.diag[0] = bt.diag[b];
+    one.info = bt.info;
+    DGPB_TRY(restore_diag_blocks(g, one, 1, st));
+    cf.n = g.n;
+    cf.valid = true;
+    return DGPB_OK;
+}
+
 static int nodes_loglik(Workspace* ws, const dgpb_node* nodes, int U, int64_t n, const double* src_override,
-                        double* sum_host, cudaStream_t st) {
+                        double* sum_host, cudaStream_t st, DenseBatchInfo* info_out = nullptr) {
+    if (info_out) info_out->B = 0;
+    int dense_batches = 0;
     double lls[256];
     DGPB_REQUIRE(U >= 1 && U <= 256, "too many upper nodes");
     int nv = 0;
@@ -100,6 +131,13 @@ static int nodes_loglik(Workspace* ws, const dgpb_node* nodes, int U, int64_t n,
         Geom g;
         double* outd;
         DGPB_TRY(loglik_batch_device(ws, kds, ys, sa, B, n, &bt, &g, &outd, st));
+        ++dense_batches;
+        if (info_out) {
+            info_out->bt = bt;
+            info_out->g = g;
+            info_out->B = dense_batches == 1 ? B : 0;
+            for (int b = 0; b < B; ++b) info_out->map[b] = map[b];
+        }
         int* info_host = reinterpret_cast<int*>(ws->pinned + 2048);
         DGPB_CUDA_TRY(cudaMemcpyAsync(ws->pinned, outd, sizeof(double) * 4 * B, cudaMemcpyDeviceToHost, st));
         DGPB_CUDA_TRY(cudaMemcpyAsync(info_host, bt.info, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
@@ -137,7 +175,7 @@ static int nodes_loglik(Workspace* ws, const dgpb_node* nodes, int U, int64_t n,
 
 // prior draws nu[k] = chol(scale K) z_k for the target nodes
 static int prior_draws(Workspace* ws, const dgpb_node* targets, int M, int64_t n, const double* z, double* nu,
-                       cudaStream_t st) {
+                       const int32_t* keys, cudaStream_t st) {
     for (int k = 0; k < M; ++k) {
         const dgpb_node* nd = &targets[k];
         if (!nd->vecch) continue;
@@ -164,21 +202,30 @@ static int prior_draws(Workspace* ws, const dgpb_node* targets, int M, int64_t n
         KernelDev kds[MAXB];
         int map[MAXB];
         int B = 0;
+        Geom g = make_geom(n, false);
         while (k0 < M && B < MAXB) {
             if (!targets[k0].vecch) {
-                DGPB_TRY(make_kernel_dev(&targets[k0], n, nullptr, &kds[B]));
-                map[B] = k0;
-                ++B;
+                // reuse chol(K) kept from an earlier block update of this I-step (same inputs, same theta)
+                auto it = keys && keys[k0] >= 0 ? ws->cache.find(keys[k0]) : ws->cache.end();
+                if (it != ws->cache.end() && it->second.valid && it->second.n == n) {
+                    DGPB_TRY(launch_trmv(it->second.T, g.ld, g.n, sqrt(targets[k0].scale), z + (int64_t)k0 * n,
+                                         nu + (int64_t)k0 * n, st));
+                } else {
+                    DGPB_TRY(make_kernel_dev(&targets[k0], n, nullptr, &kds[B]));
+                    map[B] = k0;
+                    ++B;
+                }
             }
             ++k0;
         }
-        if (B == 0) break;
-        Geom g = make_geom(n, false);
+        if (B == 0) continue;
         Batch bt;
         double* outd;
         DGPB_TRY(setup_batch(ws, g, B, &bt, &outd));
         DGPB_TRY(assemble(g, kds, nullptr, bt, B, st));
         DGPB_TRY(factorize(g, bt, B, st));
+        for (int b = 0; b < B; ++b)
+            if (keys && keys[map[b]] >= 0) DGPB_TRY(cache_store(ws, keys[map[b]], g, bt, b, st));
         DGPB_TRY(restore_diag_blocks(g, bt, B, st));
         for (int b = 0; b < B; ++b) {
             DGPB_TRY(launch_trmv(bt.T[b], g.ld, g.n, sqrt(targets[map[b]].scale), z + (int64_t)map[b] * n,
@@ -189,6 +236,7 @@ static int prior_draws(Workspace* ws, const dgpb_node* targets, int M, int64_t n
         DGPB_CUDA_TRY(cudaStreamSynchronize(st));
         for (int b = 0; b < B; ++b)
             if (info_host[b] != 0) {
+                if (keys && keys[map[b]] >= 0) ws->cache[keys[map[b]]].valid = false;
                 set_error("prior covariance of target node %d is not positive definite (pivot %d)", map[b], info_host[b]);
                 return DGPB_NOT_PD;
             }
@@ -200,10 +248,12 @@ static int prior_draws(Workspace* ws, const dgpb_node* targets, int M, int64_t n
 
 using namespace dgpb;
 
-extern "C" int dgpb_ess_block(dgpb_ws* ws, const dgpb_node* targets, int n_targets, const int32_t* target_rows_host,
-                              double* layer_out, int64_t layer_width, const dgpb_node* uppers, int n_uppers, int64_t n,
-                              const double* z, const double* u_host, int nu, int* n_prop_host, double* theta_host,
-                              void* stream) {
+extern "C" int dgpb_ess_block_cached(dgpb_ws* ws, const dgpb_node* targets, int n_targets,
+                                     const int32_t* target_rows_host, double* layer_out, int64_t layer_width,
+                                     const dgpb_node* uppers, int n_uppers, int64_t n, const double* z,
+                                     const double* u_host, int nu, int* n_prop_host, double* theta_host,
+                                     const int32_t* target_keys_host, const int32_t* upper_keys_host,
+                                     double* threshold_io_host, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     DGPB_REQUIRE(ws && targets && uppers && layer_out && z && u_host && target_rows_host, "NULL argument");
     DGPB_REQUIRE(n_targets >= 1 && n_uppers >= 1 && n >= 1 && nu >= 3, "bad sizes");
@@ -215,10 +265,14 @@ extern "C" int dgpb_ess_block(dgpb_ws* ws, const dgpb_node* targets, int n_targe
     double* nuv = (double*)pnu;
     double* prop = (double*)pprop;
 
-    DGPB_TRY(prior_draws(ws, targets, n_targets, n, z, nuv, st));
+    DGPB_TRY(prior_draws(ws, targets, n_targets, n, z, nuv, target_keys_host, st));
 
     double log_y = 0.0;
-    DGPB_TRY(nodes_loglik(ws, uppers, n_uppers, n, nullptr, &log_y, st));
+    if (threshold_io_host && *threshold_io_host == *threshold_io_host) {
+        log_y = *threshold_io_host;  // sum of the upper log-likelihoods at the current state is already known
+    } else {
+        DGPB_TRY(nodes_loglik(ws, uppers, n_uppers, n, nullptr, &log_y, st));
+    }
     int ui = 0;
     log_y += log(u_host[ui++]);                       // imputation.py:79
     double theta = 0.0 + (2.0 * M_PI - 0.0) * u_host[ui++];  // uniform(0, 2pi)          imputation.py:81
@@ -238,13 +292,25 @@ extern "C" int dgpb_ess_block(dgpb_ws* ws, const dgpb_node* targets, int n_targe
             DGPB_LAUNCHED();
         }
         double log_yp = 0.0;
-        DGPB_TRY(nodes_loglik(ws, uppers, n_uppers, n, prop, &log_yp, st));
+        DenseBatchInfo info;
+        DGPB_TRY(nodes_loglik(ws, uppers, n_uppers, n, prop, &log_yp, st, &info));
         if (log_yp > log_y) {  // imputation.py:107-110
             for (int k = 0; k < n_targets; ++k) {
                 const int64_t row = target_rows_host[k];
                 DGPB_CUDA_TRY(cudaMemcpyAsync(layer_out + row * n, prop + row * n, sizeof(double) * n,
                                               cudaMemcpyDeviceToDevice, st));
             }
+            // the factors of the accepted proposal are the prior factors these nodes need as targets of the
+            // next layer pair; the accepted log-likelihood is the next threshold when their outputs are fixed
+            if (upper_keys_host) {
+                for (int b = 0; b < info.B; ++b)
+                    if (upper_keys_host[info.map[b]] >= 0)
+                        DGPB_TRY(cache_store(ws, upper_keys_host[info.map[b]], info.g, info.bt, b, st));
+                if (info.B == 0)  // batch not reusable: drop anything stale
+                    for (int u = 0; u < n_uppers; ++u)
+                        if (upper_keys_host[u] >= 0) ws->cache[upper_keys_host[u]].valid = false;
+            }
+            if (threshold_io_host) *threshold_io_host = log_yp;
             break;
         }
         if (theta < 0.0) tmin = theta; else tmax = theta;  // imputation.py:115-118
@@ -257,4 +323,12 @@ extern "C" int dgpb_ess_block(dgpb_ws* ws, const dgpb_node* targets, int n_targe
     }
     if (n_prop_host) *n_prop_host = nprop;
     return DGPB_OK;
+}
+
+extern "C" int dgpb_ess_block(dgpb_ws* ws, const dgpb_node* targets, int n_targets, const int32_t* target_rows_host,
+                              double* layer_out, int64_t layer_width, const dgpb_node* uppers, int n_uppers, int64_t n,
+                              const double* z, const double* u_host, int nu, int* n_prop_host, double* theta_host,
+                              void* stream) {
+    return dgpb_ess_block_cached(ws, targets, n_targets, target_rows_host, layer_out, layer_width, uppers, n_uppers, n, z,
+                                 u_host, nu, n_prop_host, theta_host, nullptr, nullptr, nullptr, stream);
 }

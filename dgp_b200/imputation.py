@@ -32,6 +32,9 @@ class _DeviceLayers:
         self.all_layer = all_layer
         self.n = len(all_layer[0][0].output)
         self.F, self.nodes, self.keep = [], [], []
+        self.threshold = {}   # layer pair -> sum of upper log-likelihoods at the current state (last pair only)
+        # stored factors belong to the previous hyper-parameters / inputs
+        L.check(L.load().dgpb_cache_clear(L.workspace()))
         n = self.n
         for l, layer in enumerate(all_layer):
             for kern in layer:
@@ -62,9 +65,15 @@ class _DeviceLayers:
                 arr[k].output = Fl.data_ptr() + k * n * 8
             self.nodes.append(arr)
 
-    def ess_call(self, l, tks, uks, z, u):
-        """One `dgpb_ess_block` call with explicit draws: z (len(tks) x n) standard normals, u uniforms in the
-        reference's consumption order.  Returns (proposals evaluated, angles tried)."""
+    @staticmethod
+    def _key(l, k):
+        return l * 4096 + k
+
+    def ess_call(self, l, tks, uks, z, u, reuse=True):
+        """One `dgpb_ess_block_cached` call with explicit draws: z (len(tks) x n) standard normals, u uniforms in
+        the reference's consumption order.  Returns (proposals evaluated, angles tried).
+        `reuse`: keep Cholesky factors / the accepted likelihood across block updates of this I-step (results
+        are unchanged: the matrices being re-factored by the reference are identical)."""
         lib = L.load()
         n = self.n
         targets = (L.DgpbNode * len(tks))(*[self.nodes[l][k] for k in tks])
@@ -74,11 +83,27 @@ class _DeviceLayers:
         u = np.ascontiguousarray(u, dtype=np.float64)
         theta = np.zeros(len(u))
         nprop = ctypes.c_int(0)
-        status = lib.dgpb_ess_block(L.workspace(), targets, len(tks), rows.ctypes.data_as(L.c_vp), L.ptr(self.F[l]),
-                                    self.F[l].shape[0], uppers, len(uks), n, L.ptr(zd), u.ctypes.data_as(L.c_vp),
-                                    len(u), ctypes.byref(nprop), theta.ctypes.data_as(L.c_vp), L.stream())
+        tkeys = ukeys = thr = None
+        if reuse:
+            tkeys = np.ascontiguousarray([self._key(l, k) for k in tks], dtype=np.int32)
+            ukeys = np.ascontiguousarray([self._key(l + 1, j) for j in uks], dtype=np.int32)
+            whole = len(tks) == len(self.nodes[l]) and len(uks) == len(self.nodes[l + 1])
+            if whole and l + 2 == len(self.nodes):  # outputs of the uppers are the fixed training targets
+                thr = ctypes.c_double(self.threshold.get(l, float("nan")))
+        status = lib.dgpb_ess_block_cached(
+            L.workspace(), targets, len(tks), rows.ctypes.data_as(L.c_vp), L.ptr(self.F[l]), self.F[l].shape[0], uppers,
+            len(uks), n, L.ptr(zd), u.ctypes.data_as(L.c_vp), len(u), ctypes.byref(nprop),
+            theta.ctypes.data_as(L.c_vp), None if tkeys is None else tkeys.ctypes.data_as(L.c_vp),
+            None if ukeys is None else ukeys.ctypes.data_as(L.c_vp), None if thr is None else ctypes.byref(thr),
+            L.stream())
         self.last_nprop = nprop.value
+        if status != L.DGPB_OK:
+            self.threshold.pop(l, None)
         L.check(status)
+        if thr is not None:
+            self.threshold[l] = thr.value
+        else:
+            self.threshold.pop(l, None)
         return nprop.value, theta[:nprop.value]
 
     def block_update(self, l, tks, uks, max_u=64):

@@ -126,6 +126,25 @@ int dgpb_ess_block(dgpb_ws* ws, const dgpb_node* targets, int n_targets, const i
                    int64_t n, const double* z, const double* u_host, int nu,
                    int* n_prop_host, double* theta_host, void* stream);
 
+/* dgpb_ess_block with factor reuse inside one I-step (the hyper-parameters are fixed between M-steps, so the
+ * reference's repeated Cholesky factorisations of unchanged matrices, imputation.py:63,70-78, can be skipped
+ * without changing any result):
+ *   target_keys_host[k] >= 0 : chol(K) of target k is looked up under this key in the workspace (and stored
+ *                              there when it has to be computed) instead of being re-factored for fmvn;
+ *   upper_keys_host[u]  >= 0 : on acceptance the factor of upper node u is stored under this key -- it is the
+ *                              prior factor that node needs as a target of the next layer pair;
+ *   threshold_io_host        : NaN on entry = compute the threshold likelihoods; otherwise the sum of the upper
+ *                              log-likelihoods at the current state (valid when neither their inputs nor their
+ *                              outputs changed since the value was returned).  On return: the accepted sum.
+ * Any of the three may be NULL.  dgpb_cache_clear invalidates every stored factor (call it whenever a
+ * hyper-parameter, an ordering or a training input changes). */
+int dgpb_ess_block_cached(dgpb_ws* ws, const dgpb_node* targets, int n_targets, const int32_t* target_rows_host,
+                          double* layer_out, int64_t layer_width, const dgpb_node* uppers, int n_uppers,
+                          int64_t n, const double* z, const double* u_host, int nu,
+                          int* n_prop_host, double* theta_host, const int32_t* target_keys_host,
+                          const int32_t* upper_keys_host, double* threshold_io_host, void* stream);
+int dgpb_cache_clear(dgpb_ws* ws);
+
 /* ---- 4. Vecchia ---------------------------------------------------------------------------- */
 
 /* nn()  vecchia.py:42-109: ordered nearest neighbours of the (already ordered, already scaled)
@@ -205,6 +224,8 @@ int dgpb_potrf(dgpb_ws* ws, double* A, int64_t n, int* info_host, void* stream);
  * blocked factorisation is bracketed by CUDA events on its stream.  dgpb_profile_read fills
  * out_host[0..3] = {total ms, launches timed, algorithmic FLOPs of those launches, 0}. */
 int dgpb_profile(int on);
+/* micro-probe of the trailing-update kernel (development aid): out_host = {ms per launch, TFLOP/s} */
+int dgpb_probe_update(dgpb_ws* ws, int64_t n, int B, int flags, int reps, double* out_host);
 int dgpb_profile_read(double* out_host);
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 int64_t dgpb_launch_count(void);
