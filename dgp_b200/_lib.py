@@ -45,6 +45,8 @@ _PROTOS = {
     "dgpb_profile": (ctypes.c_int, [ctypes.c_int]),
     "dgpb_profile_read": (ctypes.c_int, [c_vp]),
     "dgpb_probe_update": (ctypes.c_int, [c_vp, c_i64, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_vp]),
+    "dgpb_probe_factorize": (ctypes.c_int, [c_vp, c_i64, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_vp]),
+    "dgpb_tune": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int]),
     "dgpb_ws_create": (ctypes.c_int, [ctypes.POINTER(c_vp), ctypes.c_int]),
     "dgpb_ws_destroy": (ctypes.c_int, [c_vp]),
     "dgpb_ws_bytes": (c_i64, [c_vp]),

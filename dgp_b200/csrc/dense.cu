@@ -151,121 +151,9 @@ __global__ void rows_init_kernel(double* __restrict__ T, int64_t ld, int n, int 
 // the critical path either way, and this removes one dependent launch per panel), inverts it, and then
 // applies X <- X * inv(L_kk)' to its own 128 rows of the panel with FP64 mma.  CTA 0 publishes L_kk and
 // diag(L_kk) to the side buffer (not into T: sibling CTAs are still reading the unfactored block).
-template <int NU>
-__device__ __forceinline__ void tri_inv_offdiag(const double* sL, double* sD, double* sT, int r0, int c0, int s,
-                                                int tid, int nthr) {
-    // sD[r0.., c0..] (s x s) = -D[r0.., r0..] * ( L[r0.., c0..] * D[c0.., c0..] ),  D lower-triangular blocks.
-    // Thread t owns row a = t / (s/NU) and NU columns b_u = (t % (s/NU)) + u * (s/NU): NU independent
-    // accumulators hide the shared-memory latency of the dot products.  Requires nthr * NU == s * s.
-    const int per = s / NU;
-    const int a = tid / per, b0 = tid % per;
-    double acc[NU];
-#pragma unroll
-    for (int u = 0; u < NU; ++u) acc[u] = 0.0;
-    for (int k = 0; k < s; ++k) {
-        const double l = sL[(r0 + a) * LDS + c0 + k];
-#pragma unroll
-        for (int u = 0; u < NU; ++u) acc[u] += l * sD[(c0 + k) * LDS + c0 + b0 + u * per];  // D[k][b] = 0 for k < b
-    }
-#pragma unroll
-    for (int u = 0; u < NU; ++u) sT[a * 33 + b0 + u * per] = acc[u];
-    __syncthreads();
-#pragma unroll
-    for (int u = 0; u < NU; ++u) acc[u] = 0.0;
-    for (int k = 0; k <= a; ++k) {
-        const double d = sD[(r0 + a) * LDS + r0 + k];
-#pragma unroll
-        for (int u = 0; u < NU; ++u) acc[u] += d * sT[k * 33 + b0 + u * per];
-    }
-#pragma unroll
-    for (int u = 0; u < NU; ++u) sD[(r0 + a) * LDS + c0 + b0 + u * per] = -acc[u];
-    __syncthreads();
-}
-
-// (a) diagonal block: ONE CTA per matrix.  Thread (pi = tid/4, pc = tid%4) keeps its 16 entries of row pi
-//     (columns 4q+pc) in registers; per column j the owners publish the raw column, everybody scales by 1/d
-//     and applies the rank-1 update in registers -- one barrier and no shared-memory read-modify-write per
-//     column.  Then inv(L_kk) by 16x16 substitution + two block levels.  Results go to the side buffer.
-__global__ void __launch_bounds__(256, 1) potf2_kernel(Batch bt, int64_t ld, int npad, int k0) {
-    extern __shared__ double smem[];
-    double* sL = smem;
-    double* sD = sL + 64 * LDS;
-    double* sT = sD + 64 * LDS;
-    __shared__ double colA[2][64];
-    __shared__ double colB[2][64];
-    const int tid = threadIdx.x;
-    const double* __restrict__ T = bt.T[blockIdx.x];
-    const int pi = tid >> 2, pc = tid & 3;
-    double reg[16];
-#pragma unroll
-    for (int q = 0; q < 16; ++q) {
-        int k = 4 * q + pc;
-        reg[q] = (k <= pi) ? T[(int64_t)(k0 + pi) * ld + k0 + k] : 0.0;
-    }
-    for (int idx = tid; idx < 64 * LDS; idx += 256) {
-        sL[idx] = 0.0;
-        sD[idx] = 0.0;
-    }
-    // two columns (j, j+1) per barrier: the 2x2 pivot is factored redundantly by every thread, the
-    // rank-2 update is applied to the register-resident rows
-#pragma unroll
-    for (int j = 0; j < 64; j += 2) {
-        const int qj = j >> 2, buf = (j >> 1) & 1;
-        const bool ownA = (pc == (j & 3)) && (pi >= j);
-        const bool ownB = (pc == (j & 3) + 1) && (pi >= j + 1);
-        if (ownA) colA[buf][pi] = reg[qj];
-        if (ownB) colB[buf][pi] = reg[qj];
-        __syncthreads();
-        const double d0 = colA[buf][j];
-        const double rs0 = rsqrt(d0);
-        const double l10 = colA[buf][j + 1] * rs0;
-        const double d1 = colB[buf][j + 1] - l10 * l10;
-        const double rs1 = rsqrt(d1);
-        if ((!(d0 > 0.0) || !(d1 > 0.0)) && tid == 0) atomicCAS(&bt.info[blockIdx.x], 0, k0 + j + (d0 > 0.0 ? 2 : 1));
-        const double li0 = colA[buf][pi] * rs0;                       // valid for pi > j
-        const double li1 = (colB[buf][pi] - li0 * l10) * rs1;         // valid for pi > j + 1
-        if (pi > j + 1) {
-#pragma unroll
-            for (int q = qj; q < 16; ++q) {
-                const int k = 4 * q + pc;
-                if (k > j + 1 && k <= pi) {
-                    const double lk0 = colA[buf][k] * rs0;
-                    const double lk1 = (colB[buf][k] - lk0 * l10) * rs1;
-                    reg[q] -= li0 * lk0 + li1 * lk1;
-                }
-            }
-        }
-        if (ownA) sL[pi * LDS + j] = (pi == j) ? d0 * rs0 : li0;
-        if (ownB) sL[pi * LDS + j + 1] = (pi == j + 1) ? d1 * rs1 : li1;
-    }
-    __syncthreads();
-
-    // inv(L_kk): 16x16 diagonal blocks by column-parallel substitution, then two block levels
-    if (tid < 64) {
-        int o = (tid >> 4) * 16, c = tid & 15;
-        sD[(o + c) * LDS + o + c] = 1.0 / sL[(o + c) * LDS + o + c];
-        for (int i = c + 1; i < 16; ++i) {
-            double s = 0.0;
-            for (int k = c; k < i; ++k) s += sL[(o + i) * LDS + o + k] * sD[(o + k) * LDS + o + c];
-            sD[(o + i) * LDS + o + c] = -s / sL[(o + i) * LDS + o + i];
-        }
-    }
-    __syncthreads();
-    {
-        const int half = tid >> 7;
-        tri_inv_offdiag<2>(sL, sD, sT + half * 16 * 33, half ? 48 : 16, half ? 32 : 0, 16, tid & 127, 128);
-    }
-    tri_inv_offdiag<4>(sL, sD, sT, 32, 0, 32, tid, 256);
-
-    double* dg = bt.diag[blockIdx.x];
-    double* blk = dg + npad + (size_t)(k0 / NB) * NB * NB;
-    double* dinv = dg + (size_t)npad * (1 + NB);
-    for (int idx = tid; idx < 64 * 64; idx += 256) {
-        blk[idx] = sL[(idx >> 6) * LDS + (idx & 63)];
-        dinv[idx] = sD[(idx >> 6) * LDS + (idx & 63)];
-    }
-    if (tid < 64) dg[k0 + tid] = sL[tid * LDS + tid];
-}
+}  // namespace dgpb
+#include "potf2.cuh"
+namespace dgpb {
 
 // (b) panel rows: X <- X * inv(L_kk)'  on the FP64 tensor path, 128-row tiles, grid-stride over tiles.
 //     105 KB of shared memory and < 128 registers so a CTA co-resides with a trailing-update CTA.
@@ -329,7 +217,6 @@ __global__ void __launch_bounds__(256, 2) trsm_kernel(Batch bt, int64_t ld, int 
     }
 }
 constexpr size_t kTrsmSmem = (size_t)(64 * LDS + TM * LDS) * sizeof(double);
-constexpr size_t kPotf2Smem = (size_t)(2 * 64 * LDS + 32 * 33 + 16) * sizeof(double);
 
 // ------------------------------------------------------------------------------------------------
 // 3. trailing update  C[r,c] -= P_r P_c'  over the lower triangle of rows/cols [lo, row_hi) restricted to
@@ -743,7 +630,7 @@ struct LookAhead {
 static thread_local LookAhead g_la;
 
 static int launch_panel(const Geom& g, const Batch& bt, int B, int k0, int row_hi, cudaStream_t st) {
-    potf2_kernel<<<B, 256, kPotf2Smem, st>>>(bt, g.ld, g.npad, k0);
+    potf2_kernel<<<B, 256, kPotf2Smem, st>>>(bt, g.ld, g.npad, k0, nullptr);
     DGPB_LAUNCHED();
     const int rows = row_hi - (k0 + NB);
     if (rows > 0) {
@@ -767,66 +654,96 @@ static int launch_update(const Batch& bt, int B, int64_t ld, int k0, int K, int 
     return DGPB_OK;
 }
 
-// Right-looking factorisation in super-steps of two 64-column panels:
-//   panel A -> narrow update of panel B's columns (K = 64) -> panel B
-//   -> look-ahead update (K = 128) of the NEXT super-step's 128 columns, on the caller's stream (critical path)
-//   -> bulk update (K = 128) of everything further right, on a side stream.
-// K = 128 halves the read-modify-write traffic of the trailing matrix per flop (16 flop/B instead of 8, ridge
-// of the chip ~5.5) and doubles the DMMA work per tile prologue; the side stream lets the next super-step's
-// panels overlap the bulk update.  Dependencies: bulk_s needs panels_s (event) and bulk_{s-1} (stream order);
-// look-ahead_s needs panels_s (stream order) and bulk_{s-1} (event: both write columns [lo, lo+128)).
+// Tunables (dgpb_tune): width of a hyper-block and the smallest remaining window for which one is used.
+static int g_hb = 512;
+static int g_hb_min_w = 2560;
+static int g_hb_graded = 1;
+
+// Right-looking factorisation on two levels.
+//   HYPER-BLOCK [h0, h1) of up to `g_hb` columns: factored by super-steps of two 64-column panels
+//     panel A -> narrow update of panel B's columns (K = 64) -> panel B -> inner update (K = 128)
+//   where the inner update only touches the hyper-block's own columns [lo2, h1) (all rows below), on the
+//   caller's stream.  Everything to the right of the hyper-block is updated ONCE per hyper-block with
+//   K = h1 - h0 (512): the look-ahead part (the next hyper-block's columns) on the caller's stream, the bulk on a
+//   low-priority side stream where it overlaps the next hyper-block's panels and inner updates.
+// K = 512 reads and writes a trailing tile once per 4 x 128 columns eliminated (64 flop per byte of C traffic
+// instead of 16) and quarters the number of bulk launches.  When the remaining window is small the hyper-block
+// degenerates to one super-step (h1 - h0 = 128): there the critical path, not the tensor pipe, bounds the
+// step, and a longer inner phase would only lengthen it.
+// Dependencies: bulk_h needs the panels of h (event) and bulk_{h-1} (side-stream order); look-ahead_h needs
+// bulk_{h-1} (event: both write columns [h1, h1 + next width)).
 int factorize(const Geom& g, const Batch& bt, int B, cudaStream_t st) {
     DGPB_TRY(configure_once());
-    const int nsuper = (g.npad + 2 * NB - 1) / (2 * NB);
-    DGPB_TRY(g_la.init(2 * (size_t)nsuper + 4));
+    DGPB_TRY(g_la.init(2 * (size_t)(g.npad / (2 * NB) + 2) + 4));
     cudaStream_t side = g_la.side;
     int evi = 0;
     DGPB_CUDA_TRY(cudaEventRecord(g_la.ev[evi], st));
     DGPB_CUDA_TRY(cudaStreamWaitEvent(side, g_la.ev[evi], 0));
     ++evi;
+    auto width_at = [&](int h0) {
+        if (h0 >= g.npad) return 0;
+        const int window = g.aug ? g.npad + 1 + 2 * NB : g.R - h0;  // rows still active at this column
+        int hb = (window >= g_hb_min_w) ? g_hb : 2 * NB;
+        if (g_hb_graded) hb = std::min(hb, std::max(2 * NB, 2 * h0));  // 128, 256, 512: start the side stream early
+        return std::min(hb, g.npad - h0);
+    };
     cudaEvent_t prev_bulk = nullptr;
-    for (int kA = 0; kA < g.npad; kA += 2 * NB) {
-        const int kB = kA + NB;
-        const bool has_b = kB < g.npad;
-        const int rhA = g.aug ? g.npad + 1 + kA + NB : g.R;
-        DGPB_TRY(launch_panel(g, bt, B, kA, rhA, st));
-        int K = NB, lo2 = kA + NB, rh = rhA;
-        if (has_b) {
-            DGPB_TRY(launch_update(bt, B, g.ld, kA, NB, kB, rhA, std::min(kB + NB, rhA), 1, st));
-            const int rhB = g.aug ? g.npad + 1 + kB + NB : g.R;
-            DGPB_TRY(launch_panel(g, bt, B, kB, rhB, st));
-            K = 2 * NB;
-            lo2 = kB + NB;
-            rh = rhB;
-        }
-        if (rh - lo2 <= 0) continue;
-        cudaEvent_t ev_panel = g_la.ev[evi++];
-        DGPB_CUDA_TRY(cudaEventRecord(ev_panel, st));
-        // ---- bulk: columns [lo2 + 128, rh) on the side stream
-        const int blo = lo2 + 2 * UBN;
-        const int brows = rh - blo;
-        cudaEvent_t this_bulk = nullptr;
-        if (brows > 0) {
-            DGPB_CUDA_TRY(cudaStreamWaitEvent(side, ev_panel, 0));
-            if (g_prof.on) {
-                std::lock_guard<std::mutex> lock(g_prof_mutex);
-                if (g_prof.used + 2 > (int)g_prof.ev.size()) DGPB_TRY(g_prof.drain());
-                const int slot = g_prof.used;
-                DGPB_CUDA_TRY(cudaEventRecord(g_prof.ev[slot], side));
-                DGPB_TRY(launch_update(bt, B, g.ld, kA, K, blo, rh, rh, 0, side));
-                DGPB_CUDA_TRY(cudaEventRecord(g_prof.ev[slot + 1], side));
-                g_prof.used += 2;
-                g_prof.flops += (double)B * 0.5 * (double)brows * (double)(brows + 1) * 2.0 * K;
-            } else {
-                DGPB_TRY(launch_update(bt, B, g.ld, kA, K, blo, rh, rh, 0, side));
+    int h0 = 0, hw = width_at(0);
+    while (hw > 0) {
+        const int h1 = h0 + hw;
+        int rh = g.R;
+        for (int kA = h0; kA < h1; kA += 2 * NB) {
+            const int kB = kA + NB;
+            const bool has_b = kB < h1;
+            const int rhA = g.aug ? g.npad + 1 + kA + NB : g.R;
+            DGPB_TRY(launch_panel(g, bt, B, kA, rhA, st));
+            int K = NB, lo2 = kA + NB;
+            rh = rhA;
+            if (has_b) {
+                DGPB_TRY(launch_update(bt, B, g.ld, kA, NB, kB, rhA, std::min(kB + NB, rhA), 1, st));
+                const int rhB = g.aug ? g.npad + 1 + kB + NB : g.R;
+                DGPB_TRY(launch_panel(g, bt, B, kB, rhB, st));
+                K = 2 * NB;
+                lo2 = kB + NB;
+                rh = rhB;
             }
-            this_bulk = g_la.ev[evi++];
-            DGPB_CUDA_TRY(cudaEventRecord(this_bulk, side));
+            if (lo2 < h1) DGPB_TRY(launch_update(bt, B, g.ld, kA, K, lo2, rh, h1, (h1 - lo2) / UBN, st));
         }
-        // ---- look-ahead: the next super-step's columns [lo2, lo2 + 128) on the critical path
-        if (prev_bulk) DGPB_CUDA_TRY(cudaStreamWaitEvent(st, prev_bulk, 0));
-        DGPB_TRY(launch_update(bt, B, g.ld, kA, K, lo2, rh, std::min(lo2 + 2 * UBN, rh), 2, st));
-        prev_bulk = this_bulk;
+        const int hw_next = width_at(h1);
+        if (rh - h1 > 0) {
+            const int K = h1 - h0;
+            cudaEvent_t ev_panel = g_la.ev[evi++];
+            DGPB_CUDA_TRY(cudaEventRecord(ev_panel, st));
+            // ---- bulk: columns [h1 + next width, rh) on the side stream
+            const int blo = h1 + hw_next;
+            const int brows = rh - blo;
+            cudaEvent_t this_bulk = nullptr;
+            if (brows > 0) {
+                DGPB_CUDA_TRY(cudaStreamWaitEvent(side, ev_panel, 0));
+                if (g_prof.on) {
+                    std::lock_guard<std::mutex> lock(g_prof_mutex);
+                    if (g_prof.used + 2 > (int)g_prof.ev.size()) DGPB_TRY(g_prof.drain());
+                    const int slot = g_prof.used;
+                    DGPB_CUDA_TRY(cudaEventRecord(g_prof.ev[slot], side));
+                    DGPB_TRY(launch_update(bt, B, g.ld, h0, K, blo, rh, rh, 0, side));
+                    DGPB_CUDA_TRY(cudaEventRecord(g_prof.ev[slot + 1], side));
+                    g_prof.used += 2;
+                    g_prof.flops += (double)B * 0.5 * (double)brows * (double)(brows + 1) * 2.0 * K;
+                } else {
+                    DGPB_TRY(launch_update(bt, B, g.ld, h0, K, blo, rh, rh, 0, side));
+                }
+                this_bulk = g_la.ev[evi++];
+                DGPB_CUDA_TRY(cudaEventRecord(this_bulk, side));
+            }
+            // ---- look-ahead: the next hyper-block's columns [h1, h1 + next width) on the critical path
+            if (hw_next > 0) {
+                if (prev_bulk) DGPB_CUDA_TRY(cudaStreamWaitEvent(st, prev_bulk, 0));
+                DGPB_TRY(launch_update(bt, B, g.ld, h0, K, h1, rh, std::min(h1 + hw_next, rh), hw_next / UBN, st));
+            }
+            prev_bulk = this_bulk;
+        }
+        h0 = h1;
+        hw = hw_next;
     }
     DGPB_CUDA_TRY(cudaEventRecord(g_la.ev[evi], side));
     DGPB_CUDA_TRY(cudaStreamWaitEvent(st, g_la.ev[evi], 0));
@@ -1007,23 +924,117 @@ int dgpb_probe_update(dgpb_ws* ws, int64_t n, int B, int flags, int reps, double
     double* out;
     DGPB_TRY(setup_batch(ws, g, B, &bt, &out));
     DGPB_CUDA_TRY(cudaMemset(bt.T[0], 0, g.elems() * sizeof(double) * B));
-    const int lo = 128, rows = g.R - lo;
+    const int lo = 512, rows = g.R - lo;
     const int ntr = (int)cdiv(rows, TM);
     cudaEvent_t e0, e1;
     DGPB_CUDA_TRY(cudaEventCreate(&e0));
     DGPB_CUDA_TRY(cudaEventCreate(&e1));
     dim3 grid((unsigned)(ntr * (ntr + 1)), 1, (unsigned)B);
-    update_kernel<<<grid, 256, kUpdateSmem, 0>>>(bt, g.ld, 0, 4, lo, g.R, g.R, 0, flags);
+    const int kc = (flags >> 8) ? (flags >> 8) : 4;  // K = 32 kc (panel columns [0, K); the window starts at 512)
+    flags &= 255;
+    update_kernel<<<grid, 256, kUpdateSmem, 0>>>(bt, g.ld, 0, kc, lo, g.R, g.R, 0, flags);
     DGPB_CUDA_TRY(cudaEventRecord(e0, 0));
-    for (int r = 0; r < reps; ++r) update_kernel<<<grid, 256, kUpdateSmem, 0>>>(bt, g.ld, 0, 4, lo, g.R, g.R, 0, flags);
+    for (int r = 0; r < reps; ++r) update_kernel<<<grid, 256, kUpdateSmem, 0>>>(bt, g.ld, 0, kc, lo, g.R, g.R, 0, flags);
     DGPB_CUDA_TRY(cudaEventRecord(e1, 0));
     DGPB_CUDA_TRY(cudaEventSynchronize(e1));
     float ms = 0.f;
     DGPB_CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
     out_host[0] = ms / reps;
-    out_host[1] = (double)B * 0.5 * (double)rows * (double)(rows + 1) * 2.0 * 128.0 / (out_host[0] * 1e-3) / 1e12;
+    out_host[1] = (double)B * 0.5 * (double)rows * (double)(rows + 1) * 2.0 * 32.0 * kc / (out_host[0] * 1e-3) / 1e12;
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
+    return DGPB_OK;
+}
+
+// Probe: time `reps` complete batched log-likelihood pipelines (assemble K from synthetic inputs, factorise,
+// reduce) of B matrices.  aug = 1 uses the [[K],[y'],[I]] layout of the gradient path (B must be 1).
+// out_host = {ms per pipeline, TFLOP/s counting n^3/3 (plain) or n^3 (aug) per matrix}.
+__global__ void probe_fill_kernel(double* __restrict__ x, int64_t len, unsigned seed) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= len) return;
+    unsigned h = (unsigned)i * 2654435761u + seed;
+    h ^= h >> 15; h *= 2246822519u; h ^= h >> 13; h *= 3266489917u; h ^= h >> 16;
+    x[i] = (double)h * (1.0 / 4294967296.0);
+}
+
+int dgpb_probe_factorize(dgpb_ws* ws, int64_t n, int B, int aug, int reps, double* out_host) {
+    DGPB_REQUIRE(ws && out_host && n >= 64 && B >= 1 && B <= MAXB && reps >= 1, "bad argument");
+    DGPB_REQUIRE(!aug || B == 1, "aug probe is single-matrix");
+    const int D = 8;
+    void* px;
+    DGPB_TRY(ws->reserve(SLOT_MISC, sizeof(double) * (size_t)(D + 1) * n * B, &px));
+    double* X = (double*)px;
+    probe_fill_kernel<<<(unsigned)cdiv((int64_t)(D + 1) * n * B, 256), 256>>>(X, (int64_t)(D + 1) * n * B, 12345u);
+    KernelDev kds[MAXB];
+    const double* ys[MAXB];
+    ScaleArgs sa;
+    for (int b = 0; b < B; ++b) {
+        KernelDev& kd = kds[b];
+        kd.kind = DGPB_SEXP;
+        kd.D = D;
+        kd.ard = 0;
+        kd.stride = 1;
+        for (int d = 0; d < D; ++d) {
+            kd.ptr[d] = X + ((size_t)b * (D + 1) + d) * n;
+            kd.len[d] = 0.6;
+        }
+        kd.nugget = 1e-4;
+        ys[b] = X + ((size_t)b * (D + 1) + D) * n;
+        sa.scale[b] = 1.0;
+        sa.est[b] = 0;
+    }
+    Geom g = make_geom(n, aug != 0);
+    Batch bt;
+    double* out;
+    DGPB_TRY(setup_batch(ws, g, B, &bt, &out));
+    cudaEvent_t e0, e1;
+    DGPB_CUDA_TRY(cudaEventCreate(&e0));
+    DGPB_CUDA_TRY(cudaEventCreate(&e1));
+    cudaStream_t st = 0;
+    auto once = [&]() -> int {
+        DGPB_TRY(assemble(g, kds, ys, bt, B, st));
+        DGPB_TRY(factorize(g, bt, B, st));
+        DGPB_TRY(reduce_logdet_quad(g, bt, B, sa, out, st));
+        return DGPB_OK;
+    };
+    DGPB_TRY(once());
+    DGPB_CUDA_TRY(cudaEventRecord(e0, st));
+    for (int r = 0; r < reps; ++r) DGPB_TRY(once());
+    DGPB_CUDA_TRY(cudaEventRecord(e1, st));
+    DGPB_CUDA_TRY(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    DGPB_CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    int info[MAXB];
+    DGPB_CUDA_TRY(cudaMemcpy(info, bt.info, sizeof(int) * B, cudaMemcpyDeviceToHost));
+    for (int b = 0; b < B; ++b) DGPB_REQUIRE(info[b] == 0, "probe matrix not positive definite");
+    out_host[0] = ms / reps;
+    const double nn = (double)n;
+    out_host[1] = (double)B * nn * nn * nn * (aug ? 1.0 : 1.0 / 3.0) / (out_host[0] * 1e-3) / 1e12;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return DGPB_OK;
+}
+
+// Development/benchmark tunables: "hb" = hyper-block width (multiple of 128), "hb_min_w" = smallest remaining
+// window factored with hyper-blocks, "hb_graded" = 128/256/512 ramp at the start, "ess_batch" = matrices per
+// speculative ESS wave.  Returns DGPB_BAD_ARG for an unknown key.
+int dgpb_tune(const char* key, int value) {
+    DGPB_REQUIRE(key != nullptr, "NULL key");
+    const std::string k(key);
+    if (k == "hb") {
+        DGPB_REQUIRE(value >= 128 && value % 128 == 0 && value <= 2048, "hb must be a multiple of 128 in [128, 2048]");
+        g_hb = value;
+    } else if (k == "hb_min_w") {
+        DGPB_REQUIRE(value >= 0, "hb_min_w must be >= 0");
+        g_hb_min_w = value;
+    } else if (k == "ess_batch") {
+        DGPB_REQUIRE(value >= 0 && value <= MAXB, "ess_batch out of range");
+        g_ess_target_b = value;
+    } else if (k == "hb_graded") {
+        g_hb_graded = value != 0;
+    } else {
+        DGPB_REQUIRE(false, "unknown tunable");
+    }
     return DGPB_OK;
 }
 

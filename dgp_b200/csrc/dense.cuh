@@ -65,4 +65,7 @@ int setup_batch(Workspace* ws, const Geom& g, int B, Batch* bt, double** out_dev
 int loglik_batch_device(Workspace* ws, const KernelDev* kds, const double* const* ys, const ScaleArgs& sa, int B,
                         int64_t n, Batch* bt_out, Geom* g_out, double** out_dev, cudaStream_t st);
 
+// matrices per speculative ESS wave (ess.cu)
+extern int g_ess_target_b;
+
 }  // namespace dgpb

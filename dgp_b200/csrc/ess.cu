@@ -248,6 +248,65 @@ static int prior_draws(Workspace* ws, const dgpb_node* targets, int M, int64_t n
 
 using namespace dgpb;
 
+namespace dgpb {
+
+int g_ess_target_b = 8;  // matrices per speculative wave (dgpb_tune "ess_batch"); 0/1 = one proposal at a time
+
+// Log-likelihood sums of `nitems` candidate states of the layer below (srcs[i] = latent layer image read by the
+// upper nodes, NULL = the nodes' own `src`), all U upper nodes dense and nitems * U <= MAXB: ONE batched
+// factorisation, matrix slot of (item i, node u) = i * U + u.  pd[i] = 0 if one of the item's matrices is not
+// positive definite (bad_node[i] = which).  The caller decides what an indefinite item means: the reference
+// only ever evaluates items up to the first accepted one.
+static int dense_items_loglik(Workspace* ws, const dgpb_node* nodes, int U, int64_t n, const double* const* srcs,
+                              int nitems, double* sums, int* pd, int* bad_node, Batch* bt_out, Geom* g_out,
+                              cudaStream_t st) {
+    const int B = nitems * U;
+    DGPB_REQUIRE(B >= 1 && B <= MAXB, "wave does not fit one batch");
+    KernelDev kds[MAXB];
+    const double* ys[MAXB];
+    ScaleArgs sa;
+    for (int i = 0; i < nitems; ++i)
+        for (int u = 0; u < U; ++u) {
+            const int b = i * U + u;
+            DGPB_TRY(make_kernel_dev(&nodes[u], n, srcs[i], &kds[b]));
+            ys[b] = nodes[u].output;
+            sa.scale[b] = nodes[u].scale;
+            sa.est[b] = 0;
+        }
+    double* outd;
+    DGPB_TRY(loglik_batch_device(ws, kds, ys, sa, B, n, bt_out, g_out, &outd, st));
+    int* info_host = reinterpret_cast<int*>(ws->pinned + 2048);
+    DGPB_CUDA_TRY(cudaMemcpyAsync(ws->pinned, outd, sizeof(double) * 4 * B, cudaMemcpyDeviceToHost, st));
+    DGPB_CUDA_TRY(cudaMemcpyAsync(info_host, bt_out->info, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
+    DGPB_CUDA_TRY(cudaStreamSynchronize(st));
+    for (int i = 0; i < nitems; ++i) {
+        double s = 0.0;
+        pd[i] = 1;
+        bad_node[i] = -1;
+        for (int u = 0; u < U; ++u) {  // same left-to-right order as imputation.py:70-78
+            const int b = i * U + u;
+            if (info_host[b] != 0 && pd[i]) {
+                pd[i] = 0;
+                bad_node[i] = u;
+            }
+            const double sc = nodes[u].scale;
+            s += -0.5 * (ws->pinned[4 * b] + (double)n * log(sc) + ws->pinned[4 * b + 1] / sc);
+        }
+        sums[i] = s;
+    }
+    return DGPB_OK;
+}
+
+}  // namespace dgpb
+
+// The angles ESS will try are known in advance: a rejection is the only branch of the bracket rule
+// (imputation.py:111-119), so theta_{k+1} depends on theta_k and the next uniform, never on a likelihood value.
+// Proposals are therefore evaluated in WAVES of consecutive candidate angles batched into one factorisation
+// (wave size = g_ess_target_b / n_uppers) and the first accepted one wins; candidates after it are discarded.
+// Accept/shrink decisions, the angles reported and the number of uniforms consumed are exactly those of the
+// one-at-a-time loop; what changes is that a 2-node upper layer fills the GPU with 4 proposals at once instead
+// of running a critical-path-bound batch of 2.  When the threshold likelihood is not cached it rides along in
+// the first wave.
 extern "C" int dgpb_ess_block_cached(dgpb_ws* ws, const dgpb_node* targets, int n_targets,
                                      const int32_t* target_rows_host, double* layer_out, int64_t layer_width,
                                      const dgpb_node* uppers, int n_uppers, int64_t n, const double* z,
@@ -259,61 +318,133 @@ extern "C" int dgpb_ess_block_cached(dgpb_ws* ws, const dgpb_node* targets, int 
     DGPB_REQUIRE(n_targets >= 1 && n_uppers >= 1 && n >= 1 && nu >= 3, "bad sizes");
     for (int k = 0; k < n_targets; ++k)
         DGPB_REQUIRE(target_rows_host[k] >= 0 && target_rows_host[k] < layer_width, "target row out of range");
+    bool all_dense = true;
+    for (int u = 0; u < n_uppers; ++u) all_dense = all_dense && !uppers[u].vecch;
+    constexpr int kMaxWave = 8;
+    int cap = 1;  // candidate angles per wave
+    if (all_dense && n_uppers <= MAXB) cap = std::max(1, std::min(kMaxWave, std::min(g_ess_target_b, (int)MAXB) / n_uppers));
+    const bool batched = all_dense && n_uppers <= MAXB;
+
     void *pnu, *pprop;
+    const size_t layer_elems = (size_t)layer_width * n;
     DGPB_TRY(ws->reserve(SLOT_NU, sizeof(double) * (size_t)n_targets * n, &pnu));
-    DGPB_TRY(ws->reserve(SLOT_PROP, sizeof(double) * (size_t)layer_width * n, &pprop));
+    DGPB_TRY(ws->reserve(SLOT_PROP, sizeof(double) * layer_elems * cap, &pprop));
     double* nuv = (double*)pnu;
     double* prop = (double*)pprop;
 
     DGPB_TRY(prior_draws(ws, targets, n_targets, n, z, nuv, target_keys_host, st));
 
     double log_y = 0.0;
-    if (threshold_io_host && *threshold_io_host == *threshold_io_host) {
+    const bool have_thr = threshold_io_host && *threshold_io_host == *threshold_io_host;
+    bool thr_pending = false;  // threshold to be computed together with the first wave
+    if (have_thr) {
         log_y = *threshold_io_host;  // sum of the upper log-likelihoods at the current state is already known
+    } else if (batched && (cap + 1) * n_uppers <= MAXB) {
+        thr_pending = true;
     } else {
         DGPB_TRY(nodes_loglik(ws, uppers, n_uppers, n, nullptr, &log_y, st));
     }
     int ui = 0;
-    log_y += log(u_host[ui++]);                       // imputation.py:79
+    const double log_u0 = log(u_host[ui++]);                 // imputation.py:79
+    if (!thr_pending) log_y += log_u0;
     double theta = 0.0 + (2.0 * M_PI - 0.0) * u_host[ui++];  // uniform(0, 2pi)          imputation.py:81
     double tmin = theta - 2.0 * M_PI, tmax = theta;
 
     // rows of the layer that are not being updated are shared by every proposal
-    DGPB_CUDA_TRY(cudaMemcpyAsync(prop, layer_out, sizeof(double) * (size_t)layer_width * n, cudaMemcpyDeviceToDevice, st));
+    for (int s = 0; s < cap; ++s)
+        DGPB_CUDA_TRY(cudaMemcpyAsync(prop + s * layer_elems, layer_out, sizeof(double) * layer_elems,
+                                      cudaMemcpyDeviceToDevice, st));
     int nprop = 0;
     while (true) {
-        if (theta_host) theta_host[nprop] = theta;
-        ++nprop;
-        const double c = cos(theta), s = sin(theta);
-        for (int k = 0; k < n_targets; ++k) {
-            const int64_t row = target_rows_host[k];
-            propose_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(prop + row * n, layer_out + row * n, nuv + (int64_t)k * n,
-                                                                  c, s, n);
-            DGPB_LAUNCHED();
+        // ---- candidate angles of this wave (each one assumes every earlier one was rejected)
+        double thetas[kMaxWave];
+        const int S = std::max(1, std::min(cap, 1 + (nu - ui)));
+        thetas[0] = theta;
+        {
+            double lmin = tmin, lmax = tmax;
+            for (int s = 1; s < S; ++s) {
+                if (thetas[s - 1] < 0.0) lmin = thetas[s - 1]; else lmax = thetas[s - 1];  // imputation.py:115-118
+                thetas[s] = lmin + (lmax - lmin) * u_host[ui + s - 1];                     // imputation.py:119
+            }
         }
-        double log_yp = 0.0;
-        DenseBatchInfo info;
-        DGPB_TRY(nodes_loglik(ws, uppers, n_uppers, n, prop, &log_yp, st, &info));
-        if (log_yp > log_y) {  // imputation.py:107-110
+        for (int s = 0; s < S; ++s) {
+            const double c = cos(thetas[s]), sn = sin(thetas[s]);
             for (int k = 0; k < n_targets; ++k) {
                 const int64_t row = target_rows_host[k];
-                DGPB_CUDA_TRY(cudaMemcpyAsync(layer_out + row * n, prop + row * n, sizeof(double) * n,
+                propose_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(prop + s * layer_elems + row * n, layer_out + row * n,
+                                                                      nuv + (int64_t)k * n, c, sn, n);
+                DGPB_LAUNCHED();
+            }
+        }
+        // ---- likelihoods of the wave
+        double sums[kMaxWave + 1];
+        int pd[kMaxWave + 1], bad[kMaxWave + 1];
+        Batch bt;
+        Geom g;
+        DenseBatchInfo info;
+        int first = 0;  // index of candidate 0 in sums[]
+        if (batched) {
+            const double* srcs[kMaxWave + 1];
+            int ni = 0;
+            if (thr_pending) srcs[ni++] = nullptr;
+            first = ni;
+            for (int s = 0; s < S; ++s) srcs[ni++] = prop + s * layer_elems;
+            DGPB_TRY(dense_items_loglik(ws, uppers, n_uppers, n, srcs, ni, sums, pd, bad, &bt, &g, st));
+            if (thr_pending) {
+                if (!pd[0]) {
+                    set_error("covariance of upper node %d is not positive definite", bad[0]);
+                    return DGPB_NOT_PD;
+                }
+                log_y = sums[0] + log_u0;
+                thr_pending = false;
+            }
+        } else {
+            DGPB_TRY(nodes_loglik(ws, uppers, n_uppers, n, prop, &sums[0], st, &info));
+            pd[0] = 1;
+        }
+        // ---- replay the one-at-a-time decisions over the wave
+        int accepted = -1;
+        for (int s = 0; s < S; ++s) {
+            if (theta_host) theta_host[nprop] = thetas[s];
+            ++nprop;
+            if (!pd[first + s]) {
+                if (n_prop_host) *n_prop_host = nprop;
+                set_error("covariance of upper node %d is not positive definite (proposal %d)", bad[first + s], nprop);
+                return DGPB_NOT_PD;
+            }
+            if (sums[first + s] > log_y) {  // imputation.py:107-110
+                accepted = s;
+                break;
+            }
+            if (thetas[s] < 0.0) tmin = thetas[s]; else tmax = thetas[s];  // imputation.py:115-118
+            if (s + 1 < S) ++ui;  // the uniform that produced thetas[s + 1]
+        }
+        if (accepted >= 0) {
+            const double* pa = prop + accepted * layer_elems;
+            for (int k = 0; k < n_targets; ++k) {
+                const int64_t row = target_rows_host[k];
+                DGPB_CUDA_TRY(cudaMemcpyAsync(layer_out + row * n, pa + row * n, sizeof(double) * n,
                                               cudaMemcpyDeviceToDevice, st));
             }
             // the factors of the accepted proposal are the prior factors these nodes need as targets of the
             // next layer pair; the accepted log-likelihood is the next threshold when their outputs are fixed
             if (upper_keys_host) {
-                for (int b = 0; b < info.B; ++b)
-                    if (upper_keys_host[info.map[b]] >= 0)
-                        DGPB_TRY(cache_store(ws, upper_keys_host[info.map[b]], info.g, info.bt, b, st));
-                if (info.B == 0)  // batch not reusable: drop anything stale
+                if (batched) {
                     for (int u = 0; u < n_uppers; ++u)
-                        if (upper_keys_host[u] >= 0) ws->cache[upper_keys_host[u]].valid = false;
+                        if (upper_keys_host[u] >= 0)
+                            DGPB_TRY(cache_store(ws, upper_keys_host[u], g, bt, (first + accepted) * n_uppers + u, st));
+                } else {
+                    for (int b = 0; b < info.B; ++b)
+                        if (upper_keys_host[info.map[b]] >= 0)
+                            DGPB_TRY(cache_store(ws, upper_keys_host[info.map[b]], info.g, info.bt, b, st));
+                    if (info.B == 0)  // batch not reusable: drop anything stale
+                        for (int u = 0; u < n_uppers; ++u)
+                            if (upper_keys_host[u] >= 0) ws->cache[upper_keys_host[u]].valid = false;
+                }
             }
-            if (threshold_io_host) *threshold_io_host = log_yp;
+            if (threshold_io_host) *threshold_io_host = sums[first + accepted];
             break;
         }
-        if (theta < 0.0) tmin = theta; else tmax = theta;  // imputation.py:115-118
         if (ui >= nu) {
             if (n_prop_host) *n_prop_host = nprop;
             set_error("ESS ran out of uniforms after %d proposals", nprop);

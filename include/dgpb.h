@@ -227,6 +227,13 @@ int dgpb_profile(int on);
 /* micro-probe of the trailing-update kernel (development aid): out_host = {ms per launch, TFLOP/s} */
 int dgpb_probe_update(dgpb_ws* ws, int64_t n, int B, int flags, int reps, double* out_host);
 int dgpb_profile_read(double* out_host);
+/* micro-probe of the whole batched likelihood pipeline (assemble, factorise, reduce) on synthetic inputs:
+ * out_host = {ms per pipeline, TFLOP/s counting n^3/3 (aug = 0) or n^3 (aug = 1, B = 1) per matrix} */
+int dgpb_probe_factorize(dgpb_ws* ws, int64_t n, int B, int aug, int reps, double* out_host);
+/* development/benchmark tunables of the blocked factorisation: "hb" (hyper-block width, multiple of 128),
+ * "hb_min_w" (smallest remaining window factored with hyper-blocks), "hb_graded" (0/1: ramp the first hyper-blocks
+ * 128, 256, 512), and of the ESS loop: "ess_batch" (matrices per speculative wave; <= 1 = one proposal at a time) */
+int dgpb_tune(const char* key, int value);
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 int64_t dgpb_launch_count(void);
 

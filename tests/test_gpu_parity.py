@@ -161,6 +161,52 @@ def test_potrf_and_gemm_building_blocks():
     assert np.max(np.abs(C.cpu().numpy() - A @ B.T)) <= 1e-12 * K
 
 
+def test_hyper_block_factorisation_variants():
+    """The two-level blocked factorisation (hyper-blocks of 128 / 256 / 512 columns, forced on at small n through
+    dgpb_tune) gives the same factor, log-likelihood, gradient and inverse as LAPACK for every setting."""
+    import ctypes
+    import dgp_b200 as D
+    from dgp_b200 import _lib as L
+    from oracle import dgp_oracle as O
+
+    lib = L.load()
+    rng = np.random.default_rng(17)
+    n = 1100
+    A = rng.standard_normal((n, n))
+    A = A @ A.T / n + np.eye(n)
+    d = 5
+    length = rng.uniform(0.6, 1.5, d)
+    X = rng.uniform(0, 1, (n, d))
+    y = np.sin(X.sum(1, keepdims=True) * 2) + 0.1 * rng.standard_normal((n, 1))
+    ll0 = O.loglik_dense(X, y, length, 0.7, 1e-3, "sexp")
+    f0, g0, s0 = O.nllik_grad_dense(X, y, length, 0.7, 1e-3, "sexp", True, True)
+    K = O.k_matrix(X, length, 1e-3, "sexp")
+    try:
+        for hb, min_w in ((128, 0), (256, 0), (512, 0), (512, 700), (1024, 0)):
+            L.check(lib.dgpb_tune(b"hb", hb))
+            L.check(lib.dgpb_tune(b"hb_min_w", min_w))
+            Ad = L.to_dev(A)
+            info = ctypes.c_int(-1)
+            L.check(lib.dgpb_potrf(L.workspace(), L.ptr(Ad), n, ctypes.byref(info), L.stream()))
+            assert info.value == 0
+            Lc = np.tril(Ad.cpu().numpy())
+            assert np.max(np.abs(Lc @ Lc.T - A)) <= 1e-12 * n, (hb, min_w)
+            k = D.kernel(length=length.copy(), name="sexp", nugget=1e-3, scale=0.7, nugget_est=True, scale_est=True)
+            k.input, k.output, k.D, k.prior_name = X, y.copy(), d, None
+            ll = k.log_likelihood_func()
+            assert abs(ll - ll0) <= 1e-9 * abs(ll0), (hb, min_w, ll, ll0)
+            f, gr = k.llik(k.log_t().copy())
+            assert abs(f[0] - f0) <= 1e-9 * max(1.0, abs(f0)), (hb, min_w)
+            assert np.max(np.abs(gr - g0)) <= 1e-8 * max(1.0, np.max(np.abs(g0))), (hb, min_w, gr, g0)
+            k.compute_stats()
+            assert np.max(np.abs(K @ k.Rinv - np.eye(n))) <= 1e-8, (hb, min_w)
+        with pytest.raises(ValueError):
+            L.check(lib.dgpb_tune(b"no_such_knob", 1))
+    finally:
+        L.check(lib.dgpb_tune(b"hb", 512))
+        L.check(lib.dgpb_tune(b"hb_min_w", 2560))
+
+
 # ------------------------------------------------------------------------------------------------ 5
 def _gp_scales(c, xt):
     from oracle import dgp_oracle as O
@@ -317,9 +363,22 @@ def _load_layers(g, prefix, widths, name, vecch):
     return layers
 
 
-def test_ess_replay_identical_decisions(golden_ess):
+@pytest.mark.parametrize("ess_batch", [8, 1, 3, 32])
+def test_ess_replay_identical_decisions(golden_ess, ess_batch):
+    """Replays the reference's ESS sweeps with its own normal / uniform draws.  `ess_batch` is the size of the
+    speculative proposal wave (1 = one proposal at a time): every setting must consume exactly the reference's
+    uniforms and try exactly its angles."""
+    from dgp_b200 import _lib as L
     from dgp_b200.imputation import _DeviceLayers
 
+    L.check(L.load().dgpb_tune(b"ess_batch", ess_batch))
+    try:
+        _ess_replay(golden_ess, _DeviceLayers)
+    finally:
+        L.check(L.load().dgpb_tune(b"ess_batch", 8))
+
+
+def _ess_replay(golden_ess, _DeviceLayers):
     g = golden_ess
     for ci in range(int(g["ncases"])):
         p = f"c{ci}_"
