@@ -112,6 +112,11 @@ def load():
             fn = getattr(lib, name)
             fn.restype = res
             fn.argtypes = args
+        # development/benchmark overrides of the library tunables: DGPB_TUNE="ess_batch=16,hb=512"
+        for item in filter(None, os.environ.get("DGPB_TUNE", "").split(",")):
+            key, _, val = item.partition("=")
+            if lib.dgpb_tune(key.strip().encode(), int(val)) != DGPB_OK:
+                raise ValueError(f"dgp_b200: bad DGPB_TUNE entry {item!r}")
         _lib = lib
     return _lib
 
@@ -191,11 +196,77 @@ def empty(shape, dtype="f8"):
     return torch.empty(shape, dtype=torch.float64 if dtype == "f8" else torch.int64, device=device())
 
 
+class PredictCache:
+    """Per-call memo of a predict() pass (`with predict_cache():`).  Identical column selections of the same
+    device tensor return the SAME tensor object, which lets the GP nodes recognise that they are asked for the
+    neighbours of identical query points; uploaded training inputs and neighbour arrays are shared between the
+    nodes / imputations that would recompute them bit for bit.  Every keyed tensor is kept alive here, so a
+    data_ptr can never be recycled while it is a key."""
+
+    def __init__(self):
+        self.cols, self.cats, self.uploads, self.nn = {}, {}, [], []
+
+
+def predict_cache():
+    import contextlib
+
+    @contextlib.contextmanager
+    def ctx():
+        prev = getattr(_tls, "pcache", None)
+        _tls.pcache = PredictCache() if prev is None else prev
+        try:
+            yield _tls.pcache
+        finally:
+            _tls.pcache = prev
+
+    return ctx()
+
+
+def active_cache():
+    return getattr(_tls, "pcache", None)
+
+
 def cols(t, idx):
     """t[:, idx] for a device tensor and a numpy/list column index (contiguous copy)."""
     torch = torch_mod()
-    ix = torch.as_tensor(np.atleast_1d(np.asarray(idx)).astype(np.int64), device=t.device)
-    return t.index_select(1, ix).contiguous()
+    idx = np.atleast_1d(np.asarray(idx)).astype(np.int64)
+    pc = active_cache()
+    key = (t.data_ptr(), tuple(t.shape), tuple(int(i) for i in idx))
+    if pc is not None and key in pc.cols:
+        return pc.cols[key][1]
+    ix = torch.as_tensor(idx, device=t.device)
+    out = t.index_select(1, ix).contiguous()
+    if pc is not None:
+        pc.cols[key] = (t, out)
+    return out
+
+
+def cat_cols(a, b):
+    """torch.cat((a, b), 1), memoised per predict pass (b may be None)."""
+    if b is None:
+        return a.contiguous()
+    pc = active_cache()
+    key = (a.data_ptr(), tuple(a.shape), b.data_ptr(), tuple(b.shape))
+    if pc is not None and key in pc.cats:
+        return pc.cats[key][2]
+    out = torch_mod().cat((a, b), 1).contiguous()
+    if pc is not None:
+        pc.cats[key] = (a, b, out)
+    return out
+
+
+def to_dev_shared(a):
+    """to_dev for read-only training inputs: within a predict pass arrays with identical contents share one
+    upload (the nodes of a first layer all see the same design matrix, once per imputation)."""
+    pc = active_cache()
+    if pc is None:
+        return to_dev(a)
+    for host, dev in pc.uploads:
+        if host is a or (host.shape == a.shape and np.array_equal(host, a)):
+            return dev
+    dev = to_dev(a)
+    pc.uploads.append((a, dev))
+    return dev
 
 
 def ptr(t):

@@ -9,6 +9,7 @@
 // Reference semantics: dgpsi/kernel_class.py:304-359 (k_matrix), :403-449 (llik), :481-492
 // (log_likelihood_func), :735-748 (compute_stats); dgpsi/functions.py:16-121.
 #include "dense.cuh"
+#include "vecchia.cuh"
 
 #include <algorithm>
 #include <mutex>
@@ -39,12 +40,15 @@ __device__ __forceinline__ void cp_async_wait() {
 // ------------------------------------------------------------------------------------------------
 // One CTA builds a 64x64 tile (lower-triangular tile pairs only).  Scaled coordinates of the 64 row
 // points and 64 column points are staged in shared memory (coalesced loads from the variable-major
-// sources); each thread then produces 16 entries with consecutive threads on consecutive columns so
-// the stores are full 128-byte lines.  HBM-write bound: 8 n^2 / 2 bytes (lower) or 8 n^2 (MIRROR).
+// sources); each thread then produces a 4 x 4 register tile -- rows 4ty..4ty+3, columns tx + 16c -- so one
+// dimension costs 6 shared-memory loads per 16 entries (the one-entry-per-thread form was LDS-bound at
+// 2 loads per entry per dimension) and consecutive threads still store consecutive columns (128-byte lines).
+// HBM-write bound: 8 n^2 / 2 bytes (lower) or 8 n^2 (MIRROR).  Arithmetic per entry is unchanged: squared
+// differences accumulated with separate multiply and add in ascending d (what scipy's pdist does).
 template <bool MIRROR>
 __global__ void __launch_bounds__(256) kbuild_kernel(KernelDev kd, double* __restrict__ T, int64_t ld, int n, int npad,
                                                      const double* __restrict__ wdiag) {
-    __shared__ double xi[kMaxDim][64];
+    __shared__ __align__(16) double xi[kMaxDim][64];
     __shared__ double xj[kMaxDim][64];
     const int tid = threadIdx.x;
     const int t = blockIdx.x;
@@ -58,27 +62,65 @@ __global__ void __launch_bounds__(256) kbuild_kernel(KernelDev kd, double* __res
         xj[d][l] = gj < n ? kd.x(d, gj) : 0.0;
     }
     __syncthreads();
-#pragma unroll 4
-    for (int e = 0; e < 16; ++e) {
-        int idx = tid + 256 * e;
-        int li = idx >> 6, lj = idx & 63;
-        int gi = ti * 64 + li, gj = tj * 64 + lj;
-        if (gj > gi) continue;
-        double v;
-        if (gi == gj) {
-            v = gi < n ? 1.0 + kd.nugget * (wdiag ? wdiag[gi] : 1.0) : 1.0;
-        } else if (gi >= n) {
-            v = 0.0;
-        } else {
-            v = corr_pair(kd.kind, D, [&](int d) { return xi[d][li]; }, [&](int d) { return xj[d][lj]; });
+    const int ty = tid >> 4, tx = tid & 15;
+    double acc[4][4];   // sexp: squared distance; matern: running product of the polynomial factors
+    double sr[4][4];    // matern: sum of r
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            acc[r][c] = kd.kind == DGPB_SEXP ? 0.0 : 1.0;
+            sr[r][c] = 0.0;
         }
-        if (MIRROR) {
-            if (gi < n) {
-                T[(int64_t)gi * ld + gj] = v;
-                T[(int64_t)gj * ld + gi] = v;
-            }
+    for (int d = 0; d < D; ++d) {
+        const double2 a01 = *reinterpret_cast<const double2*>(&xi[d][4 * ty]);
+        const double2 a23 = *reinterpret_cast<const double2*>(&xi[d][4 * ty + 2]);
+        const double av[4] = {a01.x, a01.y, a23.x, a23.y};
+        double bv[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) bv[c] = xj[d][tx + 16 * c];
+        if (kd.kind == DGPB_SEXP) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const double df = av[r] - bv[c];
+                    acc[r][c] = __dadd_rn(acc[r][c], __dmul_rn(df, df));
+                }
         } else {
-            T[(int64_t)gi * ld + gj] = v;
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const double rr = fabs(av[r] - bv[c]);
+                    acc[r][c] *= 1.0 + kSqrt5 * rr + (5.0 / 3.0) * (rr * rr);
+                    sr[r][c] += rr;
+                }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int gi = ti * 64 + 4 * ty + r;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int gj = tj * 64 + tx + 16 * c;
+            if (gj > gi) continue;
+            double v;
+            if (gi == gj) {
+                v = gi < n ? 1.0 + kd.nugget * (wdiag ? wdiag[gi] : 1.0) : 1.0;
+            } else if (gi >= n) {
+                v = 0.0;
+            } else {
+                v = kd.kind == DGPB_SEXP ? exp(-acc[r][c]) : acc[r][c] * exp(-kSqrt5 * sr[r][c]);
+            }
+            if (MIRROR) {
+                if (gi < n) {
+                    T[(int64_t)gi * ld + gj] = v;
+                    T[(int64_t)gj * ld + gi] = v;
+                }
+            } else {
+                T[(int64_t)gi * ld + gj] = v;
+            }
         }
     }
 }
@@ -1030,6 +1072,8 @@ int dgpb_tune(const char* key, int value) {
     } else if (k == "ess_batch") {
         DGPB_REQUIRE(value >= 0 && value <= MAXB, "ess_batch out of range");
         g_ess_target_b = value;
+    } else if (k == "knn_mma") {
+        knn_set_mma(value);
     } else if (k == "hb_graded") {
         g_hb_graded = value != 0;
     } else {

@@ -13,101 +13,6 @@ namespace dgpb {
 
 
 // ------------------------------------------------------------------------------------------------
-// kNN.  Distances are sum_k (a_k-b_k)^2 with separate multiply and add in ascending k (what the CPU
-// libraries compute) so the index sets match bit for bit; ties keep the smaller index.
-// Each thread owns one query and scans candidate tiles staged in shared memory, keeping its current
-// m best in a sorted private list (insertions become rare after the first few hundred candidates).
-// ------------------------------------------------------------------------------------------------
-template <int DMAX, bool ORDERED>
-__global__ void __launch_bounds__(128) knn_kernel(const double* __restrict__ q, int64_t M, const double* __restrict__ x,
-                                                  int64_t n, int D, int m, int64_t* __restrict__ NN, int ldnn) {
-    constexpr int TC = 128;
-    __shared__ double xc[TC][DMAX];
-    const int tid = threadIdx.x;
-    const int64_t qi = (int64_t)blockIdx.x * 128 + tid;
-    const bool active = qi < M;
-    double qv[DMAX];
-#pragma unroll
-    for (int k = 0; k < DMAX; ++k) qv[k] = (active && k < D) ? q[qi * D + k] : 0.0;
-    double bd[kMaxBlock];
-    int bi[kMaxBlock];
-    int cnt = 0;
-    double thr = INFINITY;
-    // ORDERED: candidates are j < i only (vecchia.py:42-51,84-107)
-    const int64_t cmax = ORDERED ? min(n, (int64_t)blockIdx.x * 128 + 128) : n;
-    for (int64_t c0 = 0; c0 < cmax; c0 += TC) {
-        __syncthreads();
-        for (int idx = tid; idx < TC * DMAX; idx += 128) {
-            int r = idx / DMAX, k = idx % DMAX;
-            int64_t j = c0 + r;
-            xc[r][k] = (j < n && k < D) ? x[j * D + k] : 0.0;
-        }
-        __syncthreads();
-        if (!active) continue;
-        int64_t lim = min((int64_t)TC, (ORDERED ? qi : n) - c0);
-        for (int r = 0; r < lim; ++r) {
-            double dist = 0.0;
-#pragma unroll
-            for (int k = 0; k < DMAX; ++k) {
-                double df = __dsub_rn(qv[k], xc[r][k]);
-                dist = __dadd_rn(dist, __dmul_rn(df, df));
-            }
-            if (m > 0 && (cnt < m || dist < thr)) {
-                int pos = cnt < m ? cnt : m - 1;
-                while (pos > 0 && bd[pos - 1] > dist) {
-                    bd[pos] = bd[pos - 1];
-                    bi[pos] = bi[pos - 1];
-                    --pos;
-                }
-                bd[pos] = dist;
-                bi[pos] = (int)(c0 + r);
-                if (cnt < m) ++cnt;
-                if (cnt == m) thr = bd[m - 1];
-            }
-        }
-    }
-    if (!active) return;
-    if (ORDERED) {
-        // row = {i} U neighbours, sorted by index descending, -1 padded
-        for (int a = 1; a < cnt; ++a) {  // insertion sort of indices, descending
-            int v = bi[a], p = a;
-            while (p > 0 && bi[p - 1] < v) {
-                bi[p] = bi[p - 1];
-                --p;
-            }
-            bi[p] = v;
-        }
-        NN[qi * ldnn] = qi;
-        for (int a = 0; a < ldnn - 1; ++a) NN[qi * ldnn + 1 + a] = a < cnt ? (int64_t)bi[a] : -1;
-    } else {
-        for (int a = 0; a < m; ++a) NN[qi * ldnn + a] = (int64_t)bi[a];
-    }
-}
-
-__global__ void knn_all_kernel(int64_t M, int m, int64_t* NN) {
-    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= M * m) return;
-    int64_t k = idx / m, c = idx % m;
-    NN[idx] = (c + k) % m;  // (arange(m)+arange(k)[:,None]) % m   vecchia.py:23-26
-}
-
-template <bool ORDERED>
-static int launch_knn(const double* q, int64_t M, const double* x, int64_t n, int D, int m, int64_t* NN, int ldnn,
-                      cudaStream_t st) {
-    unsigned grid = (unsigned)cdiv(M, 128);
-#define KNN_CASE(DM)                                                                      \
-    if (D <= DM) {                                                                        \
-        knn_kernel<DM, ORDERED><<<grid, 128, 0, st>>>(q, M, x, n, D, m, NN, ldnn);        \
-        DGPB_LAUNCHED();                                                                  \
-        return DGPB_OK;                                                                   \
-    }
-    KNN_CASE(2) KNN_CASE(4) KNN_CASE(8) KNN_CASE(12) KNN_CASE(16) KNN_CASE(24) KNN_CASE(32)
-#undef KNN_CASE
-    set_error("kNN: dimension %d > %d", D, kMaxDim);
-    return DGPB_BAD_ARG;
-}
-
-// ------------------------------------------------------------------------------------------------
 // per-warp conditioning-block machinery (packed lower-triangular storage: (i,j) -> i(i+1)/2 + j)
 // ------------------------------------------------------------------------------------------------
 int make_vkern(int kind, int64_t D, const double* length_host, int64_t nlen, VKern* vk) {
@@ -633,32 +538,6 @@ static int get_tls_ws(dgpb_ws** out) {
 }
 
 extern "C" {
-
-int dgpb_knn_ordered(const double* x, int64_t n, int64_t D, int64_t m, int64_t* NN, void* stream) {
-    DGPB_REQUIRE(x && NN && n >= 1 && D >= 1 && D <= kMaxDim, "bad argument");
-    m = std::min(m, n - 1);
-    DGPB_REQUIRE(m >= 0 && m < kMaxBlock, "m out of range");
-    if (m == 0) {
-        // single point: NN = [[0]]
-        return launch_knn<true>(x, n, x, n, (int)D, 0, NN, 1, (cudaStream_t)stream);
-    }
-    return launch_knn<true>(x, n, x, n, (int)D, (int)m, NN, (int)m + 1, (cudaStream_t)stream);
-}
-
-int dgpb_knn(const double* query, int64_t M, const double* x, int64_t n, int64_t D, int64_t m, int64_t* NN,
-             void* stream) {
-    DGPB_REQUIRE(query && x && NN && n >= 1 && D >= 1 && D <= kMaxDim, "bad argument");
-    cudaStream_t st = (cudaStream_t)stream;
-    m = std::min(m, n);
-    if (M == 0) return DGPB_OK;
-    if (m == n) {
-        knn_all_kernel<<<(unsigned)cdiv(M * m, 256), 256, 0, st>>>(M, (int)m, NN);
-        DGPB_LAUNCHED();
-        return DGPB_OK;
-    }
-    DGPB_REQUIRE(m >= 1 && m <= kMaxBlock, "m out of range (max 64)");
-    return launch_knn<false>(query, M, x, n, (int)D, (int)m, NN, (int)m, st);
-}
 
 int dgpb_vecchia_llik(const double* X, const double* y, const int64_t* NN, int64_t n, int64_t D, int64_t m1,
                       const double* length_host, int64_t nlen, double scale, double nugget, const double* nugget_diag,

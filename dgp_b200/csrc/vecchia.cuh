@@ -19,4 +19,7 @@ int vecchia_llik_device(Workspace* ws, const VKern& vk, const double* X, const d
 int vecchia_mvn_draw_device(Workspace* ws, const VKern& vk, const double* X, const int64_t* NN, int64_t n, int64_t m1,
                             double scale, double nugget, const double* z, double* out, cudaStream_t st);
 
+// knn.cu: 1 = tensor-core screen + exact ranking (default), 0 = scalar exact kernel only
+int knn_set_mma(int on);
+
 }  // namespace dgpb

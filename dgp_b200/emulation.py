@@ -101,11 +101,12 @@ class emulator:
         xd = L.to_dev(x, np.float64)
         S = len(self.all_layer_set)
         means, variances, layers_all = [], [], []
-        for s in range(S):
-            mean, var, per_layer = self._predict_one_imputation(self.all_layer_set[s], xd, m, full_layer)
-            means.append(mean)
-            variances.append(var)
-            layers_all.append(per_layer)
+        with L.predict_cache():
+            for s in range(S):
+                mean, var, per_layer = self._predict_one_imputation(self.all_layer_set[s], xd, m, full_layer)
+                means.append(mean)
+                variances.append(var)
+                layers_all.append(per_layer)
         if method == 'sampling':
             if full_layer:
                 out = []

@@ -383,18 +383,31 @@ class kernel:
 
     # ---- 5. predictions --------------------------------------------------------------------------------
     def _nn_query(self, xq, w):
+        """Neighbours of the query points among the training inputs, on coordinates divided by the
+        length-scales (vecchia.py:20-40 called from kernel_class.py:640-668).  With ONE shared length-scale the
+        division cannot change which points are nearest, so within a predict pass nodes that are asked about the
+        same query tensor and the same training inputs with the same m reuse one search (first layer of a DGP:
+        every node of every imputation).  Only an exact distance tie could be broken differently by another
+        node's scaling, and the reference's own tie-break is library-defined."""
         from .vecchia import get_pred_nn_dev
         larr = np.atleast_1d(self.length)
-        lt = L.to_dev(np.full(w.shape[1], larr[0]) if len(larr) == 1 else larr)
+        iso = len(larr) == 1
+        pc = L.active_cache()
+        if iso and pc is not None:
+            for (xq0, w0, m0, NN0) in pc.nn:
+                if xq0 is xq and w0 is w and m0 == self.pred_m:
+                    return NN0[:, 1:].contiguous() if self.loo_state else NN0
+        lt = L.to_dev(np.full(w.shape[1], larr[0]) if iso else larr)
         NN = get_pred_nn_dev(xq / lt, w / lt, self.pred_m)
+        if iso and pc is not None:
+            pc.nn.append((xq, w, self.pred_m, NN))
         return NN[:, 1:].contiguous() if self.loo_state else NN
 
     def _gp_prediction_dev(self, x, z):
         """Device tensors in / out; see `gp_prediction`."""
         lib = L.load()
-        xq = x if z is None else L.torch_mod().cat((x, z), 1)
-        xq = xq.contiguous()
-        W = L.to_dev(self._X())
+        xq = L.cat_cols(x, z)
+        W = L.to_dev_shared(self._X())
         M, D = xq.shape
         mean, var = L.empty((M,)), L.empty((M,))
         larr, lptr = L.length_host(self.length)
@@ -422,9 +435,9 @@ class kernel:
         mean, var = L.empty((M,)), L.empty((M,))
         larr, lptr = L.length_host(self.length)
         if self.vecch:
-            xq = m if z is None else torch.cat((m, z), 1)
-            w = w1 if gw is None else torch.cat((w1, gw), 1)
-            NN = self._nn_query(xq.contiguous(), w.contiguous())
+            xq = L.cat_cols(m, z)
+            w = L.cat_cols(w1, gw)
+            NN = self._nn_query(xq, w)
             y = L.to_dev(np.ascontiguousarray(self.output[:, 0]))
             L.check(lib.dgpb_linkgp_vecch(L.ptr(m), L.ptr(v), L.ptr(z), M, L.ptr(w1), L.ptr(gw), L.ptr(y), w1.shape[0],
                                           Dw, Dz, L.ptr(NN), NN.shape[1], lptr, len(larr), float(self.scale[0]),
@@ -439,8 +452,8 @@ class kernel:
         return mean, var
 
     def _linkgp_prediction_dev(self, m, v, z):
-        w1 = L.to_dev(self.input)
-        gw = L.to_dev(self.global_input) if z is not None else None
+        w1 = L.to_dev_shared(self.input)
+        gw = L.to_dev_shared(self.global_input) if z is not None else None
         return self._linkgp_dev(m, v, z, w1, gw)
 
     def _linkgp_prediction_full_dev(self, m, v, m_z, v_z, z):

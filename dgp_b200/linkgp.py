@@ -189,6 +189,10 @@ class lgp:
 
     def predict(self, x, method='mean_var', full_layer=False, sample_size=50, m=50):
         """Predictions from the linked (D)GP model (linkgp.py:285-501)."""
+        with L.predict_cache():
+            return self._predict(x, method, full_layer, sample_size, m)
+
+    def _predict(self, x, method, full_layer, sample_size, m):
         torch = L.torch_mod()
         lib = L.load()
         if isinstance(x, list) and len(x) != self.L:

@@ -292,6 +292,46 @@ def test_nn_indices_bit_exact(golden_vecchia):
     assert np.array_equal(V.nn(x[:1], 25), O.nn_ordered(x[:1], 25))
 
 
+def test_knn_tensor_core_screen_equals_scalar_search():
+    """The neighbour search screens candidates on the FP64 tensor path and ranks the survivors with the reference
+    arithmetic; its index arrays must equal those of the scalar exact kernel bit for bit -- random inputs, ragged
+    sizes, both list capacities (m <= 29 / m <= 61), the ordered variant, and inputs full of exact distance ties
+    (lattice points, duplicates) where the screen has to hand queries back to the scalar kernel."""
+    from dgp_b200 import _lib as L
+    from dgp_b200 import vecchia as V
+
+    lib = L.load()
+    rng = np.random.default_rng(23)
+
+    def both(fn):
+        L.check(lib.dgpb_tune(b"knn_mma", 0))
+        try:
+            ref = fn()
+        finally:
+            L.check(lib.dgpb_tune(b"knn_mma", 1))
+        return ref, fn()
+
+    for n, M, D, m in ((1000, 333, 3, 5), (5000, 1500, 10, 25), (3001, 700, 20, 50), (700, 129, 31, 29),
+                       (300, 64, 10, 61), (40, 17, 2, 30), (129, 1, 1, 25)):
+        x, q = rng.uniform(0, 1, (n, D)), rng.uniform(0, 1, (M, D))
+        a, b = both(lambda: V.get_pred_nn(q, x, m))
+        assert a.shape == (M, min(m, n)) and np.array_equal(a, b), (n, M, D, m)
+        a, b = both(lambda: V.nn(x, m))
+        assert np.array_equal(a, b), ("ordered", n, D, m)
+        d2 = ((q[:, None, :] - x[None, :, :]) ** 2).sum(-1) if n * M <= 2_000_000 else None
+        if d2 is not None:
+            assert np.array_equal(np.sort(a_idx := np.argsort(d2, 1, kind="stable")[:, :min(m, n)], 1),
+                                  np.sort(V.get_pred_nn(q, x, m), 1)), (n, M, D, m)
+    # exact ties: integer lattice with duplicated points, queries on lattice sites
+    g = np.stack(np.meshgrid(*[np.arange(6.0)] * 3, indexing="ij"), -1).reshape(-1, 3)
+    x = np.concatenate((g, g[:50]), 0)
+    q = g[::3] + 0.0
+    a, b = both(lambda: V.get_pred_nn(q, x, 25))
+    assert np.array_equal(a, b)
+    a, b = both(lambda: V.nn(x, 10))
+    assert np.array_equal(a, b)
+
+
 def test_vecchia_kernels_vs_reference(golden_vecchia):
     import dgp_b200 as D
     from dgp_b200 import vecchia as V
