@@ -3,9 +3,9 @@
 // The search is brute force (10-20 dimensional inputs leave nothing to prune) in two stages:
 //   1. SCREEN on the FP64 tensor path.  |q - x|^2 = |q|^2 + |x|^2 - 2 q.x ; the cross term is a DMMA product
 //      (mma.m8n8k4: 8 queries x 8 candidates x 4 dimensions per instruction), the norms initialise the
-//      accumulator.  Every query keeps the LC = 32 or 64 smallest screened distances in an unsorted
+//      accumulator.  Every query keeps the LC = 32 or 64 smallest screened distances in a sorted
 //      shared-memory list owned by its warp (insertions become rare after the first few hundred candidates and
-//      are done by the whole warp: arg-max by shuffles, replace, new maximum = the query's threshold).
+//      are done by the whole warp: ballot for the slot, shfl_up for the tail, last entry = the query's threshold).
 //   2. RANK exactly.  The LC survivors of a query are re-evaluated with the reference arithmetic -- sum_k
 //      (q_k - x_k)^2, separate multiply and add in ascending k, what the CPU libraries compute --
 //      and ranked by (distance, index), so the index sets match bit for bit and ties keep the smaller index.
@@ -128,44 +128,53 @@ __device__ __forceinline__ void knn_cp8(void* smem_dst, const void* gsrc, bool p
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(s), "l"(gsrc), "r"(sz));
 }
 
-// Offer (d, j) to the unsorted list (ld, li) of 32 * NL entries spread over the lanes; d, j and thr are
-// warp-uniform.  Returns the list's new maximum (the query's threshold).
+// Offer (d, j) to the list (ld, li) of 32 * NL entries kept SORTED ascending, slot s = lane + 32 e; d, j and thr
+// are warp-uniform.  One ballot per 32 slots gives the insertion point, the tail moves up one slot through
+// shfl_up, and the new last entry is the query's threshold: a chain of four dependent steps (the unsorted
+// arg-max / replace / re-max form was ten and bounded the kernel).  Returns the new threshold.
 template <int NL>
 __device__ __forceinline__ double knn_list_insert(double* ld, int* li, int lane, double d, int j, double thr) {
     if (!(d < thr)) return thr;
     double v[NL];
+    int ix[NL];
+    int p = 0;   // number of entries <= d: the slot the candidate takes (ties stay behind earlier candidates)
 #pragma unroll
-    for (int e = 0; e < NL; ++e) v[e] = ld[lane + 32 * e];
-    double bv = v[0];
-    int be = 0;
-#pragma unroll
-    for (int e = 1; e < NL; ++e)
-        if (v[e] > bv) {
-            bv = v[e];
-            be = e;
-        }
-    int bl = lane;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
-        const int ol = __shfl_xor_sync(0xffffffffu, bl, o);
-        if (ov > bv || (ov == bv && ol < bl)) {
-            bv = ov;
-            bl = ol;
-        }
+    for (int e = 0; e < NL; ++e) {
+        v[e] = ld[lane + 32 * e];
+        ix[e] = li[lane + 32 * e];
+        p += __popc(__ballot_sync(0xffffffffu, v[e] <= d));
     }
-    if (lane == bl) {
-        ld[lane + 32 * be] = d;
-        li[lane + 32 * be] = j;
-        v[be] = d;
+    double last = 0.0;
+#pragma unroll
+    for (int e = 0; e < NL; ++e) {
+        const int slot = lane + 32 * e;
+        double pv = __shfl_up_sync(0xffffffffu, v[e], 1);
+        int pi = __shfl_up_sync(0xffffffffu, ix[e], 1);
+        if (e > 0) {   // slot 32 e takes the last entry of the previous group
+            const double cv = __shfl_sync(0xffffffffu, v[e - 1], 31);
+            const int ci = __shfl_sync(0xffffffffu, ix[e - 1], 31);
+            if (lane == 0) {
+                pv = cv;
+                pi = ci;
+            }
+        }
+        double nv = v[e];
+        int ni = ix[e];
+        if (slot == p) {
+            nv = d;
+            ni = j;
+        } else if (slot > p) {
+            nv = pv;
+            ni = pi;
+        }
+        if (slot >= p) {
+            ld[slot] = nv;
+            li[slot] = ni;
+        }
+        if (e == NL - 1) last = __shfl_sync(0xffffffffu, nv, 31);
     }
-    double nm = v[0];
-#pragma unroll
-    for (int e = 1; e < NL; ++e) nm = fmax(nm, v[e]);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) nm = fmax(nm, __shfl_xor_sync(0xffffffffu, nm, o));
     __syncwarp();
-    return nm;
+    return last;
 }
 
 constexpr int kKnnTC = 128;   // candidates per staged tile

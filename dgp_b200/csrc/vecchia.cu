@@ -457,10 +457,162 @@ __global__ void vecchia_pred_kernel(VKern vk, VPredArgs a, int per_warp) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Register-resident variant for conditioning blocks of b <= 32 points (m <= 31: the reference's training
+// default m = 25 and BASELINE config 4): lane i owns ROW i of the block's covariance in registers.
+//   * row build: lane i evaluates k(x_i, x_k) for every k (coordinates staged in shared memory, row stride odd so
+//     the per-lane rows are conflict-free and x_k is a broadcast);
+//   * right-looking Cholesky: the pivot and the column entries l_kj travel by shuffles, the rank-1 update is one
+//     FMA per (row, column) in registers -- no shared-memory read-modify-write, no barrier per column;
+//   * the forward solve L^-1 y is fused into the same column loop (y is an extra right-hand side: w_j is final
+//     as soon as column j is).
+// PRED = true : gp_vecch (vecchia.py:635-654): block = [neighbours ; test point], y_test = 0, so the last
+//               solve entry is -m / L_last and  m = -w_last L_last,  v = scale L_last^2.
+// PRED = false: vecchia_llik terms (vecchia.py:164-180): vals[i*2 + {0,1}] = (w_last^2, 2 log L_last).
+// ------------------------------------------------------------------------------------------------
+struct VSmallArgs {
+    int64_t count;        // test points (PRED) or training points
+    int cols;             // columns of NN (mp or m1)
+    const double* xq;     // PRED: count x D test inputs
+    const double* X;      // n x D training inputs (train: Vecchia order)
+    const double* y;      // n
+    const int64_t* NN;    // count x cols
+    const double* nugget_diag;
+    double scale, nugget;
+    double* out0;         // PRED: mean;  train: vals (count x 2)
+    double* out1;         // PRED: var
+};
+
+template <bool PRED>
+__global__ void __launch_bounds__(256, 3) vecchia_small_kernel(VKern vk, VSmallArgs a) {
+    extern __shared__ double smem[];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, W = blockDim.x >> 5;
+    const int64_t t = (int64_t)blockIdx.x * W + w;
+    if (t >= a.count) return;
+    const int D = vk.D, Dp = D | 1;
+    double* xl = smem + (size_t)w * 32 * Dp;
+    // block membership: PRED -> NN[t][0..nb) then the test point; train -> valid NN entries reversed (ascending,
+    // the point itself last)
+    int nv = 0;
+    for (int c = lane; c < a.cols; c += 32) nv += a.NN[t * a.cols + c] >= 0;
+    for (int o = 16; o > 0; o >>= 1) nv += __shfl_xor_sync(0xffffffffu, nv, o);
+    const int b = PRED ? nv + 1 : nv;
+    int64_t src = -1;   // training index of this lane's point (-1: the test point / unused lane)
+    if (PRED) {
+        if (lane < nv) src = a.NN[t * a.cols + lane];
+    } else {
+        if (lane < nv) src = a.NN[t * a.cols + (nv - 1 - lane)];
+    }
+    for (int p0 = 0; p0 < b * D; p0 += 32) {   // uniform trip count: the shuffle needs the whole warp
+        const int p = p0 + lane;
+        const int r = min(p / D, b - 1), k = p - (p / D) * D;
+        const int64_t sr = __shfl_sync(0xffffffffu, src, r);
+        if (p < b * D) {
+            const double v = sr >= 0 ? a.X[sr * D + k] : a.xq[t * D + k];
+            xl[r * Dp + k] = v / vk.len[k];
+        }
+    }
+    double yacc = (src >= 0 && a.y) ? a.y[src] : 0.0;
+    const double nug = src >= 0 ? a.nugget * (a.nugget_diag ? a.nugget_diag[src] : 1.0) : a.nugget;
+    __syncwarp();
+    // ---- row `lane` of K
+    double arow[32];
+    const double* xi = xl + (lane < b ? lane : 0) * Dp;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+        double v = 0.0;
+        if (k < b) {   // warp-uniform
+            const double* xk = xl + k * Dp;
+            if (vk.kind == DGPB_SEXP) {
+                double dist = 0.0;
+                for (int d = 0; d < D; ++d) {
+                    const double df = xi[d] - xk[d];
+                    dist += df * df;
+                }
+                v = exp(-dist);
+            } else {
+                double coef = 1.0, sr = 0.0;
+                for (int d = 0; d < D; ++d) {
+                    const double r = fabs(xi[d] - xk[d]);
+                    coef *= 1.0 + kSqrt5 * r + (5.0 / 3.0) * (r * r);
+                    sr += r;
+                }
+                v = coef * exp(-kSqrt5 * sr);
+            }
+            if (k == lane) v = 1.0 + nug;
+        }
+        arow[k] = v;
+    }
+    // ---- Cholesky + fused forward solve
+    double lll = 1.0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        if (j < b) {   // warp-uniform
+            const double pj = __shfl_sync(0xffffffffu, arow[j], j);
+            const double rs = rsqrt(pj);
+            const double lij = arow[j] * rs;          // l_ij for rows i >= j (sqrt(pj) on the diagonal)
+            arow[j] = lij;
+            const double wj = __shfl_sync(0xffffffffu, yacc, j) * rs;
+            if (lane > j) yacc = fma(-lij, wj, yacc);
+            else if (lane == j) yacc = wj;
+            if (j == b - 1) lll = __shfl_sync(0xffffffffu, lij, j);
+#pragma unroll
+            for (int k = j + 1; k < 32; ++k)
+                if (k < b) arow[k] = fma(-lij, __shfl_sync(0xffffffffu, lij, k), arow[k]);
+        }
+    }
+    const double wl = __shfl_sync(0xffffffffu, yacc, b - 1);
+    if (lane == 0) {
+        if (PRED) {
+            a.out0[t] = -wl * lll;
+            a.out1[t] = a.scale * lll * lll;
+        } else {
+            a.out0[t * 2 + 0] = wl * wl;
+            a.out0[t * 2 + 1] = 2.0 * log(fabs(lll));
+        }
+    }
+}
+
+template <bool PRED>
+static int small_launch(const VKern& vk, const VSmallArgs& a, cudaStream_t st) {
+    const int W = 8;
+    const size_t smem = (size_t)W * 32 * (vk.D | 1) * sizeof(double);
+    static bool configured = false;
+    if (!configured) {
+        DGPB_CUDA_TRY(cudaFuncSetAttribute(vecchia_small_kernel<PRED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)((size_t)W * 32 * (kMaxDim | 1) * sizeof(double))));
+        configured = true;
+    }
+    vecchia_small_kernel<PRED><<<(unsigned)cdiv(a.count, W), W * 32, smem, st>>>(vk, a);
+    DGPB_LAUNCHED();
+    return DGPB_OK;
+}
+
+static int g_vecchia_small = 1;   // dgpb_tune("vecchia_small", 0): always use the shared-memory kernels
+int vecchia_set_small(int on) {
+    g_vecchia_small = on != 0;
+    return DGPB_OK;
+}
+
 static int train_launch(const VKern& vk, const double* X, const double* y, const int64_t* NN, int64_t n, int64_t m1,
                         double nugget, const double* nugget_diag, int mode, int P, int nugget_est, double* vals,
                         double* Lout, cudaStream_t st) {
     DGPB_REQUIRE(m1 >= 1 && m1 <= kMaxBlock, "conditioning block larger than 64");
+    if (mode == 0 && m1 <= 32 && g_vecchia_small) {
+        VSmallArgs a;
+        a.count = n;
+        a.cols = (int)m1;
+        a.xq = nullptr;
+        a.X = X;
+        a.y = y;
+        a.NN = NN;
+        a.nugget_diag = nugget_diag;
+        a.scale = 1.0;
+        a.nugget = nugget;
+        a.out0 = vals;
+        a.out1 = nullptr;
+        return small_launch<false>(vk, a, st);
+    }
     const int per_warp = (int)(m1 * (m1 + 1) / 2 + m1 * vk.D + 3 * m1 + (mode == 1 ? P * m1 : 0) + (m1 + 1) / 2 + 2);
     int W = 8;
     while (W > 1 && (size_t)W * per_warp * sizeof(double) > 200 * 1024) W >>= 1;
@@ -479,6 +631,21 @@ static int train_launch(const VKern& vk, const double* X, const double* y, const
 static int pred_launch(const VKern& vk, const VPredArgs& a, cudaStream_t st) {
     const int bmax = a.mp + 1;
     DGPB_REQUIRE(bmax <= kMaxBlock, "prediction conditioning set larger than 63");
+    if (a.mode == 0 && bmax <= 32 && g_vecchia_small) {
+        VSmallArgs sa;
+        sa.count = a.M;
+        sa.cols = a.mp;
+        sa.xq = a.xq;
+        sa.X = a.w1;
+        sa.y = a.y;
+        sa.NN = a.NN;
+        sa.nugget_diag = a.nugget_diag;
+        sa.scale = a.scale;
+        sa.nugget = a.nugget;
+        sa.out0 = a.mean;
+        sa.out1 = a.var;
+        return small_launch<true>(vk, sa, st);
+    }
     const int tri_sz = bmax * (bmax + 1) / 2;
     const int per_warp = tri_sz + bmax * vk.D + 2 * bmax + (a.mode ? 2 * tri_sz + 2 * bmax : 0) + (bmax + 1) / 2 + 2;
     int W = 8;

@@ -19,6 +19,8 @@ int vecchia_llik_device(Workspace* ws, const VKern& vk, const double* X, const d
 int vecchia_mvn_draw_device(Workspace* ws, const VKern& vk, const double* X, const int64_t* NN, int64_t n, int64_t m1,
                             double scale, double nugget, const double* z, double* out, cudaStream_t st);
 
+// 1 = register-resident kernel for conditioning blocks of <= 32 points (default), 0 = shared-memory kernels only
+int vecchia_set_small(int on);
 // knn.cu: 1 = tensor-core screen + exact ranking (default), 0 = scalar exact kernel only
 int knn_set_mma(int on);
 

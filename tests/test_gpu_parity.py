@@ -332,6 +332,42 @@ def test_knn_tensor_core_screen_equals_scalar_search():
     assert np.array_equal(a, b)
 
 
+def test_vecchia_register_kernel_equals_shared_memory_kernel():
+    """Blocks of <= 32 points are factored in registers (lane = row); same numbers as the shared-memory kernel
+    and as the oracle, for both kernels, ragged early blocks (-1 padded rows) and the prediction form."""
+    from dgp_b200 import _lib as L
+    from dgp_b200 import vecchia as V
+    from oracle import dgp_oracle as O
+
+    lib = L.load()
+    rng = np.random.default_rng(31)
+
+    def both(fn):
+        L.check(lib.dgpb_tune(b"vecchia_small", 0))
+        try:
+            ref = fn()
+        finally:
+            L.check(lib.dgpb_tune(b"vecchia_small", 1))
+        return ref, fn()
+
+    for n, D, m, name in ((300, 3, 5, "sexp"), (500, 10, 25, "sexp"), (257, 7, 31, "matern2.5"), (40, 2, 1, "matern2.5")):
+        X = rng.uniform(0, 1, (n, D))
+        y = np.sin(3 * X.sum(1)) + 0.05 * rng.standard_normal(n)
+        length = rng.uniform(0.5, 1.5, D)
+        NN = V.nn(X / length, m)
+        a, b = both(lambda: V.vecchia_llik(X, y, NN, 1.3, length, 1e-3, None, name))
+        assert abs(a - b) <= 1e-11 * abs(a), (n, D, m, a, b)
+        ref = O.vecchia_llik(X, y.reshape(-1, 1), NN, 1.3, length, 1e-3, np.ones(n), name)
+        assert abs(b - ref) <= 1e-9 * abs(ref), (n, D, m, b, ref)
+        # prediction form: gp_vecch through the node API
+        import dgp_b200 as Dm
+        k = Dm.kernel(length=length.copy(), name=name, nugget=1e-3, scale=1.3)
+        k.input, k.output, k.D, k.vecch, k.pred_m = X, y.reshape(-1, 1), D, True, m
+        xt = rng.uniform(0, 1, (77, D))
+        (m0, v0), (m1, v1) = both(lambda: k.gp_prediction(xt, None))
+        assert relerr(m1, m0, 1e-9) <= 1e-10 and relerr(v1, v0, 1e-12) <= 1e-9, (n, D, m)
+
+
 def test_vecchia_kernels_vs_reference(golden_vecchia):
     import dgp_b200 as D
     from dgp_b200 import vecchia as V
