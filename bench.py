@@ -297,6 +297,60 @@ def run_gpu(args):
                    "imputations": args.predict_imputations, "sharding": "test points / rank, all_gather of (mu, var)",
                    "finite": bool(np.all(np.isfinite(mu)) and np.all(np.isfinite(var)))}
 
+    # ---- secondary metric 2: Vecchia DGP prediction, BASELINE config 4 shape (n=100k, d=10, m=25, 10+1 sexp
+    #      nodes), test points sharded over the ranks; kNN included -----------------------------
+    predict_v = None
+    if args.vecchia_points > 0:
+        from dgp_b200.parallel import predict_sharded
+        seed4 = 20261017 + 3
+        rng4 = np.random.default_rng(seed4)
+        np.random.seed(seed4)
+        D.nb_seed(seed4)
+        n4, d4 = args.vecchia_n, 10
+        X4 = rng4.uniform(0, 1, (n4, d4))
+        f4 = lambda x: np.sin(2 * np.pi * x[:, 0] * x[:, 1]) + x[:, 2] ** 2 + np.cos(3 * x[:, 3:].sum(1))
+        Y4 = (f4(X4) + 0.05 * rng4.standard_normal(n4)).reshape(-1, 1)
+        l1 = [D.kernel(length=np.array([1.0]), name="sexp") for _ in range(10)]
+        l2 = [D.kernel(length=np.array([1.0]), name="sexp", scale_est=True, nugget_est=True, nugget=1e-2,
+                       connect=np.arange(10))]
+        tv0 = time.perf_counter()
+        m4 = D.dgp(X4, Y4, D.combine(l1, l2), vecchia=True, m=25)
+        m4.train(args.vecchia_train_iters, disable=True)
+        torch.cuda.synchronize()
+        t_train = (time.perf_counter() - tv0)
+        emu4 = D.emulator(m4.estimate(burnin=0), N=args.vecchia_imputations)
+        xt4 = np.random.default_rng(seed4 + 99).uniform(0, 1, size=(args.vecchia_points, d4))
+        predict_sharded(emu4, xt4[: 256 * world], dist, m=25)  # warm-up
+        barrier()
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        tp0 = time.perf_counter()
+        p0.record()
+        mu4, var4 = predict_sharded(emu4, xt4, dist, m=25)
+        p1.record()
+        barrier()
+        tp = time.perf_counter() - tp0
+        tt = torch.tensor([p0.elapsed_time(p1), tp * 1e3], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        S4, M4 = args.vecchia_imputations, len(xt4)
+        # algorithmic FLOPs: kNN 2D flop per (query, candidate) pair on the tensor path -- layer 1
+        # once (one design matrix, shared length-scale), layer 2 once per imputation (D = 20); per block
+        # b^3/3 + b^2 (3D + 25)/2 + 2 b^2 flop, b = 26, for the 10 first-layer nodes; ~70 kflop per linked block
+        b = 26.0
+        blk1 = b ** 3 / 3 + b * b * (3 * 10 + 25) / 2 + 2 * b * b
+        flops = M4 * n4 * 2.0 * 10 + S4 * M4 * n4 * 2.0 * 20 + S4 * M4 * (10 * blk1 + 7.0e4)
+        t_pred = float(tt[0]) * 1e-3
+        predict_v = {"metric": "Vecchia DGP predict points/sec (mean_var, m=25)", "value": M4 / t_pred,
+                     "e2e_value": M4 / (float(tt[1]) * 1e-3), "unit": "points/s", "points": M4, "n_train": n4,
+                     "imputations": S4, "train_iters": args.vecchia_train_iters,
+                     "train_s_per_iter_incl_construct": t_train / max(1, args.vecchia_train_iters),
+                     "node_imputation_points_per_s": M4 * S4 * 11 / t_pred,
+                     "algorithmic_tflops": flops / t_pred / 1e12,
+                     "frac_of_fp64_peak": (flops / t_pred / 1e12 / peak) if peak else None,
+                     "sharding": "test points / rank, all_gather of (mu, var)",
+                     "rmse_vs_truth": float(np.sqrt(np.mean((mu4[:, 0] - f4(xt4)) ** 2))),
+                     "finite": bool(np.all(np.isfinite(mu4)) and np.all(np.isfinite(var4)))}
+
     if rank == 0:
         value = world * args.steps / (dev_ms_max * 1e-3)
         e2e = world * args.steps / (wall_ms_max * 1e-3)
@@ -327,7 +381,7 @@ def run_gpu(args):
                 "e2e": {"value": e2e, "unit": "iters/s", "h2d_bytes_per_step": h2d // args.steps,
                         "d2h_bytes_per_step": d2h // args.steps},
                 "gpu_launches": int(launches), "ess_proposals_per_step": nprop / args.steps, "roofline": roof,
-                "cpu_baseline": cpu, "clocks": clocks.summary(), "predict": predict}
+                "cpu_baseline": cpu, "clocks": clocks.summary(), "predict": predict, "predict_vecchia": predict_v}
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
@@ -343,6 +397,11 @@ def main():
     ap.add_argument("--predict-points", type=int, default=2048, help="test points PER GPU for the predict metric")
     ap.add_argument("--predict-imputations", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--vecchia-points", type=int, default=1000000,
+                    help="test points of the Vecchia prediction metric (BASELINE config 4: 1M); 0 = skip")
+    ap.add_argument("--vecchia-n", type=int, default=100000)
+    ap.add_argument("--vecchia-imputations", type=int, default=2)
+    ap.add_argument("--vecchia-train-iters", type=int, default=2)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -192,7 +192,7 @@ constexpr size_t knn_smem_bytes() {
 
 // KS = ceil(D / 4) k-steps, NL = list entries per lane (list capacity 32 NL >= m + 3).
 template <int KS, int NL, bool ORDERED>
-__global__ void __launch_bounds__(256, 2) knn_mma_kernel(const double* __restrict__ q, int64_t M, const double* __restrict__ x,
+__global__ void __launch_bounds__(256, KS <= 3 && NL == 1 ? 3 : 2) knn_mma_kernel(const double* __restrict__ q, int64_t M, const double* __restrict__ x,
                                                       int64_t n, int D, int m, int64_t* __restrict__ NN, int ldnn,
                                                       unsigned char* __restrict__ flags) {
     constexpr int DP = KnnPad<KS>::value;
@@ -253,46 +253,89 @@ __global__ void __launch_bounds__(256, 2) knn_mma_kernel(const double* __restric
 #pragma unroll
             for (int k = 0; k < 4 * KS; ++k) sn += xt[tid * DP + k] * xt[tid * DP + k];
             xnt[tid] = sn;
+            xnmax = fmax(xnmax, sn);
         }
         __syncthreads();
         if (tile + 1 < ntiles) load_tile(tile + 1);
         const int64_t c0 = (int64_t)tile * kKnnTC;
-#pragma unroll 2
-        for (int cg = 0; cg < kKnnTC / 8; ++cg) {
-            double b[KS];
+        // candidates of this tile a query may take: local index < lim[s]
+        int lim[2];
 #pragma unroll
-            for (int ks = 0; ks < KS; ++ks) b[ks] = xt[(8 * cg + g) * DP + 4 * ks + t4];
-            const double2 nn2 = *reinterpret_cast<const double2*>(&xnt[8 * cg + 2 * t4]);
-            xnmax = fmax(xnmax, fmax(nn2.x, nn2.y));
-            const int64_t j0 = c0 + 8 * cg + 2 * t4;
+        for (int s = 0; s < 2; ++s) {
+            const int64_t qi = q0 + 16 * w + 8 * s + g;
+            const int64_t jl = (ORDERED ? min(n, qi) : n) - c0;
+            lim[s] = qi < M ? (int)max((int64_t)0, min(jl, (int64_t)kKnnTC)) : 0;
+        }
+        // two candidate octets x two query octets per step: four independent DMMA chains in flight before the
+        // first result is tested
+        for (int cg = 0; cg < kKnnTC / 8; cg += 2) {
+            double b[2][KS];
 #pragma unroll
-            for (int s = 0; s < 2; ++s) {
-                double d0 = qn[s] + nn2.x, d1 = qn[s] + nn2.y;
+            for (int h = 0; h < 2; ++h)
 #pragma unroll
-                for (int ks = 0; ks < KS; ++ks) knn_dmma(d0, d1, aq[s][ks], b[ks]);
-                const int64_t qi = q0 + 16 * w + 8 * s + g;
-                const int64_t jlim = ORDERED ? min(n, qi) : n;
-                bool h0 = d0 < thr[s] && j0 < jlim, h1 = d1 < thr[s] && j0 + 1 < jlim;
-                if (qi >= M) h0 = h1 = false;
-                unsigned hm = __ballot_sync(0xffffffffu, h0 || h1);
-                while (hm) {   // rare after warm-up: offer the hits one at a time, the whole warp helping
-                    const int src = __ffs(hm) - 1;
-                    hm &= hm - 1;
-                    const int ql = 16 * w + 8 * s + (src >> 2);
-                    const int jj = (int)(c0 + 8 * cg + 2 * (src & 3));
-                    const double e0 = __shfl_sync(0xffffffffu, d0, src), e1 = __shfl_sync(0xffffffffu, d1, src);
-                    const int f = __shfl_sync(0xffffffffu, (int)h0 | ((int)h1 << 1), src);
-                    double tq = __shfl_sync(0xffffffffu, thr[s], src);
-                    if (f & 1) tq = knn_list_insert<NL>(ldist + (size_t)ql * LC, lidx + (size_t)ql * LC, lane, e0, jj, tq);
-                    if (f & 2) tq = knn_list_insert<NL>(ldist + (size_t)ql * LC, lidx + (size_t)ql * LC, lane, e1, jj + 1, tq);
-                    if (g == (src >> 2)) thr[s] = tq;
-                }
+                for (int ks = 0; ks < KS; ++ks) b[h][ks] = xt[(8 * (cg + h) + g) * DP + 4 * ks + t4];
+            double2 nn2[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                nn2[h] = *reinterpret_cast<const double2*>(&xnt[8 * (cg + h) + 2 * t4]);
             }
+            double d[2][2][2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int s = 0; s < 2; ++s) {
+                    d[h][s][0] = qn[s] + nn2[h].x;
+                    d[h][s][1] = qn[s] + nn2[h].y;
+                }
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+#pragma unroll
+                    for (int s = 0; s < 2; ++s) knn_dmma(d[h][s][0], d[h][s][1], aq[s][ks], b[h][ks]);
+            // one vote for the whole step; the per-tile work below only runs when some lane has a hit
+            bool anyhit = false;
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int s = 0; s < 2; ++s) {
+                    const int jl0 = 8 * (cg + h) + 2 * t4;
+                    anyhit = anyhit || (d[h][s][0] < thr[s] && jl0 < lim[s]) || (d[h][s][1] < thr[s] && jl0 + 1 < lim[s]);
+                }
+            if (!__any_sync(0xffffffffu, anyhit)) continue;
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int s = 0; s < 2; ++s) {
+                    const int jl0 = 8 * (cg + h) + 2 * t4;
+                    const bool h0 = d[h][s][0] < thr[s] && jl0 < lim[s];
+                    const bool h1 = d[h][s][1] < thr[s] && jl0 + 1 < lim[s];
+                    unsigned hm = __ballot_sync(0xffffffffu, h0 || h1);
+                    while (hm) {   // rare after warm-up: offer the hits one at a time, the whole warp helping
+                        const int src = __ffs(hm) - 1;
+                        hm &= hm - 1;
+                        const int ql = 16 * w + 8 * s + (src >> 2);
+                        const int jj = (int)(c0 + 8 * (cg + h) + 2 * (src & 3));
+                        const double e0 = __shfl_sync(0xffffffffu, d[h][s][0], src);
+                        const double e1 = __shfl_sync(0xffffffffu, d[h][s][1], src);
+                        const int f = __shfl_sync(0xffffffffu, (int)h0 | ((int)h1 << 1), src);
+                        double tq = __shfl_sync(0xffffffffu, thr[s], src);
+                        if (f & 1) tq = knn_list_insert<NL>(ldist + (size_t)ql * LC, lidx + (size_t)ql * LC, lane, e0, jj, tq);
+                        if (f & 2) tq = knn_list_insert<NL>(ldist + (size_t)ql * LC, lidx + (size_t)ql * LC, lane, e1, jj + 1, tq);
+                        if (g == (src >> 2)) thr[s] = tq;
+                    }
+                }
         }
     }
+    // largest candidate norm seen (tracked by the threads that computed the norms) -> every thread
+    __shared__ double s_xnmax[8];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) xnmax = fmax(xnmax, __shfl_xor_sync(0xffffffffu, xnmax, o));
-    __syncwarp();
+    if (lane == 0) s_xnmax[w] = xnmax;
+    __syncthreads();
+    xnmax = s_xnmax[0];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) xnmax = fmax(xnmax, s_xnmax[i]);
     // ---- exact ranking of the survivors: one query at a time per warp, list entry per lane
     for (int ql = 16 * w; ql < 16 * w + 16; ++ql) {
         const int64_t qi = q0 + ql;
