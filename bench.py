@@ -149,6 +149,15 @@ def cpu_cores():
         return os.cpu_count()
 
 
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every host core (the reference's default)."""
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=os.cpu_count())
+    except Exception:
+        pass
+
+
 def blas_info():
     try:
         from threadpoolctl import threadpool_info
@@ -164,6 +173,7 @@ def run_reference(args):
         return
     n = args.n
     rng = np.random.default_rng(SEED)
+    use_all_host_threads()
     cnt = cpu_counts_small()
     for _ in range(args.warmup):
         cpu_step(min(n, 1500), rng)
@@ -356,7 +366,7 @@ def run_gpu(args):
         e2e = world * args.steps / (wall_ms_max * 1e-3)
         upd_ms, upd_n, upd_flops = prof[0], prof[1], prof[2]
         achieved = (upd_flops / upd_n) / (upd_ms / upd_n * 1e-3) / 1e12 if upd_n > 0 else None
-        roof = {"bound": "tensor", "kernel": "update_kernel, bulk launches (FP64 DMMA SYRK trailing update, K=128)",
+        roof = {"bound": "tensor", "kernel": "update_kernel, bulk launches (FP64 DMMA SYRK trailing update, K = 512 hyper-blocks / 128 tail)",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": (achieved / peak) if achieved else None,
                 "traffic": None, "launches_timed": int(upd_n), "avg_launch_ms": upd_ms / upd_n if upd_n else None,
                 "share_of_step": upd_ms / (dev_ms * 1.0) if dev_ms else None,
@@ -364,6 +374,7 @@ def run_gpu(args):
                                "(MEASURED_PEAKS.json has no FP64 entry)"}
         cpu = None
         if not args.no_cpu_baseline:
+            use_all_host_threads()
             cnt = cpu_counts_small()
             r2 = np.random.default_rng(1)
             cpu_step(1000, r2)
