@@ -368,7 +368,13 @@ def run_gpu(args):
         achieved = (upd_flops / upd_n) / (upd_ms / upd_n * 1e-3) / 1e12 if upd_n > 0 else None
         roof = {"bound": "tensor", "kernel": "update_kernel, bulk launches (FP64 DMMA SYRK trailing update, K = 512 hyper-blocks / 128 tail)",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": (achieved / peak) if achieved else None,
-                "traffic": None, "launches_timed": int(upd_n), "avg_launch_ms": upd_ms / upd_n if upd_n else None,
+                # DRAM bytes per launch: one `ncu --set full` capture of a K = 512 bulk launch (profiles/
+                # r1s2_update_ncu_raw.txt: 770.1 MB read + written for 41.94 GFLOP; algorithmic 760 MB), scaled to
+                # this run's average launch
+                "traffic": (upd_flops / upd_n) * (770.08e6 / 41.94e9) if upd_n > 0 else None,
+                "traffic_source": "profiles/r1s2_update_ncu_raw.txt (dram__bytes_read+write of one bulk launch, "
+                                  "18.4 B per kFLOP) x this run's FLOPs per launch",
+                "launches_timed": int(upd_n), "avg_launch_ms": upd_ms / upd_n if upd_n else None,
                 "share_of_step": upd_ms / (dev_ms * 1.0) if dev_ms else None,
                 "peak_source": "cuBLAS DGEMM 8192^3 via torch.matmul(float64), best of 5, measured in this run "
                                "(MEASURED_PEAKS.json has no FP64 entry)"}
