@@ -217,6 +217,9 @@ int make_kernel_dev(const dgpb_node* node, int64_t n, const double* src_override
 int make_kernel_dev_rowmajor(const double* X, int64_t D, const double* length_host, int64_t nlen,
                              double nugget, int kind, KernelDev* out);
 
+// predict.cu: 1 = link_gp sexp exponents on the FP64 tensor path (default), 0 = vector-pipe pair kernel
+int linkgp_set_mma(int on);
+
 }  // namespace dgpb
 
 // the opaque C handle is the workspace itself

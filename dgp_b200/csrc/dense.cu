@@ -1072,6 +1072,8 @@ int dgpb_tune(const char* key, int value) {
     } else if (k == "ess_batch") {
         DGPB_REQUIRE(value >= 0 && value <= MAXB, "ess_batch out of range");
         g_ess_target_b = value;
+    } else if (k == "linkgp_mma") {
+        linkgp_set_mma(value);
     } else if (k == "vecchia_small") {
         vecchia_set_small(value);
     } else if (k == "knn_mma") {

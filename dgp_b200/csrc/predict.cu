@@ -383,6 +383,257 @@ __global__ void __launch_bounds__(256) linkgp_sexp_pairs_kernel(LinkArgs a, int 
 }
 
 // ------------------------------------------------------------------------------------------------
+// link_gp second moments, squared-exponential kernel, exponents on the FP64 tensor path.
+//   J_ij(t) = jc_t exp(-E_t(i,j)),
+//   E_t(i,j) = sum_k y_tk (p_k - x'_tk)^2 + 1/2 sum_k (xi_k - xj_k)^2 + sum_k [(ai_k - z_tk)^2 + (aj_k - z_tk)^2]
+// with p = xi + xj (scaled local coordinates), a = scaled global coordinates, y = 1/(2 + 8 v/l^2), x' = 2 mu/l.
+// Using (xi-xj)^2 = 2 (xi^2 + xj^2) - p^2 the exponent is BILINEAR in a test-point coefficient vector and a pair
+// feature vector:
+//   E = c_t + 1 * [S_i + S_j] + sum_k (y_tk - 1/2) p_k^2 + sum_k (-2 y_tk x'_tk) p_k + sum_k (-2 z_tk) (ai_k + aj_k),
+//   S = sum_k x_k^2 + sum_k a_k^2 per training point,  c_t = sum_k y x'^2 + 2 sum_k z^2,
+// i.e. an (8 test points) x (8 pairs) x (F = 1 + 2 Dw + Dz features) product per mma.m8n8k4 chain instead of
+// 3 Dw + 3 Dz vector operations per (test point, pair).  What stays on the FP64 vector pipe is the exp and the
+// two weighted accumulations.  Every feature is V_i[c] + V_j[c] (optionally squared) for one column c of the
+// per-point table V = [x | a | S], so the feature generation is branch-free.
+// part[(chunk*M + t)*2 + {0,1}] = partial (a'Ja , tr(R^-1 J)) over the pair tiles of this chunk.
+// ------------------------------------------------------------------------------------------------
+constexpr int LT = 16;   // test points per CTA (two m8 octets)
+constexpr int LPT = 64;  // pair tile edge of the tensor-path kernel (64 octets per warp between barriers)
+
+__device__ __forceinline__ void link_dmma(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+// exp(x) for x <= ~0 in 18 instructions (the library routine is ~35): k = round(x log2 e) by the magic-number
+// trick, two-step Cody-Waite reduction, degree-11 Taylor polynomial on |r| <= ln2/2 (truncation 6e-15 relative),
+// scaling through the exponent field.  Arguments below -700 return 0 (the library would give a subnormal < 1e-304).
+__device__ __forceinline__ double exp_nonpos(double x) {
+    const double t = fma(x, 1.4426950408889634074, 6755399441055744.0);
+    const int k = __double2loint(t);
+    const double kf = t - 6755399441055744.0;
+    double r = fma(kf, -6.93147180369123816490e-01, x);
+    r = fma(kf, -1.90821492927058770002e-10, r);
+    double p = 2.50521083854417187751e-08;            // 1/11!
+    p = fma(p, r, 2.75573192239858906526e-07);        // 1/10!
+    p = fma(p, r, 2.75573192239858906526e-06);        // 1/9!
+    p = fma(p, r, 2.48015873015873015873e-05);        // 1/8!
+    p = fma(p, r, 1.98412698412698412698e-04);        // 1/7!
+    p = fma(p, r, 1.38888888888888888889e-03);        // 1/6!
+    p = fma(p, r, 8.33333333333333333333e-03);        // 1/5!
+    p = fma(p, r, 4.16666666666666666667e-02);        // 1/4!
+    p = fma(p, r, 1.66666666666666666667e-01);        // 1/3!
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    const double s = __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+    return x < -700.0 ? 0.0 : s;
+}
+
+// KST = number of k-steps when known at compile time (feature map and coefficient fragments live in registers,
+// the k loop is unrolled), 0 = runtime loop with the tables in shared memory.
+template <int KST>
+__global__ void __launch_bounds__(256, 2) linkgp_sexp_mma_kernel(LinkArgs a, int PC, double* __restrict__ part) {
+    extern __shared__ double lsm[];
+    const int Dw = a.Dw, Dz = a.Dz, DV = Dw + Dz + 1;      // columns of V
+    const int F = 1 + 2 * Dw + Dz, KS = (F + 3) / 4, F4 = 4 * KS;
+    const int CS = (F4 % 16 == 4 || F4 % 16 == 12) ? F4 : F4 + 4;   // coefficient row stride: conflict-free fragments
+    const int VS = DV | 1;                                           // V row stride (odd)
+    double* coef = lsm;                    // [LT][CS]
+    double* sct = coef + LT * CS;          // [LT]  c_t
+    double* sjc = sct + LT;                // [LT]  jc_t
+    double* VI = sjc + LT;                 // [PT][VS]
+    double* VJ = VI + LPT * VS;             // [PT][VS]
+    double* alI = VJ + LPT * VS;            // [PT]
+    double* alJ = alI + LPT;                // [PT]
+    double* sred = alJ + LPT;               // [8][LT][2]
+    int* fcol = reinterpret_cast<int*>(sred + 8 * LT * 2);   // [F4]: column of V, bit 30 = square the sum
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int g = lane >> 2, t4 = lane & 3;
+    const int t0 = blockIdx.x * LT;
+    // ---- per-CTA tables: feature map and test-point coefficients
+    for (int f = tid; f < F4; f += 256) {
+        int c = 0, sq = 0;
+        if (f == 0) c = Dw + Dz;
+        else if (f <= 2 * Dw) { c = (f - 1) >> 1; sq = ((f - 1) & 1) == 0; }
+        else if (f < F) c = f - 1 - Dw;
+        fcol[f] = c | (sq << 30);
+    }
+    for (int idx = tid; idx < LT * CS; idx += 256) coef[idx] = 0.0;
+    __syncthreads();
+    for (int idx = tid; idx < LT * (Dw + Dz); idx += 256) {
+        const int t = idx / (Dw + Dz), k = idx - t * (Dw + Dz), gt = t0 + t;
+        if (gt >= a.M) continue;
+        if (k < Dw) {
+            const double l = a.len[k];
+            const double y = 1.0 / (2.0 + 8.0 * a.v_in[(int64_t)gt * Dw + k] / (l * l));
+            const double xp = 2.0 * a.m_in[(int64_t)gt * Dw + k] / l;
+            coef[t * CS + 1 + 2 * k] = y - 0.5;
+            coef[t * CS + 2 + 2 * k] = -2.0 * y * xp;
+        } else {
+            const int kz = k - Dw;
+            coef[t * CS + 1 + 2 * Dw + kz] = -2.0 * (a.z[(int64_t)gt * Dz + kz] / a.len[k]);
+        }
+    }
+    if (tid < LT) {
+        const int gt = t0 + tid;
+        double c = 0.0, jc = 0.0;
+        if (gt < a.M) {
+            jc = 1.0;
+            for (int k = 0; k < Dw; ++k) {
+                const double l = a.len[k], v = a.v_in[(int64_t)gt * Dw + k];
+                const double y = 1.0 / (2.0 + 8.0 * v / (l * l));
+                const double xp = 2.0 * a.m_in[(int64_t)gt * Dw + k] / l;
+                c += y * xp * xp;
+                jc *= 1.0 + 4.0 * v / (l * l);
+            }
+            for (int k = 0; k < Dz; ++k) {
+                const double zt = a.z[(int64_t)gt * Dz + k] / a.len[Dw + k];
+                c += 2.0 * zt * zt;
+            }
+            jc = 1.0 / sqrt(jc);
+            coef[tid * CS] = 1.0;
+        }
+        sct[tid] = c;
+        sjc[tid] = jc;
+    }
+    double accq[2] = {0.0, 0.0}, acct[2] = {0.0, 0.0};
+    const int nt = (a.n + LPT - 1) / LPT;
+    const int ntiles = nt * (nt + 1) / 2;
+    // compile-time KS: this lane's feature columns and its coefficient fragments, once per CTA
+    constexpr int KR = KST > 0 ? KST : 1;
+    int rcol[KR];
+    double rco[2][KR];
+    double rct[2], rjc[2];
+    if (KST > 0) {
+        __syncthreads();
+#pragma unroll
+        for (int ks = 0; ks < KR; ++ks) {
+            rcol[ks] = fcol[4 * ks + t4];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) rco[h][ks] = coef[(8 * h + g) * CS + 4 * ks + t4];
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            rct[h] = sct[8 * h + g];
+            rjc[h] = sjc[8 * h + g];
+        }
+    }
+    for (int tl = blockIdx.y; tl < ntiles; tl += PC) {
+        int ti, tj;
+        tile_from_linear(tl, ti, tj);
+        __syncthreads();
+        // V rows of the two point tiles: [x/l | a/l | S]
+        for (int idx = tid; idx < 2 * LPT * (Dw + Dz); idx += 256) {
+            const int side = idx / (LPT * (Dw + Dz)), rem = idx - side * LPT * (Dw + Dz);
+            const int r = rem / (Dw + Dz), k = rem - r * (Dw + Dz);
+            const int gp = (side ? tj : ti) * LPT + r;
+            double v = 0.0;
+            if (gp < a.n) v = (k < Dw ? a.w1[(int64_t)gp * Dw + k] : a.gw[(int64_t)gp * Dz + (k - Dw)]) / a.len[k];
+            (side ? VJ : VI)[r * VS + k] = v;
+        }
+        if (tid < 2 * LPT) {
+            const int side = tid / LPT, r = tid - side * LPT;
+            const int gp = (side ? tj : ti) * LPT + r;
+            (side ? alJ : alI)[r] = gp < a.n ? a.alpha[gp] : 0.0;
+        }
+        __syncthreads();
+        if (tid < 2 * LPT) {
+            const int side = tid / LPT, r = tid - side * LPT;
+            double* V = (side ? VJ : VI) + r * VS;
+            double s = 0.0;
+            for (int k = 0; k < Dw + Dz; ++k) s += V[k] * V[k];
+            V[Dw + Dz] = s;
+        }
+        __syncthreads();
+        for (int o = w; o < LPT * LPT / 8; o += 8) {
+            // B role: this lane generates the features of pair (li, lj = 8 (o & 3) + g)
+            const int li = o >> 3, lj = 8 * (o & 7) + g;
+            const int gi = ti * LPT + li, gj = tj * LPT + lj;
+            const bool valid = gi < a.n && gj <= gi;
+            if (!__any_sync(0xffffffffu, valid)) continue;
+            const double wgt = valid ? (gi == gj ? 1.0 : 2.0) : 0.0;
+            const double rinv = valid ? a.Rinv[(int64_t)gi * a.n + gj] : 0.0;
+            const double wq_b = wgt * alI[li] * alJ[lj];
+            const double* vi = VI + li * VS;
+            const double* vj = VJ + lj * VS;
+            double c[2][2];
+            if (KST > 0) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) c[h][0] = c[h][1] = rct[h];
+#pragma unroll
+                for (int ks = 0; ks < KR; ++ks) {
+                    const int col = rcol[ks] & 0xffff;
+                    double b = vi[col] + vj[col];
+                    if (rcol[ks] >> 30) b *= b;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) link_dmma(c[h][0], c[h][1], rco[h][ks], b);
+                }
+            } else {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) c[h][0] = c[h][1] = sct[8 * h + g];
+                for (int ks = 0; ks < KS; ++ks) {
+                    const int fc = fcol[4 * ks + t4];
+                    const int col = fc & 0xffff;
+                    double b = vi[col] + vj[col];
+                    if (fc >> 30) b *= b;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) link_dmma(c[h][0], c[h][1], coef[(8 * h + g) * CS + 4 * ks + t4], b);
+                }
+            }
+            const double wr_b = wgt * rinv;
+            // C role: test point g (of each octet), pairs 2 t4 and 2 t4 + 1 -> their weights live on lanes 8 t4, 8 t4 + 4
+            // (exchanged here, after the tensor work, so the R^-1 load latency is covered by it)
+            const double wq0 = __shfl_sync(0xffffffffu, wq_b, 8 * t4), wq1 = __shfl_sync(0xffffffffu, wq_b, 8 * t4 + 4);
+            const double wr0 = __shfl_sync(0xffffffffu, wr_b, 8 * t4), wr1 = __shfl_sync(0xffffffffu, wr_b, 8 * t4 + 4);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const double jc = KST > 0 ? rjc[h] : sjc[8 * h + g];
+                const double J0 = jc * exp_nonpos(-c[h][0]), J1 = jc * exp_nonpos(-c[h][1]);
+                accq[h] = fma(wq1, J1, fma(wq0, J0, accq[h]));
+                acct[h] = fma(wr1, J1, fma(wr0, J0, acct[h]));
+            }
+        }
+    }
+    // lanes t4 = 0..3 of a row hold partial sums of the same test point; then the 8 warps through shared memory
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        accq[h] += __shfl_xor_sync(0xffffffffu, accq[h], 1);
+        accq[h] += __shfl_xor_sync(0xffffffffu, accq[h], 2);
+        acct[h] += __shfl_xor_sync(0xffffffffu, acct[h], 1);
+        acct[h] += __shfl_xor_sync(0xffffffffu, acct[h], 2);
+    }
+    __syncthreads();
+    if (t4 == 0) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            sred[(w * LT + 8 * h + g) * 2 + 0] = accq[h];
+            sred[(w * LT + 8 * h + g) * 2 + 1] = acct[h];
+        }
+    }
+    __syncthreads();
+    if (tid < LT * 2) {
+        const int t = tid >> 1, which = tid & 1;
+        double s = 0.0;
+        for (int ww = 0; ww < 8; ++ww) s += sred[(ww * LT + t) * 2 + which];   // fixed order
+        if (t0 + t < a.M) part[((int64_t)blockIdx.y * a.M + t0 + t) * 2 + which] = s;
+    }
+}
+
+static size_t linkgp_mma_smem(int Dw, int Dz) {
+    const int DV = Dw + Dz + 1, F = 1 + 2 * Dw + Dz, F4 = 4 * ((F + 3) / 4);
+    const int CS = (F4 % 16 == 4 || F4 % 16 == 12) ? F4 : F4 + 4, VS = DV | 1;
+    return sizeof(double) * (size_t)(LT * CS + 2 * LT + 2 * LPT * VS + 2 * LPT + 8 * LT * 2) + sizeof(int) * F4 + 16;
+}
+
+static int g_linkgp_mma = 1;   // dgpb_tune("linkgp_mma", 0): vector-pipe pair kernel
+int linkgp_set_mma(int on) {
+    g_linkgp_mma = on != 0;
+    return DGPB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // link_gp second moments, Matern-2.5 kernel (direct closed form per pair and dimension)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) linkgp_matern_pairs_kernel(LinkArgs a, int PC, double* __restrict__ part) {
@@ -594,6 +845,46 @@ int dgpb_linkgp_predict(dgpb_ws* ws, const double* m_in, const double* v_in, con
         linkgp_mean_kernel<<<(unsigned)cdiv((int64_t)Mc * 32, 256), 256, 0, st>>>(a, mean + m0);
         DGPB_LAUNCHED();
         dim3 grid((unsigned)ntt, (unsigned)PC);
+        if (kind == DGPB_SEXP && g_linkgp_mma) {
+            const int ntt2 = (int)cdiv(Mc, LT);
+            const int nt2 = (int)cdiv(n, LPT);
+            int PC2 = (int)cdiv(148 * 4, ntt2);
+            PC2 = std::max(1, std::min(PC2, nt2 * (nt2 + 1) / 2));
+            DGPB_TRY(ws->reserve(SLOT_PART, sizeof(double) * (size_t)PC2 * Mc * 2, &part));
+            const size_t smem = linkgp_mma_smem((int)Dw, (int)Dz);
+            static size_t configured = 0;
+            if (smem > configured) {
+                const int cap = (int)linkgp_mma_smem(kMaxDim, kMaxDim);
+                DGPB_CUDA_TRY(cudaFuncSetAttribute(linkgp_sexp_mma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+                DGPB_CUDA_TRY(cudaFuncSetAttribute(linkgp_sexp_mma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+                DGPB_CUDA_TRY(cudaFuncSetAttribute(linkgp_sexp_mma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+                DGPB_CUDA_TRY(cudaFuncSetAttribute(linkgp_sexp_mma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+                DGPB_CUDA_TRY(cudaFuncSetAttribute(linkgp_sexp_mma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+                DGPB_CUDA_TRY(cudaFuncSetAttribute(linkgp_sexp_mma_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+                DGPB_CUDA_TRY(cudaFuncSetAttribute(linkgp_sexp_mma_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+                DGPB_CUDA_TRY(cudaFuncSetAttribute(linkgp_sexp_mma_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+                DGPB_CUDA_TRY(cudaFuncSetAttribute(linkgp_sexp_mma_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+                configured = linkgp_mma_smem(kMaxDim, kMaxDim);
+            }
+            const int KSv = (1 + 2 * (int)Dw + (int)Dz + 3) / 4;
+            const dim3 grid2((unsigned)ntt2, (unsigned)PC2);
+#define LINK_MMA_CASE(K)                                                                                   \
+    case K:                                                                                                \
+        linkgp_sexp_mma_kernel<K><<<grid2, 256, smem, st>>>(a, PC2, (double*)part);                        \
+        break;
+            switch (KSv <= 8 ? KSv : 0) {
+                LINK_MMA_CASE(1) LINK_MMA_CASE(2) LINK_MMA_CASE(3) LINK_MMA_CASE(4) LINK_MMA_CASE(5) LINK_MMA_CASE(6)
+                LINK_MMA_CASE(7) LINK_MMA_CASE(8)
+                default:
+                    linkgp_sexp_mma_kernel<0><<<grid2, 256, smem, st>>>(a, PC2, (double*)part);
+            }
+#undef LINK_MMA_CASE
+            DGPB_LAUNCHED();
+            linkgp_finish_kernel<<<(unsigned)cdiv(Mc, 256), 256, 0, st>>>((double*)part, PC2, Mc, mean + m0, scale,
+                                                                         nugget, var + m0);
+            DGPB_LAUNCHED();
+            continue;
+        }
         if (kind == DGPB_SEXP) {
             int rc;
             if (Dw <= 1) rc = launch_sexp_pairs<1, 4>(a, grid, PC, (double*)part, st);

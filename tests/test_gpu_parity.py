@@ -244,6 +244,40 @@ def test_predictions_given_reference_stats(golden_dense):
             assert np.max(np.abs(v2 - c["lk_v"])) <= 1e-9 * c["scale_after"][0], ci
 
 
+def test_linkgp_tensor_core_kernel_equals_vector_kernel():
+    """link_gp with the squared-exponential kernel evaluates the J exponents as a DMMA product of test-point
+    coefficients and pair features; same moments as the vector-pipe kernel and the oracle, with and without
+    connected global inputs, ragged n / M."""
+    from dgp_b200 import _lib as L
+    import dgp_b200 as D
+    from oracle import dgp_oracle as O
+
+    lib = L.load()
+    rng = np.random.default_rng(41)
+    for n, M, Dw, Dz, ard in ((150, 37, 3, 0, False), (333, 70, 8, 8, False), (257, 16, 5, 2, True), (64, 100, 1, 0, False)):
+        D_all = Dw + Dz
+        length = rng.uniform(0.5, 1.5, D_all if ard else 1)
+        k = D.kernel(length=length.copy(), name="sexp", nugget=1e-3, scale=1.4,
+                     connect=np.arange(Dz) if Dz else None)
+        k.input = rng.uniform(0, 1, (n, Dw))
+        k.input_dim = np.arange(Dw)
+        if Dz:
+            k.global_input = rng.uniform(0, 1, (n, Dz))
+        k.output = np.sin(k.input.sum(1, keepdims=True) * 2)
+        k.D = D_all
+        k.compute_stats()
+        m_in, v_in = rng.uniform(0, 1, (M, Dw)), rng.uniform(1e-4, 0.05, (M, Dw))
+        z = rng.uniform(0, 1, (M, Dz)) if Dz else None
+        L.check(lib.dgpb_tune(b"linkgp_mma", 0))
+        try:
+            m0, v0 = k.linkgp_prediction(m_in, v_in, z)
+        finally:
+            L.check(lib.dgpb_tune(b"linkgp_mma", 1))
+        m1, v1 = k.linkgp_prediction(m_in, v_in, z)
+        assert relerr(m1, m0, 1e-9) <= 1e-10, (n, M, Dw, Dz)
+        assert np.max(np.abs(v1 - v0)) <= 1e-9 * max(1.0, np.max(np.abs(v0))), (n, M, Dw, Dz, np.max(np.abs(v1 - v0)))
+
+
 def test_linkgp_wide_inputs_vs_oracle():
     """Dw beyond the register-tiled template sizes and n not a multiple of the pair tile."""
     import dgp_b200 as D
