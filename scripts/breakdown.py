@@ -23,4 +23,9 @@ for it in range(2):
             c0 = D._lib.load().dgpb_launch_count()
             k.maximise()
         torch.cuda.synchronize(); tl.append(time.perf_counter() - ts)
-    print("iter %d: I-step %.2fs (%d proposals)  M-step layers %s" % (it, t1 - t0, model.imp.n_proposals - p0, ["%.2f" % t for t in tl]))
+    print("iter %d: I-step %.2fs (%d proposals)  M-step layers (one node at a time) %s" % (it, t1 - t0, model.imp.n_proposals - p0, ["%.2f" % t for t in tl]))
+for it in range(2):
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    model.imp.sample(burnin=10); torch.cuda.synchronize(); t1 = time.perf_counter()
+    model._m_step(); torch.cuda.synchronize(); t2 = time.perf_counter()
+    print("iter %d: I-step %.2fs, threaded M-step %.2fs" % (it, t1 - t0, t2 - t1))
