@@ -261,6 +261,7 @@ def run_gpu(args):
     launches0 = lib.dgpb_launch_count()
     prop0 = model.imp.n_proposals
     lib.dgpb_profile(1)
+    tim0 = dict(model.timing)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clocks:
@@ -397,7 +398,10 @@ def run_gpu(args):
                 "config": workload_config(args, world),
                 "e2e": {"value": e2e, "unit": "iters/s", "h2d_bytes_per_step": h2d // args.steps,
                         "d2h_bytes_per_step": d2h // args.steps},
-                "gpu_launches": int(launches), "ess_proposals_per_step": nprop / args.steps, "roofline": roof,
+                "gpu_launches": int(launches), "ess_proposals_per_step": nprop / args.steps,
+                "phase_ms_per_step": {"i_step": 1e3 * (model.timing["i_step"] - tim0["i_step"]) / args.steps,
+                                      "m_step": 1e3 * (model.timing["m_step"] - tim0["m_step"]) / args.steps},
+                "roofline": roof,
                 "cpu_baseline": cpu, "clocks": clocks.summary(), "predict": predict, "predict_vecchia": predict_v}
         print(json.dumps(line), flush=True)
     if dist is not None:

@@ -54,6 +54,8 @@ _PROTOS = {
                                     c_vp, c_vp]),
     "dgpb_loglik_dense": (ctypes.c_int, [c_vp, ctypes.POINTER(DgpbNode), c_i64, c_vp, c_vp]),
     "dgpb_nllik_grad_dense": (ctypes.c_int, [c_vp, ctypes.POINTER(DgpbNode), c_i64, c_vp, c_vp]),
+    "dgpb_nllik_grad_dense_batch": (ctypes.c_int, [c_vp, ctypes.POINTER(DgpbNode), ctypes.c_int, c_i64, c_vp,
+                                                   ctypes.c_int, c_vp, c_vp]),
     "dgpb_compute_stats": (ctypes.c_int, [c_vp, ctypes.POINTER(DgpbNode), c_i64, c_vp, c_vp, c_vp]),
     "dgpb_mvn_draw": (ctypes.c_int, [c_vp, ctypes.POINTER(DgpbNode), c_i64, c_vp, c_vp, c_vp]),
     "dgpb_ess_block": (ctypes.c_int, [c_vp, ctypes.POINTER(DgpbNode), ctypes.c_int, c_vp, c_vp, c_i64,

@@ -928,6 +928,56 @@ int dgpb_nllik_grad_dense(dgpb_ws* ws, const dgpb_node* node, int64_t n, double*
     return grad_pipeline(ws, node, n, true, nullptr, nullptr, out_host, (cudaStream_t)stream);
 }
 
+int dgpb_nllik_grad_dense_batch(dgpb_ws* ws, const dgpb_node* nodes, int B, int64_t n, double* out_host, int ldo,
+                                int* status_host, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    DGPB_REQUIRE(ws && nodes && out_host && status_host && n >= 1, "NULL argument");
+    DGPB_REQUIRE(B >= 1 && B <= MAXB, "batch size out of range");
+    KernelDev kds[MAXB];
+    const double* ys[MAXB];
+    ScaleArgs sa;
+    int Pmax = 0;
+    for (int b = 0; b < B; ++b) {
+        DGPB_TRY(make_kernel_dev(&nodes[b], n, nullptr, &kds[b]));
+        ys[b] = nodes[b].output;
+        sa.scale[b] = nodes[b].scale;
+        sa.est[b] = nodes[b].scale_est;
+        Pmax = std::max(Pmax, nodes[b].nlen + (nodes[b].nugget_est ? 1 : 0));
+    }
+    DGPB_REQUIRE(ldo >= Pmax + 2, "ldo too small");
+    Geom g = make_geom(n, true);
+    Batch bt;
+    double* out;
+    DGPB_TRY(setup_batch(ws, g, B, &bt, &out));
+    DGPB_TRY(assemble(g, kds, ys, bt, B, st));
+    DGPB_TRY(factorize(g, bt, B, st));
+    DGPB_TRY(reduce_logdet_quad(g, bt, B, sa, out, st));
+    const int nt = (int)cdiv(n, 64);
+    const int ntiles = nt * (nt + 1) / 2;
+    const int LDF = Pmax + 2;
+    void *part, *fin;
+    DGPB_TRY(ws->reserve(SLOT_PART, sizeof(double) * (size_t)ntiles * Pmax * B, &part));
+    DGPB_TRY(ws->reserve(SLOT_MISC2, sizeof(double) * (size_t)LDF * B, &fin));
+    DGPB_REQUIRE((size_t)LDF * B <= 2048, "result block too large for the staging buffer");
+    for (int b = 0; b < B; ++b) {
+        const int P = nodes[b].nlen + (nodes[b].nugget_est ? 1 : 0);
+        double* pb = (double*)part + (size_t)ntiles * Pmax * b;
+        grad_kernel<<<ntiles, 256, 0, st>>>(kds[b], bt.T[b], g.ld, g.n, g.npad, P, nodes[b].nugget_est, out + 4 * b, pb);
+        DGPB_LAUNCHED();
+        grad_finish_kernel<<<P, 256, 0, st>>>(pb, ntiles, P, g.n, nodes[b].scale_est, out + 4 * b, (double*)fin + (size_t)LDF * b);
+        DGPB_LAUNCHED();
+    }
+    int* info_host = reinterpret_cast<int*>(ws->pinned + 2048);
+    DGPB_CUDA_TRY(cudaMemcpyAsync(ws->pinned, fin, sizeof(double) * (size_t)LDF * B, cudaMemcpyDeviceToHost, st));
+    DGPB_CUDA_TRY(cudaMemcpyAsync(info_host, bt.info, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
+    DGPB_CUDA_TRY(cudaStreamSynchronize(st));
+    for (int b = 0; b < B; ++b) {
+        status_host[b] = info_host[b] != 0 ? DGPB_NOT_PD : DGPB_OK;
+        for (int i = 0; i < LDF; ++i) out_host[(size_t)b * ldo + i] = ws->pinned[(size_t)LDF * b + i];
+    }
+    return DGPB_OK;
+}
+
 int dgpb_compute_stats(dgpb_ws* ws, const dgpb_node* node, int64_t n, double* Rinv, double* Rinv_y, void* stream) {
     DGPB_REQUIRE(ws && node && Rinv && Rinv_y && n >= 1, "NULL argument");
     return grad_pipeline(ws, node, n, false, Rinv, Rinv_y, nullptr, (cudaStream_t)stream);

@@ -10,6 +10,7 @@ from __future__ import annotations
 
 import copy
 import threading
+import time
 
 import numpy as np
 
@@ -38,6 +39,68 @@ except Exception:  # pragma: no cover
 
 
 _tls = threading.local()
+
+
+class _GradBatcher:
+    """Rendezvous of the M-step's optimiser threads: a request blocks until every thread that is still optimising
+    has one pending, then the last arrival runs the whole batch through `dgpb_nllik_grad_dense_batch` (on the
+    workspace of the thread that started the M-step) and wakes the others."""
+
+    def __init__(self, nworkers, ws, dev):
+        import threading
+        self.cond = threading.Condition()
+        self.active = nworkers
+        self.pending = []       # [node, n, P, result slot]
+        self.ws, self.dev = ws, dev
+
+    def _flush_locked(self):
+        from . import _lib as L
+        reqs, self.pending = self.pending, []
+        try:
+            B = len(reqs)
+            n = reqs[0][1]
+            if any(r[1] != n for r in reqs):
+                raise RuntimeError("nodes of one M-step must share the number of training points")
+            ldo = max(r[2] for r in reqs) + 2
+            arr = (L.DgpbNode * B)(*[r[0] for r in reqs])
+            out = np.zeros((B, ldo))
+            status = np.zeros(B, dtype=np.int32)
+            L.torch_mod().cuda.set_device(self.dev)
+            rc = L.load().dgpb_nllik_grad_dense_batch(self.ws, arr, B, n, out.ctypes.data_as(L.c_vp), ldo,
+                                                      status.ctypes.data_as(L.c_vp), L.stream())
+            msg = L.load().dgpb_last_error().decode("utf-8", "replace") if rc != L.DGPB_OK else ""
+            for b, r in enumerate(reqs):
+                r[3].extend([rc if rc != L.DGPB_OK else int(status[b]), out[b].copy(),
+                             msg or "matrix %d of the batch is not positive definite" % b])
+        except Exception as exc:  # never leave the other optimiser threads waiting
+            for r in reqs:
+                if not r[3]:
+                    r[3].extend([L.DGPB_CUDA_ERROR, None, str(exc)])
+        self.cond.notify_all()
+
+    def evaluate(self, node, n, P):
+        from . import _lib as L
+        slot = []
+        with self.cond:
+            self.pending.append([node, n, P, slot])
+            if len(self.pending) >= self.active:
+                self._flush_locked()
+            else:
+                while not slot:
+                    self.cond.wait()
+        rc, out, msg = slot
+        if rc == L.DGPB_NOT_PD:
+            raise np.linalg.LinAlgError(msg or "matrix is not positive definite")
+        if rc != L.DGPB_OK:
+            raise RuntimeError("dgp_b200: " + msg)
+        return out
+
+    def retire(self):
+        """An optimiser thread has finished: the others no longer wait for it."""
+        with self.cond:
+            self.active -= 1
+            if self.pending and len(self.pending) >= self.active:
+                self._flush_locked()
 
 
 class dgp:
@@ -84,6 +147,7 @@ class dgp:
         self.compute_r2()
         self.N = 0
         self.burnin = None
+        self.timing = {'i_step': 0.0, 'm_step': 0.0}
 
     def __setstate__(self, state):
         for key, val in (('block', True), ('vecch', False), ('nn_method', 'exact'), ('m', 25), ('ord_fun', None),
@@ -198,10 +262,17 @@ class dgp:
             try:
                 pgb = trange(1, N + 1, disable=disable)
                 for i in pgb:
+                    t0 = time.perf_counter()
                     (self.imp).sample(burnin=ess_burn)
                     if self.vecch and (self.N + i & (self.N + i - 1)) == 0 and self.N + i > 1:
                         (self.imp).update_ord_nn()
+                    t1 = time.perf_counter()
                     self._m_step()
+                    # wall-clock split (both phases end with a device-to-host read): instrumentation for bench.py
+                    if not hasattr(self, 'timing'):
+                        self.timing = {'i_step': 0.0, 'm_step': 0.0}
+                    self.timing['i_step'] += t1 - t0
+                    self.timing['m_step'] += time.perf_counter() - t1
                     pgb.set_description('Iteration %i' % i)
                 self.N += N
                 return
@@ -217,41 +288,53 @@ class dgp:
                 self.reinit_all_layer(reset_lengthscale=True, row=self.N)
 
     def _m_step(self):
-        """M-step over every GP node (dgp.py:1391-1398).  Given the imputation the nodes are independent, so
-        their L-BFGS-B runs are issued from a small thread pool, one CUDA stream and workspace per thread: the
-        serial part of one node's blocked factorisation (panel kernels) overlaps the tensor-core updates of
-        the others.  Results do not depend on the scheduling (each node's optimisation is self-contained)."""
+        """M-step over every GP node (dgp.py:1391-1398).  Given the imputation the nodes are independent, so their
+        L-BFGS-B runs proceed side by side (one host thread each) and every round of objective/gradient requests
+        is served by ONE batched sliding-window factorisation (`dgpb_nllik_grad_dense_batch`): the batch fills the
+        GPU where a single n = 5000 node leaves the tensor pipe waiting on its serial panel chain.  Each node sees
+        exactly the numbers it would see alone (the batched kernels treat matrices independently), so parameter
+        paths do not depend on the scheduling.  Vecchia nodes keep the one-node-at-a-time path."""
         import os
         from concurrent.futures import ThreadPoolExecutor
 
         from . import _lib as L
 
         nodes = [(l, kernel) for l in range(self.n_layer) for kernel in self.all_layer[l]]
-        nthreads = max(1, min(len(nodes), int(os.environ.get('DGPB_MSTEP_THREADS', '6'))))
         torch = L.torch_mod()
         dev = L.device()
+        dense = [it for it in nodes if not it[1].vecch]
+        batch = len(dense) > 1 and os.environ.get('DGPB_MSTEP_BATCH', '1') != '0'
+        if not batch:
+            dense = []
+        for l, kernel in nodes:   # nodes outside the batch
+            if any(kernel is k for _, k in dense):
+                continue
+            if kernel.prior_name == 'ref':
+                kernel.compute_cl()
+            if l != 0:
+                kernel.r2()
+            kernel.maximise()
+        if not dense:
+            return
+        torch.cuda.current_stream().synchronize()
+        batcher = _GradBatcher(len(dense), L.workspace(), dev)
 
         def work(item):
             l, kernel = item
             torch.cuda.set_device(dev)
-            stream = getattr(_tls, 'stream', None)
-            if stream is None:
-                stream = _tls.stream = torch.cuda.Stream(device=dev)
-            with torch.cuda.stream(stream):
+            try:
                 if kernel.prior_name == 'ref':
                     kernel.compute_cl()
                 if l != 0:
                     kernel.r2()
+                kernel._batcher = batcher
                 kernel.maximise()
-                stream.synchronize()
+            finally:
+                kernel._batcher = None
+                batcher.retire()
 
-        if nthreads == 1:
-            for item in nodes:
-                work(item)
-            return
-        torch.cuda.current_stream().synchronize()
-        with ThreadPoolExecutor(max_workers=nthreads) as pool:
-            for fut in [pool.submit(work, item) for item in nodes]:
+        with ThreadPoolExecutor(max_workers=len(dense)) as pool:
+            for fut in [pool.submit(work, item) for item in dense]:
                 fut.result()
 
     def ptrain(self, *args, **kwargs):

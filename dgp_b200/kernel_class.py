@@ -99,6 +99,7 @@ class kernel:
         state['Rinv'] = _as_numpy(state.pop('_Rinv'))
         state['Rinv_y'] = _as_numpy(state.pop('_Rinv_y'))
         state.pop('_dcache', None)
+        state.pop('_batcher', None)
         return state
 
     def __setstate__(self, state):
@@ -269,8 +270,13 @@ class kernel:
         bufs = self._dcache or self._upload()
         node = self._node(bufs)
         P = len(self.length) + (1 if self.nugget_est else 0)
-        out = L.host_doubles(P + 2)
-        L.check(L.load().dgpb_nllik_grad_dense(L.workspace(), ctypes.byref(node), self.input.shape[0], out, L.stream()))
+        batcher = getattr(self, '_batcher', None)
+        if batcher is not None:
+            out = batcher.evaluate(node, self.input.shape[0], P)   # batched with the other nodes of the M-step
+        else:
+            out = L.host_doubles(P + 2)
+            L.check(L.load().dgpb_nllik_grad_dense(L.workspace(), ctypes.byref(node), self.input.shape[0], out,
+                                                   L.stream()))
         neg_llik = np.array([out[0]])
         if self.scale_est:
             self.scale = np.array([out[1]])

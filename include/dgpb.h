@@ -104,6 +104,13 @@ int dgpb_loglik_dense(dgpb_ws* ws, const dgpb_node* node, int64_t n, double* out
  * dK recomputed on the fly (the P x n x n `fod` tensor of functions.py:36-93 is never built). */
 int dgpb_nllik_grad_dense(dgpb_ws* ws, const dgpb_node* node, int64_t n, double* out_host, void* stream);
 
+/* dgpb_nllik_grad_dense for B independent nodes of the same n in ONE batched sliding-window factorisation (the
+ * M-step of a DGP: given the imputation the nodes are independent, dgp.py:1391-1398, and their L-BFGS-B runs ask
+ * for evaluations at the same time).  Row b of out_host (leading dimension ldo >= max P + 2) = [nllik, scale,
+ * grad[0..P_b)]; status_host[b] = DGPB_OK or DGPB_NOT_PD per node.  Results are bit-identical to B separate calls. */
+int dgpb_nllik_grad_dense_batch(dgpb_ws* ws, const dgpb_node* nodes, int B, int64_t n, double* out_host, int ldo,
+                                int* status_host, void* stream);
+
 /* kernel.compute_stats  kernel_class.py:735-748: Rinv (n x n, full symmetric) and Rinv_y (n). */
 int dgpb_compute_stats(dgpb_ws* ws, const dgpb_node* node, int64_t n, double* Rinv, double* Rinv_y,
                        void* stream);

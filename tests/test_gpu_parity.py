@@ -610,6 +610,34 @@ def test_linked_system_with_frozen_imputations(golden_e2e):
     assert np.max(np.abs(var[0] - g["lgp_var"])) <= 5e-6 * max(1.0, np.max(g["lgp_var"]))
 
 
+def test_batched_m_step_equals_one_node_at_a_time(monkeypatch):
+    """The M-step serves every round of L-BFGS-B requests of all dense nodes with one batched sliding-window
+    factorisation; each node must follow exactly the parameter path it follows alone."""
+    import copy
+    import dgp_b200 as D
+
+    rng = np.random.default_rng(5)
+    n, d = 180, 3
+    X = rng.uniform(0, 1, (n, d))
+    Y = np.stack([np.sin(4 * X.sum(1)), X[:, 0] * X[:, 1]], 1)
+    np.random.seed(3)
+    D.nb_seed(3)
+    l1 = [D.kernel(length=np.array([1.0]), name="sexp") for _ in range(3)]
+    l2 = [D.kernel(length=np.array([1.0, 1.2, 0.8, 1.1, 0.9, 1.0]), name="matern2.5", scale_est=True, nugget_est=True,
+                   nugget=1e-3, connect=np.arange(d)) for _ in range(2)]
+    model = D.dgp(X, Y, D.combine(l1, l2))
+    model.imp.sample(burnin=2)
+    twin = copy.deepcopy(model)
+    monkeypatch.setenv("DGPB_MSTEP_BATCH", "0")
+    twin._m_step()
+    monkeypatch.setenv("DGPB_MSTEP_BATCH", "1")
+    model._m_step()
+    for la, lb in zip(model.all_layer, twin.all_layer):
+        for ka, kb in zip(la, lb):
+            assert np.array_equal(ka.length, kb.length) and np.array_equal(ka.scale, kb.scale)
+            assert np.array_equal(ka.nugget, kb.nugget)
+
+
 def test_public_api_train_and_predict_smoke():
     """The user-facing path runs: dgp(X,Y).train -> estimate -> emulator -> predict; the fit is sane."""
     import dgp_b200 as D
