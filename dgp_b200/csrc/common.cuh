@@ -219,6 +219,8 @@ int make_kernel_dev_rowmajor(const double* X, int64_t D, const double* length_ho
 
 // predict.cu: 1 = link_gp sexp exponents on the FP64 tensor path (default), 0 = vector-pipe pair kernel
 int linkgp_set_mma(int on);
+// predict.cu: 1 = tabulated Matern-2.5 link_gp kernel (default), 0 = direct closed form per pair
+int linkgp_set_matern_tab(int on);
 
 }  // namespace dgpb
 

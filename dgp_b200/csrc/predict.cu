@@ -722,6 +722,228 @@ __global__ void __launch_bounds__(256) linkgp_matern_pairs_kernel(LinkArgs a, in
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// link_gp second moments, Matern-2.5 kernel, TABULATED form.
+// Jd(x_i, x_j; mu, v, l) = P1 + P2 + P3 (vecchia.py:915-959) looks like ~400 flop + 3 erf + 5 exp per (pair,
+// dimension, test point), but every transcendental in it depends on ONE training point and the test point:
+//   P1 = e^{10v/l^2} ep(x1) ep(x2) [ AC(x2) E3A31 + BC(x2) E3A32 ]            (x1 <= x2)
+//   P2 = ep(x1) em(x2) [ 1/2 E4A41 (F(x2) - F(x1)) + E4A42 G(x1) - E4A43 G(x2) ]
+//   P3 = e^{10v/l^2} em(x1) em(x2) [ AD(x1) E5A51 + BD(x1) E5A52 ]
+//   ep(x) = e^{sqrt5 (x - mu)/l}, em = 1/ep, AC = (1 + erf((muC - x)/sqrt(2v)))/2, BC = sqrt(v/2pi) e^{-(x-muC)^2/2v},
+//   AD, BD the same around muD = mu + 2 sqrt5 v/l, F = erf((x - mu)/sqrt(2v)), G = sqrt(v/2pi) e^{-(x-mu)^2/2v},
+// and E3Axx / E4Axx / E5Axx are polynomials in (x1, x2) whose coefficients E30..E54 do not depend on the test
+// point.  So per pair tile and dimension the kernel tabulates the 8 transcendental values per (test point,
+// training point) -- 2 x 32 points instead of 1024 pairs -- computes the 12 polynomial coefficients once per
+// pair and is left with ~110 multiply-adds per (pair, dimension, test point).  Same closed form, same terms,
+// different association (tests: equality with the direct kernel to 1e-10 and with the oracle).
+// ------------------------------------------------------------------------------------------------
+constexpr int MT = 4;   // test points per CTA of the tabulated kernel
+
+__global__ void __launch_bounds__(256, 1) linkgp_matern_tab_kernel(LinkArgs a, int PC, double* __restrict__ part) {
+    extern __shared__ double msm[];
+    const int Dw = a.Dw, DS = Dw + 1;
+    double* cst = msm;                         // [MT][Dw][16] per (test point, dimension) constants
+    double* tab = cst + MT * Dw * 16;          // [2][MT][PT][8]
+    double* sI = tab + 2 * MT * PT * 8;        // [PT][DS] raw local coordinates of the row / column points
+    double* sJ = sI + PT * DS;
+    double* gzI = sJ + PT * DS;                // [MT][PT] global-input factors
+    double* gzJ = gzI + MT * PT;
+    double* alI = gzJ + MT * PT;               // [PT]
+    double* alJ = alI + PT;
+    double* sred = alJ + PT;                   // [8]
+    const int tid = threadIdx.x;
+    const int t0 = blockIdx.x * MT;
+    for (int idx = tid; idx < MT * Dw; idx += 256) {
+        const int t = idx / Dw, k = idx - t * Dw, gt = t0 + t;
+        const double l = a.len[k];
+        const double zm = gt < a.M ? a.m_in[(int64_t)gt * Dw + k] : 0.0;
+        const double zv = gt < a.M ? a.v_in[(int64_t)gt * Dw + k] : 0.0;
+        const double muC = zm - 2.0 * kSqrt5 * zv / l, muD = zm + 2.0 * kSqrt5 * zv / l;
+        const double c2 = muC * muC, d2 = muD * muD, z2 = zm * zm;
+        double* c = cst + idx * 16;
+        c[0] = zm;
+        c[1] = zv;
+        c[2] = muC;
+        c[3] = c2 + zv;
+        c[4] = c2 * muC + 3.0 * zv * muC;
+        c[5] = c2 * c2 + 6.0 * zv * c2 + 3.0 * zv * zv;
+        c[6] = muD;
+        c[7] = d2 + zv;
+        c[8] = d2 * muD + 3.0 * zv * muD;
+        c[9] = d2 * d2 + 6.0 * zv * d2 + 3.0 * zv * zv;
+        c[10] = z2 + zv;
+        c[11] = z2 * zm + 3.0 * zv * zm;
+        c[12] = z2 * z2 + 6.0 * zv * z2 + 3.0 * zv * zv;
+        c[13] = exp(10.0 * zv / (l * l));
+        c[14] = zv == 0.0 ? 1.0 : 0.0;   // deterministic input: J factor = k(mu - x_i) k(mu - x_j)
+        c[15] = 0.0;
+    }
+    double accq[MT], acct[MT];
+#pragma unroll
+    for (int t = 0; t < MT; ++t) accq[t] = acct[t] = 0.0;
+    const int nt = (a.n + PT - 1) / PT;
+    const int ntiles = nt * (nt + 1) / 2;
+    for (int tl = blockIdx.y; tl < ntiles; tl += PC) {
+        int ti, tj;
+        tile_from_linear(tl, ti, tj);
+        __syncthreads();
+        for (int idx = tid; idx < PT * Dw; idx += 256) {
+            const int r = idx / Dw, k = idx - r * Dw;
+            const int gi = ti * PT + r, gj = tj * PT + r;
+            sI[r * DS + k] = gi < a.n ? a.w1[(int64_t)gi * Dw + k] : 0.0;
+            sJ[r * DS + k] = gj < a.n ? a.w1[(int64_t)gj * Dw + k] : 0.0;
+        }
+        if (tid < PT) {
+            const int gi = ti * PT + tid, gj = tj * PT + tid;
+            alI[tid] = gi < a.n ? a.alpha[gi] : 0.0;
+            alJ[tid] = gj < a.n ? a.alpha[gj] : 0.0;
+        }
+        for (int idx = tid; idx < MT * PT; idx += 256) {
+            const int t = idx / PT, r = idx - t * PT, gt = t0 + t;
+            const int gi = ti * PT + r, gj = tj * PT + r;
+            gzI[idx] = (gt < a.M && gi < a.n) ? global_factor(a, gi, gt) : 0.0;
+            gzJ[idx] = (gt < a.M && gj < a.n) ? global_factor(a, gj, gt) : 0.0;
+        }
+        // this thread's four pairs
+        int lis[4], ljs[4];
+        bool valid[4], diag[4];
+        double wq[4], wr[4], Jv[4][MT];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int idx = tid + 256 * e;
+            lis[e] = idx >> 5;
+            ljs[e] = idx & 31;
+            const int gi = ti * PT + lis[e], gj = tj * PT + ljs[e];
+            valid[e] = gi < a.n && gj <= gi;
+            diag[e] = gi == gj;
+            wr[e] = valid[e] ? (diag[e] ? 1.0 : 2.0) * a.Rinv[(int64_t)gi * a.n + gj] : 0.0;
+#pragma unroll
+            for (int t = 0; t < MT; ++t) Jv[e][t] = 1.0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int e = 0; e < 4; ++e) wq[e] = valid[e] ? (diag[e] ? 1.0 : 2.0) * alI[lis[e]] * alJ[ljs[e]] : 0.0;
+        for (int k = 0; k < Dw; ++k) {
+            const double l = a.len[k];
+            {   // table entry of (side, test point, training point) = thread
+                const int side = tid >> 7, t = (tid >> 5) & 3, r = tid & 31;
+                const double* c = cst + (t * Dw + k) * 16;
+                const double x = (side ? sJ : sI)[r * DS + k];
+                const double zm = c[0], zv = c[1];
+                double* T = tab + ((side * MT + t) * PT + r) * 8;
+                if (c[14] != 0.0) {
+                    T[0] = matern_plain(zm - x, l);
+                    T[1] = T[2] = T[3] = T[4] = T[5] = T[6] = T[7] = 0.0;
+                } else {
+                    const double isv = 1.0 / sqrt(2.0 * zv), gg = sqrt(0.5 * zv / M_PI), h = -0.5 / zv;
+                    const double ep = exp(kSqrt5 * (x - zm) / l);
+                    const double uC = x - c[2], uD = x - c[6], uZ = x - zm;
+                    T[0] = ep;
+                    T[1] = 1.0 / ep;
+                    T[2] = 0.5 * (1.0 + erf(-uC * isv));
+                    T[3] = gg * exp(h * uC * uC);
+                    T[4] = 0.5 * (1.0 + erf(uD * isv));
+                    T[5] = gg * exp(h * uD * uD);
+                    T[6] = erf(uZ * isv);
+                    T[7] = gg * exp(h * uZ * uZ);
+                }
+            }
+            __syncthreads();
+            const double l2 = l * l, l3 = l2 * l, i9l4 = 1.0 / (9.0 * l2 * l2);
+            const double E4 = 25.0 * i9l4;   // E34 = E44 = E54
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                if (!valid[e]) continue;
+                const double xi = sI[lis[e] * DS + k], xj = sJ[ljs[e] * DS + k];
+                const bool sw = xi > xj;
+                const double x1 = sw ? xj : xi, x2 = sw ? xi : xj;
+                const double x1s = x1 * x1, x2s = x2 * x2, x12 = x1 * x2, xs = x1 + x2, xd = x2 - x1;
+                const double q25 = 25.0 * x1s * x2s, s12 = x1s + x2s;
+                const double E30 = 1.0 + (q25 - 3.0 * kSqrt5 * (3.0 * l3 + 5.0 * l * x12) * xs + 15.0 * l2 * (s12 + 3.0 * x12)) * i9l4;
+                const double E31 = (18.0 * kSqrt5 * l3 + 15.0 * kSqrt5 * l * s12 - (75.0 * l2 + 50.0 * x12) * xs + 60.0 * kSqrt5 * l * x12) * i9l4;
+                const double E32 = 5.0 * (5.0 * s12 + 15.0 * l2 - 9.0 * kSqrt5 * l * xs + 20.0 * x12) * i9l4;
+                const double E33 = 10.0 * (3.0 * kSqrt5 * l - 5.0 * xs) * i9l4;
+                const double E40 = 1.0 + (q25 + 3.0 * kSqrt5 * (3.0 * l3 - 5.0 * l * x12) * xd + 15.0 * l2 * (s12 - 3.0 * x12)) * i9l4;
+                const double E41 = 5.0 * (3.0 * kSqrt5 * l * (x2s - x1s) + 3.0 * l2 * xs - 10.0 * x12 * xs) * i9l4;
+                const double E42 = 5.0 * (5.0 * s12 - 3.0 * l2 - 3.0 * kSqrt5 * l * xd + 20.0 * x12) * i9l4;
+                const double E43 = -50.0 * xs * i9l4;
+                const double E50 = 1.0 + (q25 + 3.0 * kSqrt5 * (3.0 * l3 + 5.0 * l * x12) * xs + 15.0 * l2 * (s12 + 3.0 * x12)) * i9l4;
+                const double E51 = (18.0 * kSqrt5 * l3 + 15.0 * kSqrt5 * l * s12 + (75.0 * l2 + 50.0 * x12) * xs + 60.0 * kSqrt5 * l * x12) * i9l4;
+                const double E52 = 5.0 * (5.0 * s12 + 15.0 * l2 + 9.0 * kSqrt5 * l * xs + 20.0 * x12) * i9l4;
+                const double E53 = 10.0 * (3.0 * kSqrt5 * l + 5.0 * xs) * i9l4;
+                const double x1c = x1s * x1, x2c = x2s * x2;
+#pragma unroll
+                for (int t = 0; t < MT; ++t) {
+                    const double* c = cst + (t * Dw + k) * 16;
+                    const double* Ti = tab + ((0 * MT + t) * PT + lis[e]) * 8;
+                    const double* Tj = tab + ((1 * MT + t) * PT + ljs[e]) * 8;
+                    const double* T1 = sw ? Tj : Ti;   // table row of the smaller coordinate
+                    const double* T2 = sw ? Ti : Tj;
+                    double Jd;
+                    if (c[14] != 0.0) {
+                        Jd = Ti[0] * Tj[0];
+                    } else {
+                        const double zm = c[0], zv = c[1], muC = c[2], muD = c[6];
+                        const double2 a01 = *reinterpret_cast<const double2*>(T1), a23 = *reinterpret_cast<const double2*>(T1 + 2);
+                        const double2 a45 = *reinterpret_cast<const double2*>(T1 + 4), a67 = *reinterpret_cast<const double2*>(T1 + 6);
+                        const double2 b01 = *reinterpret_cast<const double2*>(T2), b23 = *reinterpret_cast<const double2*>(T2 + 2);
+                        const double2 b67 = *reinterpret_cast<const double2*>(T2 + 6);
+                        const double E3A31 = E30 + muC * E31 + c[3] * E32 + c[4] * E33 + c[5] * E4;
+                        const double c2 = muC * muC;
+                        const double E3A32 = E31 + (muC + x2) * E32 + (c2 + 2.0 * zv + x2s + muC * x2) * E33 +
+                                             (c2 * muC + x2c + x2 * c2 + muC * x2s + 3.0 * zv * x2 + 5.0 * zv * muC) * E4;
+                        const double P1 = c[13] * a01.x * b01.x * (b23.x * E3A31 + b23.y * E3A32);
+                        const double z2 = zm * zm;
+                        const double E4A41 = E40 + zm * E41 + c[10] * E42 + c[11] * E43 + c[12] * E4;
+                        const double E4A42 = E41 + (zm + x1) * E42 + (z2 + 2.0 * zv + x1s + zm * x1) * E43 +
+                                             (z2 * zm + x1c + x1 * z2 + zm * x1s + 3.0 * zv * x1 + 5.0 * zv * zm) * E4;
+                        const double E4A43 = E41 + (zm + x2) * E42 + (z2 + 2.0 * zv + x2s + zm * x2) * E43 +
+                                             (z2 * zm + x2c + x2 * z2 + zm * x2s + 3.0 * zv * x2 + 5.0 * zv * zm) * E4;
+                        const double P2 = a01.x * b01.y * (0.5 * E4A41 * (b67.x - a67.x) + E4A42 * a67.y - E4A43 * b67.y);
+                        const double d2 = muD * muD;
+                        const double E5A51 = E50 - muD * E51 + c[7] * E52 - c[8] * E53 + c[9] * E4;
+                        const double E5A52 = E51 - (muD + x1) * E52 + (d2 + 2.0 * zv + x1s + muD * x1) * E53 -
+                                             (d2 * muD + x1c + x1 * d2 + muD * x1s + 3.0 * zv * x1 + 5.0 * zv * muD) * E4;
+                        const double P3 = c[13] * a01.y * b01.y * (a45.x * E5A51 + a45.y * E5A52);
+                        Jd = P1 + P2 + P3;
+                    }
+                    Jv[e][t] *= Jd;
+                }
+            }
+            __syncthreads();   // the tables are rewritten for the next dimension
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            if (!valid[e]) continue;
+#pragma unroll
+            for (int t = 0; t < MT; ++t) {
+                const double J = Jv[e][t] * gzI[t * PT + lis[e]] * gzJ[t * PT + ljs[e]];
+                accq[t] += wq[e] * J;
+                acct[t] += wr[e] * J;
+            }
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < MT; ++t) {
+        const double s1 = block_sum<256>(accq[t], sred);
+        const double s2 = block_sum<256>(acct[t], sred);
+        if (tid == 0 && t0 + t < a.M) {
+            part[((int64_t)blockIdx.y * a.M + t0 + t) * 2 + 0] = s1;
+            part[((int64_t)blockIdx.y * a.M + t0 + t) * 2 + 1] = s2;
+        }
+    }
+}
+
+static size_t linkgp_matern_tab_smem(int Dw) {
+    return sizeof(double) * (size_t)(MT * Dw * 16 + 2 * MT * PT * 8 + 2 * PT * (Dw + 1) + 2 * MT * PT + 2 * PT + 8);
+}
+
+static int g_linkgp_matern_tab = 1;   // dgpb_tune("linkgp_matern_tab", 0): direct closed form per pair
+int linkgp_set_matern_tab(int on) {
+    g_linkgp_matern_tab = on != 0;
+    return DGPB_OK;
+}
+
 // v_t = | a'Ja - m_t^2 + scale (1 + nugget - tr(R^-1 J)) |     (functions.py:429)
 __global__ void linkgp_finish_kernel(const double* __restrict__ part, int PC, int M, const double* __restrict__ mean,
                                      double scale, double nugget, double* __restrict__ var) {
@@ -900,6 +1122,24 @@ int dgpb_linkgp_predict(dgpb_ws* ws, const double* m_in, const double* v_in, con
             else if (Dw <= 24) rc = launch_sexp_pairs<24, 1>(a, grid, PC, (double*)part, st);
             else rc = launch_sexp_pairs<32, 1>(a, grid, PC, (double*)part, st);
             DGPB_TRY(rc);
+        } else if (g_linkgp_matern_tab) {
+            const int ntt3 = (int)cdiv(Mc, MT);
+            int PC3 = (int)cdiv(148 * 4, ntt3);
+            PC3 = std::max(1, std::min(PC3, ntiles));
+            DGPB_TRY(ws->reserve(SLOT_PART, sizeof(double) * (size_t)PC3 * Mc * 2, &part));
+            static bool cfg = false;
+            if (!cfg) {
+                DGPB_CUDA_TRY(cudaFuncSetAttribute(linkgp_matern_tab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                   (int)linkgp_matern_tab_smem(kMaxDim)));
+                cfg = true;
+            }
+            linkgp_matern_tab_kernel<<<dim3((unsigned)ntt3, (unsigned)PC3), 256, linkgp_matern_tab_smem((int)Dw), st>>>(
+                a, PC3, (double*)part);
+            DGPB_LAUNCHED();
+            linkgp_finish_kernel<<<(unsigned)cdiv(Mc, 256), 256, 0, st>>>((double*)part, PC3, Mc, mean + m0, scale,
+                                                                         nugget, var + m0);
+            DGPB_LAUNCHED();
+            continue;
         } else {
             linkgp_matern_pairs_kernel<<<grid, 256, 0, st>>>(a, PC, (double*)part);
             DGPB_LAUNCHED();

@@ -242,7 +242,8 @@ int dgpb_probe_factorize(dgpb_ws* ws, int64_t n, int B, int aug, int reps, doubl
  * 128, 256, 512), and of the ESS loop: "ess_batch" (matrices per speculative wave; <= 1 = one proposal at a time),
  * and of the neighbour search: "knn_mma" (1 = tensor-core screen + exact ranking, 0 = scalar exact kernel),
  * and of the Vecchia block kernels: "vecchia_small" (1 = register-resident kernel for blocks of <= 32 points),
- * and of link_gp: "linkgp_mma" (1 = squared-exponential exponents on the FP64 tensor path) */
+ * and of link_gp: "linkgp_mma" (1 = squared-exponential exponents on the FP64 tensor path), "linkgp_matern_tab" (1 = Matern-2.5 J
+ * integrals from per-point tables of their transcendental factors) */
 int dgpb_tune(const char* key, int value);
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 int64_t dgpb_launch_count(void);

@@ -278,6 +278,47 @@ def test_linkgp_tensor_core_kernel_equals_vector_kernel():
         assert np.max(np.abs(v1 - v0)) <= 1e-9 * max(1.0, np.max(np.abs(v0))), (n, M, Dw, Dz, np.max(np.abs(v1 - v0)))
 
 
+def test_linkgp_matern_tabulated_kernel_equals_direct_kernel():
+    """Matern-2.5 link_gp: the J integrals assembled from per-point tables of their transcendental factors equal
+    the direct per-pair closed form (and the oracle), including zero input variances, connected global inputs,
+    coincident coordinates and ragged sizes."""
+    from dgp_b200 import _lib as L
+    import dgp_b200 as D
+    from oracle import dgp_oracle as O
+
+    lib = L.load()
+    rng = np.random.default_rng(43)
+    for n, M, Dw, Dz, ard in ((90, 21, 2, 0, False), (200, 33, 5, 0, True), (130, 9, 3, 2, True), (33, 70, 1, 0, False)):
+        D_all = Dw + Dz
+        length = rng.uniform(0.5, 1.5, D_all if ard else 1)
+        k = D.kernel(length=length.copy(), name="matern2.5", nugget=1e-3, scale=1.4,
+                     connect=np.arange(Dz) if Dz else None)
+        k.input = rng.uniform(0, 1, (n, Dw))
+        k.input[1] = k.input[0]          # coincident training coordinates (x1 == x2 off the diagonal)
+        k.input_dim = np.arange(Dw)
+        if Dz:
+            k.global_input = rng.uniform(0, 1, (n, Dz))
+        k.output = np.sin(k.input.sum(1, keepdims=True) * 2)
+        k.D = D_all
+        k.compute_stats()
+        m_in, v_in = rng.uniform(-0.2, 1.2, (M, Dw)), rng.uniform(1e-4, 0.05, (M, Dw))
+        v_in[0, 0] = 0.0                  # deterministic input in one dimension
+        z = rng.uniform(0, 1, (M, Dz)) if Dz else None
+        L.check(lib.dgpb_tune(b"linkgp_matern_tab", 0))
+        try:
+            m0, v0 = k.linkgp_prediction(m_in, v_in, z)
+        finally:
+            L.check(lib.dgpb_tune(b"linkgp_matern_tab", 1))
+        m1, v1 = k.linkgp_prediction(m_in, v_in, z)
+        assert relerr(m1, m0, 1e-9) <= 1e-10, (n, M, Dw, Dz)
+        assert np.max(np.abs(v1 - v0)) <= 1e-9 * max(1.0, np.max(np.abs(v0))), (n, M, Dw, Dz, np.max(np.abs(v1 - v0)))
+        if Dz == 0 and n <= 100:
+            lfull = np.full(Dw, length[0]) if len(length) == 1 else length
+            m2, v2 = O.link_gp(m_in, v_in, None, k.input, None, k.Rinv, k.Rinv_y, None, None, 1.4, lfull, 1e-3, "matern2.5")
+            # two coincident training rows make R^-1 ~ 1/nugget large: the variance is a difference of O(1e3) terms
+            assert relerr(m1, m2, 1e-3) <= 1e-9 and np.max(np.abs(v1 - v2)) <= 1e-12 * np.max(np.abs(k.Rinv)) * n
+
+
 def test_linkgp_wide_inputs_vs_oracle():
     """Dw beyond the register-tiled template sizes and n not a multiple of the pair tile."""
     import dgp_b200 as D
