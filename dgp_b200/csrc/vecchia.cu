@@ -211,10 +211,23 @@ __global__ void __launch_bounds__(1024) colsum_kernel(const double* __restrict__
 // sparse forward solve  x_i = (z_i - sum_{j>=1} L[i,j] x[NN[i,j]]) / L[i,0]     (forward_solve_sp)
 // Dependency-driven: one warp per row, rows claimed in increasing order through a ticket so every
 // dependency (always a smaller row index) is owned by a warp that is already running or finished.
+// The solution vector itself is the ready flag: it is pre-filled with a sentinel NaN payload that arithmetic
+// cannot produce, a waiter polls the 8-byte word with volatile loads (and a short nanosleep back-off) and gets
+// readiness and value in one transaction -- no atomics, no fences.  (The first version polled a separate flag
+// array with atomicAdd(.., 0): ~300k spinning atomics saturated the L2 atomic units, 8.8 ms per solve at
+// n = 100k, two thirds of a Vecchia I-step.)
 // ------------------------------------------------------------------------------------------------
-__global__ void sp_solve_kernel(const double* __restrict__ L, const int64_t* __restrict__ NN, int64_t n, int m1,
-                                double inv_sqrt_scale, const double* __restrict__ z, double* x, int* ready,
-                                unsigned int* ticket) {
+constexpr unsigned long long kSpSentinel = 0x7ff8dead0000beefULL;
+
+__global__ void sp_fill_kernel(unsigned long long* __restrict__ x, int64_t n, unsigned int* ticket) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) x[i] = kSpSentinel;
+    if (i == 0) *ticket = 0u;
+}
+
+__global__ void __launch_bounds__(256) sp_solve_kernel(const double* __restrict__ L, const int64_t* __restrict__ NN, int64_t n,
+                                                       int m1, double inv_sqrt_scale, const double* __restrict__ z,
+                                                       double* x, unsigned int* ticket) {
     __shared__ unsigned int s_blk;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, W = blockDim.x >> 5;
     if (threadIdx.x == 0) s_blk = atomicAdd(ticket, 1u);
@@ -224,21 +237,26 @@ __global__ void sp_solve_kernel(const double* __restrict__ L, const int64_t* __r
     const int kmax = (int)min((int64_t)m1, i + 1);
     double s = 0.0;
     for (int j = 1 + lane; j < kmax; j += 32) {
-        int64_t dep = NN[i * m1 + j];
+        const int64_t dep = NN[i * m1 + j];
+        const double lij = L[i * m1 + j] * inv_sqrt_scale;
+        const volatile unsigned long long* px = reinterpret_cast<const volatile unsigned long long*>(x + dep);
         // bounded spin: a dependency that never arrives (corrupt NNarray) poisons the result instead of
         // hanging the device
-        long long spins = 0;
-        while (atomicAdd(&ready[dep], 0) == 0 && ++spins < (1LL << 28)) {
+        unsigned long long bits = *px;
+        int spins = 0;
+        while (bits == kSpSentinel && ++spins < (1 << 22)) {
+            __nanosleep(40);
+            bits = *px;
         }
-        __threadfence();
-        double xd = spins < (1LL << 28) ? ((volatile double*)x)[dep] : NAN;
-        s += (L[i * m1 + j] * inv_sqrt_scale) * xd;
+        const double xd = bits == kSpSentinel ? NAN : __longlong_as_double((long long)bits);
+        s += lij * xd;
     }
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if (lane == 0) {
-        x[i] = (z[i] - s) / (L[i * m1] * inv_sqrt_scale);
-        __threadfence();
-        atomicExch(&ready[i], 1);
+        double r = (z[i] - s) / (L[i * m1] * inv_sqrt_scale);
+        unsigned long long rb = (unsigned long long)__double_as_longlong(r);
+        if (rb == kSpSentinel) rb = 0x7ff8000000000000ULL;   // cannot happen for computed values; keep waiters safe
+        *reinterpret_cast<volatile unsigned long long*>(x + i) = rb;
     }
 }
 
@@ -676,14 +694,13 @@ int vecchia_mvn_draw_device(Workspace* ws, const VKern& vk, const double* X, con
                             double scale, double nugget, const double* z, double* out, cudaStream_t st) {
     void *Lm, *flags;
     DGPB_TRY(ws->reserve(SLOT_VL, sizeof(double) * (size_t)n * m1, &Lm));
-    DGPB_TRY(ws->reserve(SLOT_VFLAG, sizeof(int) * ((size_t)n + 8), &flags));
+    DGPB_TRY(ws->reserve(SLOT_VFLAG, sizeof(int) * 8, &flags));
     DGPB_TRY(train_launch(vk, X, nullptr, NN, n, m1, nugget, nullptr, 2, 0, 0, nullptr, (double*)Lm, st));
-    DGPB_CUDA_TRY(cudaMemsetAsync(flags, 0, sizeof(int) * ((size_t)n + 8), st));
-    int* ready = (int*)flags + 8;
     unsigned int* ticket = (unsigned int*)flags;
+    sp_fill_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(reinterpret_cast<unsigned long long*>(out), n, ticket);
+    DGPB_LAUNCHED();
     const int W = 8;
-    sp_solve_kernel<<<(unsigned)cdiv(n, W), W * 32, 0, st>>>((double*)Lm, NN, n, (int)m1, 1.0 / sqrt(scale), z, out, ready,
-                                                            ticket);
+    sp_solve_kernel<<<(unsigned)cdiv(n, W), W * 32, 0, st>>>((double*)Lm, NN, n, (int)m1, 1.0 / sqrt(scale), z, out, ticket);
     DGPB_LAUNCHED();
     return DGPB_OK;
 }

@@ -100,6 +100,7 @@ class kernel:
         state['Rinv_y'] = _as_numpy(state.pop('_Rinv_y'))
         state.pop('_dcache', None)
         state.pop('_batcher', None)
+        state.pop('_vcache', None)
         return state
 
     def __setstate__(self, state):
@@ -291,10 +292,24 @@ class kernel:
         self._check_supported()
         self.update(x)
         from .vecchia import vecchia_nllik
-        X = self._X()
-        neg_llik, neg_St, scale = vecchia_nllik(X[self.ord], self.output[self.ord], self.NNarray, self.scale[0],
-                                                self.length, self.nugget[0], None, self.name, self.scale_est,
-                                                self.nugget_est)
+        vc = getattr(self, '_vcache', None)
+        if vc is not None and vc[0] is self.ord and vc[1] is self.NNarray:
+            # ordered inputs / outputs / neighbour array already on the device (uploaded once per `maximise`)
+            Xd, yd, NNd = vc[2]
+            larr, lptr = L.length_host(self.length)
+            P = len(larr) + (1 if self.nugget_est else 0)
+            out = L.host_doubles(P + 2)
+            L.check(L.load().dgpb_vecchia_nllik(L.ptr(Xd), L.ptr(yd), L.ptr(NNd), Xd.shape[0], Xd.shape[1],
+                                                NNd.shape[1], lptr, len(larr), float(self.scale[0]),
+                                                float(self.nugget[0]), None, L.KIND[self.name],
+                                                int(bool(self.scale_est)), int(bool(self.nugget_est)), out,
+                                                L.stream()))
+            neg_llik, neg_St, scale = out[0], np.array(out[2:2 + P]), out[1]
+        else:
+            X = self._X()
+            neg_llik, neg_St, scale = vecchia_nllik(X[self.ord], self.output[self.ord], self.NNarray, self.scale[0],
+                                                    self.length, self.nugget[0], None, self.name, self.scale_est,
+                                                    self.nugget_est)
         self.scale = np.array([scale])
         neg_llik = np.array([neg_llik])
         if self.prior_name is not None:
@@ -347,10 +362,19 @@ class kernel:
         if bounded:
             kwargs['bounds'] = Bounds(lb, ub)
         self._dcache = None if self.vecch else self._upload()
+        self._vcache = None
+        if self.vecch:
+            # Vecchia: the ordered inputs, outputs and neighbour array go to the device once for the whole
+            # optimisation (a re-ordering by the callback replaces `ord` / `NNarray`, which invalidates the cache)
+            X = self._X()
+            self._vcache = (self.ord, self.NNarray,
+                            (L.to_dev(X[self.ord]), L.to_dev(np.ascontiguousarray(self.output[self.ord, 0])),
+                             L.to_dev(self.NNarray, np.int64)))
         try:
             minimize(fun, x0, method=method, jac=True, options=budget, **kwargs)
         finally:
             self._dcache = None
+            self._vcache = None
         if reorder:
             self.iter_count = 0
         self.add_to_path()
