@@ -5,7 +5,8 @@ sliding-window factorisation; `predict(x, method='mean_var')` pushes the test in
 the device -- first layer `gp`, deeper layers `link_gp` -- keeps the per-imputation moments in HBM and
 aggregates them with one kernel.  With a process group (one process per GPU) the test points are sharded
 and the moments all-gathered over NCCL (`dgp_b200.parallel`).
-Out of scope: LOO, ALM/MICE/VIGF, nllik, ppredict.
+`loo` re-uses the Vecchia prediction kernels with every point conditioned on the others.
+Out of scope: ALM/MICE/VIGF, nllik, process pools.
 """
 from __future__ import annotations
 
@@ -67,6 +68,54 @@ class emulator:
                 for kernel in layer:
                     kernel.vecch = False
                     kernel.compute_stats()
+
+    # ---- leave-one-out ----------------------------------------------------------------------------------
+    def change_vecch_state(self):
+        """Context of emulation.py:91-107: every GP node predicts in Vecchia form with itself removed from the
+        conditioning set."""
+        import contextlib
+
+        @contextlib.contextmanager
+        def ctx():
+            for one in self.all_layer_set:
+                for layer in one:
+                    for kernel in layer:
+                        if not self.vecch:
+                            kernel.vecch = True
+                        kernel.loo_state = True
+            try:
+                yield
+            finally:
+                for one in self.all_layer_set:
+                    for layer in one:
+                        for kernel in layer:
+                            if not self.vecch:
+                                kernel.vecch = False
+                            kernel.loo_state = False
+
+        return ctx()
+
+    def loo(self, X, method=None, sample_size=50, m=30):
+        """Leave-one-out cross-validation of the DGP emulator (emulation.py:109-144): predictions at the training
+        inputs with each GP node conditioned on the m nearest OTHER training points (Vecchia emulators) or on all
+        other points (dense emulators).  The conditioning blocks run on the Vecchia kernels, which hold at most 63
+        conditioning points: dense emulators with more than 63 training points are not supported here."""
+        if method is None:
+            method = 'mean_var'
+        n = len(self.all_layer[0][0].input)
+        if len(X) != n:
+            raise NotImplementedError("dgp_b200: replicated training inputs are outside the SI hot path")
+        m_pred = m + 1 if self.vecch else X.shape[0]
+        if m_pred - 1 > 63:
+            raise NotImplementedError("dgp_b200: leave-one-out of a dense emulator conditions every point on all "
+                                      "others; the block kernels hold at most 63 conditioning points "
+                                      "(convert with to_vecchia() for larger designs)")
+        with self.change_vecch_state():
+            return self.predict(X, method=method, sample_size=sample_size, m=m_pred)
+
+    def ploo(self, X, method=None, sample_size=50, m=30, core_num=None):
+        """emulation.py:146-168: the process pool is replaced by the GPU."""
+        return self.loo(X, method, sample_size, m)
 
     # ---- prediction -------------------------------------------------------------------------------------
     def _predict_one_imputation(self, layers, xd, m, collect_layers):

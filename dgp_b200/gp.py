@@ -1,6 +1,6 @@
 """`gp` -- single Gaussian-process emulator (dgpsi/gp.py:12-60, 211-222, 412-453), GPU-backed through
 `kernel`.  In scope as a member of linked systems: construction, `train`,
-`predict`, `export`; LOO / design metrics are not."""
+`predict`, `export`, `loo`; design metrics are not."""
 from __future__ import annotations
 
 import copy
@@ -101,4 +101,31 @@ class gp:
             return mu.reshape(-1, 1), sigma2.reshape(-1, 1)
         if method == 'sampling':
             return np.random.normal(mu, np.sqrt(sigma2), size=(sample_size, len(x))).T
+        raise Exception("method must be 'mean_var' or 'sampling'")
+
+    def loo(self, method='mean_var', sample_size=50, m=30):
+        """Leave-one-out cross-validation of the GP (gp.py:326-371).  Dense: the closed form from the diagonal of
+        R^-1 and R^-1 y already on the device; Vecchia: `gp_vecch` of every training point conditioned on its m
+        nearest OTHER training points (loo_gp_vecch, vecchia.py:657-673)."""
+        from . import _lib as L
+        k = self.kernel
+        if self.vecch:
+            k.pred_m, k.loo_state = m + 1, True
+            try:
+                z = self.X[:, k.connect] if k.connect is not None else None
+                mu, sigma2 = k.gp_prediction(x=self.X[:, k.input_dim], z=z)
+            finally:
+                k.loo_state = False
+            mu, sigma2 = mu.reshape(-1, 1), sigma2.reshape(-1, 1)
+        else:
+            Rinv, Rinv_y = k._stats_dev()
+            torch = L.torch_mod()
+            s2 = 1.0 / torch.diagonal(Rinv)
+            sigma2 = L.to_host(s2).reshape(-1, 1)
+            mu = self.Y - L.to_host(Rinv_y).reshape(-1, 1) * sigma2
+            sigma2 = k.scale * sigma2
+        if method == 'mean_var':
+            return mu, sigma2
+        if method == 'sampling':
+            return np.random.normal(mu.flatten(), np.sqrt(sigma2.flatten()), size=(sample_size, len(mu))).T
         raise Exception("method must be 'mean_var' or 'sampling'")

@@ -613,6 +613,21 @@ def gp_vecch(x, w, NNarray, y, scale, length, nugget, nugget_diag, name):
     return mo, vo
 
 
+def loo_gp_dense(Y, Rinv, Rinv_y, scale):
+    """Closed-form leave-one-out moments of a dense GP -- gp.py:353-359."""
+    s2 = (1.0 / np.diag(Rinv)).reshape(-1, 1)
+    return Y - Rinv_y.reshape(-1, 1) * s2, scale * s2
+
+
+def loo_gp_vecch(X, Y, m, scale, length, nugget, name):
+    """gp.loo in Vecchia mode -- gp.py:343-352 + loo_gp_vecch vecchia.py:657-673: every training point predicted
+    from its m nearest OTHER training points (the first neighbour returned by the search is the point itself)."""
+    Xs = _scaled(X, length)
+    NN = knn(Xs, Xs, m + 1)[:, 1:]
+    mu, var = gp_vecch(X, X, NN, Y, scale, length, nugget, np.ones(len(X)), name)
+    return mu.reshape(-1, 1), var.reshape(-1, 1)
+
+
 def link_gp_vecch(m, v, z, w1, global_w1, NNarray, y, scale, length, nugget, nugget_diag, name):
     """vecchia.py:758-796 with `IJ_nb` (vecchia.py:838-907)."""
     M = m.shape[0]

@@ -46,3 +46,8 @@ def golden_ess():
 @pytest.fixture(scope="session")
 def golden_e2e():
     return load_golden("e2e")
+
+
+@pytest.fixture(scope="session")
+def golden_loo():
+    return load_golden("loo")

@@ -347,7 +347,44 @@ def gen_e2e():
     save("e2e", **out)
 
 
+# ---------------------------------------------------------------- leave-one-out
+def gen_loo():
+    out = {}
+    rng = np.random.default_rng(SEED + 9)
+    np.random.seed(SEED + 9)
+    dgpsi.nb_seed(SEED + 9)
+    n, d = 50, 2
+    X = rng.uniform(0, 1, size=(n, d))
+    Y = (np.sin(4 * X[:, 0]) + X[:, 1] ** 2 + 0.05 * rng.standard_normal(n)).reshape(-1, 1)
+    out["gp_X"], out["gp_Y"] = X, Y
+    for tag, name in (("se", "sexp"), ("ma", "matern2.5")):
+        length = np.array([0.7, 0.9])
+        g = dgpsi.gp(X, Y, kernel(length=length.copy(), scale=1.3, nugget=1e-4, name=name))
+        mu, s2 = g.loo()
+        out[f"gp_{tag}_dense_mu"], out[f"gp_{tag}_dense_var"] = mu, s2
+        gv = dgpsi.gp(X, Y, kernel(length=length.copy(), scale=1.3, nugget=1e-4, name=name), vecchia=True, m=8)
+        mu, s2 = gv.loo(m=6)
+        out[f"gp_{tag}_vecch_mu"], out[f"gp_{tag}_vecch_var"] = mu, s2
+    # DGP emulators with frozen imputations: dense (LOO conditions on all other points) and Vecchia
+    n = 30
+    Xd = rng.uniform(0, 1, size=(n, d))
+    Yd = (np.sin(2 * np.pi * Xd[:, 0] * Xd[:, 1]) + (Xd[:, 1] - 0.5) ** 2).reshape(-1, 1)
+    out["emu_X"], out["emu_Y"] = Xd, Yd
+    for tag, vec in (("dense", False), ("vecch", True)):
+        l1 = [kernel(length=np.array([1.0]), name="matern2.5") for _ in range(d)]
+        l2 = [kernel(length=np.array([1.0]), name="matern2.5", scale_est=True, connect=np.arange(d))]
+        model = dgpsi.dgp(Xd, Yd, dgpsi.combine(l1, l2), vecchia=vec, m=6)
+        model.train(N=8, disable=True)
+        emu = dgpsi.emulator(model.estimate(), N=2)
+        mu, s2 = emu.loo(Xd, m=5)
+        out[f"emu_{tag}_mu"], out[f"emu_{tag}_var"] = mu, s2
+        out[f"emu_{tag}_nimp"] = np.array(len(emu.all_layer_set))
+        for s, al in enumerate(emu.all_layer_set):
+            snapshot(al, f"emu_{tag}_S{s}_", out)
+    save("loo", **out)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["dense", "jd", "vecchia", "ess", "e2e"]
+    which = sys.argv[1:] or ["dense", "jd", "vecchia", "ess", "e2e", "loo"]
     for w in which:
-        {"dense": gen_dense, "jd": gen_jd, "vecchia": gen_vecchia, "ess": gen_ess, "e2e": gen_e2e}[w]()
+        {"dense": gen_dense, "jd": gen_jd, "vecchia": gen_vecchia, "ess": gen_ess, "e2e": gen_e2e, "loo": gen_loo}[w]()

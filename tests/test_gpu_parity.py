@@ -679,6 +679,52 @@ def test_batched_m_step_equals_one_node_at_a_time(monkeypatch):
             assert np.array_equal(ka.nugget, kb.nugget)
 
 
+def test_leave_one_out_vs_reference(golden_loo):
+    """gp.loo (dense closed form and Vecchia) and emulator.loo (dense emulator conditioning on all other points,
+    Vecchia emulator on the m nearest others) against the reference's values on its own imputed states."""
+    import dgp_b200 as D
+
+    g = golden_loo
+    X, Y = g["gp_X"], g["gp_Y"]
+    for tag, name in (("se", "sexp"), ("ma", "matern2.5")):
+        length = np.array([0.7, 0.9])
+        gd = D.gp(X, Y, D.kernel(length=length.copy(), scale=1.3, nugget=1e-4, name=name))
+        mu, s2 = gd.loo()
+        assert mu.shape == (len(X), 1) and s2.shape == (len(X), 1)
+        assert relerr(mu, g[f"gp_{tag}_dense_mu"], 1e-2) <= 1e-7, tag        # nugget 1e-4: cond(K) ~ 1e6
+        assert relerr(s2, g[f"gp_{tag}_dense_var"], 1e-300) <= 1e-7, tag
+        gv = D.gp(X, Y, D.kernel(length=length.copy(), scale=1.3, nugget=1e-4, name=name), vecchia=True, m=8)
+        mu, s2 = gv.loo(m=6)
+        assert relerr(mu, g[f"gp_{tag}_vecch_mu"], 1e-3) <= 1e-8, tag
+        assert relerr(s2, g[f"gp_{tag}_vecch_var"], 1e-300) <= 1e-8, tag
+        samples = gv.loo(method="sampling", sample_size=7, m=6)
+        assert samples.shape == (len(X), 7) and np.all(np.isfinite(samples))
+    Xe = g["emu_X"]
+    for tag, vec in (("dense", False), ("vecch", True)):
+        emu = D.emulator.__new__(D.emulator)
+        emu.all_layer_set = []
+        for s in range(int(g[f"emu_{tag}_nimp"])):
+            layers = _snapshot_layers(g, f"emu_{tag}_S{s}_", lambda l, k: "matern2.5")
+            for layer in layers:
+                for node in layer:
+                    node.vecch = vec
+                    if not vec:
+                        node.compute_stats()
+            emu.all_layer_set.append(layers)
+        emu.all_layer, emu.n_layer, emu.vecch = emu.all_layer_set[0], 2, vec
+        mu, s2 = emu.loo(Xe, m=5)
+        ref_mu, ref_var = g[f"emu_{tag}_mu"], g[f"emu_{tag}_var"]
+        assert mu.shape == ref_mu.shape
+        assert np.max(np.abs(mu - ref_mu)) <= 1e-7 * max(1.0, np.max(np.abs(ref_mu))), tag
+        assert np.max(np.abs(s2 - ref_var)) <= 1e-7 * max(1.0, np.max(np.abs(ref_var))), tag
+        for layers in emu.all_layer_set:   # the context restores the nodes
+            assert all(node.vecch == vec and not node.loo_state for layer in layers for node in layer)
+    big = D.emulator.__new__(D.emulator)
+    big.vecch, big.all_layer = False, [[type("K", (), {"input": np.zeros((100, 1))})()]]
+    with pytest.raises(NotImplementedError):
+        big.loo(np.zeros((100, 1)))
+
+
 def test_public_api_train_and_predict_smoke():
     """The user-facing path runs: dgp(X,Y).train -> estimate -> emulator -> predict; the fit is sane."""
     import dgp_b200 as D

@@ -230,3 +230,16 @@ def test_ess_replay_identical_decisions(golden_ess):
                 node.maximise()
                 got = np.concatenate(([node.scale], node.length, [node.nugget]))
                 assert np.allclose(got, g[p + f"mstep_L{l}K{k}"], rtol=2e-4), (ci, l, k)
+
+
+def test_leave_one_out(golden_loo):
+    """gp.loo of the reference (dense closed form, Vecchia conditioning on the m nearest other points)."""
+    g = golden_loo
+    X, Y = g["gp_X"], g["gp_Y"]
+    length = np.array([0.7, 0.9])
+    for tag, name in (("se", "sexp"), ("ma", "matern2.5")):
+        Rinv, Rinv_y = O.compute_stats(X, Y, length, 1e-4, name)
+        mu, s2 = O.loo_gp_dense(Y, Rinv, Rinv_y, 1.3)
+        assert relerr(mu, g[f"gp_{tag}_dense_mu"], 1e-2) <= 1e-7 and relerr(s2, g[f"gp_{tag}_dense_var"], 1e-300) <= 1e-7
+        mu, s2 = O.loo_gp_vecch(X, Y, 6, 1.3, length, 1e-4, name)
+        assert relerr(mu, g[f"gp_{tag}_vecch_mu"], 1e-3) <= 1e-9 and relerr(s2, g[f"gp_{tag}_vecch_var"], 1e-300) <= 1e-9
