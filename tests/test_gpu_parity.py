@@ -745,6 +745,39 @@ def test_public_api_train_and_predict_smoke():
         emu.predict(np.linspace(0, 1, 5))
 
 
+def test_vecchia_dgp_public_api_roundtrip(tmp_path):
+    """Vecchia DGP through the public API (config-4 shape, small): train (ordered kNN, sparse prior draws, block
+    likelihoods, Vecchia M-step), emulator, predict, sampling, LOO, write/read; predictions survive pickling."""
+    import dgp_b200 as D
+
+    rng = np.random.default_rng(12)
+    np.random.seed(12)
+    D.nb_seed(12)
+    n, d = 400, 3
+    X = rng.uniform(0, 1, (n, d))
+    f = lambda x: np.sin(2 * np.pi * x[:, 0] * x[:, 1]) + x[:, 2] ** 2
+    Y = (f(X) + 0.02 * rng.standard_normal(n)).reshape(-1, 1)
+    l1 = [D.kernel(length=np.array([1.0]), name="sexp") for _ in range(d)]
+    l2 = [D.kernel(length=np.array([1.0]), name="sexp", scale_est=True, nugget_est=True, nugget=1e-2,
+                   connect=np.arange(d))]
+    model = D.dgp(X, Y, D.combine(l1, l2), vecchia=True, m=12)
+    model.train(N=4, disable=True)
+    assert model.N == 4 and model.timing["i_step"] > 0 and model.timing["m_step"] > 0
+    emu = D.emulator(model.estimate(burnin=0), N=2)
+    xt = rng.uniform(0, 1, (257, d))
+    mu, var = emu.predict(xt, m=12)
+    assert mu.shape == (257, 1) and np.all(np.isfinite(mu)) and np.all(var > 0)
+    assert np.sqrt(np.mean((mu[:, 0] - f(xt)) ** 2)) < 0.5
+    draws = emu.predict(xt[:9], method="sampling", sample_size=5, m=12)
+    assert len(draws) == 1 and draws[0].shape == (9, 10)
+    lmu, lvar = emu.loo(X, m=10)
+    assert lmu.shape == (n, 1) and np.all(np.isfinite(lmu)) and np.all(lvar > 0)
+    D.write(emu, str(tmp_path / "emu"))
+    emu2 = D.read(str(tmp_path / "emu"))
+    mu2, var2 = emu2.predict(xt, m=12)
+    assert np.array_equal(mu, mu2) and np.array_equal(var, var2)
+
+
 def test_property_checks_at_baseline_scale():
     """Size-independent properties at a BASELINE-sized node (n=2000, D=10): the factor reproduces K, the
     inverse is an inverse, log-likelihood agrees with an independent FP64 computation (torch/cuSOLVER used
