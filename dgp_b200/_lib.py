@@ -77,6 +77,8 @@ _PROTOS = {
                                              ctypes.c_int, c_vp, c_vp, c_vp]),
     "dgpb_gp_vecch": (ctypes.c_int, [c_vp, c_i64, c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_i64, c_dbl, c_dbl,
                                      c_vp, ctypes.c_int, c_vp, c_vp, c_vp]),
+    "dgpb_gp_vecch_multi": (ctypes.c_int, [c_vp, c_i64, c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, ctypes.c_int, c_vp, c_vp,
+                                           c_vp, c_vp, c_vp, c_vp]),
     "dgpb_linkgp_vecch": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_vp,
                                          c_i64, c_vp, c_i64, c_dbl, c_dbl, c_vp, ctypes.c_int, c_vp, c_vp, c_vp]),
     "dgpb_gp_predict": (ctypes.c_int, [c_vp, c_vp, c_i64, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_i64, c_dbl, c_dbl,

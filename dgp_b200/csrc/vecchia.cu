@@ -606,6 +606,94 @@ static int small_launch(const VKern& vk, const VSmallArgs& a, cudaStream_t st) {
     return DGPB_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// gp_vecch for SEVERAL squared-exponential nodes that share inputs and neighbours and have ONE length-scale each
+// (the first layer of a Vecchia DGP: every node sees the design matrix, vecchia.py:635-654 is called per node by
+// kernel_class.py:586-625).  The block's raw squared distances are formed once per test point; each node then
+// only exponentiates them with its own length-scale, factors and solves with its own outputs.  Same
+// lane-per-row scheme as vecchia_small_kernel.
+// ------------------------------------------------------------------------------------------------
+constexpr int kMultiMax = 32;   // nodes per launch
+struct VMultiArgs {
+    int64_t M, n;
+    int cols, D, B;
+    const double* xq;     // M x D
+    const double* X;      // n x D
+    const double* Y;      // B x n  (row b = outputs of node b)
+    const int64_t* NN;    // M x cols
+    double inv_l2[kMultiMax], scale[kMultiMax], nugget[kMultiMax];
+    double* mean;         // B x M
+    double* var;          // B x M
+};
+
+__global__ void __launch_bounds__(256, 2) vecchia_multi_kernel(VMultiArgs a) {
+    extern __shared__ double smem[];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, W = blockDim.x >> 5;
+    const int64_t t = (int64_t)blockIdx.x * W + w;
+    if (t >= a.M) return;
+    const int D = a.D, Dp = D | 1;
+    double* xl = smem + (size_t)w * (32 * Dp + 32 * 33);
+    double* ds = xl + 32 * Dp;      // raw squared distances of the block, row stride 33
+    int nv = 0;
+    for (int c = lane; c < a.cols; c += 32) nv += a.NN[t * a.cols + c] >= 0;
+    for (int o = 16; o > 0; o >>= 1) nv += __shfl_xor_sync(0xffffffffu, nv, o);
+    const int b = nv + 1;
+    const int64_t src = lane < nv ? a.NN[t * a.cols + lane] : -1;
+    for (int p0 = 0; p0 < b * D; p0 += 32) {
+        const int p = p0 + lane;
+        const int r = min(p / D, b - 1), k = p - (p / D) * D;
+        const int64_t sr = __shfl_sync(0xffffffffu, src, r);
+        if (p < b * D) xl[r * Dp + k] = sr >= 0 ? a.X[sr * D + k] : a.xq[t * D + k];
+    }
+    __syncwarp();
+    {
+        const double* xi = xl + (lane < b ? lane : 0) * Dp;
+        for (int k = 0; k < b; ++k) {
+            const double* xk = xl + k * Dp;
+            double dist = 0.0;
+            for (int d = 0; d < D; ++d) {
+                const double df = xi[d] - xk[d];
+                dist += df * df;
+            }
+            ds[lane * 33 + k] = dist;
+        }
+    }
+    __syncwarp();
+    for (int nb = 0; nb < a.B; ++nb) {
+        const double il2 = a.inv_l2[nb], nug = a.nugget[nb];
+        double yacc = src >= 0 ? a.Y[(int64_t)nb * a.n + src] : 0.0;
+        double arow[32];
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+            double v = 0.0;
+            if (k < b) v = (k == lane) ? 1.0 + nug : exp(-ds[lane * 33 + k] * il2);
+            arow[k] = v;
+        }
+        double lll = 1.0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            if (j < b) {
+                const double pj = __shfl_sync(0xffffffffu, arow[j], j);
+                const double rs = rsqrt(pj);
+                const double lij = arow[j] * rs;
+                arow[j] = lij;
+                const double wj = __shfl_sync(0xffffffffu, yacc, j) * rs;
+                if (lane > j) yacc = fma(-lij, wj, yacc);
+                else if (lane == j) yacc = wj;
+                if (j == b - 1) lll = __shfl_sync(0xffffffffu, lij, j);
+#pragma unroll
+                for (int k = j + 1; k < 32; ++k)
+                    if (k < b) arow[k] = fma(-lij, __shfl_sync(0xffffffffu, lij, k), arow[k]);
+            }
+        }
+        const double wl = __shfl_sync(0xffffffffu, yacc, b - 1);
+        if (lane == 0) {
+            a.mean[(int64_t)nb * a.M + t] = -wl * lll;
+            a.var[(int64_t)nb * a.M + t] = a.scale[nb] * lll * lll;
+        }
+    }
+}
+
 static int g_vecchia_small = 1;   // dgpb_tune("vecchia_small", 0): always use the shared-memory kernels
 int vecchia_set_small(int on) {
     g_vecchia_small = on != 0;
@@ -821,6 +909,43 @@ int dgpb_gp_vecch(const double* x, int64_t M, const double* w, const double* y, 
     a.mean = mean;
     a.var = var;
     return pred_launch(vk, a, (cudaStream_t)stream);
+}
+
+int dgpb_gp_vecch_multi(const double* x, int64_t M, const double* w, const double* Y, int64_t n, int64_t D,
+                        const int64_t* NN, int64_t mp, int B, const double* length_host, const double* scale_host,
+                        const double* nugget_host, double* mean, double* var, void* stream) {
+    DGPB_REQUIRE(x && w && Y && NN && mean && var && length_host && scale_host && nugget_host, "NULL argument");
+    DGPB_REQUIRE(B >= 1 && B <= kMultiMax, "number of nodes out of range");
+    DGPB_REQUIRE(D >= 1 && D <= kMaxDim && mp >= 1 && mp + 1 <= 32, "block too large for the multi-node kernel");
+    if (M == 0) return DGPB_OK;
+    VMultiArgs a;
+    a.M = M;
+    a.n = n;
+    a.cols = (int)mp;
+    a.D = (int)D;
+    a.B = B;
+    a.xq = x;
+    a.X = w;
+    a.Y = Y;
+    a.NN = NN;
+    for (int b = 0; b < B; ++b) {
+        a.inv_l2[b] = 1.0 / (length_host[b] * length_host[b]);
+        a.scale[b] = scale_host[b];
+        a.nugget[b] = nugget_host[b];
+    }
+    a.mean = mean;
+    a.var = var;
+    const int W = 8;
+    const size_t smem = (size_t)W * (32 * ((int)D | 1) + 32 * 33) * sizeof(double);
+    static bool configured = false;
+    if (!configured) {
+        DGPB_CUDA_TRY(cudaFuncSetAttribute(vecchia_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)((size_t)W * (32 * (kMaxDim | 1) + 32 * 33) * sizeof(double))));
+        configured = true;
+    }
+    vecchia_multi_kernel<<<(unsigned)cdiv(M, W), W * 32, smem, (cudaStream_t)stream>>>(a);
+    DGPB_LAUNCHED();
+    return DGPB_OK;
 }
 
 int dgpb_linkgp_vecch(const double* m_in, const double* v_in, const double* z, int64_t M, const double* w1,

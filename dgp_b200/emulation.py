@@ -21,6 +21,8 @@ from .imputation import imputer
 class emulator:
     """Class to make predictions from the trained DGP model (arguments: emulation.py:24)."""
 
+    group_first_layer = True   # one multi-node launch for first-layer Vecchia nodes that share inputs (see below)
+
     def __init__(self, all_layer, N=10, block=True):
         self.all_layer = all_layer
         self.n_layer = len(all_layer)
@@ -124,20 +126,68 @@ class emulator:
         mean = var = None
         per_layer = []
         for l, layer in enumerate(layers):
-            ms, vs = [], []
-            for kernel in layer:
+            ms, vs = [None] * len(layer), [None] * len(layer)
+            if l == 0 and self.group_first_layer:
+                for k, (mk, vk) in self._first_layer_vecchia_groups(layer, xd, m).items():
+                    ms[k], vs[k] = mk, vk
+            for k, kernel in enumerate(layer):
+                if ms[k] is not None:
+                    continue
                 kernel.pred_m = m
                 z = L.cols(xd, kernel.connect) if kernel.connect is not None else None
                 if l == 0:
                     mk, vk = kernel._gp_prediction_dev(L.cols(xd, kernel.input_dim), z)
                 else:
                     mk, vk = kernel._linkgp_prediction_dev(L.cols(mean, kernel.input_dim), L.cols(var, kernel.input_dim), z)
-                ms.append(mk)
-                vs.append(vk)
+                ms[k], vs[k] = mk, vk
             mean, var = torch.stack(ms, 1), torch.stack(vs, 1)
             if collect_layers:
                 per_layer.append((mean, var))
         return mean, var, per_layer
+
+    @staticmethod
+    def _first_layer_vecchia_groups(layer, xd, m):
+        """First-layer Vecchia nodes with a squared-exponential kernel, ONE length-scale and the same inputs share
+        the test points, the training inputs and (see `kernel._nn_query`) the neighbour sets: they are predicted
+        by one `dgpb_gp_vecch_multi` launch that forms each block's squared distances once.  Returns
+        {node index: (mean, var)} for the nodes it handled (blocks of at most 32 points)."""
+        import ctypes
+        done = {}
+        groups = {}
+        for k, kern in enumerate(layer):
+            if not (kern.vecch and kern.name == 'sexp' and len(np.atleast_1d(kern.length)) == 1 and kern.rep is None):
+                continue
+            key = (tuple(np.atleast_1d(kern.input_dim)), None if kern.connect is None else tuple(kern.connect))
+            groups.setdefault(key, []).append(k)
+        lib = L.load()
+        torch = L.torch_mod()
+        for key, idx in groups.items():
+            if len(idx) < 2:
+                continue
+            first = layer[idx[0]]
+            X0 = first._X()
+            if min(int(m), X0.shape[0]) - (1 if first.loo_state else 0) + 1 > 32:
+                continue
+            if any(layer[k]._X().shape != X0.shape or not np.array_equal(layer[k]._X(), X0) for k in idx[1:]):
+                continue
+            first.pred_m = m
+            z = L.cols(xd, first.connect) if first.connect is not None else None
+            xq = L.cat_cols(L.cols(xd, first.input_dim), z)
+            W = L.to_dev_shared(X0)
+            NN = first._nn_query(xq, W)
+            B, M = len(idx), xq.shape[0]
+            Y = L.to_dev(np.ascontiguousarray(np.stack([layer[k].output[:, 0] for k in idx], 0)))
+            par = np.ascontiguousarray([[float(np.atleast_1d(layer[k].length)[0]) for k in idx],
+                                        [float(layer[k].scale[0]) for k in idx],
+                                        [float(layer[k].nugget[0]) for k in idx]], dtype=np.float64)
+            mean, var = L.empty((B, M)), L.empty((B, M))
+            L.check(lib.dgpb_gp_vecch_multi(L.ptr(xq), M, L.ptr(W), L.ptr(Y), W.shape[0], W.shape[1], L.ptr(NN),
+                                            NN.shape[1], B, par[0].ctypes.data_as(L.c_vp),
+                                            par[1].ctypes.data_as(L.c_vp), par[2].ctypes.data_as(L.c_vp),
+                                            L.ptr(mean), L.ptr(var), L.stream()))
+            for b, k in enumerate(idx):
+                done[k] = (mean[b], var[b])
+        return done
 
     def predict(self, x, method='mean_var', full_layer=False, sample_size=50, m=50, aggregation=True):
         """Predictions from the trained DGP (emulation.py:631-854).  `x`: (M x d) numpy array.

@@ -191,6 +191,14 @@ int dgpb_gp_vecch(const double* x, int64_t M, const double* w, const double* y, 
                   const int64_t* NN, int64_t mp, const double* length_host, int64_t nlen, double scale,
                   double nugget, const double* nugget_diag, int kind, double* mean, double* var, void* stream);
 
+/* gp_vecch for B squared-exponential nodes with ONE length-scale each that share the inputs w, the test points and
+ * the neighbour array (the first layer of a Vecchia DGP, kernel_class.py:586-625 called per node by
+ * emulation.py:780-800): the block's raw squared distances are formed once per test point.  Y: B x n outputs,
+ * length/scale/nugget_host: B values each, mean/var: B x M.  Needs mp + 1 <= 32. */
+int dgpb_gp_vecch_multi(const double* x, int64_t M, const double* w, const double* Y, int64_t n, int64_t D,
+                        const int64_t* NN, int64_t mp, int B, const double* length_host, const double* scale_host,
+                        const double* nugget_host, double* mean, double* var, void* stream);
+
 /* link_gp_vecch + IJ_nb  vecchia.py:758-907.  m_in/v_in: M x Dw, z: M x Dz or NULL,
  * w1: n x Dw, gw: n x Dz or NULL. */
 int dgpb_linkgp_vecch(const double* m_in, const double* v_in, const double* z, int64_t M,

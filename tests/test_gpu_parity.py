@@ -768,6 +768,10 @@ def test_vecchia_dgp_public_api_roundtrip(tmp_path):
     mu, var = emu.predict(xt, m=12)
     assert mu.shape == (257, 1) and np.all(np.isfinite(mu)) and np.all(var > 0)
     assert np.sqrt(np.mean((mu[:, 0] - f(xt)) ** 2)) < 0.5
+    emu.group_first_layer = False      # one launch per node instead of the multi-node first-layer kernel
+    mu1, var1 = emu.predict(xt, m=12)
+    emu.group_first_layer = True
+    assert relerr(mu, mu1, 1e-6) <= 1e-9 and relerr(var, var1, 1e-300) <= 1e-9
     draws = emu.predict(xt[:9], method="sampling", sample_size=5, m=12)
     assert len(draws) == 1 and draws[0].shape == (9, 10)
     lmu, lvar = emu.loo(X, m=10)
