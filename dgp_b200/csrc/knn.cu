@@ -122,6 +122,11 @@ __device__ __forceinline__ void knn_dmma(double& c0, double& c1, double a, doubl
                  : "+d"(c0), "+d"(c1)
                  : "d"(a), "d"(b));
 }
+__device__ __forceinline__ void knn_dmma_init(double& d0, double& d1, double a, double b, double c0, double c1) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%4,%5};\n"
+                 : "=d"(d0), "=d"(d1)
+                 : "d"(a), "d"(b), "d"(c0), "d"(c1));
+}
 __device__ __forceinline__ void knn_cp8(void* smem_dst, const void* gsrc, bool pred) {
     unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
     int sz = pred ? 8 : 0;  // src-size 0 -> zero fill
@@ -194,7 +199,7 @@ constexpr size_t knn_smem_bytes() {
 template <int KS, int NL, bool ORDERED>
 __global__ void __launch_bounds__(256, KS <= 3 && NL == 1 ? 3 : 2) knn_mma_kernel(const double* __restrict__ q, int64_t M, const double* __restrict__ x,
                                                       int64_t n, int D, int m, int64_t* __restrict__ NN, int ldnn,
-                                                      unsigned char* __restrict__ flags) {
+                                                      unsigned char* __restrict__ flags, int dbg) {
     constexpr int DP = KnnPad<KS>::value;
     constexpr int LC = 32 * NL;
     extern __shared__ __align__(16) unsigned char knn_smem[];
@@ -211,8 +216,8 @@ __global__ void __launch_bounds__(256, KS <= 3 && NL == 1 ? 3 : 2) knn_mma_kerne
         ldist[i] = INFINITY;
         lidx[i] = -1;
     }
-    // A fragments: -2 q for the warp's two query octets; squared norms of this lane's two queries
-    double aq[2][KS], qn[2];
+    // A fragments: -2 q for the warp's two query octets
+    double aq[2][KS];
 #pragma unroll
     for (int s = 0; s < 2; ++s) {
         const int64_t qi = q0 + 16 * w + 8 * s + g;
@@ -221,10 +226,6 @@ __global__ void __launch_bounds__(256, KS <= 3 && NL == 1 ? 3 : 2) knn_mma_kerne
             const int k = 4 * ks + t4;
             aq[s][ks] = (qi < M && k < D) ? -2.0 * q[qi * D + k] : 0.0;
         }
-        double sn = 0.0;
-        if (qi < M)
-            for (int k = 0; k < D; ++k) sn += q[qi * D + k] * q[qi * D + k];
-        qn[s] = sn;
     }
     double thr[2] = {INFINITY, INFINITY};
     double xnmax = 0.0;
@@ -279,16 +280,16 @@ __global__ void __launch_bounds__(256, KS <= 3 && NL == 1 ? 3 : 2) knn_mma_kerne
             for (int h = 0; h < 2; ++h) {
                 nn2[h] = *reinterpret_cast<const double2*>(&xnt[8 * (cg + h) + 2 * t4]);
             }
+            // screened value = |x|^2 - 2 q.x  (the query's own |q|^2 is a per-list constant: it is left out of
+            // the accumulator -- the candidate norms feed the first DMMA as its C operand -- and added back only
+            // where a true distance is needed, the loss check)
             double d[2][2][2];
 #pragma unroll
             for (int h = 0; h < 2; ++h)
 #pragma unroll
-                for (int s = 0; s < 2; ++s) {
-                    d[h][s][0] = qn[s] + nn2[h].x;
-                    d[h][s][1] = qn[s] + nn2[h].y;
-                }
+                for (int s = 0; s < 2; ++s) knn_dmma_init(d[h][s][0], d[h][s][1], aq[s][0], b[h][0], nn2[h].x, nn2[h].y);
 #pragma unroll
-            for (int ks = 0; ks < KS; ++ks)
+            for (int ks = 1; ks < KS; ++ks)
 #pragma unroll
                 for (int h = 0; h < 2; ++h)
 #pragma unroll
@@ -302,6 +303,7 @@ __global__ void __launch_bounds__(256, KS <= 3 && NL == 1 ? 3 : 2) knn_mma_kerne
                     const int jl0 = 8 * (cg + h) + 2 * t4;
                     anyhit = anyhit || (d[h][s][0] < thr[s] && jl0 < lim[s]) || (d[h][s][1] < thr[s] && jl0 + 1 < lim[s]);
                 }
+            if (dbg && tile > 0) anyhit = false;   // probe only: scan cost without list maintenance (results invalid)
             if (!__any_sync(0xffffffffu, anyhit)) continue;
 #pragma unroll
             for (int h = 0; h < 2; ++h)
@@ -391,7 +393,7 @@ __global__ void __launch_bounds__(256, KS <= 3 && NL == 1 ? 3 : 2) knn_mma_kerne
             double qq = 0.0;
             for (int k = 0; k < D; ++k) qq += q[qi * D + k] * q[qi * D + k];
             const double eps = 8.0 * (double)(D + 4) * 1.1102230246251565e-16 * (qq + xnmax);
-            if (!(smax - eps > dm)) flags[qi] = 1;
+            if (!(smax + qq - eps > dm)) flags[qi] = 1;   // lists hold |x|^2 - 2 q.x
         }
         if (ORDERED) {
             // row = {i} U the m nearest j < i, sorted by index descending, -1 padded
@@ -442,7 +444,7 @@ static int knn_search(Workspace* ws, const double* q, int64_t M, const double* x
             cfg = true;                                                                                             \
         }                                                                                                           \
         knn_mma_kernel<KSV, NLV, ORDERED><<<grid, 256, knn_smem_bytes<KSV, NLV>(), st>>>(q, M, x, n, D, m, NN, ldnn, \
-                                                                                        flags);                     \
+                                                                                        flags, g_knn_mma == 2);                     \
         DGPB_LAUNCHED();                                                                                            \
         return launch_knn<ORDERED>(q, M, x, n, D, m, NN, ldnn, flags, st);                                          \
     }
@@ -453,7 +455,7 @@ static int knn_search(Workspace* ws, const double* q, int64_t M, const double* x
 }
 
 int knn_set_mma(int on) {
-    g_knn_mma = on != 0;
+    g_knn_mma = on;   // 0 = scalar kernel, 1 = screen + rank, 2 = probe: screen without list maintenance (invalid results)
     return DGPB_OK;
 }
 
