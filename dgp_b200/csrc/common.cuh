@@ -105,6 +105,8 @@ struct CachedFactor {
     size_t cap = 0;        // doubles allocated
     int64_t n = 0;
     bool valid = false;
+    double logdet = 0.0;   // log|K| of the stored factor (valid when has_logdet)
+    bool has_logdet = false;
 };
 
 struct Workspace {

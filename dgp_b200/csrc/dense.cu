@@ -1122,6 +1122,8 @@ int dgpb_tune(const char* key, int value) {
     } else if (k == "ess_batch") {
         DGPB_REQUIRE(value >= 0 && value <= MAXB, "ess_batch out of range");
         g_ess_target_b = value;
+    } else if (k == "ess_trsv") {
+        g_ess_cached_threshold = value != 0;
     } else if (k == "linkgp_matern_tab") {
         linkgp_set_matern_tab(value);
     } else if (k == "linkgp_mma") {

@@ -67,5 +67,6 @@ int loglik_batch_device(Workspace* ws, const KernelDev* kds, const double* const
 
 // matrices per speculative ESS wave (ess.cu)
 extern int g_ess_target_b;
+extern int g_ess_cached_threshold;
 
 }  // namespace dgpb

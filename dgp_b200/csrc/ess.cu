@@ -53,7 +53,8 @@ struct DenseBatchInfo {
 };
 
 // keep chol(K) of batch slot b (just factored, diagonal blocks still in the side buffer) under `key`
-static int cache_store(Workspace* ws, int key, const Geom& g, const Batch& bt, int b, cudaStream_t st) {
+static int cache_store(Workspace* ws, int key, const Geom& g, const Batch& bt, int b, cudaStream_t st,
+                       const double* logdet = nullptr) {
     CachedFactor& cf = ws->cache[key];
     if (cf.cap < g.elems()) {
         if (cf.T) DGPB_CUDA_TRY(cudaFree(cf.T));
@@ -71,6 +72,8 @@ static int cache_store(Workspace* ws, int key, const Geom& g, const Batch& bt, i
     DGPB_TRY(restore_diag_blocks(g, one, 1, st));
     cf.n = g.n;
     cf.valid = true;
+    cf.has_logdet = logdet != nullptr;
+    cf.logdet = logdet ? *logdet : 0.0;
     return DGPB_OK;
 }
 
@@ -251,6 +254,125 @@ using namespace dgpb;
 namespace dgpb {
 
 int g_ess_target_b = 8;  // matrices per speculative wave (dgpb_tune "ess_batch"); 0/1 = one proposal at a time
+int g_ess_cached_threshold = 1;  // threshold from cached factors by a triangular solve (dgpb_tune "ess_trsv")
+
+// |L^-1 y|^2 for a cached factor L (T layout, diagonal blocks restored): forward substitution by ONE CTA per matrix,
+// x kept in shared memory.  Per 64-row block the eight warps form y_i - sum_j L_ij x_j for eight rows each
+// (row-contiguous double2 loads, 16 in flight per thread), then warp 0 solves the 64 x 64 diagonal block with the
+// solution travelling by shuffles.  n^2 flop per matrix: the threshold of an ESS block update whose upper nodes
+// kept their inputs (only their outputs moved) costs this instead of a factorisation (n^3/3).
+__global__ void __launch_bounds__(256, 1) trsv_quad_kernel(const double* const* __restrict__ Ts, int64_t ld, int n,
+                                                           const double* const* __restrict__ ys, double* __restrict__ out) {
+    extern __shared__ double xs[];   // n (padded to 64) + 64 right-hand sides + 64 x 65 diagonal block
+    const double* __restrict__ T = Ts[blockIdx.x];
+    const double* __restrict__ y = ys[blockIdx.x];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int nb = (n + 63) / 64;
+    double* rs = xs + (size_t)nb * 64;   // right-hand side of the current block after the GEMV part
+    double* sd = rs + 64;                // 64 x 65 diagonal block
+    double quad = 0.0;
+    for (int b = 0; b < nb; ++b) {
+        const int r0 = 64 * b;
+        // rows r0 + 8 w + {0..7}: dot products with x[0, r0)
+        double acc[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) acc[r] = 0.0;
+        for (int c = 2 * lane; c < r0; c += 64) {
+            const double2 xv = *reinterpret_cast<const double2*>(&xs[c]);
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const int row = r0 + 8 * w + r;
+                if (row < n) {
+                    const double2 lv = *reinterpret_cast<const double2*>(&T[(int64_t)row * ld + c]);
+                    acc[r] = fma(lv.x, xv.x, fma(lv.y, xv.y, acc[r]));
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            double v = acc[r];
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            const int row = r0 + 8 * w + r;
+            if (lane == 0) rs[8 * w + r] = row < n ? y[row] - v : 0.0;
+        }
+        // the 64 x 64 diagonal block (identity outside the matrix) staged for the substitution
+        for (int idx = tid; idx < 64 * 64; idx += 256) {
+            const int i = idx >> 6, j = idx & 63;
+            const int gi = r0 + i, gj = r0 + j;
+            sd[i * 65 + j] = (gi < n && gj <= gi) ? T[(int64_t)gi * ld + gj] : (i == j ? 1.0 : 0.0);
+        }
+        __syncthreads();
+        if (w == 0) {
+            // forward substitution on the diagonal block: lane holds rows lane and lane + 32
+            double b0 = rs[lane], b1 = rs[lane + 32];
+            const int ra = r0 + lane, rb = r0 + lane + 32;
+            for (int j = 0; j < 64; ++j) {
+                const double bj = __shfl_sync(0xffffffffu, j < 32 ? b0 : b1, j & 31);
+                const double xj = bj / sd[j * 65 + j];
+                if (lane == (j & 31)) {
+                    if (j < 32) b0 = xj; else b1 = xj;
+                }
+                if (lane > j) b0 = fma(-sd[lane * 65 + j], xj, b0);
+                if (lane + 32 > j) b1 = fma(-sd[(lane + 32) * 65 + j], xj, b1);
+            }
+            xs[r0 + lane] = ra < n ? b0 : 0.0;
+            xs[r0 + lane + 32] = rb < n ? b1 : 0.0;
+            quad += (ra < n ? b0 * b0 : 0.0) + (rb < n ? b1 * b1 : 0.0);
+        }
+        __syncthreads();
+    }
+    if (w == 0) {
+        for (int o = 16; o > 0; o >>= 1) quad += __shfl_xor_sync(0xffffffffu, quad, o);
+        if (lane == 0) out[blockIdx.x] = quad;
+    }
+}
+
+// Sum of the upper nodes' log-likelihoods at the CURRENT state from cached factors (see trsv_quad_kernel).
+// Returns DGPB_OK with *used = 1 when every node had a cached factor with its log-determinant, else *used = 0.
+static int cached_threshold(Workspace* ws, const dgpb_node* nodes, int U, int64_t n, const int32_t* keys, double* sum_host,
+                            int* used, cudaStream_t st) {
+    *used = 0;
+    if (!keys || U > MAXB) return DGPB_OK;
+    const Geom g = make_geom(n, false);
+    const size_t smem = ((size_t)((n + 63) / 64) * 64 + 64 + 64 * 65) * sizeof(double);
+    if (smem > 200 * 1024) return DGPB_OK;
+    const double* hT[MAXB];
+    const double* hy[MAXB];
+    double logdets[MAXB];
+    for (int u = 0; u < U; ++u) {
+        if (nodes[u].vecch || keys[u] < 0) return DGPB_OK;
+        auto it = ws->cache.find(keys[u]);
+        if (it == ws->cache.end() || !it->second.valid || !it->second.has_logdet || it->second.n != n) return DGPB_OK;
+        hT[u] = it->second.T;
+        hy[u] = nodes[u].output;
+        logdets[u] = it->second.logdet;
+    }
+    void *ptab, *pout;
+    DGPB_TRY(ws->reserve(SLOT_MISC, sizeof(double*) * 2 * MAXB, &ptab));
+    DGPB_TRY(ws->reserve(SLOT_OUT, sizeof(double) * kOutDoubles, &pout));
+    const double** dT = (const double**)ptab;
+    const double** dy = dT + MAXB;
+    DGPB_CUDA_TRY(cudaMemcpyAsync(dT, hT, sizeof(double*) * U, cudaMemcpyHostToDevice, st));
+    DGPB_CUDA_TRY(cudaMemcpyAsync(dy, hy, sizeof(double*) * U, cudaMemcpyHostToDevice, st));
+    static bool cfg = false;
+    if (!cfg) {
+        DGPB_CUDA_TRY(cudaFuncSetAttribute(trsv_quad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        cfg = true;
+    }
+    double* out = (double*)pout + kOutVecchia;   // a region the dense batch results do not use
+    trsv_quad_kernel<<<U, 256, smem, st>>>(dT, g.ld, g.n, dy, out);
+    DGPB_LAUNCHED();
+    DGPB_CUDA_TRY(cudaMemcpyAsync(ws->pinned + 1024, out, sizeof(double) * U, cudaMemcpyDeviceToHost, st));
+    DGPB_CUDA_TRY(cudaStreamSynchronize(st));
+    double s = 0.0;
+    for (int u = 0; u < U; ++u) {   // same left-to-right order as imputation.py:70-78
+        const double sc = nodes[u].scale;
+        s += -0.5 * (logdets[u] + (double)n * log(sc) + ws->pinned[1024 + u] / sc);
+    }
+    *sum_host = s;
+    *used = 1;
+    return DGPB_OK;
+}
 
 // Log-likelihood sums of `nitems` candidate states of the layer below (srcs[i] = latent layer image read by the
 // upper nodes, NULL = the nodes' own `src`), all U upper nodes dense and nitems * U <= MAXB: ONE batched
@@ -259,7 +381,7 @@ int g_ess_target_b = 8;  // matrices per speculative wave (dgpb_tune "ess_batch"
 // only ever evaluates items up to the first accepted one.
 static int dense_items_loglik(Workspace* ws, const dgpb_node* nodes, int U, int64_t n, const double* const* srcs,
                               int nitems, double* sums, int* pd, int* bad_node, Batch* bt_out, Geom* g_out,
-                              cudaStream_t st) {
+                              double* logdets, cudaStream_t st) {
     const int B = nitems * U;
     DGPB_REQUIRE(B >= 1 && B <= MAXB, "wave does not fit one batch");
     KernelDev kds[MAXB];
@@ -291,6 +413,7 @@ static int dense_items_loglik(Workspace* ws, const dgpb_node* nodes, int U, int6
             }
             const double sc = nodes[u].scale;
             s += -0.5 * (ws->pinned[4 * b] + (double)n * log(sc) + ws->pinned[4 * b + 1] / sc);
+            if (logdets) logdets[b] = ws->pinned[4 * b];
         }
         sums[i] = s;
     }
@@ -337,8 +460,13 @@ extern "C" int dgpb_ess_block_cached(dgpb_ws* ws, const dgpb_node* targets, int 
     double log_y = 0.0;
     const bool have_thr = threshold_io_host && *threshold_io_host == *threshold_io_host;
     bool thr_pending = false;  // threshold to be computed together with the first wave
+    int thr_from_cache = 0;
+    if (!have_thr && g_ess_cached_threshold)
+        DGPB_TRY(cached_threshold(ws, uppers, n_uppers, n, upper_keys_host, &log_y, &thr_from_cache, st));
     if (have_thr) {
         log_y = *threshold_io_host;  // sum of the upper log-likelihoods at the current state is already known
+    } else if (thr_from_cache) {
+        // the upper nodes kept their inputs since their factors were stored: only their outputs moved
     } else if (batched && (cap + 1) * n_uppers <= MAXB) {
         thr_pending = true;
     } else {
@@ -378,6 +506,7 @@ extern "C" int dgpb_ess_block_cached(dgpb_ws* ws, const dgpb_node* targets, int 
         }
         // ---- likelihoods of the wave
         double sums[kMaxWave + 1];
+        double wave_logdets[MAXB];
         int pd[kMaxWave + 1], bad[kMaxWave + 1];
         Batch bt;
         Geom g;
@@ -389,7 +518,7 @@ extern "C" int dgpb_ess_block_cached(dgpb_ws* ws, const dgpb_node* targets, int 
             if (thr_pending) srcs[ni++] = nullptr;
             first = ni;
             for (int s = 0; s < S; ++s) srcs[ni++] = prop + s * layer_elems;
-            DGPB_TRY(dense_items_loglik(ws, uppers, n_uppers, n, srcs, ni, sums, pd, bad, &bt, &g, st));
+            DGPB_TRY(dense_items_loglik(ws, uppers, n_uppers, n, srcs, ni, sums, pd, bad, &bt, &g, wave_logdets, st));
             if (thr_pending) {
                 if (!pd[0]) {
                     set_error("covariance of upper node %d is not positive definite", bad[0]);
@@ -432,7 +561,8 @@ extern "C" int dgpb_ess_block_cached(dgpb_ws* ws, const dgpb_node* targets, int 
                 if (batched) {
                     for (int u = 0; u < n_uppers; ++u)
                         if (upper_keys_host[u] >= 0)
-                            DGPB_TRY(cache_store(ws, upper_keys_host[u], g, bt, (first + accepted) * n_uppers + u, st));
+                            DGPB_TRY(cache_store(ws, upper_keys_host[u], g, bt, (first + accepted) * n_uppers + u, st,
+                                                 &wave_logdets[(first + accepted) * n_uppers + u]));
                 } else {
                     for (int b = 0; b < info.B; ++b)
                         if (upper_keys_host[info.map[b]] >= 0)
