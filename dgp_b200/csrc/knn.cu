@@ -1,7 +1,8 @@
 // knn.cu -- exact FP64 nearest-neighbour search on sm_100a  (nn / get_pred_nn, dgpsi/vecchia.py:20-109).
 //
 // The search is brute force (10-20 dimensional inputs leave nothing to prune) in two stages:
-//   1. SCREEN on the FP64 tensor path.  |q - x|^2 = |q|^2 + |x|^2 - 2 q.x ; the cross term is a DMMA product
+//   1. SCREEN on the tensor path (FP64 DMMA form described here; the default is the split-TF32 form further down,
+//      which keeps everything but the arithmetic of the cross term).  |q - x|^2 = |q|^2 + |x|^2 - 2 q.x ; the cross term is a DMMA product
 //      (mma.m8n8k4: 8 queries x 8 candidates x 4 dimensions per instruction), the norms initialise the
 //      accumulator.  Every query keeps the LC = 32 or 64 smallest screened distances in a sorted
 //      shared-memory list owned by its warp (insertions become rare after the first few hundred candidates and
@@ -182,6 +183,80 @@ __device__ __forceinline__ double knn_list_insert(double* ld, int* li, int lane,
     return last;
 }
 
+// Exact ranking of one query's survivors (list entry per lane): distances re-evaluated with the reference
+// arithmetic, ranked by (distance, index), written in the reference's output format.  `bound`: every candidate the
+// screen dropped has exact distance >= bound (meaningful when the list is full); if the exact m-th distance does
+// not stay below it the query is flagged for the scalar exact kernel.
+template <int NL, bool ORDERED>
+__device__ __forceinline__ void knn_rank_and_write(const double* __restrict__ q, const double* __restrict__ x, int64_t qi,
+                                                   int D, int m, const int* __restrict__ lidx_q, double bound,
+                                                   int64_t* __restrict__ NN, int ldnn, unsigned char* __restrict__ flags,
+                                                   int lane) {
+    constexpr int LC = 32 * NL;
+    double dv[NL];
+    int jv[NL];
+    int filled = 0;
+#pragma unroll
+    for (int e = 0; e < NL; ++e) {
+        const int j = lidx_q[lane + 32 * e];
+        jv[e] = j;
+        double dist = INFINITY;
+        if (j >= 0) {
+            dist = 0.0;
+            for (int k = 0; k < D; ++k) {
+                const double df = __dsub_rn(q[qi * D + k], x[(int64_t)j * D + k]);
+                dist = __dadd_rn(dist, __dmul_rn(df, df));
+            }
+            ++filled;
+        }
+        dv[e] = dist;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) filled += __shfl_xor_sync(0xffffffffu, filled, o);
+    int rank[NL];
+#pragma unroll
+    for (int e = 0; e < NL; ++e) rank[e] = 0;
+#pragma unroll
+    for (int e2 = 0; e2 < NL; ++e2)
+        for (int l2 = 0; l2 < 32; ++l2) {
+            const double od = __shfl_sync(0xffffffffu, dv[e2], l2);
+            const int oj = __shfl_sync(0xffffffffu, jv[e2], l2);
+#pragma unroll
+            for (int e = 0; e < NL; ++e) rank[e] += (oj >= 0) && (od < dv[e] || (od == dv[e] && oj < jv[e]));
+        }
+    const int take = min(m, filled);
+    double dm = 0.0;   // exact m-th distance
+#pragma unroll
+    for (int e = 0; e < NL; ++e)
+        if (jv[e] >= 0 && rank[e] < take) dm = fmax(dm, dv[e]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dm = fmax(dm, __shfl_xor_sync(0xffffffffu, dm, o));
+    if (lane == 0 && filled == LC && !(bound > dm)) flags[qi] = 1;
+    if (ORDERED) {
+        // row = {i} U the m nearest j < i, sorted by index descending, -1 padded
+        if (lane == 0) NN[qi * ldnn] = qi;
+        for (int a = lane; a < ldnn - 1; a += 32)
+            if (a >= take) NN[qi * ldnn + 1 + a] = -1;
+#pragma unroll
+        for (int e = 0; e < NL; ++e) {
+            const bool sel = jv[e] >= 0 && rank[e] < take;
+            int r2 = 0;
+#pragma unroll
+            for (int e2 = 0; e2 < NL; ++e2)
+                for (int l2 = 0; l2 < 32; ++l2) {
+                    const int oj = __shfl_sync(0xffffffffu, jv[e2], l2);
+                    const int orank = __shfl_sync(0xffffffffu, rank[e2], l2);
+                    r2 += (oj >= 0 && orank < take && oj > jv[e]);
+                }
+            if (sel) NN[qi * ldnn + 1 + r2] = jv[e];
+        }
+    } else {
+#pragma unroll
+        for (int e = 0; e < NL; ++e)
+            if (jv[e] >= 0 && rank[e] < take) NN[qi * ldnn + rank[e]] = jv[e];
+    }
+}
+
 constexpr int kKnnTC = 128;   // candidates per staged tile
 constexpr int kKnnQ = 128;    // queries per CTA: 8 warps x 16
 
@@ -342,86 +417,260 @@ __global__ void __launch_bounds__(256, KS <= 3 && NL == 1 ? 3 : 2) knn_mma_kerne
     for (int ql = 16 * w; ql < 16 * w + 16; ++ql) {
         const int64_t qi = q0 + ql;
         if (qi >= M) break;
-        double dv[NL];
-        int jv[NL];
-        double smax = 0.0;      // screened LC-th distance (the list's maximum)
-        int filled = 0;
+        double smax = 0.0;      // screened LC-th value (the list's maximum)
 #pragma unroll
-        for (int e = 0; e < NL; ++e) {
-            const int j = lidx[(size_t)ql * LC + lane + 32 * e];
-            jv[e] = j;
-            smax = fmax(smax, ldist[(size_t)ql * LC + lane + 32 * e]);
-            double dist = INFINITY;
-            if (j >= 0) {
-                dist = 0.0;
-                for (int k = 0; k < D; ++k) {
-                    const double df = __dsub_rn(q[qi * D + k], x[(int64_t)j * D + k]);
-                    dist = __dadd_rn(dist, __dmul_rn(df, df));
-                }
-                ++filled;
-            }
-            dv[e] = dist;
-        }
+        for (int e = 0; e < NL; ++e) smax = fmax(smax, ldist[(size_t)ql * LC + lane + 32 * e]);
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            smax = fmax(smax, __shfl_xor_sync(0xffffffffu, smax, o));
-            filled += __shfl_xor_sync(0xffffffffu, filled, o);
-        }
-        // rank by (distance, index)
-        int rank[NL];
-#pragma unroll
-        for (int e = 0; e < NL; ++e) rank[e] = 0;
-#pragma unroll
-        for (int e2 = 0; e2 < NL; ++e2)
-            for (int l2 = 0; l2 < 32; ++l2) {
-                const double od = __shfl_sync(0xffffffffu, dv[e2], l2);
-                const int oj = __shfl_sync(0xffffffffu, jv[e2], l2);
-#pragma unroll
-                for (int e = 0; e < NL; ++e)
-                    rank[e] += (oj >= 0) && (od < dv[e] || (od == dv[e] && oj < jv[e]));
-            }
-        const int take = min(m, filled);
-        // exact m-th distance and the loss check
-        double dm = 0.0;
-#pragma unroll
-        for (int e = 0; e < NL; ++e)
-            if (jv[e] >= 0 && rank[e] < take) dm = fmax(dm, dv[e]);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) dm = fmax(dm, __shfl_xor_sync(0xffffffffu, dm, o));
-        if (lane == 0 && filled == LC) {
-            // candidates outside the list have screened distance >= smax; |screened - exact| <= eps
-            double qq = 0.0;
-            for (int k = 0; k < D; ++k) qq += q[qi * D + k] * q[qi * D + k];
-            const double eps = 8.0 * (double)(D + 4) * 1.1102230246251565e-16 * (qq + xnmax);
-            if (!(smax + qq - eps > dm)) flags[qi] = 1;   // lists hold |x|^2 - 2 q.x
-        }
-        if (ORDERED) {
-            // row = {i} U the m nearest j < i, sorted by index descending, -1 padded
-            if (lane == 0) NN[qi * ldnn] = qi;
-            for (int a = lane; a < ldnn - 1; a += 32)
-                if (a >= take) NN[qi * ldnn + 1 + a] = -1;
-#pragma unroll
-            for (int e = 0; e < NL; ++e) {
-                const bool sel = jv[e] >= 0 && rank[e] < take;
-                int r2 = 0;
-#pragma unroll
-                for (int e2 = 0; e2 < NL; ++e2)
-                    for (int l2 = 0; l2 < 32; ++l2) {
-                        const int oj = __shfl_sync(0xffffffffu, jv[e2], l2);
-                        const int orank = __shfl_sync(0xffffffffu, rank[e2], l2);
-                        r2 += (oj >= 0 && orank < take && oj > jv[e]);
-                    }
-                if (sel) NN[qi * ldnn + 1 + r2] = jv[e];
-            }
-        } else {
-#pragma unroll
-            for (int e = 0; e < NL; ++e)
-                if (jv[e] >= 0 && rank[e] < take) NN[qi * ldnn + rank[e]] = jv[e];
-        }
+        for (int o = 16; o > 0; o >>= 1) smax = fmax(smax, __shfl_xor_sync(0xffffffffu, smax, o));
+        // candidates outside the list have screened value >= smax; lists hold |x|^2 - 2 q.x; |screened - exact| <= eps
+        double qq = 0.0;
+        for (int k = 0; k < D; ++k) qq += q[qi * D + k] * q[qi * D + k];
+        const double eps = 8.0 * (double)(D + 4) * 1.1102230246251565e-16 * (qq + xnmax);
+        knn_rank_and_write<NL, ORDERED>(q, x, qi, D, m, lidx + (size_t)ql * LC, smax + qq - eps, NN, ldnn, flags, lane);
     }
 }
 
-static int g_knn_mma = 1;   // dgpb_tune("knn_mma", 0) forces the scalar exact kernel (tests compare the two)
+// ------------------------------------------------------------------------------------------------
+// Screen on the TF32 tensor path with split operands.  The screen only has to be right to within the gap between
+// the exact m-th and the screened LC-th distance (a few per cent of the distance itself), so it does not need
+// FP64: every coordinate (shifted by the first candidate, so offsets do not eat mantissa) is split into two TF32
+// numbers v = hi + lo (relative error 2^-22), the cross term is hi.hi + hi.lo + lo.hi -- three
+// mma.m16n8k8.tf32 with FP32 accumulation, products of 10-bit mantissas are exact in FP32 -- and the candidate
+// norm initialises the accumulator.  16 queries x 8 candidates x 8 dimensions per instruction at the HMMA rate
+// instead of 8 x 8 x 4 at the FP64 rate; the per-query lists, the exact FP64 ranking, the error-bound check
+// (bound 2^-17 (|q| + |x|max)^2, four times the analytic estimate) and the scalar fallback are those of the DMMA
+// version, so the result is still exactly that of the exact search.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned knn_tf32(float v) {
+    unsigned r;
+    asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(r) : "f"(v));
+    return r;
+}
+__device__ __forceinline__ void knn_hmma(float (&c)[4], const unsigned (&a)[4], unsigned b0, unsigned b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// Offer (d, j) to the sorted FP32 list (see knn_list_insert).
+template <int NL>
+__device__ __forceinline__ float knn_list_insert_f(float* ld, int* li, int lane, float d, int j, float thr) {
+    if (!(d < thr)) return thr;
+    float v[NL];
+    int ix[NL];
+    int p = 0;
+#pragma unroll
+    for (int e = 0; e < NL; ++e) {
+        v[e] = ld[lane + 32 * e];
+        ix[e] = li[lane + 32 * e];
+        p += __popc(__ballot_sync(0xffffffffu, v[e] <= d));
+    }
+    float last = 0.f;
+#pragma unroll
+    for (int e = 0; e < NL; ++e) {
+        const int slot = lane + 32 * e;
+        float pv = __shfl_up_sync(0xffffffffu, v[e], 1);
+        int pi = __shfl_up_sync(0xffffffffu, ix[e], 1);
+        if (e > 0) {
+            const float cv = __shfl_sync(0xffffffffu, v[e - 1], 31);
+            const int ci = __shfl_sync(0xffffffffu, ix[e - 1], 31);
+            if (lane == 0) {
+                pv = cv;
+                pi = ci;
+            }
+        }
+        float nv = v[e];
+        int ni = ix[e];
+        if (slot == p) {
+            nv = d;
+            ni = j;
+        } else if (slot > p) {
+            nv = pv;
+            ni = pi;
+        }
+        if (slot >= p) {
+            ld[slot] = nv;
+            li[slot] = ni;
+        }
+        if (e == NL - 1) last = __shfl_sync(0xffffffffu, nv, 31);
+    }
+    __syncwarp();
+    return last;
+}
+
+template <int KS8, int NL>
+constexpr size_t knn_tf32_smem_bytes() {
+    return (size_t)2 * kKnnTC * (8 * KS8 + 4) * 8 + 2 * kKnnTC * 4 + (size_t)kKnnQ * 32 * NL * 8 + 64;
+}
+
+// KS8 = ceil(D / 8) k-steps of 8 dimensions, NL = list entries per lane.
+template <int KS8, int NL, bool ORDERED>
+__global__ void __launch_bounds__(256, 2) knn_tf32_kernel(const double* __restrict__ q, int64_t M, const double* __restrict__ x,
+                                                          int64_t n, int D, int m, int64_t* __restrict__ NN, int ldnn,
+                                                          unsigned char* __restrict__ flags) {
+    constexpr int DPF = 8 * KS8 + 4;   // float2 row stride: = 4 mod 16 -> conflict-free fragment loads
+    constexpr int LC = 32 * NL;
+    extern __shared__ __align__(16) unsigned char knn_smem[];
+    float2* xs = reinterpret_cast<float2*>(knn_smem);                    // [2][TC][DPF] {hi, lo} of the shifted coordinates
+    float* xn = reinterpret_cast<float*>(xs + 2 * kKnnTC * DPF);         // [2][TC] squared norms
+    float* ldist = xn + 2 * kKnnTC;                                      // [Q][LC] screened values
+    int* lidx = reinterpret_cast<int*>(ldist + (size_t)kKnnQ * LC);      // [Q][LC]
+    float* s_xnmax = reinterpret_cast<float*>(lidx + (size_t)kKnnQ * LC);  // [8]
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int g = lane >> 2, t4 = lane & 3;
+    const int64_t q0 = (int64_t)blockIdx.x * kKnnQ;
+    for (int i = tid; i < 2 * kKnnTC * DPF; i += 256) xs[i] = make_float2(0.f, 0.f);   // pad columns stay zero
+    for (int i = tid; i < kKnnQ * LC; i += 256) {
+        ldist[i] = INFINITY;
+        lidx[i] = -1;
+    }
+    // A fragments: -2 (q - x_0), split; rows g and g + 8 of the warp's 16 queries
+    unsigned ah[KS8][4], al[KS8][4];
+#pragma unroll
+    for (int ks = 0; ks < KS8; ++ks)
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int64_t qi = q0 + 16 * w + g + 8 * (r & 1);
+            const int k = 8 * ks + t4 + 4 * (r >> 1);
+            const float v = (qi < M && k < D) ? (float)(-2.0 * (q[qi * D + k] - x[k])) : 0.f;
+            ah[ks][r] = knn_tf32(v);
+            al[ks][r] = knn_tf32(v - __uint_as_float(ah[ks][r]));
+        }
+    float thr[2] = {INFINITY, INFINITY};
+    float xnmax = 0.f;
+    const int64_t cmax = ORDERED ? min(n, q0 + kKnnQ) : n;
+    const int ntiles = (int)((cmax + kKnnTC - 1) / kKnnTC);
+    // staging: two threads per candidate, each converts half of the dimensions.  The FP64 loads of the NEXT tile
+    // are issued into registers before the current tile is scanned and converted / stored after it, so their
+    // latency is covered by the scan.
+    constexpr int KH = 4 * KS8;
+    const int sc = tid >> 1, sh = tid & 1;
+    const int kh = (D + 1) / 2, k0s = sh * kh, k1s = min(D, k0s + kh);
+    double stg[KH], shift[KH];
+#pragma unroll
+    for (int k = 0; k < KH; ++k) shift[k] = (k0s + k < k1s) ? x[k0s + k] : 0.0;
+    auto load_tile = [&](int tile) {
+        const int64_t j = (int64_t)tile * kKnnTC + sc;
+#pragma unroll
+        for (int k = 0; k < KH; ++k) stg[k] = (j < n && k0s + k < k1s) ? x[j * D + k0s + k] : shift[k];
+    };
+    auto store_tile = [&](int tile) {
+        float2* dst = xs + (size_t)(tile & 1) * kKnnTC * DPF + sc * DPF;
+        double sn = 0.0;
+#pragma unroll
+        for (int k = 0; k < KH; ++k) {
+            const double v = stg[k] - shift[k];
+            sn += v * v;
+            const float hi = __uint_as_float(knn_tf32((float)v));
+            if (k0s + k < k1s) dst[k0s + k] = make_float2(hi, __uint_as_float(knn_tf32((float)(v - (double)hi))));
+        }
+        sn += __shfl_xor_sync(0xffffffffu, sn, 1);
+        if (sh == 0) {
+            xn[(tile & 1) * kKnnTC + sc] = (float)sn;
+            xnmax = fmaxf(xnmax, (float)sn);
+        }
+    };
+    __syncthreads();
+    if (ntiles > 0) {
+        load_tile(0);
+        store_tile(0);
+    }
+    for (int tile = 0; tile < ntiles; ++tile) {
+        __syncthreads();   // tile staged; everybody done with the buffer that is refilled below
+        if (tile + 1 < ntiles) load_tile(tile + 1);
+        const float2* xt = xs + (size_t)(tile & 1) * kKnnTC * DPF;
+        const float* xnt = xn + (tile & 1) * kKnnTC;
+        const int64_t c0 = (int64_t)tile * kKnnTC;
+        int lim[2];
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            const int64_t qi = q0 + 16 * w + 8 * s + g;
+            const int64_t jl = (ORDERED ? min(n, qi) : n) - c0;
+            lim[s] = qi < M ? (int)max((int64_t)0, min(jl, (int64_t)kKnnTC)) : 0;
+        }
+        for (int cg = 0; cg < kKnnTC / 8; cg += 2) {
+            float c[2][4];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const float2 nn2 = *reinterpret_cast<const float2*>(&xnt[8 * (cg + h) + 2 * t4]);
+                c[h][0] = c[h][2] = nn2.x;
+                c[h][1] = c[h][3] = nn2.y;
+            }
+#pragma unroll
+            for (int ks = 0; ks < KS8; ++ks)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const float2 b0 = xt[(8 * (cg + h) + g) * DPF + 8 * ks + t4];
+                    const float2 b1 = xt[(8 * (cg + h) + g) * DPF + 8 * ks + t4 + 4];
+                    const unsigned bh0 = __float_as_uint(b0.x), bl0 = __float_as_uint(b0.y);
+                    const unsigned bh1 = __float_as_uint(b1.x), bl1 = __float_as_uint(b1.y);
+                    knn_hmma(c[h], ah[ks], bh0, bh1);
+                    knn_hmma(c[h], ah[ks], bl0, bl1);
+                    knn_hmma(c[h], al[ks], bh0, bh1);
+                }
+            bool anyhit = false;
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int s = 0; s < 2; ++s) {
+                    const int jl0 = 8 * (cg + h) + 2 * t4;
+                    anyhit = anyhit || (c[h][2 * s] < thr[s] && jl0 < lim[s]) || (c[h][2 * s + 1] < thr[s] && jl0 + 1 < lim[s]);
+                }
+            if (!__any_sync(0xffffffffu, anyhit)) continue;
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int s = 0; s < 2; ++s) {
+                    const int jl0 = 8 * (cg + h) + 2 * t4;
+                    const bool h0 = c[h][2 * s] < thr[s] && jl0 < lim[s];
+                    const bool h1 = c[h][2 * s + 1] < thr[s] && jl0 + 1 < lim[s];
+                    unsigned hm = __ballot_sync(0xffffffffu, h0 || h1);
+                    while (hm) {
+                        const int src = __ffs(hm) - 1;
+                        hm &= hm - 1;
+                        const int ql = 16 * w + 8 * s + (src >> 2);
+                        const int jj = (int)(c0 + 8 * (cg + h) + 2 * (src & 3));
+                        const float e0 = __shfl_sync(0xffffffffu, c[h][2 * s], src);
+                        const float e1 = __shfl_sync(0xffffffffu, c[h][2 * s + 1], src);
+                        const int f = __shfl_sync(0xffffffffu, (int)h0 | ((int)h1 << 1), src);
+                        float tq = __shfl_sync(0xffffffffu, thr[s], src);
+                        if (f & 1) tq = knn_list_insert_f<NL>(ldist + (size_t)ql * LC, lidx + (size_t)ql * LC, lane, e0, jj, tq);
+                        if (f & 2) tq = knn_list_insert_f<NL>(ldist + (size_t)ql * LC, lidx + (size_t)ql * LC, lane, e1, jj + 1, tq);
+                        if (g == (src >> 2)) thr[s] = tq;
+                    }
+                }
+        }
+        if (tile + 1 < ntiles) store_tile(tile + 1);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) xnmax = fmaxf(xnmax, __shfl_xor_sync(0xffffffffu, xnmax, o));
+    if (lane == 0) s_xnmax[w] = xnmax;
+    __syncthreads();
+    xnmax = s_xnmax[0];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) xnmax = fmaxf(xnmax, s_xnmax[i]);
+    for (int ql = 16 * w; ql < 16 * w + 16; ++ql) {
+        const int64_t qi = q0 + ql;
+        if (qi >= M) break;
+        float smaxf = 0.f;
+#pragma unroll
+        for (int e = 0; e < NL; ++e) smaxf = fmaxf(smaxf, ldist[(size_t)ql * LC + lane + 32 * e]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) smaxf = fmaxf(smaxf, __shfl_xor_sync(0xffffffffu, smaxf, o));
+        // lists hold |x - x0|^2 - 2 (q - x0).(x - x0) in FP32; |screened - exact| <= eps
+        double qq = 0.0;
+        for (int k = 0; k < D; ++k) {
+            const double v = q[qi * D + k] - x[k];
+            qq += v * v;
+        }
+        const double rr = sqrt(qq) + sqrt((double)xnmax);
+        const double eps = 7.62939453125e-06 * rr * rr;   // 2^-17 (|q| + |x|max)^2
+        knn_rank_and_write<NL, ORDERED>(q, x, qi, D, m, lidx + (size_t)ql * LC, (double)smaxf + qq - eps, NN, ldnn, flags,
+                                        lane);
+    }
+}
+
+static int g_knn_mma = 3;   // dgpb_tune("knn_mma", v): 0 scalar exact kernel, 1 FP64 DMMA screen, 3 split-TF32 screen (default)
 
 template <bool ORDERED>
 static int knn_search(Workspace* ws, const double* q, int64_t M, const double* x, int64_t n, int D, int m, int64_t* NN,
@@ -434,6 +683,26 @@ static int knn_search(Workspace* ws, const double* q, int64_t M, const double* x
     unsigned char* flags = (unsigned char*)pf;
     DGPB_CUDA_TRY(cudaMemsetAsync(flags, 0, (size_t)M, st));
     const unsigned grid = (unsigned)cdiv(M, kKnnQ);
+    if (g_knn_mma == 3) {
+        const int KS8 = (D + 7) / 8;
+#define KNN_TF32_CASE(KSV, NLV)                                                                                          \
+    if (KS8 == KSV && NL == NLV) {                                                                                       \
+        static bool cfg = false;                                                                                         \
+        if (!cfg) {                                                                                                      \
+            DGPB_CUDA_TRY(cudaFuncSetAttribute(knn_tf32_kernel<KSV, NLV, ORDERED>,                                       \
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize,                             \
+                                               (int)knn_tf32_smem_bytes<KSV, NLV>()));                                   \
+            cfg = true;                                                                                                  \
+        }                                                                                                                \
+        knn_tf32_kernel<KSV, NLV, ORDERED><<<grid, 256, knn_tf32_smem_bytes<KSV, NLV>(), st>>>(q, M, x, n, D, m, NN,      \
+                                                                                              ldnn, flags);              \
+        DGPB_LAUNCHED();                                                                                                 \
+        return launch_knn<ORDERED>(q, M, x, n, D, m, NN, ldnn, flags, st);                                               \
+    }
+        KNN_TF32_CASE(1, 1) KNN_TF32_CASE(2, 1) KNN_TF32_CASE(3, 1) KNN_TF32_CASE(4, 1)
+        KNN_TF32_CASE(1, 2) KNN_TF32_CASE(2, 2) KNN_TF32_CASE(3, 2) KNN_TF32_CASE(4, 2)
+#undef KNN_TF32_CASE
+    }
 #define KNN_MMA_CASE(KSV, NLV)                                                                                      \
     if (KS <= KSV && NL == NLV) {                                                                                   \
         static bool cfg = false;                                                                                    \
@@ -455,7 +724,8 @@ static int knn_search(Workspace* ws, const double* q, int64_t M, const double* x
 }
 
 int knn_set_mma(int on) {
-    g_knn_mma = on;   // 0 = scalar kernel, 1 = screen + rank, 2 = probe: screen without list maintenance (invalid results)
+    g_knn_mma = on;   // 0 = scalar kernel, 1 = DMMA screen + rank, 2 = probe: DMMA screen without list maintenance
+                      // (invalid results), 3 = split-TF32 screen + rank
     return DGPB_OK;
 }
 

@@ -249,7 +249,8 @@ int dgpb_probe_factorize(dgpb_ws* ws, int64_t n, int B, int aug, int reps, doubl
  * "hb_min_w" (smallest remaining window factored with hyper-blocks), "hb_graded" (0/1: ramp the first hyper-blocks
  * 128, 256, 512), and of the ESS loop: "ess_batch" (matrices per speculative wave; <= 1 = one proposal at a time), "ess_trsv" (1 = threshold of a block
  * update from cached factors by a triangular solve when only the upper nodes' outputs moved),
- * and of the neighbour search: "knn_mma" (1 = tensor-core screen + exact ranking, 0 = scalar exact kernel),
+ * and of the neighbour search: "knn_mma" (3 = split-TF32 tensor-core screen + exact FP64 ranking [default], 1 = FP64 DMMA screen, 0 = scalar
+ * exact kernel),
  * and of the Vecchia block kernels: "vecchia_small" (1 = register-resident kernel for blocks of <= 32 points),
  * and of link_gp: "linkgp_mma" (1 = squared-exponential exponents on the FP64 tensor path), "linkgp_matern_tab" (1 = Matern-2.5 J
  * integrals from per-point tables of their transcendental factors) */

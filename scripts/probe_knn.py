@@ -10,7 +10,7 @@ rng = np.random.default_rng(3)
 for D, m in ((10, 25), (20, 25), (10, 50)):
     M, n = 200000, 100000
     xq, xw = L.to_dev(rng.uniform(0, 1, (M, D))), L.to_dev(rng.uniform(0, 1, (n, D)))
-    for mode, name in ((1, "screen + lists + rank"), (2, "screen only (probe)"), (0, "scalar exact kernel")):
+    for mode, name in ((3, "split-TF32 screen + rank"), (1, "DMMA screen + lists + rank"), (2, "DMMA screen only (probe)"), (0, "scalar exact kernel")):
         if mode == 0 and D == 20: continue
         L.check(lib.dgpb_tune(b"knn_mma", mode))
         V.get_pred_nn_dev(xq, xw, m); torch.cuda.synchronize()

@@ -368,8 +368,9 @@ def test_nn_indices_bit_exact(golden_vecchia):
 
 
 def test_knn_tensor_core_screen_equals_scalar_search():
-    """The neighbour search screens candidates on the FP64 tensor path and ranks the survivors with the reference
-    arithmetic; its index arrays must equal those of the scalar exact kernel bit for bit -- random inputs, ragged
+    """The neighbour search screens candidates on the tensor path (FP64 DMMA, or split-TF32 HMMA) and ranks the
+    survivors with the reference arithmetic; its index arrays must equal those of the scalar exact kernel bit for
+    bit -- inputs with a large common offset (the TF32 screen shifts by the first candidate), random inputs, ragged
     sizes, both list capacities (m <= 29 / m <= 61), the ordered variant, and inputs full of exact distance ties
     (lattice points, duplicates) where the screen has to hand queries back to the scalar kernel."""
     from dgp_b200 import _lib as L
@@ -378,17 +379,25 @@ def test_knn_tensor_core_screen_equals_scalar_search():
     lib = L.load()
     rng = np.random.default_rng(23)
 
-    def both(fn):
-        L.check(lib.dgpb_tune(b"knn_mma", 0))
-        try:
-            ref = fn()
-        finally:
-            L.check(lib.dgpb_tune(b"knn_mma", 1))
-        return ref, fn()
+    default_mode = 3
 
+    def run(fn, mode):
+        L.check(lib.dgpb_tune(b"knn_mma", mode))
+        try:
+            return fn()
+        finally:
+            L.check(lib.dgpb_tune(b"knn_mma", default_mode))
+
+    def both(fn):
+        ref, dmma, tf32 = run(fn, 0), run(fn, 1), run(fn, 3)   # scalar exact, FP64 DMMA screen, split-TF32 screen
+        assert np.array_equal(dmma, tf32)
+        return ref, tf32
+
+    assert np.array_equal(run(lambda: V.get_pred_nn(rng.uniform(0, 1, (64, 4)), rng.uniform(0, 1, (300, 4)), 5), 1).shape, (64, 5))
     for n, M, D, m in ((1000, 333, 3, 5), (5000, 1500, 10, 25), (3001, 700, 20, 50), (700, 129, 31, 29),
                        (300, 64, 10, 61), (40, 17, 2, 30), (129, 1, 1, 25)):
-        x, q = rng.uniform(0, 1, (n, D)), rng.uniform(0, 1, (M, D))
+        off = 1000.0 if n == 5000 else 0.0
+        x, q = rng.uniform(0, 1, (n, D)) + off, rng.uniform(0, 1, (M, D)) + off
         a, b = both(lambda: V.get_pred_nn(q, x, m))
         assert a.shape == (M, min(m, n)) and np.array_equal(a, b), (n, M, D, m)
         a, b = both(lambda: V.nn(x, m))
