@@ -511,7 +511,9 @@ __global__ void __launch_bounds__(256, 2) knn_tf32_kernel(const double* __restri
     constexpr int DPF = 8 * KS8 + 4;   // float2 row stride: = 4 mod 16 -> conflict-free fragment loads
     constexpr int LC = 32 * NL;
     extern __shared__ __align__(16) unsigned char knn_smem[];
-    float2* xs = reinterpret_cast<float2*>(knn_smem);                    // [2][TC][DPF] {hi, lo} of the shifted coordinates
+    // [2][TC][DPF] float2 = {dim t4, dim t4 + 4} of one k-step (dims permuted so a B fragment is ONE 8-byte load),
+    // hi plane then lo plane
+    float2* xs = reinterpret_cast<float2*>(knn_smem);
     float* xn = reinterpret_cast<float*>(xs + 2 * kKnnTC * DPF);         // [2][TC] squared norms
     float* ldist = xn + 2 * kKnnTC;                                      // [Q][LC] screened values
     int* lidx = reinterpret_cast<int*>(ldist + (size_t)kKnnQ * LC);      // [Q][LC]
@@ -562,7 +564,12 @@ __global__ void __launch_bounds__(256, 2) knn_tf32_kernel(const double* __restri
             const double v = stg[k] - shift[k];
             sn += v * v;
             const float hi = __uint_as_float(knn_tf32((float)v));
-            if (k0s + k < k1s) dst[k0s + k] = make_float2(hi, __uint_as_float(knn_tf32((float)(v - (double)hi))));
+            if (k0s + k < k1s) {
+                const int kk = k0s + k;   // dimension kk -> k-step kk/8, slot kk%4, half (kk/4)%2
+                float* slot = reinterpret_cast<float*>(dst + (kk >> 3) * 8 + (kk & 3)) + ((kk >> 2) & 1);
+                slot[0] = hi;                                                   // hi plane
+                slot[8] = __uint_as_float(knn_tf32((float)(v - (double)hi)));   // lo plane: 4 float2 further
+            }
         }
         sn += __shfl_xor_sync(0xffffffffu, sn, 1);
         if (sh == 0) {
@@ -588,6 +595,7 @@ __global__ void __launch_bounds__(256, 2) knn_tf32_kernel(const double* __restri
             const int64_t jl = (ORDERED ? min(n, qi) : n) - c0;
             lim[s] = qi < M ? (int)max((int64_t)0, min(jl, (int64_t)kKnnTC)) : 0;
         }
+        const bool full = __all_sync(0xffffffffu, lim[0] == kKnnTC && lim[1] == kKnnTC);
         for (int cg = 0; cg < kKnnTC / 8; cg += 2) {
             float c[2][4];
 #pragma unroll
@@ -600,22 +608,27 @@ __global__ void __launch_bounds__(256, 2) knn_tf32_kernel(const double* __restri
             for (int ks = 0; ks < KS8; ++ks)
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
-                    const float2 b0 = xt[(8 * (cg + h) + g) * DPF + 8 * ks + t4];
-                    const float2 b1 = xt[(8 * (cg + h) + g) * DPF + 8 * ks + t4 + 4];
-                    const unsigned bh0 = __float_as_uint(b0.x), bl0 = __float_as_uint(b0.y);
-                    const unsigned bh1 = __float_as_uint(b1.x), bl1 = __float_as_uint(b1.y);
-                    knn_hmma(c[h], ah[ks], bh0, bh1);
-                    knn_hmma(c[h], ah[ks], bl0, bl1);
-                    knn_hmma(c[h], al[ks], bh0, bh1);
+                    const float2 bh = xt[(8 * (cg + h) + g) * DPF + 8 * ks + t4];       // {dim t4, dim t4 + 4}, hi
+                    const float2 bl = xt[(8 * (cg + h) + g) * DPF + 8 * ks + 4 + t4];   // the same two, lo
+                    knn_hmma(c[h], ah[ks], __float_as_uint(bh.x), __float_as_uint(bh.y));
+                    knn_hmma(c[h], ah[ks], __float_as_uint(bl.x), __float_as_uint(bl.y));
+                    knn_hmma(c[h], al[ks], __float_as_uint(bh.x), __float_as_uint(bh.y));
                 }
             bool anyhit = false;
+            if (full) {   // every candidate of the tile is admissible for every query of the warp: no index tests
 #pragma unroll
-            for (int h = 0; h < 2; ++h)
+                for (int h = 0; h < 2; ++h)
 #pragma unroll
-                for (int s = 0; s < 2; ++s) {
-                    const int jl0 = 8 * (cg + h) + 2 * t4;
-                    anyhit = anyhit || (c[h][2 * s] < thr[s] && jl0 < lim[s]) || (c[h][2 * s + 1] < thr[s] && jl0 + 1 < lim[s]);
-                }
+                    for (int s = 0; s < 2; ++s) anyhit = anyhit || fminf(c[h][2 * s], c[h][2 * s + 1]) < thr[s];
+            } else {
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+#pragma unroll
+                    for (int s = 0; s < 2; ++s) {
+                        const int jl0 = 8 * (cg + h) + 2 * t4;
+                        anyhit = anyhit || (c[h][2 * s] < thr[s] && jl0 < lim[s]) || (c[h][2 * s + 1] < thr[s] && jl0 + 1 < lim[s]);
+                    }
+            }
             if (!__any_sync(0xffffffffu, anyhit)) continue;
 #pragma unroll
             for (int h = 0; h < 2; ++h)
