@@ -508,7 +508,8 @@ __global__ void __launch_bounds__(256, 3) vecchia_small_kernel(VKern vk, VSmallA
     const int64_t t = (int64_t)blockIdx.x * W + w;
     if (t >= a.count) return;
     const int D = vk.D, Dp = D | 1;
-    double* xl = smem + (size_t)w * 32 * Dp;
+    double* xl = smem + (size_t)w * (32 * Dp + 64);
+    double* colb = xl + 32 * Dp;   // [2][32]: the current column of L, read back as broadcasts
     // block membership: PRED -> NN[t][0..nb) then the test point; train -> valid NN entries reversed (ascending,
     // the point itself last)
     int nv = 0;
@@ -547,7 +548,7 @@ __global__ void __launch_bounds__(256, 3) vecchia_small_kernel(VKern vk, VSmallA
                     const double df = xi[d] - xk[d];
                     dist += df * df;
                 }
-                v = exp(-dist);
+                v = exp_nonpos(-dist);
             } else {
                 double coef = 1.0, sr = 0.0;
                 for (int d = 0; d < D; ++d) {
@@ -555,7 +556,7 @@ __global__ void __launch_bounds__(256, 3) vecchia_small_kernel(VKern vk, VSmallA
                     coef *= 1.0 + kSqrt5 * r + (5.0 / 3.0) * (r * r);
                     sr += r;
                 }
-                v = coef * exp(-kSqrt5 * sr);
+                v = coef * exp_nonpos(-kSqrt5 * sr);
             }
             if (k == lane) v = 1.0 + nug;
         }
@@ -570,13 +571,16 @@ __global__ void __launch_bounds__(256, 3) vecchia_small_kernel(VKern vk, VSmallA
             const double rs = rsqrt(pj);
             const double lij = arow[j] * rs;          // l_ij for rows i >= j (sqrt(pj) on the diagonal)
             arow[j] = lij;
+            double* cb = colb + 32 * (j & 1);
+            cb[lane] = lij;                           // column j of L: one store, then broadcast loads
             const double wj = __shfl_sync(0xffffffffu, yacc, j) * rs;
             if (lane > j) yacc = fma(-lij, wj, yacc);
             else if (lane == j) yacc = wj;
-            if (j == b - 1) lll = __shfl_sync(0xffffffffu, lij, j);
+            __syncwarp();
+            if (j == b - 1) lll = cb[j];
 #pragma unroll
             for (int k = j + 1; k < 32; ++k)
-                if (k < b) arow[k] = fma(-lij, __shfl_sync(0xffffffffu, lij, k), arow[k]);
+                if (k < b) arow[k] = fma(-lij, cb[k], arow[k]);
         }
     }
     const double wl = __shfl_sync(0xffffffffu, yacc, b - 1);
@@ -594,11 +598,11 @@ __global__ void __launch_bounds__(256, 3) vecchia_small_kernel(VKern vk, VSmallA
 template <bool PRED>
 static int small_launch(const VKern& vk, const VSmallArgs& a, cudaStream_t st) {
     const int W = 8;
-    const size_t smem = (size_t)W * 32 * (vk.D | 1) * sizeof(double);
+    const size_t smem = (size_t)W * (32 * (vk.D | 1) + 64) * sizeof(double);
     static bool configured = false;
     if (!configured) {
         DGPB_CUDA_TRY(cudaFuncSetAttribute(vecchia_small_kernel<PRED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)((size_t)W * 32 * (kMaxDim | 1) * sizeof(double))));
+                                           (int)((size_t)W * (32 * (kMaxDim | 1) + 64) * sizeof(double))));
         configured = true;
     }
     vecchia_small_kernel<PRED><<<(unsigned)cdiv(a.count, W), W * 32, smem, st>>>(vk, a);
@@ -632,7 +636,7 @@ __global__ void __launch_bounds__(256, 2) vecchia_multi_kernel(VMultiArgs a) {
     const int64_t t = (int64_t)blockIdx.x * W + w;
     if (t >= a.M) return;
     const int D = a.D, Dp = D | 1;
-    double* xl = smem + (size_t)w * (32 * Dp + 32 * 33);
+    double* xl = smem + (size_t)w * (32 * Dp + 32 * 33 + 64);
     double* ds = xl + 32 * Dp;      // raw squared distances of the block, row stride 33
     int nv = 0;
     for (int c = lane; c < a.cols; c += 32) nv += a.NN[t * a.cols + c] >= 0;
@@ -659,6 +663,7 @@ __global__ void __launch_bounds__(256, 2) vecchia_multi_kernel(VMultiArgs a) {
         }
     }
     __syncwarp();
+    double* colb = ds + 32 * 33;   // [2][32]: the current column of L, read back as broadcasts
     for (int nb = 0; nb < a.B; ++nb) {
         const double il2 = a.inv_l2[nb], nug = a.nugget[nb];
         double yacc = src >= 0 ? a.Y[(int64_t)nb * a.n + src] : 0.0;
@@ -666,7 +671,7 @@ __global__ void __launch_bounds__(256, 2) vecchia_multi_kernel(VMultiArgs a) {
 #pragma unroll
         for (int k = 0; k < 32; ++k) {
             double v = 0.0;
-            if (k < b) v = (k == lane) ? 1.0 + nug : exp(-ds[lane * 33 + k] * il2);
+            if (k < b) v = (k == lane) ? 1.0 + nug : exp_nonpos(-ds[lane * 33 + k] * il2);
             arow[k] = v;
         }
         double lll = 1.0;
@@ -677,13 +682,16 @@ __global__ void __launch_bounds__(256, 2) vecchia_multi_kernel(VMultiArgs a) {
                 const double rs = rsqrt(pj);
                 const double lij = arow[j] * rs;
                 arow[j] = lij;
+                double* cb = colb + 32 * (j & 1);
+                cb[lane] = lij;                       // column j of L: one store, then broadcast loads
                 const double wj = __shfl_sync(0xffffffffu, yacc, j) * rs;
                 if (lane > j) yacc = fma(-lij, wj, yacc);
                 else if (lane == j) yacc = wj;
-                if (j == b - 1) lll = __shfl_sync(0xffffffffu, lij, j);
+                __syncwarp();
+                if (j == b - 1) lll = cb[j];
 #pragma unroll
                 for (int k = j + 1; k < 32; ++k)
-                    if (k < b) arow[k] = fma(-lij, __shfl_sync(0xffffffffu, lij, k), arow[k]);
+                    if (k < b) arow[k] = fma(-lij, cb[k], arow[k]);
             }
         }
         const double wl = __shfl_sync(0xffffffffu, yacc, b - 1);
@@ -936,11 +944,11 @@ int dgpb_gp_vecch_multi(const double* x, int64_t M, const double* w, const doubl
     a.mean = mean;
     a.var = var;
     const int W = 8;
-    const size_t smem = (size_t)W * (32 * ((int)D | 1) + 32 * 33) * sizeof(double);
+    const size_t smem = (size_t)W * (32 * ((int)D | 1) + 32 * 33 + 64) * sizeof(double);
     static bool configured = false;
     if (!configured) {
         DGPB_CUDA_TRY(cudaFuncSetAttribute(vecchia_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)((size_t)W * (32 * (kMaxDim | 1) + 32 * 33) * sizeof(double))));
+                                           (int)((size_t)W * (32 * (kMaxDim | 1) + 32 * 33 + 64) * sizeof(double))));
         configured = true;
     }
     vecchia_multi_kernel<<<(unsigned)cdiv(M, W), W * 32, smem, (cudaStream_t)stream>>>(a);
