@@ -794,6 +794,37 @@ def test_vecchia_dgp_public_api_roundtrip(tmp_path):
     assert np.array_equal(mu, mu2) and np.array_equal(var, var2)
 
 
+def test_knn_properties_at_config4_scale():
+    """BASELINE config-4 sized neighbour search (n = 100k training points, d = 10, m = 25): every row is sorted by
+    distance, sampled rows equal a numpy brute-force search bit for bit, the ordered search only returns earlier
+    points in descending index order, and no query needed a different answer from the scalar exact kernel."""
+    from dgp_b200 import vecchia as V
+
+    rng = np.random.default_rng(77)
+    n, M, d, m = 100000, 20000, 10, 25
+    x, q = rng.uniform(0, 1, (n, d)), rng.uniform(0, 1, (M, d))
+    NN = V.get_pred_nn(q, x, m)
+    assert NN.shape == (M, m) and NN.min() >= 0 and NN.max() < n
+    rows = rng.choice(M, 48, replace=False)
+    for r in rows:
+        d2 = np.zeros(n)
+        for k in range(d):          # the reference arithmetic: ascending dimension, no FMA
+            d2 = d2 + (q[r, k] - x[:, k]) * (q[r, k] - x[:, k])
+        order = np.lexsort((np.arange(n), d2))[:m]
+        assert np.array_equal(NN[r], order), r
+        assert np.all(np.diff(d2[NN[r]]) >= 0)
+    sub = rng.choice(M, 2000, replace=False)
+    dsub = ((q[sub, None, :] - x[NN[sub]]) ** 2).sum(-1)
+    assert np.all(np.diff(dsub, axis=1) >= -1e-15)
+    NNo = V.nn(x[:30000], m)
+    assert NNo.shape == (30000, m + 1) and np.array_equal(NNo[:, 0], np.arange(30000))
+    body = NNo[:, 1:]
+    assert np.all((body < np.arange(30000)[:, None]) | (body == -1))
+    valid = body >= 0
+    assert np.array_equal(valid.sum(1), np.minimum(np.arange(30000), m))
+    assert np.all((np.diff(body, axis=1) < 0) | ~valid[:, 1:])
+
+
 def test_property_checks_at_baseline_scale():
     """Size-independent properties at a BASELINE-sized node (n=2000, D=10): the factor reproduces K, the
     inverse is an inverse, log-likelihood agrees with an independent FP64 computation (torch/cuSOLVER used
