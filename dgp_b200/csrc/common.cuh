@@ -81,6 +81,7 @@ inline int64_t cdiv(int64_t x, int64_t m) { return (x + m - 1) / m; }
 // ---------------------------------------------------------------------------------------------
 enum Slot : int {
     SLOT_T = 0,       // factorisation matrices (batched)
+    SLOT_T2,          // second set: the next ESS wave is assembled while the current one is factored
     SLOT_DIAG,        // diag(L) per batch entry
     SLOT_OUT,         // small result scalars
     SLOT_INFO,        // int info flags

@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(256) kbuild_kernel(KernelDev kd, double* __res
             } else if (gi >= n) {
                 v = 0.0;
             } else {
-                v = kd.kind == DGPB_SEXP ? exp(-acc[r][c]) : acc[r][c] * exp(-kSqrt5 * sr[r][c]);
+                v = kd.kind == DGPB_SEXP ? exp_nonpos(-acc[r][c]) : acc[r][c] * exp_nonpos(-kSqrt5 * sr[r][c]);
             }
             if (MIRROR) {
                 if (gi < n) {
@@ -588,10 +588,10 @@ int launch_trmv(const double* T, int64_t ld, int n, double sqrt_scale, const dou
     return DGPB_OK;
 }
 
-int setup_batch(Workspace* ws, const Geom& g, int B, Batch* bt, double** out_dev) {
+int setup_batch_slot(Workspace* ws, int tslot, const Geom& g, int B, Batch* bt, double** out_dev) {
     DGPB_REQUIRE(B >= 1 && B <= MAXB, "batch size out of range");
     void *pT, *pD, *pO, *pI;
-    DGPB_TRY(ws->reserve(SLOT_T, g.elems() * sizeof(double) * B, &pT));
+    DGPB_TRY(ws->reserve(tslot ? SLOT_T2 : SLOT_T, g.elems() * sizeof(double) * B, &pT));
     DGPB_TRY(ws->reserve(SLOT_DIAG, diag_elems(g) * sizeof(double) * B, &pD));
     DGPB_TRY(ws->reserve(SLOT_OUT, sizeof(double) * kOutDoubles, &pO));
     DGPB_TRY(ws->reserve(SLOT_INFO, sizeof(int) * MAXB, &pI));
@@ -604,7 +604,22 @@ int setup_batch(Workspace* ws, const Geom& g, int B, Batch* bt, double** out_dev
     return DGPB_OK;
 }
 
-int assemble(const Geom& g, const KernelDev* kds, const double* const* ys, const Batch& bt, int B, cudaStream_t st) {
+int setup_batch(Workspace* ws, const Geom& g, int B, Batch* bt, double** out_dev) {
+    return setup_batch_slot(ws, 0, g, B, bt, out_dev);
+}
+
+// Grow both T sets and the side buffers to `B` matrices NOW, so that no later setup_batch_slot call of the same
+// sequence reallocates a buffer that kernels in flight still use.
+int reserve_batches(Workspace* ws, const Geom& g, int B) {
+    Batch bt;
+    double* out;
+    DGPB_TRY(setup_batch_slot(ws, 0, g, B, &bt, &out));
+    DGPB_TRY(setup_batch_slot(ws, 1, g, B, &bt, &out));
+    return DGPB_OK;
+}
+
+int assemble_matrices(const Geom& g, const KernelDev* kds, const double* const* ys, const Batch& bt, int B,
+                      cudaStream_t st) {
     const int nt = g.npad / 64;
     for (int b = 0; b < B; ++b) {
         if (g.aug) {
@@ -618,7 +633,20 @@ int assemble(const Geom& g, const KernelDev* kds, const double* const* ys, const
                                                                    g.aug ? 1 : 0);
         DGPB_LAUNCHED();
     }
+    return DGPB_OK;
+}
+
+int assemble(const Geom& g, const KernelDev* kds, const double* const* ys, const Batch& bt, int B, cudaStream_t st) {
+    DGPB_TRY(assemble_matrices(g, kds, ys, bt, B, st));
     DGPB_CUDA_TRY(cudaMemsetAsync(bt.info, 0, sizeof(int) * MAXB, st));
+    return DGPB_OK;
+}
+
+// factorise + reduce a batch whose matrices are already assembled (info flags cleared here)
+int factor_reduce(const Geom& g, const Batch& bt, int B, const ScaleArgs& sa, double* out, cudaStream_t st) {
+    DGPB_CUDA_TRY(cudaMemsetAsync(bt.info, 0, sizeof(int) * MAXB, st));
+    DGPB_TRY(factorize(g, bt, B, st));
+    DGPB_TRY(reduce_logdet_quad(g, bt, B, sa, out, st));
     return DGPB_OK;
 }
 
@@ -651,15 +679,20 @@ static std::mutex g_prof_mutex;  // the M-step issues factorisations from severa
 //   bulk_k   needs panel_k (event) and bulk_{k-1} (side-stream order);
 //   narrow_k needs panel_k (main-stream order) and bulk_{k-1} (event: both write columns [k1, k1+64)).
 struct LookAhead {
-    cudaStream_t side = nullptr;
+    cudaStream_t side = nullptr;   // bulk updates, lowest priority
+    cudaStream_t crit = nullptr;   // panels, narrow / inner / look-ahead updates: the critical path, highest priority
     std::vector<cudaEvent_t> ev;
     int init(size_t need) {
         if (!side) {
-            // lowest priority: CTAs of the critical-path kernels on the caller's stream are scheduled ahead of
-            // queued bulk-update CTAs whenever an SM slot frees up
+            // The caller's stream (torch's current stream) has priority 0, which is the LOWEST a stream can have, so
+            // a "low-priority" side stream next to it is no different: with equal priorities a kernel launched
+            // later is only dispatched once the earlier grid has no CTA left to hand out, and every panel would
+            // wait behind the whole bulk grid.  The critical path therefore runs on its own highest-priority
+            // stream (forked from / joined to the caller's stream): its CTAs take the next SM slot that frees up.
             int lo_pri = 0, hi_pri = 0;
             DGPB_CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri));
             DGPB_CUDA_TRY(cudaStreamCreateWithPriority(&side, cudaStreamNonBlocking, lo_pri));
+            DGPB_CUDA_TRY(cudaStreamCreateWithPriority(&crit, cudaStreamNonBlocking, hi_pri));
         }
         while (ev.size() < need) {
             cudaEvent_t e;
@@ -700,6 +733,7 @@ static int launch_update(const Batch& bt, int B, int64_t ld, int k0, int K, int 
 static int g_hb = 512;
 static int g_hb_min_w = 2560;
 static int g_hb_graded = 1;
+static int g_crit_stream = 1;   // critical path of the factorisation on its own highest-priority stream
 
 // Right-looking factorisation on two levels.
 //   HYPER-BLOCK [h0, h1) of up to `g_hb` columns: factored by super-steps of two 64-column panels
@@ -714,13 +748,15 @@ static int g_hb_graded = 1;
 // step, and a longer inner phase would only lengthen it.
 // Dependencies: bulk_h needs the panels of h (event) and bulk_{h-1} (side-stream order); look-ahead_h needs
 // bulk_{h-1} (event: both write columns [h1, h1 + next width)).
-int factorize(const Geom& g, const Batch& bt, int B, cudaStream_t st) {
+int factorize(const Geom& g, const Batch& bt, int B, cudaStream_t caller) {
     DGPB_TRY(configure_once());
-    DGPB_TRY(g_la.init(2 * (size_t)(g.npad / (2 * NB) + 2) + 4));
+    DGPB_TRY(g_la.init(2 * (size_t)(g.npad / (2 * NB) + 2) + 6));
     cudaStream_t side = g_la.side;
+    cudaStream_t st = g_crit_stream ? g_la.crit : caller;   // the stream of the critical path
     int evi = 0;
-    DGPB_CUDA_TRY(cudaEventRecord(g_la.ev[evi], st));
+    DGPB_CUDA_TRY(cudaEventRecord(g_la.ev[evi], caller));
     DGPB_CUDA_TRY(cudaStreamWaitEvent(side, g_la.ev[evi], 0));
+    if (st != caller) DGPB_CUDA_TRY(cudaStreamWaitEvent(st, g_la.ev[evi], 0));
     ++evi;
     auto width_at = [&](int h0) {
         if (h0 >= g.npad) return 0;
@@ -788,7 +824,12 @@ int factorize(const Geom& g, const Batch& bt, int B, cudaStream_t st) {
         hw = hw_next;
     }
     DGPB_CUDA_TRY(cudaEventRecord(g_la.ev[evi], side));
-    DGPB_CUDA_TRY(cudaStreamWaitEvent(st, g_la.ev[evi], 0));
+    DGPB_CUDA_TRY(cudaStreamWaitEvent(caller, g_la.ev[evi], 0));
+    ++evi;
+    if (st != caller) {
+        DGPB_CUDA_TRY(cudaEventRecord(g_la.ev[evi], st));
+        DGPB_CUDA_TRY(cudaStreamWaitEvent(caller, g_la.ev[evi], 0));
+    }
     return DGPB_OK;
 }
 
@@ -1122,6 +1163,8 @@ int dgpb_tune(const char* key, int value) {
     } else if (k == "ess_batch") {
         DGPB_REQUIRE(value >= 0 && value <= MAXB, "ess_batch out of range");
         g_ess_target_b = value;
+    } else if (k == "ess_prefetch") {
+        g_ess_prefetch = value != 0;
     } else if (k == "ess_trsv") {
         g_ess_cached_threshold = value != 0;
     } else if (k == "linkgp_matern_tab") {
@@ -1132,6 +1175,8 @@ int dgpb_tune(const char* key, int value) {
         vecchia_set_small(value);
     } else if (k == "knn_mma") {
         knn_set_mma(value);
+    } else if (k == "crit_stream") {
+        g_crit_stream = value != 0;
     } else if (k == "hb_graded") {
         g_hb_graded = value != 0;
     } else {

@@ -58,8 +58,14 @@ int restore_diag_blocks(const Geom& g, const Batch& bt, int B, cudaStream_t st);
 // nu = sqrt_scale * L z with L the lower factor stored in T
 int launch_trmv(const double* T, int64_t ld, int n, double sqrt_scale, const double* z, double* nu, cudaStream_t st);
 
-// allocate/partition workspace buffers for a batch
+// allocate/partition workspace buffers for a batch (tslot selects one of the two T sets)
 int setup_batch(Workspace* ws, const Geom& g, int B, Batch* bt, double** out_dev);
+int setup_batch_slot(Workspace* ws, int tslot, const Geom& g, int B, Batch* bt, double** out_dev);
+int reserve_batches(Workspace* ws, const Geom& g, int B);
+// assemble without touching the info flags / factorise + reduce an assembled batch (ESS wave pipeline, ess.cu)
+int assemble_matrices(const Geom& g, const KernelDev* kds, const double* const* ys, const Batch& bt, int B,
+                      cudaStream_t st);
+int factor_reduce(const Geom& g, const Batch& bt, int B, const ScaleArgs& sa, double* out, cudaStream_t st);
 
 // log-likelihoods of B dense nodes: out_dev[b*4 + {0,1,2}] = logdet K, quad (y'K^-1y), sigma2
 int loglik_batch_device(Workspace* ws, const KernelDev* kds, const double* const* ys, const ScaleArgs& sa, int B,
@@ -68,5 +74,6 @@ int loglik_batch_device(Workspace* ws, const KernelDev* kds, const double* const
 // matrices per speculative ESS wave (ess.cu)
 extern int g_ess_target_b;
 extern int g_ess_cached_threshold;
+extern int g_ess_prefetch;
 
 }  // namespace dgpb

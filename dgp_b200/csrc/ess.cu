@@ -255,6 +255,7 @@ namespace dgpb {
 
 int g_ess_target_b = 8;  // matrices per speculative wave (dgpb_tune "ess_batch"); 0/1 = one proposal at a time
 int g_ess_cached_threshold = 1;  // threshold from cached factors by a triangular solve (dgpb_tune "ess_trsv")
+int g_ess_prefetch = 1;          // assemble the next wave while the current one is factored (dgpb_tune "ess_prefetch")
 
 // |L^-1 y|^2 for a cached factor L (T layout, diagonal blocks restored): forward substitution by ONE CTA per matrix,
 // x kept in shared memory.  Per 64-row block the eight warps form y_i - sum_j L_ij x_j for eight rows each
@@ -379,28 +380,50 @@ static int cached_threshold(Workspace* ws, const dgpb_node* nodes, int U, int64_
 // factorisation, matrix slot of (item i, node u) = i * U + u.  pd[i] = 0 if one of the item's matrices is not
 // positive definite (bad_node[i] = which).  The caller decides what an indefinite item means: the reference
 // only ever evaluates items up to the first accepted one.
-static int dense_items_loglik(Workspace* ws, const dgpb_node* nodes, int U, int64_t n, const double* const* srcs,
-                              int nitems, double* sums, int* pd, int* bad_node, Batch* bt_out, Geom* g_out,
-                              double* logdets, cudaStream_t st) {
+// Step 1: assemble the matrices of the items into T set `tslot` (kernel matrices + y rows) on stream `st`.
+static int dense_items_assemble(Workspace* ws, int tslot, const dgpb_node* nodes, int U, int64_t n,
+                                const double* const* srcs, int nitems, Batch* bt_out, Geom* g_out, cudaStream_t st) {
     const int B = nitems * U;
     DGPB_REQUIRE(B >= 1 && B <= MAXB, "wave does not fit one batch");
     KernelDev kds[MAXB];
     const double* ys[MAXB];
-    ScaleArgs sa;
     for (int i = 0; i < nitems; ++i)
         for (int u = 0; u < U; ++u) {
             const int b = i * U + u;
             DGPB_TRY(make_kernel_dev(&nodes[u], n, srcs[i], &kds[b]));
             ys[b] = nodes[u].output;
-            sa.scale[b] = nodes[u].scale;
-            sa.est[b] = 0;
         }
+    *g_out = make_geom(n, false);
     double* outd;
-    DGPB_TRY(loglik_batch_device(ws, kds, ys, sa, B, n, bt_out, g_out, &outd, st));
+    DGPB_TRY(setup_batch_slot(ws, tslot, *g_out, B, bt_out, &outd));
+    DGPB_TRY(assemble_matrices(*g_out, kds, ys, *bt_out, B, st));
+    return DGPB_OK;
+}
+
+// Step 2: factorise the assembled batch, reduce, launch the device-to-host copies of the results (no host sync).
+static int dense_items_factor(Workspace* ws, const dgpb_node* nodes, int U, int nitems, const Batch& bt, const Geom& g,
+                              cudaStream_t st) {
+    const int B = nitems * U;
+    ScaleArgs sa;
+    for (int b = 0; b < B; ++b) {
+        sa.scale[b] = nodes[b % U].scale;
+        sa.est[b] = 0;
+    }
+    void* pO;
+    DGPB_TRY(ws->reserve(SLOT_OUT, sizeof(double) * kOutDoubles, &pO));
+    double* outd = (double*)pO;
+    DGPB_TRY(factor_reduce(g, bt, B, sa, outd, st));
     int* info_host = reinterpret_cast<int*>(ws->pinned + 2048);
     DGPB_CUDA_TRY(cudaMemcpyAsync(ws->pinned, outd, sizeof(double) * 4 * B, cudaMemcpyDeviceToHost, st));
-    DGPB_CUDA_TRY(cudaMemcpyAsync(info_host, bt_out->info, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
+    DGPB_CUDA_TRY(cudaMemcpyAsync(info_host, bt.info, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
+    return DGPB_OK;
+}
+
+// Step 3: wait for the results and form the per-item sums.
+static int dense_items_fetch(Workspace* ws, const dgpb_node* nodes, int U, int64_t n, int nitems, double* sums, int* pd,
+                             int* bad_node, double* logdets, cudaStream_t st) {
     DGPB_CUDA_TRY(cudaStreamSynchronize(st));
+    const int* info_host = reinterpret_cast<const int*>(ws->pinned + 2048);
     for (int i = 0; i < nitems; ++i) {
         double s = 0.0;
         pd[i] = 1;
@@ -421,6 +444,9 @@ static int dense_items_loglik(Workspace* ws, const dgpb_node* nodes, int U, int6
 }
 
 }  // namespace dgpb
+
+// last speculative-assembly event of this thread: the next call waits for it before it reuses the buffers
+static thread_local cudaEvent_t g_pre_done_guard = nullptr;
 
 // The angles ESS will try are known in advance: a rejection is the only branch of the bracket rule
 // (imputation.py:111-119), so theta_{k+1} depends on theta_k and the next uniform, never on a likelihood value.
@@ -448,10 +474,11 @@ extern "C" int dgpb_ess_block_cached(dgpb_ws* ws, const dgpb_node* targets, int 
     if (all_dense && n_uppers <= MAXB) cap = std::max(1, std::min(kMaxWave, std::min(g_ess_target_b, (int)MAXB) / n_uppers));
     const bool batched = all_dense && n_uppers <= MAXB;
 
+    if (g_pre_done_guard) DGPB_CUDA_TRY(cudaStreamWaitEvent(st, g_pre_done_guard, 0));  // see the wave pipeline below
     void *pnu, *pprop;
     const size_t layer_elems = (size_t)layer_width * n;
     DGPB_TRY(ws->reserve(SLOT_NU, sizeof(double) * (size_t)n_targets * n, &pnu));
-    DGPB_TRY(ws->reserve(SLOT_PROP, sizeof(double) * layer_elems * cap, &pprop));
+    DGPB_TRY(ws->reserve(SLOT_PROP, sizeof(double) * layer_elems * cap * 2, &pprop));
     double* nuv = (double*)pnu;
     double* prop = (double*)pprop;
 
@@ -479,31 +506,64 @@ extern "C" int dgpb_ess_block_cached(dgpb_ws* ws, const dgpb_node* targets, int 
     double tmin = theta - 2.0 * M_PI, tmax = theta;
 
     // rows of the layer that are not being updated are shared by every proposal
-    for (int s = 0; s < cap; ++s)
+    for (int s = 0; s < 2 * cap; ++s)
         DGPB_CUDA_TRY(cudaMemcpyAsync(prop + s * layer_elems, layer_out, sizeof(double) * layer_elems,
                                       cudaMemcpyDeviceToDevice, st));
     int nprop = 0;
-    while (true) {
-        // ---- candidate angles of this wave (each one assumes every earlier one was rejected)
-        double thetas[kMaxWave];
-        const int S = std::max(1, std::min(cap, 1 + (nu - ui)));
-        thetas[0] = theta;
-        {
-            double lmin = tmin, lmax = tmax;
-            for (int s = 1; s < S; ++s) {
-                if (thetas[s - 1] < 0.0) lmin = thetas[s - 1]; else lmax = thetas[s - 1];  // imputation.py:115-118
-                thetas[s] = lmin + (lmax - lmin) * u_host[ui + s - 1];                     // imputation.py:119
-            }
+    // Wave pipeline (dense upper nodes): while wave k is being factored, the matrices of wave k + 1 -- whose angles
+    // are known under the assumption that all of wave k is rejected, true nine times out of ten -- are proposed
+    // and assembled into the other T set on a low-priority stream, so the next factorisation starts on ready
+    // matrices.  An accepted wave simply leaves the speculative set unused.
+    static thread_local cudaStream_t pre_stream = nullptr;
+    static thread_local cudaEvent_t pre_done = nullptr, pre_go = nullptr;
+    if (batched && !pre_stream) {
+        int lo_pri = 0, hi_pri = 0;
+        DGPB_CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri));
+        DGPB_CUDA_TRY(cudaStreamCreateWithPriority(&pre_stream, cudaStreamNonBlocking, lo_pri));
+        DGPB_CUDA_TRY(cudaEventCreateWithFlags(&pre_done, cudaEventDisableTiming));
+        DGPB_CUDA_TRY(cudaEventCreateWithFlags(&pre_go, cudaEventDisableTiming));
+        g_pre_done_guard = pre_done;
+    }
+    if (batched) {
+        DGPB_TRY(reserve_batches(ws, make_geom(n, false), std::min((int)MAXB, (cap + 1) * n_uppers)));
+        // everything queued so far (prior draws, layer copies) is what the speculative stream must wait for;
+        // nothing the waves read is written again before an acceptance
+        DGPB_CUDA_TRY(cudaEventRecord(pre_go, st));
+    }
+    auto plan_wave = [&](double th0, double lmin, double lmax, int uidx, double* out_thetas) {
+        const int S = std::max(1, std::min(cap, 1 + (nu - uidx)));
+        out_thetas[0] = th0;
+        for (int s = 1; s < S; ++s) {
+            if (out_thetas[s - 1] < 0.0) lmin = out_thetas[s - 1]; else lmax = out_thetas[s - 1];  // imputation.py:115-118
+            out_thetas[s] = lmin + (lmax - lmin) * u_host[uidx + s - 1];                             // imputation.py:119
         }
+        return S;
+    };
+    auto launch_proposals = [&](const double* th, int S, double* pbuf, cudaStream_t s2) -> int {
         for (int s = 0; s < S; ++s) {
-            const double c = cos(thetas[s]), sn = sin(thetas[s]);
+            const double c = cos(th[s]), sn = sin(th[s]);
             for (int k = 0; k < n_targets; ++k) {
                 const int64_t row = target_rows_host[k];
-                propose_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(prop + s * layer_elems + row * n, layer_out + row * n,
+                propose_kernel<<<(unsigned)cdiv(n, 256), 256, 0, s2>>>(pbuf + s * layer_elems + row * n, layer_out + row * n,
                                                                       nuv + (int64_t)k * n, c, sn, n);
                 DGPB_LAUNCHED();
             }
         }
+        return DGPB_OK;
+    };
+    int wave = 0;               // parity selects the T set and the half of the proposal buffer
+    bool pre_ready = false;     // the current wave was assembled ahead of time
+    int pre_S = 0;
+    double pre_thetas[kMaxWave];
+    Batch pre_bt;
+    Geom pre_g;
+    while (true) {
+        // ---- candidate angles of this wave (each one assumes every earlier one was rejected)
+        double thetas[kMaxWave];
+        const int S = plan_wave(theta, tmin, tmax, ui, thetas);
+        double* pcur = prop + (size_t)(wave & 1) * cap * layer_elems;
+        bool use_pre = pre_ready && pre_S == S;
+        for (int s = 0; use_pre && s < S; ++s) use_pre = pre_thetas[s] == thetas[s];
         // ---- likelihoods of the wave
         double sums[kMaxWave + 1];
         double wave_logdets[MAXB];
@@ -513,13 +573,45 @@ extern "C" int dgpb_ess_block_cached(dgpb_ws* ws, const dgpb_node* targets, int 
         DenseBatchInfo info;
         int first = 0;  // index of candidate 0 in sums[]
         if (batched) {
-            const double* srcs[kMaxWave + 1];
-            int ni = 0;
-            if (thr_pending) srcs[ni++] = nullptr;
-            first = ni;
-            for (int s = 0; s < S; ++s) srcs[ni++] = prop + s * layer_elems;
-            DGPB_TRY(dense_items_loglik(ws, uppers, n_uppers, n, srcs, ni, sums, pd, bad, &bt, &g, wave_logdets, st));
-            if (thr_pending) {
+            int ni = S;
+            if (use_pre) {
+                bt = pre_bt;
+                g = pre_g;
+                DGPB_CUDA_TRY(cudaStreamWaitEvent(st, pre_done, 0));
+            } else {
+                if (pre_ready) DGPB_CUDA_TRY(cudaStreamWaitEvent(st, pre_done, 0));  // stale speculative set: let it drain
+                DGPB_TRY(launch_proposals(thetas, S, pcur, st));
+                const double* srcs[kMaxWave + 1];
+                ni = 0;
+                if (thr_pending) srcs[ni++] = nullptr;
+                first = ni;
+                for (int s = 0; s < S; ++s) srcs[ni++] = pcur + s * layer_elems;
+                DGPB_TRY(dense_items_assemble(ws, wave & 1, uppers, n_uppers, n, srcs, ni, &bt, &g, st));
+            }
+            pre_ready = false;
+            DGPB_TRY(dense_items_factor(ws, uppers, n_uppers, ni, bt, g, st));
+            // ---- speculate: assemble the next wave while this one is being factored
+            {
+                double lmin = tmin, lmax = tmax;
+                for (int s = 0; s < S; ++s)
+                    if (thetas[s] < 0.0) lmin = thetas[s]; else lmax = thetas[s];
+                const int ui_next = ui + S;   // S rejections consume S uniforms (the last one draws the next first angle)
+                if (g_ess_prefetch && ui_next <= nu && ui_next >= 1) {
+                    const double th_next = lmin + (lmax - lmin) * u_host[ui_next - 1];
+                    pre_S = plan_wave(th_next, lmin, lmax, ui_next, pre_thetas);
+                    double* pnext = prop + (size_t)((wave + 1) & 1) * cap * layer_elems;
+                    DGPB_CUDA_TRY(cudaStreamWaitEvent(pre_stream, pre_go, 0));  // the layer image and the prior draws exist
+                    DGPB_TRY(launch_proposals(pre_thetas, pre_S, pnext, pre_stream));
+                    const double* srcs2[kMaxWave];
+                    for (int s = 0; s < pre_S; ++s) srcs2[s] = pnext + s * layer_elems;
+                    DGPB_TRY(dense_items_assemble(ws, (wave + 1) & 1, uppers, n_uppers, n, srcs2, pre_S, &pre_bt, &pre_g,
+                                                  pre_stream));
+                    DGPB_CUDA_TRY(cudaEventRecord(pre_done, pre_stream));
+                    pre_ready = true;
+                }
+            }
+            DGPB_TRY(dense_items_fetch(ws, uppers, n_uppers, n, ni, sums, pd, bad, wave_logdets, st));
+            if (first == 1) {
                 if (!pd[0]) {
                     set_error("covariance of upper node %d is not positive definite", bad[0]);
                     return DGPB_NOT_PD;
@@ -528,9 +620,11 @@ extern "C" int dgpb_ess_block_cached(dgpb_ws* ws, const dgpb_node* targets, int 
                 thr_pending = false;
             }
         } else {
-            DGPB_TRY(nodes_loglik(ws, uppers, n_uppers, n, prop, &sums[0], st, &info));
+            DGPB_TRY(launch_proposals(thetas, S, pcur, st));
+            DGPB_TRY(nodes_loglik(ws, uppers, n_uppers, n, pcur, &sums[0], st, &info));
             pd[0] = 1;
         }
+        ++wave;
         // ---- replay the one-at-a-time decisions over the wave
         int accepted = -1;
         for (int s = 0; s < S; ++s) {
@@ -549,7 +643,7 @@ extern "C" int dgpb_ess_block_cached(dgpb_ws* ws, const dgpb_node* targets, int 
             if (s + 1 < S) ++ui;  // the uniform that produced thetas[s + 1]
         }
         if (accepted >= 0) {
-            const double* pa = prop + accepted * layer_elems;
+            const double* pa = pcur + accepted * layer_elems;
             for (int k = 0; k < n_targets; ++k) {
                 const int64_t row = target_rows_host[k];
                 DGPB_CUDA_TRY(cudaMemcpyAsync(layer_out + row * n, pa + row * n, sizeof(double) * n,

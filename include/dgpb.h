@@ -247,7 +247,8 @@ int dgpb_profile_read(double* out_host);
 int dgpb_probe_factorize(dgpb_ws* ws, int64_t n, int B, int aug, int reps, double* out_host);
 /* development/benchmark tunables of the blocked factorisation: "hb" (hyper-block width, multiple of 128),
  * "hb_min_w" (smallest remaining window factored with hyper-blocks), "hb_graded" (0/1: ramp the first hyper-blocks
- * 128, 256, 512), and of the ESS loop: "ess_batch" (matrices per speculative wave; <= 1 = one proposal at a time), "ess_trsv" (1 = threshold of a block
+ * 128, 256, 512), and of the ESS loop: "ess_batch" (matrices per speculative wave; <= 1 = one proposal at a time), "ess_prefetch" (1 = the next wave is proposed and assembled while the current one is
+ * factored), "ess_trsv" (1 = threshold of a block
  * update from cached factors by a triangular solve when only the upper nodes' outputs moved),
  * and of the neighbour search: "knn_mma" (3 = split-TF32 tensor-core screen + exact FP64 ranking [default], 1 = FP64 DMMA screen, 0 = scalar
  * exact kernel),

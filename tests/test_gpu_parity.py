@@ -523,22 +523,25 @@ def _load_layers(g, prefix, widths, name, vecch):
     return layers
 
 
-@pytest.mark.parametrize("ess_batch,ess_trsv", [(8, 1), (1, 1), (3, 0), (32, 1), (8, 0)])
-def test_ess_replay_identical_decisions(golden_ess, ess_batch, ess_trsv):
+@pytest.mark.parametrize("ess_batch,ess_trsv,ess_prefetch", [(8, 1, 1), (1, 1, 1), (3, 0, 1), (32, 1, 0), (8, 0, 0)])
+def test_ess_replay_identical_decisions(golden_ess, ess_batch, ess_trsv, ess_prefetch):
     """Replays the reference's ESS sweeps with its own normal / uniform draws.  `ess_batch` is the size of the
     speculative proposal wave (1 = one proposal at a time), `ess_trsv` switches the threshold-by-triangular-solve
-    shortcut (cached factors of upper nodes whose inputs did not move): every setting must consume exactly the
+    shortcut (cached factors of upper nodes whose inputs did not move), `ess_prefetch` the speculative assembly of
+    the next wave during the current factorisation: every setting must consume exactly the
     reference's uniforms and try exactly its angles."""
     from dgp_b200 import _lib as L
     from dgp_b200.imputation import _DeviceLayers
 
     L.check(L.load().dgpb_tune(b"ess_batch", ess_batch))
     L.check(L.load().dgpb_tune(b"ess_trsv", ess_trsv))
+    L.check(L.load().dgpb_tune(b"ess_prefetch", ess_prefetch))
     try:
         _ess_replay(golden_ess, _DeviceLayers)
     finally:
         L.check(L.load().dgpb_tune(b"ess_batch", 8))
         L.check(L.load().dgpb_tune(b"ess_trsv", 1))
+        L.check(L.load().dgpb_tune(b"ess_prefetch", 1))
 
 
 def _ess_replay(golden_ess, _DeviceLayers):
