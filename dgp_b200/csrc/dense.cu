@@ -656,6 +656,7 @@ struct UpdateProfiler {
     std::vector<cudaEvent_t> ev;   // pairs
     int used = 0;                  // events in flight
     double ms = 0.0, launches = 0.0, flops = 0.0;
+    double total_flops = 0.0;      // n^3/3 (n^3 augmented) per matrix of every factorisation while profiling
     cudaStream_t last = nullptr;
     int drain() {
         if (used == 0) return DGPB_OK;
@@ -750,6 +751,11 @@ static int g_crit_stream = 1;   // critical path of the factorisation on its own
 // bulk_{h-1} (event: both write columns [h1, h1 + next width)).
 int factorize(const Geom& g, const Batch& bt, int B, cudaStream_t caller) {
     DGPB_TRY(configure_once());
+    if (g_prof.on) {
+        std::lock_guard<std::mutex> lock(g_prof_mutex);
+        const double nn = (double)g.n;
+        g_prof.total_flops += (double)B * nn * nn * nn * (g.aug ? 1.0 : 1.0 / 3.0);
+    }
     DGPB_TRY(g_la.init(2 * (size_t)(g.npad / (2 * NB) + 2) + 6));
     cudaStream_t side = g_la.side;
     cudaStream_t st = g_crit_stream ? g_la.crit : caller;   // the stream of the critical path
@@ -1193,7 +1199,7 @@ int dgpb_profile(int on) {
     }
     if (on) {
         g_prof.used = 0;
-        g_prof.ms = g_prof.launches = g_prof.flops = 0.0;
+        g_prof.ms = g_prof.launches = g_prof.flops = g_prof.total_flops = 0.0;
     } else {
         DGPB_TRY(g_prof.drain());
     }
@@ -1208,7 +1214,7 @@ int dgpb_profile_read(double* out_host) {
     out_host[0] = g_prof.ms;
     out_host[1] = g_prof.launches;
     out_host[2] = g_prof.flops;
-    out_host[3] = 0.0;
+    out_host[3] = g_prof.total_flops;
     return DGPB_OK;
 }
 
