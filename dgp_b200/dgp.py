@@ -39,6 +39,8 @@ except Exception:  # pragma: no cover
 
 
 _tls = threading.local()
+_MSTEP_POOL = None      # persistent optimiser threads of the batched M-step
+_MSTEP_POOL_SIZE = 0
 
 
 class _GradBatcher:
@@ -333,9 +335,23 @@ class dgp:
                 kernel._batcher = None
                 batcher.retire()
 
-        with ThreadPoolExecutor(max_workers=len(dense)) as pool:
-            for fut in [pool.submit(work, item) for item in dense]:
+        # one long-lived pool: the library keeps per-thread CUDA streams and events (look-ahead streams of the
+        # factorisation), so the optimiser threads must not be re-created every iteration
+        global _MSTEP_POOL, _MSTEP_POOL_SIZE
+        if _MSTEP_POOL is None or _MSTEP_POOL_SIZE < len(dense):
+            if _MSTEP_POOL is not None:
+                _MSTEP_POOL.shutdown(wait=True)
+            _MSTEP_POOL_SIZE = max(len(dense), _MSTEP_POOL_SIZE)
+            _MSTEP_POOL = ThreadPoolExecutor(max_workers=_MSTEP_POOL_SIZE, thread_name_prefix="dgpb-mstep")
+        futures = [_MSTEP_POOL.submit(work, item) for item in dense]
+        errors = []
+        for fut in futures:   # wait for every optimiser before reporting a failure (dgp.train restarts on LinAlgError)
+            try:
                 fut.result()
+            except BaseException as exc:  # noqa: BLE001
+                errors.append(exc)
+        if errors:
+            raise errors[0]
 
     def ptrain(self, *args, **kwargs):
         raise NotImplementedError("dgp_b200: process-pool training is replaced by the GPU path; use train()")
