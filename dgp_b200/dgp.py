@@ -232,6 +232,102 @@ class dgp:
         (dgp.py:1097-1362, generic branch)."""
         self._wire(first_time=False, reset_row=row if reset_lengthscale else None)
 
+    # ---- warm start with new data (sequential design loops, dgp.py:824-1095) -----------------------------
+    def update_xy(self, X, Y, reset=False):
+        """Update the trained DGP with new input and output data (dgp.py:824-884).  Without `reset` the latent
+        layers are carried over: rows kept when the new design is a subset of the old one, GP conditional means at
+        the added rows when it is a superset, a fresh warm start otherwise."""
+        self.Y = Y
+        if isinstance(self.Y, list):
+            if len(self.Y) == 1:
+                self.Y = self.Y[0]
+            else:
+                raise Exception('Y has to be a numpy 2d-array rather than a list. The list version of Y (for linked '
+                                'emulation) has been reduced. Please use the dedicated lgp class for linked emulation.')
+        if (self.Y).ndim == 1 or X.ndim == 1:
+            raise Exception('The input and output data have to be numpy 2d-arrays.')
+        if self.check_rep and len(np.unique(X, axis=0)) != len(X):
+            raise NotImplementedError("dgp_b200: repeated input rows (replicates) are outside the SI hot path")
+        self.indices = None
+        origin_X = (self.X).copy()
+        self.X = X
+        self.n_data = self.X.shape[0]
+        self.m = min(self.m, self.n_data - 1)
+        if reset:
+            self.reinit_all_layer(reset_lengthscale=True)
+            burnin = 10
+        elif (self.X[:, None] == origin_X).all(-1).any(-1).all():
+            self.update_all_layer_smaller(np.where((origin_X == self.X[:, None]).all(-1))[1])
+            burnin = 50
+        elif (origin_X[:, None] == self.X).all(-1).any(-1).all():
+            self.update_all_layer_larger(np.where((self.X == origin_X[:, None]).all(-1))[1])
+            burnin = 50
+        else:
+            self.reinit_all_layer(reset_lengthscale=False)
+            burnin = 200
+        self.imp = imputer(self.all_layer, self.block)
+        (self.imp).sample(burnin=burnin)
+        self.compute_r2()
+
+    def _rewire_node(self, layer, k, last):
+        """Per-node tail shared by the two carry-over updates: global inputs, Vecchia ordering, final outputs."""
+        kernel = layer[k]
+        if kernel.connect is not None:
+            kernel.global_input = (self.X[:, kernel.connect]).copy()
+        kernel.m = self.m
+        if kernel.vecch:
+            self._share_or_draw_ord(layer, k)
+        if last:
+            kernel.output = (self.Y[:, [k]]).copy()
+        if kernel.prior_name == 'ref':
+            kernel.compute_cl()
+
+    def update_all_layer_smaller(self, sub_idx):
+        """The new design is a subset of the old one: keep those rows of every latent layer (dgp.py:1014-1095)."""
+        for l, layer in enumerate(self.all_layer):
+            last = l == self.n_layer - 1
+            for k, kernel in enumerate(layer):
+                kernel.input = kernel.input[sub_idx, :]
+                if not last:
+                    kernel.output = (kernel.output[sub_idx, :]).copy()
+                if kernel.connect is not None and l == 0 and len(np.intersect1d(kernel.connect, kernel.input_dim)) != 0:
+                    raise Exception('The local input and global input should not have any overlap. Change '
+                                    'input_dim or connect so they do not have any common indices.')
+                self._rewire_node(layer, k, last)
+
+    def update_all_layer_larger(self, sub_idx):
+        """The old design is a subset of the new one: latent values at the added rows are the conditional means of
+        the current GP nodes given their imputed outputs (dgp.py:886-1012; `cond_mean` functions.py:301-309,
+        `cond_mean_vecch` vecchia.py:624-633 with 50 neighbours), computed by the prediction kernels."""
+        from . import _lib as L
+        In = (self.X).copy()
+        mask = np.zeros(len(self.X), dtype=bool)
+        mask[sub_idx] = True
+        new_rows = np.where(~mask)[0]
+        for l, layer in enumerate(self.all_layer):
+            last = l == self.n_layer - 1
+            if not last:
+                Out = np.empty((len(In), len(layer)))
+            for k, kernel in enumerate(layer):
+                if not last:
+                    if len(new_rows):
+                        if kernel.vecch:
+                            kernel.pred_m = 50
+                        else:
+                            kernel.compute_stats()
+                        x_new = L.to_dev(np.ascontiguousarray(In[new_rows][:, kernel.input_dim]), np.float64)
+                        z_new = None if kernel.connect is None else \
+                            L.to_dev(np.ascontiguousarray(self.X[new_rows][:, kernel.connect]), np.float64)
+                        mu, _ = kernel._gp_prediction_dev(x_new, z_new)
+                        Out[new_rows, k] = L.to_host(mu)
+                        kernel._Rinv = kernel._Rinv_y = None
+                    Out[sub_idx, k] = kernel.output.flatten()
+                    kernel.output = Out[:, [k]].copy()
+                kernel.input = (In[:, kernel.input_dim]).copy()
+                self._rewire_node(layer, k, last)
+            if not last:
+                In = Out.copy()
+
     def to_vecchia(self, m=25, ord_fun=None):
         """Convert the DGP structure to the Vecchia mode (dgp.py:693-746)."""
         if self.vecch:

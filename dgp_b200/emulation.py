@@ -5,8 +5,10 @@ sliding-window factorisation; `predict(x, method='mean_var')` pushes the test in
 the device -- first layer `gp`, deeper layers `link_gp` -- keeps the per-imputation moments in HBM and
 aggregates them with one kernel.  With a process group (one process per GPU) the test points are sharded
 and the moments all-gathered over NCCL (`dgp_b200.parallel`).
-`loo` re-uses the Vecchia prediction kernels with every point conditioned on the others.
-Out of scope: ALM/MICE/VIGF, nllik, process pools.
+`loo` (SURVEY.md 8f-2) re-uses the Vecchia prediction kernels with every point conditioned on the others;
+`metric` (ALM / MICE / VIGF, same row) is host arithmetic on the per-imputation moments plus one dense inverse per
+output node (MICE) and a nearest-training-point search (VIGF).
+Out of scope: likelihood layers, nllik, process pools.
 """
 from __future__ import annotations
 
@@ -118,6 +120,76 @@ class emulator:
     def ploo(self, X, method=None, sample_size=50, m=30, core_num=None):
         """emulation.py:146-168: the process pool is replaced by the GPU."""
         return self.loo(X, method, sample_size, m)
+
+    # ---- sequential-design criteria -----------------------------------------------------------------------
+    def _layer_moments(self, x, m):
+        """Per imputation, the (mean, var) device tensors of every layer at the inputs x."""
+        xd = L.to_dev(x, np.float64)
+        with L.predict_cache():
+            return [self._predict_one_imputation(layers, xd, m, True)[2] for layers in self.all_layer_set]
+
+    @staticmethod
+    def _mice_var(x, x_extra, kern, nugget_s):
+        """Smoothed predictive variance scale / diag(R^-1) of one output node on the candidate set
+        (functions.py:244-256); R^-1 comes from the device factorisation."""
+        from .kernel_class import kernel as ker
+        kin = x[:, kern.input_dim]
+        if kern.connect is not None:
+            kin = np.concatenate((kin, x_extra[:, kern.connect]), 1)
+        node = ker(length=np.array(kern.length, dtype=np.float64), scale=float(kern.scale[0]),
+                   nugget=max(float(nugget_s), float(kern.nugget[0])), name=kern.name)
+        node.input, node.global_input = np.ascontiguousarray(kin), None
+        node.input_dim = np.arange(kin.shape[1])
+        node.output = np.zeros((len(kin), 1))
+        node.compute_stats()
+        Rinv, _ = node._stats_dev()
+        return float(kern.scale[0]) / L.to_host(L.torch_mod().diagonal(Rinv).contiguous())
+
+    def metric(self, x_cand, method='ALM', obj=None, nugget_s=1., m=50, score_only=False):
+        """ALM, MICE or VIGF criterion of sequential design at the candidate points (emulation.py:323-420).
+        Returns the (M x D_out) scores when `score_only`, else (argmax rows, their scores) per output."""
+        if x_cand.ndim == 1:
+            raise Exception('The candidate design set has to be a numpy 2d-array.')
+        if method == 'ALM':
+            _, score = self.predict(x=x_cand, m=m)
+        elif method == 'MICE':
+            if self.n_layer < 2:
+                raise Exception('The MICE criterion needs a DGP with at least two layers.')
+            score = 0.
+            for s, moments in enumerate(self._layer_moments(x_cand, m)):
+                pred_in, sigma2 = L.to_host(moments[-2][0]), L.to_host(moments[-1][1])
+                smooth = np.stack([self._mice_var(pred_in, x_cand, kern, nugget_s)
+                                   for kern in self.all_layer_set[s][-1]], 1)
+                with np.errstate(divide='ignore'):
+                    score = score + np.log(sigma2 / smooth)
+            score = score / len(self.all_layer_set)
+        elif method == 'VIGF':
+            if obj is None:
+                raise Exception('The dgp object that is used to build the emulator must be supplied to the argument '
+                                '`obj` when VIGF criterion is chosen.')
+            from .vecchia import get_pred_nn_dev
+            # nearest training input of every candidate (emulation.py:396-401), searched on the device
+            index = L.to_host(get_pred_nn_dev(L.to_dev(x_cand, np.float64), L.to_dev(obj.X, np.float64), 1)).ravel()
+            bias, sigma2 = [], []
+            for s, moments in enumerate(self._layer_moments(x_cand, m)):
+                target = np.stack([kern.output[index, 0] for kern in self.all_layer_set[s][-1]], 1)
+                bias.append((L.to_host(moments[-1][0]) - target) ** 2)
+                sigma2.append(L.to_host(moments[-1][1]))
+            bias, sigma2 = np.asarray(bias), np.asarray(sigma2)
+            E1 = np.mean(np.square(bias) + 6 * bias * sigma2 + 3 * np.square(sigma2), axis=0)
+            E2 = np.mean(bias + sigma2, axis=0)
+            score = E1 - E2 ** 2
+        else:
+            raise Exception("method must be 'ALM', 'MICE' or 'VIGF'")
+        if score_only:
+            return score
+        idx = np.argmax(score, axis=0)
+        return idx, score[idx, np.arange(score.shape[1])]
+
+    def pmetric(self, x_cand, method='ALM', obj=None, nugget_s=1., m=50, score_only=False, chunk_num=None,
+                core_num=None):
+        """emulation.py:170-321: the process pool is replaced by the GPU."""
+        return self.metric(x_cand, method, obj, nugget_s, m, score_only)
 
     # ---- prediction -------------------------------------------------------------------------------------
     def _predict_one_imputation(self, layers, xd, m, collect_layers):

@@ -628,6 +628,85 @@ def loo_gp_vecch(X, Y, m, scale, length, nugget, name):
     return mu.reshape(-1, 1), var.reshape(-1, 1)
 
 
+def mice_var(x, x_extra, input_dim, connect, name, length, scale, nugget, nugget_s):
+    """Smoothed predictive variances of a GP node on the candidate set -- functions.py:244-256."""
+    from scipy.linalg import pinvh
+    kin = x[:, input_dim]
+    if connect is not None:
+        kin = np.concatenate((kin, x_extra[:, connect]), 1)
+    R = k_matrix(kin, length, max(nugget_s, nugget), name)
+    return (scale / np.diag(pinvh(R, check_finite=False))).reshape(-1, 1)
+
+
+def mice_score(pred_inputs, variances, x_cand, last_layers, nugget_s):
+    """MICE criterion from the per-imputation moments -- emulation.py:378-392.  last_layers[s][k] =
+    (input_dim, connect, name, length, scale, nugget) of output node k in imputation s."""
+    S = len(pred_inputs)
+    score = np.zeros_like(variances[0])
+    for s in range(S):
+        smooth = np.hstack([mice_var(pred_inputs[s], x_cand, *node, nugget_s) for node in last_layers[s]])
+        with np.errstate(divide='ignore'):
+            score += np.log(variances[s] / smooth)
+    return score / S
+
+
+def vigf_score(bias, sigma2):
+    """VIGF criterion from the squared biases and variances of the imputations -- emulation.py:409-413."""
+    bias, sigma2 = np.asarray(bias), np.asarray(sigma2)
+    E1 = np.mean(np.square(bias) + 6 * bias * sigma2 + 3 * np.square(sigma2), axis=0)
+    E2 = np.mean(bias + sigma2, axis=0)
+    return E1 - E2 ** 2
+
+
+def cond_mean(x, z, w1, global_w1, y, length, nugget, name):
+    """GP conditional mean at new inputs -- functions.py:301-309 with R^-1 y from the Cholesky solve of
+    dgp.py:913-915."""
+    if z is not None:
+        x, w1 = np.concatenate((x, z), 1), np.concatenate((w1, global_w1), 1)
+    Lc = np.linalg.cholesky(k_matrix(w1, length, nugget, name))
+    return k_cross(w1, x, length, name) @ cho_solve((Lc, True), y).ravel()
+
+
+def cond_mean_vecch(x, z, w1, global_w1, y, scale, length, nugget, name, m=50):
+    """vecchia.py:624-633."""
+    if z is not None:
+        x, w1 = np.concatenate((x, z), 1), np.concatenate((w1, global_w1), 1)
+    NN = knn(_scaled(x, length), _scaled(w1, length), m)
+    return gp_vecch(x, w1, NN, y, scale, length, nugget, np.ones(len(y)), name)[0]
+
+
+def grow_layers(nodes, X, Y, sub_idx, vecch):
+    """dgp.update_all_layer_larger -- dgp.py:886-1012 (GP nodes, no replicates).  nodes[l][k] is a dict with
+    input, global_input (or None), output, length, scale, nugget, name, input_dim, connect; updated in place."""
+    In = X.copy()
+    mask = np.zeros(len(X), dtype=bool)
+    mask[sub_idx] = True
+    for l, layer in enumerate(nodes):
+        last = l == len(nodes) - 1
+        Out = np.empty((len(In), len(layer)))
+        for k, nd in enumerate(layer):
+            if not last:
+                xin = In[~mask][:, nd["input_dim"]]
+                zin = None if nd["connect"] is None else X[~mask][:, nd["connect"]]
+                if vecch:
+                    mu = cond_mean_vecch(xin, zin, nd["input"], nd["global_input"], nd["output"], nd["scale"][0],
+                                         nd["length"], nd["nugget"][0], nd["name"])
+                else:
+                    mu = cond_mean(xin, zin, nd["input"], nd["global_input"], nd["output"], nd["length"],
+                                   nd["nugget"][0], nd["name"])
+                Out[sub_idx, k] = nd["output"].ravel()
+                Out[~mask, k] = mu
+                nd["output"] = Out[:, [k]].copy()
+            else:
+                nd["output"] = Y[:, [k]].copy()
+            nd["input"] = In[:, nd["input_dim"]].copy()
+            if nd["connect"] is not None:
+                nd["global_input"] = X[:, nd["connect"]].copy()
+        if not last:
+            In = Out.copy()
+    return nodes
+
+
 def link_gp_vecch(m, v, z, w1, global_w1, NNarray, y, scale, length, nugget, nugget_diag, name):
     """vecchia.py:758-796 with `IJ_nb` (vecchia.py:838-907)."""
     M = m.shape[0]

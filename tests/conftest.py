@@ -51,3 +51,13 @@ def golden_e2e():
 @pytest.fixture(scope="session")
 def golden_loo():
     return load_golden("loo")
+
+
+@pytest.fixture(scope="session")
+def golden_metric():
+    return load_golden("metric")
+
+
+@pytest.fixture(scope="session")
+def golden_update():
+    return load_golden("update")

@@ -384,7 +384,84 @@ def gen_loo():
     save("loo", **out)
 
 
+def gen_metric():
+    """Sequential-design criteria of emulation.py:323-420 (ALM, MICE, VIGF) on frozen imputations."""
+    out = {}
+    rng = np.random.default_rng(SEED + 10)
+    np.random.seed(SEED + 10)
+    dgpsi.nb_seed(SEED + 10)
+    n, d = 30, 2
+    X = rng.uniform(0, 1, size=(n, d))
+    Y = np.stack([np.sin(2 * np.pi * X[:, 0] * X[:, 1]) + (X[:, 1] - 0.5) ** 2, np.cos(3 * X[:, 0]) * X[:, 1]], 1)
+    xc = rng.uniform(0, 1, size=(40, d))
+    out["X"], out["Y"], out["x_cand"] = X, Y, xc
+    for tag, name, depth in (("ma2", "matern2.5", 2), ("se3", "sexp", 3)):
+        layers = [[kernel(length=np.array([1.0]), name=name) for _ in range(d)]]
+        if depth == 3:
+            layers.append([kernel(length=np.array([1.0]), name=name, connect=np.arange(d)) for _ in range(2)])
+        layers.append([kernel(length=np.array([1.0]), name=name, scale_est=True, connect=np.arange(d))
+                       for _ in range(2)])
+        model = dgpsi.dgp(X, Y, dgpsi.combine(*layers))
+        model.train(N=8, disable=True)
+        emu = dgpsi.emulator(model.estimate(), N=3)
+        out[f"{tag}_alm"] = emu.metric(xc, method="ALM", score_only=True)
+        out[f"{tag}_mice"] = emu.metric(xc, method="MICE", nugget_s=1.0, score_only=True)
+        out[f"{tag}_mice_small"] = emu.metric(xc, method="MICE", nugget_s=1e-3, score_only=True)
+        out[f"{tag}_vigf"] = emu.metric(xc, method="VIGF", obj=model, score_only=True)
+        idx, val = emu.metric(xc, method="VIGF", obj=model)
+        out[f"{tag}_vigf_idx"], out[f"{tag}_vigf_val"] = np.asarray(idx), np.asarray(val)
+        # the per-imputation moments the criteria are built from (oracle check of the host arithmetic)
+        pin, s2 = emu.predict_mice(xc, False, m=50)
+        out[f"{tag}_mice_input"], out[f"{tag}_mice_var"] = np.asarray(pin), np.asarray(s2)
+        index = np.argmin(((xc[:, None, :] - X[None, :, :]) ** 2).sum(-1), axis=1)
+        bias, s2v = emu.predict_vigf(xc, index, False, m=50)
+        out[f"{tag}_vigf_bias"], out[f"{tag}_vigf_var"] = np.asarray(bias), np.asarray(s2v)
+        out[f"{tag}_nimp"] = np.array(len(emu.all_layer_set))
+        for s, al in enumerate(emu.all_layer_set):
+            snapshot(al, f"{tag}_S{s}_", out)
+    save("metric", **out)
+
+
+def gen_update():
+    """Warm start with a grown / shrunk design: the deterministic part of dgp.update_xy (dgp.py:824-1095), i.e.
+    update_all_layer_larger (conditional means at the added rows) and update_all_layer_smaller."""
+    out = {}
+    rng = np.random.default_rng(SEED + 11)
+    np.random.seed(SEED + 11)
+    dgpsi.nb_seed(SEED + 11)
+    n, n_new, d = 24, 31, 2
+    Xall = rng.uniform(0, 1, size=(n_new, d))
+    f = lambda X: (np.sin(2 * np.pi * X[:, 0] * X[:, 1]) + (X[:, 1] - 0.5) ** 2).reshape(-1, 1)
+    perm = rng.permutation(n_new)          # the grown design holds the old rows in shuffled positions
+    Xnew = Xall[perm]
+    Xold = Xall[:n]
+    out["X_old"], out["Y_old"], out["X_new"], out["Y_new"] = Xold, f(Xold), Xnew, f(Xnew)
+    for tag, vec, name in (("dense_ma", False, "matern2.5"), ("dense_se", False, "sexp"), ("vecch_se", True, "sexp")):
+        l1 = [kernel(length=np.array([1.0]), name=name) for _ in range(d)]
+        l2 = [kernel(length=np.array([1.0]), name=name, connect=np.arange(d)) for _ in range(2)]
+        l3 = [kernel(length=np.array([1.0]), name=name, scale_est=True, connect=np.arange(d))]
+        model = dgpsi.dgp(Xold, f(Xold), dgpsi.combine(l1, l2, l3), vecchia=vec, m=6)
+        model.train(N=6, disable=True)
+        snapshot(model.all_layer, f"{tag}_before_", out)
+        # preamble of update_xy (dgp.py:835-858) without the random burn-in that follows
+        model.Y, model.X = f(Xnew), Xnew
+        model.indices = None
+        model.n_data = n_new
+        sub_idx = np.where((model.X == Xold[:, None]).all(-1))[1]
+        out[f"{tag}_sub_idx"] = sub_idx
+        model.update_all_layer_larger(sub_idx)
+        snapshot(model.all_layer, f"{tag}_larger_", out)
+        keep = np.sort(rng.choice(n_new, 17, replace=False))
+        out[f"{tag}_keep"] = keep
+        model.Y, model.X = model.Y[keep], model.X[keep]
+        model.n_data = len(keep)
+        model.update_all_layer_smaller(keep)
+        snapshot(model.all_layer, f"{tag}_smaller_", out)
+    save("update", **out)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["dense", "jd", "vecchia", "ess", "e2e", "loo"]
+    which = sys.argv[1:] or ["dense", "jd", "vecchia", "ess", "e2e", "loo", "metric", "update"]
     for w in which:
-        {"dense": gen_dense, "jd": gen_jd, "vecchia": gen_vecchia, "ess": gen_ess, "e2e": gen_e2e, "loo": gen_loo}[w]()
+        {"dense": gen_dense, "jd": gen_jd, "vecchia": gen_vecchia, "ess": gen_ess, "e2e": gen_e2e, "loo": gen_loo,
+         "metric": gen_metric, "update": gen_update}[w]()

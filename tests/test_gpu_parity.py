@@ -740,6 +740,103 @@ def test_leave_one_out_vs_reference(golden_loo):
         big.loo(np.zeros((100, 1)))
 
 
+def test_design_criteria_vs_reference(golden_metric):
+    """emulator.metric (ALM / MICE / VIGF, emulation.py:323-420) on the reference's own imputed states: a 2-layer
+    Matern and a 3-layer squared-exponential DGP with two outputs.  K^-1 is recomputed on the GPU (nugget 1e-6,
+    cond ~1e10), hence the same absolute tolerance on the moments as the end-to-end predict test; the MICE score is
+    a log ratio, compared where the reference's own variance is well above that floor."""
+    import dgp_b200 as D
+
+    g = golden_metric
+    xc = g["x_cand"]
+    for tag, name in (("ma2", "matern2.5"), ("se3", "sexp")):
+        emu = _frozen_emulator(g, tag, name)
+        alm = emu.metric(xc, method="ALM", score_only=True)
+        assert alm.shape == g[f"{tag}_alm"].shape
+        assert np.max(np.abs(alm - g[f"{tag}_alm"])) <= 2e-6, tag
+        idx, val = emu.metric(xc, method="ALM")
+        assert np.array_equal(idx, np.argmax(g[f"{tag}_alm"], axis=0)) and np.allclose(val, alm[idx, [0, 1]])
+        solid = np.min(g[f"{tag}_mice_var"], axis=0) > 1e-4
+        assert solid.sum() > 20
+        for key, ns in (("mice", 1.0), ("mice_small", 1e-3)):
+            mice = emu.metric(xc, method="MICE", nugget_s=ns, score_only=True)
+            assert mice.shape == g[f"{tag}_{key}"].shape and np.all(np.isfinite(mice))
+            assert np.max(np.abs(mice - g[f"{tag}_{key}"])[solid]) <= 1e-3, (tag, key)
+            assert np.array_equal(np.argmax(mice, axis=0), np.argmax(g[f"{tag}_{key}"], axis=0)), (tag, key)
+        model = type("M", (), {"X": g["X"]})()
+        vigf = emu.metric(xc, method="VIGF", obj=model, score_only=True)
+        ref = g[f"{tag}_vigf"]
+        # squared biases reach O(1) here and inherit the 2e-6 absolute floor of the moments (see the docstring)
+        floor = 2e-6 * max(1.0, float(np.max(g[f"{tag}_vigf_bias"])))
+        assert np.max(np.abs(vigf - ref)) <= floor, tag
+        idx, val = emu.pmetric(xc, method="VIGF", obj=model)
+        assert np.array_equal(idx, g[f"{tag}_vigf_idx"])
+        assert np.max(np.abs(val - g[f"{tag}_vigf_val"])) <= floor, tag
+        with pytest.raises(Exception):
+            emu.metric(xc, method="VIGF")
+        with pytest.raises(Exception):
+            emu.metric(xc[:, 0], method="ALM")
+
+
+def test_warm_start_update_xy(golden_update):
+    """dgp.update_xy (dgp.py:824-1095): the deterministic carry-over of the latent layers against the reference
+    (conditional means at added rows through the gp / gp_vecch prediction kernels; row selection when the design
+    shrinks), then the public call on all four branches."""
+    import dgp_b200 as D
+
+    g = golden_update
+    for tag, vec, name in (("dense_ma", False, "matern2.5"), ("dense_se", False, "sexp"), ("vecch_se", True, "sexp")):
+        model = D.dgp.__new__(D.dgp)
+        model.all_layer = _snapshot_layers(g, f"{tag}_before_", lambda l, k: name)
+        for layer in model.all_layer:
+            for node in layer:
+                node.vecch, node.m = vec, 6
+        model.n_layer, model.vecch, model.m, model.block = 3, vec, 6, True
+        model.check_rep, model.indices, model.nn_method, model.ord_fun = True, None, 'exact', None
+        model.X, model.Y, model.n_data = g["X_new"], g["Y_new"], len(g["X_new"])
+        model.update_all_layer_larger(g[f"{tag}_sub_idx"])
+        tol = 1e-6 if not vec else 1e-8          # dense: R^-1 y at nugget 1e-6 (cond ~1e10)
+        for stage in ("larger", "smaller"):
+            if stage == "smaller":
+                keep = g[f"{tag}_keep"]
+                model.X, model.Y, model.n_data = model.X[keep], model.Y[keep], len(keep)
+                model.update_all_layer_smaller(keep)
+            for l, layer in enumerate(model.all_layer):
+                for k, node in enumerate(layer):
+                    p = f"{tag}_{stage}_L{l}K{k}_"
+                    assert node.input.shape == g[p + "input"].shape, (tag, stage, l, k)
+                    assert np.max(np.abs(node.input - g[p + "input"])) <= tol, (tag, stage, l, k)
+                    assert np.max(np.abs(node.output - g[p + "output"])) <= tol, (tag, stage, l, k)
+                    if node.connect is not None:
+                        assert np.array_equal(node.global_input, g[p + "global_input"])
+                    if vec:
+                        assert node.NNarray.shape == (len(model.X), 7) and sorted(node.ord) == list(range(len(model.X)))
+    # public call: grown design, shrunk design, unrelated design, reset
+    np.random.seed(5)
+    D.nb_seed(5)
+    Xo, Yo, Xn, Yn = g["X_old"], g["Y_old"], g["X_new"], g["Y_new"]
+    model = D.dgp(Xo, Yo)
+    model.train(N=2, disable=True)
+    latent_before = model.all_layer[0][0].output.copy()
+    theta = model.all_layer[1][0].length.copy()
+    model.update_xy(Xn, Yn)
+    assert model.n_data == len(Xn) and model.all_layer[0][0].input.shape == Xn.shape
+    assert model.all_layer[-1][0].output.shape == Yn.shape and np.array_equal(model.all_layer[-1][0].output, Yn)
+    assert np.array_equal(model.all_layer[1][0].length, theta)          # hyper-parameters are carried over
+    assert model.all_layer[0][0].output.shape == (len(Xn), 1) and latent_before.shape == (len(Xo), 1)
+    model.train(N=1, disable=True)
+    model.update_xy(Xn[:15], Yn[:15])
+    assert model.all_layer[1][0].input.shape == (15, 2) and model.n_data == 15
+    model.update_xy(Xo[:20] + 0.01, Yo[:20])
+    assert model.all_layer[0][1].output.shape == (20, 1)
+    model.update_xy(Xo, Yo, reset=True)
+    assert np.array_equal(model.all_layer[1][0].length, model.all_layer[1][0].para_path[0, 1:-1])
+    model.train(N=1, disable=True)
+    assert model.N == 4 and np.all(np.isfinite(model.all_layer[1][0].para_path))
+    with pytest.raises(Exception):
+        model.update_xy(Xo[:, 0], Yo)
+
+
 def test_public_api_train_and_predict_smoke():
     """The user-facing path runs: dgp(X,Y).train -> estimate -> emulator -> predict; the fit is sane."""
     import dgp_b200 as D

@@ -243,3 +243,62 @@ def test_leave_one_out(golden_loo):
         assert relerr(mu, g[f"gp_{tag}_dense_mu"], 1e-2) <= 1e-7 and relerr(s2, g[f"gp_{tag}_dense_var"], 1e-300) <= 1e-7
         mu, s2 = O.loo_gp_vecch(X, Y, 6, 1.3, length, 1e-4, name)
         assert relerr(mu, g[f"gp_{tag}_vecch_mu"], 1e-3) <= 1e-9 and relerr(s2, g[f"gp_{tag}_vecch_var"], 1e-300) <= 1e-9
+
+
+def test_design_criteria(golden_metric):
+    """MICE and VIGF scores of the reference from the reference's own per-imputation moments (emulation.py:378-413)."""
+    g = golden_metric
+    xc = g["x_cand"]
+    for tag, name in (("ma2", "matern2.5"), ("se3", "sexp")):
+        S = int(g[f"{tag}_nimp"])
+        last = []
+        for s in range(S):
+            l = 0
+            while f"{tag}_S{s}_L{l + 1}K0_input" in g.files:
+                l += 1
+            nodes, k = [], 0
+            while f"{tag}_S{s}_L{l}K{k}_input" in g.files:
+                p = f"{tag}_S{s}_L{l}K{k}_"
+                nodes.append((np.arange(g[p + "input"].shape[1]), np.arange(g[p + "global_input"].shape[1]), name,
+                              g[p + "length"], g[p + "scale"][0], g[p + "nugget"][0]))
+                k += 1
+            last.append(nodes)
+        for key, ns in (("mice", 1.0), ("mice_small", 1e-3)):
+            score = O.mice_score(list(g[f"{tag}_mice_input"]), list(g[f"{tag}_mice_var"]), xc, last, ns)
+            assert np.max(np.abs(score - g[f"{tag}_{key}"])) <= 1e-9 * max(1.0, np.max(np.abs(g[f"{tag}_{key}"]))), (tag, key)
+        vigf = O.vigf_score(g[f"{tag}_vigf_bias"], g[f"{tag}_vigf_var"])
+        assert relerr(vigf, g[f"{tag}_vigf"], 1e-300) <= 1e-12, tag
+        idx = np.argmax(vigf, axis=0)
+        assert np.array_equal(idx, g[f"{tag}_vigf_idx"])
+
+
+def _node_dicts(g, prefix, name):
+    nodes, l = [], 0
+    while f"{prefix}L{l}K0_input" in g.files:
+        layer, k = [], 0
+        while f"{prefix}L{l}K{k}_input" in g.files:
+            p = f"{prefix}L{l}K{k}_"
+            gi = g[p + "global_input"].copy() if p + "global_input" in g.files else None
+            layer.append(dict(input=g[p + "input"].copy(), global_input=gi, output=g[p + "output"].copy(),
+                              length=g[p + "length"], scale=g[p + "scale"], nugget=g[p + "nugget"], name=name,
+                              input_dim=np.arange(g[p + "input"].shape[1]),
+                              connect=None if gi is None else np.arange(gi.shape[1])))
+            k += 1
+        nodes.append(layer)
+        l += 1
+    return nodes
+
+
+def test_warm_start_with_grown_design(golden_update):
+    """dgp.update_all_layer_larger of the reference: latent values at the added rows are conditional GP means."""
+    g = golden_update
+    for tag, vec, name in (("dense_ma", False, "matern2.5"), ("dense_se", False, "sexp"), ("vecch_se", True, "sexp")):
+        nodes = O.grow_layers(_node_dicts(g, f"{tag}_before_", name), g["X_new"], g["Y_new"], g[f"{tag}_sub_idx"], vec)
+        for l, layer in enumerate(nodes):
+            for k, nd in enumerate(layer):
+                p = f"{tag}_larger_L{l}K{k}_"
+                tol = 1e-6 if not vec else 1e-9      # dense: R^-1 y at nugget 1e-6 (cond ~1e10), BLAS-order dependent
+                assert np.max(np.abs(nd["input"] - g[p + "input"])) <= tol, (tag, l, k)
+                assert np.max(np.abs(nd["output"] - g[p + "output"])) <= tol, (tag, l, k)
+                if nd["global_input"] is not None:
+                    assert np.array_equal(nd["global_input"], g[p + "global_input"])
