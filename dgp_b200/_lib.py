@@ -36,6 +36,14 @@ class DgpbNode(ctypes.Structure):
     ]
 
 
+class DgpbLik(ctypes.Structure):
+    """Mirror of `struct dgpb_lik` (include/dgpb.h)."""
+
+    _fields_ = [("kind", c_i32), ("rows", c_i32 * 3), ("y", c_vp)]
+
+
+LIK_KIND = {"Poisson": 0, "Hetero": 1, "NegBin": 2}
+
 _PROTOS = {
     # name: (restype, argtypes)
     "dgpb_last_error": (ctypes.c_char_p, []),
@@ -57,7 +65,12 @@ _PROTOS = {
     "dgpb_nllik_grad_dense_batch": (ctypes.c_int, [c_vp, ctypes.POINTER(DgpbNode), ctypes.c_int, c_i64, c_vp,
                                                    ctypes.c_int, c_vp, c_vp]),
     "dgpb_compute_stats": (ctypes.c_int, [c_vp, ctypes.POINTER(DgpbNode), c_i64, c_vp, c_vp, c_vp]),
+    "dgpb_compute_stats_shifted": (ctypes.c_int, [c_vp, ctypes.POINTER(DgpbNode), c_i64, c_vp, c_vp, c_vp, c_vp]),
     "dgpb_mvn_draw": (ctypes.c_int, [c_vp, ctypes.POINTER(DgpbNode), c_i64, c_vp, c_vp, c_vp]),
+    "dgpb_lik_loglik": (ctypes.c_int, [ctypes.POINTER(DgpbLik), ctypes.c_int, c_vp, c_i64, c_vp, c_vp]),
+    "dgpb_ess_block_lik": (ctypes.c_int, [c_vp, ctypes.POINTER(DgpbNode), ctypes.c_int, c_vp, c_vp, c_i64,
+                                          ctypes.POINTER(DgpbLik), ctypes.c_int, c_i64, c_vp, c_vp, ctypes.c_int,
+                                          ctypes.POINTER(ctypes.c_int), c_vp, c_vp, c_vp]),
     "dgpb_ess_block": (ctypes.c_int, [c_vp, ctypes.POINTER(DgpbNode), ctypes.c_int, c_vp, c_vp, c_i64,
                                       ctypes.POINTER(DgpbNode), ctypes.c_int, c_i64, c_vp, c_vp, ctypes.c_int,
                                       ctypes.POINTER(ctypes.c_int), c_vp, c_vp]),

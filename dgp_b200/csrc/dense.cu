@@ -889,8 +889,14 @@ static inline double llik_from(double logdetK, double quadK, double scale, int64
     return -0.5 * (logdetK + (double)n * log(scale) + quadK / scale);
 }
 
+// K_ii += shift_i on an assembled matrix (heteroskedastic noise on top of the node's own nugget)
+__global__ void diag_shift_kernel(double* __restrict__ T, int64_t ld, int n, const double* __restrict__ shift) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) T[(size_t)i * ld + i] += shift[i];
+}
+
 int grad_pipeline(Workspace* ws, const dgpb_node* node, int64_t n, bool want_grad, double* Rinv, double* Rinv_y,
-                  double* out_host, cudaStream_t st) {
+                  double* out_host, cudaStream_t st, const double* diag_shift = nullptr) {
     KernelDev kd;
     DGPB_TRY(make_kernel_dev(node, n, nullptr, &kd));
     Geom g = make_geom(n, true);
@@ -899,6 +905,10 @@ int grad_pipeline(Workspace* ws, const dgpb_node* node, int64_t n, bool want_gra
     DGPB_TRY(setup_batch(ws, g, 1, &bt, &out));
     const double* ys[1] = {node->output};
     DGPB_TRY(assemble(g, &kd, ys, bt, 1, st));
+    if (diag_shift) {
+        diag_shift_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(bt.T[0], g.ld, g.n, diag_shift);
+        DGPB_LAUNCHED();
+    }
     DGPB_TRY(factorize(g, bt, 1, st));
     ScaleArgs sa;
     sa.scale[0] = node->scale;
@@ -1028,6 +1038,12 @@ int dgpb_nllik_grad_dense_batch(dgpb_ws* ws, const dgpb_node* nodes, int B, int6
 int dgpb_compute_stats(dgpb_ws* ws, const dgpb_node* node, int64_t n, double* Rinv, double* Rinv_y, void* stream) {
     DGPB_REQUIRE(ws && node && Rinv && Rinv_y && n >= 1, "NULL argument");
     return grad_pipeline(ws, node, n, false, Rinv, Rinv_y, nullptr, (cudaStream_t)stream);
+}
+
+int dgpb_compute_stats_shifted(dgpb_ws* ws, const dgpb_node* node, int64_t n, const double* diag_shift, double* Rinv,
+                               double* Rinv_y, void* stream) {
+    DGPB_REQUIRE(ws && node && diag_shift && Rinv && Rinv_y && n >= 1, "NULL argument");
+    return grad_pipeline(ws, node, n, false, Rinv, Rinv_y, nullptr, (cudaStream_t)stream, diag_shift);
 }
 
 int dgpb_mvn_draw(dgpb_ws* ws, const dgpb_node* node, int64_t n, const double* z, double* nu, void* stream) {

@@ -687,3 +687,188 @@ extern "C" int dgpb_ess_block(dgpb_ws* ws, const dgpb_node* targets, int n_targe
     return dgpb_ess_block_cached(ws, targets, n_targets, target_rows_host, layer_out, layer_width, uppers, n_uppers, n, z,
                                  u_host, nu, n_prop_host, theta_host, nullptr, nullptr, nullptr, stream);
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Likelihood layers (dgpsi/likelihood_class.py): the upper "nodes" of the last GP layer are likelihood nodes whose
+// log-likelihood is a sum over data points of an elementwise function of one or two latent columns.
+namespace dgpb {
+
+constexpr int kMaxLik = 8;
+constexpr int kLikWave = 8;
+
+struct LikArgs {
+    int nl;
+    int kind[kMaxLik];
+    int row0[kMaxLik], row1[kMaxLik];
+    const double* y[kMaxLik];
+    const double* src[kLikWave + 1];   // candidate images of the feeding layer (layer_width x n)
+};
+
+__device__ __forceinline__ double lik_point(int kind, double y, double f0, double f1) {
+    if (kind == DGPB_LIK_POISSON) {        // likelihood_class.py:39-48
+        return y * f0 - exp(f0) - lgamma(y + 1.0);
+    } else if (kind == DGPB_LIK_HETERO) {  // likelihood_class.py:110-116
+        const double r2 = (y - f0) * (y - f0);
+        return -0.5 * (1.8378770664093453 + f1 + exp(log(r2) - f1));
+    } else {                               // NegBin, likelihood_class.py:264-272
+        const double nn = exp(-f1), a = f0 + f1;
+        const double softplus = fmax(a, 0.0) + log1p(exp(-fabs(a)));
+        return lgamma(y + nn) - lgamma(nn) - lgamma(y + 1.0) + y * a - (y + nn) * softplus;
+    }
+}
+
+// out[s] = sum over likelihood nodes (in order) and data points of the log-likelihood of candidate s
+__global__ void __launch_bounds__(512) lik_sum_kernel(LikArgs a, int64_t n, double* __restrict__ out) {
+    __shared__ double red[512];
+    const double* F = a.src[blockIdx.x];
+    double total = 0.0;
+    for (int l = 0; l < a.nl; ++l) {
+        const double* f0 = F + (int64_t)a.row0[l] * n;
+        const double* f1 = F + (int64_t)a.row1[l] * n;
+        const double* y = a.y[l];
+        const int kind = a.kind[l];
+        double acc = 0.0;
+        for (int64_t i = threadIdx.x; i < n; i += 512) acc += lik_point(kind, y[i], f0[i], f1[i]);
+        red[threadIdx.x] = acc;
+        __syncthreads();
+        for (int w = 256; w > 0; w >>= 1) {
+            if (threadIdx.x < w) red[threadIdx.x] += red[threadIdx.x + w];
+            __syncthreads();
+        }
+        total += red[0];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[blockIdx.x] = total;
+}
+
+}  // namespace dgpb
+
+extern "C" int dgpb_lik_loglik(const dgpb_lik* liks, int n_liks, const double* layer, int64_t n, double* out_host,
+                               void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    DGPB_REQUIRE(liks && layer && out_host && n >= 1 && n_liks >= 1 && n_liks <= kMaxLik, "bad argument");
+    LikArgs a;
+    a.nl = n_liks;
+    for (int l = 0; l < n_liks; ++l) {
+        DGPB_REQUIRE(liks[l].kind >= DGPB_LIK_POISSON && liks[l].kind <= DGPB_LIK_NEGBIN && liks[l].y, "bad likelihood node");
+        a.kind[l] = liks[l].kind;
+        a.row0[l] = liks[l].rows[0];
+        a.row1[l] = liks[l].kind == DGPB_LIK_POISSON ? liks[l].rows[0] : liks[l].rows[1];
+        a.y[l] = liks[l].y;
+    }
+    a.src[0] = layer;
+    double* outd;
+    DGPB_CUDA_TRY(cudaMallocAsync((void**)&outd, sizeof(double), st));
+    lik_sum_kernel<<<1, 512, 0, st>>>(a, n, outd);
+    DGPB_LAUNCHED();
+    DGPB_CUDA_TRY(cudaMemcpyAsync(out_host, outd, sizeof(double), cudaMemcpyDeviceToHost, st));
+    DGPB_CUDA_TRY(cudaFreeAsync(outd, st));
+    DGPB_CUDA_TRY(cudaStreamSynchronize(st));
+    return DGPB_OK;
+}
+
+// ESS update of target GP nodes whose outputs feed likelihood nodes (imputation.py:44-119 / :166-221 with
+// `linked_kernel.type == 'likelihood'`).  Same contract as dgpb_ess_block for draws, angles and uniforms; candidate
+// angles are evaluated in waves of up to 8 by one reduction launch, the threshold rides along in the first wave.
+extern "C" int dgpb_ess_block_lik(dgpb_ws* ws, const dgpb_node* targets, int n_targets, const int32_t* target_rows_host,
+                                  double* layer_out, int64_t layer_width, const dgpb_lik* liks, int n_liks, int64_t n,
+                                  const double* z, const double* u_host, int nu, int* n_prop_host, double* theta_host,
+                                  const int32_t* target_keys_host, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    DGPB_REQUIRE(ws && targets && liks && layer_out && z && u_host && target_rows_host, "NULL argument");
+    DGPB_REQUIRE(n_targets >= 1 && n_liks >= 1 && n_liks <= kMaxLik && n >= 1 && nu >= 3, "bad sizes");
+    for (int k = 0; k < n_targets; ++k)
+        DGPB_REQUIRE(target_rows_host[k] >= 0 && target_rows_host[k] < layer_width, "target row out of range");
+    LikArgs a;
+    a.nl = n_liks;
+    for (int l = 0; l < n_liks; ++l) {
+        DGPB_REQUIRE(liks[l].kind >= DGPB_LIK_POISSON && liks[l].kind <= DGPB_LIK_NEGBIN && liks[l].y, "bad likelihood node");
+        const int need = liks[l].kind == DGPB_LIK_POISSON ? 1 : 2;
+        for (int j = 0; j < need; ++j)
+            DGPB_REQUIRE(liks[l].rows[j] >= 0 && liks[l].rows[j] < layer_width, "likelihood input row out of range");
+        a.kind[l] = liks[l].kind;
+        a.row0[l] = liks[l].rows[0];
+        a.row1[l] = need == 2 ? liks[l].rows[1] : liks[l].rows[0];
+        a.y[l] = liks[l].y;
+    }
+    if (g_pre_done_guard) DGPB_CUDA_TRY(cudaStreamWaitEvent(st, g_pre_done_guard, 0));  // SLOT_PROP may still be read
+    void *pnu, *pprop, *pout;
+    const size_t layer_elems = (size_t)layer_width * n;
+    DGPB_TRY(ws->reserve(SLOT_NU, sizeof(double) * (size_t)n_targets * n, &pnu));
+    DGPB_TRY(ws->reserve(SLOT_PROP, sizeof(double) * layer_elems * kLikWave, &pprop));
+    DGPB_TRY(ws->reserve(SLOT_OUT, sizeof(double) * kOutDoubles, &pout));
+    double* nuv = (double*)pnu;
+    double* prop = (double*)pprop;
+    double* outd = (double*)pout;
+    DGPB_TRY(prior_draws(ws, targets, n_targets, n, z, nuv, target_keys_host, st));
+    for (int s = 0; s < kLikWave; ++s)  // rows that are not being updated are shared by every proposal
+        DGPB_CUDA_TRY(cudaMemcpyAsync(prop + s * layer_elems, layer_out, sizeof(double) * layer_elems,
+                                      cudaMemcpyDeviceToDevice, st));
+    int ui = 0;
+    const double log_u0 = log(u_host[ui++]);              // imputation.py:79
+    double theta = 2.0 * M_PI * u_host[ui++];             // imputation.py:81
+    double tmin = theta - 2.0 * M_PI, tmax = theta;
+    double log_y = 0.0;
+    bool have_thr = false;
+    int nprop = 0;
+    while (true) {
+        double thetas[kLikWave];
+        const int S = std::max(1, std::min(kLikWave, 1 + (nu - ui)));
+        thetas[0] = theta;
+        {
+            double lmin = tmin, lmax = tmax;
+            for (int s = 1; s < S; ++s) {
+                if (thetas[s - 1] < 0.0) lmin = thetas[s - 1]; else lmax = thetas[s - 1];
+                thetas[s] = lmin + (lmax - lmin) * u_host[ui + s - 1];
+            }
+        }
+        for (int s = 0; s < S; ++s) {
+            const double c = cos(thetas[s]), sn = sin(thetas[s]);
+            for (int k = 0; k < n_targets; ++k) {
+                const int64_t row = target_rows_host[k];
+                propose_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(prop + s * layer_elems + row * n, layer_out + row * n,
+                                                                      nuv + (int64_t)k * n, c, sn, n);
+                DGPB_LAUNCHED();
+            }
+        }
+        int first = 0;
+        if (!have_thr) a.src[first++] = layer_out;
+        for (int s = 0; s < S; ++s) a.src[first + s] = prop + s * layer_elems;
+        lik_sum_kernel<<<first + S, 512, 0, st>>>(a, n, outd);
+        DGPB_LAUNCHED();
+        DGPB_CUDA_TRY(cudaMemcpyAsync(ws->pinned, outd, sizeof(double) * (first + S), cudaMemcpyDeviceToHost, st));
+        DGPB_CUDA_TRY(cudaStreamSynchronize(st));
+        if (!have_thr) {
+            log_y = ws->pinned[0] + log_u0;
+            have_thr = true;
+        }
+        int accepted = -1;
+        for (int s = 0; s < S; ++s) {
+            if (theta_host) theta_host[nprop] = thetas[s];
+            ++nprop;
+            if (ws->pinned[first + s] > log_y) {  // imputation.py:107-110 (a NaN likelihood is a rejection there too)
+                accepted = s;
+                break;
+            }
+            if (thetas[s] < 0.0) tmin = thetas[s]; else tmax = thetas[s];
+            if (s + 1 < S) ++ui;
+        }
+        if (accepted >= 0) {
+            const double* pa = prop + accepted * layer_elems;
+            for (int k = 0; k < n_targets; ++k) {
+                const int64_t row = target_rows_host[k];
+                DGPB_CUDA_TRY(cudaMemcpyAsync(layer_out + row * n, pa + row * n, sizeof(double) * n,
+                                              cudaMemcpyDeviceToDevice, st));
+            }
+            break;
+        }
+        if (ui >= nu) {
+            if (n_prop_host) *n_prop_host = nprop;
+            set_error("ESS ran out of uniforms after %d proposals", nprop);
+            return DGPB_BAD_ARG;
+        }
+        theta = tmin + (tmax - tmin) * u_host[ui++];
+    }
+    if (n_prop_host) *n_prop_host = nprop;
+    return DGPB_OK;
+}

@@ -138,10 +138,15 @@ class dgp:
             all_layer = combine(layer1, layer2)
         self.all_layer = all_layer
         self.n_layer = len(self.all_layer)
-        for layer in self.all_layer:
+        for l, layer in enumerate(self.all_layer):
             for node in layer:
                 if getattr(node, 'type', 'gp') != 'gp':
-                    raise NotImplementedError("dgp_b200: likelihood layers are outside the SI hot path")
+                    from . import _lib as L
+                    if l != self.n_layer - 1 or l == 0 or any(nd.type == 'gp' for nd in layer):
+                        raise NotImplementedError("dgp_b200: likelihood nodes are supported as a final layer made of "
+                                                  "likelihood nodes only")
+                    if node.name not in L.LIK_KIND:
+                        raise NotImplementedError("dgp_b200: likelihood '%s' is outside the SI hot path" % node.name)
         self.initialize()
         self.block = block
         self.imp = imputer(self.all_layer, self.block)
@@ -159,6 +164,50 @@ class dgp:
         self.__dict__.update(state)
 
     # ---- wiring of inputs / outputs (generic branch of dgp.py:154-691 and :1097-1362) ---------------
+    def _latent_init_likelihood(self, In, l):
+        """Warm start of the GP layer that feeds a single likelihood node (dgp.py:163-203, 327-330, 526-532, branches
+        without replicates); None when layer l is not such a layer."""
+        if l != self.n_layer - 2 or len(self.all_layer[l + 1]) != 1:
+            return None
+        lik = self.all_layer[l + 1][0]
+        if getattr(lik, 'type', 'gp') != 'likelihood':
+            return None
+        width = len(self.all_layer[l])
+        y = self.Y.flatten()
+        if lik.name == 'Poisson':
+            return np.log(self.Y + .5 + 1e-12)
+        if lik.name == 'NegBin':
+            Out = np.empty((np.shape(In)[0], width))
+            Out[:, 0] = np.log(y + .5 + 1e-12)
+            # the reference leaves the dispersion column unset without replicates (dgp.py:527-532); start it from the
+            # method-of-moments value its replicate branch uses globally (dgp.py:534-539)
+            sigma = max((y.var(ddof=1) - y.mean()) / (y.mean() ** 2 + 1e-8), 1e-3)
+            Out[:, 1:] = np.log(sigma)
+            return Out
+        if lik.name == 'Hetero' and width == 2:
+            from .gp import gp
+            D = self.X.shape[1]
+            Out = np.empty((np.shape(In)[0], width))
+            Out[:, 0] = y
+            fit = gp(self.X, y.reshape(-1, 1), ker(length=np.ones(D), name=self.all_layer[-2][0].name, scale_est=True,
+                                                  nugget_est=True, prior_name='ref', nugget=1e-2),
+                     vecchia=self.vecch, m=self.m, ord_fun=self.ord_fun)
+            fit.train()
+            mean_mu = fit.loo()[0].flatten()
+            z = np.log(np.maximum((y - mean_mu) ** 2, 1e-12) + 1e-12)
+            fit = gp(self.X, z.reshape(-1, 1), ker(length=np.ones(D), name=self.all_layer[-2][1].name, scale_est=True,
+                                                  nugget_est=True, prior_name='ref', nugget=1e-2),
+                     vecchia=self.vecch, m=self.m, ord_fun=self.ord_fun)
+            fit.train()
+            mean_lv, var_lv = fit.loo()
+            mean_lv = mean_lv.flatten()
+            var_lv = np.maximum((var_lv - fit.kernel.nugget * fit.kernel.scale).flatten(), 1e-12)
+            sd_lv = np.sqrt(var_lv)
+            z_init = np.random.normal(loc=mean_lv, scale=sd_lv)
+            Out[:, 1] = np.clip(z_init, mean_lv - 2.576 * sd_lv, mean_lv + 2.576 * sd_lv)
+            return Out
+        return None
+
     def _latent_init(self, In, width):
         """Warm start of a latent layer: copy of its input, Nystrom kernel-PCA when it narrows, column
         resampling when it widens (dgp.py:565-576)."""
@@ -190,11 +239,19 @@ class dgp:
         for l, layer in enumerate(self.all_layer):
             last = l == self.n_layer - 1
             if not last:
-                Out = self._latent_init(In, len(layer))
+                Out = self._latent_init_likelihood(In, l)
+                if Out is None:
+                    Out = self._latent_init(In, len(layer))
             for k, kernel in enumerate(layer):
                 if kernel.input_dim is None:
                     kernel.input_dim = np.arange(np.shape(In)[1])
                 kernel.input = In[:, kernel.input_dim].copy()
+                if kernel.type == 'likelihood':  # dgp.py:584-590, 665-667
+                    if len(kernel.input_dim) != kernel.n_inputs:
+                        raise Exception('You need %d and only %d GP node(s) to feed the %s likelihood node.'
+                                        % (kernel.n_inputs, kernel.n_inputs, kernel.name))
+                    kernel.output = self.Y[:, [k]]
+                    continue
                 if kernel.connect is not None:
                     if l == 0 and len(np.intersect1d(kernel.connect, kernel.input_dim)) != 0:
                         raise Exception('The local input and global input should not have any overlap. Change '
@@ -397,7 +454,7 @@ class dgp:
 
         from . import _lib as L
 
-        nodes = [(l, kernel) for l in range(self.n_layer) for kernel in self.all_layer[l]]
+        nodes = [(l, kernel) for l in range(self.n_layer) for kernel in self.all_layer[l] if kernel.type == 'gp']
         torch = L.torch_mod()
         dev = L.device()
         dense = [it for it in nodes if not it[1].vecch]
@@ -455,7 +512,8 @@ class dgp:
     def compute_r2(self):
         for l in range(1, self.n_layer):
             for kernel in self.all_layer[l]:
-                kernel.r2(overwritten=True)
+                if kernel.type == 'gp':
+                    kernel.r2(overwritten=True)
 
     def aggregate_r2(self, burnin=0.75, agg='median'):
         """dgp.py:1481-1515."""
@@ -466,7 +524,8 @@ class dgp:
         f = np.mean if agg == 'mean' else np.median
         res = []
         for layer in self.all_layer:
-            res.append([None if k.R2 is None else f(k.R2[int(len(k.R2) * burnin):, :], axis=0) for k in layer])
+            res.append([None if getattr(k, 'R2', None) is None else f(k.R2[int(len(k.R2) * burnin):, :], axis=0)
+                        for k in layer])
         return res
 
     def estimate(self, burnin=None):
@@ -475,6 +534,8 @@ class dgp:
         final_struct = copy.deepcopy(self.all_layer)
         for layer in final_struct:
             for kernel in layer:
+                if kernel.type != 'gp':
+                    continue
                 point_est = np.mean(kernel.para_path[self.burnin:, :], axis=0)
                 kernel.scale = np.atleast_1d(point_est[0])
                 kernel.length = np.atleast_1d(point_est[1:-1])

@@ -150,6 +150,8 @@ class emulator:
         Returns the (M x D_out) scores when `score_only`, else (argmax rows, their scores) per output."""
         if x_cand.ndim == 1:
             raise Exception('The candidate design set has to be a numpy 2d-array.')
+        if self.all_layer[-1][0].type == 'likelihood':
+            raise NotImplementedError("dgp_b200: design criteria of emulators with a likelihood layer are not built")
         if method == 'ALM':
             _, score = self.predict(x=x_cand, m=m)
         elif method == 'MICE':
@@ -204,6 +206,11 @@ class emulator:
                     ms[k], vs[k] = mk, vk
             for k, kernel in enumerate(layer):
                 if ms[k] is not None:
+                    continue
+                if kernel.type == 'likelihood':   # emulation.py:752-757: moments of the observable from the latent ones
+                    mk, vk = kernel.prediction(m=L.to_host(L.cols(mean, kernel.input_dim)),
+                                               v=L.to_host(L.cols(var, kernel.input_dim)))
+                    ms[k], vs[k] = L.to_dev(np.ascontiguousarray(mk)), L.to_dev(np.ascontiguousarray(vk))
                     continue
                 kernel.pred_m = m
                 z = L.cols(xd, kernel.connect) if kernel.connect is not None else None
@@ -272,6 +279,9 @@ class emulator:
         xd = L.to_dev(x, np.float64)
         S = len(self.all_layer_set)
         means, variances, layers_all = [], [], []
+        lik_out = self.all_layer[-1][0].type == 'likelihood'
+        if method == 'sampling' and lik_out:
+            return self._sample_likelihood(xd, full_layer, sample_size, m)
         with L.predict_cache():
             for s in range(S):
                 mean, var, per_layer = self._predict_one_imputation(self.all_layer_set[s], xd, m, full_layer)
@@ -311,6 +321,40 @@ class emulator:
         if aggregation:
             return agg(means, variances)
         return [L.to_host(t) for t in means], [L.to_host(t) for t in variances]
+
+    def _sample_likelihood(self, xd, full_layer, sample_size, m):
+        """method='sampling' of an emulator whose final layer holds likelihood nodes (emulation.py:765-810): draws
+        of the latent layers from their Gaussian moments, pushed through each likelihood's sampler."""
+        with L.predict_cache():
+            moments = [self._predict_one_imputation(layers, xd, m, True)[2] for layers in self.all_layer_set]
+        host = [[(L.to_host(mu), L.to_host(va)) for mu, va in per_layer] for per_layer in moments]
+        last = self.all_layer[-1]
+
+        def observe(latent):
+            out = np.empty((latent.shape[0], len(last)))
+            for count, kernel in enumerate(last):
+                out[:, count] = kernel.sampling(latent[:, kernel.input_dim])
+            return out
+
+        if not full_layer:
+            samples = []
+            for per_layer in host:
+                mu, va = per_layer[-2]
+                for _ in range(sample_size):
+                    samples.append(observe(np.random.normal(mu, np.sqrt(va))))
+            return list(np.asarray(samples).transpose(2, 1, 0))
+        out = []
+        before = None
+        for l in range(self.n_layer):
+            if l == self.n_layer - 1:
+                draws = [observe(latent) for latent in before]
+            else:
+                draws = [np.random.normal(per_layer[l][0], np.sqrt(per_layer[l][1]))
+                         for per_layer in host for _ in range(sample_size)]
+                if l == self.n_layer - 2:
+                    before = draws
+            out.append(list(np.asarray(draws).transpose(2, 1, 0)))
+        return out
 
     def ppredict(self, x, method='mean_var', full_layer=False, sample_size=50, m=50, chunk_num=None, core_num=None):
         """The reference splits test points over a process pool (emulation.py:578-629); one GPU replaces the

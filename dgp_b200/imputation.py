@@ -36,13 +36,25 @@ class _DeviceLayers:
         # stored factors belong to the previous hyper-parameters / inputs
         L.check(L.load().dgpb_cache_clear(L.workspace()))
         n = self.n
+        self.liks = None      # descriptors of a final likelihood layer
         for l, layer in enumerate(all_layer):
             for kern in layer:
-                if kern.type != 'gp':
-                    raise NotImplementedError("dgp_b200: likelihood layers are outside the SI hot path "
-                                              "(SURVEY.md section 2, row 10)")
                 if kern.rep is not None:
                     raise NotImplementedError("dgp_b200: replicate pooling is outside the SI hot path")
+            if any(kern.type != 'gp' for kern in layer):
+                if l != len(all_layer) - 1 or l == 0 or any(kern.type != 'likelihood' for kern in layer):
+                    raise NotImplementedError("dgp_b200: likelihood nodes are supported as a final layer made of "
+                                              "likelihood nodes only")
+                self.liks = []
+                for kern in layer:
+                    if kern.name not in L.LIK_KIND:
+                        raise NotImplementedError("dgp_b200: likelihood '%s' is outside the SI hot path" % kern.name)
+                    if any(k.vecch for k in all_layer[l - 1]) and kern.exact_post_idx is not None:
+                        raise NotImplementedError("dgp_b200: the exact Hetero posterior under Vecchia is not built")
+                    y = L.to_dev(np.ascontiguousarray(kern.output[:, 0], dtype=np.float64))
+                    self.keep.append(y)
+                    self.liks.append((kern, kern._descriptor(kern.input_dim, y), y))
+                continue
             Fl = L.to_dev(np.ascontiguousarray(np.stack([k.output[:, 0] for k in layer], 0)))
             self.F.append(Fl)
             arr = (L.DgpbNode * len(layer))()
@@ -88,7 +100,7 @@ class _DeviceLayers:
             tkeys = np.ascontiguousarray([self._key(l, k) for k in tks], dtype=np.int32)
             ukeys = np.ascontiguousarray([self._key(l + 1, j) for j in uks], dtype=np.int32)
             whole = len(tks) == len(self.nodes[l]) and len(uks) == len(self.nodes[l + 1])
-            if whole and l + 2 == len(self.nodes):  # outputs of the uppers are the fixed training targets
+            if whole and l + 2 == len(self.all_layer):  # outputs of the uppers are the fixed training targets
                 thr = ctypes.c_double(self.threshold.get(l, float("nan")))
         status = lib.dgpb_ess_block_cached(
             L.workspace(), targets, len(tks), rows.ctypes.data_as(L.c_vp), L.ptr(self.F[l]), self.F[l].shape[0], uppers,
@@ -106,6 +118,36 @@ class _DeviceLayers:
             self.threshold.pop(l, None)
         return nprop.value, theta[:nprop.value]
 
+    def lik_call(self, l, tks, lks, z, u):
+        """One `dgpb_ess_block_lik` call: targets `tks` of the last GP layer, likelihood nodes `lks`."""
+        lib = L.load()
+        n = self.n
+        targets = (L.DgpbNode * len(tks))(*[self.nodes[l][k] for k in tks])
+        liks = (L.DgpbLik * len(lks))(*[self.liks[j][1] for j in lks])
+        rows = np.ascontiguousarray(tks, dtype=np.int32)
+        zd = L.to_dev(np.ascontiguousarray(z, dtype=np.float64))
+        u = np.ascontiguousarray(u, dtype=np.float64)
+        theta = np.zeros(len(u))
+        nprop = ctypes.c_int(0)
+        tkeys = np.ascontiguousarray([self._key(l, k) for k in tks], dtype=np.int32)
+        status = lib.dgpb_ess_block_lik(
+            L.workspace(), targets, len(tks), rows.ctypes.data_as(L.c_vp), L.ptr(self.F[l]), self.F[l].shape[0], liks,
+            len(lks), n, L.ptr(zd), u.ctypes.data_as(L.c_vp), len(u), ctypes.byref(nprop),
+            theta.ctypes.data_as(L.c_vp), tkeys.ctypes.data_as(L.c_vp), L.stream())
+        self.last_nprop = nprop.value
+        L.check(status)
+        return nprop.value, theta[:nprop.value]
+
+    def hetero_update(self, l, k, j, sd=None):
+        """Exact conditional draw of the mean process feeding Hetero node j (imputation.py:141-164, dense branch);
+        `sd` (n x 2 standard normals) defaults to the reference's own draw."""
+        kern, desc, y = self.liks[j]
+        row_var = int(kern.input_dim[1])
+        if sd is None:
+            sd = np.random.randn(self.n, 2)                # likelihood_class.py:200
+        f = kern.posterior_dev(self.nodes[l][k], self.n, self.F[l][row_var], y, sd)
+        self.F[l][k].copy_(f)
+
     def block_update(self, l, tks, uks, max_u=64):
         """One ESS update of the target nodes `tks` of layer l given the upper nodes `uks` of layer l+1,
         drawing from the RNG streams described in the module docstring."""
@@ -119,7 +161,10 @@ class _DeviceLayers:
             state = np.random.get_state()
             u = np.random.uniform(size=max_u)
             try:
-                nprop, _ = self.ess_call(l, tks, uks, z, u)
+                if self.liks is not None and l + 2 == len(self.all_layer):
+                    nprop, _ = self.lik_call(l, tks, uks, z, u)
+                else:
+                    nprop, _ = self.ess_call(l, tks, uks, z, u)
             except ValueError:
                 if self.last_nprop + 1 < max_u:
                     raise
@@ -137,7 +182,7 @@ class _DeviceLayers:
             for k, kern in enumerate(self.all_layer[l]):
                 kern.output[:, 0] = Fl[k]
             for kern in self.all_layer[l + 1]:
-                kern.input = np.ascontiguousarray(Fl[kern.input_dim].T)
+                kern.input = np.ascontiguousarray(Fl[np.atleast_1d(kern.input_dim)].T)
 
 
 class imputer:
@@ -164,7 +209,18 @@ class imputer:
         for _ in range(burnin + 1):
             for l in range(n_layer - 1):
                 layer, linked = self.all_layer[l], self.all_layer[l + 1]
-                if self.block:
+                exact = any(kern.type == 'likelihood' and kern.exact_post_idx is not None for kern in linked)
+                if exact:   # imputation.py:34-42: node-wise updates, closed-form draw where the likelihood has one
+                    for k in range(len(layer)):
+                        uks = [j for j, kern in enumerate(linked) if k in kern.input_dim]
+                        if len(uks) == 1 and linked[uks[0]].exact_post_idx is not None:
+                            idx = np.where(np.asarray(linked[uks[0]].input_dim) == k)[0]
+                            if idx in linked[uks[0]].exact_post_idx:
+                                dev.hetero_update(l, k, uks[0])
+                                continue
+                        self.n_proposals += dev.block_update(l, [k], uks)
+                        self.n_block_updates += 1
+                elif self.block:
                     self.n_proposals += dev.block_update(l, list(range(len(layer))), list(range(len(linked))))
                     self.n_block_updates += 1
                 else:

@@ -1,0 +1,150 @@
+"""Likelihood nodes of a final DGP layer (dgpsi/likelihood_class.py): Poisson (:8-90), Hetero (:92-243) and NegBin
+(:245-292) -- SURVEY.md section 8f-3.
+
+The log-likelihood that enters the ESS acceptance rule is evaluated on the device (`dgpb_lik_loglik`; inside an
+I-step by `dgpb_ess_block_lik`, which keeps every proposal in HBM).  `Hetero.posterior` draws the mean process from
+its exact Gaussian conditional with the sliding-window factorisation (`dgpb_mvn_draw`,
+`dgpb_compute_stats_shifted`).  `prediction` / `sampling` / `pllik` are elementwise host formulas on the moments the
+prediction kernels return.  Out of scope: Categorical, ZIP, ZINB, replicate pooling (`rep`), Hetero under Vecchia.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+from scipy.special import gammaln
+
+from . import _lib as L
+
+
+class _Likelihood:
+    n_inputs = 1
+    exact_post_idx = None
+
+    def __init__(self, input_dim=None):
+        self.type = 'likelihood'
+        self.name = type(self).__name__
+        self.input = None
+        self.output = None
+        self.input_dim = input_dim
+        self.exact_post_idx = type(self).exact_post_idx
+        self.rep = None
+
+    def _descriptor(self, rows, y_dev):
+        d = L.DgpbLik()
+        d.kind = L.LIK_KIND[self.name]
+        for j, r in enumerate(rows):
+            d.rows[j] = int(r)
+        d.y = y_dev.data_ptr()
+        return d
+
+    def llik(self):
+        """Sum of the log-likelihood of the observed outputs given the latent inputs, evaluated on the device."""
+        F = L.to_dev(np.ascontiguousarray(self.input.T))
+        y = L.to_dev(np.ascontiguousarray(self.output[:, 0]))
+        d = (L.DgpbLik * 1)(self._descriptor(range(self.input.shape[1]), y))
+        out = ctypes.c_double(0.0)
+        L.check(L.load().dgpb_lik_loglik(d, 1, L.ptr(F), F.shape[1], ctypes.byref(out), L.stream()))
+        return out.value
+
+
+class Poisson(_Likelihood):
+    """Poisson likelihood fed by one GP node, the log rate (likelihood_class.py:8-90)."""
+    n_inputs = 1
+
+    @staticmethod
+    def pllik(y, f):
+        return y * f - np.exp(f) - gammaln(y + 1)
+
+    @staticmethod
+    def prediction(m, v):
+        y_mean = np.exp(m + v / 2)
+        y_var = np.exp(m + v / 2) + (np.exp(v) - 1) * np.exp(2 * m + v)
+        return y_mean.flatten(), y_var.flatten()
+
+    def sampling(self, f_sample):
+        return np.random.poisson(np.exp(f_sample)).flatten()
+
+
+class Hetero(_Likelihood):
+    """Heteroskedastic Gaussian likelihood fed by two GP nodes: mean and log variance (likelihood_class.py:92-243).
+    The mean node has a closed-form conditional posterior (`exact_post_idx = [0]`)."""
+    n_inputs = 2
+    exact_post_idx = np.array([0])
+
+    @staticmethod
+    def pllik(y, f):
+        mu, var = f[:, :, [0]], np.exp(f[:, :, [1]])
+        return -0.5 * (np.log(2 * np.pi * var) + (y - mu) ** 2 / var)
+
+    @staticmethod
+    def prediction(m, v):
+        y_mean = m[:, 0]
+        y_var = np.exp(m[:, 1] + v[:, 1] / 2) + v[:, 0]
+        return y_mean.flatten(), y_var.flatten()
+
+    @staticmethod
+    def sampling(f_sample):
+        return np.random.normal(f_sample[:, 0], np.sqrt(np.exp(f_sample[:, 1]))).flatten()
+
+    @staticmethod
+    def posterior_dev(node, n, log_var, y, sd):
+        """Draw of the mean process f | y, log variance (post_het1, likelihood_class.py:185-210) on the device.
+        With v = scale K the prior covariance and G = diag(exp(log_var)): u = chol(v) sd0, w = sqrt(G) sd1,
+        f = mu + u - v (v+G)^-1 (u+w), mu = v (v+G)^-1 y.  Writing x = (v+G)^-1 (y-u-w) this is u + v x, and since
+        v x = (y-u-w) - G x the draw is f = y - w - G x: one shifted factorisation, no matrix-vector product.
+        node: DgpbNode of the mean GP; log_var, y: device vectors; sd: (n x 2) standard normals (host)."""
+        torch = L.torch_mod()
+        lib = L.load()
+        z0, z1 = L.to_dev(np.ascontiguousarray(sd[:, 0])), L.to_dev(np.ascontiguousarray(sd[:, 1]))
+        u = L.empty((n,))
+        L.check(lib.dgpb_mvn_draw(L.workspace(), ctypes.byref(node), n, L.ptr(z0), L.ptr(u), L.stream()))
+        gamma = torch.exp(log_var)
+        w = torch.sqrt(gamma) * z1
+        rhs = (y - u - w).contiguous()
+        shift = (gamma / node.scale).contiguous()       # v + G = scale (K + G / scale)
+        tmp = L.DgpbNode.from_buffer_copy(node)
+        tmp.output = rhs.data_ptr()
+        Rinv, x = L.empty((n, n)), L.empty((n,))
+        L.check(lib.dgpb_compute_stats_shifted(L.workspace(), ctypes.byref(tmp), n, L.ptr(shift), L.ptr(Rinv), L.ptr(x),
+                                               L.stream()))
+        return y - w - shift * x                          # G x_true = (G / scale) x
+
+    def posterior(self, idx, v_node):
+        """Host-facing form of `Hetero.posterior` (likelihood_class.py:134-151): `v_node` is the GP node (a
+        `dgp_b200.kernel`) that produces the mean; returns the drawn mean vector."""
+        if int(np.atleast_1d(idx)[0]) != 0:
+            return None
+        if self.rep is not None:
+            raise NotImplementedError("dgp_b200: replicate pooling is outside the SI hot path")
+        n = len(self.output)
+        bufs = v_node._upload()
+        node = v_node._node(bufs)
+        sd = np.random.randn(n, 2)                        # likelihood_class.py:200
+        f = self.posterior_dev(node, n, L.to_dev(np.ascontiguousarray(self.input[:, 1])),
+                               L.to_dev(np.ascontiguousarray(self.output[:, 0])), sd)
+        return L.to_host(f)
+
+
+class NegBin(_Likelihood):
+    """Negative-binomial likelihood fed by two GP nodes: log mean and log dispersion (likelihood_class.py:245-292)."""
+    n_inputs = 2
+
+    @staticmethod
+    def pllik(y, f):
+        f1, f2 = f[:, :, [0]], f[:, :, [1]]
+        n = np.exp(-f2)
+        a = f1 + f2
+        return gammaln(y + n) - gammaln(n) - gammaln(y + 1.0) + y * a - (y + n) * np.logaddexp(0.0, a)
+
+    @staticmethod
+    def prediction(m, v):
+        y_mean = np.exp(m[:, 0] + v[:, 0] / 2)
+        y_var = (np.exp(2 * m[:, 0] + v[:, 0]) * (np.exp(v[:, 0]) - 1) + np.exp(m[:, 0] + v[:, 0] / 2)
+                 + np.exp(m[:, 1] + v[:, 1] / 2) * np.exp(2 * m[:, 0] + 2 * v[:, 0]))
+        return y_mean.flatten(), y_var.flatten()
+
+    @staticmethod
+    def sampling(f_sample):
+        p, k = 1 / (1 + np.exp(f_sample[:, 0] + f_sample[:, 1])), np.exp(-f_sample[:, 1])
+        return np.random.negative_binomial(k, p).flatten()

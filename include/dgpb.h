@@ -38,6 +38,11 @@ extern "C" {
 #define DGPB_SEXP 0      /* kernel(name='sexp')      kernel_class.py:325-332 */
 #define DGPB_MATERN25 1  /* kernel(name='matern2.5') kernel_class.py:333-345 */
 
+/* likelihood nodes of a final layer (likelihood_class.py:8-90, 92-243, 245-292) */
+#define DGPB_LIK_POISSON 0
+#define DGPB_LIK_HETERO 1
+#define DGPB_LIK_NEGBIN 2
+
 #define DGPB_MAX_DIM 32  /* maximum node input dimension (local + connected global) */
 
 typedef struct dgpb_ws dgpb_ws; /* opaque workspace */
@@ -70,6 +75,14 @@ typedef struct dgpb_node {
     int32_t m;                 /* conditioning-set size */
     int32_t vecch;
 } dgpb_node;
+
+/* One likelihood node: which rows of the feeding layer it reads (`input_dim`: one row for Poisson -- the log
+ * rate; two for Hetero -- mean, log variance -- and NegBin -- log mean, log dispersion) and the observed outputs. */
+typedef struct dgpb_lik {
+    int32_t kind;     /* DGPB_LIK_* */
+    int32_t rows[3];
+    const double* y;  /* device, n */
+} dgpb_lik;
 
 const char* dgpb_last_error(void);
 int dgpb_version(void);
@@ -114,6 +127,10 @@ int dgpb_nllik_grad_dense_batch(dgpb_ws* ws, const dgpb_node* nodes, int B, int6
 /* kernel.compute_stats  kernel_class.py:735-748: Rinv (n x n, full symmetric) and Rinv_y (n). */
 int dgpb_compute_stats(dgpb_ws* ws, const dgpb_node* node, int64_t n, double* Rinv, double* Rinv_y,
                        void* stream);
+/* The same for R = K + diag(diag_shift) (device, n): the linear solves of Hetero.post_het1
+ * (likelihood_class.py:185-210), where the observation variances sit on top of the node's nugget. */
+int dgpb_compute_stats_shifted(dgpb_ws* ws, const dgpb_node* node, int64_t n, const double* diag_shift, double* Rinv,
+                               double* Rinv_y, void* stream);
 
 /* fmvn(scale*K)  functions.py:113-121 with the standard-normal vector z injected:
  * nu = chol(scale*K) z. */
@@ -151,6 +168,16 @@ int dgpb_ess_block_cached(dgpb_ws* ws, const dgpb_node* targets, int n_targets, 
                           int* n_prop_host, double* theta_host, const int32_t* target_keys_host,
                           const int32_t* upper_keys_host, double* threshold_io_host, void* stream);
 int dgpb_cache_clear(dgpb_ws* ws);
+
+/* Likelihood layers.  dgpb_lik_loglik: sum of `llik()` (likelihood_class.py:39-48, 110-116, 264-272) over the
+ * likelihood nodes for the latent layer image `layer` (layer_width x n, device); one double to the host.
+ * dgpb_ess_block_lik: imputer.one_sample_block / one_sample (imputation.py:44-119, 166-221) for target GP nodes whose
+ * outputs feed likelihood nodes only; arguments as dgpb_ess_block_cached with the upper GP nodes replaced by `liks`. */
+int dgpb_lik_loglik(const dgpb_lik* liks, int n_liks, const double* layer, int64_t n, double* out_host, void* stream);
+int dgpb_ess_block_lik(dgpb_ws* ws, const dgpb_node* targets, int n_targets, const int32_t* target_rows_host,
+                       double* layer_out, int64_t layer_width, const dgpb_lik* liks, int n_liks, int64_t n,
+                       const double* z, const double* u_host, int nu, int* n_prop_host, double* theta_host,
+                       const int32_t* target_keys_host, void* stream);
 
 /* ---- 4. Vecchia ---------------------------------------------------------------------------- */
 

@@ -833,6 +833,48 @@ class Node:
             minimize(self.objective, x0, method="L-BFGS-B", jac=True, options=opts)
 
 
+class LikNode:
+    """Likelihood node of a final layer -- likelihood_class.py: Poisson :39-48, Hetero :110-116, NegBin :264-272."""
+
+    def __init__(self, name, input_dim, output):
+        self.name, self.input_dim, self.output = name, np.asarray(input_dim), output
+        self.input = None
+
+    def loglik(self):
+        from scipy.special import gammaln
+        y, f = self.output.flatten(), self.input
+        if self.name == "Poisson":
+            return np.sum(y * f[:, 0] - np.exp(f[:, 0]) - gammaln(y + 1))
+        if self.name == "Hetero":
+            with np.errstate(divide="ignore"):
+                return np.sum(-0.5 * (np.log(2 * np.pi) + f[:, 1] + np.exp(np.log((y - f[:, 0]) ** 2) - f[:, 1])))
+        n = np.exp(-f[:, 1])
+        a = f[:, 0] + f[:, 1]
+        return np.sum(gammaln(y + n) - gammaln(n) - gammaln(y + 1.0) + y * a - (y + n) * np.logaddexp(0.0, a))
+
+    def prediction(self, m, v):
+        """Moments of the observable from Gaussian moments of the latent inputs -- likelihood_class.py:65-78,
+        124-128, 283-287."""
+        if self.name == "Poisson":
+            return (np.exp(m + v / 2)).flatten(), (np.exp(m + v / 2) + (np.exp(v) - 1) * np.exp(2 * m + v)).flatten()
+        if self.name == "Hetero":
+            return m[:, 0], np.exp(m[:, 1] + v[:, 1] / 2) + v[:, 0]
+        return (np.exp(m[:, 0] + v[:, 0] / 2),
+                np.exp(2 * m[:, 0] + v[:, 0]) * (np.exp(v[:, 0]) - 1) + np.exp(m[:, 0] + v[:, 0] / 2)
+                + np.exp(m[:, 1] + v[:, 1] / 2) * np.exp(2 * m[:, 0] + 2 * v[:, 0]))
+
+
+def post_het1(v, Gamma, y, sd):
+    """Exact conditional draw of the Hetero mean process with injected normals sd (n x 2) --
+    likelihood_class.py:185-210."""
+    Lc = cholesky(v + np.diag(Gamma), lower=True)
+    L1 = cholesky(v, lower=True)
+    mu = v @ cho_solve((Lc, True), y.flatten())
+    u = L1 @ sd[:, 0]
+    w = np.sqrt(Gamma) * sd[:, 1]
+    return -v @ cho_solve((Lc, True), u + w) + (mu + u)
+
+
 def ess_block(targets, uppers, z, u):
     """One blocked ESS update of a latent layer with INJECTED randomness -- imputation.py:44-119.
 
@@ -859,6 +901,32 @@ def ess_block(targets, uppers, z, u):
         if sum(up.loglik() for up in uppers) > log_y:
             for k, t in enumerate(targets):
                 t.output[:, 0] = fp[:, k]
+            return thetas, ui
+        if theta < 0.0:
+            tmin = theta
+        else:
+            tmax = theta
+        theta = tmin + (tmax - tmin) * u[ui]; ui += 1
+
+
+def ess_one(target, k, uppers, z, u):
+    """Node-wise ESS update of target node k of its layer with INJECTED randomness -- imputation.py:166-221: only
+    column `input_dim == k` of every linked upper node moves.  Returns (thetas tried, uniforms consumed)."""
+    f = target.output.flatten()
+    nu = target.prior_draw(z)
+    u = list(u)
+    ui = 0
+    log_y = sum(up.loglik() for up in uppers) + np.log(u[ui]); ui += 1
+    theta = u[ui] * 2.0 * np.pi; ui += 1
+    tmin, tmax = theta - 2.0 * np.pi, theta
+    thetas = []
+    while True:
+        thetas.append(theta)
+        fp = f * np.cos(theta) + nu * np.sin(theta)
+        for up in uppers:
+            up.input[:, np.asarray(up.input_dim) == k] = fp.reshape(-1, 1)
+        if sum(up.loglik() for up in uppers) > log_y:
+            target.output[:, 0] = fp
             return thetas, ui
         if theta < 0.0:
             tmin = theta

@@ -61,3 +61,8 @@ def golden_metric():
 @pytest.fixture(scope="session")
 def golden_update():
     return load_golden("update")
+
+
+@pytest.fixture(scope="session")
+def golden_lik():
+    return load_golden("likelihood")

@@ -837,6 +837,117 @@ def test_warm_start_update_xy(golden_update):
         model.update_xy(Xo[:, 0], Yo)
 
 
+LIK_CASES = (("poi", "Poisson", 1), ("nb", "NegBin", 2), ("het", "Hetero", 2))
+
+
+def _lik_model(g, prefix, likname, width, Y, stats=False):
+    import dgp_b200 as D
+
+    layers = _snapshot_layers(g, prefix, lambda l, k: "sexp" if l == 0 else "matern2.5")
+    assert len(layers) == 2 and len(layers[1]) == width
+    if stats:
+        for layer in layers:
+            for node in layer:
+                node.compute_stats()
+    lik = getattr(D, likname)(input_dim=np.arange(width))
+    lik.output = Y.copy()
+    lik.input = np.hstack([node.output for node in layers[1]])
+    return layers + [[lik]], lik
+
+
+def test_likelihood_layers_vs_reference(golden_lik):
+    """Poisson / NegBin / Hetero final layers: device log-likelihood, ESS sweeps replayed with the
+    reference's own draws through dgpb_ess_block_lik (Hetero: node-wise, the mean drawn from its exact Gaussian
+    conditional by the shifted factorisation), and emulator predictions on the reference's imputed states."""
+    from dgp_b200.imputation import _DeviceLayers
+    import dgp_b200 as D
+
+    g = golden_lik
+    for tag, likname, width in LIK_CASES:
+        p = f"{tag}_"
+        layers, lik = _lik_model(g, p + "pre_", likname, width, g[p + "Y"])
+        assert np.array_equal(lik.input, g[p + "lik_input_pre"])
+        ref = float(g[p + "llik_pre"])
+        assert abs(lik.llik() - ref) <= 1e-10 * abs(ref), tag
+        dev = _DeviceLayers(layers)
+        Z, U, SD = g[p + "Z"], g[p + "U"], g[p + "SD"]
+        pad = np.full(4, 0.5)
+        zi = ui = si = 0
+        values = []
+        for _ in range(int(g[p + "sweeps"])):
+            nprop, th = dev.ess_call(0, [0, 1], list(range(width)), Z[zi:zi + 2], np.concatenate((U[ui:], pad)))
+            zi += 2
+            values.append(U[ui]); values.extend(th); ui += 1 + nprop
+            if likname == "Hetero":
+                dev.hetero_update(1, 0, 0, sd=SD[si])
+                si += 1
+                nprop, th = dev.lik_call(1, [1], [0], Z[zi:zi + 1], np.concatenate((U[ui:], pad)))
+                zi += 1
+            else:
+                nprop, th = dev.lik_call(1, list(range(width)), [0], Z[zi:zi + width], np.concatenate((U[ui:], pad)))
+                zi += width
+            values.append(U[ui]); values.extend(th); ui += 1 + nprop
+        assert zi == len(Z) and ui == len(U) and si == len(SD), (tag, ui, len(U))
+        assert np.allclose(values, g[p + "draw_values"], rtol=1e-12, atol=0), tag
+        dev.write_back()
+        for l in range(2):
+            for k, node in enumerate(layers[l]):
+                assert relerr(node.output, g[f"{p}post_L{l}K{k}_output"], 1e-4) <= 1e-6, (tag, l, k)
+        ref = float(g[p + "llik_post"])
+        assert abs(lik.llik() - ref) <= 1e-6 * abs(ref), tag
+        # predictions on the reference's imputed states
+        emu = D.emulator.__new__(D.emulator)
+        emu.all_layer_set = [_lik_model(g, f"{p}S{s}_", likname, width, g[p + "Y"], stats=True)[0]
+                             for s in range(int(g[p + "nimp"]))]
+        emu.all_layer, emu.n_layer, emu.vecch = emu.all_layer_set[0], 3, False
+        mu, var = emu.predict(g[p + "xt"])
+        assert mu.shape == g[p + "mu"].shape
+        assert np.max(np.abs(mu - g[p + "mu"]) / (1e-3 + np.abs(g[p + "mu"]))) <= 2e-5, tag
+        assert np.max(np.abs(var - g[p + "var"]) / (1e-3 + np.abs(g[p + "var"]))) <= 2e-5, tag
+        mus, vars_ = emu.predict(g[p + "xt"], full_layer=True)
+        assert len(mus) == 3
+        assert np.max(np.abs(mus[-2] - g[p + "mu_full_gp"])) <= 5e-6 * max(1.0, np.max(np.abs(g[p + "mu_full_gp"]))), tag
+        assert np.max(np.abs(mus[-1] - g[p + "mu_full_last"]) / (1e-3 + np.abs(g[p + "mu_full_last"]))) <= 2e-5, tag
+        samples = emu.predict(g[p + "xt"], method="sampling", sample_size=3)
+        assert len(samples) == 1 and samples[0].shape == (len(g[p + "xt"]), 3 * len(emu.all_layer_set))
+        full = emu.predict(g[p + "xt"], method="sampling", sample_size=2, full_layer=True)
+        assert len(full) == 3 and full[1][0].shape == (len(g[p + "xt"]), 2 * len(emu.all_layer_set))
+
+
+@pytest.mark.parametrize("likname", ["Poisson", "NegBin", "Hetero"])
+def test_likelihood_public_api(likname):
+    """dgp(X, Y, combine(..., [likelihood])) -> train -> estimate -> emulator -> predict through the public API."""
+    import dgp_b200 as D
+
+    rng = np.random.default_rng(11)
+    np.random.seed(11)
+    D.nb_seed(11)
+    n, d = 40, 2
+    X = rng.uniform(0, 1, size=(n, d))
+    gx = np.sin(3 * X[:, 0]) + X[:, 1]
+    width = 1 if likname == "Poisson" else 2
+    if likname == "Hetero":
+        Y = (gx + np.exp(-1.5 + X[:, 0]) * rng.standard_normal(n)).reshape(-1, 1)
+    else:
+        Y = rng.poisson(np.exp(1.0 + gx)).astype(float).reshape(-1, 1)
+    l1 = [D.kernel(length=np.array([1.0]), name="sexp") for _ in range(d)]
+    l2 = [D.kernel(length=np.array([1.0]), name="sexp", scale_est=True, connect=np.arange(d)) for _ in range(width)]
+    model = D.dgp(X, Y, D.combine(l1, l2, [getattr(D, likname)()]))
+    assert model.all_layer[-1][0].input.shape == (n, width)
+    model.train(N=3, disable=True)
+    assert model.all_layer[1][0].para_path.shape[0] == 4
+    emu = D.emulator(model.estimate(), N=2)
+    xt = rng.uniform(0, 1, size=(12, d))
+    mu, var = emu.predict(xt)
+    assert mu.shape == (12, 1) and np.all(np.isfinite(mu)) and np.all(var > 0)
+    if likname != "Hetero":
+        assert np.all(mu > 0)          # a count mean
+    with pytest.raises(NotImplementedError):
+        emu.metric(xt)
+    with pytest.raises(Exception):
+        D.dgp(X, Y, D.combine(l1, [D.kernel(length=np.array([1.0]))] * (3 - width), [getattr(D, likname)()]))
+
+
 def test_public_api_train_and_predict_smoke():
     """The user-facing path runs: dgp(X,Y).train -> estimate -> emulator -> predict; the fit is sane."""
     import dgp_b200 as D
