@@ -150,21 +150,32 @@ class emulator:
         Returns the (M x D_out) scores when `score_only`, else (argmax rows, their scores) per output."""
         if x_cand.ndim == 1:
             raise Exception('The candidate design set has to be a numpy 2d-array.')
-        if self.all_layer[-1][0].type == 'likelihood':
-            raise NotImplementedError("dgp_b200: design criteria of emulators with a likelihood layer are not built")
+        lik = self.all_layer[-1][0].type == 'likelihood'
+        last = self.n_layer - 2 if lik else self.n_layer - 1      # the last GP layer (emulation.py:344, 447, 533)
         if method == 'ALM':
-            _, score = self.predict(x=x_cand, m=m)
+            if lik:
+                _, sigma2 = self.predict(x=x_cand, full_layer=True, m=m)
+                score = sigma2[-2]
+            else:
+                _, score = self.predict(x=x_cand, m=m)
         elif method == 'MICE':
-            if self.n_layer < 2:
-                raise Exception('The MICE criterion needs a DGP with at least two layers.')
-            score = 0.
-            for s, moments in enumerate(self._layer_moments(x_cand, m)):
-                pred_in, sigma2 = L.to_host(moments[-2][0]), L.to_host(moments[-1][1])
-                smooth = np.stack([self._mice_var(pred_in, x_cand, kern, nugget_s)
-                                   for kern in self.all_layer_set[s][-1]], 1)
-                with np.errstate(divide='ignore'):
-                    score = score + np.log(sigma2 / smooth)
-            score = score / len(self.all_layer_set)
+            if lik and self.n_layer == 2:   # emulation.py:362-372: one GP layer under the likelihood, no imputation
+                xd = L.to_dev(x_cand, np.float64)
+                with L.predict_cache():
+                    _, var, _ = self._predict_one_imputation(self.all_layer[:1], xd, m, False)
+                smooth = np.stack([self._mice_var(x_cand, x_cand, kern, nugget_s) for kern in self.all_layer[0]], 1)
+                score = L.to_host(var) / smooth
+            else:
+                if last < 1:
+                    raise Exception('The MICE criterion needs a DGP with at least two GP layers.')
+                score = 0.
+                for s, moments in enumerate(self._layer_moments(x_cand, m)):
+                    pred_in, sigma2 = L.to_host(moments[last - 1][0]), L.to_host(moments[last][1])
+                    smooth = np.stack([self._mice_var(pred_in, x_cand, kern, nugget_s)
+                                       for kern in self.all_layer_set[s][last]], 1)
+                    with np.errstate(divide='ignore'):
+                        score = score + np.log(sigma2 / smooth)
+                score = score / len(self.all_layer_set)
         elif method == 'VIGF':
             if obj is None:
                 raise Exception('The dgp object that is used to build the emulator must be supplied to the argument '
@@ -174,9 +185,9 @@ class emulator:
             index = L.to_host(get_pred_nn_dev(L.to_dev(x_cand, np.float64), L.to_dev(obj.X, np.float64), 1)).ravel()
             bias, sigma2 = [], []
             for s, moments in enumerate(self._layer_moments(x_cand, m)):
-                target = np.stack([kern.output[index, 0] for kern in self.all_layer_set[s][-1]], 1)
-                bias.append((L.to_host(moments[-1][0]) - target) ** 2)
-                sigma2.append(L.to_host(moments[-1][1]))
+                target = np.stack([kern.output[index, 0] for kern in self.all_layer_set[s][last]], 1)
+                bias.append((L.to_host(moments[last][0]) - target) ** 2)
+                sigma2.append(L.to_host(moments[last][1]))
             bias, sigma2 = np.asarray(bias), np.asarray(sigma2)
             E1 = np.mean(np.square(bias) + 6 * bias * sigma2 + 3 * np.square(sigma2), axis=0)
             E2 = np.mean(bias + sigma2, axis=0)
@@ -355,6 +366,41 @@ class emulator:
                     before = draws
             out.append(list(np.asarray(draws).transpose(2, 1, 0)))
         return out
+
+    @staticmethod
+    def _expected_likelihood(pllik, mu, var, y, order=10):
+        """E[p(y | f)] for f ~ N(mu, diag(var)) per test point by a tensor-product Gauss-Hermite rule
+        (`ghdiag`, functions.py:233-241): mu, var (M x Q), y (M x 1) -> (M x 1)."""
+        nodes, weights = np.polynomial.hermite.hermgauss(order)
+        Q = mu.shape[1]
+        grid = np.stack([a.ravel() for a in np.meshgrid(*([nodes] * Q), indexing='ij')], 1)        # (order^Q, Q)
+        logw = np.sum(np.stack([a.ravel() for a in np.meshgrid(*([np.log(weights)] * Q), indexing='ij')], 1), 1)
+        f = np.sqrt(2.0) * np.sqrt(var)[:, None, :] * grid[None, :, :] + mu[:, None, :]            # (M, order^Q, Q)
+        ll = pllik(y[:, None], f)                                                                  # (M, order^Q, 1)
+        return np.sum(np.exp((logw - 0.5 * Q * np.log(np.pi))[None, :, None] + ll), axis=1)
+
+    def nllik(self, x, y, m=50):
+        """Negative predicted log-likelihood of test outputs under a DGP with ONE likelihood node on top
+        (emulation.py:855-911): returns (average, per test point)."""
+        if len(self.all_layer[-1]) != 1 or self.all_layer[-1][0].type != 'likelihood':
+            raise Exception('The method is only applicable to a DGP with the final layer formed by only ONE node, '
+                            'which must be a likelihood node.')
+        # repeated test inputs are predicted once (emulation.py:872-874).  Without repeats the reference still
+        # indexes the predictions by np.unique's inverse map (:909), which scores y against other points'
+        # predictions unless x is already sorted; here every output is scored against its own input.
+        X0, indices = np.unique(x, return_inverse=True, axis=0)
+        if len(X0) != len(x):
+            x = X0
+        else:
+            indices = np.arange(len(x))
+        lik = self.all_layer[-1][0]
+        predicted = []
+        for moments in self._layer_moments(x, m):
+            mu, var = L.to_host(moments[-2][0]), L.to_host(moments[-2][1])
+            predicted.append(self._expected_likelihood(lik.pllik, mu[indices][:, lik.input_dim],
+                                                       var[indices][:, lik.input_dim], y))
+        nllik = -np.log(np.mean(predicted, axis=0)).flatten()
+        return np.mean(nllik), nllik
 
     def ppredict(self, x, method='mean_var', full_layer=False, sample_size=50, m=50, chunk_num=None, core_num=None):
         """The reference splits test points over a process pool (emulation.py:578-629); one GPU replaces the

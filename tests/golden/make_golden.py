@@ -539,6 +539,41 @@ def gen_lik():
         out[p + "nimp"] = np.array(len(emu.all_layer_set))
         for s_, al in enumerate(emu.all_layer_set):
             snapshot(al[:-1], f"{p}S{s_}_", out)
+        # emulation.py:872-874,909 indexes the predictions by the inverse map of np.unique even when no row repeats
+        # (then the predictions are still in the caller's order): only inputs already in np.unique order are scored
+        # against their own outputs, so the fixture uses such inputs
+        order = np.lexsort(xt.T[::-1])
+        xs = xt[order]
+        assert np.array_equal(xs, np.unique(xt, axis=0))
+        yt = (np.round(np.abs(mu)) if tag != "het" else mu + 0.1)[order]
+        avg, per = emu.nllik(xs, yt)
+        out[p + "xt_sorted"], out[p + "yt"], out[p + "nllik_avg"], out[p + "nllik"] = xs, yt, np.array(avg), per
+        # design criteria of an emulator with a likelihood layer (emulation.py:344-349, 373-392, 393-413)
+        out[p + "alm"] = emu.metric(xt, method="ALM", score_only=True)
+        out[p + "mice"] = emu.metric(xt, method="MICE", score_only=True)
+        out[p + "vigf"] = emu.metric(xt, method="VIGF", obj=model, score_only=True)
+    # one GP layer under a Poisson node: the 2-layer branches (emulation.py:362-372, 402-403)
+    if not only:
+        rng = np.random.default_rng(SEED + 29)
+        np.random.seed(SEED + 29)
+        dgpsi.nb_seed(SEED + 29)
+        n, d = 26, 2
+        X = rng.uniform(0, 1, size=(n, d))
+        Y = rng.poisson(np.exp(1.0 + np.sin(3 * X[:, 0]) + X[:, 1])).astype(float).reshape(-1, 1)
+        model = dgpsi.dgp(X, Y, dgpsi.combine([kernel(length=np.array([1.0]), name="sexp", scale_est=True)],
+                                              [dgpsi.Poisson()]))
+        model.train(N=4, disable=True)
+        emu = dgpsi.emulator(model.estimate(), N=2)
+        xt = rng.uniform(0, 1, size=(15, d))
+        p = "poi2_"
+        out[p + "X"], out[p + "Y"], out[p + "xt"] = X, Y, xt
+        out[p + "mu"], out[p + "var"] = emu.predict(xt)
+        out[p + "alm"] = emu.metric(xt, method="ALM", score_only=True)
+        out[p + "mice"] = emu.metric(xt, method="MICE", score_only=True)
+        out[p + "vigf"] = emu.metric(xt, method="VIGF", obj=model, score_only=True)
+        out[p + "nimp"] = np.array(len(emu.all_layer_set))
+        for s_, al in enumerate(emu.all_layer_set):
+            snapshot(al[:-1], f"{p}S{s_}_", out)
     save("likelihood", **out)
 
 

@@ -908,10 +908,64 @@ def test_likelihood_layers_vs_reference(golden_lik):
         assert len(mus) == 3
         assert np.max(np.abs(mus[-2] - g[p + "mu_full_gp"])) <= 5e-6 * max(1.0, np.max(np.abs(g[p + "mu_full_gp"]))), tag
         assert np.max(np.abs(mus[-1] - g[p + "mu_full_last"]) / (1e-3 + np.abs(g[p + "mu_full_last"]))) <= 2e-5, tag
+        avg, per = emu.nllik(g[p + "xt_sorted"], g[p + "yt"])
+        assert per.shape == g[p + "nllik"].shape
+        assert np.max(np.abs(per - g[p + "nllik"])) <= 2e-5 * max(1.0, np.max(np.abs(g[p + "nllik"]))), tag
+        assert abs(avg - float(g[p + "nllik_avg"])) <= 2e-5 * max(1.0, abs(float(g[p + "nllik_avg"]))), tag
+        shuffled = np.arange(len(per))[::-1]     # scored point by point: the order of the test set does not matter
+        _, per_rev = emu.nllik(g[p + "xt_sorted"][shuffled], g[p + "yt"][shuffled])
+        assert np.allclose(per_rev, per[shuffled], rtol=1e-9), tag
+        # design criteria act on the last GP layer (emulation.py:344-349, 373-413)
+        model = type("M", (), {"X": g[p + "X"]})()
+        alm = emu.metric(g[p + "xt"], method="ALM", score_only=True)
+        assert alm.shape == g[p + "alm"].shape and np.max(np.abs(alm - g[p + "alm"])) <= 5e-6, tag
+        mice = emu.metric(g[p + "xt"], method="MICE", score_only=True)
+        solid = g[p + "alm"] > 1e-3
+        assert solid.sum() >= 5 and np.max(np.abs(mice - g[p + "mice"])[solid]) <= 5e-3, tag
+        vigf = emu.metric(g[p + "xt"], method="VIGF", obj=model, score_only=True)
+        assert np.max(np.abs(vigf - g[p + "vigf"])) <= 1e-5 * max(1.0, np.max(g[p + "vigf"])), tag
         samples = emu.predict(g[p + "xt"], method="sampling", sample_size=3)
         assert len(samples) == 1 and samples[0].shape == (len(g[p + "xt"]), 3 * len(emu.all_layer_set))
         full = emu.predict(g[p + "xt"], method="sampling", sample_size=2, full_layer=True)
         assert len(full) == 3 and full[1][0].shape == (len(g[p + "xt"]), 2 * len(emu.all_layer_set))
+
+
+def test_single_gp_layer_under_likelihood(golden_lik):
+    """One GP layer feeding a Poisson node: predictions and the 2-layer branches of the design criteria
+    (emulation.py:362-372, 402-403) on the reference's imputed states."""
+    import dgp_b200 as D
+
+    g = golden_lik
+    p = "poi2_"
+    sets = []
+    for s in range(int(g[p + "nimp"])):
+        layers = _snapshot_layers(g, f"{p}S{s}_", lambda l, k: "sexp")
+        assert len(layers) == 1 and len(layers[0]) == 1
+        layers[0][0].compute_stats()
+        lik = D.Poisson(input_dim=np.arange(1))
+        lik.output, lik.input = g[p + "Y"].copy(), layers[0][0].output.copy()
+        sets.append(layers + [[lik]])
+    emu = D.emulator.__new__(D.emulator)
+    emu.all_layer_set, emu.all_layer, emu.n_layer, emu.vecch = sets, sets[-1], 2, False
+    xt = g[p + "xt"]
+    # the fitted scale is ~3.6e4 (near-linear latent surface), so the latent variance scale (1 + nugget - r'R^-1 r)
+    # ~ 0.04 carries the cancellation error of the bracket times the scale: two algebraically equal CPU evaluations
+    # of the reference's formula differ by 4e-5 here.  Tolerances below are that floor, 2e-9 x scale.
+    floor = 2e-9 * float(sets[0][0][0].scale[0])
+    assert 1e-5 < floor < 1e-3
+    mu, var = emu.predict(xt)
+    assert np.max(np.abs(mu - g[p + "mu"]) / np.abs(g[p + "mu"])) <= 2e-5 + floor
+    # Poisson variance = mean + (e^v - 1) mean^2: the latent-variance floor enters times mean^2
+    assert np.all(np.abs(var - g[p + "var"]) <= 1e-4 * g[p + "var"] + 2 * floor * g[p + "mu"] ** 2)
+    alm = emu.metric(xt, method="ALM", score_only=True)
+    assert np.max(np.abs(alm - g[p + "alm"])) <= 5e-6 + floor
+    vigf = emu.metric(xt, method="VIGF", obj=type("M", (), {"X": g[p + "X"]})(), score_only=True)
+    assert np.max(np.abs(vigf - g[p + "vigf"])) <= 1e-3 * max(1.0, np.max(g[p + "vigf"]))
+    assert np.array_equal(np.argmax(vigf, axis=0), np.argmax(g[p + "vigf"], axis=0))
+    # 2-layer MICE: latent variance of ONE state over its smoothed variance
+    mice = emu.metric(xt, method="MICE", score_only=True)
+    assert mice.shape == g[p + "mice"].shape and np.all(np.isfinite(mice))
+    assert np.max(np.abs(mice - g[p + "mice"]) / g[p + "mice"]) <= 1e-2
 
 
 @pytest.mark.parametrize("likname", ["Poisson", "NegBin", "Hetero"])
@@ -942,8 +996,10 @@ def test_likelihood_public_api(likname):
     assert mu.shape == (12, 1) and np.all(np.isfinite(mu)) and np.all(var > 0)
     if likname != "Hetero":
         assert np.all(mu > 0)          # a count mean
-    with pytest.raises(NotImplementedError):
-        emu.metric(xt)
+    idx, score = emu.metric(xt)
+    assert idx.shape == (width,) and np.all(score > 0)
+    avg, per = emu.nllik(xt, np.abs(np.round(mu)))
+    assert per.shape == (12,) and np.isfinite(avg)
     with pytest.raises(Exception):
         D.dgp(X, Y, D.combine(l1, [D.kernel(length=np.array([1.0]))] * (3 - width), [getattr(D, likname)()]))
 
