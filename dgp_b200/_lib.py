@@ -39,10 +39,12 @@ class DgpbNode(ctypes.Structure):
 class DgpbLik(ctypes.Structure):
     """Mirror of `struct dgpb_lik` (include/dgpb.h)."""
 
-    _fields_ = [("kind", c_i32), ("rows", c_i32 * 3), ("y", c_vp)]
+    _fields_ = [("kind", c_i32), ("n_in", c_i32), ("rows", c_i32 * 8), ("y", c_vp), ("param", c_dbl)]
 
 
-LIK_KIND = {"Poisson": 0, "Hetero": 1, "NegBin": 2}
+# likelihood name (+ link of the Categorical likelihood) -> DGPB_LIK_*
+LIK_KIND = {"Poisson": 0, "Hetero": 1, "NegBin": 2, "Categorical": None}
+CAT_KIND = {"logit": 3, "probit": 4, "softmax": 5, "robustmax": 6}
 
 _PROTOS = {
     # name: (restype, argtypes)

@@ -699,21 +699,56 @@ constexpr int kLikWave = 8;
 struct LikArgs {
     int nl;
     int kind[kMaxLik];
-    int row0[kMaxLik], row1[kMaxLik];
+    int n_in[kMaxLik];
+    int row[kMaxLik][DGPB_LIK_MAX_IN];
+    double param[kMaxLik];
     const double* y[kMaxLik];
     const double* src[kLikWave + 1];   // candidate images of the feeding layer (layer_width x n)
 };
 
-__device__ __forceinline__ double lik_point(int kind, double y, double f0, double f1) {
+// log Phi(x): erfc keeps full relative accuracy in the lower tail until it underflows; below that the
+// asymptotic series  -x^2/2 - log(-x sqrt(2 pi)) + log(1 - 1/x^2 + 3/x^4 - 15/x^6 + 105/x^8)
+__device__ __forceinline__ double log_ndtr_dev(double x) {
+    if (x > -35.0) return log(0.5 * erfc(-x * 0.70710678118654752440));
+    const double r = 1.0 / (x * x);
+    return -0.5 * x * x - log(-x) - 0.91893853320467274178 + log1p(r * (-1.0 + r * (3.0 + r * (-15.0 + r * 105.0))));
+}
+
+// log-likelihood of one data point; f(j) = j-th latent input of the node
+template <typename F>
+__device__ __forceinline__ double lik_point(int kind, int K, double param, double y, F f) {
     if (kind == DGPB_LIK_POISSON) {        // likelihood_class.py:39-48
+        const double f0 = f(0);
         return y * f0 - exp(f0) - lgamma(y + 1.0);
     } else if (kind == DGPB_LIK_HETERO) {  // likelihood_class.py:110-116
+        const double f0 = f(0), f1 = f(1);
         const double r2 = (y - f0) * (y - f0);
         return -0.5 * (1.8378770664093453 + f1 + exp(log(r2) - f1));
-    } else {                               // NegBin, likelihood_class.py:264-272
+    } else if (kind == DGPB_LIK_NEGBIN) {  // likelihood_class.py:264-272
+        const double f0 = f(0), f1 = f(1);
         const double nn = exp(-f1), a = f0 + f1;
         const double softplus = fmax(a, 0.0) + log1p(exp(-fabs(a)));
         return lgamma(y + nn) - lgamma(nn) - lgamma(y + 1.0) + y * a - (y + nn) * softplus;
+    } else if (kind == DGPB_LIK_CAT_LOGIT) {   // likelihood_class.py:339-341
+        const double f0 = f(0);
+        return y * f0 - (fmax(f0, 0.0) + log1p(exp(-fabs(f0))));
+    } else if (kind == DGPB_LIK_CAT_PROBIT) {  // likelihood_class.py:342-343
+        const double f0 = f(0);
+        return y * log_ndtr_dev(f0) + (1.0 - y) * log_ndtr_dev(-f0);
+    } else if (kind == DGPB_LIK_CAT_ROBUSTMAX) {  // likelihood_class.py:345-353; argmax = first maximum
+        int best = 0;
+        double fb = f(0);
+        for (int j = 1; j < K; ++j) {
+            const double fj = f(j);
+            if (fj > fb) { fb = fj; best = j; }
+        }
+        return best == (int)y ? log(1.0 - param) : log(param / (double)(K - 1));
+    } else {                                      // softmax, likelihood_class.py:354-358
+        double mx = f(0);
+        for (int j = 1; j < K; ++j) mx = fmax(mx, f(j));
+        double se = 0.0;
+        for (int j = 0; j < K; ++j) se += exp(f(j) - mx);
+        return f((int)y) - (log(se) + mx);
     }
 }
 
@@ -723,12 +758,12 @@ __global__ void __launch_bounds__(512) lik_sum_kernel(LikArgs a, int64_t n, doub
     const double* F = a.src[blockIdx.x];
     double total = 0.0;
     for (int l = 0; l < a.nl; ++l) {
-        const double* f0 = F + (int64_t)a.row0[l] * n;
-        const double* f1 = F + (int64_t)a.row1[l] * n;
         const double* y = a.y[l];
-        const int kind = a.kind[l];
+        const int kind = a.kind[l], K = a.n_in[l];
+        const double param = a.param[l];
         double acc = 0.0;
-        for (int64_t i = threadIdx.x; i < n; i += 512) acc += lik_point(kind, y[i], f0[i], f1[i]);
+        for (int64_t i = threadIdx.x; i < n; i += 512)
+            acc += lik_point(kind, K, param, y[i], [&](int j) { return F[(int64_t)a.row[l][j] * n + i]; });
         red[threadIdx.x] = acc;
         __syncthreads();
         for (int w = 256; w > 0; w >>= 1) {
@@ -741,21 +776,38 @@ __global__ void __launch_bounds__(512) lik_sum_kernel(LikArgs a, int64_t n, doub
     if (threadIdx.x == 0) out[blockIdx.x] = total;
 }
 
+// validate the descriptors and pack them for the kernel
+static int pack_liks(const dgpb_lik* liks, int n_liks, int64_t layer_width, LikArgs* a) {
+    DGPB_REQUIRE(n_liks >= 1 && n_liks <= kMaxLik, "bad number of likelihood nodes");
+    a->nl = n_liks;
+    for (int l = 0; l < n_liks; ++l) {
+        const int kind = liks[l].kind;
+        DGPB_REQUIRE(kind >= DGPB_LIK_POISSON && kind <= DGPB_LIK_CAT_ROBUSTMAX && liks[l].y, "bad likelihood node");
+        const int need = (kind == DGPB_LIK_POISSON || kind == DGPB_LIK_CAT_LOGIT || kind == DGPB_LIK_CAT_PROBIT) ? 1
+                         : (kind == DGPB_LIK_HETERO || kind == DGPB_LIK_NEGBIN) ? 2 : liks[l].n_in;
+        DGPB_REQUIRE(liks[l].n_in == need && need >= 1 && need <= DGPB_LIK_MAX_IN, "bad number of likelihood inputs");
+        DGPB_REQUIRE(kind < DGPB_LIK_CAT_SOFTMAX || need >= 2, "a multi-class likelihood needs at least two inputs");
+        for (int j = 0; j < need; ++j) {
+            DGPB_REQUIRE(liks[l].rows[j] >= 0 && (layer_width <= 0 || liks[l].rows[j] < layer_width),
+                         "likelihood input row out of range");
+            a->row[l][j] = liks[l].rows[j];
+        }
+        a->kind[l] = kind;
+        a->n_in[l] = need;
+        a->param[l] = liks[l].param;
+        a->y[l] = liks[l].y;
+    }
+    return DGPB_OK;
+}
+
 }  // namespace dgpb
 
 extern "C" int dgpb_lik_loglik(const dgpb_lik* liks, int n_liks, const double* layer, int64_t n, double* out_host,
                                void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
-    DGPB_REQUIRE(liks && layer && out_host && n >= 1 && n_liks >= 1 && n_liks <= kMaxLik, "bad argument");
+    DGPB_REQUIRE(liks && layer && out_host && n >= 1, "bad argument");
     LikArgs a;
-    a.nl = n_liks;
-    for (int l = 0; l < n_liks; ++l) {
-        DGPB_REQUIRE(liks[l].kind >= DGPB_LIK_POISSON && liks[l].kind <= DGPB_LIK_NEGBIN && liks[l].y, "bad likelihood node");
-        a.kind[l] = liks[l].kind;
-        a.row0[l] = liks[l].rows[0];
-        a.row1[l] = liks[l].kind == DGPB_LIK_POISSON ? liks[l].rows[0] : liks[l].rows[1];
-        a.y[l] = liks[l].y;
-    }
+    DGPB_TRY(pack_liks(liks, n_liks, 0, &a));
     a.src[0] = layer;
     double* outd;
     DGPB_CUDA_TRY(cudaMallocAsync((void**)&outd, sizeof(double), st));
@@ -780,17 +832,7 @@ extern "C" int dgpb_ess_block_lik(dgpb_ws* ws, const dgpb_node* targets, int n_t
     for (int k = 0; k < n_targets; ++k)
         DGPB_REQUIRE(target_rows_host[k] >= 0 && target_rows_host[k] < layer_width, "target row out of range");
     LikArgs a;
-    a.nl = n_liks;
-    for (int l = 0; l < n_liks; ++l) {
-        DGPB_REQUIRE(liks[l].kind >= DGPB_LIK_POISSON && liks[l].kind <= DGPB_LIK_NEGBIN && liks[l].y, "bad likelihood node");
-        const int need = liks[l].kind == DGPB_LIK_POISSON ? 1 : 2;
-        for (int j = 0; j < need; ++j)
-            DGPB_REQUIRE(liks[l].rows[j] >= 0 && liks[l].rows[j] < layer_width, "likelihood input row out of range");
-        a.kind[l] = liks[l].kind;
-        a.row0[l] = liks[l].rows[0];
-        a.row1[l] = need == 2 ? liks[l].rows[1] : liks[l].rows[0];
-        a.y[l] = liks[l].y;
-    }
+    DGPB_TRY(pack_liks(liks, n_liks, layer_width, &a));
     if (g_pre_done_guard) DGPB_CUDA_TRY(cudaStreamWaitEvent(st, g_pre_done_guard, 0));  // SLOT_PROP may still be read
     void *pnu, *pprop, *pout;
     const size_t layer_elems = (size_t)layer_width * n;

@@ -147,11 +147,21 @@ class dgp:
                                                   "likelihood nodes only")
                     if node.name not in L.LIK_KIND:
                         raise NotImplementedError("dgp_b200: likelihood '%s' is outside the SI hot path" % node.name)
+        top = self.all_layer[-1][0]
+        if getattr(top, 'name', None) == 'Categorical':   # dgp.py:112-121
+            from sklearn.preprocessing import LabelEncoder
+            top.class_encoder = LabelEncoder()
+            self.Y = top.class_encoder.fit_transform(self.Y.flatten()).reshape(-1, 1)
+            if top.num_classes is None:
+                top.num_classes = len(top.class_encoder.classes_)
+            if top.link is None:
+                top.link = "logit" if top.num_classes == 2 else "softmax"
         self.initialize()
         self.block = block
-        self.imp = imputer(self.all_layer, self.block)
-        (self.imp).sample(burnin=10)
-        self.compute_r2()
+        with self.change_init_scale():
+            self.imp = imputer(self.all_layer, self.block)
+            (self.imp).sample(burnin=10)
+            self.compute_r2()
         self.N = 0
         self.burnin = None
         self.timing = {'i_step': 0.0, 'm_step': 0.0}
@@ -164,6 +174,29 @@ class dgp:
         self.__dict__.update(state)
 
     # ---- wiring of inputs / outputs (generic branch of dgp.py:154-691 and :1097-1362) ---------------
+    def change_init_scale(self):
+        """Context of dgp.py:1575-1586: during the first burn-in the GP nodes that feed a Categorical likelihood and
+        estimate their scale run with scale 40 (the latent start values are +-2 sqrt(40))."""
+        import contextlib
+
+        @contextlib.contextmanager
+        def ctx():
+            old = []
+            cat = getattr(self.all_layer[-1][0], 'name', None) == 'Categorical'
+            if cat:
+                for kernel in self.all_layer[-2]:
+                    old.append(kernel.scale)
+                    if kernel.scale_est:
+                        kernel.scale = np.array([40.0])
+            try:
+                yield
+            finally:
+                if cat:
+                    for scale, kernel in zip(old, self.all_layer[-2]):
+                        kernel.scale = scale
+
+        return ctx()
+
     def _latent_init_likelihood(self, In, l):
         """Warm start of the GP layer that feeds a single likelihood node (dgp.py:163-203, 327-330, 526-532, branches
         without replicates); None when layer l is not such a layer."""
@@ -174,6 +207,15 @@ class dgp:
             return None
         width = len(self.all_layer[l])
         y = self.Y.flatten()
+        if lik.name == 'Categorical':   # dgp.py:279-296
+            if width != lik.n_inputs:
+                raise Exception('You need %d GP node(s) to feed the Categorical likelihood node.' % lik.n_inputs)
+            c = 2 * np.sqrt(40)
+            if lik.num_classes == 2:
+                return np.where(self.Y == 1, c, -c)
+            Out = -c * np.ones((self.n_data, lik.num_classes))
+            Out[np.arange(self.n_data), self.Y.ravel()] = c
+            return Out
         if lik.name == 'Poisson':
             return np.log(self.Y + .5 + 1e-12)
         if lik.name == 'NegBin':
@@ -305,6 +347,8 @@ class dgp:
             raise Exception('The input and output data have to be numpy 2d-arrays.')
         if self.check_rep and len(np.unique(X, axis=0)) != len(X):
             raise NotImplementedError("dgp_b200: repeated input rows (replicates) are outside the SI hot path")
+        if getattr(self.all_layer[-1][0], 'name', None) == 'Categorical':   # dgp.py:845-846
+            self.Y = self.all_layer[-1][0].class_encoder.transform(self.Y.flatten()).reshape(-1, 1)
         self.indices = None
         origin_X = (self.X).copy()
         self.X = X
@@ -329,6 +373,9 @@ class dgp:
     def _rewire_node(self, layer, k, last):
         """Per-node tail shared by the two carry-over updates: global inputs, Vecchia ordering, final outputs."""
         kernel = layer[k]
+        if kernel.type == 'likelihood':
+            kernel.output = (self.Y[:, [k]]).copy()
+            return
         if kernel.connect is not None:
             kernel.global_input = (self.X[:, kernel.connect]).copy()
         kernel.m = self.m
@@ -394,6 +441,8 @@ class dgp:
         self.ord_fun = ord_fun
         for layer in self.all_layer:
             for k, kernel in enumerate(layer):
+                if kernel.type != 'gp':
+                    continue
                 kernel.vecch, kernel.m, kernel.ord_fun = self.vecch, self.m, self.ord_fun
                 self._share_or_draw_ord(layer, k)
 
@@ -404,7 +453,8 @@ class dgp:
         self.vecch = False
         for layer in self.all_layer:
             for kernel in layer:
-                kernel.vecch = self.vecch
+                if kernel.type == 'gp':
+                    kernel.vecch = self.vecch
 
     # ---- stochastic EM ----------------------------------------------------------------------------------
     def train(self, N=500, ess_burn=10, disable=False):

@@ -219,6 +219,9 @@ class emulator:
                 if ms[k] is not None:
                     continue
                 if kernel.type == 'likelihood':   # emulation.py:752-757: moments of the observable from the latent ones
+                    if kernel.name == 'Categorical':   # :753-754 the latent moments are aggregated first, see predict
+                        ms, vs = list(L.cols(mean, kernel.input_dim).T), list(L.cols(var, kernel.input_dim).T)
+                        break
                     mk, vk = kernel.prediction(m=L.to_host(L.cols(mean, kernel.input_dim)),
                                                v=L.to_host(L.cols(var, kernel.input_dim)))
                     ms[k], vs[k] = L.to_dev(np.ascontiguousarray(mk)), L.to_dev(np.ascontiguousarray(vk))
@@ -322,15 +325,24 @@ class emulator:
                                        L.stream()))
             return L.to_host(mu), L.to_host(s2)
 
+        # Categorical likelihood: class probabilities come from the AGGREGATED latent moments (emulation.py:831-834,
+        # 841-844); without aggregation from each imputation's moments (:849-850)
+        cat = self.all_layer[-1][0] if self.all_layer[-1][0].name == 'Categorical' else None
         if full_layer:
             mu, sigma2 = [], []
             for l in range(self.n_layer):
                 a, b = agg([layers_all[s][l][0] for s in range(S)], [layers_all[s][l][1] for s in range(S)])
+                if cat is not None and l == self.n_layer - 1:
+                    a, b = cat.prediction(m=a, v=b)
                 mu.append(a)
                 sigma2.append(b)
             return mu, sigma2
         if aggregation:
-            return agg(means, variances)
+            mu, sigma2 = agg(means, variances)
+            return cat.prediction(mu, sigma2) if cat is not None else (mu, sigma2)
+        if cat is not None:
+            pairs = [cat.prediction(L.to_host(a), L.to_host(b)) for a, b in zip(means, variances)]
+            return [p[0] for p in pairs], [p[1] for p in pairs]
         return [L.to_host(t) for t in means], [L.to_host(t) for t in variances]
 
     def _sample_likelihood(self, xd, full_layer, sample_size, m):
@@ -342,6 +354,8 @@ class emulator:
         last = self.all_layer[-1]
 
         def observe(latent):
+            if last[0].name == 'Categorical':   # class probabilities, one column per class (emulation.py:794-795)
+                return last[0].sampling(latent[:, last[0].input_dim])
             out = np.empty((latent.shape[0], len(last)))
             for count, kernel in enumerate(last):
                 out[:, count] = kernel.sampling(latent[:, kernel.input_dim])

@@ -5,14 +5,15 @@ The log-likelihood that enters the ESS acceptance rule is evaluated on the devic
 I-step by `dgpb_ess_block_lik`, which keeps every proposal in HBM).  `Hetero.posterior` draws the mean process from
 its exact Gaussian conditional with the sliding-window factorisation (`dgpb_mvn_draw`,
 `dgpb_compute_stats_shifted`).  `prediction` / `sampling` / `pllik` are elementwise host formulas on the moments the
-prediction kernels return.  Out of scope: Categorical, ZIP, ZINB, replicate pooling (`rep`), Hetero under Vecchia.
+prediction kernels return.  `Categorical` (:294-468): two classes through a logit / probit link, K classes through
+softmax / robustmax.  Out of scope: ZIP, ZINB, replicate pooling (`rep`), Hetero under Vecchia.
 """
 from __future__ import annotations
 
 import ctypes
 
 import numpy as np
-from scipy.special import gammaln
+from scipy.special import expit, gammaln, log_ndtr, ndtr, owens_t
 
 from . import _lib as L
 
@@ -30,18 +31,26 @@ class _Likelihood:
         self.exact_post_idx = type(self).exact_post_idx
         self.rep = None
 
+    def _kind(self):
+        return L.LIK_KIND[self.name]
+
     def _descriptor(self, rows, y_dev):
         d = L.DgpbLik()
-        d.kind = L.LIK_KIND[self.name]
+        d.kind = self._kind()
+        rows = [int(r) for r in rows]
+        if len(rows) > 8:
+            raise NotImplementedError("dgp_b200: a likelihood node reads at most 8 latent columns")
+        d.n_in = len(rows)
         for j, r in enumerate(rows):
-            d.rows[j] = int(r)
+            d.rows[j] = r
         d.y = y_dev.data_ptr()
+        d.param = float(getattr(self, 'robustmax_eps', 0.0))
         return d
 
     def llik(self):
         """Sum of the log-likelihood of the observed outputs given the latent inputs, evaluated on the device."""
         F = L.to_dev(np.ascontiguousarray(self.input.T))
-        y = L.to_dev(np.ascontiguousarray(self.output[:, 0]))
+        y = L.to_dev(np.ascontiguousarray(self.output[:, 0], dtype=np.float64))
         d = (L.DgpbLik * 1)(self._descriptor(range(self.input.shape[1]), y))
         out = ctypes.c_double(0.0)
         L.check(L.load().dgpb_lik_loglik(d, 1, L.ptr(F), F.shape[1], ctypes.byref(out), L.stream()))
@@ -148,3 +157,87 @@ class NegBin(_Likelihood):
     def sampling(f_sample):
         p, k = 1 / (1 + np.exp(f_sample[:, 0] + f_sample[:, 1])), np.exp(-f_sample[:, 1])
         return np.random.negative_binomial(k, p).flatten()
+
+
+class Categorical(_Likelihood):
+    """Categorical likelihood (likelihood_class.py:294-468): `num_classes == 2` reads one GP node through a
+    'logit' or 'probit' link, K > 2 classes read K GP nodes through 'softmax' or 'robustmax'.  `dgp.__init__`
+    encodes the labels (`class_encoder`) and fills `num_classes` / `link` when they are None."""
+
+    def __init__(self, num_classes=None, input_dim=None, link=None, robustmax_eps=1e-3):
+        super().__init__(input_dim)
+        self.num_classes = num_classes
+        self.class_encoder = None
+        self.link = link
+        self.robustmax_eps = robustmax_eps
+
+    @property
+    def n_inputs(self):
+        return 1 if self.num_classes == 2 else self.num_classes
+
+    def _kind(self):
+        if self.num_classes == 2:
+            return L.CAT_KIND['logit' if self.link == 'logit' else 'probit']
+        return L.CAT_KIND['robustmax' if self.link == 'robustmax' else 'softmax']
+
+    def pllik(self, y, f):
+        if self.num_classes == 2:
+            if self.link == 'logit':
+                return y * f - np.logaddexp(0, f)
+            return y * log_ndtr(f) + (1 - y) * log_ndtr(-f)
+        labels = y.flatten().astype(int)
+        if self.link == 'robustmax':
+            hit = np.argmax(f, axis=2) == labels[:, None]
+            return np.where(hit, np.log(1.0 - self.robustmax_eps),
+                            np.log(self.robustmax_eps / (self.num_classes - 1)))[:, :, None]
+        top = np.max(f, axis=2, keepdims=True)
+        lse = np.log(np.sum(np.exp(f - top), axis=2)) + np.squeeze(top, axis=2)
+        return (f[np.arange(len(labels)), :, labels] - lse)[:, :, None]
+
+    def prediction(self, m, v):
+        """Class probabilities (mean) and their variances from Gaussian moments of the latent inputs
+        (likelihood_class.py:384-449): closed forms for two classes, 1000 Monte-Carlo draws from numpy's global
+        RNG -- in the reference's order and shapes -- for K classes."""
+        if self.num_classes == 2:
+            m, v = m.flatten(), v.flatten()
+            if self.link == 'logit':
+                denom = 1.0 + (np.pi / 8.0) * v
+                y_mean = expit(m / np.sqrt(denom))
+                y_var = np.clip((y_mean * (1.0 - y_mean)) ** 2 * (v / denom), 0.0, y_mean * (1.0 - y_mean))
+            else:
+                t = m / np.sqrt(1.0 + v)
+                y_mean = ndtr(t)
+                y_var = np.maximum(y_mean - 2.0 * owens_t(t, 1.0 / np.sqrt(1.0 + 2.0 * v)) - y_mean * y_mean, 0.0)
+            return y_mean.reshape(-1, 1), y_var.reshape(-1, 1)
+        K, S, chunk = self.num_classes, 1000, 200
+        std = np.sqrt(np.maximum(v, 0.0))
+        M = m.shape[0]
+        if self.link == 'robustmax':
+            wins = np.zeros((M, K))
+            for _ in range(S // chunk):
+                f = m[:, None, :] + std[:, None, :] * np.random.randn(M, chunk, K)
+                np.add.at(wins, (np.arange(M)[:, None], np.argmax(f, axis=2)), 1.0)
+            q = wins / S
+            a, b = 1.0 - self.robustmax_eps, self.robustmax_eps / (K - 1)
+            return b + (a - b) * q, (a - b) ** 2 * q * (1.0 - q)
+        sum_p, sum_p2 = np.zeros((M, K)), np.zeros((M, K))
+        for _ in range(S // chunk):
+            half = np.random.randn(M, (chunk + 1) // 2, K)             # antithetic pairs
+            f = m[:, None, :] + std[:, None, :] * np.concatenate([half, -half], axis=1)[:, :chunk, :]
+            f -= np.max(f, axis=2, keepdims=True)
+            p = np.exp(f)
+            p /= np.sum(p, axis=2, keepdims=True)
+            sum_p += p.sum(axis=1)
+            sum_p2 += (p * p).sum(axis=1)
+        y_mean = sum_p / S
+        return y_mean, sum_p2 / S - y_mean ** 2
+
+    def sampling(self, f_sample):
+        if self.num_classes == 2:
+            return expit(f_sample) if self.link == 'logit' else ndtr(f_sample)
+        if self.link == 'robustmax':
+            out = np.full_like(f_sample, self.robustmax_eps / (self.num_classes - 1), dtype=float)
+            out[np.arange(f_sample.shape[0]), np.argmax(f_sample, axis=1)] = 1.0 - self.robustmax_eps
+            return out
+        e = np.exp(f_sample - np.max(f_sample, axis=1, keepdims=True))
+        return e / np.sum(e, axis=1, keepdims=True)

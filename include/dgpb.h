@@ -42,6 +42,13 @@ extern "C" {
 #define DGPB_LIK_POISSON 0
 #define DGPB_LIK_HETERO 1
 #define DGPB_LIK_NEGBIN 2
+/* Categorical (likelihood_class.py:294-360): two classes through a logit / probit link on one latent column,
+ * K > 2 classes through softmax / robustmax on K columns */
+#define DGPB_LIK_CAT_LOGIT 3
+#define DGPB_LIK_CAT_PROBIT 4
+#define DGPB_LIK_CAT_SOFTMAX 5
+#define DGPB_LIK_CAT_ROBUSTMAX 6
+#define DGPB_LIK_MAX_IN 8 /* latent columns one likelihood node can read */
 
 #define DGPB_MAX_DIM 32  /* maximum node input dimension (local + connected global) */
 
@@ -77,11 +84,14 @@ typedef struct dgpb_node {
 } dgpb_node;
 
 /* One likelihood node: which rows of the feeding layer it reads (`input_dim`: one row for Poisson -- the log
- * rate; two for Hetero -- mean, log variance -- and NegBin -- log mean, log dispersion) and the observed outputs. */
+ * rate -- and the two-class Categorical; two for Hetero -- mean, log variance -- and NegBin -- log mean, log
+ * dispersion; K for the K-class Categorical) and the observed outputs (class labels 0..K-1 as doubles). */
 typedef struct dgpb_lik {
     int32_t kind;     /* DGPB_LIK_* */
-    int32_t rows[3];
+    int32_t n_in;     /* rows used */
+    int32_t rows[DGPB_LIK_MAX_IN];
     const double* y;  /* device, n */
+    double param;     /* robustmax_eps (DGPB_LIK_CAT_ROBUSTMAX) */
 } dgpb_lik;
 
 const char* dgpb_last_error(void);

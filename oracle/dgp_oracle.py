@@ -836,13 +836,26 @@ class Node:
 class LikNode:
     """Likelihood node of a final layer -- likelihood_class.py: Poisson :39-48, Hetero :110-116, NegBin :264-272."""
 
-    def __init__(self, name, input_dim, output):
+    def __init__(self, name, input_dim, output, link=None, eps=1e-3):
         self.name, self.input_dim, self.output = name, np.asarray(input_dim), output
+        self.link, self.eps = link, eps
         self.input = None
 
     def loglik(self):
-        from scipy.special import gammaln
+        from scipy.special import gammaln, log_ndtr
         y, f = self.output.flatten(), self.input
+        if self.name == "Categorical":   # likelihood_class.py:333-359
+            K = f.shape[1]
+            if self.link == "logit":
+                return np.sum(y * f[:, 0] - np.logaddexp(0, f[:, 0]))
+            if self.link == "probit":
+                return np.sum(y * log_ndtr(f[:, 0]) + (1 - y) * log_ndtr(-f[:, 0]))
+            if self.link == "robustmax":
+                hit = np.argmax(f, axis=1) == y.astype(int)
+                return np.sum(np.where(hit, np.log(1.0 - self.eps), np.log(self.eps / (K - 1))))
+            top = np.max(f, axis=1)
+            lse = np.log(np.sum(np.exp(f - top[:, None]), axis=1)) + top
+            return np.sum(f[np.arange(len(y)), y.astype(int)] - lse)
         if self.name == "Poisson":
             return np.sum(y * f[:, 0] - np.exp(f[:, 0]) - gammaln(y + 1))
         if self.name == "Hetero":

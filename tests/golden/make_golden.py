@@ -465,7 +465,10 @@ def gen_lik():
     layers (Hetero: node-wise updates with the exact conditional draw of the mean, its normals recorded), the
     log-likelihoods, and predictions on frozen imputations."""
     out = {}
-    cases = (("poi", dgpsi.Poisson, 1), ("nb", dgpsi.NegBin, 2), ("het", dgpsi.Hetero, 2))
+    cases = (("poi", dgpsi.Poisson, 1), ("nb", dgpsi.NegBin, 2), ("het", dgpsi.Hetero, 2),
+             ("catl", lambda: dgpsi.Categorical(link="logit"), 1), ("catp", lambda: dgpsi.Categorical(link="probit"), 1),
+             ("cats", lambda: dgpsi.Categorical(link="softmax"), 3),
+             ("catr", lambda: dgpsi.Categorical(link="robustmax"), 3))
     import os
     only = os.environ.get("GOLDEN_LIK_ONLY")
     for ci, (tag, Lik, width) in enumerate(cases):
@@ -482,6 +485,10 @@ def gen_lik():
             Y = (g + np.exp(-1.5 + X[:, 0]) * rng.standard_normal(n)).reshape(-1, 1)
         elif tag == "poi":
             Y = rng.poisson(np.exp(1.0 + g)).astype(float).reshape(-1, 1)
+        elif tag in ("catl", "catp"):
+            Y = (g + 0.3 * rng.standard_normal(n) > 0.9).astype(int).reshape(-1, 1)
+        elif tag in ("cats", "catr"):
+            Y = np.digitize(g + 0.3 * rng.standard_normal(n), [0.6, 1.2]).reshape(-1, 1)
         else:
             Y = rng.negative_binomial(3.0, 3.0 / (3.0 + np.exp(1.0 + g))).astype(float).reshape(-1, 1)
         l1 = [kernel(length=np.array([1.0]), name="sexp") for _ in range(d)]
@@ -531,8 +538,10 @@ def gen_lik():
         model.train(N=4, disable=True)
         emu = dgpsi.emulator(model.estimate(), N=2)
         xt = rng.uniform(0, 1, size=(15, d))
+        np.random.seed(SEED + 77)          # Categorical.prediction draws from numpy's RNG (K > 2 classes)
         mu, var = emu.predict(xt)
         out[p + "xt"], out[p + "mu"], out[p + "var"] = xt, mu, var
+        np.random.seed(SEED + 77)
         mus, vars_ = emu.predict(xt, full_layer=True)
         out[p + "mu_full_last"], out[p + "var_full_last"] = mus[-1], vars_[-1]
         out[p + "mu_full_gp"], out[p + "var_full_gp"] = mus[-2], vars_[-2]
@@ -545,7 +554,10 @@ def gen_lik():
         order = np.lexsort(xt.T[::-1])
         xs = xt[order]
         assert np.array_equal(xs, np.unique(xt, axis=0))
-        yt = (np.round(np.abs(mu)) if tag != "het" else mu + 0.1)[order]
+        if tag.startswith("cat"):
+            yt = (np.arange(len(xt)) % (2 if width == 1 else 3)).reshape(-1, 1)
+        else:
+            yt = (np.round(np.abs(mu)) if tag != "het" else mu + 0.1)[order]
         avg, per = emu.nllik(xs, yt)
         out[p + "xt_sorted"], out[p + "yt"], out[p + "nllik_avg"], out[p + "nllik"] = xs, yt, np.array(avg), per
         # design criteria of an emulator with a likelihood layer (emulation.py:344-349, 373-392, 393-413)
