@@ -556,8 +556,10 @@ class dgp:
         if errors:
             raise errors[0]
 
-    def ptrain(self, *args, **kwargs):
-        raise NotImplementedError("dgp_b200: process-pool training is replaced by the GPU path; use train()")
+    def ptrain(self, N=500, ess_burn=10, disable=False, core_num=None):
+        """dgp.py:1414-1467 optimises the GP nodes of a layer in a process pool; here the nodes of ALL layers already
+        share one batched factorisation per optimiser round (`_m_step`), so this is `train`."""
+        return self.train(N, ess_burn, disable)
 
     def compute_r2(self):
         for l in range(1, self.n_layer):
