@@ -291,7 +291,7 @@ def run_gpu(args):
         from dgp_b200.parallel import predict_sharded
         emu = D.emulator(model.estimate(), N=args.predict_imputations)
         xt_all = np.random.default_rng(SEED + 99).uniform(0, 1, size=(args.predict_points * world, 8))
-        predict_sharded(emu, xt_all[: 64 * world], dist)  # warm-up
+        predict_sharded(emu, xt_all, dist)  # warm-up at full size (see the Vecchia leg below)
         barrier()
         p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         tp0 = time.perf_counter()
@@ -305,7 +305,8 @@ def run_gpu(args):
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         predict = {"metric": "predict points/sec (mean_var)", "value": len(xt_all) / (float(tt[0]) * 1e-3),
                    "e2e_value": len(xt_all) / (float(tt[1]) * 1e-3), "unit": "points/s", "points": len(xt_all),
-                   "imputations": args.predict_imputations, "sharding": "test points / rank, all_gather of (mu, var)",
+                   "imputations": args.predict_imputations, "warmup": "one full-size call",
+                   "sharding": "test points / rank, all_gather of (mu, var)",
                    "finite": bool(np.all(np.isfinite(mu)) and np.all(np.isfinite(var)))}
 
     # ---- secondary metric 2: Vecchia DGP prediction, BASELINE config 4 shape (n=100k, d=10, m=25, 10+1 sexp
@@ -331,7 +332,9 @@ def run_gpu(args):
         t_train = (time.perf_counter() - tv0)
         emu4 = D.emulator(m4.estimate(burnin=0), N=args.vecchia_imputations)
         xt4 = np.random.default_rng(seed4 + 99).uniform(0, 1, size=(args.vecchia_points, d4))
-        predict_sharded(emu4, xt4[: 256 * world], dist, m=25)  # warm-up
+        # warm-up at full size: the first call at a new size re-sizes the library's scratch slots and torch's pool
+        # (cudaMalloc / cudaFree, synchronising; 0.03-0.8 s here depending on what ran before), which is not throughput
+        predict_sharded(emu4, xt4, dist, m=25)
         barrier()
         p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         tp0 = time.perf_counter()
@@ -353,7 +356,7 @@ def run_gpu(args):
         t_pred = float(tt[0]) * 1e-3
         predict_v = {"metric": "Vecchia DGP predict points/sec (mean_var, m=25)", "value": M4 / t_pred,
                      "e2e_value": M4 / (float(tt[1]) * 1e-3), "unit": "points/s", "points": M4, "n_train": n4,
-                     "imputations": S4, "train_iters": args.vecchia_train_iters,
+                     "imputations": S4, "train_iters": args.vecchia_train_iters, "warmup": "one full-size call",
                      "train_s_per_iter_incl_construct": t_train / max(1, args.vecchia_train_iters),
                      "node_imputation_points_per_s": M4 * S4 * 11 / t_pred,
                      "algorithmic_tflops": flops / t_pred / 1e12,
