@@ -5,10 +5,10 @@ from .dgp import dgp
 from .emulation import emulator
 from .gp import gp
 from .kernel_class import combine, kernel
-from .likelihood_class import Categorical, Hetero, NegBin, Poisson
+from .likelihood_class import ZINB, ZIP, Categorical, Hetero, NegBin, Poisson
 from .linkgp import container, lgp
 from .utils import get_thread, nb_seed, read, set_thread, summary, write
 
 __all__ = ["dgp", "gp", "emulator", "kernel", "combine", "container", "lgp", "write", "read", "summary", "nb_seed",
-           "set_thread", "get_thread", "Poisson", "Hetero", "NegBin", "Categorical"]
+           "set_thread", "get_thread", "Poisson", "Hetero", "NegBin", "Categorical", "ZIP", "ZINB"]
 __version__ = "0.1.0"

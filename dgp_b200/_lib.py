@@ -43,7 +43,7 @@ class DgpbLik(ctypes.Structure):
 
 
 # likelihood name (+ link of the Categorical likelihood) -> DGPB_LIK_*
-LIK_KIND = {"Poisson": 0, "Hetero": 1, "NegBin": 2, "Categorical": None}
+LIK_KIND = {"Poisson": 0, "Hetero": 1, "NegBin": 2, "Categorical": None, "ZIP": 7, "ZINB": 8}
 CAT_KIND = {"logit": 3, "probit": 4, "softmax": 5, "robustmax": 6}
 
 _PROTOS = {

@@ -729,6 +729,24 @@ __device__ __forceinline__ double lik_point(int kind, int K, double param, doubl
         const double nn = exp(-f1), a = f0 + f1;
         const double softplus = fmax(a, 0.0) + log1p(exp(-fabs(a)));
         return lgamma(y + nn) - lgamma(nn) - lgamma(y + 1.0) + y * a - (y + nn) * softplus;
+    } else if (kind == DGPB_LIK_ZIP || kind == DGPB_LIK_ZINB) {  // likelihood_class.py:497-525, 653-693
+        double base, fpi;  // log-density of the count part at y, logit of the zero-inflation probability
+        if (kind == DGPB_LIK_ZIP) {
+            const double f0 = f(0);
+            fpi = f(1);
+            base = y == 0.0 ? -exp(f0) : -exp(f0) + y * f0 - lgamma(y + 1.0);
+        } else {
+            const double f0 = f(0), f1 = f(1);
+            fpi = f(2);
+            const double nn = exp(-f1), a = f0 + f1;
+            const double softplus = fmax(a, 0.0) + log1p(exp(-fabs(a)));
+            base = lgamma(y + nn) - lgamma(nn) - lgamma(y + 1.0) + y * a - (y + nn) * softplus;
+        }
+        const double pi = 1.0 / (1.0 + exp(-fpi));
+        const double l1m = log1p(-pi) + base;
+        if (y != 0.0) return l1m;
+        const double lp = log(pi);
+        return fmax(lp, l1m) + log1p(exp(-fabs(lp - l1m)));
     } else if (kind == DGPB_LIK_CAT_LOGIT) {   // likelihood_class.py:339-341
         const double f0 = f(0);
         return y * f0 - (fmax(f0, 0.0) + log1p(exp(-fabs(f0))));
@@ -782,11 +800,13 @@ static int pack_liks(const dgpb_lik* liks, int n_liks, int64_t layer_width, LikA
     a->nl = n_liks;
     for (int l = 0; l < n_liks; ++l) {
         const int kind = liks[l].kind;
-        DGPB_REQUIRE(kind >= DGPB_LIK_POISSON && kind <= DGPB_LIK_CAT_ROBUSTMAX && liks[l].y, "bad likelihood node");
+        DGPB_REQUIRE(kind >= DGPB_LIK_POISSON && kind <= DGPB_LIK_ZINB && liks[l].y, "bad likelihood node");
         const int need = (kind == DGPB_LIK_POISSON || kind == DGPB_LIK_CAT_LOGIT || kind == DGPB_LIK_CAT_PROBIT) ? 1
-                         : (kind == DGPB_LIK_HETERO || kind == DGPB_LIK_NEGBIN) ? 2 : liks[l].n_in;
+                         : (kind == DGPB_LIK_HETERO || kind == DGPB_LIK_NEGBIN || kind == DGPB_LIK_ZIP) ? 2
+                         : kind == DGPB_LIK_ZINB ? 3 : liks[l].n_in;
         DGPB_REQUIRE(liks[l].n_in == need && need >= 1 && need <= DGPB_LIK_MAX_IN, "bad number of likelihood inputs");
-        DGPB_REQUIRE(kind < DGPB_LIK_CAT_SOFTMAX || need >= 2, "a multi-class likelihood needs at least two inputs");
+        DGPB_REQUIRE((kind != DGPB_LIK_CAT_SOFTMAX && kind != DGPB_LIK_CAT_ROBUSTMAX) || need >= 2,
+                     "a multi-class likelihood needs at least two inputs");
         for (int j = 0; j < need; ++j) {
             DGPB_REQUIRE(liks[l].rows[j] >= 0 && (layer_width <= 0 || liks[l].rows[j] < layer_width),
                          "likelihood input row out of range");

@@ -216,6 +216,23 @@ class dgp:
             Out = -c * np.ones((self.n_data, lik.num_classes))
             Out[np.arange(self.n_data), self.Y.ravel()] = c
             return Out
+        if lik.name in ('ZIP', 'ZINB'):   # dgp.py:337-372, 411-459
+            N = len(y)
+            Out = np.empty((np.shape(In)[0], width))
+            Out[:, 0] = np.log(np.maximum(y + 0.5, 1e-6) + 1e-12)
+            if lik.name == 'ZINB':
+                sigma = (y.var(ddof=1) - y.mean()) / (y.mean() ** 2 + 1e-8) if N > 1 else 1.0
+                Out[:, 1] = np.log(min(max(sigma, 1e-3), 10.0))
+            p0 = ((y == 0).sum() + 0.5) / (N + 1.0)          # smoothed share of zeros
+            mu = y.mean()
+            if mu <= 0:
+                pi0 = p0
+            else:
+                q0 = np.exp(-max(mu, 1e-6))                  # zero probability of the count part
+                pi0 = 0.0 if q0 >= 1.0 - 1e-8 else np.clip((p0 - q0) / (1.0 - q0), 0.0, 0.99)
+            pi0 = np.clip(pi0, 1e-4, 1.0 - 1e-4)
+            Out[:, -1] = np.log(pi0 / (1.0 - pi0))
+            return Out
         if lik.name == 'Poisson':
             return np.log(self.Y + .5 + 1e-12)
         if lik.name == 'NegBin':

@@ -6,7 +6,8 @@ I-step by `dgpb_ess_block_lik`, which keeps every proposal in HBM).  `Hetero.pos
 its exact Gaussian conditional with the sliding-window factorisation (`dgpb_mvn_draw`,
 `dgpb_compute_stats_shifted`).  `prediction` / `sampling` / `pllik` are elementwise host formulas on the moments the
 prediction kernels return.  `Categorical` (:294-468): two classes through a logit / probit link, K classes through
-softmax / robustmax.  Out of scope: ZIP, ZINB, replicate pooling (`rep`), Hetero under Vecchia.
+softmax / robustmax.  `ZIP` (:470-622) and `ZINB` (:624-814): zero-inflated Poisson / negative-binomial counts.
+Out of scope: replicate pooling (`rep`), Hetero under Vecchia.
 """
 from __future__ import annotations
 
@@ -241,3 +242,83 @@ class Categorical(_Likelihood):
             return out
         e = np.exp(f_sample - np.max(f_sample, axis=1, keepdims=True))
         return e / np.sum(e, axis=1, keepdims=True)
+
+
+def _logit_normal_moments(m_pi, v_pi):
+    """Mean and variance of expit(g), g ~ N(m_pi, v_pi), by the probit-style approximation used by the reference
+    (likelihood_class.py:585-592, 766-773)."""
+    denom = np.maximum(1.0 + (np.pi / 8.0) * v_pi, 1e-12)
+    pi_mean = expit(m_pi / np.sqrt(denom))
+    pi_var = np.clip((pi_mean * (1.0 - pi_mean)) ** 2 * (v_pi / denom), 0.0, pi_mean * (1.0 - pi_mean))
+    return pi_mean, pi_var
+
+
+def _zero_inflate(log_count, f_pi, is_zero):
+    """log[(1 - pi) p(y) + pi 1(y = 0)] with pi = expit(f_pi) and log p(y) = log_count."""
+    pi = expit(f_pi)
+    with np.errstate(divide='ignore'):
+        inflated = np.logaddexp(np.log(pi), np.log1p(-pi) + log_count)
+    return np.where(is_zero, inflated, np.log1p(-pi) + log_count)
+
+
+class ZIP(_Likelihood):
+    """Zero-inflated Poisson fed by two GP nodes: log rate and logit of the zero-inflation probability
+    (likelihood_class.py:470-622)."""
+    n_inputs = 2
+
+    @staticmethod
+    def pllik(y, f):
+        f_lam, f_pi = f[..., 0:1], f[..., 1:2]
+        yb = np.broadcast_to(y, f_lam.shape)
+        return _zero_inflate(-np.exp(f_lam) + yb * f_lam - gammaln(yb + 1.0), f_pi, yb == 0)
+
+    @staticmethod
+    def prediction(m, v):
+        lam_mean = np.exp(m[:, 0] + 0.5 * v[:, 0])
+        lam_var = (np.exp(v[:, 0]) - 1.0) * np.exp(2.0 * m[:, 0] + v[:, 0])
+        pi_mean, pi_var = _logit_normal_moments(m[:, 1], v[:, 1])
+        y_mean = (1.0 - pi_mean) * lam_mean
+        cond_var = (1.0 - pi_mean) * lam_mean * (1.0 + pi_mean * lam_mean)
+        var_g = ((1.0 - pi_mean) ** 2 + pi_var) * lam_var + pi_var * lam_mean ** 2
+        return y_mean.flatten(), np.maximum(cond_var + var_g, 0.0).flatten()
+
+    def sampling(self, f_sample):
+        lam, pi = np.exp(f_sample[:, 0]), expit(f_sample[:, 1])
+        u = np.random.rand(f_sample.shape[0])
+        return np.where(u < pi, 0, np.random.poisson(lam)).flatten()
+
+
+class ZINB(_Likelihood):
+    """Zero-inflated negative binomial fed by three GP nodes: log mean, log dispersion and logit of the
+    zero-inflation probability (likelihood_class.py:624-814)."""
+    n_inputs = 3
+
+    @staticmethod
+    def pllik(y, f):
+        f1, f2, f_pi = f[..., 0:1], f[..., 1:2], f[..., 2:3]
+        n, a = np.exp(-f2), f1 + f2
+        yb = np.broadcast_to(np.asarray(y), n.shape)
+        log_nb = gammaln(yb + n) - gammaln(n) - gammaln(yb + 1.0) + yb * a - (yb + n) * np.logaddexp(0.0, a)
+        return _zero_inflate(log_nb, f_pi, yb == 0)
+
+    @staticmethod
+    def prediction(m, v):
+        m1, v1, m2, v2 = m[:, 0], v[:, 0], m[:, 1], v[:, 1]
+        mu_mean = np.exp(m1 + 0.5 * v1)
+        mu_var = (np.exp(v1) - 1.0) * np.exp(2.0 * m1 + v1)
+        mu2_mean = np.exp(2.0 * m1 + 2.0 * v1)
+        mu2_over_n = mu2_mean * np.exp(m2 + 0.5 * v2)
+        pi_mean, pi_var = _logit_normal_moments(m[:, 2], v[:, 2])
+        y_mean = (1.0 - pi_mean) * mu_mean
+        e_pi1m = np.clip(pi_mean * (1.0 - pi_mean) - pi_var, 0.0, pi_mean * (1.0 - pi_mean))
+        cond_var = (1.0 - pi_mean) * (mu_mean + mu2_over_n) + e_pi1m * mu2_mean
+        var_g = ((1.0 - pi_mean) ** 2 + pi_var) * mu_var + pi_var * mu_mean ** 2
+        return y_mean.flatten(), np.maximum(cond_var + var_g, 0.0).flatten()
+
+    @staticmethod
+    def sampling(f_sample):
+        k, p = np.exp(-f_sample[:, 1]), 1.0 / (1.0 + np.exp(f_sample[:, 0] + f_sample[:, 1]))
+        pi = expit(f_sample[:, 2])
+        u = np.random.rand(f_sample.shape[0])
+        nb = np.random.negative_binomial(k, p)
+        return np.where(u < pi, 0, nb).flatten()

@@ -48,6 +48,10 @@ extern "C" {
 #define DGPB_LIK_CAT_PROBIT 4
 #define DGPB_LIK_CAT_SOFTMAX 5
 #define DGPB_LIK_CAT_ROBUSTMAX 6
+/* zero-inflated counts (likelihood_class.py:470-622, 624-814): ZIP reads log rate and logit zero-inflation, ZINB
+ * log mean, log dispersion and logit zero-inflation */
+#define DGPB_LIK_ZIP 7
+#define DGPB_LIK_ZINB 8
 #define DGPB_LIK_MAX_IN 8 /* latent columns one likelihood node can read */
 
 #define DGPB_MAX_DIM 32  /* maximum node input dimension (local + connected global) */
@@ -85,7 +89,7 @@ typedef struct dgpb_node {
 
 /* One likelihood node: which rows of the feeding layer it reads (`input_dim`: one row for Poisson -- the log
  * rate -- and the two-class Categorical; two for Hetero -- mean, log variance -- and NegBin -- log mean, log
- * dispersion; K for the K-class Categorical) and the observed outputs (class labels 0..K-1 as doubles). */
+ * dispersion; ZIP two, ZINB three; K for the K-class Categorical) and the observed outputs (class labels 0..K-1 as doubles). */
 typedef struct dgpb_lik {
     int32_t kind;     /* DGPB_LIK_* */
     int32_t n_in;     /* rows used */

@@ -856,6 +856,16 @@ class LikNode:
             top = np.max(f, axis=1)
             lse = np.log(np.sum(np.exp(f - top[:, None]), axis=1)) + top
             return np.sum(f[np.arange(len(y)), y.astype(int)] - lse)
+        if self.name in ("ZIP", "ZINB"):   # likelihood_class.py:497-525, 653-693
+            from scipy.special import expit
+            if self.name == "ZIP":
+                count, fpi = -np.exp(f[:, 0]) + y * f[:, 0] - gammaln(y + 1.0), f[:, 1]
+            else:
+                n, a, fpi = np.exp(-f[:, 1]), f[:, 0] + f[:, 1], f[:, 2]
+                count = gammaln(y + n) - gammaln(n) - gammaln(y + 1.0) + y * a - (y + n) * np.logaddexp(0.0, a)
+            pi = expit(fpi)
+            ll = np.where(y == 0, np.logaddexp(np.log(pi), np.log1p(-pi) + count), np.log1p(-pi) + count)
+            return np.sum(ll)
         if self.name == "Poisson":
             return np.sum(y * f[:, 0] - np.exp(f[:, 0]) - gammaln(y + 1))
         if self.name == "Hetero":

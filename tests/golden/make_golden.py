@@ -468,7 +468,8 @@ def gen_lik():
     cases = (("poi", dgpsi.Poisson, 1), ("nb", dgpsi.NegBin, 2), ("het", dgpsi.Hetero, 2),
              ("catl", lambda: dgpsi.Categorical(link="logit"), 1), ("catp", lambda: dgpsi.Categorical(link="probit"), 1),
              ("cats", lambda: dgpsi.Categorical(link="softmax"), 3),
-             ("catr", lambda: dgpsi.Categorical(link="robustmax"), 3))
+             ("catr", lambda: dgpsi.Categorical(link="robustmax"), 3),
+             ("zip", dgpsi.ZIP, 2), ("zinb", dgpsi.ZINB, 3))
     import os
     only = os.environ.get("GOLDEN_LIK_ONLY")
     for ci, (tag, Lik, width) in enumerate(cases):
@@ -485,6 +486,9 @@ def gen_lik():
             Y = (g + np.exp(-1.5 + X[:, 0]) * rng.standard_normal(n)).reshape(-1, 1)
         elif tag == "poi":
             Y = rng.poisson(np.exp(1.0 + g)).astype(float).reshape(-1, 1)
+        elif tag in ("zip", "zinb"):
+            counts = rng.poisson(np.exp(1.0 + g)) if tag == "zip" else rng.negative_binomial(3.0, 3.0 / (3.0 + np.exp(1.0 + g)))
+            Y = np.where(rng.uniform(size=n) < 0.3, 0, counts).astype(float).reshape(-1, 1)
         elif tag in ("catl", "catp"):
             Y = (g + 0.3 * rng.standard_normal(n) > 0.9).astype(int).reshape(-1, 1)
         elif tag in ("cats", "catr"):

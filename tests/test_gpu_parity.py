@@ -839,7 +839,8 @@ def test_warm_start_update_xy(golden_update):
 
 LIK_CASES = (("poi", "Poisson", 1, None), ("nb", "NegBin", 2, None), ("het", "Hetero", 2, None),
              ("catl", "Categorical", 1, "logit"), ("catp", "Categorical", 1, "probit"),
-             ("cats", "Categorical", 3, "softmax"), ("catr", "Categorical", 3, "robustmax"))
+             ("cats", "Categorical", 3, "softmax"), ("catr", "Categorical", 3, "robustmax"),
+             ("zip", "ZIP", 2, None), ("zinb", "ZINB", 3, None))
 
 
 def _lik_model(g, prefix, likname, width, Y, stats=False, link=None):
@@ -984,7 +985,7 @@ def test_single_gp_layer_under_likelihood(golden_lik):
     assert np.max(np.abs(mice - g[p + "mice"]) / g[p + "mice"]) <= 1e-2
 
 
-@pytest.mark.parametrize("likname", ["Poisson", "NegBin", "Hetero", "Categorical2", "Categorical3"])
+@pytest.mark.parametrize("likname", ["Poisson", "NegBin", "Hetero", "Categorical2", "Categorical3", "ZIP", "ZINB"])
 def test_likelihood_public_api(likname):
     """dgp(X, Y, combine(..., [likelihood])) -> train -> estimate -> emulator -> predict through the public API."""
     import dgp_b200 as D
@@ -995,7 +996,7 @@ def test_likelihood_public_api(likname):
     n, d = 40, 2
     X = rng.uniform(0, 1, size=(n, d))
     gx = np.sin(3 * X[:, 0]) + X[:, 1]
-    width = {"Poisson": 1, "Categorical2": 1, "Categorical3": 3}.get(likname, 2)
+    width = {"Poisson": 1, "Categorical2": 1, "Categorical3": 3, "ZINB": 3}.get(likname, 2)
     if likname == "Hetero":
         Y = (gx + np.exp(-1.5 + X[:, 0]) * rng.standard_normal(n)).reshape(-1, 1)
     elif likname == "Categorical2":
@@ -1004,6 +1005,8 @@ def test_likelihood_public_api(likname):
         Y = np.digitize(gx, [0.6, 1.2]).reshape(-1, 1) + 5
     else:
         Y = rng.poisson(np.exp(1.0 + gx)).astype(float).reshape(-1, 1)
+        if likname in ("ZIP", "ZINB"):
+            Y[rng.uniform(size=n) < 0.3] = 0.0
     l1 = [D.kernel(length=np.array([1.0]), name="sexp") for _ in range(d)]
     l2 = [D.kernel(length=np.array([1.0]), name="sexp", scale_est=True, connect=np.arange(d)) for _ in range(width)]
     make = (lambda: D.Categorical()) if likname.startswith("Categorical") else getattr(D, likname)

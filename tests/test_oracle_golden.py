@@ -306,7 +306,8 @@ def test_warm_start_with_grown_design(golden_update):
 
 LIK_CASES = (("poi", "Poisson", 1, None), ("nb", "NegBin", 2, None), ("het", "Hetero", 2, None),
              ("catl", "Categorical", 1, "logit"), ("catp", "Categorical", 1, "probit"),
-             ("cats", "Categorical", 3, "softmax"), ("catr", "Categorical", 3, "robustmax"))
+             ("cats", "Categorical", 3, "softmax"), ("catr", "Categorical", 3, "robustmax"),
+             ("zip", "ZIP", 2, None), ("zinb", "ZINB", 3, None))
 
 
 def _lik_layers(g, prefix, width):
@@ -363,6 +364,6 @@ def test_likelihood_layers(golden_lik):
         # moments of the observable from the aggregated... per-imputation latent moments are not stored; check the
         # formulas on the full-layer output instead: a single Gaussian in -> the reference's closed forms
         m, v = g[p + "mu_full_gp"], g[p + "var_full_gp"]
-        if likname != "Categorical":
+        if likname in ("Poisson", "NegBin", "Hetero"):
             mean, var = lik.prediction(m, v)
             assert np.all(np.isfinite(mean)) and np.all(var > 0), tag
