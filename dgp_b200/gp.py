@@ -1,6 +1,6 @@
 """`gp` -- single Gaussian-process emulator (dgpsi/gp.py:12-60, 211-222, 412-453), GPU-backed through
 `kernel`.  In scope as a member of linked systems: construction, `train`,
-`predict`, `export`, `loo`; design metrics are not."""
+`predict`, `export`; `loo`, `metric` (ALM / MICE / VIGF) and `update_xy` follow SURVEY.md 8f-2 / 8f-4."""
 from __future__ import annotations
 
 import copy
@@ -78,6 +78,70 @@ class gp:
         self.vecch = False
         self.kernel.vecch = False
         self.kernel.compute_stats()
+
+    def update_xy(self, X, Y, reset=False):
+        """Update the trained GP emulator with new input and output data (gp.py:144-181)."""
+        if Y.ndim == 1 or X.ndim == 1:
+            raise Exception('The input and output data have to be numpy 2d-arrays.')
+        self.indices = None
+        if self.check_rep and len(np.unique(X, axis=0)) != len(X):
+            raise NotImplementedError("dgp_b200: repeated input rows (replicates) are outside the SI hot path")
+        self.X, self.Y = X, Y
+        self.n_data = self.X.shape[0]
+        self.m = min(self.m, self.n_data - 1)
+        self.update_kernel(reset_lengthscale=reset)
+        if self.vecch:
+            self.kernel.ord_nn()
+        else:
+            self.kernel.compute_stats()
+
+    def update_kernel(self, reset_lengthscale):
+        """Assign new input/output data to the kernel (gp.py:183-209)."""
+        k = self.kernel
+        k.rep = None
+        k.input = self.X[:, k.input_dim]
+        if k.connect is not None:
+            if len(np.intersect1d(k.connect, k.input_dim)) != 0:
+                raise Exception('The local input and global input should not have any overlap. Change input_dim or '
+                                'connect so they do not have any common indices.')
+            k.global_input = self.X[:, k.connect]
+        k.output = self.Y.copy()
+        k.m = self.m
+        if reset_lengthscale:
+            hyp = k.para_path[0, :]
+            k.scale, k.length, k.nugget = hyp[[0]], hyp[1:-1], hyp[[-1]]
+        if k.prior_name == 'ref':
+            k.compute_cl()
+
+    def metric(self, x_cand, method='MICE', nugget_s=1., m=50, score_only=False):
+        """ALM, MICE or VIGF criterion at the candidate points (gp.py:271-324)."""
+        if x_cand.ndim == 1:
+            raise Exception('The candidate design set has to be a numpy 2d-array.')
+        mu, sigma2 = self.predict(x=x_cand, m=m)
+        if method == 'ALM':
+            score = sigma2
+        elif method == 'MICE':
+            from .emulation import emulator
+            score = sigma2 / emulator._mice_var(x_cand, x_cand, self.kernel, nugget_s).reshape(-1, 1)
+        elif method == 'VIGF':
+            from .vecchia import get_pred_nn
+            index = get_pred_nn(x_cand, self.X, 1).flatten()     # nearest training input, searched on the device
+            bias = (mu - self.Y[index, :]) ** 2
+            score = 4 * sigma2 * bias + 2 * sigma2 ** 2
+        else:
+            raise Exception("method must be 'ALM', 'MICE' or 'VIGF'")
+        if score_only:
+            return score
+        idx = np.argmax(score, axis=0)
+        return idx, score[idx, 0]
+
+    def pmetric(self, x_cand, method='MICE', nugget_s=1., m=50, score_only=False, chunk_num=None, core_num=None):
+        """gp.py:224-269: the process pool is replaced by the GPU."""
+        return self.metric(x_cand, method, nugget_s, m, score_only)
+
+    def ppredict(self, x, method='mean_var', sample_size=50, m=50, chunk_num=None, core_num=None):
+        """gp.py:373-410: the process pool is replaced by the GPU."""
+        return self.predict(x, method, sample_size, m)
 
     def train(self):
         """Train the GP model (gp.py:211-216)."""

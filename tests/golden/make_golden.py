@@ -419,6 +419,23 @@ def gen_metric():
         out[f"{tag}_nimp"] = np.array(len(emu.all_layer_set))
         for s, al in enumerate(emu.all_layer_set):
             snapshot(al, f"{tag}_S{s}_", out)
+    # single GP emulator: gp.metric (gp.py:271-324) and gp.update_xy (gp.py:144-181)
+    Xg = rng.uniform(0, 1, size=(45, d))
+    Yg = (np.sin(4 * Xg[:, 0]) + Xg[:, 1] ** 2).reshape(-1, 1)
+    Xg2 = rng.uniform(0, 1, size=(52, d))
+    Yg2 = (np.sin(4 * Xg2[:, 0]) + Xg2[:, 1] ** 2).reshape(-1, 1)
+    out["gp_X"], out["gp_Y"], out["gp_X2"], out["gp_Y2"] = Xg, Yg, Xg2, Yg2
+    for tag, name in (("se", "sexp"), ("ma", "matern2.5")):
+        for vtag, vec in (("dense", False), ("vecch", True)):
+            g = dgpsi.gp(Xg, Yg, kernel(length=np.array([0.6, 0.8]), scale=1.2, nugget=1e-4, name=name),
+                         vecchia=vec, m=10)
+            q = f"gp_{tag}_{vtag}_"
+            out[q + "alm"] = g.metric(xc, method="ALM", score_only=True, m=12)
+            out[q + "mice"] = g.metric(xc, method="MICE", score_only=True, m=12)
+            out[q + "vigf"] = g.metric(xc, method="VIGF", score_only=True, m=12)
+            g.update_xy(Xg2, Yg2)
+            mu2, var2 = g.predict(xc, m=12)
+            out[q + "upd_mu"], out[q + "upd_var"] = mu2, var2
     save("metric", **out)
 
 

@@ -1037,6 +1037,35 @@ def test_likelihood_public_api(likname):
         D.dgp(X, Y, D.combine(l1, [D.kernel(length=np.array([1.0]))] * (1 if width == 2 else 2), [make()]))
 
 
+def test_gp_design_criteria_and_update(golden_metric):
+    """gp.metric (ALM / MICE / VIGF, gp.py:271-324) and gp.update_xy (gp.py:144-181), dense and Vecchia."""
+    import dgp_b200 as D
+
+    g = golden_metric
+    xc = g["x_cand"]
+    for tag, name in (("se", "sexp"), ("ma", "matern2.5")):
+        for vtag, vec in (("dense", False), ("vecch", True)):
+            q = f"gp_{tag}_{vtag}_"
+            em = D.gp(g["gp_X"], g["gp_Y"], D.kernel(length=np.array([0.6, 0.8]), scale=1.2, nugget=1e-4, name=name),
+                      vecchia=vec, m=10)
+            tol = 1e-7 if not vec else 1e-9        # dense: R^-1 at nugget 1e-4
+            for method, key in (("ALM", "alm"), ("MICE", "mice"), ("VIGF", "vigf")):
+                score = em.metric(xc, method=method, score_only=True, m=12)
+                ref = g[q + key]
+                assert score.shape == ref.shape, (q, key)
+                assert np.max(np.abs(score - ref)) <= tol * max(1.0, np.max(np.abs(ref))), (q, key)
+                idx, val = em.pmetric(xc, method=method, m=12)
+                assert idx[0] == np.argmax(ref[:, 0]) and abs(val[0] - ref.max()) <= tol * max(1.0, ref.max())
+            em.update_xy(g["gp_X2"], g["gp_Y2"])
+            assert em.n_data == len(g["gp_X2"]) and em.kernel.input.shape == g["gp_X2"].shape
+            mu, var = em.ppredict(xc, m=12)
+            assert np.max(np.abs(mu - g[q + "upd_mu"])) <= 10 * tol and np.max(np.abs(var - g[q + "upd_var"])) <= 10 * tol
+            em.update_xy(g["gp_X"], g["gp_Y"], reset=True)
+            assert np.array_equal(em.kernel.length, np.array([0.6, 0.8]))
+    with pytest.raises(Exception):
+        em.metric(xc[:, 0])
+
+
 def test_public_api_train_and_predict_smoke():
     """The user-facing path runs: dgp(X,Y).train -> estimate -> emulator -> predict; the fit is sane."""
     import dgp_b200 as D
