@@ -148,6 +148,12 @@ class lgp:
         for l, layer in enumerate(structure):
             ms, vs = [], []
             for kernel in layer:
+                if kernel.type == 'likelihood':   # linkgp.py:569-571: a DGP + likelihood emulator inside the system
+                    mk, vk = kernel.prediction(m=L.to_host(L.cols(mean, kernel.input_dim)),
+                                               v=L.to_host(L.cols(var, kernel.input_dim)))
+                    ms.append(L.to_dev(np.ascontiguousarray(np.asarray(mk).reshape(-1))))
+                    vs.append(L.to_dev(np.ascontiguousarray(np.asarray(vk).reshape(-1))))
+                    continue
                 kernel.pred_m = pred_m
                 if l == 0:
                     if x is None:

@@ -607,6 +607,32 @@ def gen_lik():
         out[p + "nimp"] = np.array(len(emu.all_layer_set))
         for s_, al in enumerate(emu.all_layer_set):
             snapshot(al[:-1], f"{p}S{s_}_", out)
+    # a linked system whose second emulator is a DGP + Poisson likelihood (linkgp.py:569-571)
+    if not only:
+        rng = np.random.default_rng(SEED + 31)
+        np.random.seed(SEED + 31)
+        dgpsi.nb_seed(SEED + 31)
+        n = 30
+        X1 = rng.uniform(0, 1, size=(n, 2))
+        Y1 = (np.sin(3 * X1[:, 0]) + X1[:, 1]).reshape(-1, 1)
+        g1 = dgpsi.gp(X1, Y1, kernel(length=np.array([1.0]), name="matern2.5", scale_est=True))
+        g1.train()
+        X2 = rng.uniform(-0.2, 2.0, size=(n, 1))
+        Y2 = rng.poisson(np.exp(0.5 + X2)).astype(float)
+        d2 = dgpsi.dgp(X2, Y2, dgpsi.combine([kernel(length=np.array([1.0]), name="sexp")],
+                                             [kernel(length=np.array([1.0]), name="sexp")],
+                                             [dgpsi.Poisson()]))   # fixed unit scales: an estimated scale of 1e5
+        d2.train(N=6, disable=True)                                # makes the variances pure cancellation noise
+        system = dgpsi.lgp(dgpsi.combine([dgpsi.container(g1.export(), np.array([0, 1]))],
+                                         [dgpsi.container(d2.estimate(), np.array([0]))]), N=2)
+        xt = rng.uniform(0, 1, size=(17, 2))
+        mu, var = system.predict(xt)
+        p = "lgp_"
+        out[p + "xt"], out[p + "mu"], out[p + "var"], out[p + "Y2"] = xt, mu[0], var[0], Y2
+        out[p + "nimp"] = np.array(len(system.all_layer_set))
+        for s_, one in enumerate(system.all_layer_set):
+            snapshot([[one[0][0].structure]], f"{p}S{s_}_E0_", out)
+            snapshot(one[1][0].structure[:-1], f"{p}S{s_}_E1_", out)
     save("likelihood", **out)
 
 

@@ -666,6 +666,34 @@ def test_linked_system_with_frozen_imputations(golden_e2e):
     assert np.max(np.abs(var[0] - g["lgp_var"])) <= 5e-6 * max(1.0, np.max(g["lgp_var"]))
 
 
+def test_linked_system_with_likelihood_emulator(golden_lik):
+    """lgp whose second emulator is a DGP + Poisson likelihood (linkgp.py:569-571) on the reference's imputed states."""
+    import dgp_b200 as D
+
+    g = golden_lik
+    sets = []
+    for s in range(int(g["lgp_nimp"])):
+        first = _snapshot_layers(g, f"lgp_S{s}_E0_", lambda l, k: "matern2.5")
+        second = _snapshot_layers(g, f"lgp_S{s}_E1_", lambda l, k: "sexp")
+        for layer in first + second:
+            for node in layer:
+                node.compute_stats()
+        lik = D.Poisson(input_dim=np.arange(1))
+        lik.output, lik.input = g["lgp_Y2"].copy(), second[-1][0].output.copy()
+        c1, c2 = D.container.__new__(D.container), D.container.__new__(D.container)
+        c1.type, c1.structure, c1.vecch, c1.local_input_idx = 'gp', first[0][0], False, np.array([0, 1])
+        c2.type, c2.structure, c2.vecch, c2.local_input_idx = 'dgp', second + [[lik]], False, np.array([0])
+        sets.append([[c1], [c2]])
+    system = D.lgp.__new__(D.lgp)
+    system.L, system.all_layer, system.all_layer_set, system.num_model = 2, sets[0], sets, [1]
+    mu, var = system.predict(g["lgp_xt"])
+    assert mu[0].shape == g["lgp_mu"].shape
+    # the CPU restatement of the same chain differs from the reference by 3.4e-5 here (three emulators with
+    # cond(K) ~ 2e7-3e7 feeding an exponential)
+    assert np.max(np.abs(mu[0] - g["lgp_mu"]) / np.abs(g["lgp_mu"])) <= 2e-4
+    assert np.max(np.abs(var[0] - g["lgp_var"]) / np.abs(g["lgp_var"])) <= 1e-3
+
+
 def test_batched_m_step_equals_one_node_at_a_time(monkeypatch):
     """The M-step serves every round of L-BFGS-B requests of all dense nodes with one batched sliding-window
     factorisation; each node must follow exactly the parameter path it follows alone."""
