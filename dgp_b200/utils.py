@@ -54,6 +54,10 @@ def summary(obj, tablefmt='fancy_grid'):
             node = getattr(node, 'structure', node)
             if isinstance(node, list):
                 continue
+            if getattr(node, 'type', 'gp') == 'likelihood':   # utils.py:119-123 prints NA for these columns
+                rows.append([f"Likelihood{l + 1}.{k + 1}", node.name, 'NA', 'NA', 'NA',
+                             None if node.input_dim is None else list(np.atleast_1d(node.input_dim)), 'NA'])
+                continue
             rows.append([f"GP{l + 1}.{k + 1}", node.name, np.array2string(np.atleast_1d(node.length), precision=3),
                          float(np.atleast_1d(node.scale)[0]), float(np.atleast_1d(node.nugget)[0]),
                          None if node.input_dim is None else list(np.atleast_1d(node.input_dim)),

@@ -79,3 +79,44 @@ def test_input_validation_matches_reference():
         D.dgp(np.zeros(5), np.zeros((5, 1)))
     with pytest.raises(ValueError):
         D.kernel(length=np.array([1.0]), name="rbf")
+
+
+def test_likelihood_host_formulas_match_oracle_and_summary():
+    """Host-side pieces of the likelihood layers that need no GPU: closed-form observable moments against the oracle
+    restatement, the Gauss-Hermite expectation against direct quadrature, `summary` over a hierarchy with a
+    likelihood node, and the structure checks of `dgp`."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import dgp_b200 as D
+    import dgp_oracle as O
+    from scipy.integrate import quad
+    from scipy.special import gammaln
+
+    rng = np.random.default_rng(0)
+    m, v = rng.normal(size=(6, 2)), rng.uniform(0.01, 0.5, size=(6, 2))
+    for name, cls, cols in (("Poisson", D.Poisson, 1), ("Hetero", D.Hetero, 2), ("NegBin", D.NegBin, 2)):
+        got = cls.prediction(m[:, :cols], v[:, :cols])
+        ref = O.LikNode(name, np.arange(cols), None).prediction(m[:, :cols], v[:, :cols])
+        assert np.allclose(got[0], np.ravel(ref[0]), rtol=1e-13) and np.allclose(got[1], np.ravel(ref[1]), rtol=1e-13)
+    mu, var, y = np.array([[0.3], [1.0]]), np.array([[0.2], [0.05]]), np.array([[1.0], [3.0]])
+    q = D.emulator._expected_likelihood(D.Poisson.pllik, mu, var, y)
+    for i in range(2):
+        f = lambda t: (np.exp(y[i, 0] * t - np.exp(t) - gammaln(y[i, 0] + 1))
+                       * np.exp(-(t - mu[i, 0]) ** 2 / (2 * var[i, 0])) / np.sqrt(2 * np.pi * var[i, 0]))
+        assert abs(q[i, 0] - quad(f, -10, 10)[0]) <= 1e-7
+    # ZIP / ZINB reduce to Poisson / NegBin moments when the zero-inflation probability vanishes
+    big = np.full((6, 1), -40.0)
+    zm, zv = np.hstack((m[:, :1], big)), np.hstack((v[:, :1], np.zeros((6, 1))))
+    assert np.allclose(D.ZIP.prediction(zm, zv)[0], D.Poisson.prediction(m[:, :1], v[:, :1])[0], rtol=1e-12)
+    zm3, zv3 = np.hstack((m, big)), np.hstack((v, np.zeros((6, 1))))
+    assert np.allclose(D.ZINB.prediction(zm3, zv3)[0], D.NegBin.prediction(m, v)[0], rtol=1e-12)
+    cat = D.Categorical(num_classes=2, link="probit")
+    p_mean, p_var = cat.prediction(np.zeros((3, 1)), np.ones((3, 1)))
+    assert np.allclose(p_mean, 0.5) and np.all(p_var > 0) and np.all(p_var < 0.25)
+    layers = D.combine([D.kernel(length=np.array([1.0]))], [D.kernel(length=np.array([1.0]), scale_est=True)],
+                       [D.Poisson(input_dim=np.array([0]))])
+    text = D.summary(layers, tablefmt="plain")
+    assert "Poisson" in text and "Likelihood3.1" in text and "NA" in text
+    X, Y = rng.uniform(size=(8, 1)), rng.poisson(3.0, size=(8, 1)).astype(float)
+    with pytest.raises(NotImplementedError):   # likelihood nodes only as a final layer
+        D.dgp(X, Y, D.combine([D.kernel(length=np.array([1.0]))], [D.Poisson()], [D.kernel(length=np.array([1.0]))]))
