@@ -3,8 +3,9 @@
 Python keeps the object graph, the SEM loop, the L-BFGS-B driver and the parameter traces; the I-step
 (ESS sweeps) and every likelihood / gradient evaluation of the M-step run in libdgpb.so.  Scope follows
 SURVEY.md section 2 row 5: `__init__`, the generic branch of `initialize` (dgp.py:565-691), `train`,
-`estimate`, Vecchia switches and the restart logic.  Likelihood layers, replicated inputs, `update_xy*`,
-`ptrain` and plotting are not part of the SI hot path and raise NotImplementedError.
+`estimate`, Vecchia switches and the restart logic; widened by likelihood final layers with
+their warm starts (dgp.py:163-203, 279-296, 327-372, 411-459, 526-532) and `update_xy*`.  Replicated inputs and
+plotting are not part of the SI hot path (NotImplementedError); `ptrain` is `train`.
 """
 from __future__ import annotations
 
@@ -147,6 +148,8 @@ class dgp:
                                                   "likelihood nodes only")
                     if node.name not in L.LIK_KIND:
                         raise NotImplementedError("dgp_b200: likelihood '%s' is outside the SI hot path" % node.name)
+                    if vecchia and node.exact_post_idx is not None:
+                        raise NotImplementedError("dgp_b200: the exact Hetero posterior under Vecchia is not built")
         top = self.all_layer[-1][0]
         if getattr(top, 'name', None) == 'Categorical':   # dgp.py:112-121
             from sklearn.preprocessing import LabelEncoder
@@ -453,6 +456,8 @@ class dgp:
         """Convert the DGP structure to the Vecchia mode (dgp.py:693-746)."""
         if self.vecch:
             raise Exception('The DGP structure is already in Vecchia mode.')
+        if any(getattr(k, 'exact_post_idx', None) is not None for k in self.all_layer[-1]):
+            raise NotImplementedError("dgp_b200: the exact Hetero posterior under Vecchia is not built")
         self.vecch = True
         self.m = min(m, self.n_data - 1)
         self.ord_fun = ord_fun

@@ -8,7 +8,9 @@ and the moments all-gathered over NCCL (`dgp_b200.parallel`).
 `loo` (SURVEY.md 8f-2) re-uses the Vecchia prediction kernels with every point conditioned on the others;
 `metric` (ALM / MICE / VIGF, same row) is host arithmetic on the per-imputation moments plus one dense inverse per
 output node (MICE) and a nearest-training-point search (VIGF).
-Out of scope: likelihood layers, nllik, process pools.
+A final layer of likelihood nodes (SURVEY.md 8f-3) maps the latent moments through each likelihood's closed form;
+`nllik` integrates the likelihood against them by Gauss-Hermite quadrature.  Process pools (`ppredict`, `pmetric`,
+`ploo`) are the same calls: the GPU replaces the pool.
 """
 from __future__ import annotations
 

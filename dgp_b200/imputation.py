@@ -2,6 +2,8 @@
 I-step resident on the GPU: latent layers are uploaded once per `sample()` call, every block update runs in
 libdgpb.so (`dgpb_ess_block`), and the imputed layers are written back to the nodes' numpy attributes at the
 end, so the object graph looks exactly as the reference leaves it (`kernel.output`, `kernel.input`).
+A final layer of likelihood nodes is handled by `dgpb_ess_block_lik` (elementwise log-likelihoods in the ESS
+threshold) and, for Hetero, the exact conditional draw of the mean (`Hetero.posterior_dev`).
 
 Randomness: standard normals for dense prior draws come from the module RNG seeded by `nb_seed` (the
 reference draws them from numba's RNG inside `fmvn`, functions.py:118), Vecchia prior draws and all uniforms

@@ -975,6 +975,32 @@ def test_likelihood_layers_vs_reference(golden_lik):
             assert np.all(np.stack(samples, 0) >= 0) and np.all(np.stack(samples, 0) <= 1)
 
 
+def test_vecchia_dgp_with_likelihood_layer():
+    """Vecchia GP layers under a Poisson node: sparse prior draws feed dgpb_ess_block_lik, block likelihoods drive
+    the middle pair, predictions run on the Vecchia kernels."""
+    import dgp_b200 as D
+
+    rng = np.random.default_rng(21)
+    np.random.seed(21)
+    D.nb_seed(21)
+    n, d = 300, 2
+    X = rng.uniform(0, 1, size=(n, d))
+    rate = np.exp(1.0 + np.sin(3 * X[:, 0]) + X[:, 1])
+    Y = rng.poisson(rate).astype(float).reshape(-1, 1)
+    l1 = [D.kernel(length=np.array([0.5]), name="sexp") for _ in range(d)]
+    l2 = [D.kernel(length=np.array([0.5]), name="sexp", scale_est=True, connect=np.arange(d))]
+    model = D.dgp(X, Y, D.combine(l1, l2, [D.Poisson()]), vecchia=True, m=12)
+    model.train(N=3, disable=True)
+    emu = D.emulator(model.estimate(), N=2)
+    xt = rng.uniform(0, 1, size=(40, d))
+    mu, var = emu.predict(xt, m=20)
+    truth = np.exp(1.0 + np.sin(3 * xt[:, 0]) + xt[:, 1])
+    assert mu.shape == (40, 1) and np.all(np.isfinite(mu)) and np.all(var > 0)
+    assert np.corrcoef(mu[:, 0], truth)[0, 1] > 0.8
+    with pytest.raises(NotImplementedError):
+        D.dgp(X, Y, D.combine(l1, [D.kernel(length=np.array([0.5])) for _ in range(2)], [D.Hetero()]), vecchia=True)
+
+
 def test_single_gp_layer_under_likelihood(golden_lik):
     """One GP layer feeding a Poisson node: predictions and the 2-layer branches of the design criteria
     (emulation.py:362-372, 402-403) on the reference's imputed states."""
