@@ -633,6 +633,27 @@ def gen_lik():
         for s_, one in enumerate(system.all_layer_set):
             snapshot([[one[0][0].structure]], f"{p}S{s_}_E0_", out)
             snapshot(one[1][0].structure[:-1], f"{p}S{s_}_E1_", out)
+    # Vecchia GP layers under a Poisson node through the public API: the Vecchia path draws every random number from
+    # numpy's global generator (vecchia.py:137, imputation.py:79-119), so a reimplementation that consumes the same
+    # stream reproduces the whole run -- construction, 3 SEM iterations, emulator, prediction
+    if not only:
+        seed = 21
+        rng = np.random.default_rng(seed)
+        np.random.seed(seed)
+        dgpsi.nb_seed(seed)
+        n, d = 300, 2
+        X = rng.uniform(0, 1, size=(n, d))
+        Y = rng.poisson(np.exp(1.0 + np.sin(3 * X[:, 0]) + X[:, 1])).astype(float).reshape(-1, 1)
+        l1 = [kernel(length=np.array([0.5]), name="sexp") for _ in range(d)]
+        l2 = [kernel(length=np.array([0.5]), name="sexp", scale_est=True, connect=np.arange(d))]
+        model = dgpsi.dgp(X, Y, dgpsi.combine(l1, l2, [dgpsi.Poisson()]), vecchia=True, m=12)
+        model.train(N=3, disable=True)
+        emu = dgpsi.emulator(model.estimate(), N=2)
+        xt = rng.uniform(0, 1, size=(40, d))
+        mu, var = emu.predict(xt, m=20)
+        out["vpoi_mu"], out["vpoi_var"] = mu, var
+        out["vpoi_theta"] = np.concatenate([np.concatenate((k.scale, k.length, k.nugget)) for layer in model.all_layer[:-1]
+                                            for k in layer])
     save("likelihood", **out)
 
 
