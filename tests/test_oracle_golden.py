@@ -367,3 +367,26 @@ def test_likelihood_layers(golden_lik):
         if likname in ("Poisson", "NegBin", "Hetero"):
             mean, var = lik.prediction(m, v)
             assert np.all(np.isfinite(mean)) and np.all(var > 0), tag
+
+
+def test_gp_design_criteria(golden_metric):
+    """gp.metric of the reference (gp.py:271-324) from the oracle's dense prediction, smoothed variance and a
+    brute-force nearest training input; gp.update_xy = the same emulator on the new data (gp.py:144-181)."""
+    g = golden_metric
+    xc, X, Y = g["x_cand"], g["gp_X"], g["gp_Y"]
+    length = np.array([0.6, 0.8])
+    for tag, name in (("se", "sexp"), ("ma", "matern2.5")):
+        Rinv, Rinv_y = O.compute_stats(X, Y, length, 1e-4, name)
+        mu, s2 = O.gp_predict(xc, X, Rinv, Rinv_y, 1.2, length, 1e-4, name)
+        q = f"gp_{tag}_dense_"
+        assert relerr(s2.reshape(-1, 1), g[q + "alm"], 1e-300) <= 1e-7
+        smooth = O.mice_var(xc, xc, np.arange(2), None, name, length, 1.2, 1e-4, 1.0)
+        assert relerr(s2.reshape(-1, 1) / smooth, g[q + "mice"], 1e-300) <= 1e-7
+        index = np.argmin(((xc[:, None, :] - X[None, :, :]) ** 2).sum(-1), axis=1)
+        bias = (mu.reshape(-1, 1) - Y[index]) ** 2
+        vigf = 4 * s2.reshape(-1, 1) * bias + 2 * s2.reshape(-1, 1) ** 2
+        assert np.max(np.abs(vigf - g[q + "vigf"])) <= 1e-7 * max(1.0, np.max(g[q + "vigf"]))
+        Rinv, Rinv_y = O.compute_stats(g["gp_X2"], g["gp_Y2"], length, 1e-4, name)
+        mu2, s22 = O.gp_predict(xc, g["gp_X2"], Rinv, Rinv_y, 1.2, length, 1e-4, name)
+        assert np.max(np.abs(mu2.reshape(-1, 1) - g[q + "upd_mu"])) <= 1e-6
+        assert np.max(np.abs(s22.reshape(-1, 1) - g[q + "upd_var"])) <= 1e-6
