@@ -2,9 +2,10 @@
 
 Run in the build container only (the reference is not present on the GPU box):
 
-    python tests/golden/make_golden.py
+    python tests/golden/make_golden.py [dense jd vecchia ess e2e loo metric update lik]
 
-Writes `tests/golden/*.npz`.  Every fixture stores the exact inputs fed to the reference function
+Writes `tests/golden/*.npz` (one file per group: dense_nodes, jd, vecchia_nodes, ess_replay, e2e, loo, metric,
+update, likelihood; every group is seeded, re-running reproduces the committed files bit for bit).  Every fixture stores the exact inputs fed to the reference function
 together with what it returned, so `tests/` can check (a) the oracle (`oracle/dgp_oracle.py`) on CPU
 and (b) the CUDA path on a B200 against the reference's own numbers.  The reference ships no tests of
 its own so these files ARE the pin.
