@@ -203,7 +203,7 @@ def run_reference(args):
 def workload_config(args, world):
     return {"workload": f"BASELINE config 3: 3-layer DGP, 8+8+2 sexp nodes with global connections, n={args.n}, d=8, "
                         f"2 outputs; one step = one SEM iteration (11 ESS sweeps + M-step)",
-            "n": args.n, "ess_burn": 10, "nodes": 18, "replicas": world,
+            "n": args.n, "ess_burn": 10, "nodes": 18, "chains": 1, "gpus_sharing_the_chain": world,
             "cache": "working set per batched factorisation >> 126 MB L2 (8 x n^2 doubles); no L2 flush needed",
             "predict_points": args.predict_points, "predict_imputations": args.predict_imputations}
 
@@ -249,9 +249,14 @@ def run_gpu(args):
 
     peak = measure_fp64_peak(torch) if rank == 0 else 0.0
 
-    rng = np.random.default_rng(SEED + rank)  # independent replica per rank
-    np.random.seed(SEED + rank)
-    D.nb_seed(SEED + rank)
+    # N > 1: ONE chain shared by the ranks (same data, same draws on every rank; ESS waves and M-step nodes are
+    # dealt over the GPUs, dgp_b200/parallel.py) -- strong scaling of a single `train` call
+    if dist is not None:
+        from dgp_b200 import parallel
+        parallel.enable(dist)
+    rng = np.random.default_rng(SEED)
+    np.random.seed(SEED)
+    D.nb_seed(SEED)
     X, Y = make_config3(args.n, rng)
     model = D.dgp(X, Y, layers_config3(lambda **kw: D.kernel(**kw)))
     for _ in range(args.warmup):
@@ -366,8 +371,8 @@ def run_gpu(args):
                      "finite": bool(np.all(np.isfinite(mu4)) and np.all(np.isfinite(var4)))}
 
     if rank == 0:
-        value = world * args.steps / (dev_ms_max * 1e-3)
-        e2e = world * args.steps / (wall_ms_max * 1e-3)
+        value = args.steps / (dev_ms_max * 1e-3)     # one chain, whatever the number of GPUs
+        e2e = args.steps / (wall_ms_max * 1e-3)
         upd_ms, upd_n, upd_flops = prof[0], prof[1], prof[2]
         achieved = (upd_flops / upd_n) / (upd_ms / upd_n * 1e-3) / 1e12 if upd_n > 0 else None
         roof = {"bound": "tensor", "kernel": "update_kernel, bulk launches (FP64 DMMA SYRK trailing update, K = 512 hyper-blocks / 128 tail)",
@@ -415,7 +420,7 @@ def run_gpu(args):
                              f"{blas_info()}"}
         line = {"metric": METRIC, "value": value, "unit": "iters/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": workload_config(args, world),
                 "e2e": {"value": e2e, "unit": "iters/s", "h2d_bytes_per_step": h2d // args.steps,
                         "d2h_bytes_per_step": d2h // args.steps},

@@ -76,7 +76,7 @@ int dgpb_ws_create(dgpb_ws** ws, int device) {
     DGPB_CUDA_TRY(cudaSetDevice(device));
     dgpb_ws* w = new dgpb_ws();
     w->device = device;
-    DGPB_CUDA_TRY(cudaMallocHost((void**)&w->pinned, 4096 * sizeof(double)));
+    DGPB_CUDA_TRY(cudaMallocHost((void**)&w->pinned, kPinnedDoubles * sizeof(double)));
     *ws = w;
     return DGPB_OK;
 }
@@ -102,6 +102,7 @@ int64_t dgpb_ws_bytes(const dgpb_ws* ws) {
 int dgpb_cache_clear(dgpb_ws* ws) {
     DGPB_REQUIRE(ws != nullptr, "ws is NULL");
     for (auto& kv : ws->cache) kv.second.valid = false;
+    ws->owner.clear();
     return DGPB_OK;
 }
 

@@ -4,12 +4,16 @@
 #include <stdint.h>
 #include <math.h>
 
+#include <algorithm>
 #include <atomic>
 #include <map>
 #include <cstdarg>
 #include <cstdio>
+#include <cstring>
 #include <string>
 #include <vector>
+
+#include <nvtx3/nvToolsExt.h>
 
 #include "../../include/dgpb.h"
 
@@ -97,7 +101,43 @@ enum Slot : int {
     SLOT_VY,          // Vecchia: outputs gathered in Vecchia order
     SLOT_VL,          // Vecchia: sparse inverse-Cholesky rows
     SLOT_VFLAG,       // Vecchia: ready flags of the sparse solve
+    SLOT_COMM,        // multi-GPU: gathered result blocks of an ESS wave (world x kCommBlock doubles)
+    SLOT_COMM_FLAG,   // multi-GPU: status word
     SLOT_COUNT
+};
+
+// NVTX range of one sub-system call (tracing); costs nothing without a profiler attached.
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
+#define DGPB_NVTX(name) dgpb::NvtxRange nvtx_range__(name)
+
+// ---------------------------------------------------------------------------------------------
+// Multi-GPU (comm.cu): one chain spread over the GPUs of a box.  Every rank holds the same latent layers and
+// takes the same decisions; what is partitioned is the WORK -- the candidate angles of an ESS wave -- and the
+// Cholesky factors that work leaves behind, which stay on the rank that computed them.
+// ---------------------------------------------------------------------------------------------
+constexpr int kMaxRanks = 8;
+constexpr int kCommBlock = 128;       // doubles per rank in the wave all-gather (4 per matrix, <= 32 matrices)
+// layout of the pinned staging buffer (doubles)
+constexpr int kPinnedDoubles = 8192;
+constexpr int kPinnedVecchia = 1024;  // Vecchia per-node results, cached-threshold quads
+constexpr int kPinnedInfo = 2048;     // int info flags of a batch
+constexpr int kPinnedFlag = 3072;     // status word of comm_max_flag
+constexpr int kPinnedWave = 4096;     // gathered wave results (kMaxRanks x kCommBlock)
+
+struct Comm {
+    void* nccl = nullptr;   // ncclComm_t
+    int rank = 0, world = 1;
+};
+// which rank holds chol(K) stored under a cache key (replicated on every rank: decisions must agree)
+constexpr int kOwnerNone = -1, kOwnerAll = -2;
+struct FactorOwner {
+    int rank = kOwnerNone;
+    int64_t n = 0;
+    bool has_logdet = false;
+    double logdet = 0.0;
 };
 
 // chol(K) of a GP node kept across ESS block updates of one I-step (hyper-parameters fixed)
@@ -113,9 +153,11 @@ struct CachedFactor {
 struct Workspace {
     int device = 0;
     std::map<int, CachedFactor> cache;
+    Comm comm;
+    std::map<int, FactorOwner> owner;   // world > 1 only
     void* buf[SLOT_COUNT] = {};
     size_t cap[SLOT_COUNT] = {};
-    double* pinned = nullptr;  // small pinned host staging buffer (4096 doubles)
+    double* pinned = nullptr;  // small pinned host staging buffer (kPinnedDoubles)
 
     int reserve(int slot, size_t bytes, void** out) {
         if (bytes > cap[slot]) {

@@ -418,7 +418,7 @@ __global__ void __launch_bounds__(256) reduce_kernel(Batch bt, int64_t ld, int n
         out[b * 4 + 0] = 2.0 * s1;
         out[b * 4 + 1] = s2;
         out[b * 4 + 2] = sa.est[b] ? s2 / (double)n : sa.scale[b];
-        out[b * 4 + 3] = 0.0;
+        out[b * 4 + 3] = (double)bt.info[b];   // 0 or failing column + 1: travels with the results (ESS wave gather)
     }
 }
 

@@ -8,6 +8,7 @@
 // nodes of a proposal are evaluated by ONE batched factorisation (blockIdx.z = node).  The host only
 // sees one scalar per proposal (the summed log-likelihood) to take the accept/shrink decision with the
 // caller's uniforms, which keeps the decision sequence identical to the reference under injected draws.
+#include "comm.cuh"
 #include "dense.cuh"
 #include "vecchia.cuh"
 
@@ -51,6 +52,38 @@ struct DenseBatchInfo {
     int B = 0;           // matrices in the (single) dense batch, 0 if none or if it needed several batches
     int map[MAXB];       // batch slot -> node index
 };
+
+// ---- which rank holds chol(K) of a cache key ---------------------------------------------------------------------
+// One GPU: the workspace cache itself (kOwnerAll).  Several GPUs: the replicated owner map -- every rank takes the
+// same decisions from it, only the owning rank touches the factor.
+static int factor_owner(Workspace* ws, int key, int64_t n, bool* has_logdet = nullptr, double* logdet = nullptr) {
+    if (key < 0) return kOwnerNone;
+    if (ws->comm.world <= 1) {
+        auto it = ws->cache.find(key);
+        if (it == ws->cache.end() || !it->second.valid || it->second.n != n) return kOwnerNone;
+        if (has_logdet) *has_logdet = it->second.has_logdet;
+        if (logdet) *logdet = it->second.logdet;
+        return kOwnerAll;
+    }
+    auto it = ws->owner.find(key);
+    if (it == ws->owner.end() || it->second.rank == kOwnerNone || it->second.n != n) return kOwnerNone;
+    if (has_logdet) *has_logdet = it->second.has_logdet;
+    if (logdet) *logdet = it->second.logdet;
+    return it->second.rank;
+}
+static inline bool is_mine(const Workspace* ws, int owner) { return owner == kOwnerAll || owner == ws->comm.rank; }
+static void set_owner(Workspace* ws, int key, int rank, int64_t n, const double* logdet) {
+    if (key < 0 || ws->comm.world <= 1) return;
+    FactorOwner& o = ws->owner[key];
+    o.rank = rank;
+    o.n = n;
+    o.has_logdet = logdet != nullptr;
+    o.logdet = logdet ? *logdet : 0.0;
+    if (!is_mine(ws, rank)) {   // a factor this rank kept from an earlier update is stale now
+        auto it = ws->cache.find(key);
+        if (it != ws->cache.end()) it->second.valid = false;
+    }
+}
 
 // keep chol(K) of batch slot b (just factored, diagonal blocks still in the side buffer) under `key`
 static int cache_store(Workspace* ws, int key, const Geom& g, const Batch& bt, int b, cudaStream_t st,
@@ -141,7 +174,7 @@ static int nodes_loglik(Workspace* ws, const dgpb_node* nodes, int U, int64_t n,
             info_out->B = dense_batches == 1 ? B : 0;
             for (int b = 0; b < B; ++b) info_out->map[b] = map[b];
         }
-        int* info_host = reinterpret_cast<int*>(ws->pinned + 2048);
+        int* info_host = reinterpret_cast<int*>(ws->pinned + kPinnedInfo);
         DGPB_CUDA_TRY(cudaMemcpyAsync(ws->pinned, outd, sizeof(double) * 4 * B, cudaMemcpyDeviceToHost, st));
         DGPB_CUDA_TRY(cudaMemcpyAsync(info_host, bt.info, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
         DGPB_CUDA_TRY(cudaStreamSynchronize(st));
@@ -155,13 +188,13 @@ static int nodes_loglik(Workspace* ws, const dgpb_node* nodes, int U, int64_t n,
         }
     }
     if (nv > 0) {
-        DGPB_CUDA_TRY(cudaMemcpyAsync(ws->pinned + 1024, out + kOutVecchia, sizeof(double) * 2 * nv,
+        DGPB_CUDA_TRY(cudaMemcpyAsync(ws->pinned + kPinnedVecchia, out + kOutVecchia, sizeof(double) * 2 * nv,
                                       cudaMemcpyDeviceToHost, st));
         DGPB_CUDA_TRY(cudaStreamSynchronize(st));
         int v = 0;
         for (int u = 0; u < U; ++u) {
             if (!nodes[u].vecch) continue;
-            double quad = ws->pinned[1024 + 2 * v], logdet = ws->pinned[1024 + 2 * v + 1];
+            double quad = ws->pinned[kPinnedVecchia + 2 * v], logdet = ws->pinned[kPinnedVecchia + 2 * v + 1];
             if (!(quad == quad) || !(logdet == logdet)) {
                 set_error("Vecchia block of upper node %d is not positive definite", u);
                 return DGPB_NOT_PD;
@@ -176,9 +209,15 @@ static int nodes_loglik(Workspace* ws, const dgpb_node* nodes, int U, int64_t n,
     return DGPB_OK;
 }
 
-// prior draws nu[k] = chol(scale K) z_k for the target nodes
+// prior draws nu[k] = chol(scale K) z_k for the target nodes.
+// Several GPUs: a dense target's draw is formed on the rank that holds its factor (factors that have to be
+// computed are dealt round-robin and stay where they were computed) and the row is broadcast, so every rank ends
+// up with the same nu bit for bit.
 static int prior_draws(Workspace* ws, const dgpb_node* targets, int M, int64_t n, const double* z, double* nu,
                        const int32_t* keys, cudaStream_t st) {
+    const int G = ws->comm.world;
+    constexpr int kMaxTargets = 256;
+    DGPB_REQUIRE(M >= 1 && M <= kMaxTargets, "too many target nodes");
     for (int k = 0; k < M; ++k) {
         const dgpb_node* nd = &targets[k];
         if (!nd->vecch) continue;
@@ -200,24 +239,43 @@ static int prior_draws(Workspace* ws, const dgpb_node* targets, int M, int64_t n
         scatter_ord_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>((double*)tmp, nd->ord, n, nu + (int64_t)k * n);
         DGPB_LAUNCHED();
     }
+    // ---- dense targets: who forms which row (decided identically on every rank)
+    int own[kMaxTargets], root[kMaxTargets];
+    bool fresh[kMaxTargets];
+    int nfresh = 0;
+    const Geom g = make_geom(n, false);
+    for (int k = 0; k < M; ++k) {
+        own[k] = kOwnerNone;
+        root[k] = -1;
+        fresh[k] = false;
+        if (targets[k].vecch) continue;
+        own[k] = factor_owner(ws, keys ? keys[k] : -1, n);
+        if (own[k] == kOwnerNone) {
+            fresh[k] = true;
+            own[k] = G > 1 ? nfresh % G : kOwnerAll;
+            ++nfresh;
+        }
+        root[k] = own[k] == kOwnerAll ? -1 : own[k];
+    }
+    // ---- rows from factors kept from an earlier block update of this I-step (same inputs, same theta)
+    for (int k = 0; k < M; ++k) {
+        if (targets[k].vecch || fresh[k] || !is_mine(ws, own[k])) continue;
+        const CachedFactor& cf = ws->cache[keys[k]];
+        DGPB_REQUIRE(cf.valid && cf.T && cf.n == n, "cached factor missing on its owner rank");
+        DGPB_TRY(launch_trmv(cf.T, g.ld, g.n, sqrt(targets[k].scale), z + (int64_t)k * n, nu + (int64_t)k * n, st));
+    }
+    // ---- factors that have to be computed, in batches
+    int local_bad = 0, bad_node = -1, bad_pivot = 0;
     int k0 = 0;
     while (k0 < M) {
         KernelDev kds[MAXB];
         int map[MAXB];
         int B = 0;
-        Geom g = make_geom(n, false);
         while (k0 < M && B < MAXB) {
-            if (!targets[k0].vecch) {
-                // reuse chol(K) kept from an earlier block update of this I-step (same inputs, same theta)
-                auto it = keys && keys[k0] >= 0 ? ws->cache.find(keys[k0]) : ws->cache.end();
-                if (it != ws->cache.end() && it->second.valid && it->second.n == n) {
-                    DGPB_TRY(launch_trmv(it->second.T, g.ld, g.n, sqrt(targets[k0].scale), z + (int64_t)k0 * n,
-                                         nu + (int64_t)k0 * n, st));
-                } else {
-                    DGPB_TRY(make_kernel_dev(&targets[k0], n, nullptr, &kds[B]));
-                    map[B] = k0;
-                    ++B;
-                }
+            if (!targets[k0].vecch && fresh[k0] && is_mine(ws, own[k0])) {
+                DGPB_TRY(make_kernel_dev(&targets[k0], n, nullptr, &kds[B]));
+                map[B] = k0;
+                ++B;
             }
             ++k0;
         }
@@ -234,16 +292,34 @@ static int prior_draws(Workspace* ws, const dgpb_node* targets, int M, int64_t n
             DGPB_TRY(launch_trmv(bt.T[b], g.ld, g.n, sqrt(targets[map[b]].scale), z + (int64_t)map[b] * n,
                                  nu + (int64_t)map[b] * n, st));
         }
-        int* info_host = reinterpret_cast<int*>(ws->pinned + 2048);
+        int* info_host = reinterpret_cast<int*>(ws->pinned + kPinnedInfo);
         DGPB_CUDA_TRY(cudaMemcpyAsync(info_host, bt.info, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
         DGPB_CUDA_TRY(cudaStreamSynchronize(st));
         for (int b = 0; b < B; ++b)
             if (info_host[b] != 0) {
                 if (keys && keys[map[b]] >= 0) ws->cache[keys[map[b]]].valid = false;
-                set_error("prior covariance of target node %d is not positive definite (pivot %d)", map[b], info_host[b]);
-                return DGPB_NOT_PD;
+                if (!local_bad) {
+                    bad_node = map[b];
+                    bad_pivot = info_host[b];
+                }
+                local_bad = 1;
             }
+        if (local_bad && G <= 1) break;
     }
+    if (nfresh > 0) {
+        int bad = local_bad;
+        if (G > 1) DGPB_TRY(comm_max_flag(ws, local_bad, &bad, st));   // every rank leaves the update the same way
+        if (bad) {
+            if (local_bad)
+                set_error("prior covariance of target node %d is not positive definite (pivot %d)", bad_node, bad_pivot);
+            else
+                set_error("prior covariance of a target node is not positive definite (found on another rank)");
+            return DGPB_NOT_PD;
+        }
+        for (int k = 0; k < M; ++k)
+            if (fresh[k] && keys && keys[k] >= 0) set_owner(ws, keys[k], own[k], n, nullptr);
+    }
+    if (G > 1) DGPB_TRY(comm_bcast_rows(ws, nu, n, root, M, st));
     return DGPB_OK;
 }
 
@@ -268,6 +344,10 @@ __global__ void __launch_bounds__(256, 1) trsv_quad_kernel(const double* const* 
     const double* __restrict__ T = Ts[blockIdx.x];
     const double* __restrict__ y = ys[blockIdx.x];
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    if (T == nullptr) {   // factor held by another rank (multi-GPU): that rank fills this entry
+        if (tid == 0) out[blockIdx.x] = 0.0;
+        return;
+    }
     const int nb = (n + 63) / 64;
     double* rs = xs + (size_t)nb * 64;   // right-hand side of the current block after the GEMV part
     double* sd = rs + 64;                // 64 x 65 diagonal block
@@ -330,113 +410,145 @@ __global__ void __launch_bounds__(256, 1) trsv_quad_kernel(const double* const* 
 
 // Sum of the upper nodes' log-likelihoods at the CURRENT state from cached factors (see trsv_quad_kernel).
 // Returns DGPB_OK with *used = 1 when every node had a cached factor with its log-determinant, else *used = 0.
+// Several GPUs: every rank solves with the factors it holds and the quadratic forms are all-gathered.
 static int cached_threshold(Workspace* ws, const dgpb_node* nodes, int U, int64_t n, const int32_t* keys, double* sum_host,
                             int* used, cudaStream_t st) {
     *used = 0;
     if (!keys || U > MAXB) return DGPB_OK;
+    const int G = ws->comm.world, me = ws->comm.rank;
     const Geom g = make_geom(n, false);
     const size_t smem = ((size_t)((n + 63) / 64) * 64 + 64 + 64 * 65) * sizeof(double);
     if (smem > 200 * 1024) return DGPB_OK;
     const double* hT[MAXB];
     const double* hy[MAXB];
     double logdets[MAXB];
+    int own[MAXB];
+    int mine = 0;
     for (int u = 0; u < U; ++u) {
         if (nodes[u].vecch || keys[u] < 0) return DGPB_OK;
-        auto it = ws->cache.find(keys[u]);
-        if (it == ws->cache.end() || !it->second.valid || !it->second.has_logdet || it->second.n != n) return DGPB_OK;
-        hT[u] = it->second.T;
+        bool has_logdet = false;
+        own[u] = factor_owner(ws, keys[u], n, &has_logdet, &logdets[u]);
+        if (own[u] == kOwnerNone || !has_logdet) return DGPB_OK;
+        hT[u] = nullptr;
         hy[u] = nodes[u].output;
-        logdets[u] = it->second.logdet;
+        if (is_mine(ws, own[u])) {
+            const CachedFactor& cf = ws->cache[keys[u]];
+            DGPB_REQUIRE(cf.valid && cf.T && cf.n == n, "cached factor missing on its owner rank");
+            hT[u] = cf.T;
+            ++mine;
+        }
     }
     void *ptab, *pout;
     DGPB_TRY(ws->reserve(SLOT_MISC, sizeof(double*) * 2 * MAXB, &ptab));
     DGPB_TRY(ws->reserve(SLOT_OUT, sizeof(double) * kOutDoubles, &pout));
-    const double** dT = (const double**)ptab;
-    const double** dy = dT + MAXB;
-    DGPB_CUDA_TRY(cudaMemcpyAsync(dT, hT, sizeof(double*) * U, cudaMemcpyHostToDevice, st));
-    DGPB_CUDA_TRY(cudaMemcpyAsync(dy, hy, sizeof(double*) * U, cudaMemcpyHostToDevice, st));
-    static bool cfg = false;
-    if (!cfg) {
-        DGPB_CUDA_TRY(cudaFuncSetAttribute(trsv_quad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        cfg = true;
+    double* out = (double*)pout + kOutVecchia;   // a region the dense batch results do not use (kCommBlock doubles)
+    if (mine > 0) {
+        const double** dT = (const double**)ptab;
+        const double** dy = dT + MAXB;
+        DGPB_CUDA_TRY(cudaMemcpyAsync(dT, hT, sizeof(double*) * U, cudaMemcpyHostToDevice, st));
+        DGPB_CUDA_TRY(cudaMemcpyAsync(dy, hy, sizeof(double*) * U, cudaMemcpyHostToDevice, st));
+        static bool cfg = false;
+        if (!cfg) {
+            DGPB_CUDA_TRY(cudaFuncSetAttribute(trsv_quad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            cfg = true;
+        }
+        trsv_quad_kernel<<<U, 256, smem, st>>>(dT, g.ld, g.n, dy, out);   // nodes held elsewhere: NULL factor, skipped
+        DGPB_LAUNCHED();
     }
-    double* out = (double*)pout + kOutVecchia;   // a region the dense batch results do not use
-    trsv_quad_kernel<<<U, 256, smem, st>>>(dT, g.ld, g.n, dy, out);
-    DGPB_LAUNCHED();
-    DGPB_CUDA_TRY(cudaMemcpyAsync(ws->pinned + 1024, out, sizeof(double) * U, cudaMemcpyDeviceToHost, st));
+    const double* res = ws->pinned + kPinnedWave;
+    if (G > 1) {
+        void* pc;
+        DGPB_TRY(ws->reserve(SLOT_COMM, sizeof(double) * kCommBlock * kMaxRanks, &pc));
+        DGPB_TRY(comm_allgather(ws, out, (double*)pc, kCommBlock, st));
+        DGPB_CUDA_TRY(cudaMemcpyAsync(ws->pinned + kPinnedWave, pc, sizeof(double) * kCommBlock * G, cudaMemcpyDeviceToHost, st));
+    } else {
+        DGPB_CUDA_TRY(cudaMemcpyAsync(ws->pinned + kPinnedWave, out, sizeof(double) * U, cudaMemcpyDeviceToHost, st));
+    }
     DGPB_CUDA_TRY(cudaStreamSynchronize(st));
     double s = 0.0;
     for (int u = 0; u < U; ++u) {   // same left-to-right order as imputation.py:70-78
         const double sc = nodes[u].scale;
-        s += -0.5 * (logdets[u] + (double)n * log(sc) + ws->pinned[1024 + u] / sc);
+        const int r = own[u] == kOwnerAll ? me : own[u];
+        s += -0.5 * (logdets[u] + (double)n * log(sc) + res[(G > 1 ? r * kCommBlock : 0) + u] / sc);
     }
     *sum_host = s;
     *used = 1;
     return DGPB_OK;
 }
 
-// Log-likelihood sums of `nitems` candidate states of the layer below (srcs[i] = latent layer image read by the
-// upper nodes, NULL = the nodes' own `src`), all U upper nodes dense and nitems * U <= MAXB: ONE batched
-// factorisation, matrix slot of (item i, node u) = i * U + u.  pd[i] = 0 if one of the item's matrices is not
-// positive definite (bad_node[i] = which).  The caller decides what an indefinite item means: the reference
-// only ever evaluates items up to the first accepted one.
-// Step 1: assemble the matrices of the items into T set `tslot` (kernel matrices + y rows) on stream `st`.
+// ---- ESS waves ---------------------------------------------------------------------------------------------------
+// A wave is a list of ITEMS: optionally the threshold (the upper nodes at the current state, item 0) followed by
+// candidate angles.  Item i is evaluated by rank i % W in its local slot i / W (W = ranks sharing the wave): the U
+// upper-node matrices of local slot l are matrices l U .. l U + U - 1 of that rank's batched factorisation.
+// Step 1: assemble the matrices of this rank's items (srcs[l] = latent layer image read by the upper nodes, NULL =
+// the nodes' own `src`) into T set `tslot` on stream `st`.
 static int dense_items_assemble(Workspace* ws, int tslot, const dgpb_node* nodes, int U, int64_t n,
-                                const double* const* srcs, int nitems, Batch* bt_out, Geom* g_out, cudaStream_t st) {
-    const int B = nitems * U;
-    DGPB_REQUIRE(B >= 1 && B <= MAXB, "wave does not fit one batch");
+                                const double* const* srcs, int nlocal, Batch* bt_out, Geom* g_out, cudaStream_t st) {
+    const int B = nlocal * U;
+    *g_out = make_geom(n, false);
+    if (B == 0) return DGPB_OK;
+    DGPB_REQUIRE(B <= MAXB, "wave does not fit one batch");
     KernelDev kds[MAXB];
     const double* ys[MAXB];
-    for (int i = 0; i < nitems; ++i)
+    for (int i = 0; i < nlocal; ++i)
         for (int u = 0; u < U; ++u) {
             const int b = i * U + u;
             DGPB_TRY(make_kernel_dev(&nodes[u], n, srcs[i], &kds[b]));
             ys[b] = nodes[u].output;
         }
-    *g_out = make_geom(n, false);
     double* outd;
     DGPB_TRY(setup_batch_slot(ws, tslot, *g_out, B, bt_out, &outd));
     DGPB_TRY(assemble_matrices(*g_out, kds, ys, *bt_out, B, st));
     return DGPB_OK;
 }
 
-// Step 2: factorise the assembled batch, reduce, launch the device-to-host copies of the results (no host sync).
-static int dense_items_factor(Workspace* ws, const dgpb_node* nodes, int U, int nitems, const Batch& bt, const Geom& g,
-                              cudaStream_t st) {
-    const int B = nitems * U;
-    ScaleArgs sa;
-    for (int b = 0; b < B; ++b) {
-        sa.scale[b] = nodes[b % U].scale;
-        sa.est[b] = 0;
-    }
+// Step 2: factorise this rank's matrices, reduce, exchange the result blocks (4 doubles per matrix: log|K|, y'K^-1y,
+// -, info) and launch the device-to-host copy of all of them (no host sync).
+static int dense_items_factor(Workspace* ws, const dgpb_node* nodes, int U, int nlocal, int W, const Batch& bt,
+                              const Geom& g, cudaStream_t st) {
+    const int B = nlocal * U;
     void* pO;
     DGPB_TRY(ws->reserve(SLOT_OUT, sizeof(double) * kOutDoubles, &pO));
     double* outd = (double*)pO;
-    DGPB_TRY(factor_reduce(g, bt, B, sa, outd, st));
-    int* info_host = reinterpret_cast<int*>(ws->pinned + 2048);
-    DGPB_CUDA_TRY(cudaMemcpyAsync(ws->pinned, outd, sizeof(double) * 4 * B, cudaMemcpyDeviceToHost, st));
-    DGPB_CUDA_TRY(cudaMemcpyAsync(info_host, bt.info, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
+    if (B > 0) {
+        ScaleArgs sa;
+        for (int b = 0; b < B; ++b) {
+            sa.scale[b] = nodes[b % U].scale;
+            sa.est[b] = 0;
+        }
+        DGPB_TRY(factor_reduce(g, bt, B, sa, outd, st));
+    }
+    if (W > 1) {
+        void* pc;
+        DGPB_TRY(ws->reserve(SLOT_COMM, sizeof(double) * kCommBlock * kMaxRanks, &pc));
+        DGPB_TRY(comm_allgather(ws, outd, (double*)pc, kCommBlock, st));
+        DGPB_CUDA_TRY(cudaMemcpyAsync(ws->pinned + kPinnedWave, pc, sizeof(double) * kCommBlock * W, cudaMemcpyDeviceToHost, st));
+    } else if (B > 0) {
+        DGPB_CUDA_TRY(cudaMemcpyAsync(ws->pinned + kPinnedWave, outd, sizeof(double) * 4 * B, cudaMemcpyDeviceToHost, st));
+    }
     return DGPB_OK;
 }
 
-// Step 3: wait for the results and form the per-item sums.
-static int dense_items_fetch(Workspace* ws, const dgpb_node* nodes, int U, int64_t n, int nitems, double* sums, int* pd,
-                             int* bad_node, double* logdets, cudaStream_t st) {
+// Step 3: wait for the results and form the per-item sums.  pd[i] = 0 if one of the item's matrices is not positive
+// definite (bad_node[i] = which).  The caller decides what an indefinite item means: the reference only ever
+// evaluates items up to the first accepted one.
+static int dense_items_fetch(Workspace* ws, const dgpb_node* nodes, int U, int64_t n, int nitems, int W, double* sums,
+                             int* pd, int* bad_node, double* logdets, cudaStream_t st) {
     DGPB_CUDA_TRY(cudaStreamSynchronize(st));
-    const int* info_host = reinterpret_cast<const int*>(ws->pinned + 2048);
+    const double* res = ws->pinned + kPinnedWave;
     for (int i = 0; i < nitems; ++i) {
+        const double* blk = res + (size_t)(i % W) * kCommBlock + (size_t)(i / W) * U * 4;
         double s = 0.0;
         pd[i] = 1;
         bad_node[i] = -1;
         for (int u = 0; u < U; ++u) {  // same left-to-right order as imputation.py:70-78
-            const int b = i * U + u;
-            if (info_host[b] != 0 && pd[i]) {
+            if (blk[4 * u + 3] != 0.0 && pd[i]) {
                 pd[i] = 0;
                 bad_node[i] = u;
             }
             const double sc = nodes[u].scale;
-            s += -0.5 * (ws->pinned[4 * b] + (double)n * log(sc) + ws->pinned[4 * b + 1] / sc);
-            if (logdets) logdets[b] = ws->pinned[4 * b];
+            s += -0.5 * (blk[4 * u] + (double)n * log(sc) + blk[4 * u + 1] / sc);
+            if (logdets) logdets[i * U + u] = blk[4 * u];
         }
         sums[i] = s;
     }
@@ -450,18 +562,19 @@ static thread_local cudaEvent_t g_pre_done_guard = nullptr;
 
 // The angles ESS will try are known in advance: a rejection is the only branch of the bracket rule
 // (imputation.py:111-119), so theta_{k+1} depends on theta_k and the next uniform, never on a likelihood value.
-// Proposals are therefore evaluated in WAVES of consecutive candidate angles batched into one factorisation
-// (wave size = g_ess_target_b / n_uppers) and the first accepted one wins; candidates after it are discarded.
+// Proposals are therefore evaluated in WAVES of consecutive candidate angles and the first accepted one wins;
+// candidates after it are discarded.  On one GPU a wave is one batched factorisation (g_ess_target_b / n_uppers
+// candidates); on W GPUs every rank factors its share of the wave (W times as many candidates in the time of
+// one batch), the per-matrix results are all-gathered (1 KB per rank) and every rank replays the same decisions.
 // Accept/shrink decisions, the angles reported and the number of uniforms consumed are exactly those of the
-// one-at-a-time loop; what changes is that a 2-node upper layer fills the GPU with 4 proposals at once instead
-// of running a critical-path-bound batch of 2.  When the threshold likelihood is not cached it rides along in
-// the first wave.
+// one-at-a-time loop.  When the threshold likelihood is not cached it rides along in the first wave.
 extern "C" int dgpb_ess_block_cached(dgpb_ws* ws, const dgpb_node* targets, int n_targets,
                                      const int32_t* target_rows_host, double* layer_out, int64_t layer_width,
                                      const dgpb_node* uppers, int n_uppers, int64_t n, const double* z,
                                      const double* u_host, int nu, int* n_prop_host, double* theta_host,
                                      const int32_t* target_keys_host, const int32_t* upper_keys_host,
                                      double* threshold_io_host, void* stream) {
+    DGPB_NVTX("dgpb:ess_block");
     cudaStream_t st = (cudaStream_t)stream;
     DGPB_REQUIRE(ws && targets && uppers && layer_out && z && u_host && target_rows_host, "NULL argument");
     DGPB_REQUIRE(n_targets >= 1 && n_uppers >= 1 && n >= 1 && nu >= 3, "bad sizes");
@@ -469,16 +582,21 @@ extern "C" int dgpb_ess_block_cached(dgpb_ws* ws, const dgpb_node* targets, int 
         DGPB_REQUIRE(target_rows_host[k] >= 0 && target_rows_host[k] < layer_width, "target row out of range");
     bool all_dense = true;
     for (int u = 0; u < n_uppers; ++u) all_dense = all_dense && !uppers[u].vecch;
-    constexpr int kMaxWave = 8;
-    int cap = 1;  // candidate angles per wave
+    constexpr int kMaxWave = 8;                     // candidate angles per rank and wave
+    constexpr int kMaxCand = kMaxWave * kMaxRanks;  // candidate angles per wave
+    int cap = 1;  // candidate angles per rank and wave
     if (all_dense && n_uppers <= MAXB) cap = std::max(1, std::min(kMaxWave, std::min(g_ess_target_b, (int)MAXB) / n_uppers));
     const bool batched = all_dense && n_uppers <= MAXB;
+    // ranks that share a wave; Vecchia or oversized upper layers are evaluated by every rank (same numbers everywhere)
+    const int W = batched ? ws->comm.world : 1;
+    const int me = batched ? ws->comm.rank : 0;
+    const int nslots = cap + 1;   // local proposal images per wave (rank 0 may carry the threshold item as slot 0)
 
     if (g_pre_done_guard) DGPB_CUDA_TRY(cudaStreamWaitEvent(st, g_pre_done_guard, 0));  // see the wave pipeline below
     void *pnu, *pprop;
     const size_t layer_elems = (size_t)layer_width * n;
     DGPB_TRY(ws->reserve(SLOT_NU, sizeof(double) * (size_t)n_targets * n, &pnu));
-    DGPB_TRY(ws->reserve(SLOT_PROP, sizeof(double) * layer_elems * cap * 2, &pprop));
+    DGPB_TRY(ws->reserve(SLOT_PROP, sizeof(double) * layer_elems * nslots * 2, &pprop));
     double* nuv = (double*)pnu;
     double* prop = (double*)pprop;
 
@@ -506,7 +624,7 @@ extern "C" int dgpb_ess_block_cached(dgpb_ws* ws, const dgpb_node* targets, int 
     double tmin = theta - 2.0 * M_PI, tmax = theta;
 
     // rows of the layer that are not being updated are shared by every proposal
-    for (int s = 0; s < 2 * cap; ++s)
+    for (int s = 0; s < 2 * nslots; ++s)
         DGPB_CUDA_TRY(cudaMemcpyAsync(prop + s * layer_elems, layer_out, sizeof(double) * layer_elems,
                                       cudaMemcpyDeviceToDevice, st));
     int nprop = 0;
@@ -531,65 +649,71 @@ extern "C" int dgpb_ess_block_cached(dgpb_ws* ws, const dgpb_node* targets, int 
         DGPB_CUDA_TRY(cudaEventRecord(pre_go, st));
     }
     auto plan_wave = [&](double th0, double lmin, double lmax, int uidx, double* out_thetas) {
-        const int S = std::max(1, std::min(cap, 1 + (nu - uidx)));
-        out_thetas[0] = th0;
-        for (int s = 1; s < S; ++s) {
-            if (out_thetas[s - 1] < 0.0) lmin = out_thetas[s - 1]; else lmax = out_thetas[s - 1];  // imputation.py:115-118
-            out_thetas[s] = lmin + (lmax - lmin) * u_host[uidx + s - 1];                             // imputation.py:119
-        }
-        return S;
+        return ess_plan_wave(th0, lmin, lmax, u_host + uidx, nu - uidx, cap * W, out_thetas);
     };
-    auto launch_proposals = [&](const double* th, int S, double* pbuf, cudaStream_t s2) -> int {
-        for (int s = 0; s < S; ++s) {
-            const double c = cos(th[s]), sn = sin(th[s]);
-            for (int k = 0; k < n_targets; ++k) {
-                const int64_t row = target_rows_host[k];
-                propose_kernel<<<(unsigned)cdiv(n, 256), 256, 0, s2>>>(pbuf + s * layer_elems + row * n, layer_out + row * n,
-                                                                      nuv + (int64_t)k * n, c, sn, n);
-                DGPB_LAUNCHED();
-            }
+    auto launch_proposal = [&](double th, double* image, cudaStream_t s2) -> int {
+        const double c = cos(th), sn = sin(th);
+        for (int k = 0; k < n_targets; ++k) {
+            const int64_t row = target_rows_host[k];
+            propose_kernel<<<(unsigned)cdiv(n, 256), 256, 0, s2>>>(image + row * n, layer_out + row * n,
+                                                                  nuv + (int64_t)k * n, c, sn, n);
+            DGPB_LAUNCHED();
         }
         return DGPB_OK;
     };
+    // propose + assemble this rank's items of a wave (items [0, first) = threshold, then the candidates)
+    auto stage_wave = [&](const double* th, int S, int first, double* pbuf, int tslot, Batch* bt, Geom* g, int* nlocal,
+                          cudaStream_t s2) -> int {
+        const double* srcs[kMaxWave + 1];
+        int L = 0;
+        for (int i = me; i < first + S; i += W) {   // local slot of item i = i / W = L
+            DGPB_REQUIRE(L < nslots, "wave item does not fit the proposal buffer");
+            if (i < first) {
+                srcs[L] = nullptr;
+            } else {
+                DGPB_TRY(launch_proposal(th[i - first], pbuf + (size_t)L * layer_elems, s2));
+                srcs[L] = pbuf + (size_t)L * layer_elems;
+            }
+            ++L;
+        }
+        *nlocal = L;
+        return dense_items_assemble(ws, tslot, uppers, n_uppers, n, srcs, L, bt, g, s2);
+    };
     int wave = 0;               // parity selects the T set and the half of the proposal buffer
     bool pre_ready = false;     // the current wave was assembled ahead of time
-    int pre_S = 0;
-    double pre_thetas[kMaxWave];
+    int pre_S = 0, pre_L = 0;
+    double pre_thetas[kMaxCand];
     Batch pre_bt;
     Geom pre_g;
     while (true) {
         // ---- candidate angles of this wave (each one assumes every earlier one was rejected)
-        double thetas[kMaxWave];
+        double thetas[kMaxCand];
         const int S = plan_wave(theta, tmin, tmax, ui, thetas);
-        double* pcur = prop + (size_t)(wave & 1) * cap * layer_elems;
-        bool use_pre = pre_ready && pre_S == S;
+        double* pcur = prop + (size_t)(wave & 1) * nslots * layer_elems;
+        bool use_pre = pre_ready && pre_S == S && !thr_pending;
         for (int s = 0; use_pre && s < S; ++s) use_pre = pre_thetas[s] == thetas[s];
         // ---- likelihoods of the wave
-        double sums[kMaxWave + 1];
-        double wave_logdets[MAXB];
-        int pd[kMaxWave + 1], bad[kMaxWave + 1];
+        double sums[kMaxCand + 1];
+        double wave_logdets[(kMaxCand + 1) * MAXB / 1];
+        int pd[kMaxCand + 1], bad[kMaxCand + 1];
         Batch bt;
         Geom g;
         DenseBatchInfo info;
         int first = 0;  // index of candidate 0 in sums[]
         if (batched) {
-            int ni = S;
+            int nlocal = 0;
             if (use_pre) {
                 bt = pre_bt;
                 g = pre_g;
+                nlocal = pre_L;
                 DGPB_CUDA_TRY(cudaStreamWaitEvent(st, pre_done, 0));
             } else {
                 if (pre_ready) DGPB_CUDA_TRY(cudaStreamWaitEvent(st, pre_done, 0));  // stale speculative set: let it drain
-                DGPB_TRY(launch_proposals(thetas, S, pcur, st));
-                const double* srcs[kMaxWave + 1];
-                ni = 0;
-                if (thr_pending) srcs[ni++] = nullptr;
-                first = ni;
-                for (int s = 0; s < S; ++s) srcs[ni++] = pcur + s * layer_elems;
-                DGPB_TRY(dense_items_assemble(ws, wave & 1, uppers, n_uppers, n, srcs, ni, &bt, &g, st));
+                first = thr_pending ? 1 : 0;
+                DGPB_TRY(stage_wave(thetas, S, first, pcur, wave & 1, &bt, &g, &nlocal, st));
             }
             pre_ready = false;
-            DGPB_TRY(dense_items_factor(ws, uppers, n_uppers, ni, bt, g, st));
+            DGPB_TRY(dense_items_factor(ws, uppers, n_uppers, nlocal, W, bt, g, st));
             // ---- speculate: assemble the next wave while this one is being factored
             {
                 double lmin = tmin, lmax = tmax;
@@ -599,18 +723,14 @@ extern "C" int dgpb_ess_block_cached(dgpb_ws* ws, const dgpb_node* targets, int 
                 if (g_ess_prefetch && ui_next <= nu && ui_next >= 1) {
                     const double th_next = lmin + (lmax - lmin) * u_host[ui_next - 1];
                     pre_S = plan_wave(th_next, lmin, lmax, ui_next, pre_thetas);
-                    double* pnext = prop + (size_t)((wave + 1) & 1) * cap * layer_elems;
+                    double* pnext = prop + (size_t)((wave + 1) & 1) * nslots * layer_elems;
                     DGPB_CUDA_TRY(cudaStreamWaitEvent(pre_stream, pre_go, 0));  // the layer image and the prior draws exist
-                    DGPB_TRY(launch_proposals(pre_thetas, pre_S, pnext, pre_stream));
-                    const double* srcs2[kMaxWave];
-                    for (int s = 0; s < pre_S; ++s) srcs2[s] = pnext + s * layer_elems;
-                    DGPB_TRY(dense_items_assemble(ws, (wave + 1) & 1, uppers, n_uppers, n, srcs2, pre_S, &pre_bt, &pre_g,
-                                                  pre_stream));
+                    DGPB_TRY(stage_wave(pre_thetas, pre_S, 0, pnext, (wave + 1) & 1, &pre_bt, &pre_g, &pre_L, pre_stream));
                     DGPB_CUDA_TRY(cudaEventRecord(pre_done, pre_stream));
                     pre_ready = true;
                 }
             }
-            DGPB_TRY(dense_items_fetch(ws, uppers, n_uppers, n, ni, sums, pd, bad, wave_logdets, st));
+            DGPB_TRY(dense_items_fetch(ws, uppers, n_uppers, n, first + S, W, sums, pd, bad, wave_logdets, st));
             if (first == 1) {
                 if (!pd[0]) {
                     set_error("covariance of upper node %d is not positive definite", bad[0]);
@@ -620,7 +740,7 @@ extern "C" int dgpb_ess_block_cached(dgpb_ws* ws, const dgpb_node* targets, int 
                 thr_pending = false;
             }
         } else {
-            DGPB_TRY(launch_proposals(thetas, S, pcur, st));
+            DGPB_TRY(launch_proposal(thetas[0], pcur, st));
             DGPB_TRY(nodes_loglik(ws, uppers, n_uppers, n, pcur, &sums[0], st, &info));
             pd[0] = 1;
         }
@@ -643,27 +763,41 @@ extern "C" int dgpb_ess_block_cached(dgpb_ws* ws, const dgpb_node* targets, int 
             if (s + 1 < S) ++ui;  // the uniform that produced thetas[s + 1]
         }
         if (accepted >= 0) {
-            const double* pa = pcur + accepted * layer_elems;
+            const int ia = first + accepted;             // item index of the accepted candidate
+            const int owner = ia % W, slot = ia / W;     // the rank that evaluated it, its local slot there
+            const double* pa = pcur + (size_t)slot * layer_elems;
+            if (owner != me) {   // evaluated elsewhere: the same elementwise proposal, recomputed here
+                DGPB_TRY(launch_proposal(thetas[accepted], pcur, st));
+                pa = pcur;
+            }
             for (int k = 0; k < n_targets; ++k) {
                 const int64_t row = target_rows_host[k];
                 DGPB_CUDA_TRY(cudaMemcpyAsync(layer_out + row * n, pa + row * n, sizeof(double) * n,
                                               cudaMemcpyDeviceToDevice, st));
             }
             // the factors of the accepted proposal are the prior factors these nodes need as targets of the
-            // next layer pair; the accepted log-likelihood is the next threshold when their outputs are fixed
+            // next layer pair (they stay on the rank that computed them); the accepted log-likelihood is the
+            // next threshold when their outputs are fixed
             if (upper_keys_host) {
                 if (batched) {
-                    for (int u = 0; u < n_uppers; ++u)
-                        if (upper_keys_host[u] >= 0)
-                            DGPB_TRY(cache_store(ws, upper_keys_host[u], g, bt, (first + accepted) * n_uppers + u, st,
-                                                 &wave_logdets[(first + accepted) * n_uppers + u]));
+                    for (int u = 0; u < n_uppers; ++u) {
+                        if (upper_keys_host[u] < 0) continue;
+                        const double* ld = &wave_logdets[ia * n_uppers + u];
+                        if (owner == me) DGPB_TRY(cache_store(ws, upper_keys_host[u], g, bt, slot * n_uppers + u, st, ld));
+                        set_owner(ws, upper_keys_host[u], W > 1 ? owner : kOwnerAll, n, ld);
+                    }
                 } else {
                     for (int b = 0; b < info.B; ++b)
-                        if (upper_keys_host[info.map[b]] >= 0)
+                        if (upper_keys_host[info.map[b]] >= 0) {
                             DGPB_TRY(cache_store(ws, upper_keys_host[info.map[b]], info.g, info.bt, b, st));
+                            set_owner(ws, upper_keys_host[info.map[b]], kOwnerAll, n, nullptr);
+                        }
                     if (info.B == 0)  // batch not reusable: drop anything stale
                         for (int u = 0; u < n_uppers; ++u)
-                            if (upper_keys_host[u] >= 0) ws->cache[upper_keys_host[u]].valid = false;
+                            if (upper_keys_host[u] >= 0) {
+                                ws->cache[upper_keys_host[u]].valid = false;
+                                ws->owner.erase(upper_keys_host[u]);
+                            }
                 }
             }
             if (threshold_io_host) *threshold_io_host = sums[first + accepted];

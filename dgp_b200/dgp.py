@@ -56,25 +56,42 @@ class _GradBatcher:
         self.pending = []       # [node, n, P, result slot]
         self.ws, self.dev = ws, dev
 
+    MAX_BATCH = 32   # MAXB of the library's batched launches (dense.cuh)
+
+    def _chunk(self, n):
+        """Matrices per batched call: at most MAXB, and no more than the augmented (2n+1)^2 layouts that fit in
+        about half of the free device memory (a DGP may have any number of GP nodes; the reference has no limit)."""
+        from . import _lib as L
+        per = (2 * (n + 64) + 8) ** 2 * 8
+        try:
+            free = L.torch_mod().cuda.mem_get_info(self.dev)[0]
+        except Exception:  # pragma: no cover
+            free = 32 << 30
+        held = L.load().dgpb_ws_bytes(self.ws)   # scratch the workspace already owns is reused, not added
+        return int(max(1, min(self.MAX_BATCH, (free // 2 + held) // per)))
+
     def _flush_locked(self):
         from . import _lib as L
         reqs, self.pending = self.pending, []
         try:
-            B = len(reqs)
             n = reqs[0][1]
             if any(r[1] != n for r in reqs):
                 raise RuntimeError("nodes of one M-step must share the number of training points")
-            ldo = max(r[2] for r in reqs) + 2
-            arr = (L.DgpbNode * B)(*[r[0] for r in reqs])
-            out = np.zeros((B, ldo))
-            status = np.zeros(B, dtype=np.int32)
             L.torch_mod().cuda.set_device(self.dev)
-            rc = L.load().dgpb_nllik_grad_dense_batch(self.ws, arr, B, n, out.ctypes.data_as(L.c_vp), ldo,
-                                                      status.ctypes.data_as(L.c_vp), L.stream())
-            msg = L.load().dgpb_last_error().decode("utf-8", "replace") if rc != L.DGPB_OK else ""
-            for b, r in enumerate(reqs):
-                r[3].extend([rc if rc != L.DGPB_OK else int(status[b]), out[b].copy(),
-                             msg or "matrix %d of the batch is not positive definite" % b])
+            step = self._chunk(n)
+            for lo in range(0, len(reqs), step):
+                part = reqs[lo:lo + step]
+                B = len(part)
+                ldo = max(r[2] for r in part) + 2
+                arr = (L.DgpbNode * B)(*[r[0] for r in part])
+                out = np.zeros((B, ldo))
+                status = np.zeros(B, dtype=np.int32)
+                rc = L.load().dgpb_nllik_grad_dense_batch(self.ws, arr, B, n, out.ctypes.data_as(L.c_vp), ldo,
+                                                          status.ctypes.data_as(L.c_vp), L.stream())
+                msg = L.load().dgpb_last_error().decode("utf-8", "replace") if rc != L.DGPB_OK else ""
+                for b, r in enumerate(part):
+                    r[3].extend([rc if rc != L.DGPB_OK else int(status[b]), out[b].copy(),
+                                 msg or "matrix %d of the batch is not positive definite" % (lo + b)])
         except Exception as exc:  # never leave the other optimiser threads waiting
             for r in reqs:
                 if not r[3]:
@@ -490,7 +507,11 @@ class dgp:
                 pgb = trange(1, N + 1, disable=disable)
                 for i in pgb:
                     t0 = time.perf_counter()
-                    (self.imp).sample(burnin=ess_burn)
+                    if i == 1:   # dgp.py:1383-1385: the first I-step of a call runs under the initial scale
+                        with self.change_init_scale():
+                            (self.imp).sample(burnin=ess_burn)
+                    else:
+                        (self.imp).sample(burnin=ess_burn)
                     if self.vecch and (self.N + i & (self.N + i - 1)) == 0 and self.N + i > 1:
                         (self.imp).update_ord_nn()
                     t1 = time.perf_counter()
@@ -521,12 +542,42 @@ class dgp:
         GPU where a single n = 5000 node leaves the tensor pipe waiting on its serial panel chain.  Each node sees
         exactly the numbers it would see alone (the batched kernels treat matrices independently), so parameter
         paths do not depend on the scheduling.  Vecchia nodes keep the one-node-at-a-time path."""
+        from . import parallel
+
+        nodes = [(l, kernel) for l in range(self.n_layer) for kernel in self.all_layer[l] if kernel.type == 'gp']
+        ch = parallel.chain()
+        if ch is None:
+            self._m_step_nodes(nodes)
+            return
+        # one chain on several GPUs: the nodes are dealt over the ranks, every rank optimises its share and the
+        # results are exchanged (the reference deals the nodes of a layer to a process pool, dgp.py:1463-1467)
+        mine = parallel.mstep_share(len(nodes), ch["rank"], ch["world"])
+        failed = None
+        try:
+            self._m_step_nodes([nodes[i] for i in mine])
+        except np.linalg.LinAlgError as exc:
+            failed = exc
+        mine_set = set(mine)
+        for i, (l, kernel) in enumerate(nodes):   # cheap host state the owner updated inside its share
+            if i in mine_set:
+                continue
+            if kernel.prior_name == 'ref':
+                kernel.compute_cl()
+            if l != 0:
+                kernel.r2()
+        if parallel.sync_params([k for _, k in nodes], mine, failed is not None):
+            raise failed if failed is not None else np.linalg.LinAlgError(
+                "a GP node optimised on another rank is not positive definite")
+
+    def _m_step_nodes(self, nodes):
+        """The M-step of the nodes in `nodes` ((layer index, kernel) pairs) on this GPU."""
         import os
         from concurrent.futures import ThreadPoolExecutor
 
         from . import _lib as L
 
-        nodes = [(l, kernel) for l in range(self.n_layer) for kernel in self.all_layer[l] if kernel.type == 'gp']
+        if not nodes:
+            return
         torch = L.torch_mod()
         dev = L.device()
         dense = [it for it in nodes if not it[1].vecch]
@@ -580,7 +631,8 @@ class dgp:
 
     def ptrain(self, N=500, ess_burn=10, disable=False, core_num=None):
         """dgp.py:1414-1467 optimises the GP nodes of a layer in a process pool; here the nodes of ALL layers already
-        share one batched factorisation per optimiser round (`_m_step`), so this is `train`."""
+        share one batched factorisation per optimiser round (`_m_step`), and with `dgp_b200.parallel.enable` they are
+        dealt over the GPUs of the box (one process per GPU), so this is `train`."""
         return self.train(N, ess_burn, disable)
 
     def compute_r2(self):

@@ -60,6 +60,8 @@ class emulator:
         for one in self.all_layer_set:
             for layer in one:
                 for kernel in layer:
+                    if kernel.type != 'gp':
+                        continue
                     kernel.vecch = True
                     if kernel.ord is None:
                         kernel.m = min(25, kernel.input.shape[0] - 1) if kernel.m is None else kernel.m
@@ -72,6 +74,8 @@ class emulator:
         for one in self.all_layer_set:
             for layer in one:
                 for kernel in layer:
+                    if kernel.type != 'gp':
+                        continue
                     kernel.vecch = False
                     kernel.compute_stats()
 
@@ -86,6 +90,8 @@ class emulator:
             for one in self.all_layer_set:
                 for layer in one:
                     for kernel in layer:
+                        if kernel.type != 'gp':
+                            continue
                         if not self.vecch:
                             kernel.vecch = True
                         kernel.loo_state = True
@@ -95,6 +101,8 @@ class emulator:
                 for one in self.all_layer_set:
                     for layer in one:
                         for kernel in layer:
+                            if kernel.type != 'gp':
+                                continue
                             if not self.vecch:
                                 kernel.vecch = False
                             kernel.loo_state = False

@@ -43,6 +43,11 @@ class _DeviceLayers:
             for kern in layer:
                 if kern.rep is not None:
                     raise NotImplementedError("dgp_b200: replicate pooling is outside the SI hot path")
+                if l > 0 and kern.type == 'gp' and kern.prior_name == 'ref':
+                    # the reference adds log_prior() -- whose scale `cl` follows the proposed inputs -- to the ESS
+                    # likelihood of such a node (kernel_class.py:489-491, 506-508); the device loop has no such term
+                    raise NotImplementedError("dgp_b200: the reference prior ('ref') on a GP node above the first "
+                                              "layer changes the ESS acceptance rule and is not built")
             if any(kern.type != 'gp' for kern in layer):
                 if l != len(all_layer) - 1 or l == 0 or any(kern.type != 'likelihood' for kern in layer):
                     raise NotImplementedError("dgp_b200: likelihood nodes are supported as a final layer made of "
@@ -231,6 +236,12 @@ class imputer:
                         self.n_proposals += dev.block_update(l, [k], uks)
                         self.n_block_updates += 1
         dev.write_back()
+        import os
+        if os.environ.get('DGPB_CHAIN_CHECK') == '1':
+            from . import parallel
+            if parallel.chain() is not None:   # debug aid: the ranks of a shared chain hold identical layers
+                parallel.assert_in_step([float(np.sum(k.output)) for layer in self.all_layer for k in layer
+                                         if k.type == 'gp'] + [float(self.n_proposals)], "latent layers after an I-step")
 
     def key_stats(self):
         """Compute and store key statistics used in predictions (imputation.py:223-231)."""

@@ -40,7 +40,7 @@ class container:
     def _kernels(self):
         if self.type == 'gp':
             return [self.structure]
-        return [k for layer in self.structure for k in layer]
+        return [k for layer in self.structure for k in layer if k.type == 'gp']
 
     def to_vecchia(self):
         """linkgp.py:64-76."""

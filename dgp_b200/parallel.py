@@ -1,10 +1,126 @@
-"""Multi-GPU plumbing: one process per GPU, `torch.distributed` (NCCL over NVLink) for the only exchange the
-path has -- gathering the per-shard predictive moments.  The prediction of a test point
-depends on no other test point, so rows are split across ranks with no collective on the data path.
+"""Multi-GPU plumbing: one process per GPU.
+
+* ONE chain on several GPUs (`enable`): every rank holds the same model and draws the same random numbers; the
+  candidate angles of every ESS wave are dealt over the ranks inside libdgpb.so (its own NCCL communicator,
+  `dgpb_comm_init`) and the GP nodes of the M-step are dealt over the ranks here (`mstep_share` / `sync_params`,
+  one all-reduce of <= 36 doubles per node).  The reference's counterpart is `ptrain`'s process pool over the
+  nodes of a layer (dgp.py:1414-1472).
+* Prediction shards by test points (`predict_sharded`: each point is independent, one all-gather of the moments).
 """
 from __future__ import annotations
 
 import numpy as np
+
+_chain = None   # {"dist": torch.distributed, "rank": r, "world": G, "device": bool} once `enable` was called
+
+
+def enable(dist, seed=None):
+    """Share ONE chain between the ranks of the initialised default process group.  Every rank must then build
+    the same model from the same data and call the same methods in the same order; `seed` (optional) seeds
+    numpy's global generator and the generator behind the dense prior draws identically on every rank.  With the
+    "nccl" backend the library's own communicator is created on this thread's workspace (ESS waves); with "gloo"
+    (CPU tests) only the host-side exchanges are active."""
+    global _chain
+    if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
+        _chain = None
+        return None
+    import torch
+
+    from . import _lib as L
+    from .imputation import nb_seed
+
+    rank, world = dist.get_rank(), dist.get_world_size()
+    on_device = dist.get_backend() == "nccl"
+    if on_device:
+        lib = L.load()
+        ident = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            buf = (L.ctypes.c_char * 128)()
+            L.check(lib.dgpb_comm_unique_id(L.ctypes.cast(buf, L.c_vp)))
+            ident = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).clone()
+        ident = ident.to(L.device())
+        dist.broadcast(ident, 0)
+        raw = bytes(ident.cpu().numpy().tobytes())
+        buf = L.ctypes.create_string_buffer(raw, 128)
+        L.check(lib.dgpb_comm_init(L.workspace(), rank, world, L.ctypes.cast(buf, L.c_vp)))
+    if seed is not None:
+        np.random.seed(seed)
+        nb_seed(seed)
+    _chain = {"dist": dist, "rank": rank, "world": world, "device": on_device}
+    return _chain
+
+
+def disable():
+    """Back to one independent chain per process."""
+    global _chain
+    if _chain is not None and _chain["device"]:
+        from . import _lib as L
+        L.check(L.load().dgpb_comm_destroy(L.workspace()))
+    _chain = None
+
+
+def chain():
+    """The shared-chain state set by `enable`, or None."""
+    return _chain
+
+
+def mstep_share(n_nodes, rank, world):
+    """Indices of the GP nodes whose L-BFGS-B run this rank carries in an M-step: round-robin over all layers (given
+    the imputation the nodes are independent; the reference deals the nodes of one layer to a process pool)."""
+    return list(range(rank, n_nodes, world))
+
+
+def _allreduce_sum(arr):
+    """Element-wise sum of a float64 numpy array over the ranks of the chain (NCCL on the device, gloo on the host)."""
+    import torch
+
+    ch = _chain
+    t = torch.from_numpy(np.ascontiguousarray(arr, dtype=np.float64))
+    if ch["device"]:
+        from . import _lib as L
+        t = t.to(L.device())
+    ch["dist"].all_reduce(t)
+    return t.cpu().numpy()
+
+
+_PAR_W = 3 + 32   # scale, nugget, len(length), length[<= 32]
+
+
+def sync_params(kernels, mine, failed):
+    """After the ranks optimised their share of the GP nodes: hand every node's (scale, length, nugget) to every
+    rank.  `mine` = indices this rank optimised, `failed` = this rank hit a LinAlgError.  Rows of the other ranks'
+    nodes are zero here, so one sum all-reduce moves each value unchanged.  Returns True if ANY rank failed (every
+    rank then raises, which keeps dgp.train's restart logic in step)."""
+    buf = np.zeros((len(kernels) + 1, _PAR_W))
+    for i in mine:
+        k = kernels[i]
+        buf[i, 0], buf[i, 1], buf[i, 2] = k.scale[0], k.nugget[0], len(k.length)
+        buf[i, 3:3 + len(k.length)] = k.length
+    buf[-1, 0] = 1.0 if failed else 0.0
+    out = _allreduce_sum(buf)
+    if out[-1, 0] > 0:
+        return True
+    mine = set(mine)
+    for i, k in enumerate(kernels):
+        if i in mine:
+            continue
+        nl = int(round(out[i, 2]))
+        k.scale = np.array([out[i, 0]])
+        k.nugget = np.array([out[i, 1]])
+        k.length = out[i, 3:3 + nl].copy()
+        k.add_to_path()
+    return False
+
+
+def assert_in_step(values, what="chain state"):
+    """Debug aid (DGPB_CHAIN_CHECK=1): the ranks of a shared chain must hold identical numbers."""
+    v = np.atleast_1d(np.asarray(values, dtype=np.float64)).ravel()
+    G, r = _chain["world"], _chain["rank"]
+    buf = np.zeros((G, len(v)))
+    buf[r] = v
+    out = _allreduce_sum(buf)
+    if not all(np.array_equal(out[0], out[g], equal_nan=True) for g in range(1, G)):
+        raise RuntimeError(f"dgp_b200: the ranks of the shared chain diverged ({what}): {out.tolist()}")
 
 
 def shard_bounds(M, rank, world):

@@ -270,6 +270,27 @@ int dgpb_linkgp_predict(dgpb_ws* ws, const double* m_in, const double* v_in, con
 int dgpb_aggregate(const double* means, const double* vars, int64_t S, int64_t len, double* mu,
                    double* sigma2, void* stream);
 
+/* ---- 6. one chain on several GPUs ------------------------------------------------ */
+
+/* The reference parallelises the M-step over GP nodes in a process pool (dgp.py:1414-1472, `ptrain`) and nothing
+ * else.  Here one process drives one GPU and the processes of a box share ONE chain: every rank holds the same
+ * latent layers and takes the same decisions; the candidate angles of an ESS wave (imputation.py:107-119) are
+ * dealt over the ranks, each rank factors its share and the per-matrix results are all-gathered over NCCL.
+ * dgpb_comm_unique_id: 128-byte NCCL id, created on one rank and handed to the others by the host side
+ * (torch.distributed broadcast).  dgpb_comm_init attaches a communicator to the workspace; afterwards
+ * dgpb_ess_block_cached / dgpb_ess_block_lik on that workspace are COLLECTIVE calls: every rank must make them
+ * with identical arguments (same draws, same uniforms).  world = 1 detaches.  Results are bit-identical to the
+ * single-GPU call. */
+int dgpb_comm_unique_id(char* id128_host);
+int dgpb_comm_init(dgpb_ws* ws, int rank, int world, const char* id128_host);
+int dgpb_comm_destroy(dgpb_ws* ws);
+int dgpb_comm_info(const dgpb_ws* ws, int* rank_host, int* world_host);
+/* Host-only plan of one ESS wave (no GPU needed): candidate angles under the assumption that every earlier one is
+ * rejected (imputation.py:111-119; u_host = the uniforms those rejections consume) and the rank / local slot that
+ * evaluates each item (item 0 = the threshold when first = 1, then the candidates).  cap = candidates per rank. */
+int dgpb_ess_plan_wave(double theta0, double tmin, double tmax, const double* u_host, int nu_left, int first, int cap,
+                       int world, int* n_cand_host, double* thetas_host, int* rank_host, int* slot_host);
+
 /* ---- measurement helpers (bench.py / DESIGN.md roofline denominators) ----------------------- */
 
 /* C (M x N) = A (M x K) * B (N x K)^T with the library's own DMMA tile kernel. */
