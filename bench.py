@@ -426,7 +426,13 @@ def run_gpu(args):
                         "d2h_bytes_per_step": d2h // args.steps},
                 "gpu_launches": int(launches), "ess_proposals_per_step": nprop / args.steps,
                 "phase_ms_per_step": {"i_step": 1e3 * (model.timing["i_step"] - tim0["i_step"]) / args.steps,
-                                      "m_step": 1e3 * (model.timing["m_step"] - tim0["m_step"]) / args.steps},
+                                      "m_step": 1e3 * (model.timing["m_step"] - tim0["m_step"]) / args.steps,
+                                      "m_step_in_library": 1e3 * (model.timing.get("m_batched_s", 0.0)
+                                                                  - tim0.get("m_batched_s", 0.0)) / args.steps,
+                                      "m_step_batched_calls": (model.timing.get("m_batched_calls", 0)
+                                                               - tim0.get("m_batched_calls", 0)) / args.steps,
+                                      "m_step_matrices": (model.timing.get("m_batched_matrices", 0)
+                                                          - tim0.get("m_batched_matrices", 0)) / args.steps},
                 "roofline": roof,
                 "cpu_baseline": cpu, "clocks": clocks.summary(), "predict": predict, "predict_vecchia": predict_v}
         print(json.dumps(line), flush=True)

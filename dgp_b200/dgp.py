@@ -55,6 +55,7 @@ class _GradBatcher:
         self.active = nworkers
         self.pending = []       # [node, n, P, result slot]
         self.ws, self.dev = ws, dev
+        self.stats = [0, 0, 0.0]   # batched calls, matrices, seconds inside the library (bench.py's M-step breakdown)
 
     MAX_BATCH = 32   # MAXB of the library's batched launches (dense.cuh)
 
@@ -86,8 +87,12 @@ class _GradBatcher:
                 arr = (L.DgpbNode * B)(*[r[0] for r in part])
                 out = np.zeros((B, ldo))
                 status = np.zeros(B, dtype=np.int32)
+                t0 = time.perf_counter()
                 rc = L.load().dgpb_nllik_grad_dense_batch(self.ws, arr, B, n, out.ctypes.data_as(L.c_vp), ldo,
                                                           status.ctypes.data_as(L.c_vp), L.stream())
+                self.stats[0] += 1
+                self.stats[1] += B
+                self.stats[2] += time.perf_counter() - t0
                 msg = L.load().dgpb_last_error().decode("utf-8", "replace") if rc != L.DGPB_OK else ""
                 for b, r in enumerate(part):
                     r[3].extend([rc if rc != L.DGPB_OK else int(status[b]), out[b].copy(),
@@ -626,6 +631,9 @@ class dgp:
                 fut.result()
             except BaseException as exc:  # noqa: BLE001
                 errors.append(exc)
+        if hasattr(self, 'timing'):
+            for key, val in zip(('m_batched_calls', 'm_batched_matrices', 'm_batched_s'), batcher.stats):
+                self.timing[key] = self.timing.get(key, 0) + val
         if errors:
             raise errors[0]
 

@@ -313,18 +313,23 @@ class emulator:
                 variances.append(var)
                 layers_all.append(per_layer)
         if method == 'sampling':
+            # numpy's global generator in the reference's order (emulation.py:790-830): inner layers one (M x width)
+            # block per (imputation, replicate), the final GP layer column by column
+            def draw(mu, va, by_column):
+                mu, va = L.to_host(mu), L.to_host(va)                     # S x M x width
+                mu, va = np.repeat(mu, sample_size, 0), np.repeat(va, sample_size, 0)
+                if by_column:
+                    return np.random.normal(mu.transpose(0, 2, 1), np.sqrt(va.transpose(0, 2, 1))).transpose(1, 2, 0)
+                return np.random.normal(mu, np.sqrt(va)).transpose(2, 1, 0)
+
             if full_layer:
                 out = []
                 for l in range(self.n_layer):
-                    mu_l = L.to_host(torch.stack([layers_all[s][l][0] for s in range(S)], 0))
-                    va_l = L.to_host(torch.stack([layers_all[s][l][1] for s in range(S)], 0))
-                    draws = np.random.normal(np.repeat(mu_l, sample_size, 0), np.sqrt(np.repeat(va_l, sample_size, 0)))
-                    out.append(list(draws.transpose(2, 1, 0)))
+                    mu_l = torch.stack([layers_all[s][l][0] for s in range(S)], 0)
+                    va_l = torch.stack([layers_all[s][l][1] for s in range(S)], 0)
+                    out.append(list(draw(mu_l, va_l, l == self.n_layer - 1)))
                 return out
-            mu_s = L.to_host(torch.stack(means, 0))
-            va_s = L.to_host(torch.stack(variances, 0))
-            draws = np.random.normal(np.repeat(mu_s, sample_size, 0), np.sqrt(np.repeat(va_s, sample_size, 0)))
-            return list(draws.transpose(2, 1, 0))
+            return list(draw(torch.stack(means, 0), torch.stack(variances, 0), True))
         if method != 'mean_var':
             raise Exception("method must be 'mean_var' or 'sampling'")
 

@@ -239,25 +239,32 @@ class lgp:
             per_imp.append(outs)
         S = len(per_imp)
 
+        layers = range(self.L) if full_layer else [self.L - 1]
+        if method == 'sampling':
+            # draws in the reference's order (linkgp.py:381-384, 415-417): imputation by imputation, layer by layer,
+            # emulator by emulator, one (sample_size x M x D_out) block of normals each
+            blocks = {}
+            for s in range(S):
+                for l in layers:
+                    for k in range(len(self.all_layer[l])):
+                        mu_k, va_k = L.to_host(per_imp[s][l][k][0]), L.to_host(per_imp[s][l][k][1])
+                        draw = np.random.normal(mu_k, np.sqrt(va_k), size=(sample_size,) + mu_k.shape)
+                        blocks.setdefault((l, k), []).append(draw.transpose(2, 1, 0))
+            out = [[np.concatenate(blocks[(l, k)], axis=2) for k in range(len(self.all_layer[l]))] for l in layers]
+            return out if full_layer else out[0]
+
         def agg(l, k):
             ms = torch.stack([per_imp[s][l][k][0] for s in range(S)], 0).contiguous()
             vs = torch.stack([per_imp[s][l][k][1] for s in range(S)], 0).contiguous()
-            if method == 'sampling':
-                mu_s, va_s = L.to_host(ms), L.to_host(vs)
-                draws = np.random.normal(np.repeat(mu_s, sample_size, 0), np.sqrt(np.repeat(va_s, sample_size, 0)))
-                return draws.transpose(2, 1, 0), None
             mu, s2 = torch.empty_like(ms[0]), torch.empty_like(ms[0])
             L.check(lib.dgpb_aggregate(L.ptr(ms), L.ptr(vs), S, ms[0].numel(), L.ptr(mu), L.ptr(s2), L.stream()))
             return L.to_host(mu), L.to_host(s2)
 
-        layers = range(self.L) if full_layer else [self.L - 1]
         mus, s2s = [], []
         for l in layers:
             pairs = [agg(l, k) for k in range(len(self.all_layer[l]))]
             mus.append([p[0] for p in pairs])
             s2s.append([p[1] for p in pairs])
-        if method == 'sampling':
-            return mus if full_layer else mus[0]
         if full_layer:
             return mus, s2s
         return mus[0], s2s[0]

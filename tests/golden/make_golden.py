@@ -2,7 +2,7 @@
 
 Run in the build container only (the reference is not present on the GPU box):
 
-    python tests/golden/make_golden.py [dense jd vecchia ess e2e loo metric update lik]
+    python tests/golden/make_golden.py [dense jd vecchia ess e2e loo metric update lik floor sampling]
 
 Writes `tests/golden/*.npz` (one file per group: dense_nodes, jd, vecchia_nodes, ess_replay, e2e, loo, metric,
 update, likelihood; every group is seeded, re-running reproduces the committed files bit for bit).  Every fixture stores the exact inputs fed to the reference function
@@ -658,8 +658,299 @@ def gen_lik():
     save("likelihood", **out)
 
 
+# ---------------------------------------------------------------- noise floor of the reference against itself
+def _ulp_jitter(rng, a):
+    """Every entry moved to a neighbouring double (relative change <= 2.3e-16), at random up or down."""
+    a = np.asarray(a, dtype=np.float64)
+    return np.where(rng.uniform(size=a.shape) < 0.5, np.nextafter(a, -np.inf), np.nextafter(a, np.inf))
+
+
+def _spread(base, variants):
+    """Largest absolute deviation of any variant from the base run, element-wise."""
+    base = {k: np.atleast_1d(np.asarray(v, dtype=np.float64)) for k, v in base.items()}
+    out = {k: np.zeros_like(v) for k, v in base.items()}
+    for var in variants:
+        for k, v in var.items():
+            out[k] = np.maximum(out[k], np.abs(np.atleast_1d(np.asarray(v, dtype=np.float64)) - base[k]))
+    return out
+
+
+def gen_floor():
+    """SURVEY.md section 7 hard part 1(b): how much does the UNMODIFIED reference move when nothing meaningful
+    changes?  Three sources, element-wise maximum of all:
+      (a) the BLAS thread count (1 thread against all cores: another summation order inside LAPACK / BLAS),
+      (b) every input entry moved to a neighbouring double (8 random draws),
+      (c) the committed fixture against a fresh run of the same code on the same inputs (another process, possibly
+          another host CPU: numba compiles for the machine it runs on).
+    Written to floor.npz with the keys of the fixtures they belong to; the GPU parity tests bound every error that
+    exceeds the 1e-9 relative target by a multiple of this floor.  Reads the committed fixtures (their exact inputs)
+    and never rewrites them."""
+    from threadpoolctl import threadpool_limits
+
+    rng = np.random.default_rng(SEED + 77)
+    out = {}
+
+    # ---- dense nodes
+    g = np.load(os.path.join(HERE, "dense_nodes.npz"))
+    for ci in range(int(g["ncases"])):
+        p = f"c{ci}_"
+        nugget_est, scale_est, d_loc, d_glob = [int(v) for v in g[p + "flags"][:4]]
+        name = str(g[p + "name"])
+
+        def run(X, y, xt, zt, mt, vt):
+            k = kernel(length=g[p + "length"].copy(), scale=g[p + "scale"][0], nugget=g[p + "nugget"][0], name=name,
+                       nugget_est=bool(nugget_est), scale_est=bool(scale_est),
+                       connect=np.arange(d_glob) if d_glob else None)
+            k.input, k.input_dim = X[:, :d_loc].copy(), np.arange(d_loc)
+            if d_glob:
+                k.global_input = X[:, d_loc:].copy()
+            k.output, k.D = y.copy(), d_loc + d_glob
+            k.para_path = np.atleast_2d(np.concatenate((k.scale, k.length, k.nugget)))
+            r = {"loglik": k.log_likelihood_func()}
+            f, gr = k.llik(k.log_t().copy())
+            r["nllik"], r["nllik_grad"] = f, gr
+            k.compute_stats()
+            r["Rinv_y"] = k.Rinv_y
+            r["gp_m"], r["gp_v"] = k.gp_prediction(xt, zt)
+            r["lk_m"], r["lk_v"] = k.linkgp_prediction(mt, vt, zt)
+            return r
+
+        X, y, xt = g[p + "X"], g[p + "y"], g[p + "xt"]
+        zt = g[p + "zt"] if d_glob else None
+        mt, vt = g[p + "lk_m_in"], g[p + "lk_v_in"]
+        base = run(X, y, xt, zt, mt, vt)
+        variants = [{key: g[p + key] for key in base if p + key in g.files}]
+        with threadpool_limits(limits=1):
+            variants.append(run(X, y, xt, zt, mt, vt))
+        for _ in range(8):
+            variants.append(run(_ulp_jitter(rng, X), _ulp_jitter(rng, y), _ulp_jitter(rng, xt),
+                                None if zt is None else _ulp_jitter(rng, zt), _ulp_jitter(rng, mt), vt))
+        for key, v in _spread(base, variants).items():
+            out[f"dense_{p}{key}"] = v
+
+    # ---- Vecchia nodes (orderings and neighbour sets fixed: the integers of the fixture)
+    g = np.load(os.path.join(HERE, "vecchia_nodes.npz"))
+    for ci in range(int(g["ncases"])):
+        p = f"c{ci}_"
+        nugget_est, scale_est, d_loc, d_glob, m = [int(v) for v in g[p + "flags"]]
+        name = str(g[p + "name"])
+
+        def runv(X, y, xt, zt, mt, vt, z):
+            k = kernel(length=g[p + "length"].copy(), scale=g[p + "scale"][0], nugget=g[p + "nugget"][0], name=name,
+                       nugget_est=bool(nugget_est), scale_est=bool(scale_est),
+                       connect=np.arange(d_glob) if d_glob else None)
+            k.input, k.input_dim = X[:, :d_loc].copy(), np.arange(d_loc)
+            if d_glob:
+                k.global_input = X[:, d_loc:].copy()
+            k.output, k.D = y.copy(), d_loc + d_glob
+            k.para_path = np.atleast_2d(np.concatenate((k.scale, k.length, k.nugget)))
+            k.vecch, k.m = True, m
+            k.ord, k.NNarray = g[p + "ord"], g[p + "NNarray"]
+            k.rev_ord = np.argsort(k.ord)
+            r = {"llik": k.log_likelihood_func_vecch()}
+            Lm = V.L_matrix(X[k.ord], k.NNarray, k.length, k.nugget[0], name)
+            r["Lmatrix"] = Lm
+            r["draw"] = V.forward_solve_sp(Lm / np.sqrt(k.scale[0]), k.NNarray, z)
+            f, gr = k.llik_vecch(k.log_t().copy())
+            r["nllik"], r["nllik_grad"] = f, gr
+            k.pred_m = g[p + "pred_NN"].shape[1]
+            r["gp_m"], r["gp_v"] = k.gp_prediction(xt, zt)
+            r["lk_m"], r["lk_v"] = k.linkgp_prediction(mt, vt, zt)
+            return r
+
+        X, y, xt, z = g[p + "X"], g[p + "y"], g[p + "xt"], g[p + "z"]
+        zt = g[p + "zt"] if d_glob else None
+        mt, vt = g[p + "lk_m_in"], g[p + "lk_v_in"]
+        base = runv(X, y, xt, zt, mt, vt, z)
+        # (c) the committed fixture itself: the same reference code run in another process / on another host CPU
+        # (numba compiles for the host it runs on), which moves the ill-conditioned Matern variances by up to 2e-5
+        variants = [{key: g[p + key] for key in base if p + key in g.files}]
+        with threadpool_limits(limits=1):
+            variants.append(runv(X, y, xt, zt, mt, vt, z))
+        for _ in range(8):
+            variants.append(runv(_ulp_jitter(rng, X), _ulp_jitter(rng, y), _ulp_jitter(rng, xt),
+                                 None if zt is None else _ulp_jitter(rng, zt), _ulp_jitter(rng, mt), vt, z))
+        for key, v in _spread(base, variants).items():
+            out[f"vecchia_{p}{key}"] = v
+
+    # ---- end to end: emulator.predict on the frozen imputations of e2e.npz
+    g = np.load(os.path.join(HERE, "e2e.npz"))
+
+    def ref_layers(prefix, name, jitter):
+        layers, l = [], 0
+        while f"{prefix}L{l}K0_input" in g.files:
+            layer, kk = [], 0
+            while f"{prefix}L{l}K{kk}_input" in g.files:
+                q = f"{prefix}L{l}K{kk}_"
+                node = kernel(length=g[q + "length"].copy(), scale=g[q + "scale"][0], nugget=g[q + "nugget"][0], name=name)
+                node.input, node.output = jitter(g[q + "input"]), jitter(g[q + "output"])
+                node.input_dim = np.arange(node.input.shape[1])
+                if q + "global_input" in g.files:
+                    node.global_input = jitter(g[q + "global_input"])
+                    node.connect = np.arange(node.global_input.shape[1])
+                node.vecch = False
+                node.compute_stats()
+                layer.append(node)
+                kk += 1
+            layers.append(layer)
+            l += 1
+        return layers
+
+    def run_emu(tag, name, jitter):
+        emu = dgpsi.emulator.__new__(dgpsi.emulator)
+        emu.all_layer_set = [ref_layers(f"{tag}_S{s}_", name, jitter) for s in range(int(g[f"{tag}_nimp"]))]
+        emu.all_layer = emu.all_layer_set[0]
+        emu.n_layer = len(emu.all_layer)
+        emu.vecch = False
+        mu, var = emu.predict(jitter(g[f"{tag}_xt"]))
+        return {"mu": mu, "var": var}
+
+    for tag, name in (("step", "sexp"), ("mat", "matern2.5")):
+        base = run_emu(tag, name, lambda a: np.array(a, copy=True))
+        assert np.allclose(base["mu"], g[f"{tag}_mu"], rtol=0, atol=1e-5), tag
+        variants = [{"mu": g[f"{tag}_mu"], "var": g[f"{tag}_var"]}]
+        with threadpool_limits(limits=1):
+            variants.append(run_emu(tag, name, lambda a: np.array(a, copy=True)))
+        for _ in range(8):
+            variants.append(run_emu(tag, name, lambda a: _ulp_jitter(rng, a)))
+        for key, v in _spread(base, variants).items():
+            out[f"e2e_{tag}_{key}"] = v
+
+    # ---- ESS sweeps with injected draws: latent columns after the sweeps (decisions must not change)
+    g = np.load(os.path.join(HERE, "ess_replay.npz"))
+    for ci in range(int(g["ncases"])):
+        p = f"c{ci}_"
+        widths, name, vecch = [int(w) for w in g[p + "widths"]], str(g[p + "name"]), bool(g[p + "vecch"])
+        sweeps = int(g[p + "sweeps"])
+
+        def run_ess(jitter):
+            layers = []
+            for l, w in enumerate(widths):
+                layer = []
+                for kk in range(w):
+                    q = f"{p}pre_L{l}K{kk}_"
+                    node = kernel(length=g[q + "length"].copy(), scale=g[q + "scale"][0], nugget=g[q + "nugget"][0],
+                                  name=name, scale_est=(l == len(widths) - 1))
+                    node.input, node.output = jitter(g[q + "input"]), jitter(g[q + "output"])
+                    node.input_dim = np.arange(node.input.shape[1])
+                    if q + "global_input" in g.files:
+                        node.global_input = jitter(g[q + "global_input"])
+                        node.connect = np.arange(node.global_input.shape[1])
+                    node.D = node.input.shape[1] + (0 if node.global_input is None else node.global_input.shape[1])
+                    node.vecch = vecch
+                    if vecch:
+                        node.ord, node.NNarray = g[q + "ord"], g[q + "NNarray"]
+                        node.rev_ord = np.argsort(node.ord)
+                        node.m = node.NNarray.shape[1] - 1
+                    layer.append(node)
+                layers.append(layer)
+            # the layers feed each other: inputs of layer l+1 ARE the outputs of layer l
+            for l in range(1, len(widths)):
+                col = np.concatenate([nd.output for nd in layers[l - 1]], 1)
+                for nd in layers[l]:
+                    nd.input = col[:, nd.input_dim].copy()
+            inj = Injector(g[p + "Z"], np.concatenate((g[p + "U"], np.full(64, 0.5))))
+            old = IMP.fmvn, IMP.fmvn_sp, IMP.uniform
+            IMP.fmvn, IMP.fmvn_sp, IMP.uniform = inj.fmvn, inj.fmvn_sp, inj.uniform
+            try:
+                IMP.imputer(layers, True).sample(burnin=sweeps - 1)
+            finally:
+                IMP.fmvn, IMP.fmvn_sp, IMP.uniform = old
+            if inj.ui != len(g[p + "U"]):
+                return None   # a decision flipped under the perturbation: not a rounding-level comparison
+            return {f"post_L{l}K{kk}": layers[l][kk].output for l in range(len(widths)) for kk in range(widths[l])}
+
+        base = run_ess(lambda a: np.array(a, copy=True))
+        assert base is not None, ci
+        variants = [{key: g[f"{p}{key}_output"] for key in base}]
+        with threadpool_limits(limits=1):
+            variants.append(run_ess(lambda a: np.array(a, copy=True)))
+        for _ in range(8):
+            variants.append(run_ess(lambda a: _ulp_jitter(rng, a)))
+        variants = [v for v in variants if v is not None]
+        for key, v in _spread(base, variants).items():
+            out[f"ess_{p}{key}"] = v
+        out[f"ess_{p}variants"] = np.array(len(variants))
+    save("floor", **out)
+
+
+# ---------------------------------------------------------------- method='sampling' with the reference's own draws
+def gen_sampling():
+    """`predict(method='sampling')` of a DGP emulator (two outputs; final layer only and every
+    layer), of a linked system and of a single GP, with numpy's global generator seeded right before each call --
+    the draws ARE the injected normals: the GPU path must return the same samples from the same seed."""
+    out = {}
+    rng = np.random.default_rng(SEED + 31)
+    np.random.seed(SEED + 31)
+    dgpsi.nb_seed(SEED + 31)
+    n, d = 30, 2
+    X = rng.uniform(0, 1, size=(n, d))
+    Y = np.stack([np.sin(2 * np.pi * X[:, 0] * X[:, 1]) + (X[:, 1] - 0.5) ** 2, np.cos(3 * X[:, 0]) * X[:, 1]], 1)
+    layers = [[kernel(length=np.array([1.0]), name="sexp") for _ in range(d)],
+              [kernel(length=np.array([1.0]), name="sexp", connect=np.arange(d)) for _ in range(2)],
+              [kernel(length=np.array([1.0]), name="sexp", scale_est=True, connect=np.arange(d)) for _ in range(2)]]
+    model = dgpsi.dgp(X, Y, dgpsi.combine(*layers))
+    model.train(N=6, disable=True)
+    emu = dgpsi.emulator(model.estimate(), N=3)
+    xt = rng.uniform(0, 1, size=(17, d))
+    out["emu_xt"] = xt
+    out["emu_nimp"] = np.array(len(emu.all_layer_set))
+    for s, al in enumerate(emu.all_layer_set):
+        snapshot(al, f"emu_S{s}_", out)
+    np.random.seed(4242)
+    out["emu_last"] = np.asarray(emu.predict(xt, method="sampling", sample_size=4))
+    np.random.seed(4243)
+    full = emu.predict(xt, method="sampling", sample_size=2, full_layer=True)
+    for l, per in enumerate(full):
+        out[f"emu_full_L{l}"] = np.asarray(per)
+    # single GP
+    g = dgpsi.gp(X, Y[:, [0]], kernel(length=np.array([0.7, 0.9]), scale=1.3, nugget=1e-4, name="matern2.5"))
+    out["gp_X"], out["gp_Y"] = X, Y[:, [0]]
+    np.random.seed(4244)
+    out["gp_samples"] = g.predict(xt, method="sampling", sample_size=5)
+    # linked system GP -> DGP -> GP on the frozen imputations of e2e.npz (config-5 shape)
+    e = np.load(os.path.join(HERE, "e2e.npz"))
+    kinds = {0: "matern2.5", 1: "matern2.5", 2: "sexp"}
+    sets = []
+    for s in range(int(e["lgp_nimp"])):
+        one = []
+        for em in range(3):
+            lay, l = [], 0
+            while f"lgp_S{s}_E{em}_L{l}K0_input" in e.files:
+                q = f"lgp_S{s}_E{em}_L{l}K0_"
+                node = kernel(length=e[q + "length"].copy(), scale=e[q + "scale"][0], nugget=e[q + "nugget"][0],
+                              name=kinds[em])
+                node.input, node.output = e[q + "input"].copy(), e[q + "output"].copy()
+                node.input_dim = np.arange(node.input.shape[1])
+                if q + "global_input" in e.files:
+                    node.global_input = e[q + "global_input"].copy()
+                    node.connect = np.arange(node.global_input.shape[1])
+                node.vecch = False
+                node.compute_stats()
+                lay.append([node])
+                l += 1
+            cont = dgpsi.container.__new__(dgpsi.container)
+            if len(lay) == 1:
+                cont.type, cont.structure = "gp", lay[0][0]
+            else:
+                cont.type, cont.structure = "dgp", lay
+            cont.vecch = False
+            cont.local_input_idx = np.array([0, 1]) if em == 0 else np.array([0])
+            one.append([cont])
+        sets.append(one)
+    system = dgpsi.lgp.__new__(dgpsi.lgp)
+    system.L, system.all_layer, system.all_layer_set, system.num_model = 3, sets[0], sets, [1, 1]
+    np.random.seed(4245)
+    out["lgp_last"] = np.asarray(system.predict(e["lgp_xt"], method="sampling", sample_size=3)[0])
+    np.random.seed(4246)
+    fl = system.predict(e["lgp_xt"], method="sampling", sample_size=2, full_layer=True)
+    for l, per in enumerate(fl):
+        out[f"lgp_full_L{l}"] = np.asarray(per[0])
+    save("sampling", **out)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["dense", "jd", "vecchia", "ess", "e2e", "loo", "metric", "update", "lik"]
+    which = sys.argv[1:] or ["dense", "jd", "vecchia", "ess", "e2e", "loo", "metric", "update", "lik", "floor", "sampling"]
     for w in which:
         {"dense": gen_dense, "jd": gen_jd, "vecchia": gen_vecchia, "ess": gen_ess, "e2e": gen_e2e, "loo": gen_loo,
-         "metric": gen_metric, "update": gen_update, "lik": gen_lik}[w]()
+         "metric": gen_metric, "update": gen_update, "lik": gen_lik, "floor": gen_floor, "sampling": gen_sampling}[w]()

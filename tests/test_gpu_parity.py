@@ -10,7 +10,7 @@ Index arrays are compared bit-exactly; ESS accept/shrink decisions must be ident
 import numpy as np
 import pytest
 
-from conftest import relerr
+from conftest import floor_ok, relerr
 
 pytestmark = pytest.mark.gpu
 
@@ -78,13 +78,14 @@ def test_dense_loglik_gradient_vs_reference(golden_dense):
     for ci in range(int(g["ncases"])):
         c = _case(g, ci)
         k = _node_from_case(c)
-        well = c["nugget"][0] >= 1e-3
+        # 1e-9 relative, or -- where cond(K) makes the reference itself move by more than that -- a multiple of the
+        # reference-vs-reference floor recorded in floor.npz
         ll = k.log_likelihood_func()
-        assert abs(ll - c["loglik"][0]) <= (1e-9 if well else 1e-7) * abs(c["loglik"][0]), (ci, ll, c["loglik"])
+        assert floor_ok(f"dense_c{ci}_loglik", ll, c["loglik"]), (ci, ll, c["loglik"])
         f, gr = k.llik(k.log_t().copy())
-        assert abs(f[0] - c["nllik"][0]) <= (1e-9 if well else 1e-7) * max(1.0, abs(c["nllik"][0])), ci
-        gtol = (1e-8 if well else 2e-5) * max(1.0, np.max(np.abs(c["nllik_grad"])))
-        assert np.max(np.abs(gr - c["nllik_grad"])) <= gtol, (ci, gr, c["nllik_grad"])
+        assert floor_ok(f"dense_c{ci}_nllik", f, c["nllik"]), ci
+        assert floor_ok(f"dense_c{ci}_nllik_grad", gr, c["nllik_grad"]), (ci, gr, c["nllik_grad"])
+        well = c["nugget"][0] >= 1e-3
         assert abs(k.scale[0] - c["scale_after"][0]) <= (1e-9 if well else 1e-7) * abs(c["scale_after"][0])
 
 
@@ -462,12 +463,14 @@ def test_vecchia_kernels_vs_reference(golden_vecchia):
         nugget_est, scale_est, d_loc, d_glob, m = [int(v) for v in c["flags"]]
         X, y, o, NN = c["X"], c["y"], c["ord"], c["NNarray"]
         assert np.array_equal(V.nn((X / c["length"])[o], m), NN), ci
+        fk = f"vecchia_c{ci}_"
         ll = V.vecchia_llik(X[o], y[o], NN, c["scale"][0], c["length"], c["nugget"][0], None, c["name"])
-        assert abs(ll - c["llik"][0]) <= 1e-9 * abs(c["llik"][0]), ci
+        assert floor_ok(fk + "llik", ll, c["llik"]), ci
         Lm = V.L_matrix(X[o], NN, c["length"], c["nugget"][0], c["name"])
-        assert np.max(np.abs(Lm - c["Lmatrix"])) <= 1e-7 * np.max(np.abs(c["Lmatrix"])), ci
+        assert floor_ok(fk + "Lmatrix", Lm, c["Lmatrix"]), ci
         draw = V.fmvn_sp(X[o], NN, c["scale"][0], c["length"], c["nugget"][0], c["name"], z=c["z"])
-        assert relerr(draw, c["draw"], 1e-3 * np.max(np.abs(c["draw"]))) <= 1e-6, ci
+        # the draw divides by the entries of L: its floor entry only saw the solve, not a perturbed L
+        assert floor_ok(fk + "draw", draw, c["draw"], rel=1e-9 if nugget_est else 1e-6), ci
         k = D.kernel(length=c["length"].copy(), scale=c["scale"][0], nugget=c["nugget"][0], name=c["name"],
                      nugget_est=bool(nugget_est), scale_est=bool(scale_est),
                      connect=np.arange(d_glob) if d_glob else None)
@@ -476,22 +479,20 @@ def test_vecchia_kernels_vs_reference(golden_vecchia):
             k.global_input = X[:, d_loc:].copy()
         k.vecch, k.m, k.ord, k.NNarray, k.rev_ord = True, m, o, NN, np.argsort(o)
         f, gr = k.llik_vecch(k.log_t().copy())
-        assert abs(f[0] - c["nllik"][0]) <= 1e-9 * max(1.0, abs(c["nllik"][0])), ci
-        assert np.max(np.abs(gr - c["nllik_grad"])) <= 1e-7 * max(1.0, np.max(np.abs(c["nllik_grad"]))), (ci, gr)
+        assert floor_ok(fk + "nllik", f, c["nllik"]), ci
+        assert floor_ok(fk + "nllik_grad", gr, c["nllik_grad"]), (ci, gr)
         assert abs(k.scale[0] - c["scale_after"][0]) <= 1e-9 * abs(c["scale_after"][0])
         # predictions (neighbour search + block kernels)
         k.pred_m = c["pred_NN"].shape[1]
         zt = c["zt"] if d_glob else None
-        tol = 1e-9 if nugget_est else 1e-6
         m1, v1 = k.gp_prediction(c["xt"], zt)
-        assert relerr(m1, c["gp_m"], 1e-3) <= tol, ci
-        assert relerr(v1, c["gp_v"], 1e-9) <= 1e-5 * (1.0 if nugget_est else 100.0), ci
+        assert floor_ok(fk + "gp_m", m1, c["gp_m"]), ci
+        # the predictive variance sigma^2 (1 + eta - r'K^-1 r) cancels to ~eta at the training points' scale: its
+        # absolute error is bounded at the scale of the cancelling terms (sigma^2), as for the dense `gp`
+        assert floor_ok(fk + "gp_v", v1, c["gp_v"], rel=1e-9 * c["scale_after"][0] / max(1e-300, np.max(c["gp_v"]))), ci
         m2, v2 = k.linkgp_prediction(c["lk_m_in"], c["lk_v_in"], zt)
-        assert relerr(m2, c["lk_m"], 1e-3) <= tol, ci
-        if nugget_est:
-            assert relerr(v2, c["lk_v"], 1e-6) <= 1e-6, ci
-        else:
-            assert relerr(v2, c["lk_v"], 1.0) <= 1e-2, ci
+        assert floor_ok(fk + "lk_m", m2, c["lk_m"]), ci
+        assert floor_ok(fk + "lk_v", v2, c["lk_v"]), (ci, float(np.max(np.abs(v2 - c["lk_v"]))))
 
 
 # ------------------------------------------------------------------------------------------------ 3
@@ -569,7 +570,7 @@ def _ess_replay(golden_ess, _DeviceLayers):
         post = _load_layers(g, p + "post_", widths, name, vecch)
         for l in range(len(widths)):
             for k in range(widths[l]):
-                assert relerr(layers[l][k].output, post[l][k].output, 1e-4) <= 1e-6, (ci, l, k)
+                assert floor_ok(f"ess_c{ci}_post_L{l}K{k}", layers[l][k].output, post[l][k].output), (ci, l, k)
                 assert relerr(layers[l][k].input, post[l][k].input, 1e-4) <= 1e-6, (ci, l, k)
         # M-step from the reference's imputed state reproduces its optimiser path
         for l in range(len(widths)):
@@ -629,18 +630,17 @@ def test_end_to_end_predict_with_frozen_imputations(golden_e2e):
     emu = _frozen_emulator(g, "step", "sexp")
     mu, var = emu.predict(g["step_xt"])
     assert mu.shape == g["step_mu"].shape
-    assert np.max(np.abs(mu - g["step_mu"])) <= 2e-6
-    assert np.max(np.abs(var - g["step_var"])) <= 2e-6 * max(1.0, np.max(g["step_var"]))
+    assert floor_ok("e2e_step_mu", mu, g["step_mu"])
+    assert floor_ok("e2e_step_var", var, g["step_var"])
     emu2 = _frozen_emulator(g, "mat", "matern2.5")
     mu2, var2 = emu2.predict(g["mat_xt"])
-    assert np.max(np.abs(mu2 - g["mat_mu"])) <= 2e-6
-    assert np.max(np.abs(var2 - g["mat_var"])) <= 2e-6 * max(1.0, np.max(g["mat_var"]))
+    assert floor_ok("e2e_mat_mu", mu2, g["mat_mu"])
+    assert floor_ok("e2e_mat_var", var2, g["mat_var"])
 
 
-def test_linked_system_with_frozen_imputations(golden_e2e):
+def _frozen_linked_system(g):
     import dgp_b200 as D
 
-    g = golden_e2e
     kinds = {0: "matern2.5", 1: "matern2.5", 2: "sexp"}
     sets = []
     for s in range(int(g["lgp_nimp"])):
@@ -661,6 +661,12 @@ def test_linked_system_with_frozen_imputations(golden_e2e):
         sets.append(one)
     system = D.lgp.__new__(D.lgp)
     system.L, system.all_layer, system.all_layer_set, system.num_model = 3, sets[0], sets, [1, 1]
+    return system
+
+
+def test_linked_system_with_frozen_imputations(golden_e2e):
+    g = golden_e2e
+    system = _frozen_linked_system(g)
     mu, var = system.predict(g["lgp_xt"])
     assert np.max(np.abs(mu[0] - g["lgp_mu"])) <= 5e-6 * max(1.0, np.max(np.abs(g["lgp_mu"])))
     assert np.max(np.abs(var[0] - g["lgp_var"])) <= 5e-6 * max(1.0, np.max(g["lgp_var"]))
@@ -1246,3 +1252,221 @@ def test_property_checks_at_baseline_scale():
     k.compute_stats()
     m2, v2 = k.gp_prediction(xt, None)
     assert relerr(m2, 2 * m1, 1e-6) <= 1e-8 and np.max(np.abs(v2 - v1)) <= 1e-9 * 1.7
+
+
+# ------------------------------------------------------------------------------------------------ headline shape
+def _headline_node(rng, n=5000, scale_est=False):
+    """One GP node of BASELINE config 3's upper layers: 8 latent inputs + 8 connected global inputs, n = 5000,
+    squared exponential, one length-scale; nugget 1e-3 (the conditioning at which 1e-9 is the target)."""
+    import dgp_b200 as D
+
+    k = D.kernel(length=np.array([1.1]), name="sexp", nugget=1e-3, scale=1.3, scale_est=scale_est,
+                 connect=np.arange(8))
+    k.input = rng.uniform(0, 1, (n, 8))
+    k.global_input = rng.uniform(0, 1, (n, 8))
+    k.input_dim = np.arange(8)
+    X = np.concatenate((k.input, k.global_input), 1)
+    k.output = (np.sin(X.sum(1)) + X[:, 0] * X[:, 9] + 0.05 * rng.standard_normal(n)).reshape(-1, 1)
+    k.D = 16
+    k.para_path = np.atleast_2d(np.concatenate((k.scale, k.length, k.nugget)))
+    return k, X
+
+
+def test_headline_shape_likelihood_gradient_statistics():
+    """n = 5000, D = 16 with the PRODUCTION tunables (K = 512 hyper-blocks, graded ramp, critical-path stream): plain
+    layout (ESS log-likelihood) and augmented layout (M-step objective + gradient, K^-1) against LAPACK (the oracle)
+    to BASELINE.json's 1e-9."""
+    from oracle import dgp_oracle as O
+
+    rng = np.random.default_rng(5000)
+    k, X = _headline_node(rng, scale_est=True)
+    ll = k.log_likelihood_func()
+    ll0 = O.loglik_dense(X, k.output, k.length, 1.3, 1e-3, "sexp")
+    assert abs(ll - ll0) <= 1e-9 * abs(ll0), (ll, ll0)
+    k.prior_name = None
+    f, gr = k.llik(k.log_t().copy())
+    f0, g0, s0 = O.nllik_grad_dense(X, k.output, k.length, 1.3, 1e-3, "sexp", True, False)
+    assert abs(f[0] - f0) <= 1e-9 * abs(f0), (f, f0)
+    assert np.max(np.abs(gr - g0)) <= 1e-9 * max(1.0, np.max(np.abs(g0))), (gr, g0)
+    assert abs(k.scale[0] - s0) <= 1e-9 * s0
+    k.compute_stats()
+    Kd = torch.from_numpy(O.k_matrix(X, k.length, 1e-3, "sexp")).cuda()
+    resid = (Kd @ k._Rinv - torch.eye(len(X), dtype=torch.float64, device="cuda")).abs().max().item()
+    assert resid <= 1e-9, resid
+    from scipy.linalg import cho_factor, cho_solve
+    a0 = cho_solve(cho_factor(Kd.cpu().numpy(), lower=True), k.output[:, 0])
+    assert relerr(k.Rinv_y, a0, 1e-3 * np.max(np.abs(a0))) <= 1e-9
+
+
+def test_headline_shape_ess_wave_of_eight():
+    """One blocked ESS update of the config-3 layer pair (8 latent nodes feeding 8 upper nodes, n = 5000: a wave is 8
+    matrices of one candidate angle) checked against LAPACK: the threshold, the likelihood sums at the accepted and at
+    the last rejected angle decide exactly as the device did, and the accepted latent columns are
+    f cos(theta) + chol(K) z sin(theta) to 1e-9."""
+    import dgp_b200 as D
+    from dgp_b200.imputation import _DeviceLayers
+    from oracle import dgp_oracle as O
+
+    rng = np.random.default_rng(5001)
+    n, d, w = 5000, 8, 8
+    Xg = rng.uniform(0, 1, (n, d))
+    F = np.stack([np.sin(3 * Xg[:, j] + 0.3 * j) + 0.3 * Xg[:, (j + 1) % d] for j in range(w)], 1)
+    Yup = np.stack([np.sin(F.sum(1) + j) + 0.1 * Xg[:, j] for j in range(w)], 1)
+
+    def build(make):
+        l1 = [make(length=np.array([0.9]), name="sexp", nugget=1e-3) for _ in range(w)]
+        l2 = [make(length=np.array([1.2 + 0.05 * j]), name="sexp", nugget=1e-3, connect=np.arange(d)) for j in range(w)]
+        for j, nd in enumerate(l1):
+            nd.input, nd.input_dim, nd.output = Xg.copy(), np.arange(d), F[:, [j]].copy()
+        for j, nd in enumerate(l2):
+            nd.input, nd.input_dim, nd.global_input, nd.output = F.copy(), np.arange(w), Xg.copy(), Yup[:, [j]].copy()
+        return [l1, l2]
+
+    layers = build(lambda **kw: D.kernel(**kw))
+    for layer in layers:
+        for nd in layer:
+            nd.D = nd.input.shape[1] + (0 if nd.global_input is None else nd.global_input.shape[1])
+            nd.vecch = False
+    z, u = rng.standard_normal((w, n)), rng.uniform(size=64)
+    dev = _DeviceLayers(layers)
+    nprop, thetas = dev.ess_call(0, list(range(w)), list(range(w)), z, u)
+    dev.write_back()
+    got = np.concatenate([nd.output for nd in layers[0]], 1)
+    # ---- LAPACK side
+    ref = build(lambda **kw: O.Node(**kw))
+    Lc = np.linalg.cholesky(O.k_matrix(Xg, np.array([0.9]), 1e-3, "sexp"))   # the 8 targets share inputs and theta
+    nu = Lc @ z.T
+
+    def upper_sum(fp):
+        s = 0.0
+        for nd in ref[1]:
+            nd.input = fp
+            s += nd.loglik()
+        return s
+
+    log_y = upper_sum(F) + np.log(u[0])
+    # replay the bracket rule with the device's angles: uniforms consumed = 1 + proposals, angles as the rule draws them
+    th, lo, hi = 2 * np.pi * u[1], 2 * np.pi * u[1] - 2 * np.pi, 2 * np.pi * u[1]
+    for i in range(nprop):
+        assert abs(thetas[i] - th) <= 1e-12 * max(1.0, abs(th)), i
+        if th < 0:
+            lo = th
+        else:
+            hi = th
+        th = lo + (hi - lo) * u[2 + i]
+    acc = F * np.cos(thetas[-1]) + nu * np.sin(thetas[-1])
+    assert upper_sum(acc) > log_y                      # the accepted angle is accepted by LAPACK too
+    if nprop > 1:                                      # and the one before it rejected
+        rej = F * np.cos(thetas[-2]) + nu * np.sin(thetas[-2])
+        assert not (upper_sum(rej) > log_y)
+    assert relerr(got, acc, 1e-3) <= 1e-9
+
+
+def test_headline_shape_linked_prediction():
+    """link_gp (squared exponential, DMMA exponent kernel) for 64 Gaussian test inputs at n = 5000, Dw = 8 latent +
+    Dz = 8 global dimensions against the oracle's closed form."""
+    from oracle import dgp_oracle as O
+
+    rng = np.random.default_rng(5002)
+    k, X = _headline_node(rng)
+    k.compute_stats()
+    M = 64
+    mt, vt, zt = rng.uniform(0, 1, (M, 8)), rng.uniform(1e-4, 0.05, (M, 8)), rng.uniform(0, 1, (M, 8))
+    m2, v2 = k.linkgp_prediction(mt, vt, zt)
+    Rinv, Rinv_y = O.compute_stats(X, k.output, k.length, 1e-3, "sexp")
+    R2, P = O.sexp_stats(k.input, k.length)
+    m0, v0 = O.link_gp(mt, vt, zt, k.input, k.global_input, Rinv, Rinv_y, R2, P, 1.3, k.length, 1e-3, "sexp")
+    assert relerr(m2, m0, 1e-3) <= 1e-9
+    assert np.max(np.abs(v2 - v0)) <= 1e-9 * 1.3
+
+
+# ------------------------------------------------------------------------------------------------ sampling
+def test_sampling_reproduces_the_reference_draws():
+    """method='sampling'  with numpy's global generator seeded as the fixture script seeded it: the
+    samples are the reference's, draw for draw (same order of normal variates, moments from the GPU)."""
+    import dgp_b200 as D
+    from conftest import load_golden
+
+    g = load_golden("sampling")
+    emu = _frozen_emulator(g, "emu", "sexp")
+    np.random.seed(4242)
+    last = np.asarray(emu.predict(g["emu_xt"], method="sampling", sample_size=4))
+    assert last.shape == g["emu_last"].shape
+    assert np.max(np.abs(last - g["emu_last"])) <= 1e-6 * max(1.0, np.max(np.abs(g["emu_last"])))
+    np.random.seed(4243)
+    full = emu.predict(g["emu_xt"], method="sampling", sample_size=2, full_layer=True)
+    for l, per in enumerate(full):
+        ref = g[f"emu_full_L{l}"]
+        assert np.asarray(per).shape == ref.shape, l
+        assert np.max(np.abs(np.asarray(per) - ref)) <= 1e-6 * max(1.0, np.max(np.abs(ref))), l
+    gp1 = D.gp(g["gp_X"], g["gp_Y"], D.kernel(length=np.array([0.7, 0.9]), scale=1.3, nugget=1e-4, name="matern2.5"))
+    np.random.seed(4244)
+    s = gp1.predict(g["emu_xt"], method="sampling", sample_size=5)
+    assert s.shape == g["gp_samples"].shape and np.max(np.abs(s - g["gp_samples"])) <= 1e-7
+    # linked system on the frozen imputations of e2e.npz
+    system = _frozen_linked_system(load_golden("e2e"))
+    np.random.seed(4245)
+    ls = np.asarray(system.predict(load_golden("e2e")["lgp_xt"], method="sampling", sample_size=3)[0])
+    assert ls.shape == g["lgp_last"].shape
+    assert np.max(np.abs(ls - g["lgp_last"])) <= 5e-6 * max(1.0, np.max(np.abs(g["lgp_last"])))
+    np.random.seed(4246)
+    fl = system.predict(load_golden("e2e")["lgp_xt"], method="sampling", sample_size=2, full_layer=True)
+    for l, per in enumerate(fl):
+        ref = g[f"lgp_full_L{l}"]
+        assert np.asarray(per[0]).shape == ref.shape, l
+        assert np.max(np.abs(np.asarray(per[0]) - ref)) <= 5e-6 * max(1.0, np.max(np.abs(ref))), l
+
+
+# ------------------------------------------------------------------------------------------------ advisor findings
+def test_m_step_with_more_nodes_than_one_batched_launch():
+    """A DGP may have any number of dense GP nodes: 16 + 16 + 2 = 34 nodes exceed the library's 32 matrices per batched
+    launch, so the M-step's rendezvous has to serve them in chunks (the reference has no such limit)."""
+    import dgp_b200 as D
+
+    rng = np.random.default_rng(34)
+    np.random.seed(34)
+    D.nb_seed(34)
+    n, d = 48, 16
+    X = rng.uniform(0, 1, (n, d))
+    Y = np.stack([np.sin(X.sum(1)), np.cos(X[:, 0] * 3)], 1)
+    l1 = [D.kernel(length=np.array([1.0]), name="sexp") for _ in range(16)]
+    l2 = [D.kernel(length=np.array([1.0]), name="sexp", connect=np.arange(2)) for _ in range(16)]
+    l3 = [D.kernel(length=np.array([1.0]), name="sexp", scale_est=True, connect=np.arange(2)) for _ in range(2)]
+    model = D.dgp(X, Y, [l1, l2, l3])
+    model.train(2, disable=True)
+    for layer in model.all_layer:
+        for node in layer:
+            assert node.para_path.shape[0] == 3 and np.all(np.isfinite(node.para_path))
+
+
+def test_vecchia_mode_switches_skip_likelihood_nodes():
+    """emulator.to_vecchia / remove_vecchia / loo and container.to_vecchia / remove_vecchia (lgp.set_vecchia) on
+    structures that hold likelihood nodes (emulation.py:62-107, linkgp.py:64-90 guard with kernel.type == 'gp')."""
+    import dgp_b200 as D
+
+    rng = np.random.default_rng(7)
+    np.random.seed(7)
+    D.nb_seed(7)
+    n = 60
+    X = rng.uniform(0, 1, (n, 2))
+    Y = rng.poisson(np.exp(1.0 + np.sin(3 * X[:, 0]) + X[:, 1])).astype(float).reshape(-1, 1)
+    l1 = [D.kernel(length=np.array([0.5]), name="sexp") for _ in range(2)]
+    l2 = [D.kernel(length=np.array([0.5]), name="sexp", scale_est=True, connect=np.arange(2))]
+    model = D.dgp(X, Y, D.combine(l1, l2, [D.Poisson()]))
+    model.train(2, disable=True)
+    emu = D.emulator(model.estimate(), N=2)
+    xt = rng.uniform(0, 1, (9, 2))
+    mu0, var0 = emu.predict(xt)
+    emu.to_vecchia()
+    assert emu.vecch and all(k.vecch for one in emu.all_layer_set for layer in one for k in layer if k.type == 'gp')
+    mu1, _ = emu.predict(xt, m=n - 1)      # conditioning on every point: the Vecchia form equals the dense one
+    assert np.max(np.abs(mu1 - mu0)) <= 1e-5 * max(1.0, np.max(np.abs(mu0)))
+    emu.remove_vecchia()
+    mu2, var2 = emu.predict(xt)
+    assert np.max(np.abs(mu2 - mu0)) <= 1e-9 * max(1.0, np.max(np.abs(mu0)))
+    assert np.max(np.abs(var2 - var0)) <= 1e-9 * max(1.0, np.max(np.abs(var0)))
+    cont = D.container(model.estimate(), np.array([0, 1]))
+    cont.to_vecchia()
+    assert cont.vecch
+    cont.remove_vecchia()
+    assert not cont.vecch and all(not k.vecch for layer in cont.structure for k in layer if k.type == 'gp')
