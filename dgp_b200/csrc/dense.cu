@@ -657,6 +657,7 @@ struct UpdateProfiler {
     int used = 0;                  // events in flight
     double ms = 0.0, launches = 0.0, flops = 0.0;
     double total_flops = 0.0;      // n^3/3 (n^3 augmented) per matrix of every factorisation while profiling
+    double wasted_flops = 0.0;     // ... of which: speculative ESS candidates behind the accepted one
     cudaStream_t last = nullptr;
     int drain() {
         if (used == 0) return DGPB_OK;
@@ -673,6 +674,15 @@ struct UpdateProfiler {
 };
 static UpdateProfiler g_prof;
 static std::mutex g_prof_mutex;  // the M-step issues factorisations from several host threads
+
+// ESS waves evaluate candidate angles ahead of the decision; `matrices` of them (n x n, plain layout) turned out to
+// lie behind the accepted one.  They were issued (total_flops) but the reference's schedule never needed them.
+void profile_wasted(int matrices, int64_t n) {
+    if (!g_prof.on || matrices <= 0) return;
+    std::lock_guard<std::mutex> lock(g_prof_mutex);
+    const double nn = (double)n;
+    g_prof.wasted_flops += (double)matrices * nn * nn * nn / 3.0;
+}
 
 // Two-stream look-ahead: the caller's stream carries the critical path (panel k, then the NARROW update of
 // the next panel's 64 columns), a side stream carries the BULK update of everything to the right.  Panel k+1
@@ -1215,7 +1225,7 @@ int dgpb_profile(int on) {
     }
     if (on) {
         g_prof.used = 0;
-        g_prof.ms = g_prof.launches = g_prof.flops = g_prof.total_flops = 0.0;
+        g_prof.ms = g_prof.launches = g_prof.flops = g_prof.total_flops = g_prof.wasted_flops = 0.0;
     } else {
         DGPB_TRY(g_prof.drain());
     }
@@ -1231,6 +1241,7 @@ int dgpb_profile_read(double* out_host) {
     out_host[1] = g_prof.launches;
     out_host[2] = g_prof.flops;
     out_host[3] = g_prof.total_flops;
+    out_host[4] = g_prof.wasted_flops;
     return DGPB_OK;
 }
 

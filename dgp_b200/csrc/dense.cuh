@@ -71,6 +71,9 @@ int factor_reduce(const Geom& g, const Batch& bt, int B, const ScaleArgs& sa, do
 int loglik_batch_device(Workspace* ws, const KernelDev* kds, const double* const* ys, const ScaleArgs& sa, int B,
                         int64_t n, Batch* bt_out, Geom* g_out, double** out_dev, cudaStream_t st);
 
+// bench.py accounting: matrices of speculative ESS candidates that lay behind the accepted one
+void profile_wasted(int matrices, int64_t n);
+
 // matrices per speculative ESS wave (ess.cu)
 extern int g_ess_target_b;
 extern int g_ess_cached_threshold;

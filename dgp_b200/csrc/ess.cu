@@ -764,6 +764,11 @@ extern "C" int dgpb_ess_block_cached(dgpb_ws* ws, const dgpb_node* targets, int 
         }
         if (accepted >= 0) {
             const int ia = first + accepted;             // item index of the accepted candidate
+            if (batched) {   // this rank's candidates behind the accepted one were issued for nothing
+                int behind = 0;
+                for (int i = me; i < first + S; i += W) behind += i > ia;
+                profile_wasted(behind * n_uppers, n);
+            }
             const int owner = ia % W, slot = ia / W;     // the rank that evaluated it, its local slot there
             const double* pa = pcur + (size_t)slot * layer_elems;
             if (owner != me) {   // evaluated elsewhere: the same elementwise proposal, recomputed here

@@ -44,6 +44,19 @@ _MSTEP_POOL = None      # persistent optimiser threads of the batched M-step
 _MSTEP_POOL_SIZE = 0
 
 
+def _single_threaded_blas():
+    """The host side of an M-step is many SMALL LAPACK calls (`kernel.r2`: two ranks and a least-squares fit of
+    n x 9 matrices per node, from one optimiser thread per node).  A multi-threaded BLAS spends 30-100 ms per call
+    spinning up its pool for 1-2 ms of arithmetic (measured: lstsq 112 ms with 8 threads, 2.4 ms with one), so the
+    pool is limited to one thread for the duration."""
+    try:
+        from threadpoolctl import threadpool_limits
+        return threadpool_limits(limits=1)
+    except Exception:  # pragma: no cover
+        import contextlib
+        return contextlib.nullcontext()
+
+
 class _GradBatcher:
     """Rendezvous of the M-step's optimiser threads: a request blocks until every thread that is still optimising
     has one pending, then the last arrival runs the whole batch through `dgpb_nllik_grad_dense_batch` (on the
@@ -551,6 +564,12 @@ class dgp:
 
         nodes = [(l, kernel) for l in range(self.n_layer) for kernel in self.all_layer[l] if kernel.type == 'gp']
         ch = parallel.chain()
+        with _single_threaded_blas():
+            self._m_step_sharded(nodes, ch)
+
+    def _m_step_sharded(self, nodes, ch):
+        from . import parallel
+
         if ch is None:
             self._m_step_nodes(nodes)
             return

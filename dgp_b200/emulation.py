@@ -46,11 +46,29 @@ class emulator:
                 (self.imp).key_stats()
             (self.all_layer_set).append(copy.deepcopy(self.all_layer))
 
+    def __getstate__(self):
+        state = dict(self.__dict__)
+        state.pop('_pool', None)   # device copies are rebuilt lazily
+        return state
+
     def __setstate__(self, state):
         state.pop('all_layer_set_copy', None)
         state.pop('nb_parallel', None)
         state.setdefault('vecch', False)
         self.__dict__.update(state)
+
+    def _frozen_pool(self):
+        """The imputations of an emulator never change after construction: their training inputs and outputs are
+        uploaded once (shared between nodes / imputations that hold identical arrays) and kept for every later
+        predict / loo / metric call."""
+        if getattr(self, '_pool', None) is None:
+            self._pool = L.UploadPool()
+        for one in self.all_layer_set:
+            for layer in one:
+                for kernel in layer:
+                    if kernel.type == 'gp':
+                        kernel._frozen = True
+        return self._pool
 
     def to_vecchia(self):
         """emulation.py:62-74."""
@@ -135,7 +153,7 @@ class emulator:
     def _layer_moments(self, x, m):
         """Per imputation, the (mean, var) device tensors of every layer at the inputs x."""
         xd = L.to_dev(x, np.float64)
-        with L.predict_cache():
+        with L.predict_cache(self._frozen_pool()):
             return [self._predict_one_imputation(layers, xd, m, True)[2] for layers in self.all_layer_set]
 
     @staticmethod
@@ -268,15 +286,16 @@ class emulator:
             if len(idx) < 2:
                 continue
             first = layer[idx[0]]
-            X0 = first._X()
+            X0 = first._X_pred()
             if min(int(m), X0.shape[0]) - (1 if first.loo_state else 0) + 1 > 32:
                 continue
-            if any(layer[k]._X().shape != X0.shape or not np.array_equal(layer[k]._X(), X0) for k in idx[1:]):
+            W = L.to_dev_shared(X0)
+            # identical inputs share one device tensor in the upload pool: an identity test after the first call
+            if any(L.to_dev_shared(layer[k]._X_pred()) is not W for k in idx[1:]):
                 continue
             first.pred_m = m
             z = L.cols(xd, first.connect) if first.connect is not None else None
             xq = L.cat_cols(L.cols(xd, first.input_dim), z)
-            W = L.to_dev_shared(X0)
             NN = first._nn_query(xq, W)
             B, M = len(idx), xq.shape[0]
             Y = L.to_dev(np.ascontiguousarray(np.stack([layer[k].output[:, 0] for k in idx], 0)))
@@ -292,7 +311,7 @@ class emulator:
                 done[k] = (mean[b], var[b])
         return done
 
-    def predict(self, x, method='mean_var', full_layer=False, sample_size=50, m=50, aggregation=True):
+    def predict(self, x, method='mean_var', full_layer=False, sample_size=50, m=50, aggregation=True, _device=False):
         """Predictions from the trained DGP (emulation.py:631-854).  `x`: (M x d) numpy array.
         method='mean_var' returns (mu, sigma2) exactly as the reference; method='sampling' draws
         `sample_size` normal samples per imputation from the final-layer moments."""
@@ -306,7 +325,7 @@ class emulator:
         lik_out = self.all_layer[-1][0].type == 'likelihood'
         if method == 'sampling' and lik_out:
             return self._sample_likelihood(xd, full_layer, sample_size, m)
-        with L.predict_cache():
+        with L.predict_cache(self._frozen_pool()):
             for s in range(S):
                 mean, var, per_layer = self._predict_one_imputation(self.all_layer_set[s], xd, m, full_layer)
                 means.append(mean)
@@ -352,6 +371,13 @@ class emulator:
                 mu.append(a)
                 sigma2.append(b)
             return mu, sigma2
+        if aggregation and _device and cat is None:
+            # moments stay on the device (dgp_b200.parallel gathers them over NCCL without a host bounce)
+            ms, vs = torch.stack(means, 0).contiguous(), torch.stack(variances, 0).contiguous()
+            mu, s2 = torch.empty_like(ms[0]), torch.empty_like(ms[0])
+            L.check(lib.dgpb_aggregate(L.ptr(ms), L.ptr(vs), ms.shape[0], ms[0].numel(), L.ptr(mu), L.ptr(s2),
+                                       L.stream()))
+            return mu, s2
         if aggregation:
             mu, sigma2 = agg(means, variances)
             return cat.prediction(mu, sigma2) if cat is not None else (mu, sigma2)
@@ -363,7 +389,7 @@ class emulator:
     def _sample_likelihood(self, xd, full_layer, sample_size, m):
         """method='sampling' of an emulator whose final layer holds likelihood nodes (emulation.py:765-810): draws
         of the latent layers from their Gaussian moments, pushed through each likelihood's sampler."""
-        with L.predict_cache():
+        with L.predict_cache(self._frozen_pool()):
             moments = [self._predict_one_imputation(layers, xd, m, True)[2] for layers in self.all_layer_set]
         host = [[(L.to_host(mu), L.to_host(va)) for mu, va in per_layer] for per_layer in moments]
         last = self.all_layer[-1]

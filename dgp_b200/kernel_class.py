@@ -98,9 +98,8 @@ class kernel:
         state = dict(self.__dict__)
         state['Rinv'] = _as_numpy(state.pop('_Rinv'))
         state['Rinv_y'] = _as_numpy(state.pop('_Rinv_y'))
-        state.pop('_dcache', None)
-        state.pop('_batcher', None)
-        state.pop('_vcache', None)
+        for key in ('_dcache', '_batcher', '_vcache', '_frozen', '_Xcat', '_ycol'):
+            state.pop(key, None)
         return state
 
     def __setstate__(self, state):
@@ -115,6 +114,22 @@ class kernel:
         if self.global_input is not None:
             return np.concatenate((self.input, self.global_input), 1)
         return self.input
+
+    def _X_pred(self):
+        """`_X()` for predictions; a node marked `_frozen` (an emulator's imputation: its data no longer changes)
+        keeps the concatenated array, so the emulator's upload pool recognises it by identity on every call."""
+        if not getattr(self, '_frozen', False):
+            return self._X()
+        if getattr(self, '_Xcat', None) is None:
+            self._Xcat = np.ascontiguousarray(self._X())
+        return self._Xcat
+
+    def _y_pred(self):
+        if not getattr(self, '_frozen', False):
+            return np.ascontiguousarray(self.output[:, 0])
+        if getattr(self, '_ycol', None) is None:
+            self._ycol = np.ascontiguousarray(self.output[:, 0])
+        return self._ycol
 
     def _check_supported(self):
         if self.rep is not None:
@@ -437,13 +452,13 @@ class kernel:
         """Device tensors in / out; see `gp_prediction`."""
         lib = L.load()
         xq = L.cat_cols(x, z)
-        W = L.to_dev_shared(self._X())
+        W = L.to_dev_shared(self._X_pred())
         M, D = xq.shape
         mean, var = L.empty((M,)), L.empty((M,))
         larr, lptr = L.length_host(self.length)
         if self.vecch:
             NN = self._nn_query(xq, W)
-            y = L.to_dev(np.ascontiguousarray(self.output[:, 0]))
+            y = L.to_dev_shared(self._y_pred())
             L.check(lib.dgpb_gp_vecch(L.ptr(xq), M, L.ptr(W), L.ptr(y), W.shape[0], D, L.ptr(NN), NN.shape[1], lptr,
                                       len(larr), float(self.scale[0]), float(self.nugget[0]), None, L.KIND[self.name],
                                       L.ptr(mean), L.ptr(var), L.stream()))
@@ -468,7 +483,7 @@ class kernel:
             xq = L.cat_cols(m, z)
             w = L.cat_cols(w1, gw)
             NN = self._nn_query(xq, w)
-            y = L.to_dev(np.ascontiguousarray(self.output[:, 0]))
+            y = L.to_dev_shared(self._y_pred())
             L.check(lib.dgpb_linkgp_vecch(L.ptr(m), L.ptr(v), L.ptr(z), M, L.ptr(w1), L.ptr(gw), L.ptr(y), w1.shape[0],
                                           Dw, Dz, L.ptr(NN), NN.shape[1], lptr, len(larr), float(self.scale[0]),
                                           float(self.nugget[0]), None, L.KIND[self.name], L.ptr(mean), L.ptr(var),

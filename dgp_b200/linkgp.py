@@ -195,8 +195,25 @@ class lgp:
 
     def predict(self, x, method='mean_var', full_layer=False, sample_size=50, m=50):
         """Predictions from the linked (D)GP model (linkgp.py:285-501)."""
-        with L.predict_cache():
+        with L.predict_cache(self._frozen_pool()):
             return self._predict(x, method, full_layer, sample_size, m)
+
+    def _frozen_pool(self):
+        """The emulators of a linked system never change after construction: their data is uploaded once and kept
+        for every later call (arrays with identical contents share one device tensor)."""
+        if getattr(self, '_pool', None) is None:
+            self._pool = L.UploadPool()
+        for one in self.all_layer_set:
+            for layer in one:
+                for cont in layer:
+                    for k in cont._kernels():
+                        k._frozen = True
+        return self._pool
+
+    def __getstate__(self):
+        state = dict(self.__dict__)
+        state.pop('_pool', None)
+        return state
 
     def _predict(self, x, method, full_layer, sample_size, m):
         torch = L.torch_mod()

@@ -134,8 +134,10 @@ def shard_bounds(M, rank, world):
 
 def predict_sharded(emu, x, dist=None, **kwargs):
     """`emu.predict(x, method='mean_var')` with the rows of `x` sharded over the ranks of the default process
-    group; every rank returns the full (mu, sigma2).  `dist` is the initialised torch.distributed module or
-    None (single process).  Works with the `gloo` backend on CPU tensors (tests) and `nccl` on CUDA tensors."""
+    group; every rank returns the full (mu, sigma2).  `emu` is an `emulator` or an `lgp` (whose predict returns one
+    array per emulator of the last layer); `dist` is the initialised torch.distributed module or None (single
+    process).  With the "nccl" backend the shard's moments stay on the device from the prediction kernels to ONE
+    all-gather and come to the host once; with "gloo" (CPU tests) the same logic runs on host tensors."""
     if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
         return emu.predict(x, **kwargs)
     import torch
@@ -143,20 +145,31 @@ def predict_sharded(emu, x, dist=None, **kwargs):
     rank, world = dist.get_rank(), dist.get_world_size()
     M = x.shape[0]
     lo, hi = shard_bounds(M, rank, world)
-    mu, var = emu.predict(x[lo:hi], **kwargs)
-    D = mu.shape[1]
     use_cuda = dist.get_backend() == "nccl"
     dev = torch.device("cuda", torch.cuda.current_device()) if use_cuda else torch.device("cpu")
+    try:
+        mu, var = emu.predict(x[lo:hi], _device=True, **kwargs) if use_cuda else emu.predict(x[lo:hi], **kwargs)
+    except TypeError:   # a predictor without the device-resident return (lgp, stand-ins of the tests)
+        mu, var = emu.predict(x[lo:hi], **kwargs)
+    as_list = isinstance(mu, (list, tuple))
+    mus, vars_ = (list(mu), list(var)) if as_list else ([mu], [var])
+
+    def tens(a):
+        return a.to(dev) if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+    parts = [tens(a).reshape(hi - lo, -1) for a in mus + vars_]
+    widths = [p.shape[1] for p in parts]
     maxrows = shard_bounds(M, 0, world)[1]  # the first shard is the largest
-    buf = torch.zeros((maxrows, 2 * D), dtype=torch.float64, device=dev)
-    buf[: hi - lo, :D] = torch.from_numpy(np.ascontiguousarray(mu)).to(dev)
-    buf[: hi - lo, D:] = torch.from_numpy(np.ascontiguousarray(var)).to(dev)
-    parts = [torch.empty_like(buf) for _ in range(world)]
-    dist.all_gather(parts, buf)
-    mus, vars_ = [], []
-    for r, p in enumerate(parts):
-        a, b = shard_bounds(M, r, world)
-        p = p[: b - a].cpu().numpy()
-        mus.append(p[:, :D])
-        vars_.append(p[:, D:])
-    return np.concatenate(mus, 0), np.concatenate(vars_, 0)
+    buf = torch.zeros((maxrows, sum(widths)), dtype=torch.float64, device=dev)
+    if hi > lo:
+        buf[: hi - lo] = torch.cat(parts, 1)
+    out = torch.empty((world * maxrows, sum(widths)), dtype=torch.float64, device=dev)
+    dist.all_gather_into_tensor(out, buf)
+    out = out.cpu().numpy().reshape(world, maxrows, sum(widths))
+    full = np.concatenate([out[r, : shard_bounds(M, r, world)[1] - shard_bounds(M, r, world)[0]] for r in range(world)], 0)
+    cols = np.cumsum([0] + widths)
+    pieces = [np.ascontiguousarray(full[:, cols[i]:cols[i + 1]]) for i in range(len(widths))]
+    k = len(mus)
+    if as_list:
+        return pieces[:k], pieces[k:]
+    return pieces[0], pieces[1]

@@ -299,8 +299,9 @@ int dgpb_dgemm_nt(const double* A, const double* B, double* C, int64_t M, int64_
 int dgpb_potrf(dgpb_ws* ws, double* A, int64_t n, int* info_host, void* stream);
 /* Launch profiler for the roofline line of bench.py: while on, every trailing-update (SYRK) launch of the
  * blocked factorisation is bracketed by CUDA events on its stream.  dgpb_profile_read fills
- * out_host[0..3] = {total ms, launches timed, algorithmic FLOPs of those launches, FLOPs of every factorisation
- * issued while profiling (n^3/3 per matrix, n^3 for the augmented layout)}. */
+ * out_host[0..4] = {total ms, launches timed, algorithmic FLOPs of those launches, FLOPs of every factorisation
+ * issued while profiling (n^3/3 per matrix, n^3 for the augmented layout), the part of those FLOPs spent on
+ * speculative ESS candidates that lay behind the accepted one (issued, but not needed by the reference's schedule)}. */
 int dgpb_profile(int on);
 /* micro-probe of the trailing-update kernel (development aid): out_host = {ms per launch, TFLOP/s} */
 int dgpb_probe_update(dgpb_ws* ws, int64_t n, int B, int flags, int reps, double* out_host);

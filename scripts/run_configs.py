@@ -13,7 +13,19 @@ rng = np.random.default_rng(seed); np.random.seed(seed); D.nb_seed(seed)
 
 def tic(): torch.cuda.synchronize(); return time.perf_counter()
 
-if cfg == 2:
+if cfg == 1:
+    X = np.linspace(0, 1, 10)[:, None]
+    Y = np.array([[-1.0] if i < 0.5 else [1.0] for i in X[:, 0]])
+    layers = [[D.kernel(length=np.array([1.0]), name='sexp')], [D.kernel(length=np.array([1.0]), name='sexp')],
+              [D.kernel(length=np.array([1.0]), name='sexp', scale_est=True)]]
+    t = tic(); m = D.dgp(X, Y, D.combine(*layers)); print('construct %.2fs' % (tic()-t))
+    iters = max(10, int(500*scale)); t = tic(); m.train(iters, disable=True); dt = tic()-t
+    print('train %d iters: %.2f s = %.2f it/s (%d proposals, %d launches)' % (iters, dt, iters/dt, m.imp.n_proposals, D._lib.load().dgpb_launch_count()))
+    t = tic(); emu = D.emulator(m.estimate(), N=10); print('emulator(N=10) %.2fs' % (tic()-t))
+    xt = np.linspace(0, 1, 300)[:, None]
+    t = tic(); mu, var = emu.predict(xt); dt = tic()-t
+    print('predict 300 pts: %.4fs' % dt)
+elif cfg == 2:
     n, d = 2000, 5
     X = rng.uniform(0, 1, (n, d))
     Y = (np.sin(2*np.pi*X[:,0]*X[:,1]) + (X[:,2]-0.5)**2 + X[:,3]*np.exp(-X[:,4])).reshape(-1, 1)
