@@ -87,6 +87,11 @@ int dgpb_ws_destroy(dgpb_ws* ws) {
         if (ws->buf[i]) cudaFree(ws->buf[i]);
     for (auto& kv : ws->cache)
         if (kv.second.T) cudaFree(kv.second.T);
+    for (int c = 0; c < 2; ++c) {
+        if (ws->wave_stream[c]) cudaStreamDestroy(ws->wave_stream[c]);
+        if (ws->wave_assembled[c]) cudaEventDestroy(ws->wave_assembled[c]);
+        if (ws->wave_done[c]) cudaEventDestroy(ws->wave_done[c]);
+    }
     if (ws->pinned) cudaFreeHost(ws->pinned);
     delete ws;
     return DGPB_OK;

@@ -85,10 +85,13 @@ inline int64_t cdiv(int64_t x, int64_t m) { return (x + m - 1) / m; }
 // ---------------------------------------------------------------------------------------------
 enum Slot : int {
     SLOT_T = 0,       // factorisation matrices (batched)
-    SLOT_T2,          // second set: the next ESS wave is assembled while the current one is factored
+    SLOT_T2,          // second set: the next ESS wave is assembled (and factored) while the current one is factored
     SLOT_DIAG,        // diag(L) per batch entry
+    SLOT_DIAG2,       //   ... of the second set
     SLOT_OUT,         // small result scalars
+    SLOT_OUT2,        //   ... of the second set
     SLOT_INFO,        // int info flags
+    SLOT_INFO2,       //   ... of the second set
     SLOT_PART,        // reduction partials
     SLOT_NU,          // ESS prior draws
     SLOT_PROP,        // ESS proposal layer
@@ -125,7 +128,8 @@ constexpr int kPinnedDoubles = 8192;
 constexpr int kPinnedVecchia = 1024;  // Vecchia per-node results, cached-threshold quads
 constexpr int kPinnedInfo = 2048;     // int info flags of a batch
 constexpr int kPinnedFlag = 3072;     // status word of comm_max_flag
-constexpr int kPinnedWave = 4096;     // gathered wave results (kMaxRanks x kCommBlock)
+constexpr int kPinnedWave = 4096;     // gathered wave results (kMaxRanks x kCommBlock), one region per wave context
+constexpr int kPinnedWaveStride = 1024;
 
 struct Comm {
     void* nccl = nullptr;   // ncclComm_t
@@ -155,6 +159,11 @@ struct Workspace {
     std::map<int, CachedFactor> cache;
     Comm comm;
     std::map<int, FactorOwner> owner;   // world > 1 only
+    // ESS wave pipeline (ess.cu): two factorisation contexts (T set, side buffers, streams) so that the next wave can
+    // be assembled and factored while the current one drains its tail
+    cudaStream_t wave_stream[2] = {nullptr, nullptr};
+    cudaEvent_t wave_assembled[2] = {nullptr, nullptr}, wave_done[2] = {nullptr, nullptr};
+    int wave_cur = 0;                   // the context a new block update starts with (the other may still be busy)
     void* buf[SLOT_COUNT] = {};
     size_t cap[SLOT_COUNT] = {};
     double* pinned = nullptr;  // small pinned host staging buffer (kPinnedDoubles)

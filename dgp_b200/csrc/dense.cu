@@ -592,9 +592,9 @@ int setup_batch_slot(Workspace* ws, int tslot, const Geom& g, int B, Batch* bt, 
     DGPB_REQUIRE(B >= 1 && B <= MAXB, "batch size out of range");
     void *pT, *pD, *pO, *pI;
     DGPB_TRY(ws->reserve(tslot ? SLOT_T2 : SLOT_T, g.elems() * sizeof(double) * B, &pT));
-    DGPB_TRY(ws->reserve(SLOT_DIAG, diag_elems(g) * sizeof(double) * B, &pD));
-    DGPB_TRY(ws->reserve(SLOT_OUT, sizeof(double) * kOutDoubles, &pO));
-    DGPB_TRY(ws->reserve(SLOT_INFO, sizeof(int) * MAXB, &pI));
+    DGPB_TRY(ws->reserve(tslot ? SLOT_DIAG2 : SLOT_DIAG, diag_elems(g) * sizeof(double) * B, &pD));
+    DGPB_TRY(ws->reserve(tslot ? SLOT_OUT2 : SLOT_OUT, sizeof(double) * kOutDoubles, &pO));
+    DGPB_TRY(ws->reserve(tslot ? SLOT_INFO2 : SLOT_INFO, sizeof(int) * MAXB, &pI));
     for (int b = 0; b < MAXB; ++b) {
         bt->T[b] = b < B ? (double*)pT + g.elems() * b : nullptr;
         bt->diag[b] = b < B ? (double*)pD + diag_elems(g) * b : nullptr;
@@ -643,9 +643,9 @@ int assemble(const Geom& g, const KernelDev* kds, const double* const* ys, const
 }
 
 // factorise + reduce a batch whose matrices are already assembled (info flags cleared here)
-int factor_reduce(const Geom& g, const Batch& bt, int B, const ScaleArgs& sa, double* out, cudaStream_t st) {
+int factor_reduce(const Geom& g, const Batch& bt, int B, const ScaleArgs& sa, double* out, cudaStream_t st, int ctx) {
     DGPB_CUDA_TRY(cudaMemsetAsync(bt.info, 0, sizeof(int) * MAXB, st));
-    DGPB_TRY(factorize(g, bt, B, st));
+    DGPB_TRY(factorize(g, bt, B, st, ctx));
     DGPB_TRY(reduce_logdet_quad(g, bt, B, sa, out, st));
     return DGPB_OK;
 }
@@ -713,7 +713,13 @@ struct LookAhead {
         return DGPB_OK;
     }
 };
-static thread_local LookAhead g_la;
+static thread_local LookAhead g_las[2];
+
+int join_waves(Workspace* ws, cudaStream_t st) {
+    for (int c = 0; c < 2; ++c)
+        if (ws->wave_done[c]) DGPB_CUDA_TRY(cudaStreamWaitEvent(st, ws->wave_done[c], 0));
+    return DGPB_OK;
+}
 
 static int launch_panel(const Geom& g, const Batch& bt, int B, int k0, int row_hi, cudaStream_t st) {
     potf2_kernel<<<B, 256, kPotf2Smem, st>>>(bt, g.ld, g.npad, k0, nullptr);
@@ -759,8 +765,9 @@ static int g_crit_stream = 1;   // critical path of the factorisation on its own
 // step, and a longer inner phase would only lengthen it.
 // Dependencies: bulk_h needs the panels of h (event) and bulk_{h-1} (side-stream order); look-ahead_h needs
 // bulk_{h-1} (event: both write columns [h1, h1 + next width)).
-int factorize(const Geom& g, const Batch& bt, int B, cudaStream_t caller) {
+int factorize(const Geom& g, const Batch& bt, int B, cudaStream_t caller, int ctx) {
     DGPB_TRY(configure_once());
+    LookAhead& g_la = g_las[ctx & 1];
     if (g_prof.on) {
         std::lock_guard<std::mutex> lock(g_prof_mutex);
         const double nn = (double)g.n;
@@ -907,6 +914,7 @@ __global__ void diag_shift_kernel(double* __restrict__ T, int64_t ld, int n, con
 
 int grad_pipeline(Workspace* ws, const dgpb_node* node, int64_t n, bool want_grad, double* Rinv, double* Rinv_y,
                   double* out_host, cudaStream_t st, const double* diag_shift = nullptr) {
+    DGPB_TRY(join_waves(ws, st));
     KernelDev kd;
     DGPB_TRY(make_kernel_dev(node, n, nullptr, &kd));
     Geom g = make_geom(n, true);
@@ -974,6 +982,7 @@ int dgpb_kmatrix(const double* X, int64_t n, int64_t D, const double* length_hos
 int dgpb_loglik_dense(dgpb_ws* ws, const dgpb_node* node, int64_t n, double* out_host, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     DGPB_REQUIRE(ws && node && out_host && n >= 1, "NULL argument");
+    DGPB_TRY(join_waves(ws, st));
     KernelDev kd;
     DGPB_TRY(make_kernel_dev(node, n, nullptr, &kd));
     const double* ys[1] = {node->output};
@@ -1000,6 +1009,7 @@ int dgpb_nllik_grad_dense_batch(dgpb_ws* ws, const dgpb_node* nodes, int B, int6
     cudaStream_t st = (cudaStream_t)stream;
     DGPB_REQUIRE(ws && nodes && out_host && status_host && n >= 1, "NULL argument");
     DGPB_REQUIRE(B >= 1 && B <= MAXB, "batch size out of range");
+    DGPB_TRY(join_waves(ws, st));
     KernelDev kds[MAXB];
     const double* ys[MAXB];
     ScaleArgs sa;
@@ -1059,6 +1069,7 @@ int dgpb_compute_stats_shifted(dgpb_ws* ws, const dgpb_node* node, int64_t n, co
 int dgpb_mvn_draw(dgpb_ws* ws, const dgpb_node* node, int64_t n, const double* z, double* nu, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     DGPB_REQUIRE(ws && node && z && nu && n >= 1, "NULL argument");
+    DGPB_TRY(join_waves(ws, st));
     KernelDev kd;
     DGPB_TRY(make_kernel_dev(node, n, nullptr, &kd));
     Geom g = make_geom(n, false);
@@ -1084,6 +1095,7 @@ int dgpb_mvn_draw(dgpb_ws* ws, const dgpb_node* node, int64_t n, const double* z
 int dgpb_probe_update(dgpb_ws* ws, int64_t n, int B, int flags, int reps, double* out_host) {
     DGPB_REQUIRE(ws && out_host && n >= 256 && B >= 1 && B <= MAXB, "bad argument");
     DGPB_TRY(configure_once());
+    DGPB_TRY(join_waves(ws, 0));
     Geom g = make_geom(n, false);
     Batch bt;
     double* out;
@@ -1125,6 +1137,7 @@ __global__ void probe_fill_kernel(double* __restrict__ x, int64_t len, unsigned 
 int dgpb_probe_factorize(dgpb_ws* ws, int64_t n, int B, int aug, int reps, double* out_host) {
     DGPB_REQUIRE(ws && out_host && n >= 64 && B >= 1 && B <= MAXB && reps >= 1, "bad argument");
     DGPB_REQUIRE(!aug || B == 1, "aug probe is single-matrix");
+    DGPB_TRY(join_waves(ws, 0));
     const int D = 8;
     void* px;
     DGPB_TRY(ws->reserve(SLOT_MISC, sizeof(double) * (size_t)(D + 1) * n * B, &px));
@@ -1197,6 +1210,8 @@ int dgpb_tune(const char* key, int value) {
         g_ess_target_b = value;
     } else if (k == "ess_prefetch") {
         g_ess_prefetch = value != 0;
+    } else if (k == "ess_overlap") {
+        g_ess_overlap = value != 0;
     } else if (k == "ess_trsv") {
         g_ess_cached_threshold = value != 0;
     } else if (k == "linkgp_matern_tab") {
@@ -1248,6 +1263,7 @@ int dgpb_profile_read(double* out_host) {
 int dgpb_potrf(dgpb_ws* ws, double* A, int64_t n, int* info_host, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     DGPB_REQUIRE(ws && A && n >= 1, "NULL argument");
+    DGPB_TRY(join_waves(ws, st));
     Geom g = make_geom(n, false);
     Batch bt;
     double* out;

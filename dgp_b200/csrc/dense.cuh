@@ -43,8 +43,13 @@ inline size_t diag_elems(const Geom& g) { return (size_t)g.npad * (1 + NB) + (si
 
 // Assemble T for every batch entry: K (lower) from the kernel descriptor, y row, identity rows.
 int assemble(const Geom& g, const KernelDev* kds, const double* const* ys, const Batch& bt, int B, cudaStream_t st);
-// Sliding-window partial Cholesky of the first npad columns.
-int factorize(const Geom& g, const Batch& bt, int B, cudaStream_t st);
+// Sliding-window partial Cholesky of the first npad columns.  `ctx` (0/1) selects one of the calling thread's two
+// look-ahead stream sets: two factorisations issued with different contexts run side by side on the GPU.
+int factorize(const Geom& g, const Batch& bt, int B, cudaStream_t st, int ctx = 0);
+// `st` waits for whatever ESS wave is still in flight in either factorisation context of the workspace (a wave
+// assembled and factored ahead of an acceptance): every entry point that uses the T sets outside the wave pipeline
+// calls this first.
+int join_waves(Workspace* ws, cudaStream_t st);
 // out[b*4+0] = 2 sum log diag(L) (first n), out[b*4+1] = |L^-1 y|^2, out[b*4+2] = sigma2 used
 // (scale_est ? quad/n : scale_in[b]).
 struct ScaleArgs {
@@ -65,7 +70,7 @@ int reserve_batches(Workspace* ws, const Geom& g, int B);
 // assemble without touching the info flags / factorise + reduce an assembled batch (ESS wave pipeline, ess.cu)
 int assemble_matrices(const Geom& g, const KernelDev* kds, const double* const* ys, const Batch& bt, int B,
                       cudaStream_t st);
-int factor_reduce(const Geom& g, const Batch& bt, int B, const ScaleArgs& sa, double* out, cudaStream_t st);
+int factor_reduce(const Geom& g, const Batch& bt, int B, const ScaleArgs& sa, double* out, cudaStream_t st, int ctx = 0);
 
 // log-likelihoods of B dense nodes: out_dev[b*4 + {0,1,2}] = logdet K, quad (y'K^-1y), sigma2
 int loglik_batch_device(Workspace* ws, const KernelDev* kds, const double* const* ys, const ScaleArgs& sa, int B,
@@ -78,5 +83,6 @@ void profile_wasted(int matrices, int64_t n);
 extern int g_ess_target_b;
 extern int g_ess_cached_threshold;
 extern int g_ess_prefetch;
+extern int g_ess_overlap;
 
 }  // namespace dgpb

@@ -214,7 +214,7 @@ static int nodes_loglik(Workspace* ws, const dgpb_node* nodes, int U, int64_t n,
 // computed are dealt round-robin and stay where they were computed) and the row is broadcast, so every rank ends
 // up with the same nu bit for bit.
 static int prior_draws(Workspace* ws, const dgpb_node* targets, int M, int64_t n, const double* z, double* nu,
-                       const int32_t* keys, cudaStream_t st) {
+                       const int32_t* keys, cudaStream_t st, int ctx = 0) {
     const int G = ws->comm.world;
     constexpr int kMaxTargets = 256;
     DGPB_REQUIRE(M >= 1 && M <= kMaxTargets, "too many target nodes");
@@ -282,9 +282,11 @@ static int prior_draws(Workspace* ws, const dgpb_node* targets, int M, int64_t n
         if (B == 0) continue;
         Batch bt;
         double* outd;
-        DGPB_TRY(setup_batch(ws, g, B, &bt, &outd));
+        // the context that is free: a wave factored ahead of the last acceptance may still run in the other one
+        if (ws->wave_done[ctx]) DGPB_CUDA_TRY(cudaStreamWaitEvent(st, ws->wave_done[ctx], 0));
+        DGPB_TRY(setup_batch_slot(ws, ctx, g, B, &bt, &outd));
         DGPB_TRY(assemble(g, kds, nullptr, bt, B, st));
-        DGPB_TRY(factorize(g, bt, B, st));
+        DGPB_TRY(factorize(g, bt, B, st, ctx));
         for (int b = 0; b < B; ++b)
             if (keys && keys[map[b]] >= 0) DGPB_TRY(cache_store(ws, keys[map[b]], g, bt, b, st));
         DGPB_TRY(restore_diag_blocks(g, bt, B, st));
@@ -504,11 +506,11 @@ static int dense_items_assemble(Workspace* ws, int tslot, const dgpb_node* nodes
 
 // Step 2: factorise this rank's matrices, reduce, exchange the result blocks (4 doubles per matrix: log|K|, y'K^-1y,
 // -, info) and launch the device-to-host copy of all of them (no host sync).
-static int dense_items_factor(Workspace* ws, const dgpb_node* nodes, int U, int nlocal, int W, const Batch& bt,
+static int dense_items_factor(Workspace* ws, int ctx, const dgpb_node* nodes, int U, int nlocal, int W, const Batch& bt,
                               const Geom& g, cudaStream_t st) {
     const int B = nlocal * U;
     void* pO;
-    DGPB_TRY(ws->reserve(SLOT_OUT, sizeof(double) * kOutDoubles, &pO));
+    DGPB_TRY(ws->reserve(ctx ? SLOT_OUT2 : SLOT_OUT, sizeof(double) * kOutDoubles, &pO));
     double* outd = (double*)pO;
     if (B > 0) {
         ScaleArgs sa;
@@ -516,15 +518,16 @@ static int dense_items_factor(Workspace* ws, const dgpb_node* nodes, int U, int 
             sa.scale[b] = nodes[b % U].scale;
             sa.est[b] = 0;
         }
-        DGPB_TRY(factor_reduce(g, bt, B, sa, outd, st));
+        DGPB_TRY(factor_reduce(g, bt, B, sa, outd, st, ctx));
     }
+    double* stage = ws->pinned + kPinnedWave + (size_t)ctx * kPinnedWaveStride;
     if (W > 1) {
         void* pc;
         DGPB_TRY(ws->reserve(SLOT_COMM, sizeof(double) * kCommBlock * kMaxRanks, &pc));
         DGPB_TRY(comm_allgather(ws, outd, (double*)pc, kCommBlock, st));
-        DGPB_CUDA_TRY(cudaMemcpyAsync(ws->pinned + kPinnedWave, pc, sizeof(double) * kCommBlock * W, cudaMemcpyDeviceToHost, st));
+        DGPB_CUDA_TRY(cudaMemcpyAsync(stage, pc, sizeof(double) * kCommBlock * W, cudaMemcpyDeviceToHost, st));
     } else if (B > 0) {
-        DGPB_CUDA_TRY(cudaMemcpyAsync(ws->pinned + kPinnedWave, outd, sizeof(double) * 4 * B, cudaMemcpyDeviceToHost, st));
+        DGPB_CUDA_TRY(cudaMemcpyAsync(stage, outd, sizeof(double) * 4 * B, cudaMemcpyDeviceToHost, st));
     }
     return DGPB_OK;
 }
@@ -532,10 +535,10 @@ static int dense_items_factor(Workspace* ws, const dgpb_node* nodes, int U, int 
 // Step 3: wait for the results and form the per-item sums.  pd[i] = 0 if one of the item's matrices is not positive
 // definite (bad_node[i] = which).  The caller decides what an indefinite item means: the reference only ever
 // evaluates items up to the first accepted one.
-static int dense_items_fetch(Workspace* ws, const dgpb_node* nodes, int U, int64_t n, int nitems, int W, double* sums,
-                             int* pd, int* bad_node, double* logdets, cudaStream_t st) {
+static int dense_items_fetch(Workspace* ws, int ctx, const dgpb_node* nodes, int U, int64_t n, int nitems, int W,
+                             double* sums, int* pd, int* bad_node, double* logdets, cudaStream_t st) {
     DGPB_CUDA_TRY(cudaStreamSynchronize(st));
-    const double* res = ws->pinned + kPinnedWave;
+    const double* res = ws->pinned + kPinnedWave + (size_t)ctx * kPinnedWaveStride;
     for (int i = 0; i < nitems; ++i) {
         const double* blk = res + (size_t)(i % W) * kCommBlock + (size_t)(i / W) * U * 4;
         double s = 0.0;
@@ -557,8 +560,27 @@ static int dense_items_fetch(Workspace* ws, const dgpb_node* nodes, int U, int64
 
 }  // namespace dgpb
 
-// last speculative-assembly event of this thread: the next call waits for it before it reuses the buffers
-static thread_local cudaEvent_t g_pre_done_guard = nullptr;
+// make the two wave contexts of the workspace (streams + events) on first use
+static int wave_contexts_init(Workspace* ws) {
+    if (ws->wave_stream[0]) return DGPB_OK;
+    for (int c = 0; c < 2; ++c) {
+        DGPB_CUDA_TRY(cudaStreamCreateWithFlags(&ws->wave_stream[c], cudaStreamNonBlocking));
+        DGPB_CUDA_TRY(cudaEventCreateWithFlags(&ws->wave_assembled[c], cudaEventDisableTiming));
+        DGPB_CUDA_TRY(cudaEventCreateWithFlags(&ws->wave_done[c], cudaEventDisableTiming));
+    }
+    return DGPB_OK;
+}
+
+// every stream-ordered reader of the proposal images / prior draws of an earlier block update has finished
+static int join_wave_staging(Workspace* ws, cudaStream_t st) {
+    for (int c = 0; c < 2; ++c)
+        if (ws->wave_assembled[c]) DGPB_CUDA_TRY(cudaStreamWaitEvent(st, ws->wave_assembled[c], 0));
+    return DGPB_OK;
+}
+
+namespace dgpb {
+int g_ess_overlap = 1;   // factor the next wave while the current one drains its tail (dgpb_tune "ess_overlap")
+}
 
 // The angles ESS will try are known in advance: a rejection is the only branch of the bracket rule
 // (imputation.py:111-119), so theta_{k+1} depends on theta_k and the next uniform, never on a likelihood value.
@@ -568,6 +590,13 @@ static thread_local cudaEvent_t g_pre_done_guard = nullptr;
 // one batch), the per-matrix results are all-gathered (1 KB per rank) and every rank replays the same decisions.
 // Accept/shrink decisions, the angles reported and the number of uniforms consumed are exactly those of the
 // one-at-a-time loop.  When the threshold likelihood is not cached it rides along in the first wave.
+//
+// Wave pipeline: two factorisation contexts (T set, side buffers, look-ahead streams).  While wave k is factored in
+// one context, wave k + 1 -- whose angles are known under the assumption that all of wave k is rejected -- is
+// proposed and assembled in the other; when a wave holds a single candidate (an 8-node upper layer: acceptance
+// ends about one wave in sixteen) it is also FACTORED there, so its bulk updates fill the SMs that the serial
+// panel chain of wave k's last hyper-blocks leaves idle.  An acceptance leaves that wave running; nothing reads its
+// results, and the next block update starts in the context that is free.
 extern "C" int dgpb_ess_block_cached(dgpb_ws* ws, const dgpb_node* targets, int n_targets,
                                      const int32_t* target_rows_host, double* layer_out, int64_t layer_width,
                                      const dgpb_node* uppers, int n_uppers, int64_t n, const double* z,
@@ -591,8 +620,14 @@ extern "C" int dgpb_ess_block_cached(dgpb_ws* ws, const dgpb_node* targets, int 
     const int W = batched ? ws->comm.world : 1;
     const int me = batched ? ws->comm.rank : 0;
     const int nslots = cap + 1;   // local proposal images per wave (rank 0 may carry the threshold item as slot 0)
+    // factor the next wave ahead of the decision: single-candidate waves on one GPU (NCCL calls of two waves in
+    // flight would have to be ordered across ranks, and multi-candidate waves accept too often for the bet to pay)
+    const bool overlap = batched && g_ess_overlap && g_ess_prefetch && cap == 1 && W == 1;
 
-    if (g_pre_done_guard) DGPB_CUDA_TRY(cudaStreamWaitEvent(st, g_pre_done_guard, 0));  // see the wave pipeline below
+    DGPB_TRY(wave_contexts_init(ws));
+    DGPB_TRY(join_wave_staging(ws, st));   // readers of SLOT_PROP / SLOT_NU left over from the previous block update
+    if (!batched) DGPB_TRY(join_waves(ws, st));   // the unbatched path uses the T sets outside the pipeline
+    int cur = ws->wave_cur;   // the context whose buffers are free now (the other may hold a wave still in flight)
     void *pnu, *pprop;
     const size_t layer_elems = (size_t)layer_width * n;
     DGPB_TRY(ws->reserve(SLOT_NU, sizeof(double) * (size_t)n_targets * n, &pnu));
@@ -600,7 +635,7 @@ extern "C" int dgpb_ess_block_cached(dgpb_ws* ws, const dgpb_node* targets, int 
     double* nuv = (double*)pnu;
     double* prop = (double*)pprop;
 
-    DGPB_TRY(prior_draws(ws, targets, n_targets, n, z, nuv, target_keys_host, st));
+    DGPB_TRY(prior_draws(ws, targets, n_targets, n, z, nuv, target_keys_host, st, cur));
 
     double log_y = 0.0;
     const bool have_thr = threshold_io_host && *threshold_io_host == *threshold_io_host;
@@ -615,6 +650,7 @@ extern "C" int dgpb_ess_block_cached(dgpb_ws* ws, const dgpb_node* targets, int 
     } else if (batched && (cap + 1) * n_uppers <= MAXB) {
         thr_pending = true;
     } else {
+        DGPB_TRY(join_waves(ws, st));
         DGPB_TRY(nodes_loglik(ws, uppers, n_uppers, n, nullptr, &log_y, st));
     }
     int ui = 0;
@@ -628,24 +664,12 @@ extern "C" int dgpb_ess_block_cached(dgpb_ws* ws, const dgpb_node* targets, int 
         DGPB_CUDA_TRY(cudaMemcpyAsync(prop + s * layer_elems, layer_out, sizeof(double) * layer_elems,
                                       cudaMemcpyDeviceToDevice, st));
     int nprop = 0;
-    // Wave pipeline (dense upper nodes): while wave k is being factored, the matrices of wave k + 1 -- whose angles
-    // are known under the assumption that all of wave k is rejected, true nine times out of ten -- are proposed
-    // and assembled into the other T set on a low-priority stream, so the next factorisation starts on ready
-    // matrices.  An accepted wave simply leaves the speculative set unused.
-    static thread_local cudaStream_t pre_stream = nullptr;
-    static thread_local cudaEvent_t pre_done = nullptr, pre_go = nullptr;
-    if (batched && !pre_stream) {
-        int lo_pri = 0, hi_pri = 0;
-        DGPB_CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri));
-        DGPB_CUDA_TRY(cudaStreamCreateWithPriority(&pre_stream, cudaStreamNonBlocking, lo_pri));
-        DGPB_CUDA_TRY(cudaEventCreateWithFlags(&pre_done, cudaEventDisableTiming));
-        DGPB_CUDA_TRY(cudaEventCreateWithFlags(&pre_go, cudaEventDisableTiming));
-        g_pre_done_guard = pre_done;
-    }
+    static thread_local cudaEvent_t pre_go = nullptr;
     if (batched) {
+        if (!pre_go) DGPB_CUDA_TRY(cudaEventCreateWithFlags(&pre_go, cudaEventDisableTiming));
         DGPB_TRY(reserve_batches(ws, make_geom(n, false), std::min((int)MAXB, (cap + 1) * n_uppers)));
-        // everything queued so far (prior draws, layer copies) is what the speculative stream must wait for;
-        // nothing the waves read is written again before an acceptance
+        // everything queued so far (prior draws, layer copies) is what the wave streams must wait for; nothing
+        // the waves read is written again before an acceptance
         DGPB_CUDA_TRY(cudaEventRecord(pre_go, st));
     }
     auto plan_wave = [&](double th0, double lmin, double lmax, int uidx, double* out_thetas) {
@@ -661,9 +685,20 @@ extern "C" int dgpb_ess_block_cached(dgpb_ws* ws, const dgpb_node* targets, int 
         }
         return DGPB_OK;
     };
-    // propose + assemble this rank's items of a wave (items [0, first) = threshold, then the candidates)
-    auto stage_wave = [&](const double* th, int S, int first, double* pbuf, int tslot, Batch* bt, Geom* g, int* nlocal,
-                          cudaStream_t s2) -> int {
+    // one wave in flight in one of the two contexts
+    struct Wave {
+        bool staged = false, factored = false;
+        int S = 0, first = 0, nlocal = 0;
+        double thetas[kMaxCand];
+        Batch bt;
+        Geom g;
+    } wv[2];
+    // propose + assemble this rank's items of a wave (items [0, first) = threshold, then the candidates) in context c
+    auto stage_wave = [&](int c, const double* th, int S, int first) -> int {
+        Wave& w = wv[c];
+        cudaStream_t cs = ws->wave_stream[c];
+        double* pbuf = prop + (size_t)c * nslots * layer_elems;
+        DGPB_CUDA_TRY(cudaStreamWaitEvent(cs, pre_go, 0));   // the layer image and the prior draws exist
         const double* srcs[kMaxWave + 1];
         int L = 0;
         for (int i = me; i < first + S; i += W) {   // local slot of item i = i / W = L
@@ -671,66 +706,63 @@ extern "C" int dgpb_ess_block_cached(dgpb_ws* ws, const dgpb_node* targets, int 
             if (i < first) {
                 srcs[L] = nullptr;
             } else {
-                DGPB_TRY(launch_proposal(th[i - first], pbuf + (size_t)L * layer_elems, s2));
+                DGPB_TRY(launch_proposal(th[i - first], pbuf + (size_t)L * layer_elems, cs));
                 srcs[L] = pbuf + (size_t)L * layer_elems;
             }
             ++L;
         }
-        *nlocal = L;
-        return dense_items_assemble(ws, tslot, uppers, n_uppers, n, srcs, L, bt, g, s2);
+        w.S = S;
+        w.first = first;
+        w.nlocal = L;
+        for (int s = 0; s < S; ++s) w.thetas[s] = th[s];
+        DGPB_TRY(dense_items_assemble(ws, c, uppers, n_uppers, n, srcs, L, &w.bt, &w.g, cs));
+        DGPB_CUDA_TRY(cudaEventRecord(ws->wave_assembled[c], cs));
+        w.staged = true;
+        w.factored = false;
+        return DGPB_OK;
     };
-    int wave = 0;               // parity selects the T set and the half of the proposal buffer
-    bool pre_ready = false;     // the current wave was assembled ahead of time
-    int pre_S = 0, pre_L = 0;
-    double pre_thetas[kMaxCand];
-    Batch pre_bt;
-    Geom pre_g;
+    auto factor_wave = [&](int c) -> int {
+        Wave& w = wv[c];
+        DGPB_TRY(dense_items_factor(ws, c, uppers, n_uppers, w.nlocal, W, w.bt, w.g, ws->wave_stream[c]));
+        DGPB_CUDA_TRY(cudaEventRecord(ws->wave_done[c], ws->wave_stream[c]));
+        w.factored = true;
+        return DGPB_OK;
+    };
     while (true) {
         // ---- candidate angles of this wave (each one assumes every earlier one was rejected)
         double thetas[kMaxCand];
         const int S = plan_wave(theta, tmin, tmax, ui, thetas);
-        double* pcur = prop + (size_t)(wave & 1) * nslots * layer_elems;
-        bool use_pre = pre_ready && pre_S == S && !thr_pending;
-        for (int s = 0; use_pre && s < S; ++s) use_pre = pre_thetas[s] == thetas[s];
+        double* pcur = prop + (size_t)cur * nslots * layer_elems;
         // ---- likelihoods of the wave
         double sums[kMaxCand + 1];
-        double wave_logdets[(kMaxCand + 1) * MAXB / 1];
+        double wave_logdets[(kMaxCand + 1) * MAXB];
         int pd[kMaxCand + 1], bad[kMaxCand + 1];
-        Batch bt;
-        Geom g;
         DenseBatchInfo info;
         int first = 0;  // index of candidate 0 in sums[]
         if (batched) {
-            int nlocal = 0;
-            if (use_pre) {
-                bt = pre_bt;
-                g = pre_g;
-                nlocal = pre_L;
-                DGPB_CUDA_TRY(cudaStreamWaitEvent(st, pre_done, 0));
-            } else {
-                if (pre_ready) DGPB_CUDA_TRY(cudaStreamWaitEvent(st, pre_done, 0));  // stale speculative set: let it drain
-                first = thr_pending ? 1 : 0;
-                DGPB_TRY(stage_wave(thetas, S, first, pcur, wave & 1, &bt, &g, &nlocal, st));
-            }
-            pre_ready = false;
-            DGPB_TRY(dense_items_factor(ws, uppers, n_uppers, nlocal, W, bt, g, st));
-            // ---- speculate: assemble the next wave while this one is being factored
+            Wave& w = wv[cur];
+            bool ready = w.staged && w.S == S && !thr_pending;   // staged ahead of time with exactly these angles?
+            for (int s = 0; ready && s < S; ++s) ready = w.thetas[s] == thetas[s];
+            if (!ready) DGPB_TRY(stage_wave(cur, thetas, S, thr_pending ? 1 : 0));
+            first = w.first;
+            if (!w.factored) DGPB_TRY(factor_wave(cur));
+            // ---- speculate: the next wave in the other context while this one is being factored
             {
                 double lmin = tmin, lmax = tmax;
                 for (int s = 0; s < S; ++s)
                     if (thetas[s] < 0.0) lmin = thetas[s]; else lmax = thetas[s];
                 const int ui_next = ui + S;   // S rejections consume S uniforms (the last one draws the next first angle)
+                wv[cur ^ 1].staged = false;
                 if (g_ess_prefetch && ui_next <= nu && ui_next >= 1) {
+                    double next_thetas[kMaxCand];
                     const double th_next = lmin + (lmax - lmin) * u_host[ui_next - 1];
-                    pre_S = plan_wave(th_next, lmin, lmax, ui_next, pre_thetas);
-                    double* pnext = prop + (size_t)((wave + 1) & 1) * nslots * layer_elems;
-                    DGPB_CUDA_TRY(cudaStreamWaitEvent(pre_stream, pre_go, 0));  // the layer image and the prior draws exist
-                    DGPB_TRY(stage_wave(pre_thetas, pre_S, 0, pnext, (wave + 1) & 1, &pre_bt, &pre_g, &pre_L, pre_stream));
-                    DGPB_CUDA_TRY(cudaEventRecord(pre_done, pre_stream));
-                    pre_ready = true;
+                    const int Sn = plan_wave(th_next, lmin, lmax, ui_next, next_thetas);
+                    DGPB_TRY(stage_wave(cur ^ 1, next_thetas, Sn, 0));
+                    if (overlap) DGPB_TRY(factor_wave(cur ^ 1));
                 }
             }
-            DGPB_TRY(dense_items_fetch(ws, uppers, n_uppers, n, first + S, W, sums, pd, bad, wave_logdets, st));
+            DGPB_TRY(dense_items_fetch(ws, cur, uppers, n_uppers, n, first + S, W, sums, pd, bad, wave_logdets,
+                                       ws->wave_stream[cur]));
             if (first == 1) {
                 if (!pd[0]) {
                     set_error("covariance of upper node %d is not positive definite", bad[0]);
@@ -744,7 +776,6 @@ extern "C" int dgpb_ess_block_cached(dgpb_ws* ws, const dgpb_node* targets, int 
             DGPB_TRY(nodes_loglik(ws, uppers, n_uppers, n, pcur, &sums[0], st, &info));
             pd[0] = 1;
         }
-        ++wave;
         // ---- replay the one-at-a-time decisions over the wave
         int accepted = -1;
         for (int s = 0; s < S; ++s) {
@@ -764,12 +795,14 @@ extern "C" int dgpb_ess_block_cached(dgpb_ws* ws, const dgpb_node* targets, int 
         }
         if (accepted >= 0) {
             const int ia = first + accepted;             // item index of the accepted candidate
+            const int owner = ia % W, slot = ia / W;     // the rank that evaluated it, its local slot there
             if (batched) {   // this rank's candidates behind the accepted one were issued for nothing
                 int behind = 0;
                 for (int i = me; i < first + S; i += W) behind += i > ia;
+                if (wv[cur ^ 1].factored) behind += wv[cur ^ 1].nlocal;   // ... and so was the wave factored ahead
                 profile_wasted(behind * n_uppers, n);
+                DGPB_CUDA_TRY(cudaStreamWaitEvent(st, ws->wave_done[cur], 0));   // (already complete: the host waited)
             }
-            const int owner = ia % W, slot = ia / W;     // the rank that evaluated it, its local slot there
             const double* pa = pcur + (size_t)slot * layer_elems;
             if (owner != me) {   // evaluated elsewhere: the same elementwise proposal, recomputed here
                 DGPB_TRY(launch_proposal(thetas[accepted], pcur, st));
@@ -788,7 +821,8 @@ extern "C" int dgpb_ess_block_cached(dgpb_ws* ws, const dgpb_node* targets, int 
                     for (int u = 0; u < n_uppers; ++u) {
                         if (upper_keys_host[u] < 0) continue;
                         const double* ld = &wave_logdets[ia * n_uppers + u];
-                        if (owner == me) DGPB_TRY(cache_store(ws, upper_keys_host[u], g, bt, slot * n_uppers + u, st, ld));
+                        if (owner == me)
+                            DGPB_TRY(cache_store(ws, upper_keys_host[u], wv[cur].g, wv[cur].bt, slot * n_uppers + u, st, ld));
                         set_owner(ws, upper_keys_host[u], W > 1 ? owner : kOwnerAll, n, ld);
                     }
                 } else {
@@ -806,6 +840,8 @@ extern "C" int dgpb_ess_block_cached(dgpb_ws* ws, const dgpb_node* targets, int 
                 }
             }
             if (threshold_io_host) *threshold_io_host = sums[first + accepted];
+            // the next block update starts in this context: the other one may still hold the wave factored ahead
+            ws->wave_cur = cur;
             break;
         }
         if (ui >= nu) {
@@ -814,6 +850,7 @@ extern "C" int dgpb_ess_block_cached(dgpb_ws* ws, const dgpb_node* targets, int 
             return DGPB_BAD_ARG;
         }
         theta = tmin + (tmax - tmin) * u_host[ui++];  // imputation.py:119
+        if (batched) cur ^= 1;   // the wave staged (and maybe factored) ahead becomes the current one
     }
     if (n_prop_host) *n_prop_host = nprop;
     return DGPB_OK;
@@ -992,7 +1029,7 @@ extern "C" int dgpb_ess_block_lik(dgpb_ws* ws, const dgpb_node* targets, int n_t
         DGPB_REQUIRE(target_rows_host[k] >= 0 && target_rows_host[k] < layer_width, "target row out of range");
     LikArgs a;
     DGPB_TRY(pack_liks(liks, n_liks, layer_width, &a));
-    if (g_pre_done_guard) DGPB_CUDA_TRY(cudaStreamWaitEvent(st, g_pre_done_guard, 0));  // SLOT_PROP may still be read
+    DGPB_TRY(join_wave_staging(ws, st));   // SLOT_PROP / SLOT_NU may still be read by a wave staged ahead
     void *pnu, *pprop, *pout;
     const size_t layer_elems = (size_t)layer_width * n;
     DGPB_TRY(ws->reserve(SLOT_NU, sizeof(double) * (size_t)n_targets * n, &pnu));
@@ -1001,7 +1038,7 @@ extern "C" int dgpb_ess_block_lik(dgpb_ws* ws, const dgpb_node* targets, int n_t
     double* nuv = (double*)pnu;
     double* prop = (double*)pprop;
     double* outd = (double*)pout;
-    DGPB_TRY(prior_draws(ws, targets, n_targets, n, z, nuv, target_keys_host, st));
+    DGPB_TRY(prior_draws(ws, targets, n_targets, n, z, nuv, target_keys_host, st, ws->wave_cur));
     for (int s = 0; s < kLikWave; ++s)  // rows that are not being updated are shared by every proposal
         DGPB_CUDA_TRY(cudaMemcpyAsync(prop + s * layer_elems, layer_out, sizeof(double) * layer_elems,
                                       cudaMemcpyDeviceToDevice, st));

@@ -102,6 +102,24 @@ class kernel:
             state.pop(key, None)
         return state
 
+    def __deepcopy__(self, memo):
+        """`copy.deepcopy` of a node (emulator.__init__ keeps one copy of the hierarchy per imputation,
+        emulation.py:44): numpy state is copied, R^-1 / R^-1 y stay the SAME device tensors -- `compute_stats` always
+        binds fresh tensors, nothing updates them in place -- instead of a round trip of n^2 doubles through the host."""
+        import copy as _copy
+        new = type(self).__new__(type(self))
+        memo[id(self)] = new
+        for key, val in self.__dict__.items():
+            if key in ('_Rinv', '_Rinv_y'):
+                new.__dict__[key] = val if not isinstance(val, np.ndarray) else val.copy()
+            elif key in ('_dcache', '_batcher', '_vcache', '_Xcat', '_ycol'):
+                new.__dict__[key] = None
+            elif key == '_frozen':
+                new.__dict__[key] = False
+            else:
+                new.__dict__[key] = _copy.deepcopy(val, memo)
+        return new
+
     def __setstate__(self, state):
         state = dict(state)
         state['_Rinv'] = state.pop('Rinv', None)
