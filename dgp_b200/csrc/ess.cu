@@ -579,7 +579,11 @@ static int join_wave_staging(Workspace* ws, cudaStream_t st) {
 }
 
 namespace dgpb {
-int g_ess_overlap = 1;   // factor the next wave while the current one drains its tail (dgpb_tune "ess_overlap")
+// Factor the next single-candidate wave while the current one drains its tail (dgpb_tune "ess_overlap").  Measured on
+// BASELINE config 3 (n = 5000, B200): two waves in flight raise the FLOP rate issued from 59.7 % to 63.4 % of the DGEMM
+// peak, and the wave that is in flight at every acceptance (one in ~17 for the 8-node layer pair) costs the same
+// 6 % again: 0.323 against 0.321 iterations/s.  Off by default: same speed, less energy.
+int g_ess_overlap = 0;
 }
 
 // The angles ESS will try are known in advance: a rejection is the only branch of the bracket rule
