@@ -103,6 +103,8 @@ _PROTOS = {
     "dgpb_aggregate": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp]),
     "dgpb_dgemm_nt": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_vp]),
     "dgpb_potrf": (ctypes.c_int, [c_vp, c_vp, c_i64, ctypes.POINTER(ctypes.c_int), c_vp]),
+    "dgpb_ess_sweeps_small": (ctypes.c_int, [c_vp, ctypes.POINTER(DgpbNode), c_vp, ctypes.c_int, c_vp, c_i64, ctypes.c_int,
+                                             c_vp, c_i64, c_vp, ctypes.c_int, c_vp, c_vp]),
     "dgpb_comm_unique_id": (ctypes.c_int, [c_vp]),
     "dgpb_comm_init": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int, c_vp]),
     "dgpb_comm_destroy": (ctypes.c_int, [c_vp]),

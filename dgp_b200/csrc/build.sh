@@ -7,10 +7,10 @@ NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-O3 -Xptxas -v"
 mkdir -p "$HERE/_obj"
 pids=()
-for f in common comm dense predict vecchia knn ess; do
+for f in common comm dense predict vecchia knn ess ess_small; do
   ( $NVCC $FLAGS -c "$HERE/$f.cu" -o "$HERE/_obj/$f.o" > "$HERE/_obj/$f.log" 2>&1 || { cat "$HERE/_obj/$f.log"; exit 1; } ) &
   pids+=($!)
 done
 for p in "${pids[@]}"; do wait $p; done
-$NVCC -shared -o "$OUT" "$HERE"/_obj/{common,comm,dense,predict,vecchia,knn,ess}.o -lcudart_static -lpthread -ldl -lrt
+$NVCC -shared -o "$OUT" "$HERE"/_obj/{common,comm,dense,predict,vecchia,knn,ess,ess_small}.o -lcudart_static -lpthread -ldl -lrt
 echo "built $OUT"

@@ -766,6 +766,7 @@ static int g_crit_stream = 1;   // critical path of the factorisation on its own
 // Dependencies: bulk_h needs the panels of h (event) and bulk_{h-1} (side-stream order); look-ahead_h needs
 // bulk_{h-1} (event: both write columns [h1, h1 + next width)).
 int factorize(const Geom& g, const Batch& bt, int B, cudaStream_t caller, int ctx) {
+    DGPB_NVTX("dgpb:factorize");
     DGPB_TRY(configure_once());
     LookAhead& g_la = g_las[ctx & 1];
     if (g_prof.on) {
@@ -914,6 +915,7 @@ __global__ void diag_shift_kernel(double* __restrict__ T, int64_t ld, int n, con
 
 int grad_pipeline(Workspace* ws, const dgpb_node* node, int64_t n, bool want_grad, double* Rinv, double* Rinv_y,
                   double* out_host, cudaStream_t st, const double* diag_shift = nullptr) {
+    DGPB_NVTX("dgpb:grad_pipeline");
     DGPB_TRY(join_waves(ws, st));
     KernelDev kd;
     DGPB_TRY(make_kernel_dev(node, n, nullptr, &kd));
@@ -964,6 +966,7 @@ extern "C" {
 
 int dgpb_kmatrix(const double* X, int64_t n, int64_t D, const double* length_host, int64_t nlen, double nugget,
                  const double* wdiag, int kind, int nugget_est, double* K, double* dK, void* stream) {
+    DGPB_NVTX("dgpb:kmatrix");
     cudaStream_t st = (cudaStream_t)stream;
     DGPB_REQUIRE(n >= 1 && K != nullptr, "n < 1 or K is NULL");
     KernelDev kd;
@@ -980,6 +983,7 @@ int dgpb_kmatrix(const double* X, int64_t n, int64_t D, const double* length_hos
 }
 
 int dgpb_loglik_dense(dgpb_ws* ws, const dgpb_node* node, int64_t n, double* out_host, void* stream) {
+    DGPB_NVTX("dgpb:loglik_dense");
     cudaStream_t st = (cudaStream_t)stream;
     DGPB_REQUIRE(ws && node && out_host && n >= 1, "NULL argument");
     DGPB_TRY(join_waves(ws, st));
@@ -1006,6 +1010,7 @@ int dgpb_nllik_grad_dense(dgpb_ws* ws, const dgpb_node* node, int64_t n, double*
 
 int dgpb_nllik_grad_dense_batch(dgpb_ws* ws, const dgpb_node* nodes, int B, int64_t n, double* out_host, int ldo,
                                 int* status_host, void* stream) {
+    DGPB_NVTX("dgpb:nllik_grad_dense_batch");
     cudaStream_t st = (cudaStream_t)stream;
     DGPB_REQUIRE(ws && nodes && out_host && status_host && n >= 1, "NULL argument");
     DGPB_REQUIRE(B >= 1 && B <= MAXB, "batch size out of range");
@@ -1067,6 +1072,7 @@ int dgpb_compute_stats_shifted(dgpb_ws* ws, const dgpb_node* node, int64_t n, co
 }
 
 int dgpb_mvn_draw(dgpb_ws* ws, const dgpb_node* node, int64_t n, const double* z, double* nu, void* stream) {
+    DGPB_NVTX("dgpb:mvn_draw");
     cudaStream_t st = (cudaStream_t)stream;
     DGPB_REQUIRE(ws && node && z && nu && n >= 1, "NULL argument");
     DGPB_TRY(join_waves(ws, st));

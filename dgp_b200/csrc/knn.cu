@@ -760,6 +760,7 @@ using namespace dgpb;
 extern "C" {
 
 int dgpb_knn_ordered(const double* x, int64_t n, int64_t D, int64_t m, int64_t* NN, void* stream) {
+    DGPB_NVTX("dgpb:knn_ordered");
     DGPB_REQUIRE(x && NN && n >= 1 && D >= 1 && D <= kMaxDim, "bad argument");
     m = std::min(m, n - 1);
     DGPB_REQUIRE(m >= 0 && m < kMaxBlock, "m out of range");
@@ -774,6 +775,7 @@ int dgpb_knn_ordered(const double* x, int64_t n, int64_t D, int64_t m, int64_t* 
 
 int dgpb_knn(const double* query, int64_t M, const double* x, int64_t n, int64_t D, int64_t m, int64_t* NN,
              void* stream) {
+    DGPB_NVTX("dgpb:knn");
     DGPB_REQUIRE(query && x && NN && n >= 1 && D >= 1 && D <= kMaxDim, "bad argument");
     cudaStream_t st = (cudaStream_t)stream;
     m = std::min(m, n);

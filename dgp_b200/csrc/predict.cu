@@ -970,6 +970,7 @@ int dgpb_dgemm_nt(const double* A, const double* B, double* C, int64_t M, int64_
 int dgpb_gp_predict(dgpb_ws* ws, const double* x, int64_t M, const double* W, int64_t n, int64_t D, const double* Rinv,
                     const double* Rinv_y, const double* length_host, int64_t nlen, double scale, double nugget,
                     int kind, double* mean, double* var, void* stream) {
+    DGPB_NVTX("dgpb:gp_predict");
     cudaStream_t st = (cudaStream_t)stream;
     DGPB_REQUIRE(ws && x && W && Rinv && Rinv_y && mean && var, "NULL argument");
     if (M == 0) return DGPB_OK;
@@ -1004,6 +1005,7 @@ int dgpb_linkgp_predict(dgpb_ws* ws, const double* m_in, const double* v_in, con
                         const double* w1, const double* gw, int64_t n, int64_t Dw, int64_t Dz, const double* Rinv,
                         const double* Rinv_y, const double* length_host, int64_t nlen, double scale, double nugget,
                         int kind, double* mean, double* var, void* stream) {
+    DGPB_NVTX("dgpb:linkgp_predict");
     cudaStream_t st = (cudaStream_t)stream;
     DGPB_REQUIRE(ws && m_in && v_in && w1 && Rinv && Rinv_y && mean && var && length_host, "NULL argument");
     DGPB_REQUIRE(Dw >= 1 && Dz >= 0 && Dw + Dz <= kMaxDim, "dimension out of range");
@@ -1128,6 +1130,7 @@ int dgpb_linkgp_predict(dgpb_ws* ws, const double* m_in, const double* v_in, con
 
 int dgpb_aggregate(const double* means, const double* vars, int64_t S, int64_t len, double* mu, double* sigma2,
                    void* stream) {
+    DGPB_NVTX("dgpb:aggregate");
     DGPB_REQUIRE(means && vars && mu && sigma2 && S >= 1, "NULL argument");
     if (len == 0) return DGPB_OK;
     aggregate_kernel<<<(unsigned)cdiv(len, 256), 256, 0, (cudaStream_t)stream>>>(means, vars, (int)S, len, mu, sigma2);

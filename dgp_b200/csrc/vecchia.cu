@@ -822,6 +822,7 @@ extern "C" {
 int dgpb_vecchia_llik(const double* X, const double* y, const int64_t* NN, int64_t n, int64_t D, int64_t m1,
                       const double* length_host, int64_t nlen, double scale, double nugget, const double* nugget_diag,
                       int kind, double* out_host, void* stream) {
+    DGPB_NVTX("dgpb:vecchia_llik");
     cudaStream_t st = (cudaStream_t)stream;
     DGPB_REQUIRE(X && y && NN && out_host, "NULL argument");
     VKern vk;
@@ -845,6 +846,7 @@ int dgpb_vecchia_llik(const double* X, const double* y, const int64_t* NN, int64
 int dgpb_vecchia_nllik(const double* X, const double* y, const int64_t* NN, int64_t n, int64_t D, int64_t m1,
                        const double* length_host, int64_t nlen, double scale, double nugget, const double* nugget_diag,
                        int kind, int scale_est, int nugget_est, double* out_host, void* stream) {
+    DGPB_NVTX("dgpb:vecchia_nllik");
     cudaStream_t st = (cudaStream_t)stream;
     DGPB_REQUIRE(X && y && NN && out_host, "NULL argument");
     VKern vk;
@@ -876,6 +878,7 @@ int dgpb_vecchia_nllik(const double* X, const double* y, const int64_t* NN, int6
 
 int dgpb_vecchia_Lmatrix(const double* X, const int64_t* NN, int64_t n, int64_t D, int64_t m1, const double* length_host,
                          int64_t nlen, double nugget, int kind, double* L, void* stream) {
+    DGPB_NVTX("dgpb:vecchia_Lmatrix");
     DGPB_REQUIRE(X && NN && L, "NULL argument");
     VKern vk;
     DGPB_TRY(make_vkern(kind, D, length_host, nlen, &vk));
@@ -885,6 +888,7 @@ int dgpb_vecchia_Lmatrix(const double* X, const int64_t* NN, int64_t n, int64_t 
 int dgpb_vecchia_mvn_draw(const double* X, const int64_t* NN, int64_t n, int64_t D, int64_t m1,
                           const double* length_host, int64_t nlen, double scale, double nugget, int kind,
                           const double* z, double* out, void* stream) {
+    DGPB_NVTX("dgpb:vecchia_mvn_draw");
     DGPB_REQUIRE(X && NN && z && out, "NULL argument");
     VKern vk;
     DGPB_TRY(make_vkern(kind, D, length_host, nlen, &vk));
@@ -896,6 +900,7 @@ int dgpb_vecchia_mvn_draw(const double* X, const int64_t* NN, int64_t n, int64_t
 int dgpb_gp_vecch(const double* x, int64_t M, const double* w, const double* y, int64_t n, int64_t D, const int64_t* NN,
                   int64_t mp, const double* length_host, int64_t nlen, double scale, double nugget,
                   const double* nugget_diag, int kind, double* mean, double* var, void* stream) {
+    DGPB_NVTX("dgpb:gp_vecch");
     DGPB_REQUIRE(x && w && y && NN && mean && var, "NULL argument");
     if (M == 0) return DGPB_OK;
     VKern vk;
@@ -922,6 +927,7 @@ int dgpb_gp_vecch(const double* x, int64_t M, const double* w, const double* y, 
 int dgpb_gp_vecch_multi(const double* x, int64_t M, const double* w, const double* Y, int64_t n, int64_t D,
                         const int64_t* NN, int64_t mp, int B, const double* length_host, const double* scale_host,
                         const double* nugget_host, double* mean, double* var, void* stream) {
+    DGPB_NVTX("dgpb:gp_vecch_multi");
     DGPB_REQUIRE(x && w && Y && NN && mean && var && length_host && scale_host && nugget_host, "NULL argument");
     DGPB_REQUIRE(B >= 1 && B <= kMultiMax, "number of nodes out of range");
     DGPB_REQUIRE(D >= 1 && D <= kMaxDim && mp >= 1 && mp + 1 <= 32, "block too large for the multi-node kernel");
@@ -960,6 +966,7 @@ int dgpb_linkgp_vecch(const double* m_in, const double* v_in, const double* z, i
                       const double* gw, const double* y, int64_t n, int64_t Dw, int64_t Dz, const int64_t* NN,
                       int64_t mp, const double* length_host, int64_t nlen, double scale, double nugget,
                       const double* nugget_diag, int kind, double* mean, double* var, void* stream) {
+    DGPB_NVTX("dgpb:linkgp_vecch");
     DGPB_REQUIRE(m_in && v_in && w1 && y && NN && mean && var, "NULL argument");
     DGPB_REQUIRE(Dz == 0 || (z && gw), "z/gw required when Dz > 0");
     if (M == 0) return DGPB_OK;

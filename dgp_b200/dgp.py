@@ -605,7 +605,10 @@ class dgp:
         torch = L.torch_mod()
         dev = L.device()
         dense = [it for it in nodes if not it[1].vecch]
-        batch = len(dense) > 1 and os.environ.get('DGPB_MSTEP_BATCH', '1') != '0'
+        # small models: an evaluation is a handful of microsecond kernels, the rendezvous of one host thread per node
+        # would cost more than it saves; the nodes are optimised one after the other (same numbers either way)
+        batch = len(dense) > 1 and os.environ.get('DGPB_MSTEP_BATCH', '1') != '0' and \
+            (self.n_data >= 128 or os.environ.get('DGPB_MSTEP_BATCH') == '1')
         if not batch:
             dense = []
         for l, kernel in nodes:   # nodes outside the batch

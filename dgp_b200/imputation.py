@@ -182,6 +182,59 @@ class _DeviceLayers:
             np.random.uniform(size=1 + nprop)  # consume exactly what the reference would have
             return nprop
 
+    SMALL_N = 64   # training points up to which the whole I-step runs in one kernel (csrc/ess_small.cu)
+
+    def small_ok(self, block):
+        """The whole I-step can run in ONE launch (`dgpb_ess_sweeps_small`): a dense GP hierarchy with block updates,
+        at most 64 training points and 8 nodes per layer, one process (no shared chain)."""
+        import os
+        from . import parallel
+        if not block or self.liks is not None or self.n > self.SMALL_N or parallel.chain() is not None:
+            return False
+        if os.environ.get('DGPB_ESS_SMALL', '1') == '0':
+            return False
+        for l, layer in enumerate(self.all_layer):
+            if len(layer) > 8 or any(k.vecch or k.type != 'gp' for k in layer):
+                return False
+        return len(self.all_layer) <= 8
+
+    def sweeps_small(self, sweeps, z=None, u=None, max_u=48):
+        """`sweeps` block-update sweeps over all layer pairs in one kernel launch.  Draws as in `block_update`: n
+        normals per target node and update from the module generator, uniforms from numpy's global generator, which
+        is advanced by exactly the number the reference would have consumed.  `z` / `u` inject explicit draws
+        (tests).  Returns the number of proposals evaluated."""
+        n, Lg = self.n, len(self.all_layer)
+        widths = np.ascontiguousarray([len(layer) for layer in self.all_layer], dtype=np.int32)
+        draws = int(sweeps * widths[:-1].sum())
+        if z is None:
+            z = _nb_rng.standard_normal((draws, n))
+        zd = L.to_dev(np.ascontiguousarray(z, dtype=np.float64))
+        flat = (L.DgpbNode * int(widths.sum()))(*[nd for arr in self.nodes for nd in arr])
+        ptrs = (L.c_vp * Lg)(*[L.c_vp(F.data_ptr()) for F in self.F])
+        counts = np.zeros(3, dtype=np.int32)
+        injected = u is not None
+        updates = sweeps * (Lg - 1)
+        while True:
+            state = None if injected else np.random.get_state()
+            uu = np.ascontiguousarray(u if injected else np.random.uniform(size=updates * max_u), dtype=np.float64)
+            saved = [F.clone() for F in self.F[:-1]]
+            status = L.load().dgpb_ess_sweeps_small(L.workspace(), flat, widths.ctypes.data_as(L.c_vp), Lg, ptrs, n, sweeps,
+                                                    L.ptr(zd), zd.shape[0], uu.ctypes.data_as(L.c_vp), len(uu),
+                                                    counts.ctypes.data_as(L.c_vp), L.stream())
+            if status == L.DGPB_BAD_ARG and not injected and updates * max_u < 1 << 22:
+                # ran out of uniforms: the same sweeps again from the same state with a longer block
+                np.random.set_state(state)
+                for F, old in zip(self.F, saved):
+                    F.copy_(old)
+                max_u *= 4
+                continue
+            if not injected:
+                np.random.set_state(state)
+                np.random.uniform(size=int(counts[0]))   # consume exactly what the reference would have
+            L.check(status)
+            self.last_uniforms = int(counts[0])
+            return int(counts[1])
+
     def write_back(self):
         """Imputed layers -> `kernel.output` of their nodes and `kernel.input` of the nodes they feed."""
         for l in range(len(self.all_layer) - 1):
@@ -213,6 +266,11 @@ class imputer:
         if n_layer < 2:
             return
         dev = _DeviceLayers(self.all_layer)
+        if dev.small_ok(self.block):   # the whole I-step in one launch (n <= 64)
+            self.n_proposals += dev.sweeps_small(burnin + 1)
+            self.n_block_updates += (burnin + 1) * (n_layer - 1)
+            dev.write_back()
+            return
         for _ in range(burnin + 1):
             for l in range(n_layer - 1):
                 layer, linked = self.all_layer[l], self.all_layer[l + 1]

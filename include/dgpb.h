@@ -183,6 +183,21 @@ int dgpb_ess_block_cached(dgpb_ws* ws, const dgpb_node* targets, int n_targets, 
                           const int32_t* upper_keys_host, double* threshold_io_host, void* stream);
 int dgpb_cache_clear(dgpb_ws* ws);
 
+/* imputer.sample(burnin) (imputation.py:22-42 with block updates, :44-119) of a SMALL dense DGP -- n <= 64 training
+ * points, at most 8 nodes per layer and 8 GP layers -- in ONE kernel launch: one CTA keeps the layers, the prior draws
+ * and the kernel matrix in shared memory and runs every block update of `sweeps` sweeps (prior draws, threshold,
+ * propose -> kernel matrix -> Cholesky -> solve -> accept / shrink) with the caller's pre-drawn numbers; no host
+ * round trip per proposal, per update or per sweep.
+ * nodes_host: the GP nodes layer by layer (widths_host[l] per layer); layer_ptrs_host[l]: device image of layer l
+ * (width_l x n, one latent column per row; nodes of layer l + 1 read it through src / input_dim; the last layer holds
+ * the training outputs).  z: device, z_rows x n standard normals, one row per prior draw in the reference's order
+ * (sweep, layer pair, target node); u_host: nu uniforms in the reference's order (threshold, first angle, one per
+ * rejection, update after update).  counts_host = {uniforms consumed, proposals evaluated, prior draws made}.
+ * Returns DGPB_BAD_ARG when the uniforms ran out (the layers are then partly updated: restore and retry). */
+int dgpb_ess_sweeps_small(dgpb_ws* ws, const dgpb_node* nodes_host, const int32_t* widths_host, int n_layers,
+                          double* const* layer_ptrs_host, int64_t n, int sweeps, const double* z, int64_t z_rows,
+                          const double* u_host, int nu, int32_t* counts_host, void* stream);
+
 /* Likelihood layers.  dgpb_lik_loglik: sum of `llik()` (likelihood_class.py:39-48, 110-116, 264-272) over the
  * likelihood nodes for the latent layer image `layer` (layer_width x n, device); one double to the host.
  * dgpb_ess_block_lik: imputer.one_sample_block / one_sample (imputation.py:44-119, 166-221) for target GP nodes whose

@@ -1471,3 +1471,59 @@ def test_vecchia_mode_switches_skip_likelihood_nodes():
     assert cont.vecch
     cont.remove_vecchia()
     assert not cont.vecch and all(not k.vecch for layer in cont.structure for k in layer if k.type == 'gp')
+
+
+# ------------------------------------------------------------------------------------------------ small models
+def test_small_model_istep_in_one_launch(golden_ess):
+    """`dgpb_ess_sweeps_small` (n <= 64: all sweeps of an I-step in ONE kernel launch, csrc/ess_small.cu) replays the
+    reference's sweeps from the fixture with its own normals and uniforms: it consumes exactly the reference's
+    uniforms (identical accept / shrink decisions) and ends in the reference's latent layers."""
+    from dgp_b200.imputation import _DeviceLayers
+
+    g = golden_ess
+    done = 0
+    for ci in range(int(g["ncases"])):
+        p = f"c{ci}_"
+        widths, name, vecch = [int(w) for w in g[p + "widths"]], str(g[p + "name"]), bool(g[p + "vecch"])
+        if vecch:
+            continue
+        layers = _load_layers(g, p + "pre_", widths, name, vecch)
+        dev = _DeviceLayers(layers)
+        assert dev.small_ok(True)
+        Z, U, sweeps = g[p + "Z"], g[p + "U"], int(g[p + "sweeps"])
+        nprop = dev.sweeps_small(sweeps, z=Z, u=np.concatenate((U, np.full(8, 0.5))))
+        assert dev.last_uniforms == len(U), (ci, dev.last_uniforms, len(U))
+        assert nprop == len(U) - sweeps * (len(widths) - 1), ci      # one uniform per proposal + one per threshold
+        dev.write_back()
+        post = _load_layers(g, p + "post_", widths, name, vecch)
+        for l in range(len(widths)):
+            for k in range(widths[l]):
+                assert floor_ok(f"ess_c{ci}_post_L{l}K{k}", layers[l][k].output, post[l][k].output), (ci, l, k)
+        done += 1
+    assert done == 2
+
+
+def test_small_model_path_equals_general_path(monkeypatch):
+    """The public API takes the one-launch path for small models: same seeds, same chain as the general (wave) path --
+    same number of proposals, same uniforms consumed, same imputed layers to rounding."""
+    import dgp_b200 as D
+
+    def run(small):
+        monkeypatch.setenv("DGPB_ESS_SMALL", "1" if small else "0")
+        np.random.seed(77)
+        D.nb_seed(77)
+        X = np.linspace(0, 1, 10)[:, None]
+        Y = np.array([[-1.0] if i < 0.5 else [1.0] for i in X[:, 0]])
+        layers = [[D.kernel(length=np.array([1.0]), name="sexp")], [D.kernel(length=np.array([1.0]), name="sexp")],
+                  [D.kernel(length=np.array([1.0]), name="sexp", scale_est=True)]]
+        model = D.dgp(X, Y, D.combine(*layers))
+        model.train(5, disable=True)
+        return model, np.random.uniform(size=2)
+
+    a, ra = run(True)
+    b, rb = run(False)
+    assert a.imp.n_proposals == b.imp.n_proposals and np.array_equal(ra, rb)
+    for la, lb in zip(a.all_layer, b.all_layer):
+        for ka, kb in zip(la, lb):
+            assert np.allclose(ka.output, kb.output, rtol=1e-7, atol=1e-9)
+            assert np.allclose(ka.para_path, kb.para_path, rtol=1e-6, atol=1e-9)
