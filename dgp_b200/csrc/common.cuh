@@ -104,6 +104,7 @@ enum Slot : int {
     SLOT_VY,          // Vecchia: outputs gathered in Vecchia order
     SLOT_VL,          // Vecchia: sparse inverse-Cholesky rows
     SLOT_VFLAG,       // Vecchia: ready flags of the sparse solve
+    SLOT_KNN_PACK,    // neighbour search: candidates packed as TF32 screen rows (tcgen05 path)
     SLOT_COMM,        // multi-GPU: gathered result blocks of an ESS wave (world x kCommBlock doubles)
     SLOT_COMM_FLAG,   // multi-GPU: status word
     SLOT_COUNT

@@ -683,7 +683,47 @@ __global__ void __launch_bounds__(256, 2) knn_tf32_kernel(const double* __restri
     }
 }
 
-static int g_knn_mma = 3;   // dgpb_tune("knn_mma", v): 0 scalar exact kernel, 1 FP64 DMMA screen, 3 split-TF32 screen (default)
+}  // namespace dgpb
+#include "knn_tc5.cuh"
+namespace dgpb {
+
+// dgpb_tune("knn_mma", v): 0 scalar exact kernel, 1 FP64 DMMA screen, 3 warp-level split-TF32 screen (mma.sync),
+// 5 split-TF32 screen on tcgen05 (TMA bulk copies, TMEM accumulators; default)
+static int g_knn_mma = 5;
+
+// tcgen05 screen: pack the candidates once, then one CTA per 128 queries.  Returns DGPB_OK with *done = 0 when the
+// shape does not fit (too many dimensions for the shared-memory stages): the caller takes the warp-level kernel.
+template <bool ORDERED>
+static int knn_tc5_search(Workspace* ws, const double* q, int64_t M, const double* x, int64_t n, int D, int m, int NL,
+                          int64_t* NN, int ldnn, unsigned char* flags, cudaStream_t st, int* done) {
+    *done = 0;
+    const int K8 = tc5::k8_of(D);
+    const size_t smem = NL == 1 ? tc5::smem_bytes<1>(K8) : tc5::smem_bytes<2>(K8);
+    if (K8 > tc5::kMaxK8 || smem > 227 * 1024) return DGPB_OK;
+    const int64_t tiles = cdiv(n, tc5::kN);
+    void* pp;
+    const size_t pack_bytes = (size_t)tiles * 2 * K8 * tc5::kN * 16;
+    DGPB_TRY(ws->reserve(SLOT_KNN_PACK, pack_bytes + 256, &pp));
+    float* packed = (float*)pp;
+    float* xnmax = reinterpret_cast<float*>((char*)pp + pack_bytes);
+    DGPB_CUDA_TRY(cudaMemsetAsync(xnmax, 0, sizeof(float), st));
+    tc5::knn_tc5_pack_kernel<<<(unsigned)tiles, tc5::kN, 0, st>>>(x, n, D, K8, packed, xnmax);
+    DGPB_LAUNCHED();
+    const unsigned grid = (unsigned)cdiv(M, tc5::kQ);
+#define KNN_TC5_CASE(NLV)                                                                                               \
+    if (NL == NLV) {                                                                                                    \
+        DGPB_CUDA_TRY(cudaFuncSetAttribute(tc5::knn_tc5_kernel<NLV, ORDERED>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                           (int)smem));                                                                 \
+        tc5::knn_tc5_kernel<NLV, ORDERED><<<grid, tc5::kThreads, smem, st>>>(q, M, x, n, D, K8, m, packed, xnmax, NN, ldnn, \
+                                                                             flags);                                    \
+        DGPB_LAUNCHED();                                                                                                \
+    }
+    KNN_TC5_CASE(1) KNN_TC5_CASE(2)
+#undef KNN_TC5_CASE
+    *done = 1;
+    return DGPB_OK;
+}
+
 
 template <bool ORDERED>
 static int knn_search(Workspace* ws, const double* q, int64_t M, const double* x, int64_t n, int D, int m, int64_t* NN,
@@ -696,7 +736,12 @@ static int knn_search(Workspace* ws, const double* q, int64_t M, const double* x
     unsigned char* flags = (unsigned char*)pf;
     DGPB_CUDA_TRY(cudaMemsetAsync(flags, 0, (size_t)M, st));
     const unsigned grid = (unsigned)cdiv(M, kKnnQ);
-    if (g_knn_mma == 3) {
+    if (g_knn_mma == 5) {
+        int done = 0;
+        DGPB_TRY(knn_tc5_search<ORDERED>(ws, q, M, x, n, D, m, NL, NN, ldnn, flags, st, &done));
+        if (done) return launch_knn<ORDERED>(q, M, x, n, D, m, NN, ldnn, flags, st);
+    }
+    if (g_knn_mma == 3 || g_knn_mma == 5) {
         const int KS8 = (D + 7) / 8;
 #define KNN_TF32_CASE(KSV, NLV)                                                                                          \
     if (KS8 == KSV && NL == NLV) {                                                                                       \

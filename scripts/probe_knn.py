@@ -10,7 +10,7 @@ rng = np.random.default_rng(3)
 for D, m in ((10, 25), (20, 25), (10, 50)):
     M, n = 200000, 100000
     xq, xw = L.to_dev(rng.uniform(0, 1, (M, D))), L.to_dev(rng.uniform(0, 1, (n, D)))
-    for mode, name in ((3, "split-TF32 screen + rank"), (1, "DMMA screen + lists + rank"), (2, "DMMA screen only (probe)"), (0, "scalar exact kernel")):
+    for mode, name in ((5, "tcgen05 TF32 screen + rank"), (3, "split-TF32 screen + rank"), (1, "DMMA screen + lists + rank"), (2, "DMMA screen only (probe)"), (0, "scalar exact kernel")):
         if mode == 0 and D == 20: continue
         L.check(lib.dgpb_tune(b"knn_mma", mode))
         V.get_pred_nn_dev(xq, xw, m); torch.cuda.synchronize()
@@ -18,4 +18,4 @@ for D, m in ((10, 25), (20, 25), (10, 50)):
         e0.record(); V.get_pred_nn_dev(xq, xw, m); e1.record(); torch.cuda.synchronize()
         t = e0.elapsed_time(e1) * 1e-3
         print(f"D={D} m={m} {name:24s} {t*1e3:8.2f} ms  {M*n/t/1e9:7.1f} G pairs/s  {M*n*2*D/t/1e12:5.1f} TFLOP/s (2D flop/pair)", flush=True)
-L.check(lib.dgpb_tune(b"knn_mma", 1))
+L.check(lib.dgpb_tune(b"knn_mma", 5))

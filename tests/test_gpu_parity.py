@@ -380,7 +380,7 @@ def test_knn_tensor_core_screen_equals_scalar_search():
     lib = L.load()
     rng = np.random.default_rng(23)
 
-    default_mode = 3
+    default_mode = 5
 
     def run(fn, mode):
         L.check(lib.dgpb_tune(b"knn_mma", mode))
@@ -390,9 +390,10 @@ def test_knn_tensor_core_screen_equals_scalar_search():
             L.check(lib.dgpb_tune(b"knn_mma", default_mode))
 
     def both(fn):
-        ref, dmma, tf32 = run(fn, 0), run(fn, 1), run(fn, 3)   # scalar exact, FP64 DMMA screen, split-TF32 screen
-        assert np.array_equal(dmma, tf32)
-        return ref, tf32
+        # scalar exact, FP64 DMMA screen, warp-level split-TF32 screen, tcgen05 split-TF32 screen (TMA + TMEM)
+        ref, dmma, tf32, tc5 = run(fn, 0), run(fn, 1), run(fn, 3), run(fn, 5)
+        assert np.array_equal(dmma, tf32) and np.array_equal(dmma, tc5)
+        return ref, tc5
 
     assert np.array_equal(run(lambda: V.get_pred_nn(rng.uniform(0, 1, (64, 4)), rng.uniform(0, 1, (300, 4)), 5), 1).shape, (64, 5))
     for n, M, D, m in ((1000, 333, 3, 5), (5000, 1500, 10, 25), (3001, 700, 20, 50), (700, 129, 31, 29),
