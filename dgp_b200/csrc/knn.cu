@@ -191,14 +191,14 @@ template <int NL, bool ORDERED>
 __device__ __forceinline__ void knn_rank_and_write(const double* __restrict__ q, const double* __restrict__ x, int64_t qi,
                                                    int D, int m, const int* __restrict__ lidx_q, double bound,
                                                    int64_t* __restrict__ NN, int ldnn, unsigned char* __restrict__ flags,
-                                                   int lane) {
+                                                   int lane, int istride = 1) {
     constexpr int LC = 32 * NL;
     double dv[NL];
     int jv[NL];
     int filled = 0;
 #pragma unroll
     for (int e = 0; e < NL; ++e) {
-        const int j = lidx_q[lane + 32 * e];
+        const int j = lidx_q[(lane + 32 * e) * istride];   // istride: survivor slots of one query (1, or slot-major sets)
         jv[e] = j;
         double dist = INFINITY;
         if (j >= 0) {
@@ -698,7 +698,12 @@ static int knn_tc5_search(Workspace* ws, const double* q, int64_t M, const doubl
                           int64_t* NN, int ldnn, unsigned char* flags, cudaStream_t st, int* done) {
     *done = 0;
     const int K8 = tc5::k8_of(D);
-    const size_t smem = NL == 1 ? tc5::smem_bytes<1>(K8) : tc5::smem_bytes<2>(K8);
+    int stages = tc5::kMaxStages;
+    size_t smem = NL == 1 ? tc5::smem_bytes<1>(K8, stages) : tc5::smem_bytes<2>(K8, stages);
+    if (smem > 227 * 1024) {
+        stages = 2;
+        smem = NL == 1 ? tc5::smem_bytes<1>(K8, stages) : tc5::smem_bytes<2>(K8, stages);
+    }
     if (K8 > tc5::kMaxK8 || smem > 227 * 1024) return DGPB_OK;
     const int64_t tiles = cdiv(n, tc5::kN);
     void* pp;
@@ -714,7 +719,7 @@ static int knn_tc5_search(Workspace* ws, const double* q, int64_t M, const doubl
     if (NL == NLV) {                                                                                                    \
         DGPB_CUDA_TRY(cudaFuncSetAttribute(tc5::knn_tc5_kernel<NLV, ORDERED>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                            (int)smem));                                                                 \
-        tc5::knn_tc5_kernel<NLV, ORDERED><<<grid, tc5::kThreads, smem, st>>>(q, M, x, n, D, K8, m, packed, xnmax, NN, ldnn, \
+        tc5::knn_tc5_kernel<NLV, ORDERED><<<grid, tc5::kThreads, smem, st>>>(q, M, x, n, D, K8, stages, m, packed, xnmax, NN, ldnn, \
                                                                              flags);                                    \
         DGPB_LAUNCHED();                                                                                                \
     }

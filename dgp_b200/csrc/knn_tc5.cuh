@@ -13,23 +13,27 @@
 //     v = hi + lo as three K-blocks [b_hi | b_lo | b_hi] against query rows [a_hi | a_hi | a_lo] (so one MMA chain
 //     forms hi.hi + hi.lo + lo.hi), and |x_j - x_0|^2 split three ways against three columns of ones -- the
 //     accumulator IS s(q, j), no epilogue arithmetic;
-//   * the packed rows are stored tile by tile in the canonical K-major no-swizzle UMMA layout, so a 256-candidate
+//   * the packed rows are stored tile by tile in the canonical K-major no-swizzle UMMA layout, so a 128-candidate
 //     tile is ONE contiguous block that the TMA engine copies with a single cp.async.bulk (mbarrier complete_tx);
-//   * ONE thread issues tcgen05.mma.kind::tf32 (M = 128 queries, N = 256 candidates, K = 8 per instruction) into a
-//     double-buffered TMEM accumulator (2 x 256 columns), tcgen05.commit releases the shared-memory stage and hands
-//     the accumulator to the epilogue;
-//   * four epilogue warps read their 32 TMEM lanes with tcgen05.ld (32 candidates per instruction and thread): one
-//     THREAD owns one query, so a candidate costs one compare against the query's threshold; the rare hits go through
-//     the same warp-cooperative sorted-list insertion as before.
+//   * ONE thread issues tcgen05.mma.kind::tf32 (M = 128 queries, N = 128 candidates, K = 8 per instruction) for TWO
+//     query groups per candidate tile into double-buffered TMEM accumulators (2 groups x 2 buffers x 128 columns = all
+//     512 columns), tcgen05.commit releases the shared-memory stage and hands the accumulators to the epilogue;
+//   * eight epilogue warps (two per scheduler) read their 32 TMEM lanes with tcgen05.ld (32 candidates per instruction
+//     and thread): one THREAD owns one query, so a candidate costs one compare against the query's threshold, folded
+//     into a 32-bit hit mask; the values are parked in shared memory and the rare hits go through the same
+//     warp-cooperative sorted-list insertion as before.
 #pragma once
 
 namespace tc5 {
 
-constexpr int kQ = 128;          // queries per CTA = TMEM lanes = UMMA M
-constexpr int kN = 256;          // candidates per tile = UMMA N
-constexpr int kStages = 2;       // shared-memory stages of packed candidate tiles
+constexpr int kQG = 128;         // queries per group = TMEM lanes = UMMA M
+constexpr int kGroups = 2;       // query groups per CTA: both multiply the SAME candidate tile (half the TMA traffic)
+constexpr int kQ = kQG * kGroups;   // queries per CTA
+constexpr int kN = 128;          // candidates per tile = UMMA N
+constexpr int kMaxStages = 3;    // shared-memory stages of packed candidate tiles (2 when 3 do not fit)
 constexpr int kMaxK8 = 12;       // K' = 8 * K8 <= 96 screen columns (D <= 31)
-constexpr int kThreads = 192;    // warps 0-3: epilogue (TMEM lane quarter = warp id), warp 4: TMA, warp 5: MMA + TMEM alloc
+constexpr int kEpiWarps = 4 * kGroups;   // warp w: query group w / 4, TMEM lane quarter w % 4
+constexpr int kThreads = 32 * (kEpiWarps + 2);   // + one TMA warp + one MMA / TMEM-allocation warp
 
 // screen columns: [0, D) a_hi.b_hi, [D, 2D) a_hi.b_lo, [2D, 3D) a_lo.b_hi, [3D, 3D + 3) 1 . |x - x0|^2 (3-way split)
 __host__ __device__ inline int k8_of(int D) { return (3 * D + 3 + 7) / 8; }
@@ -62,6 +66,22 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
         "r"(parity)
         : "memory");
 }
+// the same for the single-thread roles (TMA producer, MMA issuer): they share their schedulers with epilogue warps, so a
+// failed poll backs off instead of spinning in their issue slots
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, unsigned parity) {
+    while (true) {
+        unsigned ok;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}\n"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (ok) return;
+        __nanosleep(64);
+    }
+}
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -85,8 +105,8 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_b
     d |= (uint64_t)1 << 46;   // descriptor version of sm_100
     return d;                 // base offset 0, layout type 0 = SWIZZLE_NONE
 }
-// kind::tf32, FP32 accumulate, A and B K-major, M = 128, N = 256   (InstrDescriptor, same header)
-constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kN >> 3) << 17) | ((uint32_t)(kQ >> 4) << 24);
+// kind::tf32, FP32 accumulate, A and B K-major, M = 128, N = 128   (InstrDescriptor, same header)
+constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kN >> 3) << 17) | ((uint32_t)(kQG >> 4) << 24);
 
 __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, bool accumulate) {
     asm volatile(
@@ -117,9 +137,35 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// ---- per-query survivor set: the LC smallest screened values as a binary MAX-HEAP owned by ONE thread -----------------
+// Layout [slot][query of the CTA]: the 32 threads of a warp touch 32 consecutive words per slot (no bank conflicts).
+// The root is the query's threshold; a hit replaces the root and sifts down (<= log2 LC levels, no shuffles, no votes):
+// every lane of a warp that holds a hit inserts at the same time.  The exact ranking that follows orders the set.
+template <int LC>
+__device__ __forceinline__ float heap_replace_root(float* K, int* I, int stride, float key, int idx) {
+    int i = 0;
+#pragma unroll 1
+    while (true) {
+        const int l = 2 * i + 1, r = l + 1;
+        if (l >= LC) break;
+        const float kl = K[l * stride];
+        const float kr = r < LC ? K[r * stride] : -INFINITY;
+        const bool right = kr > kl;
+        const int ch = right ? r : l;
+        const float kc = right ? kr : kl;
+        if (!(kc > key)) break;
+        K[i * stride] = kc;
+        I[i * stride] = I[ch * stride];
+        i = ch;
+    }
+    K[i * stride] = key;
+    I[i * stride] = idx;
+    return K[0];
+}
+
 // ---- pack: candidates -> TF32 screen rows, tile by tile in the UMMA layout ------------------------------------------
-// packed[tile][chunk c = k / 4][row r < 256][k % 4], K' = 8 K8 columns: a tile is NCH x 4096 contiguous bytes.
-__global__ void __launch_bounds__(256) knn_tc5_pack_kernel(const double* __restrict__ x, int64_t n, int D, int K8,
+// packed[tile][chunk c = k / 4][row r < 128][k % 4], K' = 8 K8 columns: a tile is NCH x 2048 contiguous bytes.
+__global__ void __launch_bounds__(kN) knn_tc5_pack_kernel(const double* __restrict__ x, int64_t n, int D, int K8,
                                                            float* __restrict__ packed, float* __restrict__ xnmax_out) {
     const int64_t j = (int64_t)blockIdx.x * kN + threadIdx.x;     // one thread per candidate row of the tile
     const int NCH = 2 * K8;
@@ -146,43 +192,44 @@ __global__ void __launch_bounds__(256) knn_tc5_pack_kernel(const double* __restr
         tile[((size_t)(k >> 2) * kN + r) * 4 + (k & 3)] = val;
     }
     // largest |x - x0|^2 (error bound of the screen)
-    __shared__ float smax[8];
+    __shared__ float smax[kN / 32];
     float mx = j < n ? (float)sn : 0.f;
     for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     if ((threadIdx.x & 31) == 0) smax[threadIdx.x >> 5] = mx;
     __syncthreads();
     if (threadIdx.x == 0) {
-        for (int i = 1; i < 8; ++i) mx = fmaxf(mx, smax[i]);
+        for (int i = 1; i < kN / 32; ++i) mx = fmaxf(mx, smax[i]);
         atomicMax(reinterpret_cast<int*>(xnmax_out), __float_as_int(mx));   // non-negative floats order like ints
     }
 }
 
 template <int NL>
-constexpr size_t smem_bytes(int K8) {
+constexpr size_t smem_bytes(int K8, int kStages) {
     return 1024 /* alignment slack */ + (size_t)2 * K8 * kQ * 16 + (size_t)kStages * 2 * K8 * kN * 16 +
-           (size_t)kQ * 32 * NL * 8 + 256;
+           (size_t)kQ * 32 * NL * 8 + (size_t)kEpiWarps * 32 * 33 * 4 + 256;
 }
 
 template <int NL, bool ORDERED>
 __global__ void __launch_bounds__(kThreads, 1) knn_tc5_kernel(const double* __restrict__ q, int64_t M,
-                                                             const double* __restrict__ x, int64_t n, int D, int K8, int m,
-                                                             const float* __restrict__ packed,
+                                                             const double* __restrict__ x, int64_t n, int D, int K8,
+                                                             int kStages, int m, const float* __restrict__ packed,
                                                              const float* __restrict__ xnmax_in, int64_t* __restrict__ NN,
                                                              int ldnn, unsigned char* __restrict__ flags) {
     constexpr int LC = 32 * NL;
     extern __shared__ unsigned char raw_smem[];
     unsigned char* sm = reinterpret_cast<unsigned char*>(((uintptr_t)raw_smem + 1023) & ~(uintptr_t)1023);
     const int NCH = 2 * K8;                                        // 16-byte K chunks
-    float* sA = reinterpret_cast<float*>(sm);                      // [NCH][128][4]
-    float* sB = sA + (size_t)NCH * kQ * 4;                         // [stages][NCH][256][4]
-    float* ldist = sB + (size_t)kStages * NCH * kN * 4;            // [128][LC]
-    int* lidx = reinterpret_cast<int*>(ldist + (size_t)kQ * LC);   // [128][LC]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(lidx + (size_t)kQ * LC);
-    uint64_t* full = bars;               // [kStages] TMA -> MMA
-    uint64_t* empty = bars + kStages;    // [kStages] MMA -> TMA
-    uint64_t* tfull = bars + 2 * kStages;        // [2] MMA -> epilogue
-    uint64_t* tempty = bars + 2 * kStages + 2;   // [2] epilogue -> MMA
-    uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+    float* sA = reinterpret_cast<float*>(sm);                      // [group][NCH][128][4]
+    float* sB = sA + (size_t)kGroups * NCH * kQG * 4;              // [stages][NCH][128][4]
+    float* lkey = sB + (size_t)kStages * NCH * kN * 4;             // [LC][256] heap keys, slot-major
+    int* lidx = reinterpret_cast<int*>(lkey + (size_t)kQ * LC);    // [LC][256]
+    float* park = reinterpret_cast<float*>(lidx + (size_t)kQ * LC);   // [epilogue warp][32 lanes][33]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(park + (size_t)kEpiWarps * 32 * 33);
+    uint64_t* full = bars;                  // [kStages] TMA -> MMA
+    uint64_t* empty = bars + kMaxStages;    // [kStages] MMA -> TMA
+    uint64_t* tfull = bars + 2 * kMaxStages;        // [2] MMA -> epilogue
+    uint64_t* tempty = bars + 2 * kMaxStages + 2;   // [2] epilogue -> MMA
+    uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int64_t q0 = (int64_t)blockIdx.x * kQ;
     const int64_t cmax = ORDERED ? min(n, q0 + kQ) : n;
@@ -197,11 +244,11 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc5_kernel(const double* __re
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(&tfull[b], 1);
-            mbar_init(&tempty[b], 4);   // one arrival per epilogue warp
+            mbar_init(&tempty[b], kEpiWarps);   // one arrival per epilogue warp
         }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
-    if (w == 5) {   // TMEM: 512 columns = two 128 x 256 FP32 accumulators
+    if (w == kEpiWarps + 1) {   // TMEM: all 512 columns = 2 groups x 2 buffers of 128 x 128 FP32 accumulators
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_base_slot)),
                      "r"(512));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
@@ -221,10 +268,10 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc5_kernel(const double* __re
                 val = 1.f;
             }
         }
-        sA[((size_t)(k >> 2) * kQ + r) * 4 + (k & 3)] = val;
+        sA[(((size_t)(r / kQG) * NCH + (k >> 2)) * kQG + (r % kQG)) * 4 + (k & 3)] = val;
     }
     for (int i = tid; i < kQ * LC; i += kThreads) {
-        ldist[i] = INFINITY;
+        lkey[i] = INFINITY;
         lidx[i] = -1;
     }
     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic-proxy writes of sA -> visible to the MMA
@@ -233,40 +280,44 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc5_kernel(const double* __re
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
     const uint32_t tmem_base = *tmem_base_slot;
 
-    if (w == 4) {
-        // ===== TMA producer: one bulk copy per 256-candidate tile
+    if (w == kEpiWarps) {
+        // ===== TMA producer: one bulk copy per 128-candidate tile
         if (lane == 0) {
             for (int t = 0; t < ntiles; ++t) {
                 const int s = t % kStages;
-                if (t >= kStages) mbar_wait(&empty[s], ((t / kStages) - 1) & 1);
+                if (t >= kStages) mbar_wait_relaxed(&empty[s], ((t / kStages) - 1) & 1);
                 mbar_expect_tx(&full[s], tile_bytes);
                 tma_bulk_load(sB + (size_t)s * NCH * kN * 4, packed + (size_t)t * NCH * kN * 4, tile_bytes, &full[s]);
             }
         }
-    } else if (w == 5) {
-        // ===== MMA issuer: one thread, K8 instructions per tile into the TMEM buffer of the tile's parity
+    } else if (w == kEpiWarps + 1) {
+        // ===== MMA issuer: one thread, K8 instructions per tile and query group into the TMEM buffers of the tile's parity
         if (lane == 0) {
             const uint32_t a_base = smem_u32(sA);
             for (int t = 0; t < ntiles; ++t) {
                 const int s = t % kStages, b = t & 1;
-                if (t >= 2) mbar_wait(&tempty[b], ((t >> 1) - 1) & 1);   // the epilogue has drained this accumulator
-                mbar_wait(&full[s], (t / kStages) & 1);                  // the tile has landed
+                if (t >= 2) mbar_wait_relaxed(&tempty[b], ((t >> 1) - 1) & 1);   // the epilogue has drained these accumulators
+                mbar_wait_relaxed(&full[s], (t / kStages) & 1);                  // the tile has landed
                 asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
                 const uint32_t b_base = smem_u32(sB + (size_t)s * NCH * kN * 4);
-                for (int k8 = 0; k8 < K8; ++k8) {
-                    const uint64_t da = umma_desc(a_base + (uint32_t)(2 * k8) * kQ * 16, kQ * 16, 128);
-                    const uint64_t db = umma_desc(b_base + (uint32_t)(2 * k8) * kN * 16, kN * 16, 128);
-                    umma_tf32(tmem_base + (uint32_t)b * kN, da, db, k8 > 0);
-                }
+                for (int g = 0; g < kGroups; ++g)
+                    for (int k8 = 0; k8 < K8; ++k8) {
+                        const uint64_t da = umma_desc(a_base + (uint32_t)((g * NCH + 2 * k8) * kQG * 16), kQG * 16, 128);
+                        const uint64_t db = umma_desc(b_base + (uint32_t)(2 * k8) * kN * 16, kN * 16, 128);
+                        umma_tf32(tmem_base + (uint32_t)((g * 2 + b) * kN), da, db, k8 > 0);
+                    }
                 umma_commit(&empty[s]);    // the stage can be refilled once these MMAs have read it
-                umma_commit(&tfull[b]);    // ... and the accumulator is complete
+                umma_commit(&tfull[b]);    // ... and the accumulators are complete
             }
         }
     } else {
-        // ===== epilogue: warp w owns TMEM lanes [32 w, 32 w + 32) = queries q0 + 32 w + lane
-        const int ql = 32 * w + lane;
+        // ===== epilogue: warp w = (group g, lane quarter lq) owns TMEM lanes [32 lq, 32 lq + 32) of the group's buffers
+        const int g = w >> 2, lq = w & 3;
+        const int ql = kQG * g + 32 * lq + lane;
         const int64_t qi = q0 + ql;
         float thr = qi < M ? INFINITY : -INFINITY;
+        float* mypark = park + (size_t)w * 32 * 33;
+        const int qbase = kQG * g + 32 * lq;     // first query (CTA-local) of this warp
         for (int t = 0; t < ntiles; ++t) {
             const int b = t & 1;
             mbar_wait(&tfull[b], (t >> 1) & 1);
@@ -276,22 +327,22 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc5_kernel(const double* __re
             const int lim = qi < M ? (int)max((int64_t)0, min(jl, (int64_t)kN)) : 0;   // admissible columns of this tile
             for (int ch = 0; ch < kN / 32; ++ch) {
                 float v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(32 * w) << 16) + (uint32_t)(b * kN + 32 * ch), v);
+                tmem_ld32(tmem_base + ((uint32_t)(32 * lq) << 16) + (uint32_t)((g * 2 + b) * kN + 32 * ch), v);
+                unsigned mask = 0;
 #pragma unroll
-                for (int c = 0; c < 32; ++c) {
-                    const int col = 32 * ch + c;
-                    unsigned hm = __ballot_sync(0xffffffffu, v[c] < thr && col < lim);
-                    while (hm) {
-                        const int src = __ffs(hm) - 1;
-                        hm &= hm - 1;
-                        const float e = __shfl_sync(0xffffffffu, v[c], src);
-                        float tq = __shfl_sync(0xffffffffu, thr, src);
-                        const int qs = 32 * w + src;
-                        tq = dgpb::knn_list_insert_f<NL>(ldist + (size_t)qs * LC, lidx + (size_t)qs * LC, lane, e,
-                                                         (int)(c0 + col), tq);
-                        if (lane == src) thr = tq;
-                    }
+                for (int c = 0; c < 32; ++c) mask |= (v[c] < thr ? 1u : 0u) << c;
+                const int rem = lim - 32 * ch;
+                mask &= rem >= 32 ? 0xffffffffu : (rem <= 0 ? 0u : ((1u << rem) - 1u));
+                if (!__any_sync(0xffffffffu, mask != 0)) continue;
+#pragma unroll
+                for (int c = 0; c < 32; ++c) mypark[lane * 33 + c] = v[c];   // own row, stride 33: conflict-free
+                while (mask) {   // every lane with hits inserts into ITS query's heap, all at the same time
+                    const int c = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    const float e = mypark[lane * 33 + c];
+                    if (e < thr) thr = heap_replace_root<LC>(lkey + ql, lidx + ql, kQ, e, (int)(c0 + 32 * ch + c));
                 }
+                __syncwarp();
             }
             asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
             __syncwarp();
@@ -299,14 +350,10 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc5_kernel(const double* __re
         }
         // ---- exact FP64 ranking of the survivors, error-bound check (as the warp-level kernels)
         const float xnmax = *xnmax_in;
-        for (int qs = 32 * w; qs < 32 * w + 32; ++qs) {
+        for (int qs = qbase; qs < qbase + 32; ++qs) {
             const int64_t qq_i = q0 + qs;
             if (qq_i >= M) break;
-            float smaxf = 0.f;
-#pragma unroll
-            for (int e = 0; e < NL; ++e) smaxf = fmaxf(smaxf, ldist[(size_t)qs * LC + lane + 32 * e]);
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) smaxf = fmaxf(smaxf, __shfl_xor_sync(0xffffffffu, smaxf, o));
+            const float smaxf = lkey[qs];   // root of the heap = largest survivor (+inf while the set is not full)
             double qq = 0.0;
             for (int k = 0; k < D; ++k) {
                 const double vv = q[qq_i * D + k] - x[k];
@@ -314,14 +361,15 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc5_kernel(const double* __re
             }
             const double rr = sqrt(qq) + sqrt((double)xnmax);
             const double eps = 7.62939453125e-06 * rr * rr;   // 2^-17 (|q| + |x|max)^2
-            dgpb::knn_rank_and_write<NL, ORDERED>(q, x, qq_i, D, m, lidx + (size_t)qs * LC, (double)smaxf + qq - eps, NN,
-                                                  ldnn, flags, lane);
+            dgpb::knn_rank_and_write<NL, ORDERED>(q, x, qq_i, D, m, lidx + qs, (double)smaxf + qq - eps, NN, ldnn, flags,
+                                                  lane, kQ);
         }
     }
     // ---- teardown
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
     __syncthreads();
-    if (w == 5) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(512));
+    if (w == kEpiWarps + 1)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(512));
 }
 
 }  // namespace tc5
