@@ -62,12 +62,16 @@ class _GradBatcher:
     has one pending, then the last arrival runs the whole batch through `dgpb_nllik_grad_dense_batch` (on the
     workspace of the thread that started the M-step) and wakes the others."""
 
-    def __init__(self, nworkers, ws, dev):
+    def __init__(self, nworkers, ws, dev, shard=None):
         import threading
         self.cond = threading.Condition()
         self.active = nworkers
-        self.pending = []       # [node, n, P, result slot]
+        self.pending = []       # [node, n, P, result slot, request id]
         self.ws, self.dev = ws, dev
+        # one chain on several GPUs: (rank, world, torch.distributed).  Every rank runs every optimiser (identical
+        # numbers in, identical decisions out); the matrices of a round are dealt over the ranks and the results
+        # exchanged, so the ranks stay balanced however unevenly the optimisers finish.
+        self.shard = shard
         self.stats = [0, 0, 0.0]   # batched calls, matrices, seconds inside the library (bench.py's M-step breakdown)
 
     MAX_BATCH = 32   # MAXB of the library's batched launches (dense.cuh)
@@ -87,40 +91,54 @@ class _GradBatcher:
     def _flush_locked(self):
         from . import _lib as L
         reqs, self.pending = self.pending, []
+        reqs.sort(key=lambda r: r[4])     # the same order on every rank, whatever the thread timing
         try:
             n = reqs[0][1]
             if any(r[1] != n for r in reqs):
                 raise RuntimeError("nodes of one M-step must share the number of training points")
             L.torch_mod().cuda.set_device(self.dev)
+            ldo = max(r[2] for r in reqs) + 2
+            out = np.zeros((len(reqs), ldo + 1))          # last column: status
+            rank, world = (self.shard[0], self.shard[1]) if self.shard else (0, 1)
+            mine = [i for i in range(len(reqs)) if i % world == rank]
             step = self._chunk(n)
-            for lo in range(0, len(reqs), step):
-                part = reqs[lo:lo + step]
+            msg = ""
+            for lo in range(0, len(mine), step):
+                part = mine[lo:lo + step]
                 B = len(part)
-                ldo = max(r[2] for r in part) + 2
-                arr = (L.DgpbNode * B)(*[r[0] for r in part])
-                out = np.zeros((B, ldo))
+                arr = (L.DgpbNode * B)(*[reqs[i][0] for i in part])
+                res = np.zeros((B, ldo))
                 status = np.zeros(B, dtype=np.int32)
                 t0 = time.perf_counter()
-                rc = L.load().dgpb_nllik_grad_dense_batch(self.ws, arr, B, n, out.ctypes.data_as(L.c_vp), ldo,
+                rc = L.load().dgpb_nllik_grad_dense_batch(self.ws, arr, B, n, res.ctypes.data_as(L.c_vp), ldo,
                                                           status.ctypes.data_as(L.c_vp), L.stream())
                 self.stats[0] += 1
                 self.stats[1] += B
                 self.stats[2] += time.perf_counter() - t0
-                msg = L.load().dgpb_last_error().decode("utf-8", "replace") if rc != L.DGPB_OK else ""
-                for b, r in enumerate(part):
-                    r[3].extend([rc if rc != L.DGPB_OK else int(status[b]), out[b].copy(),
-                                 msg or "matrix %d of the batch is not positive definite" % (lo + b)])
+                if rc != L.DGPB_OK:
+                    msg = L.load().dgpb_last_error().decode("utf-8", "replace")
+                for b, i in enumerate(part):
+                    out[i, :ldo] = res[b]
+                    out[i, ldo] = rc if rc != L.DGPB_OK else int(status[b])
+            if world > 1:   # rows of the other ranks are zero here: one sum all-reduce hands every result to every rank
+                torch = L.torch_mod()
+                t = torch.from_numpy(out).to(L.device())
+                self.shard[2].all_reduce(t)
+                out = t.cpu().numpy()
+            for i, r in enumerate(reqs):
+                r[3].extend([int(out[i, ldo]), out[i, :ldo].copy(),
+                             msg or "matrix %d of the batch is not positive definite" % i])
         except Exception as exc:  # never leave the other optimiser threads waiting
             for r in reqs:
                 if not r[3]:
                     r[3].extend([L.DGPB_CUDA_ERROR, None, str(exc)])
         self.cond.notify_all()
 
-    def evaluate(self, node, n, P):
+    def evaluate(self, node, n, P, rid=0):
         from . import _lib as L
         slot = []
         with self.cond:
-            self.pending.append([node, n, P, slot])
+            self.pending.append([node, n, P, slot, rid])
             if len(self.pending) >= self.active:
                 self._flush_locked()
             else:
@@ -568,13 +586,23 @@ class dgp:
             self._m_step_sharded(nodes, ch)
 
     def _m_step_sharded(self, nodes, ch):
+        import os
+
         from . import parallel
 
         if ch is None:
             self._m_step_nodes(nodes)
             return
-        # one chain on several GPUs: the nodes are dealt over the ranks, every rank optimises its share and the
-        # results are exchanged (the reference deals the nodes of a layer to a process pool, dgp.py:1463-1467)
+        # One chain on several GPUs (the reference deals the nodes of a layer to a process pool, dgp.py:1463-1467).
+        # Dense nodes: every rank runs every optimiser and the EVALUATIONS of each round are dealt over the ranks
+        # (`_GradBatcher.shard`), so no rank waits for a slow optimiser it does not hold.  Other nodes (Vecchia): the
+        # nodes themselves are dealt, then the results are exchanged.
+        dense = [it for it in nodes if not it[1].vecch]
+        if len(dense) > 1 and self.n_data >= 128 and ch["device"] and os.environ.get('DGPB_MSTEP_BATCH', '1') != '0':
+            self._m_step_nodes(dense, shard=(ch["rank"], ch["world"], ch["dist"]))
+            nodes = [it for it in nodes if it[1].vecch]
+            if not nodes:
+                return
         mine = parallel.mstep_share(len(nodes), ch["rank"], ch["world"])
         failed = None
         try:
@@ -593,8 +621,9 @@ class dgp:
             raise failed if failed is not None else np.linalg.LinAlgError(
                 "a GP node optimised on another rank is not positive definite")
 
-    def _m_step_nodes(self, nodes):
-        """The M-step of the nodes in `nodes` ((layer index, kernel) pairs) on this GPU."""
+    def _m_step_nodes(self, nodes, shard=None):
+        """The M-step of the nodes in `nodes` ((layer index, kernel) pairs) on this GPU; with `shard` = (rank, world,
+        dist) every rank calls this with the SAME dense nodes and the evaluations are dealt over the ranks."""
         import os
         from concurrent.futures import ThreadPoolExecutor
 
@@ -607,8 +636,8 @@ class dgp:
         dense = [it for it in nodes if not it[1].vecch]
         # small models: an evaluation is a handful of microsecond kernels, the rendezvous of one host thread per node
         # would cost more than it saves; the nodes are optimised one after the other (same numbers either way)
-        batch = len(dense) > 1 and os.environ.get('DGPB_MSTEP_BATCH', '1') != '0' and \
-            (self.n_data >= 128 or os.environ.get('DGPB_MSTEP_BATCH') == '1')
+        batch = shard is not None or (len(dense) > 1 and os.environ.get('DGPB_MSTEP_BATCH', '1') != '0' and
+                                      (self.n_data >= 128 or os.environ.get('DGPB_MSTEP_BATCH') == '1'))
         if not batch:
             dense = []
         for l, kernel in nodes:   # nodes outside the batch
@@ -622,7 +651,9 @@ class dgp:
         if not dense:
             return
         torch.cuda.current_stream().synchronize()
-        batcher = _GradBatcher(len(dense), L.workspace(), dev)
+        batcher = _GradBatcher(len(dense), L.workspace(), dev, shard)
+        for rid, (_, kernel) in enumerate(dense):
+            kernel._mid = rid        # request id: the rounds are ordered by it on every rank
 
         def work(item):
             l, kernel = item

@@ -98,7 +98,7 @@ class kernel:
         state = dict(self.__dict__)
         state['Rinv'] = _as_numpy(state.pop('_Rinv'))
         state['Rinv_y'] = _as_numpy(state.pop('_Rinv_y'))
-        for key in ('_dcache', '_batcher', '_vcache', '_frozen', '_Xcat', '_ycol'):
+        for key in ('_dcache', '_batcher', '_vcache', '_frozen', '_Xcat', '_ycol', '_mid'):
             state.pop(key, None)
         return state
 
@@ -306,7 +306,7 @@ class kernel:
         P = len(self.length) + (1 if self.nugget_est else 0)
         batcher = getattr(self, '_batcher', None)
         if batcher is not None:
-            out = batcher.evaluate(node, self.input.shape[0], P)   # batched with the other nodes of the M-step
+            out = batcher.evaluate(node, self.input.shape[0], P, getattr(self, '_mid', 0))   # batched with the other nodes
         else:
             out = L.host_doubles(P + 2)
             L.check(L.load().dgpb_nllik_grad_dense(L.workspace(), ctypes.byref(node), self.input.shape[0], out,
