@@ -1218,6 +1218,9 @@ int dgpb_tune(const char* key, int value) {
         g_ess_prefetch = value != 0;
     } else if (k == "ess_overlap") {
         g_ess_overlap = value != 0;
+    } else if (k == "ess_wave_total") {
+        DGPB_REQUIRE(value >= 1 && value <= 64, "ess_wave_total out of range");
+        g_ess_wave_total = value;
     } else if (k == "ess_trsv") {
         g_ess_cached_threshold = value != 0;
     } else if (k == "linkgp_matern_tab") {

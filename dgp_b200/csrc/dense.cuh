@@ -84,5 +84,6 @@ extern int g_ess_target_b;
 extern int g_ess_cached_threshold;
 extern int g_ess_prefetch;
 extern int g_ess_overlap;
+extern int g_ess_wave_total;
 
 }  // namespace dgpb

@@ -579,6 +579,7 @@ static int join_wave_staging(Workspace* ws, cudaStream_t st) {
 }
 
 namespace dgpb {
+int g_ess_wave_total = 8;   // candidates per wave aimed at when several GPUs share it (dgpb_tune "ess_wave_total")
 // Factor the next single-candidate wave while the current one drains its tail (dgpb_tune "ess_overlap").  Measured on
 // BASELINE config 3 (n = 5000, B200): two waves in flight raise the FLOP rate issued from 59.7 % to 63.4 % of the DGEMM
 // peak, and the wave that is in flight at every acceptance (one in ~17 for the 8-node layer pair) costs the same
@@ -623,6 +624,10 @@ extern "C" int dgpb_ess_block_cached(dgpb_ws* ws, const dgpb_node* targets, int 
     // ranks that share a wave; Vecchia or oversized upper layers are evaluated by every rank (same numbers everywhere)
     const int W = batched ? ws->comm.world : 1;
     const int me = batched ? ws->comm.rank : 0;
+    // several GPUs: W ranks already multiply the candidates of a wave; beyond ~g_ess_wave_total candidates per wave the
+    // extra ones are almost always behind the accepted one, so each rank takes fewer and its batch gets smaller (a
+    // 2-node upper layer on 8 GPUs: one candidate = 2 matrices per rank, 6 ms instead of 15 ms for 4 candidates)
+    if (W > 1) cap = std::max(1, std::min(cap, (g_ess_wave_total + W - 1) / W));
     const int nslots = cap + 1;   // local proposal images per wave (rank 0 may carry the threshold item as slot 0)
     // factor the next wave ahead of the decision: single-candidate waves on one GPU (NCCL calls of two waves in
     // flight would have to be ordered across ranks, and multi-candidate waves accept too often for the bet to pay)
