@@ -98,7 +98,7 @@ class kernel:
         state = dict(self.__dict__)
         state['Rinv'] = _as_numpy(state.pop('_Rinv'))
         state['Rinv_y'] = _as_numpy(state.pop('_Rinv_y'))
-        for key in ('_dcache', '_batcher', '_vcache', '_frozen', '_Xcat', '_ycol', '_mid'):
+        for key in ('_dcache', '_batcher', '_vcache', '_frozen', '_Xcat', '_ycol', '_mid', '_nfev', '_r2_fresh'):
             state.pop(key, None)
         return state
 
@@ -183,6 +183,7 @@ class kernel:
                 self.R2 = np.atleast_2d(rsq)
             else:
                 self.R2 = np.vstack((self.R2, rsq))
+            self._r2_fresh = True
 
     def ord_nn(self, ord=None, NNarray=None, pointer=False):
         """Vecchia ordering and ordered nearest neighbours (kernel_class.py:245-267); the neighbour search
@@ -404,7 +405,8 @@ class kernel:
                             (L.to_dev(X[self.ord]), L.to_dev(np.ascontiguousarray(self.output[self.ord, 0])),
                              L.to_dev(self.NNarray, np.int64)))
         try:
-            minimize(fun, x0, method=method, jac=True, options=budget, **kwargs)
+            res = minimize(fun, x0, method=method, jac=True, options=budget, **kwargs)
+            self._nfev = int(getattr(res, 'nfev', 0))   # next M-step's load balancing on several GPUs
         finally:
             self._dcache = None
             self._vcache = None

@@ -64,10 +64,21 @@ def chain():
     return _chain
 
 
-def mstep_share(n_nodes, rank, world):
-    """Indices of the GP nodes whose L-BFGS-B run this rank carries in an M-step: round-robin over all layers (given
-    the imputation the nodes are independent; the reference deals the nodes of one layer to a process pool)."""
-    return list(range(rank, n_nodes, world))
+def mstep_share(n_nodes, rank, world, costs=None):
+    """Indices of the GP nodes whose L-BFGS-B run this rank carries in an M-step (given the imputation the nodes
+    are independent; the reference deals the nodes of one layer to a process pool).  Without `costs`: round-robin
+    over all layers.  With `costs` (one number per node: its objective evaluations in the previous M-step, known to
+    every rank): longest-processing-time-first, so the optimiser that needs the most rounds does not share its rank
+    with other slow ones.  Every rank computes the same assignment."""
+    if costs is None or len(costs) != n_nodes:
+        return list(range(rank, n_nodes, world))
+    load, mine = [0.0] * world, []
+    for i in sorted(range(n_nodes), key=lambda i: (-float(costs[i]), i)):
+        r = min(range(world), key=lambda r: (load[r], r))
+        load[r] += max(1.0, float(costs[i]))
+        if r == rank:
+            mine.append(i)
+    return sorted(mine)
 
 
 def _allreduce_sum(arr):
@@ -83,7 +94,7 @@ def _allreduce_sum(arr):
     return t.cpu().numpy()
 
 
-_PAR_W = 3 + 32   # scale, nugget, len(length), length[<= 32]
+_PAR_W = 5 + 32 + 32   # scale, nugget, len(length), objective evaluations, len(R2 row), length[<= 32], R2 row[<= 32]
 
 
 def sync_params(kernels, mine, failed):
@@ -95,7 +106,13 @@ def sync_params(kernels, mine, failed):
     for i in mine:
         k = kernels[i]
         buf[i, 0], buf[i, 1], buf[i, 2] = k.scale[0], k.nugget[0], len(k.length)
-        buf[i, 3:3 + len(k.length)] = k.length
+        buf[i, 3] = getattr(k, '_nfev', 0)
+        buf[i, 5:5 + len(k.length)] = k.length
+        r2 = getattr(k, 'R2', None)
+        if r2 is not None and getattr(k, '_r2_fresh', False):   # the row the owner appended in this M-step
+            row = np.atleast_2d(r2)[-1]
+            buf[i, 4] = len(row)
+            buf[i, 37:37 + len(row)] = row
     buf[-1, 0] = 1.0 if failed else 0.0
     out = _allreduce_sum(buf)
     if out[-1, 0] > 0:
@@ -107,7 +124,12 @@ def sync_params(kernels, mine, failed):
         nl = int(round(out[i, 2]))
         k.scale = np.array([out[i, 0]])
         k.nugget = np.array([out[i, 1]])
-        k.length = out[i, 3:3 + nl].copy()
+        k.length = out[i, 5:5 + nl].copy()
+        k._nfev = int(round(out[i, 3]))
+        nr = int(round(out[i, 4]))
+        if nr:   # R2 of the regression on the global input (kernel.r2): computed by the owner, appended here
+            row = out[i, 37:37 + nr].copy()
+            k.R2 = np.atleast_2d(row) if k.R2 is None else np.vstack((k.R2, row))
         k.add_to_path()
     return False
 

@@ -59,6 +59,7 @@ class _FakeKernel:
         self.scale, self.nugget = np.array([1.0]), np.array([1e-6])
         self.length = np.ones(1 + i % 3)
         self.path = []
+        self.R2 = None
 
     def add_to_path(self):
         self.path.append(np.concatenate((self.scale, self.length, self.nugget)))
@@ -97,6 +98,12 @@ def test_mstep_shares_and_parameter_handover(tmp_path, fail_rank):
             shares = [mstep_share(n_nodes, r, world) for r in range(world)]
             assert sorted(i for s in shares for i in s) == list(range(n_nodes))
             assert max(map(len, shares)) - min(map(len, shares)) <= 1
+            # with the evaluation counts of the previous M-step: every node exactly once, loads within one node's cost
+            costs = [3 + (7 * i) % 11 for i in range(n_nodes)]
+            shares = [mstep_share(n_nodes, r, world, costs) for r in range(world)]
+            assert sorted(i for s in shares for i in s) == list(range(n_nodes))
+            loads = [sum(costs[i] for i in s) for s in shares]
+            assert max(loads) - min(loads) <= max(costs)
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
