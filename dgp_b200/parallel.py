@@ -72,10 +72,15 @@ def mstep_share(n_nodes, rank, world, costs=None):
     with other slow ones.  Every rank computes the same assignment."""
     if costs is None or len(costs) != n_nodes:
         return list(range(rank, n_nodes, world))
-    load, mine = [0.0] * world, []
+    # A rank's M-step is a sequence of rounds (one batched evaluation each): as many as its slowest optimiser needs,
+    # and a round costs a fixed part plus a part per matrix (measured at n = 5000: ~6.5 ms + ~3 ms per matrix).  Greedy
+    # on that estimate, longest optimiser first; ties go to the lowest rank so every rank computes the same answer.
+    FIXED, PER = 6.5, 3.0
+    top, tot, mine = [0.0] * world, [0.0] * world, []
     for i in sorted(range(n_nodes), key=lambda i: (-float(costs[i]), i)):
-        r = min(range(world), key=lambda r: (load[r], r))
-        load[r] += max(1.0, float(costs[i]))
+        c = max(1.0, float(costs[i]))
+        r = min(range(world), key=lambda r: (FIXED * max(top[r], c) + PER * (tot[r] + c), r))
+        top[r], tot[r] = max(top[r], c), tot[r] + c
         if r == rank:
             mine.append(i)
     return sorted(mine)

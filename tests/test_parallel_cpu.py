@@ -102,8 +102,9 @@ def test_mstep_shares_and_parameter_handover(tmp_path, fail_rank):
             costs = [3 + (7 * i) % 11 for i in range(n_nodes)]
             shares = [mstep_share(n_nodes, r, world, costs) for r in range(world)]
             assert sorted(i for s in shares for i in s) == list(range(n_nodes))
-            loads = [sum(costs[i] for i in s) for s in shares]
-            assert max(loads) - min(loads) <= max(costs)
+            est = [6.5 * max([costs[i] for i in s] or [0]) + 3.0 * sum(costs[i] for i in s) for s in shares]
+            # list-scheduling bound under the cost model: slowest optimiser's rounds + (average + one node) of matrices
+            assert max(est) <= 6.5 * max(costs) + 3.0 * (sum(costs) / world + max(costs)) + 1e-9
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
