@@ -90,6 +90,8 @@ _PROTOS = {
                                             c_vp]),
     "dgpb_vecchia_mvn_draw": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_dbl, c_dbl,
                                              ctypes.c_int, c_vp, c_vp, c_vp]),
+    "dgpb_hetero_vecchia_draw": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_dbl, ctypes.c_int, c_vp,
+                                                c_vp, c_vp, c_vp, c_vp, c_vp]),
     "dgpb_gp_vecch": (ctypes.c_int, [c_vp, c_i64, c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_i64, c_dbl, c_dbl,
                                      c_vp, ctypes.c_int, c_vp, c_vp, c_vp]),
     "dgpb_gp_vecch_multi": (ctypes.c_int, [c_vp, c_i64, c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, ctypes.c_int, c_vp, c_vp,

@@ -786,6 +786,108 @@ int vecchia_llik_device(Workspace* ws, const VKern& vk, const double* X, const d
     return DGPB_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Exact conditional draw of the MEAN process under a heteroskedastic Gaussian likelihood with the Vecchia
+// approximation (latent Vecchia: imputation.py:141-158, U_matrix / U_matrix_sp vecchia.py:426-445,612-622,
+// Hetero.post_het_vecch likelihood_class.py:165-183).  2n variables: y_j (index j < n, observed, noise Gamma_j)
+// and f_j (index j + n, latent).  Row i of imp_NN = [i + n, i, neighbours]: f_i conditioned on y_i, on the latent
+// values of its neighbours that come EARLIER in the ordering (index + n) and on the observations of those that come
+// later.  Per row: K = scale corr(x) (nugget 0) + diag(Gamma on the observed entries + 1e-10), u = chol(K)^-T e_last.
+//   U[i][c] (entry of imp_NN[i][c]) is written in imp_NN's own order; the latent entries of row i form row i of the
+//   lower-triangular L = U_latent^T (diagonal = c 0), compacted into (depL, depNN, cnt) for the sparse solve;
+//   rhs[i] = sd[i] - sum over observed entries U[i][c] y[imp_NN[i][c]]      (one solve gives mu + sample)
+// One warp per row.
+// ------------------------------------------------------------------------------------------------
+__global__ void hetero_u_kernel(VKern vk, const double* __restrict__ X, const int64_t* __restrict__ NN, int64_t n, int m1,
+                                double scale, const double* __restrict__ gamma, const double* __restrict__ y,
+                                const double* __restrict__ sd, double* __restrict__ Uout, double* __restrict__ depL,
+                                int64_t* __restrict__ depNN, int* __restrict__ cnt, double* __restrict__ rhs, int per_warp) {
+    extern __shared__ double smem[];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, W = blockDim.x >> 5;
+    const int64_t i = (int64_t)blockIdx.x * W + w;
+    if (i >= n) return;
+    double* base = smem + (size_t)w * per_warp;
+    double* A = base;                                  // packed K -> L       m1(m1+1)/2
+    double* xl = A + m1 * (m1 + 1) / 2;                // scaled coords       m1 * D
+    double* nug = xl + m1 * vk.D;                      // diagonal additions  m1
+    double* bv = nug + m1;                             // L^-T e_last         m1
+    int* idx = reinterpret_cast<int*>(bv + m1);        // entries, reversed: the latent f_i itself last
+    int b = 0;
+    for (int c = 0; c < m1; ++c) b += NN[i * m1 + c] >= 0;
+    for (int c = lane; c < b; c += 32) idx[c] = (int)NN[i * m1 + (b - 1 - c)];
+    __syncwarp();
+    for (int p = lane; p < b * vk.D; p += 32) {
+        const int r = p / vk.D, k = p % vk.D;
+        xl[p] = X[(int64_t)(idx[r] % n) * vk.D + k] / vk.len[k];
+    }
+    for (int c = lane; c < b; c += 32) {
+        const bool latent = idx[c] >= n;
+        nug[c] = ((latent ? 0.0 : gamma[idx[c]]) + 1e-10) / scale;    // K / scale = corr + diag(...) / scale
+        bv[c] = (c == b - 1) ? 1.0 : 0.0;
+    }
+    __syncwarp();
+    warp_build_K(vk, xl, b, nug, A, lane);
+    warp_chol(A, b, lane);
+    warp_bwd(A, bv, b, lane);
+    const double rs = 1.0 / sqrt(scale);                // chol(scale M) = sqrt(scale) chol(M)
+    if (Uout)
+        for (int c = lane; c < m1; c += 32) Uout[i * m1 + c] = c < b ? bv[b - 1 - c] * rs : 0.0;
+    if (lane == 0) {
+        int k = 0;
+        double acc = sd[i];
+        for (int c = 0; c < b; ++c) {                  // c in imp_NN order: entry c lives at bv[b - 1 - c]
+            const int e = idx[b - 1 - c];
+            const double u = bv[b - 1 - c] * rs;
+            if (e >= n) {
+                depL[i * m1 + k] = u;
+                depNN[i * m1 + k] = e - n;
+                ++k;
+            } else {
+                acc -= u * y[e];
+            }
+        }
+        cnt[i] = k;
+        rhs[i] = acc;
+    }
+}
+
+// sp_solve_kernel with an explicit number of entries per row (entry 0 = the diagonal)
+__global__ void __launch_bounds__(256) sp_solve_cnt_kernel(const double* __restrict__ L, const int64_t* __restrict__ NN,
+                                                           const int* __restrict__ cnt, int64_t n, int m1,
+                                                           const double* __restrict__ z, double* x, unsigned int* ticket) {
+    __shared__ unsigned int s_blk;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, W = blockDim.x >> 5;
+    if (threadIdx.x == 0) s_blk = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const int64_t i = (int64_t)s_blk * W + w;
+    if (i >= n) return;
+    const int kmax = cnt[i];
+    double s = 0.0;
+    for (int j = 1 + lane; j < kmax; j += 32) {
+        const int64_t dep = NN[i * m1 + j];
+        const double lij = L[i * m1 + j];
+        double xd = NAN;
+        if (dep >= 0 && dep < i) {   // a dependency is always an earlier row; anything else poisons instead of hanging
+            const volatile unsigned long long* px = reinterpret_cast<const volatile unsigned long long*>(x + dep);
+            unsigned long long bits = *px;
+            int spins = 0;
+            while (bits == kSpSentinel && ++spins < (1 << 22)) {
+                __nanosleep(40);
+                bits = *px;
+            }
+            if (bits != kSpSentinel) xd = __longlong_as_double((long long)bits);
+        }
+        s += lij * xd;
+    }
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) {
+        double r = (z[i] - s) / L[i * m1];
+        unsigned long long rb = (unsigned long long)__double_as_longlong(r);
+        if (rb == kSpSentinel) rb = 0x7ff8000000000000ULL;
+        *reinterpret_cast<volatile unsigned long long*>(x + i) = rb;
+    }
+}
+
 int vecchia_mvn_draw_device(Workspace* ws, const VKern& vk, const double* X, const int64_t* NN, int64_t n, int64_t m1,
                             double scale, double nugget, const double* z, double* out, cudaStream_t st) {
     void *Lm, *flags;
@@ -895,6 +997,45 @@ int dgpb_vecchia_mvn_draw(const double* X, const int64_t* NN, int64_t n, int64_t
     dgpb_ws* ws;
     DGPB_TRY(get_tls_ws(&ws));
     return vecchia_mvn_draw_device(ws, vk, X, NN, n, m1, scale, nugget, z, out, (cudaStream_t)stream);
+}
+
+int dgpb_hetero_vecchia_draw(const double* X, const int64_t* imp_NN, int64_t n, int64_t D, int64_t m1,
+                             const double* length_host, int64_t nlen, double scale, int kind, const double* gamma,
+                             const double* y, const double* sd, double* f_out, double* U_out, void* stream) {
+    DGPB_NVTX("dgpb:hetero_vecchia_draw");
+    cudaStream_t st = (cudaStream_t)stream;
+    DGPB_REQUIRE(X && imp_NN && gamma && y && sd && f_out, "NULL argument");
+    DGPB_REQUIRE(n >= 1 && m1 >= 2 && m1 <= 128 && scale > 0.0, "bad sizes");
+    VKern vk;
+    DGPB_TRY(make_vkern(kind, D, length_host, nlen, &vk));
+    dgpb_ws* ws;
+    DGPB_TRY(get_tls_ws(&ws));
+    void *pL, *pN, *pmisc, *pflag;
+    DGPB_TRY(ws->reserve(SLOT_VL, sizeof(double) * (size_t)n * m1, &pL));
+    DGPB_TRY(ws->reserve(SLOT_MISC, sizeof(int64_t) * (size_t)n * m1, &pN));
+    DGPB_TRY(ws->reserve(SLOT_MISC2, (sizeof(double) + sizeof(int)) * (size_t)n + 64, &pmisc));
+    DGPB_TRY(ws->reserve(SLOT_VFLAG, sizeof(int) * 8, &pflag));
+    double* rhs = (double*)pmisc;
+    int* cnt = reinterpret_cast<int*>(rhs + n);
+    const int W = 4;
+    const int per_warp = (int)(m1 * (m1 + 1) / 2 + m1 * vk.D + 2 * m1 + (m1 + 1) / 2 + 2);
+    const size_t smem = sizeof(double) * (size_t)per_warp * W;
+    DGPB_REQUIRE(smem <= 200 * 1024, "conditioning set too large for the block kernel");
+    static size_t configured = 0;
+    if (smem > configured) {
+        DGPB_CUDA_TRY(cudaFuncSetAttribute(hetero_u_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    hetero_u_kernel<<<(unsigned)cdiv(n, W), W * 32, smem, st>>>(vk, X, imp_NN, n, (int)m1, scale, gamma, y, sd, U_out,
+                                                               (double*)pL, (int64_t*)pN, cnt, rhs, per_warp);
+    DGPB_LAUNCHED();
+    unsigned int* ticket = (unsigned int*)pflag;
+    sp_fill_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(reinterpret_cast<unsigned long long*>(f_out), n, ticket);
+    DGPB_LAUNCHED();
+    sp_solve_cnt_kernel<<<(unsigned)cdiv(n, 8), 8 * 32, 0, st>>>((double*)pL, (int64_t*)pN, cnt, n, (int)m1, rhs, f_out,
+                                                                ticket);
+    DGPB_LAUNCHED();
+    return DGPB_OK;
 }
 
 int dgpb_gp_vecch(const double* x, int64_t M, const double* w, const double* y, int64_t n, int64_t D, const int64_t* NN,

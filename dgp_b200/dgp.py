@@ -201,8 +201,6 @@ class dgp:
                                                   "likelihood nodes only")
                     if node.name not in L.LIK_KIND:
                         raise NotImplementedError("dgp_b200: likelihood '%s' is outside the SI hot path" % node.name)
-                    if vecchia and node.exact_post_idx is not None:
-                        raise NotImplementedError("dgp_b200: the exact Hetero posterior under Vecchia is not built")
         top = self.all_layer[-1][0]
         if getattr(top, 'name', None) == 'Categorical':   # dgp.py:112-121
             from sklearn.preprocessing import LabelEncoder
@@ -336,18 +334,29 @@ class dgp:
             return KernelPCA(n_components=width, kernel='sigmoid').fit_transform(In)
         return np.concatenate((In, In[:, np.random.choice(d, width - d)]), 1)
 
-    def _share_or_draw_ord(self, layer, k):
+    def _needs_pointer(self, l, k):
+        """dgp.py:632-639: the node is the mean process of a Hetero likelihood (its exact conditional draw under the
+        Vecchia approximation needs the latent-Vecchia conditioning sets, kernel.ord_nn(pointer=True))."""
+        if l != self.n_layer - 2:
+            return False
+        linked = [lk for lk in self.all_layer[l + 1] if lk.input_dim is None or k in lk.input_dim]
+        if len(linked) != 1 or linked[0].type != 'likelihood' or linked[0].exact_post_idx is None:
+            return False
+        idx = np.where(np.asarray(linked[0].input_dim) == k)[0] if linked[0].input_dim is not None else np.array([k])
+        return bool(np.isin(idx, linked[0].exact_post_idx).all()) and len(idx) > 0
+
+    def _share_or_draw_ord(self, layer, k, pointer=False):
         kernel = layer[k]
         for j in range(k):
             same = np.array_equal(kernel.input_dim, layer[j].input_dim) and np.array_equal(kernel.connect,
                                                                                            layer[j].connect)
             if len(kernel.length) == 1 and same and len(layer[j].length) == 1:
-                kernel.ord_nn(ord=layer[j].ord, NNarray=layer[j].NNarray)
+                kernel.ord_nn(ord=layer[j].ord, NNarray=layer[j].NNarray, pointer=pointer)
                 return
             if len(kernel.length) != 1 and same and np.array_equal(kernel.length, layer[j].length):
-                kernel.ord_nn(ord=layer[j].ord.copy(), NNarray=layer[j].NNarray.copy())
+                kernel.ord_nn(ord=layer[j].ord.copy(), NNarray=layer[j].NNarray.copy(), pointer=pointer)
                 return
-        kernel.ord_nn()
+        kernel.ord_nn(pointer=pointer)
 
     def _wire(self, first_time, reset_row=None):
         In = self.X
@@ -382,7 +391,7 @@ class dgp:
                     hyp = kernel.para_path[reset_row, :]
                     kernel.scale, kernel.length, kernel.nugget = hyp[[0]], hyp[1:-1], hyp[[-1]]
                 if kernel.vecch:
-                    self._share_or_draw_ord(layer, k)
+                    self._share_or_draw_ord(layer, k, self._needs_pointer(l, k))
                 kernel.output = self.Y[:, [k]] if last else Out[:, [k]].copy()
                 if kernel.prior_name == 'ref':
                     if first_time:
@@ -453,7 +462,7 @@ class dgp:
             kernel.global_input = (self.X[:, kernel.connect]).copy()
         kernel.m = self.m
         if kernel.vecch:
-            self._share_or_draw_ord(layer, k)
+            self._share_or_draw_ord(layer, k, kernel.imp_pointer_row is not None)
         if last:
             kernel.output = (self.Y[:, [k]]).copy()
         if kernel.prior_name == 'ref':
@@ -509,17 +518,15 @@ class dgp:
         """Convert the DGP structure to the Vecchia mode (dgp.py:693-746)."""
         if self.vecch:
             raise Exception('The DGP structure is already in Vecchia mode.')
-        if any(getattr(k, 'exact_post_idx', None) is not None for k in self.all_layer[-1]):
-            raise NotImplementedError("dgp_b200: the exact Hetero posterior under Vecchia is not built")
         self.vecch = True
         self.m = min(m, self.n_data - 1)
         self.ord_fun = ord_fun
-        for layer in self.all_layer:
+        for l, layer in enumerate(self.all_layer):
             for k, kernel in enumerate(layer):
                 if kernel.type != 'gp':
                     continue
                 kernel.vecch, kernel.m, kernel.ord_fun = self.vecch, self.m, self.ord_fun
-                self._share_or_draw_ord(layer, k)
+                self._share_or_draw_ord(layer, k, self._needs_pointer(l, k))
 
     def remove_vecchia(self):
         """Remove the Vecchia mode from the DGP structure (dgp.py:748-758)."""

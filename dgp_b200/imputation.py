@@ -56,8 +56,6 @@ class _DeviceLayers:
                 for kern in layer:
                     if kern.name not in L.LIK_KIND:
                         raise NotImplementedError("dgp_b200: likelihood '%s' is outside the SI hot path" % kern.name)
-                    if any(k.vecch for k in all_layer[l - 1]) and kern.exact_post_idx is not None:
-                        raise NotImplementedError("dgp_b200: the exact Hetero posterior under Vecchia is not built")
                     y = L.to_dev(np.ascontiguousarray(kern.output[:, 0], dtype=np.float64))
                     self.keep.append(y)
                     self.liks.append((kern, kern._descriptor(kern.input_dim, y), y))
@@ -150,9 +148,20 @@ class _DeviceLayers:
         `sd` (n x 2 standard normals) defaults to the reference's own draw."""
         kern, desc, y = self.liks[j]
         row_var = int(kern.input_dim[1])
-        if sd is None:
-            sd = np.random.randn(self.n, 2)                # likelihood_class.py:200
-        f = kern.posterior_dev(self.nodes[l][k], self.n, self.F[l][row_var], y, sd)
+        target = self.all_layer[l][k]
+        if target.vecch:   # latent-Vecchia draw (imputation.py:141-158); the reference draws np.random.randn(n)
+            if target.imp_NNarray is None:
+                raise RuntimeError("dgp_b200: the mean node of a Hetero likelihood needs ord_nn(pointer=True)")
+            if sd is None:
+                sd = np.random.randn(self.n)               # likelihood_class.py:178
+            # the node's inputs may be latent themselves: take them from the device image of the layer below
+            if l > 0:
+                target.input = np.ascontiguousarray(L.to_host(self.F[l - 1])[np.atleast_1d(target.input_dim)].T)
+            f = kern.posterior_vecch_dev(target, self.n, self.F[l][row_var], y, sd)
+        else:
+            if sd is None:
+                sd = np.random.randn(self.n, 2)            # likelihood_class.py:200
+            f = kern.posterior_dev(self.nodes[l][k], self.n, self.F[l][row_var], y, sd)
         self.F[l][k].copy_(f)
 
     def block_update(self, l, tks, uks, max_u=64):
@@ -326,9 +335,10 @@ class imputer:
                     if ok:
                         match = layer[j]
                         break
+                pointer = kernel.imp_pointer_row is not None      # imputation.py:241
                 if match is None:
-                    kernel.ord_nn()
+                    kernel.ord_nn(pointer=pointer)
                 elif len(kernel.length) == 1:
-                    kernel.ord_nn(ord=match.ord, NNarray=match.NNarray)
+                    kernel.ord_nn(ord=match.ord, NNarray=match.NNarray, pointer=pointer)
                 else:
-                    kernel.ord_nn(ord=match.ord.copy(), NNarray=match.NNarray.copy())
+                    kernel.ord_nn(ord=match.ord.copy(), NNarray=match.NNarray.copy(), pointer=pointer)

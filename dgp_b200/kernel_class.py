@@ -188,8 +188,6 @@ class kernel:
     def ord_nn(self, ord=None, NNarray=None, pointer=False):
         """Vecchia ordering and ordered nearest neighbours (kernel_class.py:245-267); the neighbour search
         runs on the GPU (exact FP64 brute force, bit-exact with the reference's exact kNN)."""
-        if pointer:
-            raise NotImplementedError("dgp_b200: imputation pointers (Hetero exact posterior) are out of scope")
         X = self._X() / self.length
         if ord is None:
             self.ord = np.random.permutation(self.input.shape[0]) if self.ord_fun is None else self.ord_fun(X)
@@ -201,6 +199,21 @@ class kernel:
             self.NNarray = nn(X[self.ord], self.m)
         else:
             self.NNarray = NNarray
+        if pointer:
+            # conditioning sets of the latent-Vecchia draw of a mean process under a Hetero likelihood
+            # (kernel_class.py:268-275): point i of the ordering -> [f_i (index i + n), y_i (index i), its m - 1
+            # nearest other points: as latent values (index + n) when they come earlier in the ordering, as
+            # observations when they come later]
+            from .vecchia import get_pred_nn
+            Xo = np.ascontiguousarray(X[self.ord])
+            n = Xo.shape[0]
+            NNs = get_pred_nn(Xo, Xo, self.m)[:, 1:]
+            prev = NNs < np.arange(n)[:, None]
+            NNs = np.where(prev, NNs + n, NNs)
+            self.imp_NNarray = np.hstack((np.arange(n).reshape(-1, 1) + n, np.arange(n).reshape(-1, 1), NNs))
+            # the reference also keeps COO pointers of the sparse U (imp_pointers, vecchia.py:462-476); here the
+            # entries stay in imp_NNarray's own order, so only their presence is recorded
+            self.imp_pointer_row = self.imp_pointer_col = True
 
     def log_t(self):
         if self.nugget_est:

@@ -120,6 +120,28 @@ class Hetero(_Likelihood):
                                                L.stream()))
         return y - w - shift * x                          # G x_true = (G / scale) x
 
+    @staticmethod
+    def posterior_vecch_dev(kern, n, log_var, y, sd):
+        """Draw of the mean process under the Vecchia approximation (imputation.py:141-158, U_matrix_sp,
+        post_het_vecch): `dgpb_hetero_vecchia_draw` on the inputs, outputs and variances gathered in Vecchia order.
+        kern: the GP node of the mean (a `dgp_b200.kernel` with `imp_NNarray`); log_var, y: device vectors in data
+        order; sd: n standard normals (host).  Returns the draw in data order (device)."""
+        torch = L.torch_mod()
+        ordd = L.to_dev(kern.ord, np.int64)
+        Xo = L.to_dev(np.ascontiguousarray(kern._X()[kern.ord]))
+        NN = L.to_dev(np.ascontiguousarray(kern.imp_NNarray), np.int64)
+        gamma = torch.exp(log_var).index_select(0, ordd).contiguous()
+        yo = y.index_select(0, ordd).contiguous()
+        z = L.to_dev(np.ascontiguousarray(sd, dtype=np.float64))
+        f = L.empty((n,))
+        larr, lptr = L.length_host(kern.length)
+        L.check(L.load().dgpb_hetero_vecchia_draw(L.ptr(Xo), L.ptr(NN), n, Xo.shape[1], NN.shape[1], lptr, len(larr),
+                                                  float(kern.scale[0]), L.KIND[kern.name], L.ptr(gamma), L.ptr(yo),
+                                                  L.ptr(z), L.ptr(f), None, L.stream()))
+        out = torch.empty_like(f)
+        out.index_copy_(0, ordd, f)     # f[rev_ord]
+        return out
+
     def posterior(self, idx, v_node):
         """Host-facing form of `Hetero.posterior` (likelihood_class.py:134-151): `v_node` is the GP node (a
         `dgp_b200.kernel`) that produces the mean; returns the drawn mean vector."""

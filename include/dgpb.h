@@ -242,6 +242,17 @@ int dgpb_vecchia_mvn_draw(const double* X, const int64_t* NN, int64_t n, int64_t
                           const double* length_host, int64_t nlen, double scale, double nugget, int kind,
                           const double* z, double* out, void* stream);
 
+/* Exact conditional draw of the mean process under the heteroskedastic Gaussian likelihood with the Vecchia
+ * approximation: imputer.one_sample imputation.py:141-158 -> U_matrix_sp (vecchia.py:426-445, 612-622) +
+ * Hetero.post_het_vecch (likelihood_class.py:165-183).  X: n x D node inputs and y, gamma = exp(log variance),
+ * sd (standard normals, the reference's np.random.randn(n)): n each, ALL in Vecchia order; imp_NN: n x m1 =
+ * kernel.imp_NNarray (kernel_class.py:268-273; entries >= n are latent, < n observed, -1 padding); kernel scale, no
+ * nugget (the reference passes 0).  f_out: n, the drawn mean process in Vecchia order (the caller applies rev_ord).
+ * U_out (optional, n x m1): the entries of U in imp_NN's order, i.e. U_matrix()'s rows reversed. */
+int dgpb_hetero_vecchia_draw(const double* X, const int64_t* imp_NN, int64_t n, int64_t D, int64_t m1,
+                             const double* length_host, int64_t nlen, double scale, int kind, const double* gamma,
+                             const double* y, const double* sd, double* f_out, double* U_out, void* stream);
+
 /* gp_vecch  vecchia.py:635-654.  x: M x D test inputs, w: n x D training inputs, NN: M x mp. */
 int dgpb_gp_vecch(const double* x, int64_t M, const double* w, const double* y, int64_t n, int64_t D,
                   const int64_t* NN, int64_t mp, const double* length_host, int64_t nlen, double scale,

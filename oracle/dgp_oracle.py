@@ -1007,3 +1007,55 @@ def sem_iteration(all_layer, rng, ess_burn=10):
         for node in layer:
             node.maximise()
     return n_prop
+
+
+# ------------------------------------------------------------------------------------------------
+# Hetero likelihood: exact draw of the mean process under the Vecchia approximation
+# ------------------------------------------------------------------------------------------------
+def imp_nn_array(Xo_scaled, m):
+    """Conditioning sets of the latent-Vecchia draw -- kernel_class.py:268-273.  Xo_scaled: inputs / length in
+    Vecchia order.  Row i = [i + n (latent f_i), i (observed y_i), the m - 1 nearest other points: index + n when
+    they come earlier in the ordering (latent), plain index when later (observed)]."""
+    n = Xo_scaled.shape[0]
+    NNs = knn(Xo_scaled, Xo_scaled, m)[:, 1:]
+    prev = NNs < np.arange(n)[:, None]
+    NNs = np.where(prev, NNs + n, NNs)
+    return np.hstack((np.arange(n).reshape(-1, 1) + n, np.arange(n).reshape(-1, 1), NNs))
+
+
+def hetero_u_matrix(Xo, imp_NN, scale, length, name, gamma_o):
+    """Entries of the sparse U in imp_NN's own order (n x m1) -- U_matrix, vecchia.py:426-445, whose rows are these
+    reversed: per row K = scale corr(x) + diag(gamma on the observed entries + 1e-10), u = chol(K)^-T e_last."""
+    n, m1 = imp_NN.shape
+    out = np.zeros((n, m1))
+    for i in range(n):
+        idx = imp_NN[i]
+        idx = idx[idx >= 0][::-1]
+        b = len(idx)
+        Ki = scale * k_matrix(Xo[idx % n], length, 0.0, name)
+        Ki[np.diag_indices(b)] += np.where(idx >= n, 0.0, gamma_o[idx % n]) + 1e-10
+        Li = np.linalg.cholesky(Ki)
+        e = np.zeros(b)
+        e[-1] = 1.0
+        out[i, :b] = solve_triangular(Li.T, e, lower=False)[::-1]
+    return out
+
+
+def hetero_vecchia_draw(Xo, imp_NN, scale, length, name, gamma_o, y_o, sd):
+    """Hetero.post_het_vecch (likelihood_class.py:165-183) on the U of `hetero_u_matrix`: L = U_latent^T,
+    mu = -L^-1 U_obs^T y, sample = L^-1 sd; returns mu + sample in Vecchia order."""
+    n, m1 = imp_NN.shape
+    U = hetero_u_matrix(Xo, imp_NN, scale, length, name, gamma_o)
+    f = np.zeros(n)
+    for i in range(n):   # forward substitution, row i of L = the latent entries of row i of imp_NN (diagonal first)
+        acc = sd[i]
+        for c in range(1, m1):
+            e = imp_NN[i, c]
+            if e < 0:
+                continue
+            if e >= n:
+                acc -= U[i, c] * f[e - n]
+            else:
+                acc -= U[i, c] * y_o[e]
+        f[i] = acc / U[i, 0]
+    return f

@@ -2,7 +2,7 @@
 
 Run in the build container only (the reference is not present on the GPU box):
 
-    python tests/golden/make_golden.py [dense jd vecchia ess e2e loo metric update lik floor sampling]
+    python tests/golden/make_golden.py [dense jd vecchia ess e2e loo metric update lik floor sampling hetvecch]
 
 Writes `tests/golden/*.npz` (one file per group: dense_nodes, jd, vecchia_nodes, ess_replay, e2e, loo, metric,
 update, likelihood; every group is seeded, re-running reproduces the committed files bit for bit).  Every fixture stores the exact inputs fed to the reference function
@@ -949,8 +949,69 @@ def gen_sampling():
     save("sampling", **out)
 
 
+# ---------------------------------------------------------------- Hetero exact draw under Vecchia
+def gen_hetvecch():
+    """Latent-Vecchia draw of the mean process under a heteroskedastic Gaussian likelihood: the conditioning sets
+    (kernel.ord_nn(pointer=True), kernel_class.py:268-275), the sparse U (U_matrix, vecchia.py:426-445) and the draw
+    (U_matrix_sp + Hetero.post_het_vecch, likelihood_class.py:165-183) with its normals recorded; then a whole public
+    API run of a Vecchia DGP with a Hetero layer from one seed (numpy's generator drives everything under Vecchia)."""
+    from dgpsi.likelihood_class import Hetero
+    out = {}
+    rng = np.random.default_rng(SEED + 41)
+    ci = 0
+    for name in ("sexp", "matern2.5"):
+        for ard in (False, True):
+            n, d, m = 90 + 20 * ci, 2, 8
+            k, X = make_node(rng, n, d, 0, name, ard, nugget=1e-6, scale=0.7 + 0.4 * ci)
+            k.vecch, k.m = True, m
+            np.random.seed(SEED + 100 + ci)
+            k.ord_nn(pointer=True)
+            p = f"c{ci}_"
+            gamma = np.exp(rng.uniform(-3, 0.5, size=n))          # data order
+            y = k.output[:, 0] + np.sqrt(gamma) * rng.standard_normal(n)
+            Xo = X[k.ord]
+            out[p + "X"], out[p + "ord"], out[p + "imp_NN"] = X, k.ord.copy(), k.imp_NNarray.copy()
+            out[p + "length"], out[p + "scale"], out[p + "name"] = k.length.copy(), k.scale.copy(), np.array(name)
+            out[p + "m"] = np.array(m)
+            out[p + "gamma"], out[p + "y"] = gamma, y
+            g2 = np.concatenate((gamma[k.ord], gamma[k.ord]))
+            NNarray = k.imp_NNarray
+            Cond = NNarray > n - 1
+            U = V.U_matrix(np.vstack((Xo, Xo)), NNarray[:, ::-1], Cond[:, ::-1], k.length, 0.0, k.scale[0], g2, name)
+            out[p + "U_rev"] = U                                  # rows in revNNarray order
+            U_l, U_ol = V.U_matrix_sp(Xo, NNarray, k.scale[0], k.length, 0.0, name, g2, k.imp_pointer_row,
+                                      k.imp_pointer_col)
+            np.random.seed(4300 + ci)
+            sd = np.random.randn(n)
+            np.random.seed(4300 + ci)
+            f_ord = Hetero.post_het_vecch(U_l, U_ol, y[k.ord])
+            out[p + "sd"], out[p + "f"] = sd, f_ord[k.rev_ord]
+            ci += 1
+    out["ncases"] = np.array(ci)
+    # public API run: Vecchia DGP + Hetero
+    seed = 33
+    rng = np.random.default_rng(seed)
+    np.random.seed(seed)
+    dgpsi.nb_seed(seed)
+    n, d = 200, 2
+    X = rng.uniform(0, 1, size=(n, d))
+    Y = (np.sin(4 * X[:, 0]) + X[:, 1] + np.exp(-1.5 + X[:, 0]) * rng.standard_normal(n)).reshape(-1, 1)
+    l1 = [kernel(length=np.array([0.5]), name="sexp") for _ in range(d)]
+    l2 = [kernel(length=np.array([0.5]), name="sexp", scale_est=True, connect=np.arange(d)) for _ in range(2)]
+    model = dgpsi.dgp(X, Y, dgpsi.combine(l1, l2, [dgpsi.Hetero()]), vecchia=True, m=10)
+    model.train(N=3, disable=True)
+    out["api_theta"] = np.concatenate([np.concatenate((k.scale, k.length, k.nugget)) for layer in model.all_layer[:-1]
+                                       for k in layer])
+    out["api_latent"] = np.concatenate([k.output for k in model.all_layer[1]], 1)
+    emu = dgpsi.emulator(model.estimate(), N=2)
+    xt = rng.uniform(0, 1, size=(30, d))
+    mu, var = emu.predict(xt, m=15)
+    out["api_mu"], out["api_var"] = mu, var
+    save("hetvecch", **out)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["dense", "jd", "vecchia", "ess", "e2e", "loo", "metric", "update", "lik", "floor", "sampling"]
+    which = sys.argv[1:] or ["dense", "jd", "vecchia", "ess", "e2e", "loo", "metric", "update", "lik", "floor", "sampling", "hetvecch"]
     for w in which:
         {"dense": gen_dense, "jd": gen_jd, "vecchia": gen_vecchia, "ess": gen_ess, "e2e": gen_e2e, "loo": gen_loo,
-         "metric": gen_metric, "update": gen_update, "lik": gen_lik, "floor": gen_floor, "sampling": gen_sampling}[w]()
+         "metric": gen_metric, "update": gen_update, "lik": gen_lik, "floor": gen_floor, "sampling": gen_sampling, "hetvecch": gen_hetvecch}[w]()

