@@ -165,6 +165,10 @@ struct Workspace {
     cudaStream_t wave_stream[2] = {nullptr, nullptr};
     cudaEvent_t wave_assembled[2] = {nullptr, nullptr}, wave_done[2] = {nullptr, nullptr};
     int wave_cur = 0;                   // the context a new block update starts with (the other may still be busy)
+    // proposals per block update of a layer pair (keyed by its first upper node): running mean / spread, used to
+    // factor waves ahead only while an acceptance is still unlikely
+    struct PropStat { double mean = 0.0, m2 = 0.0; int cnt = 0; };
+    std::map<int, PropStat> prop_stats;
     void* buf[SLOT_COUNT] = {};
     size_t cap[SLOT_COUNT] = {};
     double* pinned = nullptr;  // small pinned host staging buffer (kPinnedDoubles)

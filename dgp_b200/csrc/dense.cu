@@ -1217,7 +1217,8 @@ int dgpb_tune(const char* key, int value) {
     } else if (k == "ess_prefetch") {
         g_ess_prefetch = value != 0;
     } else if (k == "ess_overlap") {
-        g_ess_overlap = value != 0;
+        DGPB_REQUIRE(value >= 0 && value <= 2, "ess_overlap is 0, 1 or 2");
+        g_ess_overlap = value;
     } else if (k == "ess_wave_total") {
         DGPB_REQUIRE(value >= 1 && value <= 64, "ess_wave_total out of range");
         g_ess_wave_total = value;

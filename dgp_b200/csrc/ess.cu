@@ -632,6 +632,22 @@ extern "C" int dgpb_ess_block_cached(dgpb_ws* ws, const dgpb_node* targets, int 
     // factor the next wave ahead of the decision: single-candidate waves on one GPU (NCCL calls of two waves in
     // flight would have to be ordered across ranks, and multi-candidate waves accept too often for the bet to pay)
     const bool overlap = batched && g_ess_overlap && g_ess_prefetch && cap == 1 && W == 1;
+    // g_ess_overlap = 2: only while the wave factored ahead is very unlikely to be wasted -- ESS needs about as many
+    // proposals every time a given layer pair is updated (the bracket halves per rejection), so a wave that would
+    // END two standard deviations before the running mean of this pair's proposal count is almost never behind an
+    // acceptance
+    int overlap_until = 1 << 30;   // candidates [0, overlap_until) may be factored ahead
+    Workspace::PropStat* pstat = nullptr;
+    if (upper_keys_host && upper_keys_host[0] >= 0) {
+        pstat = &ws->prop_stats[upper_keys_host[0]];
+        if (g_ess_overlap == 2) {
+            overlap_until = 0;
+            if (pstat->cnt >= 4) {
+                const double sd = sqrt(pstat->m2 / (pstat->cnt - 1));
+                overlap_until = (int)floor(pstat->mean - 2.0 * sd - 1.0);
+            }
+        }
+    }
 
     DGPB_TRY(wave_contexts_init(ws));
     DGPB_TRY(join_wave_staging(ws, st));   // readers of SLOT_PROP / SLOT_NU left over from the previous block update
@@ -767,7 +783,7 @@ extern "C" int dgpb_ess_block_cached(dgpb_ws* ws, const dgpb_node* targets, int 
                     const double th_next = lmin + (lmax - lmin) * u_host[ui_next - 1];
                     const int Sn = plan_wave(th_next, lmin, lmax, ui_next, next_thetas);
                     DGPB_TRY(stage_wave(cur ^ 1, next_thetas, Sn, 0));
-                    if (overlap) DGPB_TRY(factor_wave(cur ^ 1));
+                    if (overlap && nprop + S + Sn <= overlap_until) DGPB_TRY(factor_wave(cur ^ 1));
                 }
             }
             DGPB_TRY(dense_items_fetch(ws, cur, uppers, n_uppers, n, first + S, W, sums, pd, bad, wave_logdets,
@@ -862,6 +878,12 @@ extern "C" int dgpb_ess_block_cached(dgpb_ws* ws, const dgpb_node* targets, int 
         if (batched) cur ^= 1;   // the wave staged (and maybe factored) ahead becomes the current one
     }
     if (n_prop_host) *n_prop_host = nprop;
+    if (pstat) {   // Welford update of this pair's proposal count
+        pstat->cnt += 1;
+        const double d = nprop - pstat->mean;
+        pstat->mean += d / pstat->cnt;
+        pstat->m2 += d * (nprop - pstat->mean);
+    }
     return DGPB_OK;
 }
 

@@ -502,8 +502,9 @@ class kernel:
                                         L.KIND[self.name], L.ptr(mean), L.ptr(var), L.stream()))
         return mean, var
 
-    def _linkgp_dev(self, m, v, z, w1, gw):
-        """Shared body of linkgp_prediction / linkgp_prediction_full on device tensors."""
+    def _linkgp_dev(self, m, v, z, w1, gw, loo=True):
+        """Shared body of linkgp_prediction / linkgp_prediction_full on device tensors.  `loo=False`: keep the
+        nearest neighbour even in LOO state (kernel_class.py:672-733: `linkgp_prediction_full` has no LOO slice)."""
         lib = L.load()
         torch = L.torch_mod()
         m, v = m.contiguous(), v.contiguous()
@@ -515,7 +516,11 @@ class kernel:
         if self.vecch:
             xq = L.cat_cols(m, z)
             w = L.cat_cols(w1, gw)
-            NN = self._nn_query(xq, w)
+            state, self.loo_state = self.loo_state, self.loo_state and loo
+            try:
+                NN = self._nn_query(xq, w)
+            finally:
+                self.loo_state = state
             y = L.to_dev_shared(self._y_pred())
             L.check(lib.dgpb_linkgp_vecch(L.ptr(m), L.ptr(v), L.ptr(z), M, L.ptr(w1), L.ptr(gw), L.ptr(y), w1.shape[0],
                                           Dw, Dz, L.ptr(NN), NN.shape[1], lptr, len(larr), float(self.scale[0]),
@@ -541,7 +546,7 @@ class kernel:
         v = torch.cat((v, v_z), 1)
         w1 = L.to_dev(np.concatenate((self.input, self.global_input[:, :k1]), axis=1))
         gw = L.to_dev(self.global_input[:, k1:]) if z is not None else None
-        return self._linkgp_dev(m, v, z, w1, gw)
+        return self._linkgp_dev(m, v, z, w1, gw, loo=False)
 
     def gp_prediction(self, x, z):
         """GP predictive mean/variance at deterministic inputs (kernel_class.py:587-625)."""
