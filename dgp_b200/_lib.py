@@ -80,6 +80,7 @@ _PROTOS = {
                                              ctypes.POINTER(DgpbNode), ctypes.c_int, c_i64, c_vp, c_vp, ctypes.c_int,
                                              ctypes.POINTER(ctypes.c_int), c_vp, c_vp, c_vp, c_vp, c_vp]),
     "dgpb_cache_clear": (ctypes.c_int, [c_vp]),
+    "dgpb_cache_output_changed": (ctypes.c_int, [c_vp, ctypes.c_int]),
     "dgpb_knn_ordered": (ctypes.c_int, [c_vp, c_i64, c_i64, c_i64, c_vp, c_vp]),
     "dgpb_knn": (ctypes.c_int, [c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp]),
     "dgpb_vecchia_llik": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_dbl, c_dbl, c_vp,

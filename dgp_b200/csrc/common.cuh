@@ -143,6 +143,7 @@ struct FactorOwner {
     int64_t n = 0;
     bool has_logdet = false;
     double logdet = 0.0;
+    bool w_synced = false;   // see CachedFactor
 };
 
 // chol(K) of a GP node kept across ESS block updates of one I-step (hyper-parameters fixed)
@@ -153,6 +154,7 @@ struct CachedFactor {
     bool valid = false;
     double logdet = 0.0;   // log|K| of the stored factor (valid when has_logdet)
     bool has_logdet = false;
+    bool w_synced = false; // row npad of T holds L^-1 y for the node's CURRENT output (kept in step by rotate_cached_w)
 };
 
 struct Workspace {

@@ -1224,6 +1224,8 @@ int dgpb_tune(const char* key, int value) {
         g_ess_wave_total = value;
     } else if (k == "ess_trsv") {
         g_ess_cached_threshold = value != 0;
+    } else if (k == "ess_rotate_w") {
+        g_ess_rotate_w = value != 0;
     } else if (k == "linkgp_matern_tab") {
         linkgp_set_matern_tab(value);
     } else if (k == "linkgp_mma") {

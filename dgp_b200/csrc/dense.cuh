@@ -82,6 +82,7 @@ void profile_wasted(int matrices, int64_t n);
 // matrices per speculative ESS wave (ess.cu)
 extern int g_ess_target_b;
 extern int g_ess_cached_threshold;
+extern int g_ess_rotate_w;
 extern int g_ess_prefetch;
 extern int g_ess_overlap;
 extern int g_ess_wave_total;

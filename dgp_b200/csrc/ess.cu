@@ -56,19 +56,22 @@ struct DenseBatchInfo {
 // ---- which rank holds chol(K) of a cache key ---------------------------------------------------------------------
 // One GPU: the workspace cache itself (kOwnerAll).  Several GPUs: the replicated owner map -- every rank takes the
 // same decisions from it, only the owning rank touches the factor.
-static int factor_owner(Workspace* ws, int key, int64_t n, bool* has_logdet = nullptr, double* logdet = nullptr) {
+static int factor_owner(Workspace* ws, int key, int64_t n, bool* has_logdet = nullptr, double* logdet = nullptr,
+                        bool* w_synced = nullptr) {
     if (key < 0) return kOwnerNone;
     if (ws->comm.world <= 1) {
         auto it = ws->cache.find(key);
         if (it == ws->cache.end() || !it->second.valid || it->second.n != n) return kOwnerNone;
         if (has_logdet) *has_logdet = it->second.has_logdet;
         if (logdet) *logdet = it->second.logdet;
+        if (w_synced) *w_synced = it->second.w_synced;
         return kOwnerAll;
     }
     auto it = ws->owner.find(key);
     if (it == ws->owner.end() || it->second.rank == kOwnerNone || it->second.n != n) return kOwnerNone;
     if (has_logdet) *has_logdet = it->second.has_logdet;
     if (logdet) *logdet = it->second.logdet;
+    if (w_synced) *w_synced = it->second.w_synced;
     return it->second.rank;
 }
 static inline bool is_mine(const Workspace* ws, int owner) { return owner == kOwnerAll || owner == ws->comm.rank; }
@@ -79,6 +82,7 @@ static void set_owner(Workspace* ws, int key, int rank, int64_t n, const double*
     o.n = n;
     o.has_logdet = logdet != nullptr;
     o.logdet = logdet ? *logdet : 0.0;
+    o.w_synced = logdet != nullptr;   // stored from a wave: the y row of T is L^-1 y for the node's output of that moment
     if (!is_mine(ws, rank)) {   // a factor this rank kept from an earlier update is stale now
         auto it = ws->cache.find(key);
         if (it != ws->cache.end()) it->second.valid = false;
@@ -107,7 +111,46 @@ static int cache_store(Workspace* ws, int key, const Geom& g, const Batch& bt, i
     cf.valid = true;
     cf.has_logdet = logdet != nullptr;
     cf.logdet = logdet ? *logdet : 0.0;
+    cf.w_synced = logdet != nullptr;
     return DGPB_OK;
+}
+
+// An accepted ESS move replaces the output y of target node k by y cos(theta) + nu sin(theta) with nu = sqrt(scale) L z,
+// L = chol(K_k) -- so L^-1 y, kept as row npad of the node's cached factor, becomes cos(theta) L^-1 y + sin(theta)
+// sqrt(scale) z: n multiply-adds keep it in step with the output, and the next threshold that needs y'K^-1y of this
+// node (it is an upper node of the layer pair below) is a dot product instead of a triangular solve (n^2).
+__global__ void rotate_w_kernel(double* __restrict__ w, const double* __restrict__ z, double c, double s_sq, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) w[i] = fma(c, w[i], s_sq * z[i]);
+}
+static int rotate_cached_w(Workspace* ws, const dgpb_node* targets, int M, const int32_t* keys, int64_t n, const double* z,
+                           double theta, cudaStream_t st) {
+    if (!keys) return DGPB_OK;
+    const Geom g = make_geom(n, false);
+    for (int k = 0; k < M; ++k) {
+        if (keys[k] < 0 || targets[k].vecch) continue;
+        bool synced = false;
+        const int own = factor_owner(ws, keys[k], n, nullptr, nullptr, &synced);
+        if (own == kOwnerNone || !synced || !is_mine(ws, own)) continue;
+        CachedFactor& cf = ws->cache[keys[k]];
+        if (!cf.valid || !cf.T || !cf.w_synced) continue;
+        rotate_w_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(cf.T + (size_t)g.npad * g.ld, z + (int64_t)k * n, cos(theta),
+                                                               sin(theta) * sqrt(targets[k].scale), n);
+        DGPB_LAUNCHED();
+    }
+    return DGPB_OK;
+}
+
+// out[b] = sum_i w_b[i]^2 over the y rows of cached factors (fixed-order tree sum); NULL row -> 0 (held elsewhere)
+__global__ void __launch_bounds__(256) wnorm_kernel(const double* const* __restrict__ Ts, int64_t row_off, int n,
+                                                    double* __restrict__ out) {
+    __shared__ double sred[8];
+    const double* T = Ts[blockIdx.x];
+    double s = 0.0;
+    if (T)
+        for (int i = threadIdx.x; i < n; i += 256) s = fma(T[row_off + i], T[row_off + i], s);
+    s = block_sum<256>(s, sred);
+    if (threadIdx.x == 0) out[blockIdx.x] = s;
 }
 
 static int nodes_loglik(Workspace* ws, const dgpb_node* nodes, int U, int64_t n, const double* src_override,
@@ -333,6 +376,7 @@ namespace dgpb {
 
 int g_ess_target_b = 8;  // matrices per speculative wave (dgpb_tune "ess_batch"); 0/1 = one proposal at a time
 int g_ess_cached_threshold = 1;  // threshold from cached factors by a triangular solve (dgpb_tune "ess_trsv")
+int g_ess_rotate_w = 1;          // ... or, when the cached L^-1 y was kept in step with the outputs, by a dot product
 int g_ess_prefetch = 1;          // assemble the next wave while the current one is factored (dgpb_tune "ess_prefetch")
 
 // |L^-1 y|^2 for a cached factor L (T layout, diagonal blocks restored): forward substitution by ONE CTA per matrix,
@@ -426,11 +470,13 @@ static int cached_threshold(Workspace* ws, const dgpb_node* nodes, int U, int64_
     double logdets[MAXB];
     int own[MAXB];
     int mine = 0;
+    bool all_synced = true;   // every node's cached L^-1 y follows its current output: dot products instead of solves
     for (int u = 0; u < U; ++u) {
         if (nodes[u].vecch || keys[u] < 0) return DGPB_OK;
-        bool has_logdet = false;
-        own[u] = factor_owner(ws, keys[u], n, &has_logdet, &logdets[u]);
+        bool has_logdet = false, synced = false;
+        own[u] = factor_owner(ws, keys[u], n, &has_logdet, &logdets[u], &synced);
         if (own[u] == kOwnerNone || !has_logdet) return DGPB_OK;
+        all_synced = all_synced && synced;
         hT[u] = nullptr;
         hy[u] = nodes[u].output;
         if (is_mine(ws, own[u])) {
@@ -454,7 +500,10 @@ static int cached_threshold(Workspace* ws, const dgpb_node* nodes, int U, int64_
             DGPB_CUDA_TRY(cudaFuncSetAttribute(trsv_quad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
             cfg = true;
         }
-        trsv_quad_kernel<<<U, 256, smem, st>>>(dT, g.ld, g.n, dy, out);   // nodes held elsewhere: NULL factor, skipped
+        if (all_synced && g_ess_rotate_w)
+            wnorm_kernel<<<U, 256, 0, st>>>(dT, (int64_t)g.npad * g.ld, g.n, out);
+        else
+            trsv_quad_kernel<<<U, 256, smem, st>>>(dT, g.ld, g.n, dy, out);   // nodes held elsewhere: NULL factor, skipped
         DGPB_LAUNCHED();
     }
     const double* res = ws->pinned + kPinnedWave;
@@ -838,6 +887,7 @@ extern "C" int dgpb_ess_block_cached(dgpb_ws* ws, const dgpb_node* targets, int 
                 DGPB_CUDA_TRY(cudaMemcpyAsync(layer_out + row * n, pa + row * n, sizeof(double) * n,
                                               cudaMemcpyDeviceToDevice, st));
             }
+            DGPB_TRY(rotate_cached_w(ws, targets, n_targets, target_keys_host, n, z, thetas[accepted], st));
             // the factors of the accepted proposal are the prior factors these nodes need as targets of the
             // next layer pair (they stay on the rank that computed them); the accepted log-likelihood is the
             // next threshold when their outputs are fixed
@@ -884,6 +934,17 @@ extern "C" int dgpb_ess_block_cached(dgpb_ws* ws, const dgpb_node* targets, int 
         pstat->mean += d / pstat->cnt;
         pstat->m2 += d * (nprop - pstat->mean);
     }
+    return DGPB_OK;
+}
+
+// The output of the node stored under `key` was changed by something other than an ESS move of this library (the
+// exact Hetero draw): its cached L^-1 y no longer matches, the next threshold solves with the factor again.
+extern "C" int dgpb_cache_output_changed(dgpb_ws* ws, int key) {
+    DGPB_REQUIRE(ws != nullptr, "ws is NULL");
+    auto it = ws->cache.find(key);
+    if (it != ws->cache.end()) it->second.w_synced = false;
+    auto io = ws->owner.find(key);
+    if (io != ws->owner.end()) io->second.w_synced = false;
     return DGPB_OK;
 }
 
@@ -1129,6 +1190,7 @@ extern "C" int dgpb_ess_block_lik(dgpb_ws* ws, const dgpb_node* targets, int n_t
                 DGPB_CUDA_TRY(cudaMemcpyAsync(layer_out + row * n, pa + row * n, sizeof(double) * n,
                                               cudaMemcpyDeviceToDevice, st));
             }
+            DGPB_TRY(rotate_cached_w(ws, targets, n_targets, target_keys_host, n, z, thetas[accepted], st));
             break;
         }
         if (ui >= nu) {

@@ -163,6 +163,7 @@ class _DeviceLayers:
                 sd = np.random.randn(self.n, 2)            # likelihood_class.py:200
             f = kern.posterior_dev(self.nodes[l][k], self.n, self.F[l][row_var], y, sd)
         self.F[l][k].copy_(f)
+        L.check(L.load().dgpb_cache_output_changed(L.workspace(), self._key(l, k)))
 
     def block_update(self, l, tks, uks, max_u=64):
         """One ESS update of the target nodes `tks` of layer l given the upper nodes `uks` of layer l+1,

@@ -182,6 +182,9 @@ int dgpb_ess_block_cached(dgpb_ws* ws, const dgpb_node* targets, int n_targets, 
                           int* n_prop_host, double* theta_host, const int32_t* target_keys_host,
                           const int32_t* upper_keys_host, double* threshold_io_host, void* stream);
 int dgpb_cache_clear(dgpb_ws* ws);
+/* The output of the node stored under `key` was replaced by the caller (e.g. the exact Hetero draw): the cached
+ * L^-1 y of that node is stale; thresholds that need y'K^-1y of it solve with the cached factor again. */
+int dgpb_cache_output_changed(dgpb_ws* ws, int key);
 
 /* imputer.sample(burnin) (imputation.py:22-42 with block updates, :44-119) of a SMALL dense DGP -- n <= 64 training
  * points, at most 8 nodes per layer and 8 GP layers -- in ONE kernel launch: one CTA keeps the layers, the prior draws
