@@ -18,6 +18,13 @@ class _FakeEmulator:
         return np.stack([x.sum(1), x[:, 0] * 2], 1), np.stack([np.abs(x[:, 0]), x.var(1)], 1)
 
 
+class _FakeLinkedSystem:
+    """`lgp.predict` returns one array per emulator of the last layer."""
+
+    def predict(self, x, **kw):
+        return [x.sum(1, keepdims=True), x[:, :2] * 3], [np.abs(x[:, :1]), x[:, :2] ** 2]
+
+
 def _worker(rank, world, port, M, out):
     import torch.distributed as dist
 
@@ -27,6 +34,10 @@ def _worker(rank, world, port, M, out):
     mu, var = predict_sharded(_FakeEmulator(), x, dist)
     np.save(os.path.join(out, f"mu{rank}.npy"), mu)
     np.save(os.path.join(out, f"var{rank}.npy"), var)
+    mus, vars_ = predict_sharded(_FakeLinkedSystem(), x, dist)
+    assert isinstance(mus, list) and len(mus) == 2 and len(vars_) == 2
+    np.save(os.path.join(out, f"lmu{rank}.npy"), np.concatenate(mus, 1))
+    np.save(os.path.join(out, f"lvar{rank}.npy"), np.concatenate(vars_, 1))
     dist.destroy_process_group()
 
 
@@ -48,9 +59,12 @@ def test_sharded_predict_matches_single_process(tmp_path, M):
     mp.spawn(_worker, args=(2, port, M, str(tmp_path)), nprocs=2, join=True)
     x = np.random.default_rng(0).uniform(size=(M, 3))
     mu, var = _FakeEmulator().predict(x)
+    lmu, lvar = _FakeLinkedSystem().predict(x)
     for r in range(2):
         assert np.array_equal(np.load(tmp_path / f"mu{r}.npy"), mu)
         assert np.array_equal(np.load(tmp_path / f"var{r}.npy"), var)
+        assert np.array_equal(np.load(tmp_path / f"lmu{r}.npy"), np.concatenate(lmu, 1))
+        assert np.array_equal(np.load(tmp_path / f"lvar{r}.npy"), np.concatenate(lvar, 1))
 
 
 # ---- one chain on several ranks: the host-side exchanges (M-step shares, parameter hand-over, wave plan) -----------
