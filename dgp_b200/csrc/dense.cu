@@ -199,7 +199,8 @@ namespace dgpb {
 
 // (b) panel rows: X <- X * inv(L_kk)'  on the FP64 tensor path, 128-row tiles, grid-stride over tiles.
 //     105 KB of shared memory and < 128 registers so a CTA co-resides with a trailing-update CTA.
-__global__ void __launch_bounds__(256, 2) trsm_kernel(Batch bt, int64_t ld, int npad, int k0, int row_lo, int row_hi) {
+__global__ void __launch_bounds__(256, 2) trsm_kernel(Batch bt, int64_t ld, int npad, int k0, int row_lo, int row_hi,
+                                                      int early) {
     extern __shared__ double smem[];
     double* sD = smem;             // 64 x LDS : inv(L_kk)
     double* sA = sD + 64 * LDS;    // 128 x LDS: panel rows being solved
@@ -207,6 +208,8 @@ __global__ void __launch_bounds__(256, 2) trsm_kernel(Batch bt, int64_t ld, int 
     double* __restrict__ T = bt.T[blockIdx.z];
     const double* __restrict__ dinv = bt.diag[blockIdx.z] + (size_t)npad * (1 + NB);
     const int ntiles = (row_hi - row_lo + TM - 1) / TM;
+    pdl_wait();
+    if (early) pdl_trigger();
     auto load_tile = [&](int tile) {
         const int r0 = row_lo + tile * TM;
         for (int c = tid; c < TM * 32; c += 256) {
@@ -227,6 +230,7 @@ __global__ void __launch_bounds__(256, 2) trsm_kernel(Batch bt, int64_t ld, int 
         const int r0 = row_lo + tile * TM;
         cp_async_wait<0>();
         __syncthreads();
+        if (tile + (int)gridDim.x >= ntiles) pdl_trigger();   // this CTA's last tile
         double acc[2][8][2];
 #pragma unroll
         for (int mi = 0; mi < 2; ++mi)
@@ -275,7 +279,7 @@ constexpr int ULD = 36;  // 32-wide K chunks, 36 % 16 == 4
 constexpr size_t kUpdateSmem = (size_t)(2 * (TM + UBN) * ULD) * sizeof(double);
 
 // `flags` (probe only, 0 in production): 1 = skip C loads, 2 = skip C stores, 4 = skip the DMMA loop body,
-// 8 = skip the panel loads.
+// 8 = skip the panel loads.  16 (production): trigger the dependent launch at once instead of near the end.
 __global__ void __launch_bounds__(256, 2) update_kernel(Batch bt, int64_t ld, int k0, int kc, int lo, int row_hi,
                                                         int col_hi, int ncol_tiles, int flags) {
     extern __shared__ double smem[];
@@ -288,6 +292,8 @@ __global__ void __launch_bounds__(256, 2) update_kernel(Batch bt, int64_t ld, in
     }
     const int ra = lo + ti * TM, rb = lo + tj * UBN;
     if (rb >= col_hi || ra >= row_hi || rb > ra + TM - 1) return;
+    pdl_wait();
+    if (flags & 16) pdl_trigger();
     const int tid = threadIdx.x;
     double* __restrict__ T = bt.T[blockIdx.z];
     // per-thread cp.async slots: 8 (A) + 4 (B) 16-byte chunks per 32-wide K chunk
@@ -370,6 +376,7 @@ __global__ void __launch_bounds__(256, 2) update_kernel(Batch bt, int64_t ld, in
         __syncthreads();
         const double* a_s = smem + (size_t)(c & 1) * (TM + UBN) * ULD;
         const double* b_s = a_s + TM * ULD;
+        if (c + 2 >= kc) pdl_trigger();
 #pragma unroll 2
         for (int kk = 0; kk < ((flags & 4) ? 0 : 32); kk += 4) {
             double a[4], b[4];
@@ -721,27 +728,49 @@ int join_waves(Workspace* ws, cudaStream_t st) {
     return DGPB_OK;
 }
 
+// Launch with the programmatic-stream-serialisation attribute (`pdl`): the grid may become resident before the
+// preceding kernel of the stream has finished; every kernel launched this way starts with pdl_wait().
+static int g_pdl = 1;
+static int g_pdl_early_b = 4;   // trigger early while the batch has at most this many matrices
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_chain(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (pdl && g_pdl) ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 static int launch_panel(const Geom& g, const Batch& bt, int B, int k0, int row_hi, cudaStream_t st) {
-    potf2_kernel<<<B, 256, kPotf2Smem, st>>>(bt, g.ld, g.npad, k0, nullptr);
+    DGPB_CUDA_TRY(launch_chain(true, potf2_kernel, dim3((unsigned)B), dim3(256), kPotf2Smem, st, bt, g.ld, g.npad, k0,
+                               (long long*)nullptr, (int)(B <= g_pdl_early_b)));
     DGPB_LAUNCHED();
     const int rows = row_hi - (k0 + NB);
     if (rows > 0) {
         const int tiles = (int)cdiv(rows, TM);
         dim3 grid((unsigned)std::min(tiles, std::max(1, 296 / B)), 1, (unsigned)B);
-        trsm_kernel<<<grid, 256, kTrsmSmem, st>>>(bt, g.ld, g.npad, k0, k0 + NB, row_hi);
+        DGPB_CUDA_TRY(launch_chain(true, trsm_kernel, grid, dim3(256), kTrsmSmem, st, bt, g.ld, g.npad, k0, k0 + NB,
+                                   row_hi, (int)(B <= g_pdl_early_b)));
         DGPB_LAUNCHED();
     }
     return DGPB_OK;
 }
 
 static int launch_update(const Batch& bt, int B, int64_t ld, int k0, int K, int lo, int row_hi, int col_hi,
-                         int ncol_tiles, cudaStream_t st) {
+                         int ncol_tiles, cudaStream_t st, bool pdl = false) {
     const int rows = row_hi - lo;
     if (rows <= 0 || col_hi <= lo) return DGPB_OK;
     const int ntr = (int)cdiv(rows, TM);
     const unsigned nblk = ncol_tiles > 0 ? (unsigned)(ntr * ncol_tiles) : (unsigned)(ntr * (ntr + 1));
-    update_kernel<<<dim3(nblk, 1, (unsigned)B), 256, kUpdateSmem, st>>>(bt, ld, k0, K / 32, lo, row_hi, col_hi,
-                                                                      ncol_tiles, 0);
+    DGPB_CUDA_TRY(launch_chain(pdl, update_kernel, dim3(nblk, 1, (unsigned)B), dim3(256), kUpdateSmem, st, bt, ld, k0,
+                               K / 32, lo, row_hi, col_hi, ncol_tiles, (pdl && B <= g_pdl_early_b) ? 16 : 0));
     DGPB_LAUNCHED();
     return DGPB_OK;
 }
@@ -802,14 +831,14 @@ int factorize(const Geom& g, const Batch& bt, int B, cudaStream_t caller, int ct
             int K = NB, lo2 = kA + NB;
             rh = rhA;
             if (has_b) {
-                DGPB_TRY(launch_update(bt, B, g.ld, kA, NB, kB, rhA, std::min(kB + NB, rhA), 1, st));
+                DGPB_TRY(launch_update(bt, B, g.ld, kA, NB, kB, rhA, std::min(kB + NB, rhA), 1, st, true));
                 const int rhB = g.aug ? g.npad + 1 + kB + NB : g.R;
                 DGPB_TRY(launch_panel(g, bt, B, kB, rhB, st));
                 K = 2 * NB;
                 lo2 = kB + NB;
                 rh = rhB;
             }
-            if (lo2 < h1) DGPB_TRY(launch_update(bt, B, g.ld, kA, K, lo2, rh, h1, (h1 - lo2) / UBN, st));
+            if (lo2 < h1) DGPB_TRY(launch_update(bt, B, g.ld, kA, K, lo2, rh, h1, (h1 - lo2) / UBN, st, true));
         }
         const int hw_next = width_at(h1);
         if (rh - h1 > 0) {
@@ -840,7 +869,8 @@ int factorize(const Geom& g, const Batch& bt, int B, cudaStream_t caller, int ct
             // ---- look-ahead: the next hyper-block's columns [h1, h1 + next width) on the critical path
             if (hw_next > 0) {
                 if (prev_bulk) DGPB_CUDA_TRY(cudaStreamWaitEvent(st, prev_bulk, 0));
-                DGPB_TRY(launch_update(bt, B, g.ld, h0, K, h1, rh, std::min(h1 + hw_next, rh), hw_next / UBN, st));
+                DGPB_TRY(launch_update(bt, B, g.ld, h0, K, h1, rh, std::min(h1 + hw_next, rh), hw_next / UBN, st,
+                                       true));
             }
             prev_bulk = this_bulk;
         }
@@ -1234,6 +1264,9 @@ int dgpb_tune(const char* key, int value) {
         vecchia_set_small(value);
     } else if (k == "knn_mma") {
         knn_set_mma(value);
+    } else if (k == "pdl") {
+        g_pdl = value != 0;
+        g_pdl_early_b = value > 1 ? value : (value ? 4 : 0);
     } else if (k == "crit_stream") {
         g_crit_stream = value != 0;
     } else if (k == "hb_graded") {

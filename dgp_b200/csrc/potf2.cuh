@@ -63,7 +63,8 @@ __device__ __forceinline__ void tri_inv_offdiag(const double* sL, double* sD, do
 //   Then inv(L_kk): the four 16 x 16 diagonal blocks by forward substitution with one warp per block (column
 //   per lane, solution kept in registers), and two block levels.  Results go to the side buffer.
 // `stamps` (probe only, NULL in production): clock64 at the phase boundaries, 8 per CTA.
-__global__ void __launch_bounds__(256, 2) potf2_kernel(Batch bt, int64_t ld, int npad, int k0, long long* stamps) {
+__global__ void __launch_bounds__(256, 2) potf2_kernel(Batch bt, int64_t ld, int npad, int k0, long long* stamps,
+                                                       int early = 0) {
 #define DGPB_STAMP(i) do { if (stamps && threadIdx.x == 0) stamps[blockIdx.x * 8 + (i)] = clock64(); } while (0)
 #if DGPB_POTF2_VARIANT == 9   // fine-grained stamps inside one loop iteration (thread 0 = block (15,15))
 #define DGPB_FSTAMP(i, dep) do { if (stamps && threadIdx.x == 0 && jj == 9) { long long t_; \
@@ -92,6 +93,8 @@ __global__ void __launch_bounds__(256, 2) potf2_kernel(Batch bt, int64_t ld, int
         tri_index(135 - (tid & ~31), bi2, bk2);
         warp_row_hi = 4 * bi2 + 3;
     }
+    pdl_wait();
+    if (early) pdl_trigger();
     double a[4][4];
 #pragma unroll
     for (int r = 0; r < 4; ++r)
@@ -212,6 +215,7 @@ __global__ void __launch_bounds__(256, 2) potf2_kernel(Batch bt, int64_t ld, int
     }
     __syncthreads();
     DGPB_STAMP(3);
+    pdl_trigger();   // the panel-row solve may become resident while the off-diagonal inverse blocks finish
     {
         const int half = tid >> 7;  // warps 0-3: block (16..31, 0..15); warps 4-7: block (48..63, 32..47)
         tri_inv_offdiag(sL, sD, sT + half * 16 * 33, half ? 48 : 16, half ? 32 : 0, 16, (tid >> 5) & 3, 4, tid & 31);
