@@ -768,6 +768,10 @@ def run_gpu(args):
                 "phase_ms_per_step": {"i_step": 1e3 * (tim["i_step"] - tim0["i_step"]) / steps,
                                       "m_step": 1e3 * (tim["m_step"] - tim0["m_step"]) / steps,
                                       "m_step_in_library": 1e3 * (tim.get("m_batched_s", 0.0) - tim0.get("m_batched_s", 0.0)) / steps,
+                                      "m_step_between_rounds": 1e3 * (tim.get("m_round_gap_s", 0.0) - tim0.get("m_round_gap_s", 0.0)) / steps,
+                                      "m_step_before_first_round": 1e3 * (tim.get("m_first_round_s", 0.0) - tim0.get("m_first_round_s", 0.0)) / steps,
+                                      "m_step_rounds": 1e3 * (tim.get("m_rounds_s", 0.0) - tim0.get("m_rounds_s", 0.0)) / steps,
+                                      "m_step_after_last_round": 1e3 * (tim.get("m_tail_s", 0.0) - tim0.get("m_tail_s", 0.0)) / steps,
                                       "m_step_batched_calls": (tim.get("m_batched_calls", 0) - tim0.get("m_batched_calls", 0)) / steps,
                                       "m_step_matrices": (tim.get("m_batched_matrices", 0) - tim0.get("m_batched_matrices", 0)) / steps},
                 "multi_gpu": None if world == 1 else {

@@ -72,7 +72,12 @@ class _GradBatcher:
         # numbers in, identical decisions out); the matrices of a round are dealt over the ranks and the results
         # exchanged, so the ranks stay balanced however unevenly the optimisers finish.
         self.shard = shard
-        self.stats = [0, 0, 0.0]   # batched calls, matrices, seconds inside the library (bench.py's M-step breakdown)
+        # batched calls, matrices, seconds inside the library, seconds between rounds (optimiser threads on the host),
+        # seconds before the first round: bench.py's M-step breakdown
+        self.stats = [0, 0, 0.0, 0.0, 0.0, 0.0, 0.0]   # ... + whole rounds, tail after the last round
+        self._t_last = time.perf_counter()
+        self._first = True
+        self._step = None          # matrices per batched call, fixed at the first round (cudaMemGetInfo is not free)
 
     MAX_BATCH = 32   # MAXB of the library's batched launches (dense.cuh)
 
@@ -92,6 +97,9 @@ class _GradBatcher:
         from . import _lib as L
         reqs, self.pending = self.pending, []
         reqs.sort(key=lambda r: r[4])     # the same order on every rank, whatever the thread timing
+        t_in = time.perf_counter()
+        self.stats[4 if self._first else 3] += t_in - self._t_last
+        self._first = False
         try:
             n = reqs[0][1]
             if any(r[1] != n for r in reqs):
@@ -101,7 +109,9 @@ class _GradBatcher:
             out = np.zeros((len(reqs), ldo + 1))          # last column: status
             rank, world = (self.shard[0], self.shard[1]) if self.shard else (0, 1)
             mine = [i for i in range(len(reqs)) if i % world == rank]
-            step = self._chunk(n)
+            if self._step is None:
+                self._step = self._chunk(n)
+            step = self._step
             msg = ""
             for lo in range(0, len(mine), step):
                 part = mine[lo:lo + step]
@@ -132,6 +142,8 @@ class _GradBatcher:
             for r in reqs:
                 if not r[3]:
                     r[3].extend([L.DGPB_CUDA_ERROR, None, str(exc)])
+        self._t_last = time.perf_counter()
+        self.stats[5] += self._t_last - t_in
         self.cond.notify_all()
 
     def evaluate(self, node, n, P, rid=0):
@@ -695,8 +707,10 @@ class dgp:
                 fut.result()
             except BaseException as exc:  # noqa: BLE001
                 errors.append(exc)
+        batcher.stats[6] = time.perf_counter() - batcher._t_last
         if hasattr(self, 'timing'):
-            for key, val in zip(('m_batched_calls', 'm_batched_matrices', 'm_batched_s'), batcher.stats):
+            for key, val in zip(('m_batched_calls', 'm_batched_matrices', 'm_batched_s', 'm_round_gap_s',
+                                 'm_first_round_s', 'm_rounds_s', 'm_tail_s'), batcher.stats):
                 self.timing[key] = self.timing.get(key, 0) + val
         if errors:
             raise errors[0]
