@@ -779,6 +779,10 @@ static int launch_update(const Batch& bt, int B, int64_t ld, int k0, int K, int 
 static int g_hb = 512;
 static int g_hb_min_w = 2560;
 static int g_hb_graded = 1;
+static int g_hb_small_b = 3;    // batches of at most this many matrices use 256-column hyper-blocks: there the
+                                // critical path bounds the factorisation, and a K = 512 look-ahead update on it costs
+                                // more than the bulk's extra C traffic (n = 5000: B = 1 4.25 -> 3.93 ms, B = 2 5.43 ->
+                                // 5.22 ms, augmented 6.82 -> 6.45 ms; B >= 4 is faster with 512)
 static int g_crit_stream = 1;   // critical path of the factorisation on its own highest-priority stream
 
 // Right-looking factorisation on two levels.
@@ -814,7 +818,7 @@ int factorize(const Geom& g, const Batch& bt, int B, cudaStream_t caller, int ct
     auto width_at = [&](int h0) {
         if (h0 >= g.npad) return 0;
         const int window = g.aug ? g.npad + 1 + 2 * NB : g.R - h0;  // rows still active at this column
-        int hb = (window >= g_hb_min_w) ? g_hb : 2 * NB;
+        int hb = (window >= g_hb_min_w) ? (B <= g_hb_small_b ? std::min(g_hb, 256) : g_hb) : 2 * NB;
         if (g_hb_graded) hb = std::min(hb, std::max(2 * NB, 2 * h0));  // 128, 256, 512: start the side stream early
         return std::min(hb, g.npad - h0);
     };
@@ -1238,6 +1242,8 @@ int dgpb_tune(const char* key, int value) {
     if (k == "hb") {
         DGPB_REQUIRE(value >= 128 && value % 128 == 0 && value <= 2048, "hb must be a multiple of 128 in [128, 2048]");
         g_hb = value;
+    } else if (k == "hb_small_b") {
+        g_hb_small_b = value;
     } else if (k == "hb_min_w") {
         DGPB_REQUIRE(value >= 0, "hb_min_w must be >= 0");
         g_hb_min_w = value;
