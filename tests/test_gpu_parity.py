@@ -164,7 +164,10 @@ def test_potrf_and_gemm_building_blocks():
 
 def test_hyper_block_factorisation_variants():
     """The two-level blocked factorisation (hyper-blocks of 128 / 256 / 512 columns, forced on at small n through
-    dgpb_tune) gives the same factor, log-likelihood, gradient and inverse as LAPACK for every setting."""
+    dgpb_tune) gives the same factor, log-likelihood, gradient and inverse as LAPACK for every setting -- and the
+    SAME BITS for every setting: each entry is updated in ascending column order in groups of four whatever the
+    blocking, so a batch of three matrices (256-column hyper-blocks) and a batch of eight (512) agree exactly,
+    which is what keeps a chain shared by several GPUs identical to the chain on one."""
     import ctypes
     import dgp_b200 as D
     from dgp_b200 import _lib as L
@@ -182,7 +185,9 @@ def test_hyper_block_factorisation_variants():
     ll0 = O.loglik_dense(X, y, length, 0.7, 1e-3, "sexp")
     f0, g0, s0 = O.nllik_grad_dense(X, y, length, 0.7, 1e-3, "sexp", True, True)
     K = O.k_matrix(X, length, 1e-3, "sexp")
+    bits = []
     try:
+        L.check(lib.dgpb_tune(b"hb_small_b", 0))   # a single matrix would otherwise be capped at 256 columns
         for hb, min_w in ((128, 0), (256, 0), (512, 0), (512, 700), (1024, 0)):
             L.check(lib.dgpb_tune(b"hb", hb))
             L.check(lib.dgpb_tune(b"hb_min_w", min_w))
@@ -201,11 +206,16 @@ def test_hyper_block_factorisation_variants():
             assert np.max(np.abs(gr - g0)) <= 1e-8 * max(1.0, np.max(np.abs(g0))), (hb, min_w, gr, g0)
             k.compute_stats()
             assert np.max(np.abs(K @ k.Rinv - np.eye(n))) <= 1e-8, (hb, min_w)
+            bits.append((Lc, ll, f[0], gr.copy()))
+        for Lc, ll, f, gr in bits[1:]:
+            assert np.array_equal(Lc, bits[0][0]) and ll == bits[0][1] and f == bits[0][2]
+            assert np.array_equal(gr, bits[0][3])
         with pytest.raises(ValueError):
             L.check(lib.dgpb_tune(b"no_such_knob", 1))
     finally:
         L.check(lib.dgpb_tune(b"hb", 512))
         L.check(lib.dgpb_tune(b"hb_min_w", 2560))
+        L.check(lib.dgpb_tune(b"hb_small_b", 3))
 
 
 # ------------------------------------------------------------------------------------------------ 5
