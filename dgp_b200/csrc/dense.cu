@@ -45,8 +45,12 @@ __device__ __forceinline__ void cp_async_wait() {
 // 2 loads per entry per dimension) and consecutive threads still store consecutive columns (128-byte lines).
 // HBM-write bound: 8 n^2 / 2 bytes (lower) or 8 n^2 (MIRROR).  Arithmetic per entry is unchanged: squared
 // differences accumulated with separate multiply and add in ascending d (what scipy's pdist does).
-template <bool MIRROR>
-__global__ void __launch_bounds__(256) kbuild_kernel(KernelDev kd, double* __restrict__ T, int64_t ld, int n, int npad,
+// KIND is a template parameter so the squared-exponential instance does not carry the Matern accumulators: 64
+// registers instead of 96, four resident CTAs per SM instead of two -- the kernel is bound by FP64 issue (three
+// non-fused operations per dimension and entry, kept for bit-parity with pdist) plus the prologue / store phases
+// that only other resident CTAs can cover.
+template <bool MIRROR, int KIND>
+__global__ void __launch_bounds__(256, KIND == DGPB_SEXP ? 4 : 2) kbuild_kernel(KernelDev kd, double* __restrict__ T, int64_t ld, int n, int npad,
                                                      const double* __restrict__ wdiag) {
     __shared__ __align__(16) double xi[kMaxDim][64];
     __shared__ double xj[kMaxDim][64];
@@ -69,7 +73,7 @@ __global__ void __launch_bounds__(256) kbuild_kernel(KernelDev kd, double* __res
     for (int r = 0; r < 4; ++r)
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-            acc[r][c] = kd.kind == DGPB_SEXP ? 0.0 : 1.0;
+            acc[r][c] = KIND == DGPB_SEXP ? 0.0 : 1.0;
             sr[r][c] = 0.0;
         }
     for (int d = 0; d < D; ++d) {
@@ -79,7 +83,7 @@ __global__ void __launch_bounds__(256) kbuild_kernel(KernelDev kd, double* __res
         double bv[4];
 #pragma unroll
         for (int c = 0; c < 4; ++c) bv[c] = xj[d][tx + 16 * c];
-        if (kd.kind == DGPB_SEXP) {
+        if (KIND == DGPB_SEXP) {
 #pragma unroll
             for (int r = 0; r < 4; ++r)
 #pragma unroll
@@ -111,7 +115,7 @@ __global__ void __launch_bounds__(256) kbuild_kernel(KernelDev kd, double* __res
             } else if (gi >= n) {
                 v = 0.0;
             } else {
-                v = kd.kind == DGPB_SEXP ? exp_nonpos(-acc[r][c]) : acc[r][c] * exp_nonpos(-kSqrt5 * sr[r][c]);
+                v = KIND == DGPB_SEXP ? exp_nonpos(-acc[r][c]) : acc[r][c] * exp_nonpos(-kSqrt5 * sr[r][c]);
             }
             if (MIRROR) {
                 if (gi < n) {
@@ -634,7 +638,10 @@ int assemble_matrices(const Geom& g, const KernelDev* kds, const double* const* 
             DGPB_CUDA_TRY(cudaMemsetAsync(bt.T[b] + (size_t)(g.npad + 1) * g.ld, 0,
                                           (size_t)(g.R - g.npad - 1) * g.ld * sizeof(double), st));
         }
-        kbuild_kernel<false><<<nt * (nt + 1) / 2, 256, 0, st>>>(kds[b], bt.T[b], g.ld, g.n, g.npad, nullptr);
+        if (kds[b].kind == DGPB_SEXP)
+            kbuild_kernel<false, DGPB_SEXP><<<nt * (nt + 1) / 2, 256, 0, st>>>(kds[b], bt.T[b], g.ld, g.n, g.npad, nullptr);
+        else
+            kbuild_kernel<false, DGPB_MATERN25><<<nt * (nt + 1) / 2, 256, 0, st>>>(kds[b], bt.T[b], g.ld, g.n, g.npad, nullptr);
         DGPB_LAUNCHED();
         rows_init_kernel<<<(unsigned)cdiv(g.ld, 256), 256, 0, st>>>(bt.T[b], g.ld, g.n, g.npad, ys ? ys[b] : nullptr,
                                                                    g.aug ? 1 : 0);
@@ -1006,7 +1013,10 @@ int dgpb_kmatrix(const double* X, int64_t n, int64_t D, const double* length_hos
     KernelDev kd;
     DGPB_TRY(make_kernel_dev_rowmajor(X, D, length_host, nlen, nugget, kind, &kd));
     const int nt = (int)cdiv(n, 64);
-    kbuild_kernel<true><<<nt * (nt + 1) / 2, 256, 0, st>>>(kd, K, n, (int)n, nt * 64, wdiag);
+    if (kd.kind == DGPB_SEXP)
+        kbuild_kernel<true, DGPB_SEXP><<<nt * (nt + 1) / 2, 256, 0, st>>>(kd, K, n, (int)n, nt * 64, wdiag);
+    else
+        kbuild_kernel<true, DGPB_MATERN25><<<nt * (nt + 1) / 2, 256, 0, st>>>(kd, K, n, (int)n, nt * 64, wdiag);
     DGPB_LAUNCHED();
     if (dK) {
         const int P = (int)nlen + (nugget_est ? 1 : 0);
