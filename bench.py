@@ -277,7 +277,7 @@ def workload_config(args, world):
                         f"2 outputs; one step = one SEM iteration (11 ESS sweeps + M-step)",
             "n": args.n, "ess_burn": 10, "nodes": 18, "chains": 1, "gpus_sharing_the_chain": world,
             "cache": "working set per batched factorisation >> 126 MB L2 (8 x n^2 doubles); no L2 flush needed",
-            "legs": args.legs}
+            "legs": args.legs, "leg_seconds": args.leg_seconds}
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
@@ -297,6 +297,19 @@ def measure_fp64_peak(torch):
     del a, b
     torch.cuda.empty_cache()
     return best
+
+
+def fit_points(stated, probe, t_probe, budget_s, granule):
+    """Test points of a predict leg that fit `budget_s` seconds, from a timed probe of `probe` points: the stated
+    number when it fits (or when there is no budget), else the largest multiple of `granule` that does (at least the
+    probe).  Throughput of these legs is a steady-state rate (identical chunks), so fewer points change the duration,
+    not the points/s."""
+    if budget_s <= 0 or t_probe <= 0 or stated <= probe:
+        return int(stated)
+    if stated * t_probe / probe <= budget_s:
+        return int(stated)
+    fit = int(budget_s * probe / t_probe) // granule * granule
+    return int(min(stated, max(probe, fit)))
 
 
 class Ctx:
@@ -367,6 +380,14 @@ class Ctx:
         from dgp_b200.parallel import predict_sharded
         return predict_sharded(emu, x, self.dist, **kw)
 
+    def bounded_points(self, emu, xt, stated, **kw):
+        """`stated` test points, or as many as fit --leg-seconds (default run: the whole bench line within minutes on
+        one GPU; `--leg-seconds 0` runs every leg at the size BASELINE.json states).  Decided from a timed probe whose
+        duration is the maximum over the ranks, so every rank takes the same decision."""
+        probe = min(stated, 1024 * self.world)
+        _, t_probe, _ = self.timed(lambda: self.predict(emu, xt[:probe], **kw))
+        return fit_points(stated, probe, t_probe, self.args.leg_seconds, 256 * self.world)
+
     def cpu_reference(self):
         """The unmodified reference for the bounded CPU samples of the legs: rank 0 of a single-GPU run only."""
         if self.args.no_cpu_baseline or self.world != 1:
@@ -422,9 +443,12 @@ def leg_predict3(ctx, model):
     emu, t_emu, _ = ctx.timed(lambda: D.emulator(model.estimate(), N=S))
     xt = np.random.default_rng(SEED + 99).uniform(0, 1, size=(M, 8))
     ctx.predict(emu, xt[: min(M, 256 * ctx.world)])                     # sizes the scratch buffers
+    M_stated, M = M, ctx.bounded_points(emu, xt, M)
+    xt = xt[:M]
     (mu, var), t, t_wall = ctx.timed(lambda: ctx.predict(emu, xt))
     entries = float(M) * S * 10 * (n * (n + 1) / 2)                     # J entries of the 10 linked nodes
     leg = {"workload": f"config 3 predict: emulator(N={S}).predict, {M} points, n={n}, 8 gp + 10 link_gp nodes",
+           "points": M, "points_stated": M_stated,
            "points_per_s": M / t, "e2e_points_per_s": M / t_wall, "seconds": t, "emulator_build_s": t_emu,
            "node_imputation_points_per_s": M * S * 18 / t,
            "J_entries_per_s": entries / t,
@@ -533,10 +557,13 @@ def leg_cfg2(ctx):
     emu, t_emu, _ = ctx.timed(lambda: D.emulator(model.estimate(), N=S))
     xt = rng.uniform(0, 1, (M, d))
     ctx.predict(emu, xt[: min(M, 256 * ctx.world)])
+    M_stated, M = M, ctx.bounded_points(emu, xt, M)
+    xt = xt[:M]
     (mu, var), t, t_wall = ctx.timed(lambda: ctx.predict(emu, xt))
     evals = float(M) * S * (n * (n + 1) / 2) * 5          # Jd evaluations: pairs x Dw
     leg = {"workload": f"config 2: 2-layer Matern-2.5 DGP (5 + 1 nodes, global connection), n={n}, d=5; train({iters}) then "
                        f"emulator(N={S}).predict, {M} points",
+           "points": M, "points_stated": M_stated,
            "points_per_s": M / t, "e2e_points_per_s": M / t_wall, "seconds": t,
            "train_iters_per_s": iters / t_train, "emulator_build_s": t_emu,
            "node_imputation_points_per_s": M * S * 6 / t,
@@ -593,12 +620,15 @@ def leg_cfg5(ctx):
                                                            [D.container(g3.export(), np.array([0]))]), N=S))
     xt = rng.uniform(0, 1, (M, 2))
     ctx.predict(system, xt[: min(M, 256 * ctx.world)])
+    M_stated, M = M, ctx.bounded_points(system, xt, M)
+    xt = xt[:M]
     (mu, var), t, t_wall = ctx.timed(lambda: ctx.predict(system, xt))
     truth = np.tanh(2 * ((np.sin(3 * xt[:, 0]) + xt[:, 1] ** 2) - 0.9))
     truth = truth ** 2 - 0.3 * truth
     pairs = n * (n + 1) / 2
     leg = {"workload": f"config 5: linked GP(2-D, Matern) -> 2-layer DGP (Matern) -> GP (sexp), n={n} each; "
                        f"lgp(N={S}).predict, {M} points",
+           "points": M, "points_stated": M_stated,
            "points_per_s": M / t, "e2e_points_per_s": M / t_wall, "seconds": t, "lgp_build_s": t_build,
            "emulator_imputation_points_per_s": M * S * 3 / t,
            "J_entries_per_s": float(M) * S * 3 * pairs / t,
@@ -809,6 +839,10 @@ def main():
     ap.add_argument("--cfg5-points", type=int, default=1000000)
     ap.add_argument("--cfg5-imputations", type=int, default=50)
     ap.add_argument("--cfg1-iters", type=int, default=500)
+    ap.add_argument("--leg-seconds", type=float, default=60.0,
+                    help="time budget of the timed predict call of the predict3 / cfg2 / cfg5 legs: when the stated "
+                         "number of test points would take longer, as many as fit are used (same model, same "
+                         "imputations; reported as `points` next to `points_stated`); 0 = always the stated sizes")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -120,3 +120,21 @@ def test_likelihood_host_formulas_match_oracle_and_summary():
     X, Y = rng.uniform(size=(8, 1)), rng.poisson(3.0, size=(8, 1)).astype(float)
     with pytest.raises(NotImplementedError):   # likelihood nodes only as a final layer
         D.dgp(X, Y, D.combine([D.kernel(length=np.array([1.0]))], [D.Poisson()], [D.kernel(length=np.array([1.0]))]))
+
+
+def test_bench_leg_budget_keeps_stated_sizes_when_they_fit():
+    """bench.py's predict legs run the number of test points BASELINE.json states unless a timed probe says the call
+    would exceed --leg-seconds; then the largest multiple of the shard granule that fits (never fewer than the probe)."""
+    import sys
+    sys.path.insert(0, ROOT)
+    from bench import fit_points
+
+    assert fit_points(10000, 1024, 6.0, 60.0, 256) == 10000               # 58.6 s: fits
+    assert fit_points(1000000, 1024, 0.32, 60.0, 256) == 192000           # 312 s stated -> 60 s worth, multiple of 256
+    assert fit_points(1000000, 1024, 0.32, 0.0, 256) == 1000000           # no budget: stated size
+    assert fit_points(500, 1024, 1.0, 60.0, 256) == 500                   # fewer points than the probe
+    assert fit_points(100000, 8192, 100.0, 60.0, 2048) == 8192            # never fewer than the probe
+    assert fit_points(100000, 8192, 0.0, 60.0, 2048) == 100000            # degenerate timer
+    for stated, probe, t, budget, g in ((123457, 1024, 1.7, 60.0, 256), (10 ** 6, 4096, 0.9, 30.0, 1024)):
+        m = fit_points(stated, probe, t, budget, g)
+        assert probe <= m <= stated and (m == stated or m % g == 0) and m * t / probe <= budget * 1.0001
