@@ -138,3 +138,75 @@ def test_bench_leg_budget_keeps_stated_sizes_when_they_fit():
     for stated, probe, t, budget, g in ((123457, 1024, 1.7, 60.0, 256), (10 ** 6, 4096, 0.9, 30.0, 1024)):
         m = fit_points(stated, probe, t, budget, g)
         assert probe <= m <= stated and (m == stated or m % g == 0) and m * t / probe <= budget * 1.0001
+
+
+def test_m_step_rendezvous_chunks_and_sizes_once(monkeypatch):
+    """The M-step's rendezvous (`_GradBatcher`) on the host, with the library replaced by a stand-in: 40 optimiser
+    threads (more than the 32 matrices one batched launch takes) get their own results back round after round, no call
+    exceeds the limit, the batch size is derived from free device memory ONCE per M-step (cudaMemGetInfo costs
+    milliseconds), and a thread that retires no longer holds the others up."""
+    import threading
+
+    from dgp_b200 import _lib as L
+    import importlib
+    dgp_mod = importlib.import_module("dgp_b200.dgp")
+
+    calls, mem_queries = [], []
+
+    class FakeLib:
+        def dgpb_ws_bytes(self, ws):
+            return 0
+
+        def dgpb_last_error(self):
+            return b""
+
+        def dgpb_nllik_grad_dense_batch(self, ws, arr, B, n, res_ptr, ldo, status_ptr, stream):
+            calls.append(B)
+            res = np.ctypeslib.as_array(ctypes.cast(res_ptr, ctypes.POINTER(ctypes.c_double)), shape=(B, ldo))
+            for b in range(B):
+                res[b, :] = arr[b].scale * 10 + np.arange(ldo)       # recognisable per node
+            return L.DGPB_OK
+
+    class FakeCuda:
+        @staticmethod
+        def set_device(dev):
+            pass
+
+        @staticmethod
+        def mem_get_info(dev):
+            mem_queries.append(dev)
+            return (64 << 30, 180 << 30)
+
+    class FakeTorch:
+        cuda = FakeCuda
+
+    monkeypatch.setattr(L, "load", lambda: FakeLib())
+    monkeypatch.setattr(L, "torch_mod", lambda: FakeTorch)
+    monkeypatch.setattr(L, "stream", lambda: None)
+
+    nthreads, rounds, P = 40, 3, 4
+    batcher = dgp_mod._GradBatcher(nthreads, None, 0)
+    got = [[] for _ in range(nthreads)]
+
+    def worker(i):
+        node = L.DgpbNode()
+        node.scale = float(i)
+        for r in range(rounds if i % 2 else rounds - 1):      # even threads finish one round early
+            out = batcher.evaluate(node, 100, P, rid=i)
+            got[i].append(out.copy())
+        batcher.retire()
+
+    threads = [threading.Thread(target=worker, args=(i,)) for i in range(nthreads)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=60)
+    assert not any(t.is_alive() for t in threads)
+    for i in range(nthreads):
+        assert len(got[i]) == (rounds if i % 2 else rounds - 1)
+        for out in got[i]:
+            assert np.array_equal(out, i * 10 + np.arange(P + 2))
+    assert max(calls) <= dgp_mod._GradBatcher.MAX_BATCH and sum(calls) == 20 * rounds + 20 * (rounds - 1)
+    assert calls[:2] == [32, 8]                                # 40 requests of the first round: 32 + 8
+    assert len(mem_queries) == 1
+    assert batcher.stats[0] == len(calls) and batcher.stats[1] == sum(calls)
