@@ -1280,7 +1280,7 @@ int dgpb_tune(const char* key, int value) {
         vecchia_set_small(value);
     } else if (k == "knn_mma") {
         knn_set_mma(value);
-    } else if (k == "pdl") {
+    } else if (k == "pdl") {   // 0: plain launches; 1: dependent launches, early trigger for B <= 4; v > 1: for B <= v
         g_pdl = value != 0;
         g_pdl_early_b = value > 1 ? value : (value ? 4 : 0);
     } else if (k == "crit_stream") {
