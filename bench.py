@@ -839,7 +839,7 @@ def main():
     ap.add_argument("--cfg5-points", type=int, default=1000000)
     ap.add_argument("--cfg5-imputations", type=int, default=50)
     ap.add_argument("--cfg1-iters", type=int, default=500)
-    ap.add_argument("--leg-seconds", type=float, default=60.0,
+    ap.add_argument("--leg-seconds", type=float, default=75.0,
                     help="time budget of the timed predict call of the predict3 / cfg2 / cfg5 legs: when the stated "
                          "number of test points would take longer, as many as fit are used (same model, same "
                          "imputations; reported as `points` next to `points_stated`); 0 = always the stated sizes")
